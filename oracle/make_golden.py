@@ -1,0 +1,177 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (imported through oracle/shims.py).
+TEST INFRASTRUCTURE ONLY.  Run in the authoring container:  python -m oracle.make_golden
+
+The reference ships no golden vectors, so these are outputs of the reference's
+own Python modules run here on CPU fp32 -- models/dvae.py (Group, Encoder), models/act.py
+(TransformerEncoder, ACT_PointDistillation), utils/transformer_layers.py (Block, BASELINE config 1)
+-- on seeded inputs with the deterministic weights of oracle.ref_model.fill_params.  The native ops
+under Group are the C oracle (the upstream CUDA packages cannot run here).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+from . import shims, cpu_ref                      # noqa: E402
+from .ref_model import fill_params, synthetic_clouds  # noqa: E402
+
+
+def adversarial_clouds():
+    """SURVEY.md 8(d) parity set: duplicates, lattice (many equal distances), >=8 points with
+    |p|^2 <= 1e-3, N not a multiple of 512, all-identical cloud.  dict name -> [B,N,3] f32."""
+    rng = np.random.default_rng(7)
+    out = {}
+    base = synthetic_clouds(2, 1024, seed=11).numpy()
+    dup = base.copy()
+    dup[:, 512:768] = dup[:, 0:256]                       # exact duplicates
+    out["dup"] = dup
+    g = np.stack(np.meshgrid(np.arange(8), np.arange(8), np.arange(16), indexing="ij"), -1).reshape(-1, 3)
+    lat = (g.astype(np.float32) - np.array([3.5, 3.5, 7.5], np.float32)) * 0.125
+    out["lattice"] = np.stack([lat, lat[rng.permutation(1024)]])
+    org = base.copy()
+    org[:, 5:17] = (rng.standard_normal((2, 12, 3)) * 0.01).astype(np.float32)   # |p|^2 <= 1e-3
+    out["near_origin"] = org
+    out["n1000"] = synthetic_clouds(2, 1000, seed=12).numpy()
+    out["n600"] = synthetic_clouds(3, 600, seed=13).numpy()
+    out["identical"] = np.full((1, 1024, 3), 0.25, np.float32)
+    return out
+
+
+def gen_group():
+    from models.dvae import Group, knn_point
+    res = {}
+    clouds = {"shapenet": synthetic_clouds(4, 1024).numpy()}
+    clouds.update(adversarial_clouds())
+    for name, xyz in clouds.items():
+        grp = Group(64, 32)
+        x = torch.from_numpy(xyz)
+        nb, center = grp(x)                                  # reference Group.forward over the C oracle
+        fps_idx = cpu_ref.fps(xyz, 64)
+        _, idx = cpu_ref.knn(xyz, center.numpy(), 32)
+        res[name + "/xyz"] = xyz
+        res[name + "/fps_idx"] = fps_idx
+        res[name + "/knn_idx"] = idx.astype(np.int32)
+        res[name + "/center"] = center.numpy()
+        res[name + "/neighborhood"] = nb.numpy()
+        if name == "shapenet":                               # tie-free: same neighbour SET as the in-repo knn_point
+            s = knn_point(32, x, center).sort(-1)[0].numpy()
+            assert (np.sort(idx, -1) == s).mean() > 0.999, "oracle kNN disagrees with reference knn_point"
+    np.savez_compressed(os.path.join(GOLD, "group.npz"), **res)
+    print("group.npz", {k: v.shape for k, v in res.items() if k.startswith("shapenet")})
+
+
+def gen_block_cfg1():
+    """BASELINE config 1: utils/transformer_layers.Block x12, d=384, 64 tokens, batch 2, CPU, eval."""
+    from utils.transformer_layers import Block
+    blocks = torch.nn.ModuleList([Block(384, 6) for _ in range(12)]).eval()
+    fill_params(blocks, seed=1)
+    x = torch.from_numpy(np.random.default_rng(0).standard_normal((2, 64, 384)).astype(np.float32))
+    with torch.no_grad():
+        y = x
+        for b in blocks:
+            y = b(y)
+    np.savez_compressed(os.path.join(GOLD, "block12_cfg1.npz"), x=x.numpy(), y=y.numpy())
+    print("block12_cfg1.npz", y.abs().mean().item())
+
+
+def gen_encoder():
+    from models.dvae import Encoder
+    g = np.load(os.path.join(GOLD, "group.npz"))
+    nb = torch.from_numpy(g["shapenet/neighborhood"][:2])
+    enc = fill_params(Encoder(384), seed=2).train()
+    nb.requires_grad_(True)
+    out = enc(nb)
+    w = torch.from_numpy(np.random.default_rng(3).standard_normal(out.shape).astype(np.float32))
+    (out * w).sum().backward()
+    res = {"out": out.detach().numpy(), "wout": w.numpy(), "grad_in": nb.grad.numpy()}
+    for k, p in enc.named_parameters():
+        res["grad/" + k] = p.grad.numpy()
+    for k, b in enc.named_buffers():
+        res["buf/" + k] = b.numpy()
+    enc.eval()
+    with torch.no_grad():
+        res["out_eval"] = enc(nb.detach()).numpy()
+    np.savez_compressed(os.path.join(GOLD, "encoder.npz"), **res)
+    print("encoder.npz", out.abs().mean().item())
+
+
+def gen_student_step():
+    """ACT_PointDistillation.forward/backward of the real reference (act.py:1203-1258), B=4, mask 0.6,
+    drop_path 0, with the frozen teacher replaced by a stub returning seeded features."""
+    import models.act as act
+    B, G = 4, 64
+    cfg = shims.easydict(dict(
+        NAME="ACT_PointDistillation", loss="cosine",
+        transformer_config=dict(mask_ratio=0.6, mask_type="rand", proj="linear", embed_dim=384, encoder_dims=384,
+                                depth=12, drop_path_rate=0.0, cls_dim=512, replace_pob=0.0, num_heads=6,
+                                decoder_depth=2, decoder_num_heads=6, return_all_tokens=False, cls_loss=False,
+                                register_shallow_hook=9),
+        dvae_config=dict(num_group=G, group_size=32, encoder_dims=384, num_tokens=8192, tokens_dims=384,
+                         decoder_dims=384, ckpt="")))
+    teacher = torch.from_numpy(np.random.default_rng(5).standard_normal((B, G, 384)).astype(np.float32))
+
+    class StubTokenizer(torch.nn.Module):
+        def forward_tokenizer_features(self, neighborhood, center, return_global=True):
+            return teacher
+
+    def build_tokenizer(self, cfg_):
+        self.dvae_tokenizer = StubTokenizer()
+
+    act.ACT_PointDistillation.build_tokenizer = build_tokenizer
+    model = act.ACT_PointDistillation(cfg)
+    fill_params(model, seed=4)
+    model.train()
+    pts = synthetic_clouds(B, 1024, seed=21)
+    np.random.seed(123)
+    captured = {}
+    orig = act.VisableOnlyMaskTransformer._mask_center_rand
+
+    def capture(self, center, noaug=False):
+        m = orig(self, center, noaug)
+        captured["mask"] = m.clone()
+        return m
+
+    act.VisableOnlyMaskTransformer._mask_center_rand = capture
+    loss = model(pts)
+    loss.backward()
+    res = {"pts": pts.numpy(), "teacher": teacher.numpy(), "mask": captured["mask"].numpy(),
+           "loss": np.float32(loss.item())}
+    keep_full = ("proj_head.bias", "mask_token", "ACT_encoder.cls_token", "ACT_encoder.encoder.first_conv.0.weight",
+                 "ACT_encoder.blocks.blocks.0.norm1.weight", "ACT_decoder.norm.bias",
+                 "ACT_encoder.pos_embed.0.weight", "ACT_encoder.blocks.blocks.11.attn.proj.bias")
+    names, norms = [], []
+    for k, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        names.append(k)
+        norms.append(p.grad.norm().item())
+        if k in keep_full:
+            res["grad/" + k] = p.grad.numpy()
+    res["grad_names"] = np.array(names)
+    res["grad_norms"] = np.array(norms, np.float64)
+    for k, b in model.named_buffers():
+        if "running" in k:
+            res["buf/" + k] = b.numpy()
+    np.savez_compressed(os.path.join(GOLD, "student_step.npz"), **res)
+    print("student_step.npz loss", loss.item(), "n grads", len(names))
+
+
+def main():
+    if not os.path.isdir(shims.REFERENCE_ROOT):
+        sys.exit("needs /root/reference (authoring container only)")
+    shims.install()
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(8)
+    gen_group()
+    gen_block_cfg1()
+    gen_encoder()
+    gen_student_step()
+
+
+if __name__ == "__main__":
+    main()
