@@ -1,0 +1,85 @@
+// Shared device helpers for libact_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/act_b200.h"
+
+#define ACT_CHECK_LAUNCH()                                \
+    do {                                                  \
+        cudaError_t e__ = cudaGetLastError();             \
+        if (e__ != cudaSuccess) return (int)e__;          \
+    } while (0)
+
+#define ACT_CUDA(call)                                    \
+    do {                                                  \
+        cudaError_t e__ = (call);                         \
+        if (e__ != cudaSuccess) return (int)e__;          \
+    } while (0)
+
+namespace act {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier + 1-D bulk async copy (cp.async.bulk, SASS UBLKCP): global -> shared ------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// bytes % 16 == 0, src and dst 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Stage `bytes` of a cloud into shared memory: one bulk copy when alignment allows, else a plain
+// cooperative copy.  All threads of the CTA must call; returns after the data is visible to all.
+__device__ __forceinline__ void stage_cloud(float *dst, const float *src, int nfloats, uint64_t *bar,
+                                            uint32_t parity) {
+    const uint32_t bytes = (uint32_t)nfloats * 4u;
+    const bool bulk_ok = ((bytes & 15u) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
+    if (bulk_ok) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(dst, src, bytes, bar);
+        }
+        mbar_wait(bar, parity);
+    } else {
+        for (int i = threadIdx.x; i < nfloats; i += blockDim.x) dst[i] = __ldg(src + i);
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ uint32_t redux_max(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+__device__ __forceinline__ uint32_t redux_min(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }
+
+}  // namespace act

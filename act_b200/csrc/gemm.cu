@@ -1,0 +1,412 @@
+// bf16 x bf16 -> fp32 GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM),
+// operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle), with the element-wise work that
+// surrounds every dense op of the ACT step fused into the epilogue.
+//
+// This is the engine under every Linear / 1x1-Conv of the hot path (reference: nn.Linear in
+// /root/reference/models/act.py:35-69, nn.Conv1d k=1 in models/dvae.py:189-200 -- cuBLAS/cuDNN fp32
+// there) and of their backward passes:
+//     D[M,N] = epilogue( sum_k A[m,k] * B[n,k] )
+// Each operand may be K-major (row-major [MN, K], the forward layout of activations and of
+// nn.Linear.weight) or MN-major (row-major [K, MN]); MN-major operands let dgrad (dX = dY . W) and wgrad
+// (dW = dY^T . X) read the SAME tensors the forward wrote, so no transposed copies of weights,
+// activations or gradients ever exist in HBM.
+//
+// Kernel anatomy (one 128 x BN output tile per CTA, 2 CTAs resident per SM so one CTA's epilogue overlaps
+// the other's main loop):  warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected
+// lane; tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16 per instruction, tcgen05.commit releases
+// smem stages / signals the epilogue), warps 2-5 = epilogue (tcgen05.ld 32x32b, one accumulator row per
+// thread).  3-stage smem ring guarded by full/empty mbarriers; TMEM allocation of BN columns.
+//
+// Epilogue (all optional, runtime-selected, warp-uniform): + bias[n];  store pre-activation (bf16);
+// GELU(erf) / ReLU;  multiply by GELU'(aux) or by (aux > 0) (dgrad through the activation);
+// + residual[m,n] (fp32, may alias the output: the residual stream is updated in place);  output bf16 or
+// fp32;  split-K with fp32 atomic accumulation (wgrad: K = B*T tokens, few output tiles).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace act {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;          // 64 bf16 = 128 B = one swizzle row
+constexpr int GEMM_THREADS = 192;
+
+struct GemmEpi {
+    void *out;             // [M, ldo] bf16 or fp32
+    void *preact_out;      // nullable, bf16 [M, ldo]: acc + bias before the activation
+    const float *bias;     // nullable, [N]
+    const float *resid;    // nullable, fp32 [M, ldr]
+    const __nv_bfloat16 *mul_in;  // nullable, bf16 [M, ldm]
+    int ldo, ldr, ldm;
+    int out_fp32;          // 0: bf16, 1: fp32
+    int atomic;            // 1: fp32 atomicAdd into out (split-K)
+    int act;               // 0 none, 1 GELU(erf), 2 ReLU
+    int mul_mode;          // 0 none, 1: *= GELU'(mul_in), 2: *= (mul_in > 0)
+    float alpha;           // scales the accumulator first
+};
+
+// ---------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address >> 4 in [0,14),
+// leading byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version = 1 in [46,48),
+// layout type in [61,64) (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @ [4,6), a/b format BF16 = 1 @
+// [7,10) / [10,13), a_major @ 15, b_major @ 16 (1 = MN-major), N >> 3 @ [17,23), M >> 4 @ [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+// ------------------------------------------------------------------------------------- the kernel
+template <int BN, bool A_MN, bool B_MN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a,
+                                                                 const __grid_constant__ CUtensorMap tma_b,
+                                                                 const GemmEpi epi, int M, int N, int K,
+                                                                 int kb_per_split) {
+    constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
+    constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
+    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+    __shared__ uint32_t tmem_slot;
+
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * GEMM_BM, n0 = blockIdx.x * BN;
+    const int total_kb = (K + GEMM_BK - 1) / GEMM_BK;
+    const int kb0 = blockIdx.z * kb_per_split;
+    const int nkb = min(kb_per_split, total_kb - kb0);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&tmem_full_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES, ph = (i / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                uint8_t *sa = smem + s * STAGE_BYTES, *sb = sa + A_BYTES;
+                const int k = (kb0 + i) * GEMM_BK;
+                if (!A_MN) {
+                    tma_load_2d(&tma_a, &full_bar[s], sa, k, m0);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < GEMM_BM / 64; ++j)
+                        tma_load_2d(&tma_a, &full_bar[s], sa + j * (GEMM_BK * 128), m0 + j * 64, k);
+                }
+                if (!B_MN) {
+                    tma_load_2d(&tma_b, &full_bar[s], sb, k, n0);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < BN / 64; ++j)
+                        tma_load_2d(&tma_b, &full_bar[s], sb + j * (GEMM_BK * 128), n0 + j * 64, k);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(GEMM_BM, BN, A_MN, B_MN);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES, ph = (i / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+#pragma unroll
+                for (int k = 0; k < GEMM_BK / 16; ++k) {
+                    // K-major: 16 bf16 = 32 B further along the swizzled row; SBO = 8 rows x 128 B.
+                    // MN-major: 16 k-rows x 128 B further; LBO = next 64-wide MN atom, SBO = 8 k-rows.
+                    const uint64_t ad = A_MN ? make_smem_desc(sa + k * 2048, GEMM_BK * 128, 1024)
+                                             : make_smem_desc(sa + k * 32, 0, 1024);
+                    const uint64_t bd = B_MN ? make_smem_desc(sb + k * 2048, GEMM_BK * 128, 1024)
+                                             : make_smem_desc(sb + k * 32, 0, 1024);
+                    umma_bf16(tmem_d, ad, bd, idesc, (i | k) != 0);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(&tmem_full_bar);
+        }
+    } else {
+        // epilogue warps 2..5 -> TMEM lane quadrant warp % 4
+        const int quad = warp & 3;
+        const int row = m0 + quad * 32 + lane;
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        const bool row_ok = row < M;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            __syncwarp();
+            if (nkb > 0) {
+                tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
+            const int n = n0 + c0;
+            if (!row_ok || n >= N) continue;
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * epi.alpha;
+            const int ncols = min(32, N - n);   // N % 8 == 0 guaranteed by the host
+            if (epi.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (j < ncols) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(epi.bias + n + j));
+                        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                    }
+                }
+            }
+            if (epi.preact_out) {
+                __nv_bfloat16 *po = reinterpret_cast<__nv_bfloat16 *>(epi.preact_out) + (size_t)row * epi.ldo + n;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    if (j < ncols) {
+                        uint4 pk;
+                        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
+                        *reinterpret_cast<uint4 *>(po + j) = pk;
+                    }
+                }
+            }
+            if (epi.act == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+            } else if (epi.act == 2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (epi.mul_mode) {
+                const __nv_bfloat16 *mi = epi.mul_in + (size_t)row * epi.ldm + n;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    if (j < ncols) {
+                        const uint4 pk = __ldg(reinterpret_cast<const uint4 *>(mi + j));
+                        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&pk);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const float2 u = __bfloat1622float2(h[t]);
+                            if (epi.mul_mode == 1) {
+                                f[j + 2 * t] *= gelu_erf_grad(u.x);
+                                f[j + 2 * t + 1] *= gelu_erf_grad(u.y);
+                            } else {
+                                f[j + 2 * t] = u.x > 0.f ? f[j + 2 * t] : 0.f;
+                                f[j + 2 * t + 1] = u.y > 0.f ? f[j + 2 * t + 1] : 0.f;
+                            }
+                        }
+                    }
+                }
+            }
+            if (epi.resid) {
+                const float *r = epi.resid + (size_t)row * epi.ldr + n;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (j < ncols) {
+                        const float4 r4 = *reinterpret_cast<const float4 *>(r + j);
+                        f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+                    }
+                }
+            }
+            if (epi.out_fp32) {
+                float *o = reinterpret_cast<float *>(epi.out) + (size_t)row * epi.ldo + n;
+                if (epi.atomic) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncols) atomicAdd(o + j, f[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        if (j < ncols) *reinterpret_cast<float4 *>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                }
+            } else {
+                __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(epi.out) + (size_t)row * epi.ldo + n;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    if (j < ncols) {
+                        uint4 pk;
+                        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
+                        *reinterpret_cast<uint4 *>(o + j) = pk;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_d, BN);
+    }
+}
+
+// -------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;   // idempotent lazy lookup; racing threads store the same value
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2-D bf16 row-major tensor [rows, cols] with pitch ld (elements); box = [box_rows, 64 cols], 128B swizzle.
+static int make_map(CUtensorMap *map, const void *ptr, long long rows, long long cols, long long ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return ACT_EUNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * 2) % 16) return ACT_EALIGN;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? ACT_OK : ACT_EINVAL;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmEpi &epi, int M, int N, int K,
+                       int splits, cudaStream_t st) {
+    constexpr int STAGES = 3;
+    constexpr size_t smem = (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024;
+    auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES>;
+    ACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int total_kb = (K + GEMM_BK - 1) / GEMM_BK;
+    const int kbps = (total_kb + splits - 1) / splits;
+    const int nsplit = (total_kb + kbps - 1) / kbps;
+    dim3 grid((N + BN - 1) / BN, (M + GEMM_BM - 1) / GEMM_BM, nsplit);
+    kern<<<grid, GEMM_THREADS, smem, st>>>(ta, tb, epi, M, N, K, kbps);
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}
+
+}  // namespace act
+
+extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, int a_mn_major, int b_mn_major,
+                             int lda, int ldb, void *out, int ldo, int out_fp32, const float *bias, int act_kind,
+                             void *preact_out, const void *mul_in, int ldm, int mul_mode, const float *resid, int ldr,
+                             float alpha, int splits, int block_n, void *stream) {
+    using namespace act;
+    if (!A || !B || !out || M <= 0 || N <= 0 || K <= 0) return ACT_EINVAL;
+    if ((N % 8) || (ldo % 8) || (reinterpret_cast<uintptr_t>(out) & 15)) return ACT_EALIGN;
+    if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) return ACT_EALIGN;
+    if (resid && ((reinterpret_cast<uintptr_t>(resid) & 15) || (ldr % 4))) return ACT_EALIGN;
+    if (mul_in && ((reinterpret_cast<uintptr_t>(mul_in) & 15) || (ldm % 8))) return ACT_EALIGN;
+    if (preact_out && (reinterpret_cast<uintptr_t>(preact_out) & 15)) return ACT_EALIGN;
+    if (splits < 1) splits = 1;
+    if (splits > 1 && !out_fp32) return ACT_EINVAL;
+    if (splits > 1 && (bias || act_kind || mul_mode || resid || preact_out)) return ACT_EINVAL;
+    const int BN = (block_n == 64 || block_n == 128) ? block_n : (N <= 64 ? 64 : 128);
+    GemmEpi epi;
+    epi.out = out; epi.preact_out = preact_out; epi.bias = bias; epi.resid = resid;
+    epi.mul_in = reinterpret_cast<const __nv_bfloat16 *>(mul_in);
+    epi.ldo = ldo; epi.ldr = ldr; epi.ldm = ldm; epi.out_fp32 = out_fp32; epi.atomic = splits > 1 ? 1 : 0;
+    epi.act = act_kind; epi.mul_mode = mul_in ? mul_mode : 0; epi.alpha = alpha;
+    CUtensorMap ta, tb;
+    int rc;
+    // K-major operand: global [MN, K], box [BLOCK_MN rows, 64].  MN-major: global [K, MN], box [64 k-rows, 64].
+    rc = a_mn_major ? make_map(&ta, A, K, M, lda, GEMM_BK) : make_map(&ta, A, M, K, lda, GEMM_BM);
+    if (rc) return rc;
+    rc = b_mn_major ? make_map(&tb, B, K, N, ldb, GEMM_BK) : make_map(&tb, B, N, K, ldb, BN);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+#define ACT_GEMM_DISPATCH(BN_)                                                                         \
+    do {                                                                                               \
+        if (!a_mn_major && !b_mn_major) return launch_gemm<BN_, false, false>(ta, tb, epi, M, N, K, splits, st); \
+        if (!a_mn_major && b_mn_major) return launch_gemm<BN_, false, true>(ta, tb, epi, M, N, K, splits, st);   \
+        if (a_mn_major && !b_mn_major) return launch_gemm<BN_, true, false>(ta, tb, epi, M, N, K, splits, st);   \
+        return launch_gemm<BN_, true, true>(ta, tb, epi, M, N, K, splits, st);                         \
+    } while (0)
+    if (BN == 64) ACT_GEMM_DISPATCH(64);
+    ACT_GEMM_DISPATCH(128);
+#undef ACT_GEMM_DISPATCH
+}

@@ -1,0 +1,1 @@
+from . import pointnet2_utils  # noqa: F401

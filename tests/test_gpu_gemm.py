@@ -1,0 +1,96 @@
+"""GPU numerics: the tcgen05/TMA GEMM and its fused epilogues vs a plain PyTorch fp32 reference on the SAME
+bf16-rounded operands.  Tolerance: fp32 accumulation of exact bf16 products, so the only differences are
+summation order (<= 1e-5 relative to the row scale) and, for bf16 outputs, the final rounding (2^-8)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from act_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(*shape, scale=1.0):
+    return (torch.randn(*shape, device="cuda") * scale).to(torch.bfloat16)
+
+
+def check(got, want, out_bf16):
+    want = want.float()
+    scale = want.abs().max().item() + 1e-6
+    tol = (2 ** -7 if out_bf16 else 2e-5) * scale
+    err = (got.float() - want).abs().max().item()
+    assert err <= tol, (err, tol)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (3456, 1152, 384), (3456, 384, 1536), (108, 384, 384),
+                                   (8192, 1536, 384), (300, 72, 200), (128, 64, 1024), (4096, 512, 512)])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_layouts(M, N, K, a_mn, b_mn):
+    torch.manual_seed(M + N + K)
+    if (a_mn and M % 8) or (b_mn and N % 8) or K % 8:
+        pytest.skip("pitch must be a multiple of 8 elements")
+    a, b = rnd(M, K), rnd(N, K)
+    want = a.float() @ b.float().t()
+    A = a.t().contiguous() if a_mn else a
+    B = b.t().contiguous() if b_mn else b
+    for out_dtype in (torch.float32, torch.bfloat16):
+        got = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, out_dtype=out_dtype)
+        check(got, want, out_dtype == torch.bfloat16)
+
+
+@pytest.mark.parametrize("block_n", [64, 128])
+def test_gemm_epilogues(block_n):
+    torch.manual_seed(0)
+    M, N, K = 1000, 384, 256
+    a, w = rnd(M, K), rnd(N, K, scale=0.1)
+    bias = torch.randn(N, device="cuda")
+    lin = F.linear(a.float(), w.float(), bias)
+    # bias + GELU with pre-activation side output (fc1)
+    pre = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    got = ops.gemm(a, w, bias=bias, act=ops.ACT_GELU, preact_out=pre, block_n=block_n)
+    check(pre, lin, True)
+    check(got, F.gelu(lin), True)
+    # bias + ReLU
+    check(ops.gemm(a, w, bias=bias, act=ops.ACT_RELU, block_n=block_n), F.relu(lin), True)
+    # bias + residual, fp32, in place on the residual stream (proj / fc2)
+    x = torch.randn(M, N, device="cuda")
+    want = x + lin
+    got = ops.gemm(a, w, bias=bias, resid=x, out=x, block_n=block_n)
+    assert got.data_ptr() == x.data_ptr()
+    check(x, want, False)
+    # dgrad through GELU: (dY . W) * gelu'(u), MN-major weight
+    dy, u = rnd(M, N), rnd(M, K)
+    uu = u.float().requires_grad_(True)
+    F.gelu(uu).backward(dy.float() @ w.float())
+    got = ops.gemm(dy, w, b_mn=True, mul_in=u, mul_mode=ops.MUL_GELU_GRAD, block_n=block_n)
+    check(got, uu.grad, True)
+    got = ops.gemm(dy, w, b_mn=True, mul_in=u, mul_mode=ops.MUL_RELU_MASK, block_n=block_n)
+    check(got, (dy.float() @ w.float()) * (u.float() > 0), True)
+    # alpha
+    check(ops.gemm(a, w, alpha=0.125, out_dtype=torch.float32, block_n=block_n), 0.125 * (lin - bias), False)
+
+
+@pytest.mark.parametrize("splits", [1, 2, 7, 64])
+def test_gemm_wgrad_splitk(splits):
+    """dW[N,K] = dY^T X with both operands MN-major, split over the token dimension, atomically accumulated."""
+    torch.manual_seed(1)
+    T, N, K = 3456, 384, 1536
+    dy, x = rnd(T, N, scale=0.1), rnd(T, K)
+    want = dy.float().t() @ x.float()
+    got = ops.gemm(dy, x, a_mn=True, b_mn=True, out_dtype=torch.float32, splits=splits)
+    check(got, want, False)
+    acc = torch.ones(N, K, device="cuda")
+    ops.gemm(dy, x, a_mn=True, b_mn=True, out=acc, splits=max(splits, 2))
+    check(acc, want + 1, False)
+
+
+def test_gemm_strided_views():
+    """Operands / outputs that are column slices of wider buffers (pitch != width), as the qkv split uses."""
+    torch.manual_seed(2)
+    big = rnd(512, 1152)
+    w = rnd(384, 384, scale=0.1)
+    a = big[:, 384:768]
+    out_big = torch.zeros(512, 1024, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(a, w, out=out_big[:, 128:512])
+    check(out_big[:, 128:512], a.float() @ w.float().t(), True)
+    assert (out_big[:, :128] == 0).all() and (out_big[:, 512:] == 0).all()

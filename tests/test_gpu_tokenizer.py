@@ -1,0 +1,150 @@
+"""GPU parity: FPS / kNN / Group / gather / Chamfer kernels (through the C ABI) vs the CPU oracle and the
+golden fixtures -- bit-exact indices, exact fp32 for copies/subtractions, tolerance only where the reference
+itself is order-dependent (atomic scatter in the Chamfer backward)."""
+import numpy as np
+import pytest
+import torch
+
+from act_b200 import ops
+from oracle import cpu_ref, ref_model
+
+pytestmark = pytest.mark.gpu
+CLOUDS = ["shapenet", "dup", "lattice", "near_origin", "n1000", "n600", "identical"]
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("name", CLOUDS)
+def test_group_matches_golden(golden, name):
+    g = golden("group.npz")
+    xyz = dev(g[name + "/xyz"])
+    nb, center, idx, fps_idx = ops.group(xyz, 64, 32)
+    assert np.array_equal(fps_idx.cpu().numpy(), g[name + "/fps_idx"])
+    assert np.array_equal(idx.cpu().numpy(), g[name + "/knn_idx"].astype(np.int64))
+    assert np.array_equal(center.cpu().numpy(), g[name + "/center"])
+    assert np.array_equal(nb.cpu().numpy(), g[name + "/neighborhood"])
+    assert idx.dtype == torch.int64 and idx.is_contiguous() and fps_idx.dtype == torch.int32
+
+
+@pytest.mark.parametrize("B,N,G", [(3, 64, 16), (2, 257, 33), (5, 512, 64), (2, 2048, 128), (2, 4096, 128),
+                                   (2, 8192, 512), (1, 10000, 64), (130, 1024, 64)])
+def test_fps_vs_oracle_sizes(B, N, G):
+    xyz = ref_model.synthetic_clouds(B, N, seed=N + G).numpy()
+    idx, center = ops.furthest_point_sample(dev(xyz), G, return_center=True)
+    want = cpu_ref.fps(xyz, G)
+    assert np.array_equal(idx.cpu().numpy(), want)
+    assert np.array_equal(center.cpu().numpy(), np.take_along_axis(xyz, want[..., None].astype(np.int64), 1))
+
+
+def test_fps_quantised_ties():
+    """Coordinates on a coarse grid -> many exactly equal distances: exercises the (k mod 512, k) tie rule."""
+    rng = np.random.default_rng(3)
+    xyz = (rng.integers(-4, 5, size=(4, 1536, 3)) * 0.25).astype(np.float32)
+    assert np.array_equal(ops.furthest_point_sample(dev(xyz), 96).cpu().numpy(), cpu_ref.fps(xyz, 96))
+
+
+@pytest.mark.parametrize("B,N,Q,K", [(2, 40, 7, 32), (3, 1000, 64, 32), (2, 1024, 64, 4), (1, 8192, 512, 32),
+                                     (2, 333, 50, 1), (128, 1024, 64, 32)])
+def test_knn_vs_oracle(B, N, Q, K):
+    rng = np.random.default_rng(N + K)
+    ref = ref_model.synthetic_clouds(B, N, seed=N).numpy()
+    query = ref[:, rng.permutation(N)[:Q]] if Q <= N else rng.standard_normal((B, Q, 3)).astype(np.float32)
+    query = np.ascontiguousarray(query + (0.01 * rng.standard_normal(query.shape)).astype(np.float32) * (K % 2))
+    d, i, nb = ops.knn(dev(ref), dev(query), K, want_dist=True, want_neighborhood=True)
+    wd, wi = cpu_ref.knn(ref, query, K)
+    assert np.array_equal(i.cpu().numpy(), wi)
+    assert np.array_equal(d.cpu().numpy(), wd)          # sqrtf is correctly rounded on both sides
+    want_nb = np.take_along_axis(ref[:, None], wi[..., None], 2) - query[:, :, None]
+    assert np.array_equal(nb.cpu().numpy(), want_nb)
+
+
+def test_knn_quantised_ties_and_dropin_layouts():
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dropin"))
+    from knn_cuda import KNN
+    rng = np.random.default_rng(5)
+    ref = (rng.integers(-3, 4, size=(2, 700, 3)) * 0.5).astype(np.float32)
+    query = ref[:, :20].copy()
+    wd, wi = cpu_ref.knn(ref, query, 4)
+    d, i = KNN(4, transpose_mode=True)(dev(ref), dev(query))
+    assert np.array_equal(i.cpu().numpy(), wi) and np.array_equal(d.cpu().numpy(), wd)
+    d, i = KNN(4, transpose_mode=False)(dev(ref).transpose(1, 2).contiguous(), dev(query).transpose(1, 2).contiguous())
+    assert i.is_contiguous() and i.shape == (2, 4, 20)
+    assert np.array_equal(i.cpu().numpy(), wi.transpose(0, 2, 1))
+    i.view(-1)                                            # the reference's callers do this (dvae.py:72,178)
+
+
+def test_gather_operation_fwd_bwd():
+    rng = np.random.default_rng(0)
+    feat = rng.standard_normal((3, 5, 100)).astype(np.float32)
+    idx = rng.integers(0, 100, size=(3, 17)).astype(np.int32)
+    f = dev(feat).requires_grad_(True)
+    out = ops.gather_operation(f, dev(idx))
+    assert np.array_equal(out.detach().cpu().numpy(), cpu_ref.gather(feat, idx))
+    g = rng.standard_normal(out.shape).astype(np.float32)
+    out.backward(dev(g))
+    np.testing.assert_allclose(f.grad.cpu().numpy(), cpu_ref.gather_grad(g, idx, 100), rtol=1e-6, atol=1e-6)
+
+
+def test_misc_fps_through_dropin():
+    """utils/misc.py:39-46 composition: fps -> gather_operation on the transposed cloud."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dropin"))
+    from pointnet2_ops import pointnet2_utils
+    xyz = ref_model.synthetic_clouds(2, 1024, seed=9)
+    data = xyz.cuda()
+    fps_idx = pointnet2_utils.furthest_point_sample(data, 64)
+    fps_data = pointnet2_utils.gather_operation(data.transpose(1, 2).contiguous(), fps_idx).transpose(1, 2).contiguous()
+    _, center, _, _ = cpu_ref.group(xyz.numpy(), 64, 32)
+    assert np.array_equal(fps_data.cpu().numpy(), center)
+
+
+@pytest.mark.parametrize("B,n,m", [(4096, 8, 32), (4096, 32, 32), (1, 512, 1024), (1, 2048, 1024), (3, 600, 1030),
+                                   (2, 1, 1), (5, 4100, 3000)])
+def test_chamfer_vs_oracle(B, n, m):
+    rng = np.random.default_rng(n * 7 + m)
+    Bc = min(B, 64)                                            # oracle on a slice for the big batches
+    a = rng.standard_normal((B, n, 3)).astype(np.float32)
+    b = rng.standard_normal((B, m, 3)).astype(np.float32)
+    d1, d2, i1, i2 = ops.chamfer_forward(dev(a), dev(b))
+    w = cpu_ref.chamfer_forward(a[-Bc:], b[-Bc:])
+    for got, want in zip((d1, d2, i1, i2), w):
+        assert np.array_equal(got[-Bc:].cpu().numpy(), want)
+    g1 = rng.standard_normal((B, n)).astype(np.float32)
+    g2 = rng.standard_normal((B, m)).astype(np.float32)
+    gx1, gx2 = ops.chamfer_backward(dev(a), dev(b), i1, i2, dev(g1), dev(g2))
+    w1, w2 = cpu_ref.chamfer_backward(a[-Bc:], b[-Bc:], w[2], w[3], g1[-Bc:], g2[-Bc:])
+    np.testing.assert_allclose(gx1[-Bc:].cpu().numpy(), w1, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(gx2[-Bc:].cpu().numpy(), w2, rtol=1e-4, atol=1e-4)
+
+
+def test_chamfer_ties_and_autograd_function():
+    a = torch.zeros(2, 4, 3, device="cuda")
+    b = torch.zeros(2, 2500, 3, device="cuda")
+    d1, d2, i1, i2 = ops.chamfer_forward(a, b)
+    assert (i1 == 0).all() and (i2 == 0).all() and (d1 == 0).all()
+    x = torch.randn(3, 32, 3, device="cuda", requires_grad=True)
+    y = torch.randn(3, 32, 3, device="cuda", requires_grad=True)
+    d1, d2 = ops.ChamferFunction.apply(x, y)
+    (d1.mean() + d2.mean()).backward()
+    xx, yy = x.detach().double().requires_grad_(True), y.detach().double().requires_grad_(True)
+    dd = ((xx[:, :, None] - yy[:, None]) ** 2).sum(-1)
+    (dd.min(2)[0].mean() + dd.min(1)[0].mean()).backward()
+    torch.testing.assert_close(x.grad.double(), xx.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(y.grad.double(), yy.grad, rtol=1e-4, atol=1e-5)
+
+
+def test_group_full_size_properties():
+    """BASELINE size (B=128): properties that need no oracle -- centre is neighbour 0, distances ascending,
+    every index in range, neighbourhood == xyz[idx] - centre."""
+    xyz = ref_model.synthetic_clouds(128, 1024).cuda()
+    nb, center, idx, fps_idx = ops.group(xyz, 64, 32)
+    assert (idx[:, :, 0] == fps_idx.long()).all()
+    assert idx.min() >= 0 and idx.max() < 1024
+    gathered = torch.gather(xyz[:, None].expand(-1, 64, -1, -1), 2, idx[..., None].expand(-1, -1, -1, 3))
+    assert torch.equal(nb, gathered - center[:, :, None])
+    d = nb.pow(2).sum(-1)
+    assert (d[:, :, 1:] >= d[:, :, :-1] - 1e-6).all()
+    assert all(len(set(r.tolist())) == 64 for r in fps_idx[:4].cpu())
