@@ -38,6 +38,9 @@ struct GemmEpi {
     const float *bias;     // nullable, [N]
     const float *resid;    // nullable, fp32 [M, ldr]
     const __nv_bfloat16 *mul_in;  // nullable, bf16 [M, ldm]
+    const float *row_scale;       // nullable, f32 [ceil(M / rows_per_scale)]: DropPath gate of the branch
+    int rows_per_scale;
+    int resid_row_div;            // residual row = m / resid_row_div (broadcast of a per-group term over its points)
     int ldo, ldr, ldm;
     int out_fp32;          // 0: bf16, 1: fp32
     int atomic;            // 1: fp32 atomicAdd into out (split-K)
@@ -277,8 +280,13 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_co
                     }
                 }
             }
+            if (epi.row_scale) {
+                const float rsc = __ldg(epi.row_scale + row / epi.rows_per_scale);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] *= rsc;
+            }
             if (epi.resid) {
-                const float *r = epi.resid + (size_t)row * epi.ldr + n;
+                const float *r = epi.resid + (size_t)(row / epi.resid_row_div) * epi.ldr + n;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     if (j < ncols) {
@@ -291,8 +299,11 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_co
                 float *o = reinterpret_cast<float *>(epi.out) + (size_t)row * epi.ldo + n;
                 if (epi.atomic) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < ncols) atomicAdd(o + j, f[j]);
+                    for (int j = 0; j < 32; j += 4)
+                        if (j < ncols)
+                            asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j),
+                                         "f"(f[j]), "f"(f[j + 1]), "f"(f[j + 2]), "f"(f[j + 3])
+                                         : "memory");
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
@@ -374,7 +385,8 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmE
 extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, int a_mn_major, int b_mn_major,
                              int lda, int ldb, void *out, int ldo, int out_fp32, const float *bias, int act_kind,
                              void *preact_out, const void *mul_in, int ldm, int mul_mode, const float *resid, int ldr,
-                             float alpha, int splits, int block_n, void *stream) {
+                             int resid_row_div, const float *row_scale, int rows_per_scale, float alpha, int splits,
+                             int block_n, void *stream) {
     using namespace act;
     if (!A || !B || !out || M <= 0 || N <= 0 || K <= 0) return ACT_EINVAL;
     if ((N % 8) || (ldo % 8) || (reinterpret_cast<uintptr_t>(out) & 15)) return ACT_EALIGN;
@@ -384,13 +396,16 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
     if (preact_out && (reinterpret_cast<uintptr_t>(preact_out) & 15)) return ACT_EALIGN;
     if (splits < 1) splits = 1;
     if (splits > 1 && !out_fp32) return ACT_EINVAL;
-    if (splits > 1 && (bias || act_kind || mul_mode || resid || preact_out)) return ACT_EINVAL;
+    if (splits > 1 && (bias || act_kind || mul_mode || resid || preact_out || row_scale)) return ACT_EINVAL;
+    if (row_scale && rows_per_scale <= 0) return ACT_EINVAL;
     const int BN = (block_n == 64 || block_n == 128) ? block_n : (N <= 64 ? 64 : 128);
     GemmEpi epi;
     epi.out = out; epi.preact_out = preact_out; epi.bias = bias; epi.resid = resid;
     epi.mul_in = reinterpret_cast<const __nv_bfloat16 *>(mul_in);
     epi.ldo = ldo; epi.ldr = ldr; epi.ldm = ldm; epi.out_fp32 = out_fp32; epi.atomic = splits > 1 ? 1 : 0;
     epi.act = act_kind; epi.mul_mode = mul_in ? mul_mode : 0; epi.alpha = alpha;
+    epi.row_scale = row_scale; epi.rows_per_scale = rows_per_scale;
+    epi.resid_row_div = resid_row_div > 0 ? resid_row_div : 1;
     CUtensorMap ta, tb;
     int rc;
     // K-major operand: global [MN, K], box [BLOCK_MN rows, 64].  MN-major: global [K, MN], box [64 k-rows, 64].

@@ -1,0 +1,467 @@
+// Bandwidth-bound pieces of the per-group mini-PointNet (Encoder, /root/reference/models/dvae.py:185-215)
+// for sm_100a.  The four 1x1 convs are GEMMs on the tcgen05 path (gemm.cu); this file holds what sits
+// between them, fused so that every [B*G*k, C] activation is touched the minimum number of times:
+//
+//   conv1 (3->128) + BatchNorm1 + ReLU  : K = 3 is not tensor-core work.  BN1's batch statistics follow
+//       ANALYTICALLY from the input's mean and 3x3 second moment (conv1 is linear), so one 9-number reduction
+//       over the points replaces a pass over the [M,128] conv output; conv1, BN1 (folded into the weights)
+//       and ReLU then run as one kernel writing the bf16 operand of conv2.
+//   max over the k points of a group (+ arg-max for the backward), group sums, BatchNorm2 statistics /
+//       apply(+ReLU) / backward, and the conv1/BN1 backward with x-hat recomputed from the 3-D input instead
+//       of stored.
+// All kernels use the same access pattern: a thread owns 8 consecutive channels (one 16-byte bf16 vector) of
+// a row, consecutive threads own consecutive vectors, so every warp access is a contiguous 512-byte segment.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace act {
+
+__device__ __forceinline__ void unpack8(const uint4 &u, float (&f)[8]) {
+    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const float2 v = __bfloat1622float2(h[t]);
+        f[2 * t] = v.x;
+        f[2 * t + 1] = v.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 u;
+    __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&u);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(f[2 * t], f[2 * t + 1]);
+    return u;
+}
+
+// ---- input moments: out[0..2] = sum p, out[3..8] = sum (xx, xy, xz, yy, yz, zz), in double -------------
+__global__ void __launch_bounds__(256) pn_moments_kernel(const float *__restrict__ p, long long M,
+                                                         double *__restrict__ out) {
+    double a[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a[i] = 0.0;
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+        const float x = __ldg(p + m * 3), y = __ldg(p + m * 3 + 1), z = __ldg(p + m * 3 + 2);
+        a[0] += x; a[1] += y; a[2] += z;
+        a[3] += (double)x * x; a[4] += (double)x * y; a[5] += (double)x * z;
+        a[6] += (double)y * y; a[7] += (double)y * z; a[8] += (double)z * z;
+    }
+    __shared__ double s[8][9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        double v = a[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 9) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s[w][threadIdx.x];
+        atomicAdd(out + threadIdx.x, t);
+    }
+}
+
+// ---- conv1 (+ folded BN1) + ReLU: out[m, c] = relu(W[c] . p[m] + b[c]) as bf16, C = 128 -----------------
+__global__ void __launch_bounds__(256) pn_conv1_kernel(const float *__restrict__ p, const float *__restrict__ W,
+                                                       const float *__restrict__ b, long long M, int relu,
+                                                       __nv_bfloat16 *__restrict__ out) {
+    __shared__ float sW[128 * 3], sb[128];
+    for (int i = threadIdx.x; i < 384; i += 256) sW[i] = __ldg(W + i);
+    for (int i = threadIdx.x; i < 128; i += 256) sb[i] = __ldg(b + i);
+    __syncthreads();
+    const int c0 = (threadIdx.x & 15) * 8;
+    for (long long m = blockIdx.x * 16LL + (threadIdx.x >> 4); m < M; m += gridDim.x * 16LL) {
+        const float x = __ldg(p + m * 3), y = __ldg(p + m * 3 + 1), z = __ldg(p + m * 3 + 2);
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            float v = fmaf(sW[c * 3 + 2], z, fmaf(sW[c * 3 + 1], y, fmaf(sW[c * 3], x, sb[c])));
+            f[j] = relu ? fmaxf(v, 0.f) : v;
+        }
+        *reinterpret_cast<uint4 *>(out + m * 128 + c0) = pack8(f);
+    }
+}
+
+// ---- max / sum over the k rows of each group -----------------------------------------------------------
+// x bf16 [G*k, C] -> out_bf16 / out_f32 (nullable each) [G, C], arg u8 [G, C] (nullable)
+__global__ void __launch_bounds__(256) group_max_kernel(const __nv_bfloat16 *__restrict__ x, int G, int k, int C,
+                                                        __nv_bfloat16 *__restrict__ out_bf16,
+                                                        float *__restrict__ out_f32, uint8_t *__restrict__ arg) {
+    const int vec_per_row = C / 8;
+    const long long total = (long long)G * vec_per_row;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i / vec_per_row), c0 = (int)(i % vec_per_row) * 8;
+        const __nv_bfloat16 *src = x + ((size_t)g * k) * C + c0;
+        float best[8];
+        int bi[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+        for (int r = 0; r < k; ++r) {
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * C)), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (f[j] > best[j]) { best[j] = f[j]; bi[j] = r; }
+        }
+        if (out_bf16) *reinterpret_cast<uint4 *>(out_bf16 + (size_t)g * C + c0) = pack8(best);
+        if (out_f32) {
+            *reinterpret_cast<float4 *>(out_f32 + (size_t)g * C + c0) = make_float4(best[0], best[1], best[2], best[3]);
+            *reinterpret_cast<float4 *>(out_f32 + (size_t)g * C + c0 + 4) = make_float4(best[4], best[5], best[6], best[7]);
+        }
+        if (arg) {
+            uint2 pk;
+            pk.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+            pk.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+            *reinterpret_cast<uint2 *>(arg + (size_t)g * C + c0) = pk;
+        }
+    }
+}
+
+// scatter of the max's gradient: dF[g*k + r, c] (+)= (arg[g,c] == r) ? dout[g,c] : 0      (dense, bf16)
+__global__ void __launch_bounds__(256) group_max_bwd_kernel(const float *__restrict__ dout,
+                                                            const uint8_t *__restrict__ arg, int G, int k, int C,
+                                                            int accumulate, __nv_bfloat16 *__restrict__ dF) {
+    const int vec_per_row = C / 8;
+    const long long total = (long long)G * vec_per_row;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i / vec_per_row), c0 = (int)(i % vec_per_row) * 8;
+        const float4 d0 = __ldg(reinterpret_cast<const float4 *>(dout + (size_t)g * C + c0));
+        const float4 d1 = __ldg(reinterpret_cast<const float4 *>(dout + (size_t)g * C + c0 + 4));
+        const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        const uint2 pk = __ldg(reinterpret_cast<const uint2 *>(arg + (size_t)g * C + c0));
+        int a[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { a[j] = (pk.x >> (8 * j)) & 0xff; a[4 + j] = (pk.y >> (8 * j)) & 0xff; }
+        __nv_bfloat16 *dst = dF + ((size_t)g * k) * C + c0;
+        for (int r = 0; r < k; ++r) {
+            float f[8];
+            if (accumulate) unpack8(*reinterpret_cast<const uint4 *>(dst + (size_t)r * C), f);
+            else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += (a[j] == r) ? d[j] : 0.f;
+            *reinterpret_cast<uint4 *>(dst + (size_t)r * C) = pack8(f);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) group_sum_kernel(const __nv_bfloat16 *__restrict__ x, int G, int k, int C,
+                                                        __nv_bfloat16 *__restrict__ out_bf16,
+                                                        float *__restrict__ out_f32) {
+    const int vec_per_row = C / 8;
+    const long long total = (long long)G * vec_per_row;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i / vec_per_row), c0 = (int)(i % vec_per_row) * 8;
+        const __nv_bfloat16 *src = x + ((size_t)g * k) * C + c0;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int r = 0; r < k; ++r) {
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * C)), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+        if (out_bf16) *reinterpret_cast<uint4 *>(out_bf16 + (size_t)g * C + c0) = pack8(acc);
+        if (out_f32) {
+            *reinterpret_cast<float4 *>(out_f32 + (size_t)g * C + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<float4 *>(out_f32 + (size_t)g * C + c0 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+    }
+}
+
+// ---- per-channel reductions over rows --------------------------------------------------------------------
+// MODE 0: s1 = sum x, s2 = sum x^2                         (BatchNorm forward statistics)
+// MODE 1: s1 = sum dz, s2 = sum dz * xhat, xhat from x      (BatchNorm backward statistics)
+// Thread = 8 channels of one row; threads of a CTA tile [rows_per_cta][C/8]; partials -> smem -> atomics.
+template <int MODE>
+__global__ void __launch_bounds__(256) chan_reduce_kernel(const __nv_bfloat16 *__restrict__ a,
+                                                          const __nv_bfloat16 *__restrict__ x,
+                                                          const float *__restrict__ mean,
+                                                          const float *__restrict__ rstd, long long M, int C,
+                                                          float *__restrict__ s1, float *__restrict__ s2) {
+    extern __shared__ float sm[];  // [rows_per_cta][2][C]
+    const int vpr = C / 8, rpc = 256 / vpr;
+    const int v = threadIdx.x % vpr, rl = threadIdx.x / vpr;
+    const int c0 = v * 8;
+    float acc1[8], acc2[8], mu[8], rs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc1[j] = acc2[j] = 0.f; mu[j] = 0.f; rs[j] = 1.f; }
+    if (rl < rpc) {
+        if (MODE == 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { mu[j] = __ldg(mean + c0 + j); rs[j] = __ldg(rstd + c0 + j); }
+        }
+        for (long long m = blockIdx.x * (long long)rpc + rl; m < M; m += (long long)gridDim.x * rpc) {
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4 *>(a + m * C + c0)), f);
+            if (MODE == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { acc1[j] += f[j]; acc2[j] = fmaf(f[j], f[j], acc2[j]); }
+            } else {
+                float xv[8];
+                unpack8(__ldg(reinterpret_cast<const uint4 *>(x + m * C + c0)), xv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { acc1[j] += f[j]; acc2[j] = fmaf(f[j], (xv[j] - mu[j]) * rs[j], acc2[j]); }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sm[(rl * 2) * C + c0 + j] = acc1[j]; sm[(rl * 2 + 1) * C + c0 + j] = acc2[j]; }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * C; c += 256) {
+        const int which = c / C, cc = c % C;
+        float t = 0.f;
+        for (int r = 0; r < rpc; ++r) t += sm[(r * 2 + which) * C + cc];
+        atomicAdd((which ? s2 : s1) + cc, t);
+    }
+}
+
+// y = relu?(x * scale[c] + shift[c])
+__global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16 *__restrict__ x,
+                                                       const float *__restrict__ scale,
+                                                       const float *__restrict__ shift, long long nvec, int C, int relu,
+                                                       __nv_bfloat16 *__restrict__ y) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)((i * 8) % C);
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(x) + i), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float v = fmaf(f[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j));
+            f[j] = relu ? fmaxf(v, 0.f) : v;
+        }
+        reinterpret_cast<uint4 *>(y)[i] = pack8(f);
+    }
+}
+
+// dH = gamma * rstd * (dz - s1/M - xhat * s2/M)
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dz,
+                                                           const __nv_bfloat16 *__restrict__ x,
+                                                           const float *__restrict__ mean,
+                                                           const float *__restrict__ rstd,
+                                                           const float *__restrict__ gamma,
+                                                           const float *__restrict__ s1, const float *__restrict__ s2,
+                                                           long long M, int C, __nv_bfloat16 *__restrict__ dh) {
+    const long long nvec = M * C / 8;
+    const float invM = 1.f / (float)M;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)((i * 8) % C);
+        float d[8], xv[8];
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(dz) + i), d);
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(x) + i), xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            const float rs = __ldg(rstd + c);
+            const float xh = (xv[j] - __ldg(mean + c)) * rs;
+            d[j] = __ldg(gamma + c) * rs * (d[j] - __ldg(s1 + c) * invM - xh * __ldg(s2 + c) * invM);
+        }
+        reinterpret_cast<uint4 *>(dh)[i] = pack8(d);
+    }
+}
+
+// ---- conv1 + BN1 backward with x-hat recomputed from the 3-D input (C = 128) -----------------------------
+// h1[m,c] = W[c].p[m] + b[c];  xhat = (h1 - mean) * rstd;  dz = gradient w.r.t. the BN1 output (already
+// ReLU-masked by the conv2 dgrad epilogue).
+// PASS 0: s1[c] += sum dz, s2[c] += sum dz * xhat.
+// PASS 1: dh = gamma*rstd*(dz - s1/M - xhat*s2/M);  dW[c,:] += sum dh * p;  db[c] += sum dh.
+template <int PASS>
+__global__ void __launch_bounds__(256) pn_conv1_bwd_kernel(const __nv_bfloat16 *__restrict__ dz,
+                                                           const float *__restrict__ p, const float *__restrict__ W,
+                                                           const float *__restrict__ b, const float *__restrict__ mean,
+                                                           const float *__restrict__ rstd,
+                                                           const float *__restrict__ gamma, float *__restrict__ s1,
+                                                           float *__restrict__ s2, long long M,
+                                                           float *__restrict__ dW, float *__restrict__ db) {
+    __shared__ float sm[16][4][128];
+    const int c0 = (threadIdx.x & 15) * 8, rl = threadIdx.x >> 4;
+    float w[8][3], bb[8], mu[8], rs[8], k1[8], k2[8], gs[8];
+    const float invM = 1.f / (float)M;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        w[j][0] = __ldg(W + c * 3); w[j][1] = __ldg(W + c * 3 + 1); w[j][2] = __ldg(W + c * 3 + 2);
+        bb[j] = __ldg(b + c); mu[j] = __ldg(mean + c); rs[j] = __ldg(rstd + c);
+        if (PASS == 1) { k1[j] = __ldg(s1 + c) * invM; k2[j] = __ldg(s2 + c) * invM; gs[j] = __ldg(gamma + c) * rs[j]; }
+        else { k1[j] = k2[j] = gs[j] = 0.f; }
+    }
+    float acc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    for (long long m = blockIdx.x * 16LL + rl; m < M; m += gridDim.x * 16LL) {
+        const float x = __ldg(p + m * 3), y = __ldg(p + m * 3 + 1), z = __ldg(p + m * 3 + 2);
+        float d[8];
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(dz + m * 128 + c0)), d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float h = fmaf(w[j][2], z, fmaf(w[j][1], y, fmaf(w[j][0], x, bb[j])));
+            const float xh = (h - mu[j]) * rs[j];
+            if (PASS == 0) {
+                acc[j][0] += d[j];
+                acc[j][1] = fmaf(d[j], xh, acc[j][1]);
+            } else {
+                const float dh = gs[j] * (d[j] - k1[j] - xh * k2[j]);
+                acc[j][0] = fmaf(dh, x, acc[j][0]);
+                acc[j][1] = fmaf(dh, y, acc[j][1]);
+                acc[j][2] = fmaf(dh, z, acc[j][2]);
+                acc[j][3] += dh;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sm[rl][q][c0 + j] = acc[j][q];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * 128; i += 256) {
+        const int q = i / 128, c = i % 128;
+        float t = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) t += sm[r][q][c];
+        if (PASS == 0) {
+            if (q == 0) atomicAdd(s1 + c, t);
+            else if (q == 1) atomicAdd(s2 + c, t);
+        } else {
+            if (q < 3) atomicAdd(dW + c * 3 + q, t);
+            else atomicAdd(db + c, t);
+        }
+    }
+}
+
+static inline int grid_for(long long work_items, int per_cta) {
+    long long g = (work_items + per_cta - 1) / per_cta;
+    const long long cap = 148LL * 8;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace act
+
+extern "C" int act_pn_moments(const float *points, long long M, double *out9, void *stream) {
+    using namespace act;
+    if (!points || !out9 || M <= 0) return ACT_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    ACT_CUDA(cudaMemsetAsync(out9, 0, 9 * sizeof(double), st));
+    pn_moments_kernel<<<grid_for(M, 256 * 8), 256, 0, st>>>(points, M, out9);
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}
+
+extern "C" int act_pn_conv1(const float *points, const float *W, const float *b, long long M, int relu, void *out_bf16,
+                            void *stream) {
+    using namespace act;
+    if (!points || !W || !b || !out_bf16 || M <= 0) return ACT_EINVAL;
+    pn_conv1_kernel<<<grid_for(M, 16 * 8), 256, 0, (cudaStream_t)stream>>>(points, W, b, M, relu,
+                                                                          reinterpret_cast<__nv_bfloat16 *>(out_bf16));
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}
+
+extern "C" int act_group_max(const void *x_bf16, int G, int k, int C, void *out_bf16, float *out_f32, uint8_t *arg,
+                             void *stream) {
+    using namespace act;
+    if (!x_bf16 || G <= 0 || k <= 0 || k > 255 || C <= 0) return ACT_EINVAL;
+    if (C % 8) return ACT_EUNSUPPORTED;
+    group_max_kernel<<<grid_for((long long)G * C / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16 *>(x_bf16), G, k, C, reinterpret_cast<__nv_bfloat16 *>(out_bf16), out_f32,
+        arg);
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}
+
+extern "C" int act_group_max_bwd(const float *dout, const uint8_t *arg, int G, int k, int C, int accumulate,
+                                 void *dF_bf16, void *stream) {
+    using namespace act;
+    if (!dout || !arg || !dF_bf16 || G <= 0 || k <= 0 || C <= 0) return ACT_EINVAL;
+    if (C % 8) return ACT_EUNSUPPORTED;
+    group_max_bwd_kernel<<<grid_for((long long)G * C / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+        dout, arg, G, k, C, accumulate, reinterpret_cast<__nv_bfloat16 *>(dF_bf16));
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}
+
+extern "C" int act_group_sum(const void *x_bf16, int G, int k, int C, void *out_bf16, float *out_f32, void *stream) {
+    using namespace act;
+    if (!x_bf16 || G <= 0 || k <= 0 || C <= 0) return ACT_EINVAL;
+    if (C % 8) return ACT_EUNSUPPORTED;
+    group_sum_kernel<<<grid_for((long long)G * C / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16 *>(x_bf16), G, k, C, reinterpret_cast<__nv_bfloat16 *>(out_bf16), out_f32);
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}
+
+static int chan_reduce(int mode, const void *a, const void *x, const float *mean, const float *rstd, long long M, int C,
+                       float *s1, float *s2, cudaStream_t st) {
+    using namespace act;
+    if (!a || !s1 || !s2 || M <= 0 || C <= 0) return ACT_EINVAL;
+    if (C % 8 || C / 8 > 256) return ACT_EUNSUPPORTED;
+    ACT_CUDA(cudaMemsetAsync(s1, 0, C * sizeof(float), st));
+    ACT_CUDA(cudaMemsetAsync(s2, 0, C * sizeof(float), st));
+    const int rpc = 256 / (C / 8);
+    const size_t smem = (size_t)rpc * 2 * C * sizeof(float);
+    const int grid = grid_for(M, rpc * 32);
+    const __nv_bfloat16 *ap = reinterpret_cast<const __nv_bfloat16 *>(a), *xp = reinterpret_cast<const __nv_bfloat16 *>(x);
+    if (mode == 0) chan_reduce_kernel<0><<<grid, 256, smem, st>>>(ap, xp, mean, rstd, M, C, s1, s2);
+    else chan_reduce_kernel<1><<<grid, 256, smem, st>>>(ap, xp, mean, rstd, M, C, s1, s2);
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}
+
+extern "C" int act_bn_stats(const void *x_bf16, long long M, int C, float *sum, float *sumsq, void *stream) {
+    return chan_reduce(0, x_bf16, nullptr, nullptr, nullptr, M, C, sum, sumsq, (cudaStream_t)stream);
+}
+
+extern "C" int act_bn_bwd_stats(const void *dz_bf16, const void *x_bf16, const float *mean, const float *rstd,
+                                long long M, int C, float *sum_dz, float *sum_dz_xhat, void *stream) {
+    if (!x_bf16 || !mean || !rstd) return ACT_EINVAL;
+    return chan_reduce(1, dz_bf16, x_bf16, mean, rstd, M, C, sum_dz, sum_dz_xhat, (cudaStream_t)stream);
+}
+
+extern "C" int act_bn_apply(const void *x_bf16, const float *scale, const float *shift, long long M, int C, int relu,
+                            void *y_bf16, void *stream) {
+    using namespace act;
+    if (!x_bf16 || !scale || !shift || !y_bf16 || M <= 0 || C <= 0) return ACT_EINVAL;
+    if (C % 8) return ACT_EUNSUPPORTED;
+    const long long nvec = M * C / 8;
+    bn_apply_kernel<<<grid_for(nvec, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16 *>(x_bf16), scale, shift, nvec, C, relu,
+        reinterpret_cast<__nv_bfloat16 *>(y_bf16));
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}
+
+extern "C" int act_bn_bwd_apply(const void *dz_bf16, const void *x_bf16, const float *mean, const float *rstd,
+                                const float *gamma, const float *sum_dz, const float *sum_dz_xhat, long long M, int C,
+                                void *dh_bf16, void *stream) {
+    using namespace act;
+    if (!dz_bf16 || !x_bf16 || !mean || !rstd || !gamma || !sum_dz || !sum_dz_xhat || !dh_bf16 || M <= 0 || C <= 0)
+        return ACT_EINVAL;
+    if (C % 8) return ACT_EUNSUPPORTED;
+    bn_bwd_apply_kernel<<<grid_for(M * C / 8, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16 *>(dz_bf16), reinterpret_cast<const __nv_bfloat16 *>(x_bf16), mean, rstd,
+        gamma, sum_dz, sum_dz_xhat, M, C, reinterpret_cast<__nv_bfloat16 *>(dh_bf16));
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}
+
+extern "C" int act_pn_conv1_bwd(const void *dz_bf16, const float *points, const float *W, const float *b,
+                                const float *mean, const float *rstd, const float *gamma, long long M, float *s1,
+                                float *s2, float *dW, float *db, void *stream) {
+    using namespace act;
+    if (!dz_bf16 || !points || !W || !b || !mean || !rstd || !gamma || !s1 || !s2 || !dW || !db || M <= 0)
+        return ACT_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    ACT_CUDA(cudaMemsetAsync(s1, 0, 128 * sizeof(float), st));
+    ACT_CUDA(cudaMemsetAsync(s2, 0, 128 * sizeof(float), st));
+    const __nv_bfloat16 *dz = reinterpret_cast<const __nv_bfloat16 *>(dz_bf16);
+    const int grid = grid_for(M, 16 * 32);
+    pn_conv1_bwd_kernel<0><<<grid, 256, 0, st>>>(dz, points, W, b, mean, rstd, gamma, s1, s2, M, dW, db);
+    pn_conv1_bwd_kernel<1><<<grid, 256, 0, st>>>(dz, points, W, b, mean, rstd, gamma, s1, s2, M, dW, db);
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}

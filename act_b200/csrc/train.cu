@@ -1,0 +1,129 @@
+// Loss and optimizer kernels of the Stage-II step for sm_100a.
+//
+//  * cosine distillation loss, forward + gradient in one pass -- replaces the 128-iteration Python loop of
+//    /root/reference/models/act.py:1243-1254 (NegativeCosineSimilarity = -cosine_similarity(x0,x1,dim=1,
+//    eps=1e-8).mean(), lightly 1.2.28):  loss = (1/B) sum_b (1 - mean_tok cos(student, teacher)).
+//  * AdamW over the FLAT parameter / gradient / moment buffers (torch.optim.AdamW semantics, as built by
+//    /root/reference/tools/builder.py:37-55: decay group + no-decay group), fused with the refresh of the bf16
+//    shadow weights the tensor-core GEMMs read -- one launch per step instead of a multi-tensor foreach.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace act {
+
+__device__ __forceinline__ float warp_sum_t(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// one warp per token row; C % 128 == 0
+__global__ void __launch_bounds__(256) cosine_loss_kernel(const float *__restrict__ s, const float *__restrict__ t,
+                                                          int R, int C, float eps, float *__restrict__ loss,
+                                                          float *__restrict__ grad_s) {
+    const int lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= R) return;
+    const float4 *sp = reinterpret_cast<const float4 *>(s + (size_t)row * C);
+    const float4 *tp = reinterpret_cast<const float4 *>(t + (size_t)row * C);
+    float dot = 0.f, ns = 0.f, nt = 0.f;
+    for (int i = lane; i < C / 4; i += 32) {
+        const float4 a = __ldg(sp + i), b = __ldg(tp + i);
+        dot += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+        ns += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+        nt += b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+    }
+    dot = warp_sum_t(dot); ns = warp_sum_t(ns); nt = warp_sum_t(nt);
+    const float n1 = fmaxf(sqrtf(ns), eps), n2 = fmaxf(sqrtf(nt), eps);
+    const float cosv = dot / (n1 * n2);
+    const float invR = 1.f / (float)R;
+    if (lane == 0) atomicAdd(loss, (1.f - cosv) * invR);
+    if (grad_s) {
+        // d(1-cos)/ds = -(t/(|s||t|) - cos * s/|s|^2)
+        const float a = -invR / (n1 * n2), b = invR * cosv / (n1 * n1);
+        float4 *gp = reinterpret_cast<float4 *>(grad_s + (size_t)row * C);
+        for (int i = lane; i < C / 4; i += 32) {
+            const float4 sv = __ldg(sp + i), tv = __ldg(tp + i);
+            gp[i] = make_float4(a * tv.x + b * sv.x, a * tv.y + b * sv.y, a * tv.z + b * sv.z, a * tv.w + b * sv.w);
+        }
+    }
+}
+
+// hp[0..7] = lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, grad_scale  (device memory, so a
+// captured CUDA graph sees the scheduler's new values on every replay)
+__global__ void __launch_bounds__(256) adamw_kernel(float *__restrict__ p, const float *__restrict__ g,
+                                                    float *__restrict__ m, float *__restrict__ v,
+                                                    __nv_bfloat16 *__restrict__ shadow, long long n,
+                                                    long long n_decay, const float *__restrict__ hp) {
+    const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], wd = hp[4], bc1 = hp[5], bc2 = hp[6], gs = hp[7];
+    const float step = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+    for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < n;
+         i += (long long)gridDim.x * blockDim.x * 4) {
+        if (i + 4 <= n) {
+            float4 pv = *reinterpret_cast<float4 *>(p + i);
+            const float4 gv = *reinterpret_cast<const float4 *>(g + i);
+            float4 mv = *reinterpret_cast<float4 *>(m + i), vv = *reinterpret_cast<float4 *>(v + i);
+            float *pp = &pv.x, *mp = &mv.x, *vp = &vv.x;
+            const float *gp = &gv.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float gr = gp[k] * gs;
+                if (i + k < n_decay) pp[k] *= 1.f - lr * wd;
+                mp[k] = b1 * mp[k] + (1.f - b1) * gr;
+                vp[k] = b2 * vp[k] + (1.f - b2) * gr * gr;
+                pp[k] -= step * mp[k] / (sqrtf(vp[k]) * inv_sqrt_bc2 + eps);
+            }
+            *reinterpret_cast<float4 *>(p + i) = pv;
+            *reinterpret_cast<float4 *>(m + i) = mv;
+            *reinterpret_cast<float4 *>(v + i) = vv;
+            if (shadow) {
+                uint2 pk;
+                *reinterpret_cast<__nv_bfloat162 *>(&pk.x) = __floats2bfloat162_rn(pv.x, pv.y);
+                *reinterpret_cast<__nv_bfloat162 *>(&pk.y) = __floats2bfloat162_rn(pv.z, pv.w);
+                *reinterpret_cast<uint2 *>(shadow + i) = pk;
+            }
+        } else {
+            for (long long k = i; k < n; ++k) {
+                const float gr = g[k] * gs;
+                float pk = p[k];
+                if (k < n_decay) pk *= 1.f - lr * wd;
+                const float mk = b1 * m[k] + (1.f - b1) * gr, vk = b2 * v[k] + (1.f - b2) * gr * gr;
+                pk -= step * mk / (sqrtf(vk) * inv_sqrt_bc2 + eps);
+                p[k] = pk; m[k] = mk; v[k] = vk;
+                if (shadow) shadow[k] = __float2bfloat16_rn(pk);
+            }
+        }
+    }
+}
+
+}  // namespace act
+
+extern "C" int act_cosine_loss(const float *student, const float *teacher, int R, int C, float eps, float *loss,
+                               float *grad_student, void *stream) {
+    using namespace act;
+    if (!student || !teacher || !loss || R <= 0 || C <= 0) return ACT_EINVAL;
+    if (C % 4) return ACT_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    ACT_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+    cosine_loss_kernel<<<(R + 7) / 8, 256, 0, st>>>(student, teacher, R, C, eps, loss, grad_student);
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}
+
+extern "C" int act_adamw(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, void *shadow_bf16,
+                         long long n, long long n_decay, const float *hyper, void *stream) {
+    using namespace act;
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !hyper || n < 0) return ACT_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(exp_avg) |
+         reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15)
+        return ACT_EALIGN;
+    if (n_decay % 4) return ACT_EALIGN;
+    if (n == 0) return ACT_OK;
+    long long blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    adamw_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq,
+                                                                reinterpret_cast<__nv_bfloat16 *>(shadow_bf16), n,
+                                                                n_decay, hyper);
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}

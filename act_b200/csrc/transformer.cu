@@ -1,0 +1,599 @@
+// Non-GEMM pieces of the point-Transformer Block for sm_100a: LayerNorm (with the "+pos" of
+// TransformerEncoder.forward fused in), small-sequence multi-head attention, bias-gradient column sums.
+//
+// Reference: /root/reference/models/act.py:45-69 (Attention), :72-90 (Block), :109-112 (x = block(x + pos)),
+// nn.LayerNorm eps 1e-5.  The reference runs each of these as 4-15 separate ATen kernels per block with the
+// [B,H,T,T] score matrix and several permute/contiguous copies in HBM; here LayerNorm reads the fp32 residual
+// stream once and emits the bf16 GEMM operand, and attention keeps scores in registers (online softmax,
+// exp2 with a pre-scaled exponent) -- T is 27 / 64 tokens, so tensor cores would idle on 128-row tiles;
+// the attention FLOPs are <5% of the block and run on the FMA pipes with K/V staged in shared memory.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace act {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------ LayerNorm forward
+// One warp per row; VPL float4 per lane (C = 128 * VPL).  If pos != null: xs = x + pos is normalised and
+// also written to xsum_out (the block's residual input).  out is bf16 (GEMM operand) or fp32.
+template <int VPL>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float *__restrict__ x, const float *__restrict__ pos,
+                                                            const float *__restrict__ gamma,
+                                                            const float *__restrict__ beta, float eps, int M,
+                                                            float *__restrict__ xsum_out, void *__restrict__ out,
+                                                            int out_fp32, float *__restrict__ mean_out,
+                                                            float *__restrict__ rstd_out) {
+    constexpr int C = 128 * VPL;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)row * C);
+    float4 v[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        v[i] = xr[lane + 32 * i];
+        if (pos) {
+            const float4 p = __ldg(reinterpret_cast<const float4 *>(pos + (size_t)row * C) + lane + 32 * i);
+            v[i].x += p.x; v[i].y += p.y; v[i].z += p.z; v[i].w += p.w;
+        }
+        s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+    if (xsum_out) {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) reinterpret_cast<float4 *>(xsum_out + (size_t)row * C)[lane + 32 * i] = v[i];
+    }
+    const float mean = warp_sum(s) * (1.f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += a * a + b * b + c * c + d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+    if (lane == 0) {
+        if (mean_out) mean_out[row] = mean;
+        if (rstd_out) rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma) + lane + 32 * i);
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(beta) + lane + 32 * i);
+        float4 y;
+        y.x = (v[i].x - mean) * rstd * g.x + b.x;
+        y.y = (v[i].y - mean) * rstd * g.y + b.y;
+        y.z = (v[i].z - mean) * rstd * g.z + b.z;
+        y.w = (v[i].w - mean) * rstd * g.w + b.w;
+        if (out_fp32) {
+            reinterpret_cast<float4 *>(reinterpret_cast<float *>(out) + (size_t)row * C)[lane + 32 * i] = y;
+        } else {
+            uint2 pk;
+            *reinterpret_cast<__nv_bfloat162 *>(&pk.x) = __floats2bfloat162_rn(y.x, y.y);
+            *reinterpret_cast<__nv_bfloat162 *>(&pk.y) = __floats2bfloat162_rn(y.z, y.w);
+            reinterpret_cast<uint2 *>(reinterpret_cast<__nv_bfloat16 *>(out) + (size_t)row * C)[lane + 32 * i] = pk;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------- LayerNorm backward
+// dx_out = dres + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  dgamma += sum dy*xhat,
+// dbeta += sum dy (register partials per lane over the rows a warp visits, smem across warps, one atomic
+// per column per CTA).
+template <int VPL>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void *__restrict__ dy, int dy_fp32,
+                                                            const float *__restrict__ x,
+                                                            const float *__restrict__ mean,
+                                                            const float *__restrict__ rstd,
+                                                            const float *__restrict__ gamma,
+                                                            const float *__restrict__ dres, int M,
+                                                            float *__restrict__ dx_out, float *__restrict__ dgamma,
+                                                            float *__restrict__ dbeta, float *__restrict__ dacc,
+                                                            __nv_bfloat16 *__restrict__ g_bf16,
+                                                            const float *__restrict__ row_scale, int rows_per_scale,
+                                                            float *__restrict__ dbias) {
+    constexpr int C = 128 * VPL;
+    __shared__ float s_part[8][C];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 ag[VPL], ab[VPL], ac[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) ag[i] = ab[i] = ac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 gm[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) gm[i] = __ldg(reinterpret_cast<const float4 *>(gamma) + lane + 32 * i);
+
+    for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
+        const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+        float4 xh[VPL], d[VPL];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const float4 xv = __ldg(reinterpret_cast<const float4 *>(x + (size_t)row * C) + lane + 32 * i);
+            if (dy_fp32) {
+                d[i] = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(dy) + (size_t)row * C) +
+                             lane + 32 * i);
+            } else {
+                const uint2 pk = __ldg(reinterpret_cast<const uint2 *>(
+                                           reinterpret_cast<const __nv_bfloat16 *>(dy) + (size_t)row * C) +
+                                       lane + 32 * i);
+                const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&pk.x));
+                const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&pk.y));
+                d[i] = make_float4(a.x, a.y, b.x, b.y);
+            }
+            xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+            ag[i].x += d[i].x * xh[i].x; ag[i].y += d[i].y * xh[i].y; ag[i].z += d[i].z * xh[i].z; ag[i].w += d[i].w * xh[i].w;
+            ab[i].x += d[i].x; ab[i].y += d[i].y; ab[i].z += d[i].z; ab[i].w += d[i].w;
+            d[i].x *= gm[i].x; d[i].y *= gm[i].y; d[i].z *= gm[i].z; d[i].w *= gm[i].w;
+            s1 += d[i].x + d[i].y + d[i].z + d[i].w;
+            s2 += d[i].x * xh[i].x + d[i].y * xh[i].y + d[i].z * xh[i].z + d[i].w * xh[i].w;
+        }
+        const float m1 = warp_sum(s1) * (1.f / C), m2 = warp_sum(s2) * (1.f / C);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            float4 o;
+            o.x = rs * (d[i].x - m1 - xh[i].x * m2);
+            o.y = rs * (d[i].y - m1 - xh[i].y * m2);
+            o.z = rs * (d[i].z - m1 - xh[i].z * m2);
+            o.w = rs * (d[i].w - m1 - xh[i].w * m2);
+            if (dres) {
+                const float4 r = __ldg(reinterpret_cast<const float4 *>(dres + (size_t)row * C) + lane + 32 * i);
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            }
+            reinterpret_cast<float4 *>(dx_out + (size_t)row * C)[lane + 32 * i] = o;
+            if (dacc) {
+                float4 *ap = reinterpret_cast<float4 *>(dacc + (size_t)row * C) + lane + 32 * i;
+                float4 a = *ap;
+                a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+                *ap = a;
+            }
+            if (g_bf16 || dbias) {
+                const float sc = row_scale ? __ldg(row_scale + row / rows_per_scale) : 1.f;
+                o.x *= sc; o.y *= sc; o.z *= sc; o.w *= sc;
+                ac[i].x += o.x; ac[i].y += o.y; ac[i].z += o.z; ac[i].w += o.w;
+                if (g_bf16) {
+                    uint2 pk;
+                    *reinterpret_cast<__nv_bfloat162 *>(&pk.x) = __floats2bfloat162_rn(o.x, o.y);
+                    *reinterpret_cast<__nv_bfloat162 *>(&pk.y) = __floats2bfloat162_rn(o.z, o.w);
+                    reinterpret_cast<uint2 *>(g_bf16 + (size_t)row * C)[lane + 32 * i] = pk;
+                }
+            }
+        }
+    }
+    // reduce dgamma / dbeta / dbias partials across the CTA's 8 warps
+    for (int pass = 0; pass < 3; ++pass) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+            reinterpret_cast<float4 *>(s_part[warp])[lane + 32 * i] = pass == 0 ? ag[i] : (pass == 1 ? ab[i] : ac[i]);
+        __syncthreads();
+        float *dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dbias);
+        if (dst) {
+            for (int c = threadIdx.x; c < C; c += 256) {
+                float t = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) t += s_part[w][c];
+                atomicAdd(dst + c, t);
+            }
+        }
+    }
+}
+
+// bf16(x * row_scale) + column sums: the first dY of a Block backward when the incoming grad is fp32.
+template <int VPL>
+__global__ void __launch_bounds__(256) cast_rows_kernel(const float *__restrict__ x, int M,
+                                                        const float *__restrict__ row_scale, int rows_per_scale,
+                                                        __nv_bfloat16 *__restrict__ g_bf16, float *__restrict__ dbias) {
+    constexpr int C = 128 * VPL;
+    __shared__ float s_part[8][C];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 ac[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) ac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
+        const float sc = row_scale ? __ldg(row_scale + row / rows_per_scale) : 1.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            float4 o = __ldg(reinterpret_cast<const float4 *>(x + (size_t)row * C) + lane + 32 * i);
+            o.x *= sc; o.y *= sc; o.z *= sc; o.w *= sc;
+            ac[i].x += o.x; ac[i].y += o.y; ac[i].z += o.z; ac[i].w += o.w;
+            uint2 pk;
+            *reinterpret_cast<__nv_bfloat162 *>(&pk.x) = __floats2bfloat162_rn(o.x, o.y);
+            *reinterpret_cast<__nv_bfloat162 *>(&pk.y) = __floats2bfloat162_rn(o.z, o.w);
+            reinterpret_cast<uint2 *>(g_bf16 + (size_t)row * C)[lane + 32 * i] = pk;
+        }
+    }
+    if (dbias) {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) reinterpret_cast<float4 *>(s_part[warp])[lane + 32 * i] = ac[i];
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += 256) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += s_part[w][c];
+            atomicAdd(dbias + c, t);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- attention
+// qkv: bf16 [B*T, 3*H*64] (q | k | v, head-major inside each third, as nn.Linear(dim, 3*dim) + the
+// reference's reshape(B,N,3,H,C/H) lays it out).  Two lanes own one query row (32 of the 64 head dims each).
+constexpr int AT_D = 64;
+constexpr int AT_TILE = 64;   // keys per shared-memory tile
+
+__device__ __forceinline__ void load_row32(const __nv_bfloat16 *src, float (&dst)[32]) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(src);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint4 u = __ldg(p + i);
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 f = __bfloat1622float2(h[t]);
+            dst[i * 8 + 2 * t] = f.x;
+            dst[i * 8 + 2 * t + 1] = f.y;
+        }
+    }
+}
+__device__ __forceinline__ void lds_row32(const __nv_bfloat16 *src, float (&dst)[32]) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(src);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint4 u = p[i];
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float2 f = __bfloat1622float2(h[t]);
+            dst[i * 8 + 2 * t] = f.x;
+            dst[i * 8 + 2 * t + 1] = f.y;
+        }
+    }
+}
+__device__ __forceinline__ void store_row32(__nv_bfloat16 *dst, const float (&src)[32]) {
+    uint4 *p = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&u);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(src[i * 8 + 2 * t], src[i * 8 + 2 * t + 1]);
+        p[i] = u;
+    }
+}
+// cooperative copy of `rows` rows x 64 bf16 (128 B each) from a strided global matrix into smem [rows][64]
+__device__ __forceinline__ void stage_rows(__nv_bfloat16 *dst, const __nv_bfloat16 *src, int ld, int rows) {
+    for (int i = threadIdx.x; i < rows * 8; i += blockDim.x) {
+        const int r = i >> 3, c = i & 7;
+        reinterpret_cast<uint4 *>(dst)[i] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * ld) + c);
+    }
+}
+
+// forward: o[b*T+i, h*64 + :] = softmax(q k^T * scale) v ; lse[b,h,i] = log-sum-exp of the scaled scores.
+template <int QT>
+__global__ void __launch_bounds__(QT * 2) attention_fwd_kernel(const __nv_bfloat16 *__restrict__ qkv, int T, int H,
+                                                               float scale, __nv_bfloat16 *__restrict__ o,
+                                                               float *__restrict__ lse) {
+    __shared__ __align__(16) __nv_bfloat16 s_k[AT_TILE][AT_D], s_v[AT_TILE][AT_D];
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int i = blockIdx.x * QT + (threadIdx.x >> 1), half = threadIdx.x & 1;
+    const int ld = 3 * H * AT_D;
+    const __nv_bfloat16 *base = qkv + (size_t)b * T * ld + h * AT_D;
+    const bool act_q = i < T;
+    float q[32], acc[32];
+    const float sl2 = scale * 1.4426950408889634f;
+    if (act_q) {
+        load_row32(base + (size_t)i * ld + half * 32, q);
+#pragma unroll
+        for (int d = 0; d < 32; ++d) q[d] *= sl2;
+    } else {
+#pragma unroll
+        for (int d = 0; d < 32; ++d) q[d] = 0.f;
+    }
+#pragma unroll
+    for (int d = 0; d < 32; ++d) acc[d] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    for (int j0 = 0; j0 < T; j0 += AT_TILE) {
+        const int rows = min(AT_TILE, T - j0);
+        __syncthreads();
+        stage_rows(&s_k[0][0], base + (size_t)j0 * ld + H * AT_D, ld, rows);
+        stage_rows(&s_v[0][0], base + (size_t)j0 * ld + 2 * H * AT_D, ld, rows);
+        __syncthreads();
+        for (int j = 0; j < rows; ++j) {
+            float kv[32];
+            lds_row32(&s_k[j][half * 32], kv);
+            float s = 0.f;
+#pragma unroll
+            for (int d = 0; d < 32; ++d) s = fmaf(q[d], kv[d], s);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            const float mn = fmaxf(m, s);
+            const float corr = exp2f(m - mn), p = exp2f(s - mn);
+            m = mn;
+            l = l * corr + p;
+            lds_row32(&s_v[j][half * 32], kv);
+#pragma unroll
+            for (int d = 0; d < 32; ++d) acc[d] = fmaf(acc[d], corr, p * kv[d]);
+        }
+    }
+    if (act_q) {
+        const float inv = 1.f / l;
+#pragma unroll
+        for (int d = 0; d < 32; ++d) acc[d] *= inv;
+        store_row32(o + ((size_t)b * T + i) * (H * AT_D) + h * AT_D + half * 32, acc);
+        if (half == 0 && lse) lse[((size_t)b * H + h) * T + i] = (m + log2f(l)) * 0.6931471805599453f;
+    }
+}
+
+// backward, query side: dq_i = scale * sum_j ds_ij k_j,  ds_ij = p_ij (dO_i . v_j - D_i),  D_i = dO_i . o_i.
+template <int QT>
+__global__ void __launch_bounds__(QT * 2) attention_bwd_dq_kernel(const __nv_bfloat16 *__restrict__ qkv,
+                                                                  const __nv_bfloat16 *__restrict__ o,
+                                                                  const __nv_bfloat16 *__restrict__ dO,
+                                                                  const float *__restrict__ lse, int T, int H,
+                                                                  float scale, __nv_bfloat16 *__restrict__ dqkv,
+                                                                  float *__restrict__ delta) {
+    __shared__ __align__(16) __nv_bfloat16 s_k[AT_TILE][AT_D], s_v[AT_TILE][AT_D];
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int i = blockIdx.x * QT + (threadIdx.x >> 1), half = threadIdx.x & 1;
+    const int ld = 3 * H * AT_D, ldo = H * AT_D;
+    const __nv_bfloat16 *base = qkv + (size_t)b * T * ld + h * AT_D;
+    const bool act_q = i < T;
+    float q[32], g[32], dq[32];
+    float D = 0.f, L = 0.f;
+    if (act_q) {
+        load_row32(base + (size_t)i * ld + half * 32, q);
+        load_row32(dO + ((size_t)b * T + i) * ldo + h * AT_D + half * 32, g);
+        float ov[32];
+        load_row32(o + ((size_t)b * T + i) * ldo + h * AT_D + half * 32, ov);
+#pragma unroll
+        for (int d = 0; d < 32; ++d) D = fmaf(g[d], ov[d], D);
+        L = __ldg(lse + ((size_t)b * H + h) * T + i);
+    } else {
+#pragma unroll
+        for (int d = 0; d < 32; ++d) q[d] = g[d] = 0.f;
+    }
+    D += __shfl_xor_sync(0xffffffffu, D, 1);
+    if (act_q && half == 0) delta[((size_t)b * H + h) * T + i] = D;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) dq[d] = 0.f;
+    for (int j0 = 0; j0 < T; j0 += AT_TILE) {
+        const int rows = min(AT_TILE, T - j0);
+        __syncthreads();
+        stage_rows(&s_k[0][0], base + (size_t)j0 * ld + H * AT_D, ld, rows);
+        stage_rows(&s_v[0][0], base + (size_t)j0 * ld + 2 * H * AT_D, ld, rows);
+        __syncthreads();
+        for (int j = 0; j < rows; ++j) {
+            float kr[32], vr[32];
+            lds_row32(&s_k[j][half * 32], kr);
+            lds_row32(&s_v[j][half * 32], vr);
+            float s = 0.f, dp = 0.f;
+#pragma unroll
+            for (int d = 0; d < 32; ++d) {
+                s = fmaf(q[d], kr[d], s);
+                dp = fmaf(g[d], vr[d], dp);
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            dp += __shfl_xor_sync(0xffffffffu, dp, 1);
+            const float p = __expf(s * scale - L);
+            const float ds = p * (dp - D) * scale;
+#pragma unroll
+            for (int d = 0; d < 32; ++d) dq[d] = fmaf(ds, kr[d], dq[d]);
+        }
+    }
+    if (act_q) store_row32(dqkv + ((size_t)b * T + i) * ld + h * AT_D + half * 32, dq);
+}
+
+// backward, key side: dv_j = sum_i p_ij dO_i,  dk_j = scale * sum_i ds_ij q_i  (p recomputed from lse).
+template <int QT>
+__global__ void __launch_bounds__(QT * 2) attention_bwd_dkv_kernel(const __nv_bfloat16 *__restrict__ qkv,
+                                                                   const __nv_bfloat16 *__restrict__ dO,
+                                                                   const float *__restrict__ lse,
+                                                                   const float *__restrict__ delta, int T, int H,
+                                                                   float scale, __nv_bfloat16 *__restrict__ dqkv) {
+    __shared__ __align__(16) __nv_bfloat16 s_q[AT_TILE][AT_D], s_g[AT_TILE][AT_D];
+    __shared__ float s_l[AT_TILE], s_d[AT_TILE];
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int j = blockIdx.x * QT + (threadIdx.x >> 1), half = threadIdx.x & 1;
+    const int ld = 3 * H * AT_D, ldo = H * AT_D;
+    const __nv_bfloat16 *base = qkv + (size_t)b * T * ld + h * AT_D;
+    const bool act_k = j < T;
+    float kr[32], vr[32], dk[32], dv[32];
+    if (act_k) {
+        load_row32(base + (size_t)j * ld + H * AT_D + half * 32, kr);
+        load_row32(base + (size_t)j * ld + 2 * H * AT_D + half * 32, vr);
+    } else {
+#pragma unroll
+        for (int d = 0; d < 32; ++d) kr[d] = vr[d] = 0.f;
+    }
+#pragma unroll
+    for (int d = 0; d < 32; ++d) dk[d] = dv[d] = 0.f;
+    for (int i0 = 0; i0 < T; i0 += AT_TILE) {
+        const int rows = min(AT_TILE, T - i0);
+        __syncthreads();
+        stage_rows(&s_q[0][0], base + (size_t)i0 * ld, ld, rows);
+        stage_rows(&s_g[0][0], dO + ((size_t)b * T + i0) * ldo + h * AT_D, ldo, rows);
+        for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+            s_l[r] = __ldg(lse + ((size_t)b * H + h) * T + i0 + r);
+            s_d[r] = __ldg(delta + ((size_t)b * H + h) * T + i0 + r);
+        }
+        __syncthreads();
+        for (int i = 0; i < rows; ++i) {
+            float qr[32], gr[32];
+            lds_row32(&s_q[i][half * 32], qr);
+            lds_row32(&s_g[i][half * 32], gr);
+            float s = 0.f, dp = 0.f;
+#pragma unroll
+            for (int d = 0; d < 32; ++d) {
+                s = fmaf(qr[d], kr[d], s);
+                dp = fmaf(gr[d], vr[d], dp);
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            dp += __shfl_xor_sync(0xffffffffu, dp, 1);
+            const float p = __expf(s * scale - s_l[i]);
+            const float ds = p * (dp - s_d[i]) * scale;
+#pragma unroll
+            for (int d = 0; d < 32; ++d) {
+                dv[d] = fmaf(p, gr[d], dv[d]);
+                dk[d] = fmaf(ds, qr[d], dk[d]);
+            }
+        }
+    }
+    if (act_k) {
+        store_row32(dqkv + ((size_t)b * T + j) * ld + H * AT_D + h * AT_D + half * 32, dk);
+        store_row32(dqkv + ((size_t)b * T + j) * ld + 2 * H * AT_D + h * AT_D + half * 32, dv);
+    }
+}
+
+// ------------------------------------------------------------------------------------ column sums
+// out[n] += sum_m x[m, n]  (bias gradients).  x bf16 or fp32 [M, ld]; 32 columns x 8 row-lanes per CTA.
+__global__ void __launch_bounds__(256) colsum_kernel(const void *__restrict__ x, int x_fp32, int M, int N, int ld,
+                                                     float *__restrict__ out) {
+    __shared__ float s[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
+    float acc = 0.f;
+    if (c < N) {
+        for (int r = blockIdx.y * 8 + ry; r < M; r += gridDim.y * 8) {
+            acc += x_fp32 ? __ldg(reinterpret_cast<const float *>(x) + (size_t)r * ld + c)
+                          : __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(x)[(size_t)r * ld + c]);
+        }
+    }
+    s[ry][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (ry == 0 && c < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s[w][threadIdx.x & 31];
+        atomicAdd(out + c, t);
+    }
+}
+
+}  // namespace act
+
+extern "C" int act_layernorm_fwd(const float *x, const float *pos, const float *gamma, const float *beta, float eps,
+                                 int M, int C, float *xsum_out, void *out, int out_fp32, float *mean, float *rstd,
+                                 void *stream) {
+    using namespace act;
+    if (!x || !gamma || !beta || !out || M < 0 || C <= 0) return ACT_EINVAL;
+    if (M == 0) return ACT_OK;
+    if (C % 128 || C > 1024) return ACT_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+#define LN_CASE(V)                                                                                                   \
+    case V:                                                                                                          \
+        layernorm_fwd_kernel<V><<<(M + 7) / 8, 256, 0, st>>>(x, pos, gamma, beta, eps, M, xsum_out, out, out_fp32, mean, \
+                                                             rstd);                                                  \
+        break;
+    switch (C / 128) {
+        LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(6) LN_CASE(8)
+        default: return ACT_EUNSUPPORTED;
+    }
+#undef LN_CASE
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}
+
+extern "C" int act_layernorm_bwd(const void *dy, int dy_fp32, const float *x, const float *mean, const float *rstd,
+                                 const float *gamma, const float *dres, int M, int C, float *dx_out, float *dgamma,
+                                 float *dbeta, float *dacc, void *g_bf16, const float *row_scale, int rows_per_scale,
+                                 float *dbias, void *stream) {
+    using namespace act;
+    if (!dy || !x || !mean || !rstd || !gamma || !dx_out || M < 0 || C <= 0) return ACT_EINVAL;
+    if (M == 0) return ACT_OK;
+    if (C % 128 || C > 1024) return ACT_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (M + 7) / 8 < 148 * 2 ? (M + 7) / 8 : 148 * 2;
+#define LN_CASE(V)                                                                                                \
+    case V:                                                                                                       \
+        layernorm_bwd_kernel<V><<<grid, 256, 0, st>>>(dy, dy_fp32, x, mean, rstd, gamma, dres, M, dx_out, dgamma, \
+                                                      dbeta, dacc, reinterpret_cast<__nv_bfloat16 *>(g_bf16),     \
+                                                      row_scale, rows_per_scale > 0 ? rows_per_scale : 1, dbias); \
+        break;
+    switch (C / 128) {
+        LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(6) LN_CASE(8)
+        default: return ACT_EUNSUPPORTED;
+    }
+#undef LN_CASE
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}
+
+extern "C" int act_cast_rows(const float *x, int M, int C, const float *row_scale, int rows_per_scale, void *g_bf16,
+                             float *dbias, void *stream) {
+    using namespace act;
+    if (!x || !g_bf16 || M < 0 || C <= 0) return ACT_EINVAL;
+    if (M == 0) return ACT_OK;
+    if (C % 128 || C > 1024) return ACT_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (M + 7) / 8 < 148 * 2 ? (M + 7) / 8 : 148 * 2;
+    const int rps = rows_per_scale > 0 ? rows_per_scale : 1;
+    __nv_bfloat16 *g = reinterpret_cast<__nv_bfloat16 *>(g_bf16);
+    switch (C / 128) {
+        case 1: cast_rows_kernel<1><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, dbias); break;
+        case 2: cast_rows_kernel<2><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, dbias); break;
+        case 3: cast_rows_kernel<3><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, dbias); break;
+        case 4: cast_rows_kernel<4><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, dbias); break;
+        case 6: cast_rows_kernel<6><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, dbias); break;
+        case 8: cast_rows_kernel<8><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, dbias); break;
+        default: return ACT_EUNSUPPORTED;
+    }
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}
+
+extern "C" int act_attention_fwd(const void *qkv, int B, int T, int H, int head_dim, float scale, void *o, float *lse,
+                                 void *stream) {
+    using namespace act;
+    if (!qkv || !o || B < 0 || T <= 0 || H <= 0) return ACT_EINVAL;
+    if (head_dim != AT_D) return ACT_EUNSUPPORTED;
+    if (B == 0) return ACT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const __nv_bfloat16 *p = reinterpret_cast<const __nv_bfloat16 *>(qkv);
+    __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(o);
+    if (T <= 16) {
+        attention_fwd_kernel<16><<<dim3((T + 15) / 16, H, B), 32, 0, st>>>(p, T, H, scale, op, lse);
+    } else if (T <= 32 || (T > 64 && T <= 96)) {
+        attention_fwd_kernel<32><<<dim3((T + 31) / 32, H, B), 64, 0, st>>>(p, T, H, scale, op, lse);
+    } else {
+        attention_fwd_kernel<64><<<dim3((T + 63) / 64, H, B), 128, 0, st>>>(p, T, H, scale, op, lse);
+    }
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}
+
+extern "C" int act_attention_bwd(const void *qkv, const void *o, const void *dO, const float *lse, int B, int T, int H,
+                                 int head_dim, float scale, void *dqkv, float *delta, void *stream) {
+    using namespace act;
+    if (!qkv || !o || !dO || !lse || !dqkv || !delta || B < 0 || T <= 0 || H <= 0) return ACT_EINVAL;
+    if (head_dim != AT_D) return ACT_EUNSUPPORTED;
+    if (B == 0) return ACT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const __nv_bfloat16 *p = reinterpret_cast<const __nv_bfloat16 *>(qkv);
+    const __nv_bfloat16 *op = reinterpret_cast<const __nv_bfloat16 *>(o);
+    const __nv_bfloat16 *gp = reinterpret_cast<const __nv_bfloat16 *>(dO);
+    __nv_bfloat16 *dp = reinterpret_cast<__nv_bfloat16 *>(dqkv);
+    if (T <= 32 || (T > 64 && T <= 96)) {
+        dim3 grid((T + 31) / 32, H, B);
+        attention_bwd_dq_kernel<32><<<grid, 64, 0, st>>>(p, op, gp, lse, T, H, scale, dp, delta);
+        attention_bwd_dkv_kernel<32><<<grid, 64, 0, st>>>(p, gp, lse, delta, T, H, scale, dp);
+    } else {
+        dim3 grid((T + 63) / 64, H, B);
+        attention_bwd_dq_kernel<64><<<grid, 128, 0, st>>>(p, op, gp, lse, T, H, scale, dp, delta);
+        attention_bwd_dkv_kernel<64><<<grid, 128, 0, st>>>(p, gp, lse, delta, T, H, scale, dp);
+    }
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}
+
+extern "C" int act_colsum(const void *x, int x_fp32, int M, int N, int ld, float *out, void *stream) {
+    using namespace act;
+    if (!x || !out || M < 0 || N <= 0) return ACT_EINVAL;
+    if (M == 0) return ACT_OK;
+    int gy = (M + 63) / 64;
+    if (gy > 128) gy = 128;
+    colsum_kernel<<<dim3((N + 31) / 32, gy), 256, 0, (cudaStream_t)stream>>>(x, x_fp32, M, N, ld, out);
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}

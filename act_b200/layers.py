@@ -1,0 +1,415 @@
+"""Autograd glue between the reference's nn.Module surface and the act_b200 kernels.
+
+Each autograd.Function here is one FUSED region of the ACT step, forward and hand-written backward, made
+only of libact_b200 launches (ops.py) plus O(channels) host-side tensor arithmetic:
+
+  TransformerStack  -- N pre-LN Blocks, `x = block(x + pos)`           (models/act.py:72-112, 140-142)
+  LayerNormFn       -- the trailing nn.LayerNorm of encoder / decoder   (act.py:301, 144)
+  LinearFn          -- nn.Linear (+GELU) on the tcgen05 GEMM           (pos_embed[2], proj_head, reduce_dim)
+  PointNetEncoderFn -- the per-group mini-PointNet `Encoder`            (models/dvae.py:185-215)
+  CosineLossFn      -- the distillation loss                            (act.py:1243-1254)
+
+Parameters stay fp32 nn.Parameters (state_dict compatible with the reference).  When a module has been
+adopted by `FlatParams`, every parameter is a view into one flat fp32 buffer, carries `_act_shadow` (its
+bf16 copy inside one flat bf16 buffer, refreshed by the fused AdamW kernel) and `_act_grad` (its slice of one
+flat fp32 gradient buffer): weight-gradient GEMMs then accumulate straight into that slice and the Functions
+return None for those inputs.  Without FlatParams the Functions cast weights on the fly and return gradients
+the normal autograd way, so the modules also work inside a stock PyTorch training loop / DDP.
+"""
+import math
+
+import torch
+
+from . import ops
+
+
+def shadow(p):
+    s = getattr(p, "_act_shadow", None)
+    return s if s is not None else p.detach().to(torch.bfloat16)
+
+
+class _GradSink:
+    """Hands out accumulation targets for parameter gradients: the flat-buffer slice when there is one
+    (result: None returned to autograd), else a fresh zero tensor (returned to autograd)."""
+
+    def __init__(self):
+        self.ret = {}
+
+    def get(self, p, key):
+        g = getattr(p, "_act_grad", None)
+        if g is not None:
+            self.ret[key] = None
+            return g
+        g = torch.zeros_like(p, dtype=torch.float32)
+        self.ret[key] = g
+        return g
+
+    def result(self, key):
+        return self.ret.get(key)
+
+
+class FlatParams:
+    """Re-homes a module's trainable parameters into flat buffers: fp32 master `flat`, fp32 `grad`, bf16
+    `shadow`, AdamW moments.  Decay group first, no-decay group after (tools/builder.py:38-51: no decay for
+    1-D tensors, `.bias`, and names containing `token`).  Each tensor is padded to a multiple of 8 elements so
+    every bf16 shadow starts 16-byte aligned (TMA requirement)."""
+
+    def __init__(self, module, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05):
+        named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+        if not named:
+            raise ValueError("no trainable parameters")
+        dev = named[0][1].device
+
+        def no_decay(n, p):
+            return p.dim() <= 1 or n.endswith(".bias") or "token" in n
+
+        order = [(n, p) for n, p in named if not no_decay(n, p)] + [(n, p) for n, p in named if no_decay(n, p)]
+        self.n_decay_params = sum(1 for n, p in named if not no_decay(n, p))
+        offs, total = [], 0
+        for i, (n, p) in enumerate(order):
+            if i == self.n_decay_params:
+                self.n_decay = total
+            offs.append(total)
+            total += (p.numel() + 7) // 8 * 8
+        if self.n_decay_params == len(order):
+            self.n_decay = total
+        self.total = total
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.shadow = torch.zeros(total, dtype=torch.bfloat16, device=dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.params, self.names = [], []
+        for (n, p), o in zip(order, offs):
+            k = p.numel()
+            self.flat[o:o + k].copy_(p.detach().reshape(-1))
+            p.data = self.flat[o:o + k].view(p.shape)
+            p.grad = self.grad[o:o + k].view(p.shape)
+            p._act_grad = p.grad
+            p._act_shadow = self.shadow[o:o + k].view(p.shape)
+            self.params.append(p)
+            self.names.append(n)
+        self.shadow.copy_(self.flat)
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.step_count = 0
+        self.hyper = torch.zeros(8, dtype=torch.float32, device=dev)
+        self._hyper_host = torch.zeros(8, dtype=torch.float32).pin_memory() if dev.type == "cuda" else None
+
+    def refresh_shadow(self):
+        """After loading a state_dict (which writes through the fp32 views)."""
+        self.shadow.copy_(self.flat)
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def set_hyper(self, grad_scale=1.0):
+        """Stage this step's AdamW scalars (lr from the scheduler, bias corrections) into device memory."""
+        self.step_count += 1
+        t = self.step_count
+        vals = [self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 - self.betas[0] ** t,
+                1.0 - self.betas[1] ** t, grad_scale]
+        self._hyper_host.copy_(torch.tensor(vals, dtype=torch.float32))
+        self.hyper.copy_(self._hyper_host, non_blocking=True)
+
+    def step(self):
+        """One fused AdamW launch over the flat buffers (hyper-parameters read from device memory)."""
+        ops.adamw(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.shadow, self.n_decay, self.hyper)
+
+
+# ------------------------------------------------------------------------------------- Transformer stack
+BLOCK_KEYS = ("norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.proj.weight", "attn.proj.bias", "norm2.weight",
+              "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias")
+NP = len(BLOCK_KEYS)
+
+
+class TransformerStack(torch.autograd.Function):
+    """y = blocks[-1](... blocks[0](x + pos) ... + pos): `depth` pre-LN Blocks with `pos` re-added before every
+    Block (models/act.py:109-112).  gates: None or f32 [2*depth, B] DropPath gates (0 or 1/keep) for the
+    attention / MLP branch of each Block (timm DropPath, act.py:88-89)."""
+
+    @staticmethod
+    def forward(ctx, x, pos, gates, num_heads, eps, *params):
+        B, T, C = x.shape
+        M = B * T
+        depth = len(params) // NP
+        scale = (C // num_heads) ** -0.5
+        need = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params) or
+                                            (pos is not None and pos.requires_grad))
+        cur = x.reshape(M, C).contiguous().float()
+        pos2 = pos.reshape(M, C).contiguous().float() if pos is not None else None
+        saved = []
+        for l in range(depth):
+            n1w, n1b, wqkv, wproj, bproj, n2w, n2b, w1, b1, w2, b2 = params[l * NP:(l + 1) * NP]
+            g1 = gates[2 * l] if gates is not None else None
+            g2 = gates[2 * l + 1] if gates is not None else None
+            h1, xs, mean1, rstd1 = ops.layernorm_fwd(cur, n1w, n1b, eps, pos=pos2)
+            if xs is None:
+                xs = cur
+            qkv = ops.gemm(h1, shadow(wqkv))
+            o, lse = ops.attention_fwd(qkv, B, T, num_heads, scale)
+            xmid = ops.gemm(o, shadow(wproj), bias=bproj, resid=xs, row_scale=g1, rows_per_scale=T,
+                            out_dtype=torch.float32)
+            h2, _, mean2, rstd2 = ops.layernorm_fwd(xmid, n2w, n2b, eps)
+            u = torch.empty(M, w1.shape[0], dtype=torch.bfloat16, device=x.device) if need else None
+            a = ops.gemm(h2, shadow(w1), bias=b1, act=ops.ACT_GELU, preact_out=u)
+            cur = ops.gemm(a, shadow(w2), bias=b2, resid=xmid, row_scale=g2, rows_per_scale=T,
+                           out_dtype=torch.float32)
+            if need:
+                saved += [xs, h1, mean1, rstd1, qkv, o, lse, xmid, h2, mean2, rstd2, u, a]
+        if need:
+            ctx.save_for_backward(*params, *saved)
+            ctx.gates = gates
+            ctx.meta = (B, T, C, depth, num_heads, scale, pos is not None)
+        return cur.view(B, T, C)
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, T, C, depth, H, scale, has_pos = ctx.meta
+        M = B * T
+        tensors = ctx.saved_tensors
+        params, saved = tensors[:depth * NP], tensors[depth * NP:]
+        gates = ctx.gates
+        sink = _GradSink()
+        dx = dy.reshape(M, C).contiguous().float()
+        dpos = torch.zeros(M, C, dtype=torch.float32, device=dy.device) if has_pos else None
+        g = None
+        NS = 13
+        for l in reversed(range(depth)):
+            n1w, n1b, wqkv, wproj, bproj, n2w, n2b, w1, b1, w2, b2 = params[l * NP:(l + 1) * NP]
+            xs, h1, mean1, rstd1, qkv, o, lse, xmid, h2, mean2, rstd2, u, a = saved[l * NS:(l + 1) * NS]
+            gate1 = gates[2 * l] if gates is not None else None
+            gate2 = gates[2 * l + 1] if gates is not None else None
+            G = lambda p, k: sink.get(p, (l, k))  # noqa: E731
+            if g is None:       # top of the stack: the incoming gradient is plain fp32
+                g = ops.cast_rows(dx, gate2, T, dbias=G(b2, 10))
+            # MLP branch
+            ops.wgrad(g, a, G(w2, 9))
+            du = ops.gemm(g, shadow(w2), b_mn=True, mul_in=u, mul_mode=ops.MUL_GELU_GRAD)
+            ops.wgrad(du, h2, G(w1, 7))
+            ops.colsum(du, G(b1, 8))
+            dh2 = ops.gemm(du, shadow(w1), b_mn=True)
+            dxm, g2 = ops.layernorm_bwd(dh2, xmid, mean2, rstd2, n2w, G(n2w, 5), G(n2b, 6), dres=dx, want_bf16=True,
+                                        row_scale=gate1, rows_per_scale=T, dbias=G(bproj, 4))
+            # attention branch
+            ops.wgrad(g2, o, G(wproj, 3))
+            do = ops.gemm(g2, shadow(wproj), b_mn=True)
+            dqkv = ops.attention_bwd(qkv, o, do, lse, B, T, H, scale)
+            ops.wgrad(dqkv, h1, G(wqkv, 2))
+            dh1 = ops.gemm(dqkv, shadow(wqkv), b_mn=True)
+            if l > 0:           # this LayerNorm backward also emits the gated bf16 dY (+ bias grad) of Block l-1's fc2
+                pb2 = params[(l - 1) * NP + 10]
+                pg2 = gates[2 * (l - 1) + 1] if gates is not None else None
+                dx, g = ops.layernorm_bwd(dh1, xs, mean1, rstd1, n1w, G(n1w, 0), G(n1b, 1), dres=dxm, dacc=dpos,
+                                          want_bf16=True, row_scale=pg2, rows_per_scale=T,
+                                          dbias=sink.get(pb2, (l - 1, 10)))
+            else:
+                dx, _ = ops.layernorm_bwd(dh1, xs, mean1, rstd1, n1w, G(n1w, 0), G(n1b, 1), dres=dxm, dacc=dpos)
+        pgrads = [sink.result((l, k)) for l in range(depth) for k in range(NP)]
+        return (dx.view(B, T, C), dpos.view(B, T, C) if has_pos else None, None, None, None, *pgrads)
+
+
+def transformer_stack(x, pos, blocks, num_heads, eps=1e-5, gates=None):
+    params = []
+    for blk in blocks:
+        sd = dict(blk.named_parameters())
+        params += [sd[k] for k in BLOCK_KEYS]
+    return TransformerStack.apply(x, pos, gates, num_heads, eps, *params)
+
+
+def drop_path_gates(rates, batch, device, training):
+    """timm 0.5.4 DropPath: per-sample gate floor(keep + U[0,1)) / keep, drawn independently for the
+    attention and the MLP branch of every Block.  None when no Block drops (eval, or all rates 0)."""
+    if not training or all(r == 0.0 for r in rates):
+        return None
+    keep = torch.tensor([1.0 - r for r in rates for _ in (0, 1)], dtype=torch.float32, device=device).view(-1, 1)
+    u = torch.rand(2 * len(rates), batch, dtype=torch.float32, device=device)
+    return (torch.floor(keep + u) / keep).contiguous()
+
+
+# ------------------------------------------------------------------------------------------- LayerNorm
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1]).contiguous().float()
+        y, _, mean, rstd = ops.layernorm_fwd(x2, weight, bias, eps, out_dtype=torch.float32)
+        ctx.save_for_backward(x2, mean, rstd, weight, bias)
+        return y.view(shp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, mean, rstd, weight, bias = ctx.saved_tensors
+        sink = _GradSink()
+        dx, _ = ops.layernorm_bwd(dy.reshape(x2.shape).contiguous().float(), x2, mean, rstd, weight,
+                                  sink.get(weight, "w"), sink.get(bias, "b"))
+        return dx.view(dy.shape), sink.result("w"), sink.result("b"), None
+
+
+def layer_norm(x, weight, bias, eps=1e-5):
+    return LayerNormFn.apply(x, weight, bias, eps)
+
+
+# ---------------------------------------------------------------------------------------------- Linear
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b), fp32 in / fp32 out, bf16 tensor-core GEMM inside (K, N multiples of 8)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gelu):
+        shp = x.shape
+        xb = x.reshape(-1, shp[-1]).to(torch.bfloat16).contiguous()
+        u = None
+        if gelu:
+            u = torch.empty(xb.shape[0], weight.shape[0], dtype=torch.bfloat16, device=x.device)
+            y = ops.gemm(xb, shadow(weight), bias=bias, act=ops.ACT_GELU, preact_out=u, out_dtype=torch.float32)
+        else:
+            y = ops.gemm(xb, shadow(weight), bias=bias, out_dtype=torch.float32)
+        ctx.save_for_backward(xb, weight, bias, u)
+        ctx.x_needs = x.requires_grad
+        return y.view(*shp[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, weight, bias, u = ctx.saved_tensors
+        sink = _GradSink()
+        N = weight.shape[0]
+        d2 = dy.reshape(-1, N).contiguous().float()
+        if u is not None:      # through the GELU first (needs its own pass: bias grad is of the pre-activation)
+            uu = u.float()
+            cdf = 0.5 * (1 + torch.erf(uu * 0.7071067811865476))
+            d2 = d2 * (cdf + uu * torch.exp(-0.5 * uu * uu) * 0.3989422804014327)
+        if N % 128 == 0 and N <= 1024:
+            g = ops.cast_rows(d2, dbias=sink.get(bias, "b") if bias is not None else None)
+        else:
+            g = d2.to(torch.bfloat16)
+            if bias is not None:
+                ops.colsum(d2, sink.get(bias, "b"))
+        ops.wgrad(g, xb, sink.get(weight, "w"))
+        dx = None
+        if ctx.x_needs:
+            dx = ops.gemm(g, shadow(weight), b_mn=True, out_dtype=torch.float32).view(*dy.shape[:-1], weight.shape[1])
+        return dx, sink.result("w"), sink.result("b") if bias is not None else None, None
+
+
+def linear(x, weight, bias=None, gelu=False):
+    return LinearFn.apply(x, weight, bias, gelu)
+
+
+# --------------------------------------------------------------------------------- mini-PointNet Encoder
+class PointNetEncoderFn(torch.autograd.Function):
+    """Encoder.forward (models/dvae.py:201-215) with train-mode BatchNorm1d: four tcgen05 GEMMs + the fused
+    elementwise / reduction kernels of csrc/pointnet.cu.  The `cat([global, local])` + conv3 is computed
+    hoisted: W3[:, :256] . global (per GROUP) is added to W3[:, 256:] . local (per point) in the GEMM epilogue."""
+
+    @staticmethod
+    def forward(ctx, nb, training, momentum, eps, bufs, w1, b1, g1, be1, w2, b2, w3, b3, g2, be2, w4, b4):
+        B, G, k, _ = nb.shape
+        M = B * G * k
+        p = nb.reshape(M, 3).contiguous().float()
+        rm1, rv1, nbt1, rm2, rv2, nbt2 = bufs
+        W1 = w1.view(128, 3)
+        if training:
+            mom = ops.pn_moments(p) / M
+            mu = mom[:3]
+            S = torch.stack([mom[3], mom[4], mom[5], mom[4], mom[6], mom[7], mom[5], mom[7], mom[8]]).view(3, 3)
+            S = S - torch.outer(mu, mu)
+            W1d = W1.double()
+            mean1 = W1d @ mu + b1.double()
+            var1 = ((W1d @ S) * W1d).sum(1).clamp_min(0)
+            with torch.no_grad():
+                rm1.mul_(1 - momentum).add_(mean1.float(), alpha=momentum)
+                rv1.mul_(1 - momentum).add_((var1 * (M / (M - 1))).float(), alpha=momentum)
+                nbt1.add_(1)
+        else:
+            mean1, var1 = rm1.double(), rv1.double()
+        rstd1 = torch.rsqrt(var1 + eps)
+        s1 = g1.double() * rstd1
+        Wf = (W1.double() * s1[:, None]).float().contiguous()
+        bf = ((b1.double() - mean1) * s1 + be1.double()).float()
+        a1 = ops.pn_conv1(p, Wf, bf, relu=True)                                   # [M,128]
+        f2 = ops.gemm(a1, shadow(w2).view(256, 128), bias=b2)                     # [M,256]
+        gmax, _, arg2 = ops.group_max(f2, k)                                      # [BG,256]
+        w3s = shadow(w3).view(512, 512)
+        gpart = ops.gemm(gmax, w3s[:, :256], bias=b3, out_dtype=torch.float32)    # [BG,512]
+        h3 = ops.gemm(f2, w3s[:, 256:], resid=gpart, resid_row_div=k)             # [M,512]
+        if training:
+            sm, sq = ops.bn_stats(h3)
+            mean2 = sm.double() / M
+            var2 = (sq.double() / M - mean2 * mean2).clamp_min(0)
+            with torch.no_grad():
+                rm2.mul_(1 - momentum).add_(mean2.float(), alpha=momentum)
+                rv2.mul_(1 - momentum).add_((var2 * (M / (M - 1))).float(), alpha=momentum)
+                nbt2.add_(1)
+        else:
+            mean2, var2 = rm2.double(), rv2.double()
+        rstd2 = torch.rsqrt(var2 + eps)
+        sc2 = g2.double() * rstd2
+        a3 = ops.bn_apply(h3, sc2.float(), (be2.double() - mean2 * sc2).float(), relu=True)   # [M,512]
+        C = w4.shape[0]
+        f4 = ops.gemm(a3, shadow(w4).view(C, 512), bias=b4)                       # [M,C]
+        _, tokens, arg4 = ops.group_max(f4, k, want_bf16=False, want_f32=True)
+        ctx.save_for_backward(p, a1, f2, gmax, arg2, h3, a3, arg4, mean1.float(), rstd1.float(), mean2.float(),
+                              rstd2.float(), w1, b1, g1, be1, w2, b2, w3, b3, g2, be2, w4, b4)
+        ctx.meta = (B, G, k, C, training)
+        ctx.mark_non_differentiable(*[])
+        return tokens.view(B, G, C)
+
+    @staticmethod
+    def backward(ctx, dtok):
+        (p, a1, f2, gmax, arg2, h3, a3, arg4, mean1, rstd1, mean2, rstd2, w1, b1, g1, be1, w2, b2, w3, b3, g2, be2, w4,
+         b4) = ctx.saved_tensors
+        B, G, k, C, training = ctx.meta
+        if not training:
+            raise RuntimeError("act_b200 Encoder: backward is implemented for train-mode BatchNorm only")
+        sink = _GradSink()
+        BG = B * G
+        d = dtok.reshape(BG, C).contiguous().float()
+        ops.colsum(d, sink.get(b4, "b4"))
+        dF4 = ops.group_max_bwd(d, arg4, k)                                       # [M,C] dense
+        ops.wgrad(dF4, a3, sink.get(w4, "w4").view(C, 512))
+        dZ3 = ops.gemm(dF4, shadow(w4).view(C, 512), b_mn=True, mul_in=a3, mul_mode=ops.MUL_RELU_MASK)
+        dH3, dbe2, dg2 = ops.bn_bwd(dZ3, h3, mean2, rstd2, g2)
+        sink.get(g2, "g2").add_(dg2)
+        sink.get(be2, "be2").add_(dbe2)
+        dGp_b, dGp_f = ops.group_sum(dH3, k, want_bf16=True, want_f32=True)       # [BG,512]
+        sink.get(b3, "b3").add_(dGp_f.sum(0))
+        gw3 = sink.get(w3, "w3").view(512, 512)
+        ops.wgrad(dH3, f2, gw3[:, 256:])
+        ops.wgrad(dGp_b, gmax, gw3[:, :256])
+        w3s = shadow(w3).view(512, 512)
+        dgmax = ops.gemm(dGp_b, w3s[:, :256], b_mn=True, out_dtype=torch.float32)  # [BG,256]
+        dF2 = ops.gemm(dH3, w3s[:, 256:], b_mn=True)                              # [M,256]
+        ops.group_max_bwd(dgmax, arg2, k, out=dF2)
+        ops.wgrad(dF2, a1, sink.get(w2, "w2").view(256, 128))
+        ops.colsum(dF2, sink.get(b2, "b2"))
+        dZ1 = ops.gemm(dF2, shadow(w2).view(256, 128), b_mn=True, mul_in=a1, mul_mode=ops.MUL_RELU_MASK)
+        dbe1, dg1 = ops.pn_conv1_bwd(dZ1, p, w1.view(128, 3).contiguous(), b1, mean1, rstd1, g1,
+                                     sink.get(w1, "w1").view(128, 3), sink.get(b1, "b1"))
+        sink.get(g1, "g1").add_(dg1)
+        sink.get(be1, "be1").add_(dbe1)
+        r = sink.result
+        return (None, None, None, None, None, r("w1"), r("b1"), r("g1"), r("be1"), r("w2"), r("b2"), r("w3"), r("b3"),
+                r("g2"), r("be2"), r("w4"), r("b4"))
+
+
+# --------------------------------------------------------------------------------------------- the loss
+class CosineLossFn(torch.autograd.Function):
+    """(1/B) sum_b (1 - mean_tok cos(student[b], teacher[b])) -- act.py:1243-1254 without the Python loop."""
+
+    @staticmethod
+    def forward(ctx, student, teacher):
+        C = student.shape[-1]
+        s2 = student.reshape(-1, C).contiguous().float()
+        t2 = teacher.reshape(-1, C).contiguous().float()
+        loss, grad = ops.cosine_loss(s2, t2, 1e-8, want_grad=True)
+        ctx.save_for_backward(grad)
+        ctx.shape = student.shape
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (grad,) = ctx.saved_tensors
+        return (grad * dloss).view(ctx.shape), None
+
+
+def cosine_loss(student, teacher):
+    return CosineLossFn.apply(student, teacher)

@@ -1,0 +1,127 @@
+"""Registry-compatible model classes of the hot path (same NAME, constructor contract `cls(cfg)` and
+state_dict keys as the reference: /root/reference/models/act.py:1099-1258, utils/registry.py:272-285).
+
+`ACT_PointDistillation` is the Stage-II model that tools/runner_pretrain.py:139 calls as
+`loss = base_model(points)`.  The frozen Stage-I teacher (`dvae_tokenizer`, act.py:1151-1160, 1216-1217 --
+a prompt-tuned ViT-B whose pretrained weights are not obtainable offline) is SURVEY.md row f1 ("next"): it is
+pluggable here through `teacher` (any callable (neighborhood, center) -> [B,G,C] features, e.g. the reference's
+own ACTPromptedDiscreteVAEwithVIT module); the default is a deterministic synthetic target so that the student
+path can be trained / timed / parity-checked stand-alone.
+"""
+import torch
+import torch.nn as nn
+
+from . import layers
+from .modules import Group, TransformerDecoder, VisableOnlyMaskTransformer, pos_mlp
+
+MODELS = {}
+
+
+def register(cls):
+    MODELS[cls.__name__] = cls
+    return cls
+
+
+class Cfg(dict):
+    """Minimal EasyDict look-alike (the reference passes easydict.EasyDict built from cfgs/*.yaml)."""
+
+    def __init__(self, d=None, **kw):
+        super().__init__()
+        for k, v in dict(d or {}, **kw).items():
+            self[k] = Cfg(v) if isinstance(v, dict) else v
+
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+def default_config(mask_ratio=0.6, drop_path_rate=0.1, num_group=64, group_size=32, depth=12, decoder_depth=2):
+    """model: block of cfgs/pretrain/pretrain_act_distill.yaml (BASELINE config 2 uses mask_ratio 0.6)."""
+    return Cfg(NAME="ACT_PointDistillation", loss="cosine",
+               transformer_config=dict(mask_ratio=mask_ratio, mask_type="rand", proj="linear", embed_dim=384,
+                                       encoder_dims=384, depth=depth, drop_path_rate=drop_path_rate, cls_dim=512,
+                                       replace_pob=0.0, num_heads=6, decoder_depth=decoder_depth,
+                                       decoder_num_heads=6, return_all_tokens=False, cls_loss=False,
+                                       register_shallow_hook=9),
+               dvae_config=dict(num_group=num_group, group_size=group_size, encoder_dims=384, num_tokens=8192,
+                                tokens_dims=384, decoder_dims=384, ckpt=None))
+
+
+class SyntheticTeacher(nn.Module):
+    """Stand-in for dvae_tokenizer.forward_tokenizer_features: fixed pseudo-random features that depend on the
+    group centres (so different clouds get different targets), no parameters, no gradient."""
+
+    def __init__(self, dim):
+        super().__init__()
+        g = torch.Generator().manual_seed(1234)
+        self.register_buffer("proj", torch.randn(3, dim, generator=g), persistent=False)
+        self.register_buffer("phase", torch.rand(dim, generator=g) * 6.2831853, persistent=False)
+
+    @torch.no_grad()
+    def forward(self, neighborhood, center):
+        return torch.sin(center @ self.proj * 3.0 + self.phase)
+
+
+@register
+class ACT_PointDistillation(nn.Module):
+    def __init__(self, config, teacher=None):
+        super().__init__()
+        self.config = config
+        tc, dc = config.transformer_config, config.dvae_config
+        if tc.cls_loss or tc.proj != "linear" or config.loss != "cosine":
+            raise NotImplementedError("act_b200 implements the shipped config: cls_loss False, proj linear, cosine loss")
+        self.mask_ratio = tc.mask_ratio
+        self.embed_dim = tc.embed_dim
+        self.ACT_encoder = VisableOnlyMaskTransformer(config)
+        self.group_size, self.num_group = dc.group_size, dc.num_group
+        self.drop_path_rate = tc.drop_path_rate
+        self.decoder_depth, self.decoder_num_heads = tc.decoder_depth, tc.decoder_num_heads
+        # teacher: not registered as a submodule -> not in state_dict / not trained (the reference keeps its frozen
+        # teacher under `dvae_tokenizer.*`; loading such a checkpoint needs strict=False)
+        object.__setattr__(self, "teacher", teacher if teacher is not None else SyntheticTeacher(dc.tokens_dims))
+        self.group_divider = Group(num_group=self.num_group, group_size=self.group_size)
+        self.proj_head = nn.Linear(self.embed_dim, dc.tokens_dims)
+        if self.mask_ratio > 0.:
+            self.mask_token = nn.Parameter(torch.zeros(1, 1, self.embed_dim))
+            self.decoder_pos_embed = nn.Sequential(nn.Linear(3, 128), nn.GELU(), nn.Linear(128, self.embed_dim))
+            dpr = [x.item() for x in torch.linspace(0, self.drop_path_rate, self.decoder_depth)]
+            self.ACT_decoder = TransformerDecoder(embed_dim=self.embed_dim, depth=self.decoder_depth,
+                                                  drop_path_rate=dpr, num_heads=self.decoder_num_heads)
+            nn.init.trunc_normal_(self.mask_token, std=.02)
+        else:
+            raise NotImplementedError("mask_ratio 0 (no decoder) is not part of the hot path")
+
+    def _apply(self, fn, *a, **k):
+        super()._apply(fn, *a, **k)
+        if isinstance(self.teacher, nn.Module):
+            self.teacher._apply(fn)
+        return self
+
+    def forward_eval(self, pts):
+        with torch.no_grad():
+            neighborhood, center = self.group_divider(pts)
+            return self.ACT_encoder(neighborhood, center, only_cls_tokens=True, noaug=True)
+
+    def forward(self, pts, noaug=False, mask=None, teacher_feat=None, **kwargs):
+        if noaug:
+            return self.forward_eval(pts)
+        neighborhood, center = self.group_divider(pts)
+        x_vis, mask = self.ACT_encoder(neighborhood, center, mask=mask)
+        B, n_vis, C = x_vis.shape
+        G = center.shape[1]
+        num_mask = G - n_vis
+        if teacher_feat is None:
+            with torch.no_grad():
+                teacher_feat = self.teacher(neighborhood, center)
+        order = self.ACT_encoder._order                       # visible groups first, then masked, original order
+        centers_sorted = torch.gather(center, 1, order[..., None].expand(-1, -1, 3))
+        pos_full = pos_mlp(self.decoder_pos_embed, centers_sorted)            # [pos(vis) | pos(mask)]
+        x_full = torch.cat([x_vis, self.mask_token.expand(B, num_mask, -1)], dim=1)
+        x_dec = self.ACT_decoder(x_full, pos_full, num_mask)
+        student = layers.linear(x_dec, self.proj_head.weight, self.proj_head.bias)
+        teacher = torch.gather(teacher_feat, 1, order[:, n_vis:, None].expand(-1, -1, student.shape[-1]))
+        return layers.cosine_loss(student, teacher)
+
+
+def build_model_from_cfg(cfg, **kwargs):
+    """models/build.py:7-17 equivalent: look up cfg.NAME, call cls(cfg)."""
+    return MODELS[cfg.NAME](cfg, **kwargs)

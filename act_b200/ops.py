@@ -138,10 +138,16 @@ class ChamferFunction(torch.autograd.Function):
 # ------------------------------------------------------------------------------ tcgen05 GEMM + epilogues
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 MUL_NONE, MUL_GELU_GRAD, MUL_RELU_MASK = 0, 1, 2
+_vp = _lib.ctypes.c_void_p
+
+
+def _p(t):
+    return _vp(t.data_ptr()) if t is not None else None
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bias=None, act=ACT_NONE,
-         preact_out=None, mul_in=None, mul_mode=MUL_NONE, resid=None, alpha=1.0, splits=1, block_n=0):
+         preact_out=None, mul_in=None, mul_mode=MUL_NONE, resid=None, resid_row_div=1, row_scale=None,
+         rows_per_scale=1, alpha=1.0, splits=1, block_n=0):
     """out[M,N] = epilogue(alpha * A . B^T) on the tcgen05 GEMM (include/act_b200.h: act_gemm_bf16).
     a: bf16 [M,K] (or [K,M] if a_mn);  b: bf16 [N,K] (or [K,N] if b_mn).  2-D, last-dim contiguous."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.dim() == 2 and b.dim() == 2
@@ -154,11 +160,187 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bi
     assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype in (torch.bfloat16, torch.float32)
     if preact_out is not None:
         assert preact_out.dtype == torch.bfloat16 and preact_out.stride(0) == out.stride(0)
-    _lib.call("act_gemm_bf16", _lib.ctypes.c_void_p(a.data_ptr()), _lib.ctypes.c_void_p(b.data_ptr()), M, N, K,
-              int(a_mn), int(b_mn), a.stride(0), b.stride(0), _lib.ctypes.c_void_p(out.data_ptr()), out.stride(0),
-              int(out.dtype == torch.float32), bias, int(act), preact_out, mul_in,
-              mul_in.stride(0) if mul_in is not None else 0, int(mul_mode),
-              _lib.ctypes.c_void_p(resid.data_ptr()) if resid is not None else None,
-              resid.stride(0) if resid is not None else 0, float(alpha), int(splits), int(block_n))
+    _lib.call("act_gemm_bf16", _p(a), _p(b), M, N, K, int(a_mn), int(b_mn), a.stride(0), b.stride(0), _p(out),
+              out.stride(0), int(out.dtype == torch.float32), bias, int(act), preact_out, _p(mul_in),
+              mul_in.stride(0) if mul_in is not None else 0, int(mul_mode), _p(resid),
+              resid.stride(0) if resid is not None else 0, int(resid_row_div), row_scale, int(rows_per_scale),
+              float(alpha),
+              int(splits), int(block_n))
     _count()
     return out
+
+
+def wgrad_splits(n_out, k_out, tokens):
+    """Split-K factor for dW[n_out,k_out] = dY^T X over `tokens`: aim at ~2 CTAs per SM."""
+    tiles = ((n_out + 127) // 128) * ((k_out + 127) // 128)
+    kb = (tokens + 63) // 64
+    return max(1, min(kb, (296 + tiles - 1) // tiles))
+
+
+def wgrad(dy, x, grad_out):
+    """grad_out[N,K] (f32, accumulated in place) += dy[T,N]^T . x[T,K]   (both operands read MN-major)."""
+    T, N = dy.shape
+    K = x.shape[1]
+    sp = wgrad_splits(N, K, T)
+    if sp == 1:
+        gemm(dy, x, a_mn=True, b_mn=True, out=grad_out, resid=grad_out)
+    else:
+        gemm(dy, x, a_mn=True, b_mn=True, out=grad_out, splits=sp)
+    return grad_out
+
+
+# ------------------------------------------------------------------------------ Block pieces
+def layernorm_fwd(x, gamma, beta, eps=1e-5, pos=None, out_dtype=torch.bfloat16, want_sum=False, save_stats=True):
+    """x f32 [M,C] (+ pos) -> (y, xsum or None, mean, rstd)."""
+    M, C = x.shape
+    y = torch.empty(M, C, dtype=out_dtype, device=x.device)
+    xs = torch.empty_like(x) if (want_sum or pos is not None) else None
+    mean = torch.empty(M, dtype=torch.float32, device=x.device) if save_stats else None
+    rstd = torch.empty(M, dtype=torch.float32, device=x.device) if save_stats else None
+    _lib.call("act_layernorm_fwd", x, pos, gamma, beta, float(eps), M, C, xs, _p(y), int(out_dtype == torch.float32),
+              mean, rstd)
+    _count()
+    return y, xs, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None, dacc=None, want_bf16=False, row_scale=None,
+                  rows_per_scale=1, dbias=None):
+    """-> (dx f32 [M,C], g bf16 or None); dgamma/dbeta/dbias/dacc accumulated in place."""
+    M, C = x.shape
+    dx = torch.empty(M, C, dtype=torch.float32, device=x.device)
+    g = torch.empty(M, C, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    _lib.call("act_layernorm_bwd", _p(dy), int(dy.dtype == torch.float32), x, mean, rstd, gamma, dres, M, C, dx,
+              dgamma, dbeta, dacc, g, row_scale, int(rows_per_scale), dbias)
+    _count()
+    return dx, g
+
+
+def cast_rows(x, row_scale=None, rows_per_scale=1, dbias=None):
+    M, C = x.shape
+    g = torch.empty(M, C, dtype=torch.bfloat16, device=x.device)
+    _lib.call("act_cast_rows", x, M, C, row_scale, int(rows_per_scale), g, dbias)
+    _count()
+    return g
+
+
+def attention_fwd(qkv, B, T, H, scale):
+    o = torch.empty(B * T, H * 64, dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty(B, H, T, dtype=torch.float32, device=qkv.device)
+    _lib.call("act_attention_fwd", qkv, B, T, H, 64, float(scale), o, lse)
+    _count()
+    return o, lse
+
+
+def attention_bwd(qkv, o, do, lse, B, T, H, scale):
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty_like(lse)
+    _lib.call("act_attention_bwd", qkv, o, do, lse, B, T, H, 64, float(scale), dqkv, delta)
+    _count(2)
+    return dqkv
+
+
+def colsum(x, out):
+    M, N = x.shape
+    _lib.call("act_colsum", _p(x), int(x.dtype == torch.float32), M, N, x.stride(0), out)
+    _count()
+    return out
+
+
+def cosine_loss(student, teacher, eps=1e-8, want_grad=True):
+    R, C = student.shape
+    loss = torch.empty(1, dtype=torch.float32, device=student.device)
+    grad = torch.empty_like(student) if want_grad else None
+    _lib.call("act_cosine_loss", student, teacher, R, C, float(eps), loss, grad)
+    _count()
+    return loss, grad
+
+
+def adamw(param, grad, exp_avg, exp_avg_sq, shadow, n_decay, hyper):
+    _lib.call("act_adamw", param, grad, exp_avg, exp_avg_sq, shadow, _lib.ctypes.c_int64(param.numel()),
+              _lib.ctypes.c_int64(n_decay), hyper)
+    _count()
+
+
+# ------------------------------------------------------------------------------ mini-PointNet pieces
+def pn_moments(points):
+    M = points.shape[0]
+    out = torch.empty(9, dtype=torch.float64, device=points.device)
+    _lib.call("act_pn_moments", points, _lib.ctypes.c_int64(M), out)
+    _count()
+    return out
+
+
+def pn_conv1(points, W, b, relu=True):
+    M = points.shape[0]
+    out = torch.empty(M, 128, dtype=torch.bfloat16, device=points.device)
+    _lib.call("act_pn_conv1", points, W, b, _lib.ctypes.c_int64(M), int(relu), out)
+    _count()
+    return out
+
+
+def group_max(x, k, want_bf16=True, want_f32=False, want_arg=True):
+    Mk, C = x.shape
+    G = Mk // k
+    ob = torch.empty(G, C, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    of = torch.empty(G, C, dtype=torch.float32, device=x.device) if want_f32 else None
+    arg = torch.empty(G, C, dtype=torch.uint8, device=x.device) if want_arg else None
+    _lib.call("act_group_max", x, G, k, C, ob, of, arg)
+    _count()
+    return ob, of, arg
+
+
+def group_max_bwd(dout, arg, k, out=None):
+    G, C = dout.shape
+    acc = out is not None
+    if out is None:
+        out = torch.empty(G * k, C, dtype=torch.bfloat16, device=dout.device)
+    _lib.call("act_group_max_bwd", dout, arg, G, k, C, int(acc), out)
+    _count()
+    return out
+
+
+def group_sum(x, k, want_bf16=True, want_f32=False):
+    Mk, C = x.shape
+    G = Mk // k
+    ob = torch.empty(G, C, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    of = torch.empty(G, C, dtype=torch.float32, device=x.device) if want_f32 else None
+    _lib.call("act_group_sum", x, G, k, C, ob, of)
+    _count()
+    return ob, of
+
+
+def bn_stats(x):
+    M, C = x.shape
+    s = torch.empty(2, C, dtype=torch.float32, device=x.device)
+    _lib.call("act_bn_stats", x, _lib.ctypes.c_int64(M), C, s[0], s[1])
+    _count()
+    return s[0], s[1]
+
+
+def bn_apply(x, scale, shift, relu=True, out=None):
+    M, C = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.call("act_bn_apply", x, scale, shift, _lib.ctypes.c_int64(M), C, int(relu), out)
+    _count()
+    return out
+
+
+def bn_bwd(dz, x, mean, rstd, gamma):
+    """-> (dh bf16, sum_dz (= dbeta), sum_dz_xhat (= dgamma))."""
+    M, C = x.shape
+    s = torch.empty(2, C, dtype=torch.float32, device=x.device)
+    _lib.call("act_bn_bwd_stats", dz, x, mean, rstd, _lib.ctypes.c_int64(M), C, s[0], s[1])
+    dh = torch.empty_like(dz)
+    _lib.call("act_bn_bwd_apply", dz, x, mean, rstd, gamma, s[0], s[1], _lib.ctypes.c_int64(M), C, dh)
+    _count(2)
+    return dh, s[0], s[1]
+
+
+def pn_conv1_bwd(dz, points, W, b, mean, rstd, gamma, dW, db):
+    """Accumulates dW [128,3], db [128]; returns (dbeta, dgamma) of BatchNorm1."""
+    M = points.shape[0]
+    s = torch.empty(2, 128, dtype=torch.float32, device=points.device)
+    _lib.call("act_pn_conv1_bwd", dz, points, W, b, mean, rstd, gamma, _lib.ctypes.c_int64(M), s[0], s[1], dW, db)
+    _count(2)
+    return s[0], s[1]

@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- ACT Stage-II masked-point-modeling training step on B200 (BASELINE.json configs[1]/[3]).
+
+One "step" = Group tokenizer (FPS + kNN) -> mini-PointNet embed -> 12-block student encoder -> 2-block decoder
+-> proj head -> cosine distillation loss -> backward -> (N>1: one NCCL all-reduce of the flat gradient) ->
+fused AdamW, on B=128 synthetic ShapeNet-shaped clouds per GPU (N=1024, G=64, k=32, d=384, mask 0.6,
+drop_path 0.1), bf16 tensor-core operands / fp32 accumulation and master weights.  The frozen teacher is replaced
+by a synthetic target (the teacher is row f1, "next").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+  N>1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0).  `value`: clouds/s with the batch already resident in HBM; `e2e`: the same step
+called with a pinned HOST batch (H2D inside the timed region, D2H of the loss).  `--impl reference` times the
+reference's path restated for the host CPU (oracle/ref_model.py + oracle/cpu_ref.c: the reference itself is
+Python + CUDA-only extensions and cannot run on the box without a GPU build), all host threads.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "clouds_per_sec_act_stage2_step"
+UNIT = "clouds/s"
+N_POINTS, N_GROUP, GROUP_SIZE, MASK_RATIO, DROP_PATH = 1024, 64, 32, 0.6, 0.1
+
+
+def workload_cfg(batch, n_gpus):
+    return {"workload": "ACT Stage-II student step: N=1024, G=64 x k=32, 12L d=384 + 2L decoder, mask 0.6, "
+                        "drop_path 0.1, cosine loss, fwd+bwd+AdamW; synthetic teacher target (teacher fwd = row f1)",
+            "batch_per_gpu": batch, "global_batch": batch * n_gpus, "n_points": N_POINTS, "num_group": N_GROUP,
+            "group_size": GROUP_SIZE, "depth": 12, "embed_dim": 384, "mask_ratio": MASK_RATIO,
+            "parallelism": f"dp{n_gpus}",
+            "l2": "per-step activation working set (~3 GB) >> 126 MB L2; an extra 256 MB L2-flush write runs "
+                  "between timed steps, outside the per-step event pairs"}
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+    try:
+        p.update(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))))
+        p["src"] = "measured"
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        # under-load samples: the upper half of the observed clocks
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+    from act_b200 import layers, models, ops
+    from oracle.ref_model import synthetic_clouds          # synthetic input generator only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: the act_b200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    torch.manual_seed(0)
+    np.random.seed(1234 + rank)
+    cfg = models.default_config(mask_ratio=MASK_RATIO, drop_path_rate=DROP_PATH, num_group=N_GROUP,
+                                group_size=GROUP_SIZE)
+    model = models.ACT_PointDistillation(cfg).to(dev).train()
+    fp = layers.FlatParams(model, lr=1e-3, weight_decay=0.05)
+    if world > 1:
+        dist.broadcast(fp.flat, 0)
+        fp.refresh_shadow()
+
+    n_batches = 4
+    host = [synthetic_clouds(B, N_POINTS, seed=20231017 + 97 * rank + i).pin_memory() for i in range(n_batches)]
+    resident = [h.to(dev) for h in host]
+    stage = torch.empty_like(resident[0])
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(points):
+        fp.zero_grad()
+        loss = model(points)
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(fp.grad)                         # the step's ONE collective: flat fp32 gradient
+        fp.set_hyper(grad_scale=1.0 / world)
+        fp.step()
+        return loss
+
+    def step_e2e(i):
+        stage.copy_(host[i % n_batches], non_blocking=True)  # H2D from pinned memory, inside the timed region
+        loss = step(stage)
+        loss_host.copy_(loss.detach(), non_blocking=True)    # D2H of the step's result
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, K):
+        evs = []
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            flush.zero_()                                     # L2 flush, outside the event pair
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn(i)
+            b.record()
+            evs.append((a, b))
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / K, wall
+
+    for i in range(args.warmup):
+        step(resident[i % n_batches])
+    for i in range(max(1, args.warmup // 2)):
+        step_e2e(i)
+    barrier()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ops.LAUNCHES
+    ms_step, wall = timed(lambda i: step(resident[i % n_batches]), args.steps)
+    launches = (ops.LAUNCHES - l0) // args.steps
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if sampler else None
+    last_loss = float(loss_host.item())
+
+    # ---- roofline of the dominant kernel: every launch of gemm_bf16_kernel inside one step, timed with CUDA
+    # events on the launching stream (instrumented extra steps, not part of `value`)
+    pk = peaks()
+    roof = None
+    if rank == 0:
+        recs = []
+        orig = ops.gemm
+
+        def timed_gemm(a, b, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = orig(a, b, **kw)
+            e1.record()
+            K_, M_ = (a.shape if kw.get("a_mn") else a.shape[::-1])
+            N_ = b.shape[1] if kw.get("b_mn") else b.shape[0]
+            recs.append((e0, e1, 2.0 * M_ * N_ * K_))
+            return out
+
+        ops.gemm = timed_gemm
+        layers.ops.gemm = timed_gemm
+        try:
+            for i in range(2):
+                step(resident[i % n_batches])
+            torch.cuda.synchronize()
+        finally:
+            ops.gemm = orig
+        tot_ms = sum(a.elapsed_time(b) for a, b, _ in recs)
+        tot_fl = sum(f for _, _, f in recs)
+        n = len(recs)
+        ach = tot_fl / (tot_ms * 1e-3) / 1e12
+        peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        roof = {"kernel": "gemm_bf16_kernel (tcgen05/TMA GEMM, all launches of a step)", "bound": "tensor",
+                "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4),
+                "peak_src": pk["src"] + " bf16 sustained", "launches_per_step": n // 2,
+                "flops_per_launch": tot_fl / n, "avg_launch_us": round(tot_ms * 1e3 / n, 2),
+                "gemm_ms_per_step": round(tot_ms / 2, 3), "gemm_share_of_step": round(tot_ms / 2 / ms_step, 3),
+                "traffic": None}
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        cpu = cpu_baseline(sample_batch=8, steps=1) if world == 1 and not args.no_cpu_baseline else None
+        clouds = B * world
+        line = {"metric": METRIC, "value": round(clouds / (ms_step * 1e-3), 1), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": workload_cfg(B, world), "impl": "ours",
+                "e2e": {"value": round(clouds / (ms_e2e * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms_e2e, 4),
+                        "h2d_bytes_per_step": int(stage.numel() * 4), "d2h_bytes_per_step": 4},
+                "gpu_launches": int(launches), "loss": last_loss, "wall_s_timed": round(wall, 3),
+                "clocks": clocks, "roofline": roof}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------- CPU baseline / reference arm
+def cpu_student_step_time(batch, steps, warmup, threads):
+    """The reference's path restated for the host (oracle/): Group on the C oracle, fp32 PyTorch modules,
+    torch.optim.AdamW with the reference's two parameter groups (tools/builder.py:37-55)."""
+    from oracle import ref_model
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = ref_model.ACTPointDistillationStudent(mask_ratio=MASK_RATIO).train()
+    decay = [p for n, p in model.named_parameters() if not (p.dim() <= 1 or n.endswith(".bias") or "token" in n)]
+    nodecay = [p for n, p in model.named_parameters() if (p.dim() <= 1 or n.endswith(".bias") or "token" in n)]
+    opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.05}, {"params": nodecay, "weight_decay": 0.0}],
+                            lr=1e-3)
+    pts = ref_model.synthetic_clouds(batch, N_POINTS)
+    teacher = torch.randn(batch, N_GROUP, 384)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss = model(pts, teacher)
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sum(times) / len(times)
+
+
+def cpu_baseline(sample_batch=8, steps=1):
+    threads = os.cpu_count() or 1
+    t = cpu_student_step_time(sample_batch, steps, 1, threads)
+    return {"value": round(sample_batch / t, 3), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{steps} timed step(s) after 1 warm-up of the oracle restatement (fp32 PyTorch + C FPS/kNN) "
+                      f"at batch {sample_batch} (same per-cloud workload; the full batch of 128 would take minutes)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = 8
+    steps = max(1, min(args.steps, 3))
+    warm = max(1, min(args.warmup, 1))
+    t = cpu_student_step_time(sample, steps, warm, threads)
+    world = max(1, args.gpus)
+    val = round(sample / t, 3)
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(t * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_cfg(args.batch, world),
+            "impl": "reference",
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{steps} timed step(s) at batch {sample} per step (bounded sample of the "
+                                       f"batch-128 workload), oracle restatement of the reference path on all host "
+                                       f"threads; the reference's own native ops are CUDA-only"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=128, help="clouds per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

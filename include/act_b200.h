@@ -81,14 +81,106 @@ int act_chamfer_backward(const float *xyz1, const float *xyz2, const int32_t *id
  * A / B are bf16, row-major: K-major = [MN, K] with pitch lda/ldb (elements), MN-major = [K, MN].
  * Epilogue, in order, each part optional: + bias[N] (f32);  preact_out (bf16 [M,ldo]) <- value;
  * act_kind 1 = GELU(erf) / 2 = ReLU;  mul_mode 1: *= GELU'(mul_in) / 2: *= (mul_in > 0)  (mul_in bf16 [M,ldm]);
- * + resid[M,ldr] (f32, may alias out);  out bf16 (out_fp32 = 0) or f32 (1), pitch ldo.
+ * *= row_scale[m / rows_per_scale] (nullable f32: the per-sample DropPath gate of timm, models/act.py:88-89);
+ * + resid[m / resid_row_div, ldr] (f32; may alias out when resid_row_div == 1; resid_row_div = group_size
+ * broadcasts a per-group term over the group's points: the hoisted "global feature" half of the mini-PointNet's
+ * third conv, models/dvae.py:211-213);  out bf16 (out_fp32 = 0) or f32 (1), pitch ldo.
  * splits > 1: split-K, fp32 atomic accumulation into out (caller zeroes it; no other epilogue parts).
  * block_n: 64 / 128 output-tile width (0 = choose).  Requirements: N % 8 == 0, K % 8 == 0 pitches,
  * 16-byte aligned pointers. */
 int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, int a_mn_major, int b_mn_major, int lda, int ldb,
                   void *out, int ldo, int out_fp32, const float *bias, int act_kind, void *preact_out,
-                  const void *mul_in, int ldm, int mul_mode, const float *resid, int ldr, float alpha, int splits,
-                  int block_n, void *stream);
+                  const void *mul_in, int ldm, int mul_mode, const float *resid, int ldr, int resid_row_div,
+                  const float *row_scale, int rows_per_scale, float alpha, int splits, int block_n, void *stream);
+
+/* ---- Transformer Block pieces (models/act.py:45-90, 109-112) ------------------------------------------ */
+
+/* nn.LayerNorm(C, eps) over fp32 rows x[M,C] (C % 128 == 0, <= 1024).  pos (nullable, f32 [M,C]): the
+ * "x + pos" of TransformerEncoder.forward (act.py:111) is fused in -- xs = x + pos is normalised and also
+ * written to xsum_out (nullable).  out: bf16 (out_fp32 = 0, the next GEMM's operand) or f32.  mean/rstd
+ * (nullable, [M]) are saved for the backward. */
+int act_layernorm_fwd(const float *x, const float *pos, const float *gamma, const float *beta, float eps, int M,
+                      int C, float *xsum_out, void *out, int out_fp32, float *mean, float *rstd, void *stream);
+
+/* LayerNorm backward: dx_out[M,C] = dres (nullable f32: gradient arriving on the residual branch) + dLN;
+ * dgamma/dbeta [C] (nullable) are ACCUMULATED (atomics) -- they point into the flat gradient buffer.
+ * Fused extras for the Block backward (all nullable): dacc[M,C] += dx_out (gradient of `pos`, which every
+ * layer adds again); g_bf16[M,C] = bf16(dx_out * row_scale[m / rows_per_scale]) -- the dY operand of the
+ * next (lower) Linear's dgrad/wgrad, already gated by that branch's DropPath; dbias[C] += column sums of the
+ * same gated value (that Linear's bias gradient). */
+int act_layernorm_bwd(const void *dy, int dy_fp32, const float *x, const float *mean, const float *rstd,
+                      const float *gamma, const float *dres, int M, int C, float *dx_out, float *dgamma,
+                      float *dbeta, float *dacc, void *g_bf16, const float *row_scale, int rows_per_scale,
+                      float *dbias, void *stream);
+
+/* g_bf16[M,C] = bf16(x[M,C] * row_scale[m / rows_per_scale]) (row_scale nullable); dbias[C] (nullable) +=
+ * its column sums.  Entry point of a Block backward when the incoming gradient is plain fp32. */
+int act_cast_rows(const float *x, int M, int C, const float *row_scale, int rows_per_scale, void *g_bf16,
+                  float *dbias, void *stream);
+
+/* Attention.forward core (act.py:57-66): qkv bf16 [B*T, 3*H*64] -> o bf16 [B*T, H*64] =
+ * softmax(q k^T * scale) v per (batch, head); lse f32 [B,H,T] saved for the backward.  head_dim must be 64. */
+int act_attention_fwd(const void *qkv, int B, int T, int H, int head_dim, float scale, void *o, float *lse,
+                      void *stream);
+
+/* Attention backward: dO bf16 [B*T, H*64] -> dqkv bf16 [B*T, 3*H*64]; delta f32 [B,H,T] is scratch. */
+int act_attention_bwd(const void *qkv, const void *o, const void *dO, const float *lse, int B, int T, int H,
+                      int head_dim, float scale, void *dqkv, float *delta, void *stream);
+
+/* out[N] += column sums of x[M, ld] (bf16 or f32): bias gradients. */
+int act_colsum(const void *x, int x_fp32, int M, int N, int ld, float *out, void *stream);
+
+/* ---- mini-PointNet (Encoder, models/dvae.py:185-215): everything between the four 1x1-conv GEMMs ------- */
+/* Rows are points: M = B*G*k, row m belongs to group m / k.  Activations are bf16 [M, C]. */
+
+/* out9 (double) = {sum x, sum y, sum z, sum xx, xy, xz, yy, yz, zz} over points [M,3] f32: BatchNorm1's batch
+ * statistics follow analytically from these because conv1 is linear in the 3-D input. */
+int act_pn_moments(const float *points, long long M, double *out9, void *stream);
+/* out[M,128] bf16 = relu?(W[128,3] . p + b): first_conv[0] with BatchNorm1 folded into (W, b) + ReLU. */
+int act_pn_conv1(const float *points, const float *W, const float *b, long long M, int relu, void *out_bf16,
+                 void *stream);
+/* torch.max(feature, dim=2) over the k points of each group (dvae.py:211,214): x bf16 [G*k, C] ->
+ * out_bf16 / out_f32 (nullable) [G, C] and arg (nullable, u8 [G,C]: winning row, first on ties). */
+int act_group_max(const void *x_bf16, int G, int k, int C, void *out_bf16, float *out_f32, uint8_t *arg,
+                  void *stream);
+/* its backward: dF[G*k, C] bf16 (+)= scatter of dout f32 [G,C] to the arg-max rows (dense output). */
+int act_group_max_bwd(const float *dout, const uint8_t *arg, int G, int k, int C, int accumulate, void *dF_bf16,
+                      void *stream);
+/* sum over the k rows of each group (backward of the expand() of the global feature, dvae.py:212). */
+int act_group_sum(const void *x_bf16, int G, int k, int C, void *out_bf16, float *out_f32, void *stream);
+/* BatchNorm1d (train mode) statistics of x bf16 [M,C]: sum[C], sumsq[C] (f32, zeroed here). */
+int act_bn_stats(const void *x_bf16, long long M, int C, float *sum, float *sumsq, void *stream);
+/* y = relu?(x * scale[c] + shift[c]) (normalise + affine folded into scale/shift by the caller). */
+int act_bn_apply(const void *x_bf16, const float *scale, const float *shift, long long M, int C, int relu,
+                 void *y_bf16, void *stream);
+/* BatchNorm backward, pass 1: sum_dz[C], sum_dz_xhat[C] (zeroed here); pass 2:
+ * dh = gamma*rstd*(dz - sum_dz/M - xhat*sum_dz_xhat/M) with xhat = (x - mean)*rstd. */
+int act_bn_bwd_stats(const void *dz_bf16, const void *x_bf16, const float *mean, const float *rstd, long long M,
+                     int C, float *sum_dz, float *sum_dz_xhat, void *stream);
+int act_bn_bwd_apply(const void *dz_bf16, const void *x_bf16, const float *mean, const float *rstd,
+                     const float *gamma, const float *sum_dz, const float *sum_dz_xhat, long long M, int C,
+                     void *dh_bf16, void *stream);
+/* conv1 + BatchNorm1 backward in two passes over dz bf16 [M,128] with x-hat recomputed from the points:
+ * s1/s2 [128] = BN1 sums (= dbeta, dgamma; zeroed here); dW[128,3], db[128] ACCUMULATED (atomics). */
+int act_pn_conv1_bwd(const void *dz_bf16, const float *points, const float *W, const float *b, const float *mean,
+                     const float *rstd, const float *gamma, long long M, float *s1, float *s2, float *dW, float *db,
+                     void *stream);
+
+/* ---- Loss and optimizer ------------------------------------------------------------------------------ */
+
+/* Cosine distillation loss of ACT_PointDistillation.forward (/root/reference/models/act.py:1243-1254):
+ * student, teacher f32 [R, C] (R = B * num_mask rows, equal count per cloud) ->
+ * *loss = (1/R) sum_r (1 - cos_r)  (== (1/B) sum_b (1 - mean_tok cos));  grad_student (nullable) [R,C] =
+ * d loss / d student. */
+int act_cosine_loss(const float *student, const float *teacher, int R, int C, float eps, float *loss,
+                    float *grad_student, void *stream);
+
+/* torch.optim.AdamW over flat buffers (/root/reference/tools/builder.py:37-55 builds it with a decay and a
+ * no-decay group): elements [0, n_decay) get weight decay, [n_decay, n) do not.  hyper (device, f32[8]) =
+ * {lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, grad_scale}.  shadow_bf16 (nullable) receives
+ * the bf16 copy of the updated parameters (what the GEMMs read). */
+int act_adamw(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, void *shadow_bf16, long long n,
+              long long n_decay, const float *hyper, void *stream);
 
 #ifdef __cplusplus
 }
