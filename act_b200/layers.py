@@ -133,8 +133,7 @@ class TransformerStack(torch.autograd.Function):
         M = B * T
         depth = len(params) // NP
         scale = (C // num_heads) ** -0.5
-        need = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params) or
-                                            (pos is not None and pos.requires_grad))
+        need = any(ctx.needs_input_grad)
         cur = x.reshape(M, C).contiguous().float()
         pos2 = pos.reshape(M, C).contiguous().float() if pos is not None else None
         saved = []
@@ -216,12 +215,19 @@ def transformer_stack(x, pos, blocks, num_heads, eps=1e-5, gates=None):
     return TransformerStack.apply(x, pos, gates, num_heads, eps, *params)
 
 
+_KEEP_CACHE = {}
+
+
 def drop_path_gates(rates, batch, device, training):
     """timm 0.5.4 DropPath: per-sample gate floor(keep + U[0,1)) / keep, drawn independently for the
     attention and the MLP branch of every Block.  None when no Block drops (eval, or all rates 0)."""
     if not training or all(r == 0.0 for r in rates):
         return None
-    keep = torch.tensor([1.0 - r for r in rates for _ in (0, 1)], dtype=torch.float32, device=device).view(-1, 1)
+    key = (tuple(rates), str(device))
+    keep = _KEEP_CACHE.get(key)
+    if keep is None:       # built once, outside any CUDA-graph capture (the engine warms up eagerly first)
+        keep = torch.tensor([1.0 - r for r in rates for _ in (0, 1)], dtype=torch.float32).view(-1, 1).to(device)
+        _KEEP_CACHE[key] = keep
     u = torch.rand(2 * len(rates), batch, dtype=torch.float32, device=device)
     return (torch.floor(keep + u) / keep).contiguous()
 
@@ -326,8 +332,14 @@ class PointNetEncoderFn(torch.autograd.Function):
         Wf = (W1.double() * s1[:, None]).float().contiguous()
         bf = ((b1.double() - mean1) * s1 + be1.double()).float()
         a1 = ops.pn_conv1(p, Wf, bf, relu=True)                                   # [M,128]
-        f2 = ops.gemm(a1, shadow(w2).view(256, 128), bias=b2)                     # [M,256]
-        gmax, _, arg2 = ops.group_max(f2, k)                                      # [BG,256]
+        BG = B * G
+        if k == 32:      # max over the group's 32 points fused into the GEMM epilogue (fp32 accumulators)
+            gmax = torch.empty(BG, 256, dtype=torch.bfloat16, device=p.device)
+            arg2 = torch.empty(BG, 256, dtype=torch.uint8, device=p.device)
+            f2 = ops.gemm(a1, shadow(w2).view(256, 128), bias=b2, gmax_bf16=gmax, garg=arg2)   # [M,256]
+        else:
+            f2 = ops.gemm(a1, shadow(w2).view(256, 128), bias=b2)
+            gmax, _, arg2 = ops.group_max(f2, k)                                  # [BG,256]
         w3s = shadow(w3).view(512, 512)
         gpart = ops.gemm(gmax, w3s[:, :256], bias=b3, out_dtype=torch.float32)    # [BG,512]
         h3 = ops.gemm(f2, w3s[:, 256:], resid=gpart, resid_row_div=k)             # [M,512]
@@ -345,8 +357,13 @@ class PointNetEncoderFn(torch.autograd.Function):
         sc2 = g2.double() * rstd2
         a3 = ops.bn_apply(h3, sc2.float(), (be2.double() - mean2 * sc2).float(), relu=True)   # [M,512]
         C = w4.shape[0]
-        f4 = ops.gemm(a3, shadow(w4).view(C, 512), bias=b4)                       # [M,C]
-        _, tokens, arg4 = ops.group_max(f4, k, want_bf16=False, want_f32=True)
+        if k == 32:      # conv4's [M,C] output is never written: only its per-group max (+ arg-max) leaves the SM
+            tokens = torch.empty(BG, C, dtype=torch.float32, device=p.device)
+            arg4 = torch.empty(BG, C, dtype=torch.uint8, device=p.device)
+            ops.gemm(a3, shadow(w4).view(C, 512), bias=b4, gmax_f32=tokens, garg=arg4, no_out=True)
+        else:
+            f4 = ops.gemm(a3, shadow(w4).view(C, 512), bias=b4)                   # [M,C]
+            _, tokens, arg4 = ops.group_max(f4, k, want_bf16=False, want_f32=True)
         ctx.save_for_backward(p, a1, f2, gmax, arg2, h3, a3, arg4, mean1.float(), rstd1.float(), mean2.float(),
                               rstd2.float(), w1, b1, g1, be1, w2, b2, w3, b3, g2, be2, w4, b4)
         ctx.meta = (B, G, k, C, training)

@@ -147,25 +147,33 @@ def _p(t):
 
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bias=None, act=ACT_NONE,
          preact_out=None, mul_in=None, mul_mode=MUL_NONE, resid=None, resid_row_div=1, row_scale=None,
-         rows_per_scale=1, alpha=1.0, splits=1, block_n=0):
+         rows_per_scale=1, gmax_f32=None, gmax_bf16=None, garg=None, no_out=False, alpha=1.0, splits=1, block_n=0,
+         persistent=-1):
     """out[M,N] = epilogue(alpha * A . B^T) on the tcgen05 GEMM (include/act_b200.h: act_gemm_bf16).
-    a: bf16 [M,K] (or [K,M] if a_mn);  b: bf16 [N,K] (or [K,N] if b_mn).  2-D, last-dim contiguous."""
+    a: bf16 [M,K] (or [K,M] if a_mn);  b: bf16 [N,K] (or [K,N] if b_mn).  2-D, last-dim contiguous.
+    gmax_f32 / gmax_bf16 / garg: [M/32, N] outputs of the fused per-32-row max; no_out=True skips `out`."""
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.dim() == 2 and b.dim() == 2
     assert a.stride(1) == 1 and b.stride(1) == 1
     K, M = (a.shape if a_mn else a.shape[::-1])
     Kb, N = (b.shape if b_mn else b.shape[::-1])
     assert K == Kb, (a.shape, b.shape, a_mn, b_mn)
-    if out is None:
+    if no_out:
+        out = None
+    elif out is None:
         out = (torch.zeros if splits > 1 else torch.empty)(M, N, dtype=out_dtype, device=a.device)
-    assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype in (torch.bfloat16, torch.float32)
+    if out is not None:
+        assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype in (torch.bfloat16, torch.float32)
     if preact_out is not None:
         assert preact_out.dtype == torch.bfloat16 and preact_out.stride(0) == out.stride(0)
+    gm = [t for t in (gmax_f32, gmax_bf16, garg) if t is not None]
+    ldg = gm[0].stride(0) if gm else 0
+    assert all(t.stride(0) == ldg and t.shape == (M // 32, N) for t in gm)
     _lib.call("act_gemm_bf16", _p(a), _p(b), M, N, K, int(a_mn), int(b_mn), a.stride(0), b.stride(0), _p(out),
-              out.stride(0), int(out.dtype == torch.float32), bias, int(act), preact_out, _p(mul_in),
-              mul_in.stride(0) if mul_in is not None else 0, int(mul_mode), _p(resid),
-              resid.stride(0) if resid is not None else 0, int(resid_row_div), row_scale, int(rows_per_scale),
-              float(alpha),
-              int(splits), int(block_n))
+              out.stride(0) if out is not None else 0, int(out is not None and out.dtype == torch.float32), bias,
+              int(act), preact_out, _p(mul_in), mul_in.stride(0) if mul_in is not None else 0, int(mul_mode),
+              _p(resid), resid.stride(0) if resid is not None else 0, int(resid_row_div), row_scale,
+              int(rows_per_scale), gmax_f32, gmax_bf16, garg, int(ldg), float(alpha), int(splits), int(block_n),
+              int(persistent))
     _count()
     return out
 
@@ -241,6 +249,10 @@ def attention_bwd(qkv, o, do, lse, B, T, H, scale):
 
 def colsum(x, out):
     M, N = x.shape
+    if x.dtype == torch.bfloat16 and x.is_contiguous() and N % 8 == 0 and N <= 2048:
+        _lib.call("act_colsum_bf16_dense", x, _lib.ctypes.c_int64(M), N, out)
+        _count()
+        return out
     _lib.call("act_colsum", _p(x), int(x.dtype == torch.float32), M, N, x.stride(0), out)
     _count()
     return out

@@ -102,7 +102,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch.distributed as dist
-    from act_b200 import layers, models, ops
+    from act_b200 import dp, layers, models, ops
     from oracle.ref_model import synthetic_clouds          # synthetic input generator only
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -121,31 +121,23 @@ def run_ours(args):
                                 group_size=GROUP_SIZE)
     model = models.ACT_PointDistillation(cfg).to(dev).train()
     fp = layers.FlatParams(model, lr=1e-3, weight_decay=0.05)
-    if world > 1:
-        dist.broadcast(fp.flat, 0)
-        fp.refresh_shadow()
+    dp.broadcast_params(fp)
 
     n_batches = 4
-    host = [synthetic_clouds(B, N_POINTS, seed=20231017 + 97 * rank + i).pin_memory() for i in range(n_batches)]
+    host = [synthetic_clouds(B, N_POINTS, seed=dp.shard_seed(20231017, rank, i)).pin_memory() for i in range(n_batches)]
     resident = [h.to(dev) for h in host]
-    stage = torch.empty_like(resident[0])
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def step(points):
-        fp.zero_grad()
-        loss = model(points)
-        loss.backward()
-        if world > 1:
-            dist.all_reduce(fp.grad)                         # the step's ONE collective: flat fp32 gradient
-        fp.set_hyper(grad_scale=1.0 / world)
-        fp.step()
-        return loss
+    from act_b200.engine import PretrainStep
+    eng = PretrainStep(model, fp, B, N_POINTS, use_graph=not args.no_graph, device=dev).capture()
+
+    def step(points):                                        # batch already resident in HBM
+        return eng.run(points)
 
     def step_e2e(i):
-        stage.copy_(host[i % n_batches], non_blocking=True)  # H2D from pinned memory, inside the timed region
-        loss = step(stage)
-        loss_host.copy_(loss.detach(), non_blocking=True)    # D2H of the step's result
+        loss = eng.run(host[i % n_batches])                  # pinned HOST batch: H2D inside the timed region
+        loss_host.copy_(loss, non_blocking=True)             # D2H of the step's result
         return loss
 
     def barrier():
@@ -181,7 +173,7 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = ops.LAUNCHES
     ms_step, wall = timed(lambda i: step(resident[i % n_batches]), args.steps)
-    launches = (ops.LAUNCHES - l0) // args.steps
+    launches = eng.launches_per_step
     ms_e2e, _ = timed(step_e2e, args.steps)
     clocks = sampler.stop() if sampler else None
     last_loss = float(loss_host.item())
@@ -208,7 +200,8 @@ def run_ours(args):
         layers.ops.gemm = timed_gemm
         try:
             for i in range(2):
-                step(resident[i % n_batches])
+                eng._host_prologue(resident[i % n_batches])
+                eng._body()                                  # eager (not the graph) so each GEMM gets its event pair
             torch.cuda.synchronize()
         finally:
             ops.gemm = orig
@@ -234,8 +227,9 @@ def run_ours(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": workload_cfg(B, world), "impl": "ours",
                 "e2e": {"value": round(clouds / (ms_e2e * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms_e2e, 4),
-                        "h2d_bytes_per_step": int(stage.numel() * 4), "d2h_bytes_per_step": 4},
-                "gpu_launches": int(launches), "loss": last_loss, "wall_s_timed": round(wall, 3),
+                        "h2d_bytes_per_step": int(host[0].numel() * 4 + B * N_GROUP + 32), "d2h_bytes_per_step": 4},
+                "gpu_launches": int(launches), "cuda_graph": not args.no_graph, "loss": last_loss,
+                "wall_s_timed": round(wall, 3),
                 "clocks": clocks, "roofline": roof}
         if cpu is not None:
             line["cpu_baseline"] = cpu
@@ -311,6 +305,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="clouds per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -85,13 +85,19 @@ int act_chamfer_backward(const float *xyz1, const float *xyz2, const int32_t *id
  * + resid[m / resid_row_div, ldr] (f32; may alias out when resid_row_div == 1; resid_row_div = group_size
  * broadcasts a per-group term over the group's points: the hoisted "global feature" half of the mini-PointNet's
  * third conv, models/dvae.py:211-213);  out bf16 (out_fp32 = 0) or f32 (1), pitch ldo.
+ * gmax_f32 / gmax_bf16 / garg (nullable, [M/32, ldg]): fused torch.max(feature, dim=2) of the mini-PointNet
+ * (models/dvae.py:211,214) for group_size 32 -- max over each 32 consecutive rows of (acc + bias) taken on the
+ * fp32 accumulators, and the winning row (first on ties); `out` may then be NULL (conv4: only the max is kept).
  * splits > 1: split-K, fp32 atomic accumulation into out (caller zeroes it; no other epilogue parts).
+ * persistent: 1 = one CTA per SM looping over tiles with a double-buffered TMEM accumulator (many-tile GEMMs),
+ * 0 = one tile per CTA, -1 = choose.
  * block_n: 64 / 128 output-tile width (0 = choose).  Requirements: N % 8 == 0, K % 8 == 0 pitches,
  * 16-byte aligned pointers. */
 int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, int a_mn_major, int b_mn_major, int lda, int ldb,
                   void *out, int ldo, int out_fp32, const float *bias, int act_kind, void *preact_out,
                   const void *mul_in, int ldm, int mul_mode, const float *resid, int ldr, int resid_row_div,
-                  const float *row_scale, int rows_per_scale, float alpha, int splits, int block_n, void *stream);
+                  const float *row_scale, int rows_per_scale, float *gmax_f32, void *gmax_bf16, uint8_t *garg, int ldg,
+                  float alpha, int splits, int block_n, int persistent, void *stream);
 
 /* ---- Transformer Block pieces (models/act.py:45-90, 109-112) ------------------------------------------ */
 
@@ -148,6 +154,8 @@ int act_group_max_bwd(const float *dout, const uint8_t *arg, int G, int k, int C
                       void *stream);
 /* sum over the k rows of each group (backward of the expand() of the global feature, dvae.py:212). */
 int act_group_sum(const void *x_bf16, int G, int k, int C, void *out_bf16, float *out_f32, void *stream);
+/* out[C] += column sums of a dense bf16 [M,C] matrix (C % 8 == 0, C <= 2048): bias gradients of the convs. */
+int act_colsum_bf16_dense(const void *x_bf16, long long M, int C, float *out, void *stream);
 /* BatchNorm1d (train mode) statistics of x bf16 [M,C]: sum[C], sumsq[C] (f32, zeroed here). */
 int act_bn_stats(const void *x_bf16, long long M, int C, float *sum, float *sumsq, void *stream);
 /* y = relu?(x * scale[c] + shift[c]) (normalise + affine folded into scale/shift by the caller). */

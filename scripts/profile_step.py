@@ -1,0 +1,39 @@
+"""One profiled Stage-II step for ncu: warm up, then bracket ONE step (or N) with cudaProfilerStart/Stop.
+  ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+      --log-file gpurun_out/launches.csv python scripts/profile_step.py [steps] [batch]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from act_b200 import layers, models  # noqa: E402
+from oracle.ref_model import synthetic_clouds  # noqa: E402  (input generator)
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+torch.manual_seed(0)
+np.random.seed(0)
+model = models.ACT_PointDistillation(models.default_config(0.6, 0.1)).cuda().train()
+fp = layers.FlatParams(model)
+pts = synthetic_clouds(B, 1024).cuda()
+
+
+def step():
+    fp.zero_grad()
+    loss = model(pts)
+    loss.backward()
+    fp.set_hyper()
+    fp.step()
+    return loss
+
+
+for _ in range(3):
+    step()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()
+for _ in range(steps):
+    step()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()

@@ -94,3 +94,57 @@ def test_gemm_strided_views():
     ops.gemm(a, w, out=out_big[:, 128:512])
     check(out_big[:, 128:512], a.float() @ w.float().t(), True)
     assert (out_big[:, :128] == 0).all() and (out_big[:, 512:] == 0).all()
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(262144, 256, 128, 0), (65536, 512, 256, 256), (65536, 384, 512, 128),
+                                      (40000, 512, 512, 256), (128 * 700, 128, 64, 128)])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+def test_gemm_persistent(M, N, K, bn, a_mn, b_mn):
+    """Persistent kernel (one CTA per SM, double-buffered TMEM accumulator) vs the PyTorch reference and vs the
+    one-tile-per-CTA kernel."""
+    torch.manual_seed(N + K)
+    a, b = rnd(M, K), rnd(N, K, scale=0.2)
+    bias = torch.randn(N, device="cuda")
+    A = a.t().contiguous() if a_mn else a
+    B = b.t().contiguous() if b_mn else b
+    got = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, bias=bias, act=ops.ACT_RELU, block_n=bn, persistent=1)
+    ref = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, bias=bias, act=ops.ACT_RELU, persistent=0)
+    assert torch.equal(got, ref)
+    sl = slice(0, M, 37)
+    check(got[sl], torch.relu(a[sl].float() @ b.float().t() + bias), True)
+
+
+def test_gemm_persistent_splitk_wgrad():
+    torch.manual_seed(5)
+    T, N, K = 262144, 384, 512
+    dy, x = rnd(T, N, scale=0.05), rnd(T, K)
+    want = dy.float().t() @ x.float()
+    for persistent in (0, 1):
+        got = ops.gemm(dy, x, a_mn=True, b_mn=True, out_dtype=torch.float32, splits=ops.wgrad_splits(N, K, T),
+                       persistent=persistent)
+        check(got, want, False)
+
+
+@pytest.mark.parametrize("persistent", [0, 1])
+def test_gemm_fused_group_max(persistent):
+    """Fused max over each 32 consecutive rows on the fp32 accumulators (+ arg-max), with and without `out`."""
+    torch.manual_seed(6)
+    G, N, K = 4100, 384, 512
+    M = G * 32
+    a, w = rnd(M, K), rnd(N, K, scale=0.1)
+    bias = torch.randn(N, device="cuda")
+    full = a.float() @ w.float().t() + bias
+    v, i = full.view(G, 32, N).max(1)
+    gf = torch.empty(G, N, device="cuda")
+    gb = torch.empty(G, N, dtype=torch.bfloat16, device="cuda")
+    ga = torch.empty(G, N, dtype=torch.uint8, device="cuda")
+    out = ops.gemm(a, w, bias=bias, gmax_f32=gf, gmax_bf16=gb, garg=ga, persistent=persistent)
+    check(out, full, True)
+    torch.testing.assert_close(gf, v, rtol=1e-4, atol=1e-4)
+    assert torch.equal(gb, gf.bfloat16())
+    picked = torch.gather(full.view(G, 32, N), 1, ga.long()[:, None]).squeeze(1)
+    torch.testing.assert_close(picked, v, rtol=1e-4, atol=1e-4)       # arg points at a (near-)maximal row
+    assert (ga.long() == i).float().mean().item() > 0.999
+    gf2 = torch.zeros(G, N, device="cuda")
+    assert ops.gemm(a, w, bias=bias, gmax_f32=gf2, no_out=True, persistent=persistent) is None
+    assert torch.equal(gf2, gf)
