@@ -131,9 +131,35 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
     return cdf + x * pdf;
 }
 
+// ------------------------------------------------------------------------------------------ epilogue
 // One 32-column chunk of one accumulator row per thread (lane = row within the warp's 32-row slab).
-__device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_t (&v)[32], int row, bool row_ok,
-                                               int n, int N, int lane) {
+// Operands that do not depend on the accumulator (the residual row / the mul_in row) are PREFETCHED into
+// registers by epi_prefetch() before the accumulator is waited for -- for the next chunk while the current one
+// is processed -- because with one row per thread every such load is a full L2 round trip on the critical path.
+struct EpiPre {
+    uint4 r[8];   // 128 B: either 32 f32 of the residual row or 32 bf16 of mul_in in r[0..3]
+};
+
+__device__ __forceinline__ void epi_prefetch(const GemmEpi &epi, EpiPre &pre, int row, bool row_ok, int n, int N) {
+    if (!row_ok || n >= N) return;
+    const int ncols = min(32, N - n);
+    if (epi.mul_mode) {
+        const uint4 *mi = reinterpret_cast<const uint4 *>(epi.mul_in + (size_t)row * epi.ldm + n);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j * 8 < ncols) pre.r[j] = __ldg(mi + j);
+    } else if (epi.resid) {
+        const uint4 *rp =
+            reinterpret_cast<const uint4 *>(epi.resid + (size_t)(row / epi.resid_row_div) * epi.ldr + n);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j * 4 < ncols) pre.r[j] = rp[j];          // plain load: resid may alias out
+    }
+}
+
+// gscratch: per-warp shared scratch [32][33] floats for the transposed group max (nullable -> redux path)
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_t (&v)[32], const EpiPre &pre, int row,
+                                               bool row_ok, int n, int N, int lane, float *gscratch) {
     if (n >= N) return;                       // warp-uniform
     const bool gmode = epi.gmax_f32 || epi.gmax_bf16 || epi.garg;
     if (!row_ok && !gmode) return;
@@ -141,37 +167,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * epi.alpha;
     const int ncols = min(32, N - n);   // N % 8 == 0 guaranteed by the host
-    if (gmode) {
-        // bias, then the group max (bias is per column, so max(x) + b == max(x + b)); rows >= M never win
-        if (epi.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                if (j < ncols) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4 *>(epi.bias + n + j));
-                    f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-                }
-            }
-        }
-        uint32_t my_max = 0, my_arg = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const uint32_t b = __float_as_uint(f[j]);
-            const uint32_t u = row_ok ? ((b & 0x80000000u) ? ~b : (b | 0x80000000u)) : 0u;   // order-preserving map
-            const uint32_t mx = __reduce_max_sync(0xffffffffu, u);
-            const uint32_t ar = __reduce_min_sync(0xffffffffu, u == mx ? (uint32_t)lane : 32u);
-            if (lane == j) { my_max = mx; my_arg = ar; }
-        }
-        const bool any_ok = __any_sync(0xffffffffu, row_ok);
-        if (lane < ncols && any_ok) {
-            const uint32_t b = (my_max & 0x80000000u) ? (my_max & 0x7fffffffu) : ~my_max;
-            const float best = __uint_as_float(b);
-            const size_t o = (size_t)(row >> 5) * epi.ldg + n + lane;
-            if (epi.gmax_f32) epi.gmax_f32[o] = best;
-            if (epi.gmax_bf16) epi.gmax_bf16[o] = __float2bfloat16_rn(best);
-            if (epi.garg) epi.garg[o] = (uint8_t)my_arg;
-        }
-        if (!epi.out || !row_ok) return;
-    } else if (epi.bias) {
+    if (epi.bias) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
             if (j < ncols) {
@@ -179,6 +175,46 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_
                 f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
             }
         }
+    }
+    if (gmode) {
+        // max over the warp's 32 rows of (acc + bias), per column; rows >= M never win; first row wins ties
+        float best;
+        int barg;
+        const bool any_ok = __any_sync(0xffffffffu, row_ok);
+        if (gscratch) {
+            // transpose through shared memory: lane = row writes its 32 columns (pitch 33: conflict-free), then
+            // lane = column scans the 32 rows
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) gscratch[lane * 33 + j] = row_ok ? f[j] : -INFINITY;
+            __syncwarp();
+            best = gscratch[lane];
+            barg = 0;
+#pragma unroll
+            for (int r = 1; r < 32; ++r) {
+                const float x = gscratch[r * 33 + lane];
+                if (x > best) { best = x; barg = r; }
+            }
+        } else {
+            uint32_t my_max = 0, my_arg = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const uint32_t bb = __float_as_uint(f[j]);
+                const uint32_t u = row_ok ? ((bb & 0x80000000u) ? ~bb : (bb | 0x80000000u)) : 0u;
+                const uint32_t mx = __reduce_max_sync(0xffffffffu, u);
+                const uint32_t ar = __reduce_min_sync(0xffffffffu, u == mx ? (uint32_t)lane : 32u);
+                if (lane == j) { my_max = mx; my_arg = ar; }
+            }
+            best = __uint_as_float((my_max & 0x80000000u) ? (my_max & 0x7fffffffu) : ~my_max);
+            barg = (int)my_arg;
+        }
+        if (lane < ncols && any_ok) {
+            const size_t o = (size_t)(row >> 5) * epi.ldg + n + lane;
+            if (epi.gmax_f32) epi.gmax_f32[o] = best;
+            if (epi.gmax_bf16) epi.gmax_bf16[o] = __float2bfloat16_rn(best);
+            if (epi.garg) epi.garg[o] = (uint8_t)barg;
+        }
+        if (!epi.out || !row_ok) return;
     }
     if (epi.preact_out) {
         __nv_bfloat16 *po = reinterpret_cast<__nv_bfloat16 *>(epi.preact_out) + (size_t)row * epi.ldo + n;
@@ -201,12 +237,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_
         for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
     }
     if (epi.mul_mode) {
-        const __nv_bfloat16 *mi = epi.mul_in + (size_t)row * epi.ldm + n;
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
             if (j < ncols) {
-                const uint4 pk = __ldg(reinterpret_cast<const uint4 *>(mi + j));
-                const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&pk);
+                const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&pre.r[j >> 3]);
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const float2 u = __bfloat1622float2(h[t]);
@@ -227,12 +261,24 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_
         for (int j = 0; j < 32; ++j) f[j] *= rsc;
     }
     if (epi.resid) {
-        const float *r = epi.resid + (size_t)(row / epi.resid_row_div) * epi.ldr + n;
+        if (!epi.mul_mode) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            if (j < ncols) {
-                const float4 r4 = *reinterpret_cast<const float4 *>(r + j);
-                f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+            for (int j = 0; j < 32; j += 4) {
+                if (j < ncols) {
+                    const uint4 r4 = pre.r[j >> 2];
+                    f[j] += __uint_as_float(r4.x); f[j + 1] += __uint_as_float(r4.y);
+                    f[j + 2] += __uint_as_float(r4.z); f[j + 3] += __uint_as_float(r4.w);
+                }
+            }
+        } else {
+            // the rare resid + mul_in combination: direct loads
+            const float *r = epi.resid + (size_t)(row / epi.resid_row_div) * epi.ldr + n;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                if (j < ncols) {
+                    const float4 r4 = *reinterpret_cast<const float4 *>(r + j);
+                    f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+                }
             }
         }
     }
@@ -351,11 +397,14 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_co
         // epilogue warps 2..5 -> TMEM lane quadrant warp % 4
         const int quad = warp & 3;
         const int row = m0 + quad * 32 + lane;
+        const bool row_ok = row < M;
+        EpiPre cur, nxt;
+        epi_prefetch(epi, cur, row, row_ok, n0, N);             // overlaps the whole main loop
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
-        const bool row_ok = row < M;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
+            if (c0 + 32 < BN) epi_prefetch(epi, nxt, row, row_ok, n0 + c0 + 32, N);
             uint32_t v[32];
             __syncwarp();
             if (nkb > 0) {
@@ -364,7 +413,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_co
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0u;
             }
-            epilogue_chunk(epi, v, row, row_ok, n0 + c0, N, lane);
+            epilogue_chunk(epi, v, cur, row, row_ok, n0 + c0, N, lane, nullptr);
+            cur = nxt;
         }
     }
     tc_fence_before();
@@ -480,21 +530,31 @@ __global__ void __launch_bounds__(GEMM_P_THREADS, 1) gemm_bf16_persistent_kernel
     } else {
         const int e = warp - 2;
         const int quad = warp & 3, half = e >> 2;
+        // per-warp [32][33] fp32 scratch for the transposed group max, carved after the pipeline stages
+        float *gscratch = (epi.gmax_f32 || epi.gmax_bf16 || epi.garg)
+                              ? reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES) + e * (32 * 33)
+                              : nullptr;
         uint32_t lt = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
             const int n0 = (t % tiles_n) * BN, m0 = ((t / tiles_n) % tiles_m) * GEMM_BM;
             const uint32_t buf = lt & 1;
             const int row = m0 + quad * 32 + lane;
             const bool row_ok = row < M;
+            constexpr int NCH = BN / 64;                              // 32-column chunks per epilogue warp
+            const int cbase = n0 + half * (BN / 2);
+            EpiPre cur, nxt;
+            epi_prefetch(epi, cur, row, row_ok, cbase, N);            // before the accumulator is waited for
             mbar_wait(&tfull_bar[buf], (lt >> 1) & 1);
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + buf * BN + ((uint32_t)(quad * 32) << 16);
+            const uint32_t tmem_d = tmem_base + buf * BN + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * (BN / 2));
 #pragma unroll 1
-            for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+            for (int c = 0; c < NCH; ++c) {
+                if (c + 1 < NCH) epi_prefetch(epi, nxt, row, row_ok, cbase + (c + 1) * 32, N);
                 uint32_t v[32];
                 __syncwarp();
-                tmem_ld32(tmem_d + (uint32_t)c0, v);
-                epilogue_chunk(epi, v, row, row_ok, n0 + c0, N, lane);
+                tmem_ld32(tmem_d + (uint32_t)(c * 32), v);
+                epilogue_chunk(epi, v, cur, row, row_ok, cbase + c * 32, N, lane, gscratch);
+                cur = nxt;
             }
             tc_fence_before();
             __syncwarp();
@@ -560,8 +620,8 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmE
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm_persistent(const CUtensorMap &ta, const CUtensorMap &tb, const GemmEpi &epi, int M, int N, int K,
                                   int splits, cudaStream_t st) {
-    constexpr int STAGES = BN == 128 ? 5 : 4;
-    constexpr size_t smem = (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024;
+    constexpr int STAGES = 4;
+    constexpr size_t smem = (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024 + 8 * 32 * 33 * 4;
     auto kern = gemm_bf16_persistent_kernel<BN, A_MN, B_MN, STAGES>;
     ACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int total_kb = (K + GEMM_BK - 1) / GEMM_BK;

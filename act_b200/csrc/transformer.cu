@@ -224,27 +224,14 @@ __global__ void __launch_bounds__(256) cast_rows_kernel(const float *__restrict_
 // qkv: bf16 [B*T, 3*H*64] (q | k | v, head-major inside each third, as nn.Linear(dim, 3*dim) + the
 // reference's reshape(B,N,3,H,C/H) lays it out).  Two lanes own one query row (32 of the 64 head dims each).
 constexpr int AT_D = 64;
-constexpr int AT_TILE = 64;   // keys per shared-memory tile
+constexpr int AT_PITCH = 72;   // fp32 row pitch in smem: [32 dims of half 0][4 pad][32 dims of half 1][4 pad]
+                               // -> the two lanes of a pair hit different banks on their LDS.128
 
 __device__ __forceinline__ void load_row32(const __nv_bfloat16 *src, float (&dst)[32]) {
     const uint4 *p = reinterpret_cast<const uint4 *>(src);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const uint4 u = __ldg(p + i);
-        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const float2 f = __bfloat1622float2(h[t]);
-            dst[i * 8 + 2 * t] = f.x;
-            dst[i * 8 + 2 * t + 1] = f.y;
-        }
-    }
-}
-__device__ __forceinline__ void lds_row32(const __nv_bfloat16 *src, float (&dst)[32]) {
-    const uint4 *p = reinterpret_cast<const uint4 *>(src);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint4 u = p[i];
         const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -265,11 +252,36 @@ __device__ __forceinline__ void store_row32(__nv_bfloat16 *dst, const float (&sr
         p[i] = u;
     }
 }
-// cooperative copy of `rows` rows x 64 bf16 (128 B each) from a strided global matrix into smem [rows][64]
-__device__ __forceinline__ void stage_rows(__nv_bfloat16 *dst, const __nv_bfloat16 *src, int ld, int rows) {
+// cooperative copy of `rows` rows x 64 bf16 from a strided global matrix into smem as FP32 [rows][AT_PITCH]
+// (converted once per CTA instead of once per consumer thread)
+__device__ __forceinline__ void stage_rows_f32(float *dst, const __nv_bfloat16 *src, int ld, int rows) {
     for (int i = threadIdx.x; i < rows * 8; i += blockDim.x) {
         const int r = i >> 3, c = i & 7;
-        reinterpret_cast<uint4 *>(dst)[i] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * ld) + c);
+        const uint4 u = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * ld) + c);
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+        const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+        const float2 f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
+        float *d = dst + r * AT_PITCH + c * 8 + (c >= 4 ? 4 : 0);
+        *reinterpret_cast<float4 *>(d) = make_float4(f0.x, f0.y, f1.x, f1.y);
+        *reinterpret_cast<float4 *>(d + 4) = make_float4(f2.x, f2.y, f3.x, f3.y);
+    }
+}
+// dot of a register row-half with a smem row-half, 4 independent accumulators
+__device__ __forceinline__ float dot32(const float (&a)[32], const float *b) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; d += 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(b + d);
+        s0 = fmaf(a[d], v.x, s0); s1 = fmaf(a[d + 1], v.y, s1); s2 = fmaf(a[d + 2], v.z, s2); s3 = fmaf(a[d + 3], v.w, s3);
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+__device__ __forceinline__ void axpy32(float (&acc)[32], float w, const float *b) {
+#pragma unroll
+    for (int d = 0; d < 32; d += 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(b + d);
+        acc[d] = fmaf(w, v.x, acc[d]); acc[d + 1] = fmaf(w, v.y, acc[d + 1]);
+        acc[d + 2] = fmaf(w, v.z, acc[d + 2]); acc[d + 3] = fmaf(w, v.w, acc[d + 3]);
     }
 }
 
@@ -278,10 +290,11 @@ template <int QT>
 __global__ void __launch_bounds__(QT * 2) attention_fwd_kernel(const __nv_bfloat16 *__restrict__ qkv, int T, int H,
                                                                float scale, __nv_bfloat16 *__restrict__ o,
                                                                float *__restrict__ lse) {
-    __shared__ __align__(16) __nv_bfloat16 s_k[AT_TILE][AT_D], s_v[AT_TILE][AT_D];
+    constexpr int TILE = QT <= 32 ? 32 : 64;   // rows of the other operand per smem tile
+    __shared__ __align__(16) float s_k[TILE * AT_PITCH], s_v[TILE * AT_PITCH];
     const int b = blockIdx.z, h = blockIdx.y;
     const int i = blockIdx.x * QT + (threadIdx.x >> 1), half = threadIdx.x & 1;
-    const int ld = 3 * H * AT_D;
+    const int ld = 3 * H * AT_D, ho = half * 36;
     const __nv_bfloat16 *base = qkv + (size_t)b * T * ld + h * AT_D;
     const bool act_q = i < T;
     float q[32], acc[32];
@@ -297,26 +310,36 @@ __global__ void __launch_bounds__(QT * 2) attention_fwd_kernel(const __nv_bfloat
 #pragma unroll
     for (int d = 0; d < 32; ++d) acc[d] = 0.f;
     float m = -INFINITY, l = 0.f;
-    for (int j0 = 0; j0 < T; j0 += AT_TILE) {
-        const int rows = min(AT_TILE, T - j0);
+    for (int j0 = 0; j0 < T; j0 += TILE) {
+        const int rows = min(TILE, T - j0);
         __syncthreads();
-        stage_rows(&s_k[0][0], base + (size_t)j0 * ld + H * AT_D, ld, rows);
-        stage_rows(&s_v[0][0], base + (size_t)j0 * ld + 2 * H * AT_D, ld, rows);
+        stage_rows_f32(s_k, base + (size_t)j0 * ld + H * AT_D, ld, rows);
+        stage_rows_f32(s_v, base + (size_t)j0 * ld + 2 * H * AT_D, ld, rows);
         __syncthreads();
-        for (int j = 0; j < rows; ++j) {
-            float kv[32];
-            lds_row32(&s_k[j][half * 32], kv);
-            float s = 0.f;
-#pragma unroll
-            for (int d = 0; d < 32; ++d) s = fmaf(q[d], kv[d], s);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            const float mn = fmaxf(m, s);
-            const float corr = exp2f(m - mn), p = exp2f(s - mn);
+        int j = 0;
+        for (; j + 1 < rows; j += 2) {      // two keys per iteration: independent score chains
+            float sa = dot32(q, s_k + j * AT_PITCH + ho), sb = dot32(q, s_k + (j + 1) * AT_PITCH + ho);
+            sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+            sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+            const float mn = fmaxf(m, fmaxf(sa, sb));
+            const float corr = exp2f(m - mn), pa = exp2f(sa - mn), pb = exp2f(sb - mn);
             m = mn;
-            l = l * corr + p;
-            lds_row32(&s_v[j][half * 32], kv);
+            l = fmaf(l, corr, pa + pb);
 #pragma unroll
-            for (int d = 0; d < 32; ++d) acc[d] = fmaf(acc[d], corr, p * kv[d]);
+            for (int d = 0; d < 32; ++d) acc[d] *= corr;
+            axpy32(acc, pa, s_v + j * AT_PITCH + ho);
+            axpy32(acc, pb, s_v + (j + 1) * AT_PITCH + ho);
+        }
+        if (j < rows) {
+            float sa = dot32(q, s_k + j * AT_PITCH + ho);
+            sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+            const float mn = fmaxf(m, sa);
+            const float corr = exp2f(m - mn), pa = exp2f(sa - mn);
+            m = mn;
+            l = fmaf(l, corr, pa);
+#pragma unroll
+            for (int d = 0; d < 32; ++d) acc[d] *= corr;
+            axpy32(acc, pa, s_v + j * AT_PITCH + ho);
         }
     }
     if (act_q) {
@@ -336,14 +359,16 @@ __global__ void __launch_bounds__(QT * 2) attention_bwd_dq_kernel(const __nv_bfl
                                                                   const float *__restrict__ lse, int T, int H,
                                                                   float scale, __nv_bfloat16 *__restrict__ dqkv,
                                                                   float *__restrict__ delta) {
-    __shared__ __align__(16) __nv_bfloat16 s_k[AT_TILE][AT_D], s_v[AT_TILE][AT_D];
+    constexpr int TILE = QT <= 32 ? 32 : 64;   // rows of the other operand per smem tile
+    __shared__ __align__(16) float s_k[TILE * AT_PITCH], s_v[TILE * AT_PITCH];
     const int b = blockIdx.z, h = blockIdx.y;
     const int i = blockIdx.x * QT + (threadIdx.x >> 1), half = threadIdx.x & 1;
-    const int ld = 3 * H * AT_D, ldo = H * AT_D;
+    const int ld = 3 * H * AT_D, ldo = H * AT_D, ho = half * 36;
     const __nv_bfloat16 *base = qkv + (size_t)b * T * ld + h * AT_D;
     const bool act_q = i < T;
     float q[32], g[32], dq[32];
     float D = 0.f, L = 0.f;
+    const float sl2 = scale * 1.4426950408889634f;
     if (act_q) {
         load_row32(base + (size_t)i * ld + half * 32, q);
         load_row32(dO + ((size_t)b * T + i) * ldo + h * AT_D + half * 32, g);
@@ -351,7 +376,9 @@ __global__ void __launch_bounds__(QT * 2) attention_bwd_dq_kernel(const __nv_bfl
         load_row32(o + ((size_t)b * T + i) * ldo + h * AT_D + half * 32, ov);
 #pragma unroll
         for (int d = 0; d < 32; ++d) D = fmaf(g[d], ov[d], D);
-        L = __ldg(lse + ((size_t)b * H + h) * T + i);
+        L = __ldg(lse + ((size_t)b * H + h) * T + i) * 1.4426950408889634f;
+#pragma unroll
+        for (int d = 0; d < 32; ++d) q[d] *= sl2;
     } else {
 #pragma unroll
         for (int d = 0; d < 32; ++d) q[d] = g[d] = 0.f;
@@ -360,28 +387,18 @@ __global__ void __launch_bounds__(QT * 2) attention_bwd_dq_kernel(const __nv_bfl
     if (act_q && half == 0) delta[((size_t)b * H + h) * T + i] = D;
 #pragma unroll
     for (int d = 0; d < 32; ++d) dq[d] = 0.f;
-    for (int j0 = 0; j0 < T; j0 += AT_TILE) {
-        const int rows = min(AT_TILE, T - j0);
+    for (int j0 = 0; j0 < T; j0 += TILE) {
+        const int rows = min(TILE, T - j0);
         __syncthreads();
-        stage_rows(&s_k[0][0], base + (size_t)j0 * ld + H * AT_D, ld, rows);
-        stage_rows(&s_v[0][0], base + (size_t)j0 * ld + 2 * H * AT_D, ld, rows);
+        stage_rows_f32(s_k, base + (size_t)j0 * ld + H * AT_D, ld, rows);
+        stage_rows_f32(s_v, base + (size_t)j0 * ld + 2 * H * AT_D, ld, rows);
         __syncthreads();
         for (int j = 0; j < rows; ++j) {
-            float kr[32], vr[32];
-            lds_row32(&s_k[j][half * 32], kr);
-            lds_row32(&s_v[j][half * 32], vr);
-            float s = 0.f, dp = 0.f;
-#pragma unroll
-            for (int d = 0; d < 32; ++d) {
-                s = fmaf(q[d], kr[d], s);
-                dp = fmaf(g[d], vr[d], dp);
-            }
+            float s = dot32(q, s_k + j * AT_PITCH + ho), dp = dot32(g, s_v + j * AT_PITCH + ho);
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             dp += __shfl_xor_sync(0xffffffffu, dp, 1);
-            const float p = __expf(s * scale - L);
-            const float ds = p * (dp - D) * scale;
-#pragma unroll
-            for (int d = 0; d < 32; ++d) dq[d] = fmaf(ds, kr[d], dq[d]);
+            const float p = exp2f(s - L);
+            axpy32(dq, p * (dp - D) * scale, s_k + j * AT_PITCH + ho);
         }
     }
     if (act_q) store_row32(dqkv + ((size_t)b * T + i) * ld + h * AT_D + half * 32, dq);
@@ -394,52 +411,44 @@ __global__ void __launch_bounds__(QT * 2) attention_bwd_dkv_kernel(const __nv_bf
                                                                    const float *__restrict__ lse,
                                                                    const float *__restrict__ delta, int T, int H,
                                                                    float scale, __nv_bfloat16 *__restrict__ dqkv) {
-    __shared__ __align__(16) __nv_bfloat16 s_q[AT_TILE][AT_D], s_g[AT_TILE][AT_D];
-    __shared__ float s_l[AT_TILE], s_d[AT_TILE];
+    constexpr int TILE = QT <= 32 ? 32 : 64;
+    __shared__ __align__(16) float s_q[TILE * AT_PITCH], s_g[TILE * AT_PITCH];
+    __shared__ float s_l[TILE], s_d[TILE];
     const int b = blockIdx.z, h = blockIdx.y;
     const int j = blockIdx.x * QT + (threadIdx.x >> 1), half = threadIdx.x & 1;
-    const int ld = 3 * H * AT_D, ldo = H * AT_D;
+    const int ld = 3 * H * AT_D, ldo = H * AT_D, ho = half * 36;
     const __nv_bfloat16 *base = qkv + (size_t)b * T * ld + h * AT_D;
     const bool act_k = j < T;
     float kr[32], vr[32], dk[32], dv[32];
+    const float sl2 = scale * 1.4426950408889634f;
     if (act_k) {
         load_row32(base + (size_t)j * ld + H * AT_D + half * 32, kr);
         load_row32(base + (size_t)j * ld + 2 * H * AT_D + half * 32, vr);
+#pragma unroll
+        for (int d = 0; d < 32; ++d) kr[d] *= sl2;
     } else {
 #pragma unroll
         for (int d = 0; d < 32; ++d) kr[d] = vr[d] = 0.f;
     }
 #pragma unroll
     for (int d = 0; d < 32; ++d) dk[d] = dv[d] = 0.f;
-    for (int i0 = 0; i0 < T; i0 += AT_TILE) {
-        const int rows = min(AT_TILE, T - i0);
+    for (int i0 = 0; i0 < T; i0 += TILE) {
+        const int rows = min(TILE, T - i0);
         __syncthreads();
-        stage_rows(&s_q[0][0], base + (size_t)i0 * ld, ld, rows);
-        stage_rows(&s_g[0][0], dO + ((size_t)b * T + i0) * ldo + h * AT_D, ldo, rows);
+        stage_rows_f32(s_q, base + (size_t)i0 * ld, ld, rows);
+        stage_rows_f32(s_g, dO + ((size_t)b * T + i0) * ldo + h * AT_D, ldo, rows);
         for (int r = threadIdx.x; r < rows; r += blockDim.x) {
-            s_l[r] = __ldg(lse + ((size_t)b * H + h) * T + i0 + r);
+            s_l[r] = __ldg(lse + ((size_t)b * H + h) * T + i0 + r) * 1.4426950408889634f;
             s_d[r] = __ldg(delta + ((size_t)b * H + h) * T + i0 + r);
         }
         __syncthreads();
         for (int i = 0; i < rows; ++i) {
-            float qr[32], gr[32];
-            lds_row32(&s_q[i][half * 32], qr);
-            lds_row32(&s_g[i][half * 32], gr);
-            float s = 0.f, dp = 0.f;
-#pragma unroll
-            for (int d = 0; d < 32; ++d) {
-                s = fmaf(qr[d], kr[d], s);
-                dp = fmaf(gr[d], vr[d], dp);
-            }
+            float s = dot32(kr, s_q + i * AT_PITCH + ho), dp = dot32(vr, s_g + i * AT_PITCH + ho);
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             dp += __shfl_xor_sync(0xffffffffu, dp, 1);
-            const float p = __expf(s * scale - s_l[i]);
-            const float ds = p * (dp - s_d[i]) * scale;
-#pragma unroll
-            for (int d = 0; d < 32; ++d) {
-                dv[d] = fmaf(p, gr[d], dv[d]);
-                dk[d] = fmaf(ds, qr[d], dk[d]);
-            }
+            const float p = exp2f(s - s_l[i]);
+            axpy32(dv, p, s_g + i * AT_PITCH + ho);
+            axpy32(dk, p * (dp - s_d[i]) * scale, s_q + i * AT_PITCH + ho);
         }
     }
     if (act_k) {
