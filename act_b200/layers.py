@@ -17,10 +17,47 @@ return None for those inputs.  Without FlatParams the Functions cast weights on 
 the normal autograd way, so the modules also work inside a stock PyTorch training loop / DDP.
 """
 import math
+import os
 
 import torch
 
 from . import ops
+
+
+class _SideStream:
+    """Weight-gradient work (wgrad GEMMs, bias column sums) is off the critical path of a backward pass: only
+    the dgrad chain feeds the next layer.  It is issued on a second CUDA stream, forked after the dY it needs
+    and joined once at the end of the Function's backward, so inside the captured graph the wgrads run
+    CONCURRENTLY with the latency-bound dgrad / LayerNorm / attention kernels of the following layers."""
+    _streams = {}
+    enabled = os.environ.get("ACT_B200_SIDE_STREAM", "1") != "0"
+
+    def __init__(self, device):
+        self.main = torch.cuda.current_stream(device)
+        self.side = None
+        if _SideStream.enabled:
+            key = (device.index, self.main.cuda_stream)
+            if key not in _SideStream._streams:
+                _SideStream._streams[key] = torch.cuda.Stream(device=device)
+            self.side = _SideStream._streams[key]
+        self.used = False
+
+    def run(self, fn, *tensors):
+        """fn() launches kernels reading `tensors` (already produced on the main stream)."""
+        if self.side is None:
+            fn()
+            return
+        self.side.wait_stream(self.main)
+        for t in tensors:
+            if t is not None:
+                t.record_stream(self.side)
+        with torch.cuda.stream(self.side):
+            fn()
+        self.used = True
+
+    def join(self):
+        if self.side is not None and self.used:
+            self.main.wait_stream(self.side)
 
 
 def shadow(p):
@@ -169,6 +206,7 @@ class TransformerStack(torch.autograd.Function):
         params, saved = tensors[:depth * NP], tensors[depth * NP:]
         gates = ctx.gates
         sink = _GradSink()
+        side = _SideStream(dy.device)
         dx = dy.reshape(M, C).contiguous().float()
         dpos = torch.zeros(M, C, dtype=torch.float32, device=dy.device) if has_pos else None
         g = None
@@ -181,19 +219,19 @@ class TransformerStack(torch.autograd.Function):
             G = lambda p, k: sink.get(p, (l, k))  # noqa: E731
             if g is None:       # top of the stack: the incoming gradient is plain fp32
                 g = ops.cast_rows(dx, gate2, T, dbias=G(b2, 10))
-            # MLP branch
-            ops.wgrad(g, a, G(w2, 9))
+            # MLP branch (weight / bias gradients go to the side stream)
+            gw2, gw1, gb1, gwp, gwq = G(w2, 9), G(w1, 7), G(b1, 8), G(wproj, 3), G(wqkv, 2)
+            side.run(lambda: ops.wgrad(g, a, gw2), g)
             du = ops.gemm(g, shadow(w2), b_mn=True, mul_in=u, mul_mode=ops.MUL_GELU_GRAD)
-            ops.wgrad(du, h2, G(w1, 7))
-            ops.colsum(du, G(b1, 8))
+            side.run(lambda: (ops.wgrad(du, h2, gw1), ops.colsum(du, gb1)), du)
             dh2 = ops.gemm(du, shadow(w1), b_mn=True)
             dxm, g2 = ops.layernorm_bwd(dh2, xmid, mean2, rstd2, n2w, G(n2w, 5), G(n2b, 6), dres=dx, want_bf16=True,
                                         row_scale=gate1, rows_per_scale=T, dbias=G(bproj, 4))
             # attention branch
-            ops.wgrad(g2, o, G(wproj, 3))
+            side.run(lambda: ops.wgrad(g2, o, gwp), g2)
             do = ops.gemm(g2, shadow(wproj), b_mn=True)
             dqkv = ops.attention_bwd(qkv, o, do, lse, B, T, H, scale)
-            ops.wgrad(dqkv, h1, G(wqkv, 2))
+            side.run(lambda: ops.wgrad(dqkv, h1, gwq), dqkv)
             dh1 = ops.gemm(dqkv, shadow(wqkv), b_mn=True)
             if l > 0:           # this LayerNorm backward also emits the gated bf16 dY (+ bias grad) of Block l-1's fc2
                 pb2 = params[(l - 1) * NP + 10]
@@ -203,6 +241,7 @@ class TransformerStack(torch.autograd.Function):
                                           dbias=sink.get(pb2, (l - 1, 10)))
             else:
                 dx, _ = ops.layernorm_bwd(dh1, xs, mean1, rstd1, n1w, G(n1w, 0), G(n1b, 1), dres=dxm, dacc=dpos)
+        side.join()
         pgrads = [sink.result((l, k)) for l in range(depth) for k in range(NP)]
         return (dx.view(B, T, C), dpos.view(B, T, C) if has_pos else None, None, None, None, *pgrads)
 
@@ -307,7 +346,12 @@ class PointNetEncoderFn(torch.autograd.Function):
     hoisted: W3[:, :256] . global (per GROUP) is added to W3[:, 256:] . local (per point) in the GEMM epilogue."""
 
     @staticmethod
-    def forward(ctx, nb, training, momentum, eps, bufs, w1, b1, g1, be1, w2, b2, w3, b3, g2, be2, w4, b4):
+    def forward(ctx, nb, training, momentum, eps, bufs, n_keep, w1, b1, g1, be1, w2, b2, w3, b3, g2, be2, w4, b4):
+        # nb [B,G,k,3] or flattened [BG,k,3]; n_keep (None = all): only the first n_keep groups' tokens are
+        # produced -- conv4 and everything downstream of BatchNorm2 skip the other groups' rows (their tokens are
+        # dead values when the caller drops masked groups), while both BatchNorms still see every point.
+        if nb.dim() == 3:
+            nb = nb.unsqueeze(0)
         B, G, k, _ = nb.shape
         M = B * G * k
         p = nb.reshape(M, 3).contiguous().float()
@@ -357,54 +401,65 @@ class PointNetEncoderFn(torch.autograd.Function):
         sc2 = g2.double() * rstd2
         a3 = ops.bn_apply(h3, sc2.float(), (be2.double() - mean2 * sc2).float(), relu=True)   # [M,512]
         C = w4.shape[0]
+        GK = BG if n_keep is None else int(n_keep)
+        a3k = a3[:GK * k]
         if k == 32:      # conv4's [M,C] output is never written: only its per-group max (+ arg-max) leaves the SM
-            tokens = torch.empty(BG, C, dtype=torch.float32, device=p.device)
-            arg4 = torch.empty(BG, C, dtype=torch.uint8, device=p.device)
-            ops.gemm(a3, shadow(w4).view(C, 512), bias=b4, gmax_f32=tokens, garg=arg4, no_out=True)
+            tokens = torch.empty(GK, C, dtype=torch.float32, device=p.device)
+            arg4 = torch.empty(GK, C, dtype=torch.uint8, device=p.device)
+            ops.gemm(a3k, shadow(w4).view(C, 512), bias=b4, gmax_f32=tokens, garg=arg4, no_out=True)
         else:
-            f4 = ops.gemm(a3, shadow(w4).view(C, 512), bias=b4)                   # [M,C]
+            f4 = ops.gemm(a3k, shadow(w4).view(C, 512), bias=b4)                  # [GK*k,C]
             _, tokens, arg4 = ops.group_max(f4, k, want_bf16=False, want_f32=True)
         ctx.save_for_backward(p, a1, f2, gmax, arg2, h3, a3, arg4, mean1.float(), rstd1.float(), mean2.float(),
                               rstd2.float(), w1, b1, g1, be1, w2, b2, w3, b3, g2, be2, w4, b4)
-        ctx.meta = (B, G, k, C, training)
-        ctx.mark_non_differentiable(*[])
-        return tokens.view(B, G, C)
+        ctx.meta = (B, G, k, C, training, GK)
+        return tokens.view(B, G, C) if n_keep is None else tokens
 
     @staticmethod
     def backward(ctx, dtok):
         (p, a1, f2, gmax, arg2, h3, a3, arg4, mean1, rstd1, mean2, rstd2, w1, b1, g1, be1, w2, b2, w3, b3, g2, be2, w4,
          b4) = ctx.saved_tensors
-        B, G, k, C, training = ctx.meta
+        B, G, k, C, training, GK = ctx.meta
         if not training:
             raise RuntimeError("act_b200 Encoder: backward is implemented for train-mode BatchNorm only")
         sink = _GradSink()
         BG = B * G
-        d = dtok.reshape(BG, C).contiguous().float()
+        M = BG * k
+        side = _SideStream(dtok.device)
+        d = dtok.reshape(GK, C).contiguous().float()
         ops.colsum(d, sink.get(b4, "b4"))
-        dF4 = ops.group_max_bwd(d, arg4, k)                                       # [M,C] dense
-        ops.wgrad(dF4, a3, sink.get(w4, "w4").view(C, 512))
-        dZ3 = ops.gemm(dF4, shadow(w4).view(C, 512), b_mn=True, mul_in=a3, mul_mode=ops.MUL_RELU_MASK)
+        dF4 = ops.group_max_bwd(d, arg4, k)                                       # [GK*k,C] dense
+        a3k = a3[:GK * k]
+        gw4 = sink.get(w4, "w4").view(C, 512)
+        side.run(lambda: ops.wgrad(dF4, a3k, gw4), dF4)
+        if GK == BG:
+            dZ3 = ops.gemm(dF4, shadow(w4).view(C, 512), b_mn=True, mul_in=a3, mul_mode=ops.MUL_RELU_MASK)
+        else:            # rows of the dropped groups receive no gradient from conv4
+            dZ3 = torch.empty(M, 512, dtype=torch.bfloat16, device=d.device)
+            ops.gemm(dF4, shadow(w4).view(C, 512), b_mn=True, mul_in=a3k, mul_mode=ops.MUL_RELU_MASK,
+                     out=dZ3[:GK * k])
+            dZ3[GK * k:].zero_()
         dH3, dbe2, dg2 = ops.bn_bwd(dZ3, h3, mean2, rstd2, g2)
         sink.get(g2, "g2").add_(dg2)
         sink.get(be2, "be2").add_(dbe2)
         dGp_b, dGp_f = ops.group_sum(dH3, k, want_bf16=True, want_f32=True)       # [BG,512]
         sink.get(b3, "b3").add_(dGp_f.sum(0))
         gw3 = sink.get(w3, "w3").view(512, 512)
-        ops.wgrad(dH3, f2, gw3[:, 256:])
-        ops.wgrad(dGp_b, gmax, gw3[:, :256])
+        side.run(lambda: (ops.wgrad(dH3, f2, gw3[:, 256:]), ops.wgrad(dGp_b, gmax, gw3[:, :256])), dH3, dGp_b)
         w3s = shadow(w3).view(512, 512)
         dgmax = ops.gemm(dGp_b, w3s[:, :256], b_mn=True, out_dtype=torch.float32)  # [BG,256]
         dF2 = ops.gemm(dH3, w3s[:, 256:], b_mn=True)                              # [M,256]
         ops.group_max_bwd(dgmax, arg2, k, out=dF2)
-        ops.wgrad(dF2, a1, sink.get(w2, "w2").view(256, 128))
-        ops.colsum(dF2, sink.get(b2, "b2"))
+        gw2, gb2 = sink.get(w2, "w2").view(256, 128), sink.get(b2, "b2")
+        side.run(lambda: (ops.wgrad(dF2, a1, gw2), ops.colsum(dF2, gb2)), dF2)
         dZ1 = ops.gemm(dF2, shadow(w2).view(256, 128), b_mn=True, mul_in=a1, mul_mode=ops.MUL_RELU_MASK)
         dbe1, dg1 = ops.pn_conv1_bwd(dZ1, p, w1.view(128, 3).contiguous(), b1, mean1, rstd1, g1,
                                      sink.get(w1, "w1").view(128, 3), sink.get(b1, "b1"))
         sink.get(g1, "g1").add_(dg1)
         sink.get(be1, "be1").add_(dbe1)
+        side.join()
         r = sink.result
-        return (None, None, None, None, None, r("w1"), r("b1"), r("g1"), r("be1"), r("w2"), r("b2"), r("w3"), r("b3"),
+        return (None, None, None, None, None, None, r("w1"), r("b1"), r("g1"), r("be1"), r("w2"), r("b2"), r("w3"), r("b3"),
                 r("g2"), r("be2"), r("w4"), r("b4"))
 
 

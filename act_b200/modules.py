@@ -40,12 +40,14 @@ class Encoder(nn.Module):
         self.second_conv = nn.Sequential(nn.Conv1d(512, 512, 1), nn.BatchNorm1d(512), nn.ReLU(inplace=True),
                                          nn.Conv1d(512, self.encoder_channel, 1))
 
-    def forward(self, point_groups):
+    def forward(self, point_groups, n_keep=None):
+        """point_groups [B,G,k,3] -> [B,G,C] (the reference contract).  With n_keep (groups flattened to [BG,k,3],
+        the first n_keep of them wanted) -> [n_keep, C]: tokens of groups the caller discards are not computed."""
         c1, bn1, _, c2 = self.first_conv
         c3, bn2, _, c4 = self.second_conv
         bufs = (bn1.running_mean, bn1.running_var, bn1.num_batches_tracked, bn2.running_mean, bn2.running_var,
                 bn2.num_batches_tracked)
-        return layers.PointNetEncoderFn.apply(point_groups, self.training, bn1.momentum, bn1.eps, bufs, c1.weight,
+        return layers.PointNetEncoderFn.apply(point_groups, self.training, bn1.momentum, bn1.eps, bufs, n_keep, c1.weight,
                                               c1.bias, bn1.weight, bn1.bias, c2.weight, c2.bias, c3.weight, c3.bias,
                                               bn2.weight, bn2.bias, c4.weight, c4.bias)
 
@@ -229,14 +231,26 @@ class VisableOnlyMaskTransformer(nn.Module):
         if mask is None:
             mask = self._mask_center_rand(center, noaug=noaug)
         num_mask = 0 if (noaug or self.mask_ratio == 0) else int(self.mask_ratio * G)
-        tokens = self.encoder(neighborhood)
-        if not isinstance(self.reduce_dim, nn.Identity):
-            tokens = layers.linear(tokens, self.reduce_dim.weight, self.reduce_dim.bias)
-        C = tokens.shape[-1]
-        # visible tokens in original order == tokens[~mask].reshape(B,-1,C), via a stable argsort (no host sync)
+        # visible groups in original order == tokens[~mask].reshape(B,-1,C), via a stable argsort (no host sync)
         order = torch.argsort(mask.to(torch.uint8), dim=1, stable=True)
-        vis_idx = order[:, :G - num_mask]
-        x_vis = torch.gather(tokens, 1, vis_idx[..., None].expand(-1, -1, C))
+        n_vis = G - num_mask
+        vis_idx = order[:, :n_vis]
+        k = neighborhood.shape[2]
+        if num_mask > 0 and isinstance(self.reduce_dim, nn.Identity):
+            # The reference embeds all G groups and then throws the masked ones away (act.py:276-281).  Both
+            # BatchNorms need every point, but the last conv + max-pool only matter for visible groups: reorder
+            # the groups (all clouds' visible groups first) so that those rows are one contiguous prefix.
+            nb_sorted = torch.gather(neighborhood, 1, order[:, :, None, None].expand(-1, -1, k, 3))
+            nb_perm = torch.cat([nb_sorted[:, :n_vis].reshape(B * n_vis, k, 3),
+                                 nb_sorted[:, n_vis:].reshape(B * num_mask, k, 3)], dim=0)
+            x_vis = self.encoder(nb_perm, n_keep=B * n_vis).view(B, n_vis, -1)
+            C = x_vis.shape[-1]
+        else:
+            tokens = self.encoder(neighborhood)
+            if not isinstance(self.reduce_dim, nn.Identity):
+                tokens = layers.linear(tokens, self.reduce_dim.weight, self.reduce_dim.bias)
+            C = tokens.shape[-1]
+            x_vis = torch.gather(tokens, 1, vis_idx[..., None].expand(-1, -1, C))
         vis_center = torch.gather(center, 1, vis_idx[..., None].expand(-1, -1, 3))
         pos = pos_mlp(self.pos_embed, vis_center)
         x_vis = torch.cat((self.cls_token.expand(B, -1, -1), x_vis), dim=1)
