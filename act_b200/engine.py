@@ -3,8 +3,8 @@
 Reference hot loop: /root/reference/tools/runner_pretrain.py:130-157 (points.cuda(); loss = base_model(points);
 loss.backward(); optimizer.step(); zero_grad) -- ~460 kernel launches per step from Python, plus four O(B) host
 loops and several host<->device syncs.  Here the whole step -- Group tokenizer, mini-PointNet,
-encoder, decoder, loss, backward, gradient all-reduce (N>1) and the fused AdamW -- is captured once into a CUDA
-graph (CUDA streams and graphs instead of a tracing compiler) and replayed; per step the host only (a) draws the
+encoder, decoder, loss, backward and the fused AdamW -- is captured once into a CUDA
+graph (two graphs around the NCCL gradient all-reduce when N>1) (CUDA streams and graphs instead of a tracing compiler) and replayed; per step the host only (a) draws the
 random mask exactly as the reference does (numpy RNG, act.py:244-267) into a pinned buffer, (b) stages the AdamW
 scalars, (c) copies the batch into the graph's static input, (d) launches the graph.  Nothing synchronises.
 """
@@ -28,16 +28,25 @@ class PretrainStep:
         self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
         self.use_graph = use_graph
         self.graph = None
+        self.graph_b = None
         self.launches_per_step = None
 
-    # the device work of one step (capturable: no host sync, no pageable copy)
-    def _body(self):
+    # the device work of one step (capturable: no host sync, no pageable copy), in two halves so that for N>1 the
+    # step's one collective sits BETWEEN two graphs (NCCL's watchdog thread and stream capture do not mix safely;
+    # the all-reduce is one eager launch on the same stream, ordered after graph A and before graph B)
+    def _body_a(self):
         self.fp.zero_grad()
         loss = self.model(self.points, mask=self.mask)
         loss.backward()
-        dp.sync_gradients(self.fp)                  # N>1: the step's one collective (NCCL, captured in the graph)
-        self.fp.step()                              # fused AdamW (+ bf16 shadow refresh); scalars read from device
         self.loss.copy_(loss.detach())
+
+    def _body_b(self):
+        self.fp.step()                              # fused AdamW (+ bf16 shadow refresh); scalars read from device
+
+    def _body(self):
+        self._body_a()
+        dp.sync_gradients(self.fp)                  # N>1: flat fp32 gradient all-reduce (NCCL over NVLink)
+        self._body_b()
 
     def _host_prologue(self, points):
         m = mask_center_rand(self.B, self.G, self.mask_ratio, "cpu")
@@ -64,16 +73,27 @@ class PretrainStep:
         self.launches_per_step = (l1 - l0) // 2
         if self.use_graph:
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self._body()
+            if dp.world_size() == 1:
+                with torch.cuda.graph(self.graph):
+                    self._body()
+            else:
+                with torch.cuda.graph(self.graph):
+                    self._body_a()
+                self.graph_b = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_b, pool=self.graph.pool()):
+                    self._body_b()
         return self
 
     def run(self, points):
         """One training step on `points` ([B,N,3] f32: device tensor, or pinned host tensor).  Returns the (device,
         asynchronous) loss scalar of this step."""
         self._host_prologue(points)
-        if self.graph is not None:
+        if self.graph is None:
+            self._body()
+        elif self.graph_b is None:
             self.graph.replay()
         else:
-            self._body()
+            self.graph.replay()
+            dp.sync_gradients(self.fp)
+            self.graph_b.replay()
         return self.loss

@@ -100,6 +100,11 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- our arm
+def _log(msg):
+    if os.environ.get("ACT_BENCH_VERBOSE"):
+        print(f"[bench rank {os.environ.get('RANK', '0')} {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(args):
     import torch.distributed as dist
     from act_b200 import dp, layers, models, ops
@@ -114,6 +119,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    _log("process group up")
     B = args.batch
     torch.manual_seed(0)
     np.random.seed(1234 + rank)
@@ -130,7 +136,9 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     from act_b200.engine import PretrainStep
+    _log("model + flat params built; capturing")
     eng = PretrainStep(model, fp, B, N_POINTS, use_graph=not args.no_graph, device=dev).capture()
+    _log("captured")
 
     def step(points):                                        # batch already resident in HBM
         return eng.run(points)
@@ -170,11 +178,13 @@ def run_ours(args):
         step_e2e(i)
     barrier()
 
+    _log("warm-up done")
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = ops.LAUNCHES
     ms_step, wall = timed(lambda i: step(resident[i % n_batches]), args.steps)
     launches = eng.launches_per_step
     ms_e2e, _ = timed(step_e2e, args.steps)
+    _log("timed regions done")
     clocks = sampler.stop() if sampler else None
     last_loss = float(loss_host.item())
 
@@ -204,7 +214,8 @@ def run_ours(args):
                 # eager (not the graph) so each GEMM gets its own event pair; a ~40 ms device-side sleep first lets
                 # the host enqueue the whole step ahead of the GPU, so the pairs time kernels, not launch gaps
                 torch.cuda._sleep(80_000_000)
-                eng._body()
+                eng._body_a()
+                eng._body_b()
                 torch.cuda.synchronize()
         finally:
             ops.gemm = orig
