@@ -17,7 +17,46 @@
         if (e__ != cudaSuccess) return (int)e__;          \
     } while (0)
 
+#include <cstdlib>
+#include <utility>
+
 namespace act {
+
+// ---- Programmatic dependent launch (PDL) -------------------------------------------------------------------
+// The step is a chain of ~400 short, mutually dependent kernels; between two of them the GPU normally drains
+// completely (launch gap + prologue of the next kernel: barrier init, TMEM allocation, descriptor prefetch).
+// Kernels launched through launch_k() with pdl=true may start while their predecessor in the stream is still
+// running; they do their data-independent prologue, then pdl_wait() blocks until the predecessor has fully
+// completed and flushed (so every global read AND write sits after it), and pdl_trigger() lets their own
+// successor start early in turn.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static const int on = [] {
+        const char *e = std::getenv("ACT_B200_PDL");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    return on != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                            Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (pdl && pdl_enabled()) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(std::forward<Args>(args))...);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

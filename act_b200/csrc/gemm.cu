@@ -365,6 +365,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = tmem_slot;
+    pdl_wait();          // everything above overlapped the predecessor's tail; all global traffic is below
+    pdl_trigger();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -486,6 +488,8 @@ __global__ void __launch_bounds__(GEMM_P_THREADS, 1) gemm_bf16_persistent_kernel
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    pdl_wait();
+    pdl_trigger();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -631,8 +635,7 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmE
     const int kbps = (total_kb + splits - 1) / splits;
     const int nsplit = (total_kb + kbps - 1) / kbps;
     dim3 grid((N + BN - 1) / BN, (M + GEMM_BM - 1) / GEMM_BM, nsplit);
-    kern<<<grid, GEMM_THREADS, smem, st>>>(ta, tb, epi, M, N, K, kbps);
-    ACT_CHECK_LAUNCH();
+    ACT_CUDA(launch_k(kern, grid, dim3(GEMM_THREADS), smem, st, true, ta, tb, epi, M, N, K, kbps));
     return ACT_OK;
 }
 
@@ -652,8 +655,8 @@ static int launch_gemm_persistent(const CUtensorMap &ta, const CUtensorMap &tb, 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = (int)(total < sms ? total : sms);
-    kern<<<grid, GEMM_P_THREADS, smem, st>>>(ta, tb, epi, M, N, K, kbps, tiles_m, tiles_n, (int)total);
-    ACT_CHECK_LAUNCH();
+    ACT_CUDA(launch_k(kern, dim3(grid), dim3(GEMM_P_THREADS), smem, st, true, ta, tb, epi, M, N, K, kbps, tiles_m,
+                      tiles_n, (int)total));
     return ACT_OK;
 }
 

@@ -32,6 +32,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float *__restr
     constexpr int C = 128 * VPL;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    pdl_wait();
+    pdl_trigger();
     if (row >= M) return;
     const float4 *xr = reinterpret_cast<const float4 *>(x + (size_t)row * C);
     float4 v[VPL];
@@ -103,6 +105,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void *__restri
     float4 ag[VPL], ab[VPL], ac[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) ag[i] = ab[i] = ac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pdl_wait();
+    pdl_trigger();
     float4 gm[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) gm[i] = __ldg(reinterpret_cast<const float4 *>(gamma) + lane + 32 * i);
@@ -292,6 +296,8 @@ __global__ void __launch_bounds__(QT * 2) attention_fwd_kernel(const __nv_bfloat
                                                                float *__restrict__ lse) {
     constexpr int TILE = QT <= 32 ? 32 : 64;   // rows of the other operand per smem tile
     __shared__ __align__(16) float s_k[TILE * AT_PITCH], s_v[TILE * AT_PITCH];
+    pdl_wait();
+    pdl_trigger();
     const int b = blockIdx.z, h = blockIdx.y;
     const int i = blockIdx.x * QT + (threadIdx.x >> 1), half = threadIdx.x & 1;
     const int ld = 3 * H * AT_D, ho = half * 36;
@@ -361,6 +367,8 @@ __global__ void __launch_bounds__(QT * 2) attention_bwd_dq_kernel(const __nv_bfl
                                                                   float *__restrict__ delta) {
     constexpr int TILE = QT <= 32 ? 32 : 64;   // rows of the other operand per smem tile
     __shared__ __align__(16) float s_k[TILE * AT_PITCH], s_v[TILE * AT_PITCH];
+    pdl_wait();
+    pdl_trigger();
     const int b = blockIdx.z, h = blockIdx.y;
     const int i = blockIdx.x * QT + (threadIdx.x >> 1), half = threadIdx.x & 1;
     const int ld = 3 * H * AT_D, ldo = H * AT_D, ho = half * 36;
@@ -414,6 +422,8 @@ __global__ void __launch_bounds__(QT * 2) attention_bwd_dkv_kernel(const __nv_bf
     constexpr int TILE = QT <= 32 ? 32 : 64;
     __shared__ __align__(16) float s_q[TILE * AT_PITCH], s_g[TILE * AT_PITCH];
     __shared__ float s_l[TILE], s_d[TILE];
+    pdl_wait();
+    pdl_trigger();
     const int b = blockIdx.z, h = blockIdx.y;
     const int j = blockIdx.x * QT + (threadIdx.x >> 1), half = threadIdx.x & 1;
     const int ld = 3 * H * AT_D, ldo = H * AT_D, ho = half * 36;
@@ -492,8 +502,8 @@ extern "C" int act_layernorm_fwd(const float *x, const float *pos, const float *
     cudaStream_t st = (cudaStream_t)stream;
 #define LN_CASE(V)                                                                                                   \
     case V:                                                                                                          \
-        layernorm_fwd_kernel<V><<<(M + 7) / 8, 256, 0, st>>>(x, pos, gamma, beta, eps, M, xsum_out, out, out_fp32, mean, \
-                                                             rstd);                                                  \
+        ACT_CUDA(launch_k(layernorm_fwd_kernel<V>, dim3((M + 7) / 8), dim3(256), 0, st, true, x, pos, gamma, beta, eps, \
+                          M, xsum_out, out, out_fp32, mean, rstd));                                                  \
         break;
     switch (C / 128) {
         LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(6) LN_CASE(8)
@@ -516,9 +526,9 @@ extern "C" int act_layernorm_bwd(const void *dy, int dy_fp32, const float *x, co
     const int grid = (M + 7) / 8 < 148 ? (M + 7) / 8 : 148;
 #define LN_CASE(V)                                                                                                \
     case V:                                                                                                       \
-        layernorm_bwd_kernel<V><<<grid, 256, 0, st>>>(dy, dy_fp32, x, mean, rstd, gamma, dres, M, dx_out, dgamma, \
-                                                      dbeta, dacc, reinterpret_cast<__nv_bfloat16 *>(g_bf16),     \
-                                                      row_scale, rows_per_scale > 0 ? rows_per_scale : 1, dbias); \
+        ACT_CUDA(launch_k(layernorm_bwd_kernel<V>, dim3(grid), dim3(256), 0, st, true, dy, dy_fp32, x, mean, rstd,  \
+                          gamma, dres, M, dx_out, dgamma, dbeta, dacc, reinterpret_cast<__nv_bfloat16 *>(g_bf16), \
+                          row_scale, rows_per_scale > 0 ? rows_per_scale : 1, dbias));                            \
         break;
     switch (C / 128) {
         LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(6) LN_CASE(8)
@@ -562,13 +572,12 @@ extern "C" int act_attention_fwd(const void *qkv, int B, int T, int H, int head_
     const __nv_bfloat16 *p = reinterpret_cast<const __nv_bfloat16 *>(qkv);
     __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(o);
     if (T <= 16) {
-        attention_fwd_kernel<16><<<dim3((T + 15) / 16, H, B), 32, 0, st>>>(p, T, H, scale, op, lse);
+        ACT_CUDA(launch_k(attention_fwd_kernel<16>, dim3((T + 15) / 16, H, B), dim3(32), 0, st, true, p, T, H, scale, op, lse));
     } else if (T <= 32 || (T > 64 && T <= 96)) {
-        attention_fwd_kernel<32><<<dim3((T + 31) / 32, H, B), 64, 0, st>>>(p, T, H, scale, op, lse);
+        ACT_CUDA(launch_k(attention_fwd_kernel<32>, dim3((T + 31) / 32, H, B), dim3(64), 0, st, true, p, T, H, scale, op, lse));
     } else {
-        attention_fwd_kernel<64><<<dim3((T + 63) / 64, H, B), 128, 0, st>>>(p, T, H, scale, op, lse);
+        ACT_CUDA(launch_k(attention_fwd_kernel<64>, dim3((T + 63) / 64, H, B), dim3(128), 0, st, true, p, T, H, scale, op, lse));
     }
-    ACT_CHECK_LAUNCH();
     return ACT_OK;
 }
 
@@ -585,14 +594,13 @@ extern "C" int act_attention_bwd(const void *qkv, const void *o, const void *dO,
     __nv_bfloat16 *dp = reinterpret_cast<__nv_bfloat16 *>(dqkv);
     if (T <= 32 || (T > 64 && T <= 96)) {
         dim3 grid((T + 31) / 32, H, B);
-        attention_bwd_dq_kernel<32><<<grid, 64, 0, st>>>(p, op, gp, lse, T, H, scale, dp, delta);
-        attention_bwd_dkv_kernel<32><<<grid, 64, 0, st>>>(p, gp, lse, delta, T, H, scale, dp);
+        ACT_CUDA(launch_k(attention_bwd_dq_kernel<32>, grid, dim3(64), 0, st, true, p, op, gp, lse, T, H, scale, dp, delta));
+        ACT_CUDA(launch_k(attention_bwd_dkv_kernel<32>, grid, dim3(64), 0, st, true, p, gp, lse, delta, T, H, scale, dp));
     } else {
         dim3 grid((T + 63) / 64, H, B);
-        attention_bwd_dq_kernel<64><<<grid, 128, 0, st>>>(p, op, gp, lse, T, H, scale, dp, delta);
-        attention_bwd_dkv_kernel<64><<<grid, 128, 0, st>>>(p, gp, lse, delta, T, H, scale, dp);
+        ACT_CUDA(launch_k(attention_bwd_dq_kernel<64>, grid, dim3(128), 0, st, true, p, op, gp, lse, T, H, scale, dp, delta));
+        ACT_CUDA(launch_k(attention_bwd_dkv_kernel<64>, grid, dim3(128), 0, st, true, p, gp, lse, delta, T, H, scale, dp));
     }
-    ACT_CHECK_LAUNCH();
     return ACT_OK;
 }
 
