@@ -14,3 +14,11 @@ extern "C" const char *act_error_string(int code) {
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
     return "act_b200: unknown error";
 }
+
+extern "C" int act_set_option(int key, int value) {
+    if (key == ACT_OPT_PDL) {
+        act::pdl_flag() = value ? 1 : 0;
+        return ACT_OK;
+    }
+    return ACT_EINVAL;
+}

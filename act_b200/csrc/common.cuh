@@ -32,13 +32,16 @@ namespace act {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-inline bool pdl_enabled() {
-    static const int on = [] {
+// process-wide switch (default on; ACT_B200_PDL=0 or act_set_option(ACT_OPT_PDL, 0) turns it off, e.g. to time
+// kernels one by one).  A plain int written only through act_set_option: benign configuration state.
+inline int &pdl_flag() {
+    static int on = [] {
         const char *e = std::getenv("ACT_B200_PDL");
         return (e && e[0] == '0') ? 0 : 1;
     }();
-    return on != 0;
+    return on;
 }
+inline bool pdl_enabled() { return pdl_flag() != 0; }
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,

@@ -128,25 +128,32 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool 
 // Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of the stored result), which needs exactly the
 // exponential exp(-x^2/2) that the Gaussian pdf of GELU' needs too: 1 MUFU.EX2 + 1 MUFU.RCP + ~10 FMA per element
 // instead of erff()'s branchy ~30 instructions -- the GELU epilogues were ALU-bound on 4 epilogue warps.
-__device__ __forceinline__ void gelu_parts(float x, float &cdf, float &e) {
-    const float ax = fabsf(x);
-    e = exp2f(-0.72134752044448170368f * x * x);                       // exp(-x^2 / 2)
-    const float t = __fdividef(1.f, fmaf(0.23164189467977f, ax, 1.f));  // 1 / (1 + p |x| / sqrt(2))
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float tail = 0.5f * poly * t * e;                            // 0.5 * (1 - erf(|x| / sqrt(2)))
-    cdf = x >= 0.f ? 1.f - tail : tail;
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// tail(x) = 0.5 * (1 - erf(|x| / sqrt(2)));  e = exp(-x^2 / 2)
+__device__ __forceinline__ float gelu_tail(float ax, float &e) {
+    e = ex2_approx(-0.72134752044448170368f * ax * ax);
+    const float t = __fdividef(1.f, fmaf(0.23164189467977f, ax, 1.f));
+    float poly = fmaf(0.5307027145f, t, -0.7265760135f);        // 0.5 * A&S 7.1.26 coefficients
+    poly = fmaf(poly, t, 0.7107068705f);
+    poly = fmaf(poly, t, -0.142248368f);
+    poly = fmaf(poly, t, 0.127414796f);
+    return poly * t * e;
 }
 __device__ __forceinline__ float gelu_erf(float x) {
-    float cdf, e;
-    gelu_parts(x, cdf, e);
-    return x * cdf;
+    const float ax = fabsf(x);
+    float e;
+    const float tail = gelu_tail(ax, e);
+    return fmaf(-ax, tail, fmaxf(x, 0.f));                      // x >= 0: x - x*tail;  x < 0: x*tail
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-    float cdf, e;
-    gelu_parts(x, cdf, e);
+    const float ax = fabsf(x);
+    float e;
+    const float tail = gelu_tail(ax, e);
+    const float cdf = x >= 0.f ? 1.f - tail : tail;
     return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 
@@ -184,7 +191,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_
     if (!row_ok && !gmode) return;
     float f[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * epi.alpha;
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (epi.alpha != 1.f) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] *= epi.alpha;
+    }
     const int ncols = min(32, N - n);   // N % 8 == 0 guaranteed by the host
     if (epi.bias) {
 #pragma unroll
@@ -360,7 +371,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_co
         mbar_init(&tmem_full_bar, 1);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(&tmem_slot, BN);
+    constexpr uint32_t TMEM_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);   // power of two >= BN
+    if (warp == 1) tmem_alloc(&tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -442,7 +454,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_co
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_d, BN);
+        tmem_dealloc(tmem_d, TMEM_COLS);
     }
 }
 
@@ -627,7 +639,7 @@ static int make_map(CUtensorMap *map, const void *ptr, long long rows, long long
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmEpi &epi, int M, int N, int K,
                        int splits, cudaStream_t st) {
-    constexpr int STAGES = 3;
+    constexpr int STAGES = BN > 128 ? 2 : 3;     // keep two CTAs resident per SM (<= ~113 KB each)
     constexpr size_t smem = (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024;
     auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES>;
     ACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -683,8 +695,17 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
     if (row_scale && rows_per_scale <= 0) return ACT_EINVAL;
     const long long tiles128 = (long long)((M + 127) / 128) * ((N + 127) / 128) * splits;
     if (persistent < 0) persistent = tiles128 > 592 ? 1 : 0;     // > 2 waves of the one-tile-per-CTA kernel
-    const int BN = persistent ? ((block_n == 256 || (block_n == 0 && N % 256 == 0 && !gmode)) ? 256 : 128)
-                              : ((block_n == 64 || block_n == 128) ? block_n : (N <= 64 ? 64 : 128));
+    int BN;
+    if (persistent) {
+        BN = (block_n == 256 || (block_n == 0 && N % 256 == 0 && !gmode)) ? 256 : 128;
+    } else if (block_n == 64 || block_n == 128 || block_n == 192) {
+        BN = block_n;
+    } else {
+        // one-tile-per-CTA kernel, 2 CTAs per SM = 296 slots: prefer the widest tile that fits one wave
+        const long long rows = (M + 127) / 128;
+        BN = N <= 64 ? 64 : 128;
+        if (N % 192 == 0 && rows * ((N + 127) / 128) * splits > 296 && rows * (N / 192) * splits <= 296) BN = 192;
+    }
     GemmEpi epi;
     epi.out = out; epi.preact_out = preact_out; epi.bias = bias; epi.resid = resid;
     epi.mul_in = reinterpret_cast<const __nv_bfloat16 *>(mul_in);
@@ -720,6 +741,7 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
         ACT_GEMM_DISPATCH_P(128);
     }
     if (BN == 64) ACT_GEMM_DISPATCH(64);
+    if (BN == 192) ACT_GEMM_DISPATCH(192);
     ACT_GEMM_DISPATCH(128);
 #undef ACT_GEMM_DISPATCH
 #undef ACT_GEMM_DISPATCH_P

@@ -28,6 +28,10 @@ extern "C" {
 
 int act_version(void);
 const char *act_error_string(int code);
+/* Process-wide options.  ACT_OPT_PDL (default 1): launch the kernels of the dependent chain with programmatic
+ * dependent launch (prologue overlaps the predecessor's tail); 0 serialises them (per-kernel timing). */
+#define ACT_OPT_PDL 1
+int act_set_option(int key, int value);
 
 /* ---- Group tokenizer ------------------------------------------------------------------------------ */
 

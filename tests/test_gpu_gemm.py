@@ -38,7 +38,7 @@ def test_gemm_layouts(M, N, K, a_mn, b_mn):
         check(got, want, out_dtype == torch.bfloat16)
 
 
-@pytest.mark.parametrize("block_n", [64, 128])
+@pytest.mark.parametrize("block_n", [64, 128, 192])
 def test_gemm_epilogues(block_n):
     torch.manual_seed(0)
     M, N, K = 1000, 384, 256
@@ -148,3 +148,17 @@ def test_gemm_fused_group_max(persistent):
     gf2 = torch.zeros(G, N, device="cuda")
     assert ops.gemm(a, w, bias=bias, gmax_f32=gf2, no_out=True, persistent=persistent) is None
     assert torch.equal(gf2, gf)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+def test_gemm_bn192(a_mn, b_mn):
+    """128 x 192 tiles (N = 1536 / 1152 in one wave of the one-tile-per-CTA kernel)."""
+    torch.manual_seed(9)
+    M, N, K = 3456, 1536, 384
+    a, b = rnd(M, K), rnd(N, K, scale=0.1)
+    A = a.t().contiguous() if a_mn else a
+    B = b.t().contiguous() if b_mn else b
+    got = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, block_n=192, out_dtype=torch.float32)
+    check(got, a.float() @ b.float().t(), False)
+    auto = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32)
+    assert torch.equal(got, auto)          # the heuristic picks the 192-wide tile here

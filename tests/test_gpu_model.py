@@ -170,3 +170,25 @@ def test_engine_graph_replay_matches_eager():
     # loose afterwards.
     np.testing.assert_allclose(graph[:2], eager[:2], rtol=1e-3)
     np.testing.assert_allclose(graph, eager, rtol=0.15)
+
+
+def test_dense_regime_step_runs():
+    """BASELINE config 5 shapes (N=8192, G=512 x k=32, mask 0.6 -> T_enc=206, T_dec=512) at a small batch: the
+    tokenizer is bit-exact against the C oracle, the step (long-sequence attention path, N=8192 FPS) is finite."""
+    from oracle import cpu_ref
+    torch.manual_seed(0)
+    np.random.seed(0)
+    B = 2
+    pts = ref_model.synthetic_clouds(B, 8192, seed=8)
+    cfg = models.default_config(mask_ratio=0.6, drop_path_rate=0.0, num_group=512, group_size=32, depth=2)
+    model = models.ACT_PointDistillation(cfg).cuda().train()
+    nb, center = model.group_divider(pts.cuda())
+    onb, ocenter, oidx, ofps = cpu_ref.group(pts.numpy(), 512, 32)
+    assert np.array_equal(model.group_divider.last_fps_idx.cpu().numpy(), ofps)
+    assert np.array_equal(model.group_divider.last_idx.cpu().numpy(), oidx)
+    assert np.array_equal(nb.cpu().numpy(), onb)
+    loss = model(pts.cuda())
+    loss.backward()
+    assert np.isfinite(loss.item()) and 0 < loss.item() < 2
+    g = model.ACT_encoder.blocks.blocks[0].attn.qkv.weight.grad
+    assert torch.isfinite(g).all() and g.abs().max() > 0
