@@ -705,6 +705,7 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
         const long long rows = (M + 127) / 128;
         BN = N <= 64 ? 64 : 128;
         if (N % 192 == 0 && rows * ((N + 127) / 128) * splits > 296 && rows * (N / 192) * splits <= 296) BN = 192;
+        else if (rows * ((N + 127) / 128) * splits < 148) BN = 64;     // fewer tiles than SMs: halve them
     }
     GemmEpi epi;
     epi.out = out; epi.preact_out = preact_out; epi.bias = bias; epi.resid = resid;

@@ -37,6 +37,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // ---- input moments: out[0..2] = sum p, out[3..8] = sum (xx, xy, xz, yy, yz, zz), in double -------------
 __global__ void __launch_bounds__(256) pn_moments_kernel(const float *__restrict__ p, long long M,
                                                          double *__restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     double a[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) a[i] = 0.0;
@@ -67,6 +69,8 @@ __global__ void __launch_bounds__(256) pn_moments_kernel(const float *__restrict
 __global__ void __launch_bounds__(256) pn_conv1_kernel(const float *__restrict__ p, const float *__restrict__ W,
                                                        const float *__restrict__ b, long long M, int relu,
                                                        __nv_bfloat16 *__restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float sW[128 * 3], sb[128];
     for (int i = threadIdx.x; i < 384; i += 256) sW[i] = __ldg(W + i);
     for (int i = threadIdx.x; i < 128; i += 256) sb[i] = __ldg(b + i);
@@ -90,6 +94,8 @@ __global__ void __launch_bounds__(256) pn_conv1_kernel(const float *__restrict__
 __global__ void __launch_bounds__(256) group_max_kernel(const __nv_bfloat16 *__restrict__ x, int G, int k, int C,
                                                         __nv_bfloat16 *__restrict__ out_bf16,
                                                         float *__restrict__ out_f32, uint8_t *__restrict__ arg) {
+    pdl_wait();
+    pdl_trigger();
     const int vec_per_row = C / 8;
     const long long total = (long long)G * vec_per_row;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -124,6 +130,8 @@ __global__ void __launch_bounds__(256) group_max_kernel(const __nv_bfloat16 *__r
 __global__ void __launch_bounds__(256) group_max_bwd_kernel(const float *__restrict__ dout,
                                                             const uint8_t *__restrict__ arg, int G, int k, int C,
                                                             int accumulate, __nv_bfloat16 *__restrict__ dF) {
+    pdl_wait();
+    pdl_trigger();
     const int vec_per_row = C / 8;
     const long long total = (long long)G * vec_per_row;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -153,6 +161,8 @@ __global__ void __launch_bounds__(256) group_max_bwd_kernel(const float *__restr
 __global__ void __launch_bounds__(256) group_sum_kernel(const __nv_bfloat16 *__restrict__ x, int G, int k, int C,
                                                         __nv_bfloat16 *__restrict__ out_bf16,
                                                         float *__restrict__ out_f32) {
+    pdl_wait();
+    pdl_trigger();
     const int vec_per_row = C / 8;
     const long long total = (long long)G * vec_per_row;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -185,6 +195,8 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const __nv_bfloat16 *_
                                                           const float *__restrict__ mean,
                                                           const float *__restrict__ rstd, long long M, int C,
                                                           float *__restrict__ s1, float *__restrict__ s2) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ float sm[];  // [rows_per_cta][2][C]
     const int vpr = C / 8, rpc = 256 / vpr;
     const int v = threadIdx.x % vpr, rl = threadIdx.x / vpr;
@@ -231,6 +243,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16 *__re
                                                        const float *__restrict__ scale,
                                                        const float *__restrict__ shift, long long M, int C, int relu,
                                                        __nv_bfloat16 *__restrict__ y) {
+    pdl_wait();
+    pdl_trigger();
     const int vpr = C / 8, rpc = 256 / vpr;
     const int v = threadIdx.x % vpr, rl = threadIdx.x / vpr;
     if (rl >= rpc) return;
@@ -258,6 +272,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16 *
                                                            const float *__restrict__ gamma,
                                                            const float *__restrict__ s1, const float *__restrict__ s2,
                                                            long long M, int C, __nv_bfloat16 *__restrict__ dh) {
+    pdl_wait();
+    pdl_trigger();
     const int vpr = C / 8, rpc = 256 / vpr;
     const int v = threadIdx.x % vpr, rl = threadIdx.x / vpr;
     if (rl >= rpc) return;
@@ -296,6 +312,8 @@ __global__ void __launch_bounds__(256) pn_conv1_bwd_kernel(const __nv_bfloat16 *
                                                            const float *__restrict__ gamma, float *__restrict__ s1,
                                                            float *__restrict__ s2, long long M,
                                                            float *__restrict__ dW, float *__restrict__ db) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float sm[16][4][128];
     const int c0 = (threadIdx.x & 15) * 8, rl = threadIdx.x >> 4;
     float w[8][3], bb[8], mu[8], rs[8], k1[8], k2[8], gs[8];
@@ -351,6 +369,66 @@ __global__ void __launch_bounds__(256) pn_conv1_bwd_kernel(const __nv_bfloat16 *
     }
 }
 
+// ---- BatchNorm bookkeeping (O(C) work, one CTA): replaces ~25 tiny double-precision PyTorch kernels per step ----
+// BN1: statistics of h1 = W p + b follow from the input moments:  mean_c = W_c . mu + b_c,  var_c = W_c^T Cov W_c.
+// Outputs the folded conv1 (Wf, bf) = gamma * rstd * (W, b - mean) + (0, beta), mean, rstd, and updates the running
+// statistics (momentum, unbiased variance) and num_batches_tracked exactly as nn.BatchNorm1d does in train mode.
+__global__ void __launch_bounds__(128) pn_bn1_fold_kernel(const double *__restrict__ mom9, long long M,
+                                                         const float *__restrict__ W, const float *__restrict__ b,
+                                                         const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                         float eps, float momentum, float *__restrict__ rmean,
+                                                         float *__restrict__ rvar, long long *__restrict__ nbt,
+                                                         float *__restrict__ Wf, float *__restrict__ bf,
+                                                         float *__restrict__ mean_out, float *__restrict__ rstd_out) {
+    pdl_wait();
+    pdl_trigger();
+    const int c = threadIdx.x;
+    const double inv = 1.0 / (double)M;
+    const double mx = mom9[0] * inv, my = mom9[1] * inv, mz = mom9[2] * inv;
+    const double sxx = mom9[3] * inv - mx * mx, sxy = mom9[4] * inv - mx * my, sxz = mom9[5] * inv - mx * mz;
+    const double syy = mom9[6] * inv - my * my, syz = mom9[7] * inv - my * mz, szz = mom9[8] * inv - mz * mz;
+    const double w0 = W[c * 3], w1 = W[c * 3 + 1], w2 = W[c * 3 + 2];
+    const double mean = w0 * mx + w1 * my + w2 * mz + (double)b[c];
+    double var = w0 * (sxx * w0 + sxy * w1 + sxz * w2) + w1 * (sxy * w0 + syy * w1 + syz * w2) +
+                 w2 * (sxz * w0 + syz * w1 + szz * w2);
+    var = var > 0.0 ? var : 0.0;
+    const double rstd = 1.0 / sqrt(var + (double)eps);
+    const double sc = (double)gamma[c] * rstd;
+    Wf[c * 3] = (float)(w0 * sc); Wf[c * 3 + 1] = (float)(w1 * sc); Wf[c * 3 + 2] = (float)(w2 * sc);
+    bf[c] = (float)(((double)b[c] - mean) * sc + (double)beta[c]);
+    mean_out[c] = (float)mean;
+    rstd_out[c] = (float)rstd;
+    rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mean;
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)(var * ((double)M / (double)(M - 1)));
+    if (c == 0 && nbt) *nbt += 1;
+}
+
+// BN2 (any C): from sum / sumsq over M rows -> mean, rstd, scale = gamma*rstd, shift = beta - mean*scale, running stats
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float *__restrict__ sum, const float *__restrict__ sumsq,
+                                                         long long M, int C, const float *__restrict__ gamma,
+                                                         const float *__restrict__ beta, float eps, float momentum,
+                                                         float *__restrict__ rmean, float *__restrict__ rvar,
+                                                         long long *__restrict__ nbt, float *__restrict__ scale,
+                                                         float *__restrict__ shift, float *__restrict__ mean_out,
+                                                         float *__restrict__ rstd_out) {
+    pdl_wait();
+    pdl_trigger();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const double mean = (double)sum[c] / (double)M;
+        double var = (double)sumsq[c] / (double)M - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        const double rstd = 1.0 / sqrt(var + (double)eps);
+        const double sc = (double)gamma[c] * rstd;
+        scale[c] = (float)sc;
+        shift[c] = (float)((double)beta[c] - mean * sc);
+        mean_out[c] = (float)mean;
+        rstd_out[c] = (float)rstd;
+        rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mean;
+        rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)(var * ((double)M / (double)(M - 1)));
+    }
+    if (threadIdx.x == 0 && nbt) *nbt += 1;
+}
+
 static inline int grid_for(long long work_items, int per_cta) {
     long long g = (work_items + per_cta - 1) / per_cta;
     const long long cap = 148LL * 8;
@@ -364,8 +442,7 @@ extern "C" int act_pn_moments(const float *points, long long M, double *out9, vo
     if (!points || !out9 || M <= 0) return ACT_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     ACT_CUDA(cudaMemsetAsync(out9, 0, 9 * sizeof(double), st));
-    pn_moments_kernel<<<grid_for(M, 256 * 8), 256, 0, st>>>(points, M, out9);
-    ACT_CHECK_LAUNCH();
+    ACT_CUDA(launch_k(pn_moments_kernel, dim3(grid_for(M, 256 * 8)), dim3(256), 0, st, true, points, M, out9));
     return ACT_OK;
 }
 
@@ -373,9 +450,33 @@ extern "C" int act_pn_conv1(const float *points, const float *W, const float *b,
                             void *stream) {
     using namespace act;
     if (!points || !W || !b || !out_bf16 || M <= 0) return ACT_EINVAL;
-    pn_conv1_kernel<<<grid_for(M, 16 * 8), 256, 0, (cudaStream_t)stream>>>(points, W, b, M, relu,
-                                                                          reinterpret_cast<__nv_bfloat16 *>(out_bf16));
-    ACT_CHECK_LAUNCH();
+    ACT_CUDA(launch_k(pn_conv1_kernel, dim3(grid_for(M, 16 * 8)), dim3(256), 0, (cudaStream_t)stream, true, points, W, b, M,
+                      relu, reinterpret_cast<__nv_bfloat16 *>(out_bf16)));
+    return ACT_OK;
+}
+
+extern "C" int act_pn_bn1_fold(const double *mom9, long long M, const float *W, const float *b, const float *gamma,
+                               const float *beta, float eps, float momentum, float *running_mean, float *running_var,
+                               long long *num_batches_tracked, float *Wf, float *bf, float *mean, float *rstd,
+                               void *stream) {
+    using namespace act;
+    if (!mom9 || !W || !b || !gamma || !beta || !running_mean || !running_var || !Wf || !bf || !mean || !rstd || M < 2)
+        return ACT_EINVAL;
+    ACT_CUDA(launch_k(pn_bn1_fold_kernel, dim3(1), dim3(128), 0, (cudaStream_t)stream, true, mom9, M, W, b, gamma, beta, eps,
+                      momentum, running_mean, running_var, num_batches_tracked, Wf, bf, mean, rstd));
+    return ACT_OK;
+}
+
+extern "C" int act_bn_finalize(const float *sum, const float *sumsq, long long M, int C, const float *gamma,
+                               const float *beta, float eps, float momentum, float *running_mean, float *running_var,
+                               long long *num_batches_tracked, float *scale, float *shift, float *mean, float *rstd,
+                               void *stream) {
+    using namespace act;
+    if (!sum || !sumsq || !gamma || !beta || !running_mean || !running_var || !scale || !shift || !mean || !rstd ||
+        M < 2 || C <= 0)
+        return ACT_EINVAL;
+    ACT_CUDA(launch_k(bn_finalize_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, true, sum, sumsq, M, C, gamma, beta,
+                      eps, momentum, running_mean, running_var, num_batches_tracked, scale, shift, mean, rstd));
     return ACT_OK;
 }
 
@@ -384,10 +485,9 @@ extern "C" int act_group_max(const void *x_bf16, int G, int k, int C, void *out_
     using namespace act;
     if (!x_bf16 || G <= 0 || k <= 0 || k > 255 || C <= 0) return ACT_EINVAL;
     if (C % 8) return ACT_EUNSUPPORTED;
-    group_max_kernel<<<grid_for((long long)G * C / 8, 256), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __nv_bfloat16 *>(x_bf16), G, k, C, reinterpret_cast<__nv_bfloat16 *>(out_bf16), out_f32,
-        arg);
-    ACT_CHECK_LAUNCH();
+    ACT_CUDA(launch_k(group_max_kernel, dim3(grid_for((long long)G * C / 8, 256)), dim3(256), 0, (cudaStream_t)stream, true,
+                      reinterpret_cast<const __nv_bfloat16 *>(x_bf16), G, k, C,
+                      reinterpret_cast<__nv_bfloat16 *>(out_bf16), out_f32, arg));
     return ACT_OK;
 }
 
@@ -396,9 +496,8 @@ extern "C" int act_group_max_bwd(const float *dout, const uint8_t *arg, int G, i
     using namespace act;
     if (!dout || !arg || !dF_bf16 || G <= 0 || k <= 0 || C <= 0) return ACT_EINVAL;
     if (C % 8) return ACT_EUNSUPPORTED;
-    group_max_bwd_kernel<<<grid_for((long long)G * C / 8, 256), 256, 0, (cudaStream_t)stream>>>(
-        dout, arg, G, k, C, accumulate, reinterpret_cast<__nv_bfloat16 *>(dF_bf16));
-    ACT_CHECK_LAUNCH();
+    ACT_CUDA(launch_k(group_max_bwd_kernel, dim3(grid_for((long long)G * C / 8, 256)), dim3(256), 0, (cudaStream_t)stream,
+                      true, dout, arg, G, k, C, accumulate, reinterpret_cast<__nv_bfloat16 *>(dF_bf16)));
     return ACT_OK;
 }
 
@@ -406,9 +505,9 @@ extern "C" int act_group_sum(const void *x_bf16, int G, int k, int C, void *out_
     using namespace act;
     if (!x_bf16 || G <= 0 || k <= 0 || C <= 0) return ACT_EINVAL;
     if (C % 8) return ACT_EUNSUPPORTED;
-    group_sum_kernel<<<grid_for((long long)G * C / 8, 256), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __nv_bfloat16 *>(x_bf16), G, k, C, reinterpret_cast<__nv_bfloat16 *>(out_bf16), out_f32);
-    ACT_CHECK_LAUNCH();
+    ACT_CUDA(launch_k(group_sum_kernel, dim3(grid_for((long long)G * C / 8, 256)), dim3(256), 0, (cudaStream_t)stream, true,
+                      reinterpret_cast<const __nv_bfloat16 *>(x_bf16), G, k, C,
+                      reinterpret_cast<__nv_bfloat16 *>(out_bf16), out_f32));
     return ACT_OK;
 }
 
@@ -425,10 +524,9 @@ static int chan_reduce(int mode, const void *a, const void *x, const float *mean
     const size_t smem = (size_t)rpc * 2 * C * sizeof(float);
     const int grid = grid_for(M, rpc * 32);
     const __nv_bfloat16 *ap = reinterpret_cast<const __nv_bfloat16 *>(a), *xp = reinterpret_cast<const __nv_bfloat16 *>(x);
-    if (mode == 0) chan_reduce_kernel<0><<<grid, 256, smem, st>>>(ap, xp, mean, rstd, M, C, s1, s2);
-    else if (mode == 1) chan_reduce_kernel<1><<<grid, 256, smem, st>>>(ap, xp, mean, rstd, M, C, s1, s2);
-    else chan_reduce_kernel<2><<<grid, 256, smem, st>>>(ap, xp, mean, rstd, M, C, s1, s2);
-    ACT_CHECK_LAUNCH();
+    if (mode == 0) ACT_CUDA(launch_k(chan_reduce_kernel<0>, dim3(grid), dim3(256), smem, st, true, ap, xp, mean, rstd, M, C, s1, s2));
+    else if (mode == 1) ACT_CUDA(launch_k(chan_reduce_kernel<1>, dim3(grid), dim3(256), smem, st, true, ap, xp, mean, rstd, M, C, s1, s2));
+    else ACT_CUDA(launch_k(chan_reduce_kernel<2>, dim3(grid), dim3(256), smem, st, true, ap, xp, mean, rstd, M, C, s1, s2));
     return ACT_OK;
 }
 
@@ -453,10 +551,9 @@ extern "C" int act_bn_apply(const void *x_bf16, const float *scale, const float 
     if (!x_bf16 || !scale || !shift || !y_bf16 || M <= 0 || C <= 0) return ACT_EINVAL;
     if (C % 8) return ACT_EUNSUPPORTED;
     if (C / 8 > 256) return ACT_EUNSUPPORTED;
-    bn_apply_kernel<<<grid_for(M, (256 / (C / 8)) * 16), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __nv_bfloat16 *>(x_bf16), scale, shift, M, C, relu,
-        reinterpret_cast<__nv_bfloat16 *>(y_bf16));
-    ACT_CHECK_LAUNCH();
+    ACT_CUDA(launch_k(bn_apply_kernel, dim3(grid_for(M, (256 / (C / 8)) * 16)), dim3(256), 0, (cudaStream_t)stream, true,
+                      reinterpret_cast<const __nv_bfloat16 *>(x_bf16), scale, shift, M, C, relu,
+                      reinterpret_cast<__nv_bfloat16 *>(y_bf16)));
     return ACT_OK;
 }
 
@@ -467,10 +564,9 @@ extern "C" int act_bn_bwd_apply(const void *dz_bf16, const void *x_bf16, const f
     if (!dz_bf16 || !x_bf16 || !mean || !rstd || !gamma || !sum_dz || !sum_dz_xhat || !dh_bf16 || M <= 0 || C <= 0)
         return ACT_EINVAL;
     if (C % 8 || C / 8 > 256) return ACT_EUNSUPPORTED;
-    bn_bwd_apply_kernel<<<grid_for(M, (256 / (C / 8)) * 16), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const __nv_bfloat16 *>(dz_bf16), reinterpret_cast<const __nv_bfloat16 *>(x_bf16), mean, rstd,
-        gamma, sum_dz, sum_dz_xhat, M, C, reinterpret_cast<__nv_bfloat16 *>(dh_bf16));
-    ACT_CHECK_LAUNCH();
+    ACT_CUDA(launch_k(bn_bwd_apply_kernel, dim3(grid_for(M, (256 / (C / 8)) * 16)), dim3(256), 0, (cudaStream_t)stream, true,
+                      reinterpret_cast<const __nv_bfloat16 *>(dz_bf16), reinterpret_cast<const __nv_bfloat16 *>(x_bf16),
+                      mean, rstd, gamma, sum_dz, sum_dz_xhat, M, C, reinterpret_cast<__nv_bfloat16 *>(dh_bf16)));
     return ACT_OK;
 }
 
@@ -485,8 +581,9 @@ extern "C" int act_pn_conv1_bwd(const void *dz_bf16, const float *points, const 
     ACT_CUDA(cudaMemsetAsync(s2, 0, 128 * sizeof(float), st));
     const __nv_bfloat16 *dz = reinterpret_cast<const __nv_bfloat16 *>(dz_bf16);
     const int grid = grid_for(M, 16 * 32);
-    pn_conv1_bwd_kernel<0><<<grid, 256, 0, st>>>(dz, points, W, b, mean, rstd, gamma, s1, s2, M, dW, db);
-    pn_conv1_bwd_kernel<1><<<grid, 256, 0, st>>>(dz, points, W, b, mean, rstd, gamma, s1, s2, M, dW, db);
-    ACT_CHECK_LAUNCH();
+    ACT_CUDA(launch_k(pn_conv1_bwd_kernel<0>, dim3(grid), dim3(256), 0, st, true, dz, points, W, b, mean, rstd, gamma, s1, s2,
+                      M, dW, db));
+    ACT_CUDA(launch_k(pn_conv1_bwd_kernel<1>, dim3(grid), dim3(256), 0, st, true, dz, points, W, b, mean, rstd, gamma, s1, s2,
+                      M, dW, db));
     return ACT_OK;
 }

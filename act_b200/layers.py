@@ -357,24 +357,15 @@ class PointNetEncoderFn(torch.autograd.Function):
         p = nb.reshape(M, 3).contiguous().float()
         rm1, rv1, nbt1, rm2, rv2, nbt2 = bufs
         W1 = w1.view(128, 3)
-        if training:
-            mom = ops.pn_moments(p) / M
-            mu = mom[:3]
-            S = torch.stack([mom[3], mom[4], mom[5], mom[4], mom[6], mom[7], mom[5], mom[7], mom[8]]).view(3, 3)
-            S = S - torch.outer(mu, mu)
-            W1d = W1.double()
-            mean1 = W1d @ mu + b1.double()
-            var1 = ((W1d @ S) * W1d).sum(1).clamp_min(0)
-            with torch.no_grad():
-                rm1.mul_(1 - momentum).add_(mean1.float(), alpha=momentum)
-                rv1.mul_(1 - momentum).add_((var1 * (M / (M - 1))).float(), alpha=momentum)
-                nbt1.add_(1)
+        if training:     # statistics, folding and running-stat update in one O(128) kernel
+            Wf, bf, mean1, rstd1 = ops.pn_bn1_fold(ops.pn_moments(p), M, W1, b1, g1, be1, eps, momentum, rm1, rv1, nbt1)
         else:
             mean1, var1 = rm1.double(), rv1.double()
-        rstd1 = torch.rsqrt(var1 + eps)
-        s1 = g1.double() * rstd1
-        Wf = (W1.double() * s1[:, None]).float().contiguous()
-        bf = ((b1.double() - mean1) * s1 + be1.double()).float()
+            rstd1 = torch.rsqrt(var1 + eps)
+            s1 = g1.double() * rstd1
+            Wf = (W1.double() * s1[:, None]).float().contiguous()
+            bf = ((b1.double() - mean1) * s1 + be1.double()).float()
+            mean1, rstd1 = mean1.float(), rstd1.float()
         a1 = ops.pn_conv1(p, Wf, bf, relu=True)                                   # [M,128]
         BG = B * G
         if k == 32:      # max over the group's 32 points fused into the GEMM epilogue (fp32 accumulators)
@@ -389,17 +380,14 @@ class PointNetEncoderFn(torch.autograd.Function):
         h3 = ops.gemm(f2, w3s[:, 256:], resid=gpart, resid_row_div=k)             # [M,512]
         if training:
             sm, sq = ops.bn_stats(h3)
-            mean2 = sm.double() / M
-            var2 = (sq.double() / M - mean2 * mean2).clamp_min(0)
-            with torch.no_grad():
-                rm2.mul_(1 - momentum).add_(mean2.float(), alpha=momentum)
-                rv2.mul_(1 - momentum).add_((var2 * (M / (M - 1))).float(), alpha=momentum)
-                nbt2.add_(1)
+            sc2, sh2, mean2, rstd2 = ops.bn_finalize(sm, sq, M, g2, be2, eps, momentum, rm2, rv2, nbt2)
         else:
             mean2, var2 = rm2.double(), rv2.double()
-        rstd2 = torch.rsqrt(var2 + eps)
-        sc2 = g2.double() * rstd2
-        a3 = ops.bn_apply(h3, sc2.float(), (be2.double() - mean2 * sc2).float(), relu=True)   # [M,512]
+            rstd2 = torch.rsqrt(var2 + eps)
+            sc2d = g2.double() * rstd2
+            sc2, sh2 = sc2d.float(), (be2.double() - mean2 * sc2d).float()
+            mean2, rstd2 = mean2.float(), rstd2.float()
+        a3 = ops.bn_apply(h3, sc2, sh2, relu=True)                                # [M,512]
         C = w4.shape[0]
         GK = BG if n_keep is None else int(n_keep)
         a3k = a3[:GK * k]
@@ -410,8 +398,8 @@ class PointNetEncoderFn(torch.autograd.Function):
         else:
             f4 = ops.gemm(a3k, shadow(w4).view(C, 512), bias=b4)                  # [GK*k,C]
             _, tokens, arg4 = ops.group_max(f4, k, want_bf16=False, want_f32=True)
-        ctx.save_for_backward(p, a1, f2, gmax, arg2, h3, a3, arg4, mean1.float(), rstd1.float(), mean2.float(),
-                              rstd2.float(), w1, b1, g1, be1, w2, b2, w3, b3, g2, be2, w4, b4)
+        ctx.save_for_backward(p, a1, f2, gmax, arg2, h3, a3, arg4, mean1, rstd1, mean2,
+                              rstd2, w1, b1, g1, be1, w2, b2, w3, b3, g2, be2, w4, b4)
         ctx.meta = (B, G, k, C, training, GK)
         return tokens.view(B, G, C) if n_keep is None else tokens
 

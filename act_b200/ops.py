@@ -356,3 +356,24 @@ def pn_conv1_bwd(dz, points, W, b, mean, rstd, gamma, dW, db):
     _lib.call("act_pn_conv1_bwd", dz, points, W, b, mean, rstd, gamma, _lib.ctypes.c_int64(M), s[0], s[1], dW, db)
     _count(2)
     return s[0], s[1]
+
+
+def pn_bn1_fold(mom9, M, W, b, gamma, beta, eps, momentum, rmean, rvar, nbt):
+    """-> (Wf [128,3], bf [128], mean [128], rstd [128]); running stats / counter updated in place."""
+    dev = W.device
+    o = torch.empty(128 * 6, dtype=torch.float32, device=dev)
+    Wf, bf, mean, rstd = o[:384].view(128, 3), o[384:512], o[512:640], o[640:768]
+    _lib.call("act_pn_bn1_fold", mom9, _lib.ctypes.c_int64(M), W, b, gamma, beta, float(eps), float(momentum), rmean,
+              rvar, nbt, Wf, bf, mean, rstd)
+    _count()
+    return Wf, bf, mean, rstd
+
+
+def bn_finalize(s1, s2, M, gamma, beta, eps, momentum, rmean, rvar, nbt):
+    """-> (scale, shift, mean, rstd) [C] each; running stats / counter updated in place."""
+    C = gamma.numel()
+    o = torch.empty(4, C, dtype=torch.float32, device=gamma.device)
+    _lib.call("act_bn_finalize", s1, s2, _lib.ctypes.c_int64(M), C, gamma, beta, float(eps), float(momentum), rmean, rvar,
+              nbt, o[0], o[1], o[2], o[3])
+    _count()
+    return o[0], o[1], o[2], o[3]

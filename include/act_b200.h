@@ -146,6 +146,17 @@ int act_colsum(const void *x, int x_fp32, int M, int N, int ld, float *out, void
 /* out9 (double) = {sum x, sum y, sum z, sum xx, xy, xz, yy, yz, zz} over points [M,3] f32: BatchNorm1's batch
  * statistics follow analytically from these because conv1 is linear in the 3-D input. */
 int act_pn_moments(const float *points, long long M, double *out9, void *stream);
+/* Train-mode BatchNorm1d(128) after conv1, from the input moments: outputs conv1 with BN1 folded in (Wf[128,3],
+ * bf[128]), the batch mean / rstd of the conv output (for the backward), and updates running_mean / running_var
+ * (momentum, unbiased variance) and num_batches_tracked (nullable) as nn.BatchNorm1d does. */
+int act_pn_bn1_fold(const double *mom9, long long M, const float *W, const float *b, const float *gamma,
+                    const float *beta, float eps, float momentum, float *running_mean, float *running_var,
+                    long long *num_batches_tracked, float *Wf, float *bf, float *mean, float *rstd, void *stream);
+/* Same bookkeeping for a BatchNorm whose statistics were reduced by act_bn_stats: -> scale = gamma*rstd,
+ * shift = beta - mean*scale (the operands of act_bn_apply), mean, rstd, running statistics. */
+int act_bn_finalize(const float *sum, const float *sumsq, long long M, int C, const float *gamma, const float *beta,
+                    float eps, float momentum, float *running_mean, float *running_var, long long *num_batches_tracked,
+                    float *scale, float *shift, float *mean, float *rstd, void *stream);
 /* out[M,128] bf16 = relu?(W[128,3] . p + b): first_conv[0] with BatchNorm1 folded into (W, b) + ReLU. */
 int act_pn_conv1(const float *points, const float *W, const float *b, long long M, int relu, void *out_bf16,
                  void *stream);
