@@ -62,6 +62,17 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *ba
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N_PENDING>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N_PENDING) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -162,19 +173,30 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 // Operands that do not depend on the accumulator (the residual row / the mul_in row) are PREFETCHED into
 // registers by epi_prefetch() before the accumulator is waited for -- for the next chunk while the current one
 // is processed -- because with one row per thread every such load is a full L2 round trip on the critical path.
+// Epilogue specialisation: MODE is a compile-time hint that fixes which optional parts exist, so that the hot
+// instantiations carry no flag tests, no dead register arrays and ~half the instructions per chunk (the epilogue
+// runs on 4-8 warps per SM: it is bound by its own dependent-instruction chains, not by memory).  E_GENERIC keeps
+// every part a runtime decision (any combination, used for the cold layouts).
+enum : int { E_GENERIC = 0, E_PLAIN, E_GELU, E_MULGELU, E_MULRELU, E_RESID, E_ATOMIC, E_GMAX };
+
 struct EpiPre {
     uint4 r[8];   // 128 B: either 32 f32 of the residual row or 32 bf16 of mul_in in r[0..3]
 };
 
+template <int MODE>
 __device__ __forceinline__ void epi_prefetch(const GemmEpi &epi, EpiPre &pre, int row, bool row_ok, int n, int N) {
+    constexpr bool G = MODE == E_GENERIC;
+    if (!G && MODE != E_MULGELU && MODE != E_MULRELU && MODE != E_RESID) return;
     if (!row_ok || n >= N) return;
     const int ncols = min(32, N - n);
-    if (epi.mul_mode) {
+    const bool has_mul = G ? (epi.mul_mode != 0) : (MODE == E_MULGELU || MODE == E_MULRELU);
+    const bool has_resid = G ? (epi.resid != nullptr) : (MODE == E_RESID);
+    if (has_mul) {
         const uint4 *mi = reinterpret_cast<const uint4 *>(epi.mul_in + (size_t)row * epi.ldm + n);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             if (j * 8 < ncols) pre.r[j] = __ldg(mi + j);
-    } else if (epi.resid) {
+    } else if (has_resid) {
         const uint4 *rp =
             reinterpret_cast<const uint4 *>(epi.resid + (size_t)(row / epi.resid_row_div) * epi.ldr + n);
 #pragma unroll
@@ -184,20 +206,33 @@ __device__ __forceinline__ void epi_prefetch(const GemmEpi &epi, EpiPre &pre, in
 }
 
 // gscratch: per-warp shared scratch [32][33] floats for the transposed group max (nullable -> redux path)
+// stage (nullable): per-warp shared tile [32 rows][32 cols] (bf16: 64 B rows, fp32: 128 B rows) that the caller
+// hands to a TMA store; when given, the final result goes there instead of straight to global memory.
+template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_t (&v)[32], const EpiPre &pre, int row,
-                                               bool row_ok, int n, int N, int lane, float *gscratch) {
+                                               bool row_ok, int n, int N, int lane, float *gscratch,
+                                               uint8_t *stage = nullptr) {
+    constexpr bool G = MODE == E_GENERIC;
     if (n >= N) return;                       // warp-uniform
-    const bool gmode = epi.gmax_f32 || epi.gmax_bf16 || epi.garg;
+    const bool gmode = G ? (epi.gmax_f32 || epi.gmax_bf16 || epi.garg) : (MODE == E_GMAX);
+    const int act_kind = G ? epi.act : (MODE == E_GELU ? 1 : 0);
+    const int mul_mode = G ? epi.mul_mode : (MODE == E_MULGELU ? 1 : (MODE == E_MULRELU ? 2 : 0));
+    const bool has_resid = G ? (epi.resid != nullptr) : (MODE == E_RESID);
+    const bool has_rscale = (G || MODE == E_RESID) ? (epi.row_scale != nullptr) : false;
+    const bool has_preact = (G || MODE == E_GELU) ? (epi.preact_out != nullptr) : false;
+    const bool atomic = G ? (epi.atomic != 0) : (MODE == E_ATOMIC);
+    const bool has_bias = (MODE == E_ATOMIC || MODE == E_MULGELU || MODE == E_MULRELU) ? false : (epi.bias != nullptr);
+    const bool out_fp32 = MODE == E_ATOMIC ? true : (epi.out_fp32 != 0);
     if (!row_ok && !gmode) return;
     float f[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-    if (epi.alpha != 1.f) {
+    if (G && epi.alpha != 1.f) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] *= epi.alpha;
     }
     const int ncols = min(32, N - n);   // N % 8 == 0 guaranteed by the host
-    if (epi.bias) {
+    if (has_bias) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
             if (j < ncols) {
@@ -246,7 +281,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_
         }
         if (!epi.out || !row_ok) return;
     }
-    if (epi.preact_out) {
+    if (has_preact) {
         __nv_bfloat16 *po = reinterpret_cast<__nv_bfloat16 *>(epi.preact_out) + (size_t)row * epi.ldo + n;
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
@@ -259,14 +294,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_
             }
         }
     }
-    if (epi.act == 1) {
+    if (act_kind == 1) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-    } else if (epi.act == 2) {
+    } else if (act_kind == 2) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
     }
-    if (epi.mul_mode) {
+    if (mul_mode) {
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
             if (j < ncols) {
@@ -274,7 +309,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const float2 u = __bfloat1622float2(h[t]);
-                    if (epi.mul_mode == 1) {
+                    if (mul_mode == 1) {
                         f[j + 2 * t] *= gelu_erf_grad(u.x);
                         f[j + 2 * t + 1] *= gelu_erf_grad(u.y);
                     } else {
@@ -285,13 +320,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_
             }
         }
     }
-    if (epi.row_scale) {
+    if (has_rscale) {
         const float rsc = __ldg(epi.row_scale + row / epi.rows_per_scale);
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] *= rsc;
     }
-    if (epi.resid) {
-        if (!epi.mul_mode) {
+    if (has_resid) {
+        if (!mul_mode) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 if (j < ncols) {
@@ -312,9 +347,28 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_
             }
         }
     }
-    if (epi.out_fp32) {
+    if (stage) {
+        // row-per-thread writes into the staging tile; columns past N are clipped by the TMA store
+        if (out_fp32) {
+            float4 *o = reinterpret_cast<float4 *>(stage + lane * 128);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else {
+            uint4 *o = reinterpret_cast<uint4 *>(stage + lane * 64);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint4 pk;
+                __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(f[8 * j + 2 * t], f[8 * j + 2 * t + 1]);
+                o[j] = pk;
+            }
+        }
+        return;
+    }
+    if (out_fp32) {
         float *o = reinterpret_cast<float *>(epi.out) + (size_t)row * epi.ldo + n;
-        if (epi.atomic) {
+        if (atomic) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
                 if (j < ncols)
@@ -342,7 +396,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_
 }
 
 // ------------------------------------------------------------------------------------- the kernel
-template <int BN, bool A_MN, bool B_MN, int STAGES>
+template <int BN, bool A_MN, bool B_MN, int STAGES, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                                  const __grid_constant__ CUtensorMap tma_b,
                                                                  const GemmEpi epi, int M, int N, int K,
@@ -432,12 +486,12 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_co
         const int row = m0 + quad * 32 + lane;
         const bool row_ok = row < M;
         EpiPre cur, nxt;
-        epi_prefetch(epi, cur, row, row_ok, n0, N);             // overlaps the whole main loop
+        epi_prefetch<MODE>(epi, cur, row, row_ok, n0, N);       // overlaps the whole main loop
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
-            if (c0 + 32 < BN) epi_prefetch(epi, nxt, row, row_ok, n0 + c0 + 32, N);
+            if (c0 + 32 < BN) epi_prefetch<MODE>(epi, nxt, row, row_ok, n0 + c0 + 32, N);
             uint32_t v[32];
             __syncwarp();
             if (nkb > 0) {
@@ -446,7 +500,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_co
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0u;
             }
-            epilogue_chunk(epi, v, cur, row, row_ok, n0 + c0, N, lane, nullptr);
+            epilogue_chunk<MODE>(epi, v, cur, row, row_ok, n0 + c0, N, lane, nullptr);
             cur = nxt;
         }
     }
@@ -467,10 +521,11 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_co
 // per SM instead of once per tile.
 constexpr int GEMM_P_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quadrant)
 
-template <int BN, bool A_MN, bool B_MN, int STAGES>
+template <int BN, bool A_MN, bool B_MN, int STAGES, int MODE>
 __global__ void __launch_bounds__(GEMM_P_THREADS, 1) gemm_bf16_persistent_kernel(
-    const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmEpi epi, int M,
-    int N, int K, int kb_per_split, int tiles_m, int tiles_n, int total_tiles) {
+    const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+    const __grid_constant__ CUtensorMap tma_out, int use_tma_store, const GemmEpi epi, int M, int N, int K,
+    int kb_per_split, int tiles_m, int tiles_n, int total_tiles) {
     constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
     constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -566,9 +621,13 @@ __global__ void __launch_bounds__(GEMM_P_THREADS, 1) gemm_bf16_persistent_kernel
         const int e = warp - 2;
         const int quad = warp & 3, half = e >> 2;
         // per-warp [32][33] fp32 scratch for the transposed group max, carved after the pipeline stages
-        float *gscratch = (epi.gmax_f32 || epi.gmax_bf16 || epi.garg)
-                              ? reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES) + e * (32 * 33)
-                              : nullptr;
+        const bool gm = MODE == E_GENERIC ? (epi.gmax_f32 || epi.gmax_bf16 || epi.garg) : (MODE == E_GMAX);
+        float *gscratch = gm ? reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES) + e * (32 * 33) : nullptr;
+        // output staging for the TMA store: 2 x 4 KB per warp (double-buffered against the in-flight bulk store)
+        constexpr uint32_t GS_BYTES = BN == 256 ? 0 : 8 * 32 * 33 * 4;      // the fused group max only runs with BN = 128
+        uint8_t *stage_base = smem + STAGES * STAGE_BYTES + GS_BYTES + e * 8192;
+        uint32_t nstore = 0;
+        if (use_tma_store && warp == 2 && lane == 0) tma_prefetch_desc(&tma_out);
         uint32_t lt = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
             const int n0 = (t % tiles_n) * BN, m0 = ((t / tiles_n) % tiles_m) * GEMM_BM;
@@ -578,23 +637,36 @@ __global__ void __launch_bounds__(GEMM_P_THREADS, 1) gemm_bf16_persistent_kernel
             constexpr int NCH = BN / 64;                              // 32-column chunks per epilogue warp
             const int cbase = n0 + half * (BN / 2);
             EpiPre cur, nxt;
-            epi_prefetch(epi, cur, row, row_ok, cbase, N);            // before the accumulator is waited for
+            epi_prefetch<MODE>(epi, cur, row, row_ok, cbase, N);      // before the accumulator is waited for
             mbar_wait(&tfull_bar[buf], (lt >> 1) & 1);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + buf * BN + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * (BN / 2));
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
-                if (c + 1 < NCH) epi_prefetch(epi, nxt, row, row_ok, cbase + (c + 1) * 32, N);
+                if (c + 1 < NCH) epi_prefetch<MODE>(epi, nxt, row, row_ok, cbase + (c + 1) * 32, N);
                 uint32_t v[32];
                 __syncwarp();
                 tmem_ld32(tmem_d + (uint32_t)(c * 32), v);
-                epilogue_chunk(epi, v, cur, row, row_ok, cbase + c * 32, N, lane, gscratch);
+                const int n = cbase + c * 32;
+                if (use_tma_store && n < N) {
+                    uint8_t *stage = stage_base + (nstore & 1) * 4096;
+                    if (lane == 0) bulk_wait_read<1>();      // the store issued two chunks ago has read its tile
+                    __syncwarp();
+                    epilogue_chunk<MODE>(epi, v, cur, row, row_ok, n, N, lane, gscratch, stage);
+                    fence_proxy_async();                     // generic-proxy smem writes -> visible to the TMA engine
+                    __syncwarp();
+                    if (lane == 0) tma_store_2d(&tma_out, stage, n, m0 + quad * 32);
+                    ++nstore;
+                } else {
+                    epilogue_chunk<MODE>(epi, v, cur, row, row_ok, n, N, lane, gscratch);
+                }
                 cur = nxt;
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);
         }
+        if (use_tma_store && lane == 0) bulk_wait_all();     // all bulk stores of this warp have completed
     }
     tc_fence_before();
     __syncthreads();
@@ -636,12 +708,12 @@ static int make_map(CUtensorMap *map, const void *ptr, long long rows, long long
     return r == CUDA_SUCCESS ? ACT_OK : ACT_EINVAL;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int MODE = E_GENERIC>
 static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmEpi &epi, int M, int N, int K,
                        int splits, cudaStream_t st) {
     constexpr int STAGES = BN > 128 ? 2 : 3;     // keep two CTAs resident per SM (<= ~113 KB each)
     constexpr size_t smem = (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024;
-    auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES>;
+    auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES, MODE>;
     ACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int total_kb = (K + GEMM_BK - 1) / GEMM_BK;
     const int kbps = (total_kb + splits - 1) / splits;
@@ -651,12 +723,35 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmE
     return ACT_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+// 2-D row-major output [rows, cols] (bf16 or fp32), box = 32 rows x 32 cols, no swizzle: the epilogue's TMA store
+static int make_out_map(CUtensorMap *map, const void *ptr, long long rows, long long cols, long long ld, bool fp32) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return ACT_EUNSUPPORTED;
+    const int es = fp32 ? 4 : 2;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * es) % 16) return ACT_EALIGN;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                     const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? ACT_OK : ACT_EINVAL;
+}
+
+template <int BN, bool A_MN, bool B_MN, int MODE = E_GENERIC>
 static int launch_gemm_persistent(const CUtensorMap &ta, const CUtensorMap &tb, const GemmEpi &epi, int M, int N, int K,
                                   int splits, cudaStream_t st) {
-    constexpr int STAGES = 4;
-    constexpr size_t smem = (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024 + 8 * 32 * 33 * 4;
-    auto kern = gemm_bf16_persistent_kernel<BN, A_MN, B_MN, STAGES>;
+    constexpr int STAGES = 3;
+    constexpr size_t smem =
+        (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024 + (BN == 256 ? 0 : 8 * 32 * 33 * 4) + 8 * 8192;
+    // results leave through smem + TMA bulk stores (full-line writes, no per-thread store wavefronts) whenever the
+    // epilogue has a plain tile output: not for split-K atomics, not with the pre-activation side output
+    CUtensorMap tout;
+    int use_tma_store = (epi.out && !epi.atomic && !epi.preact_out) ? 1 : 0;
+    if (use_tma_store && make_out_map(&tout, epi.out, M, N, epi.ldo, epi.out_fp32 != 0) != ACT_OK) use_tma_store = 0;
+    if (!use_tma_store) tout = ta;
+    auto kern = gemm_bf16_persistent_kernel<BN, A_MN, B_MN, STAGES, MODE>;
     ACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int total_kb = (K + GEMM_BK - 1) / GEMM_BK;
     const int kbps = (total_kb + splits - 1) / splits;
@@ -667,8 +762,8 @@ static int launch_gemm_persistent(const CUtensorMap &ta, const CUtensorMap &tb, 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = (int)(total < sms ? total : sms);
-    ACT_CUDA(launch_k(kern, dim3(grid), dim3(GEMM_P_THREADS), smem, st, true, ta, tb, epi, M, N, K, kbps, tiles_m,
-                      tiles_n, (int)total));
+    ACT_CUDA(launch_k(kern, dim3(grid), dim3(GEMM_P_THREADS), smem, st, true, ta, tb, tout, use_tma_store, epi, M, N, K,
+                      kbps, tiles_m, tiles_n, (int)total));
     return ACT_OK;
 }
 
@@ -723,6 +818,39 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
     rc = b_mn_major ? make_map(&tb, B, K, N, ldb, GEMM_BK) : make_map(&tb, B, N, K, ldb, BN);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    // epilogue mode (see the enum): the specialised instantiations below cover the hot layouts of the ACT step
+    int mode = E_GENERIC;
+    if (alpha == 1.f) {
+        const bool simple_out = !preact_out && !epi.mul_mode && !resid && !row_scale && !gmode && !epi.atomic;
+        if (simple_out && !act_kind) mode = E_PLAIN;
+        else if (act_kind == 1 && !epi.mul_mode && !resid && !row_scale && !gmode && !epi.atomic && !out_fp32) mode = E_GELU;
+        else if (epi.mul_mode && !bias && !act_kind && !preact_out && !resid && !row_scale && !gmode && !epi.atomic)
+            mode = epi.mul_mode == 1 ? E_MULGELU : E_MULRELU;
+        else if (resid && !act_kind && !preact_out && !epi.mul_mode && !gmode && !epi.atomic) mode = E_RESID;
+        else if (epi.atomic && !bias && !act_kind) mode = E_ATOMIC;
+        else if (gmode && !act_kind && !preact_out && !epi.mul_mode && !resid && !row_scale) mode = E_GMAX;
+    }
+    const int lay = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);     // 0 = K/K, 1 = K/MN (dgrad), 3 = MN/MN (wgrad)
+#define ACT_SPEC(P_, BN_, LAY_, MODE_)                                                                             \
+    if (persistent == P_ && BN == BN_ && lay == LAY_ && mode == MODE_) {                                           \
+        if (P_) return launch_gemm_persistent<BN_, (LAY_ & 2) != 0, (LAY_ & 1) != 0, MODE_>(ta, tb, epi, M, N, K, splits, st); \
+        return launch_gemm<BN_, (LAY_ & 2) != 0, (LAY_ & 1) != 0, MODE_>(ta, tb, epi, M, N, K, splits, st);           \
+    }
+    // one tile per CTA: transformer forward / dgrad / wgrad
+    ACT_SPEC(0, 128, 0, E_PLAIN) ACT_SPEC(0, 192, 0, E_PLAIN) ACT_SPEC(0, 64, 0, E_PLAIN)
+    ACT_SPEC(0, 128, 1, E_PLAIN) ACT_SPEC(0, 192, 1, E_PLAIN) ACT_SPEC(0, 64, 1, E_PLAIN)
+    ACT_SPEC(0, 128, 0, E_GELU) ACT_SPEC(0, 192, 0, E_GELU)
+    ACT_SPEC(0, 128, 1, E_MULGELU) ACT_SPEC(0, 192, 1, E_MULGELU)
+    ACT_SPEC(0, 128, 0, E_RESID) ACT_SPEC(0, 64, 0, E_RESID)
+    ACT_SPEC(0, 128, 3, E_ATOMIC) ACT_SPEC(0, 192, 3, E_ATOMIC) ACT_SPEC(0, 64, 3, E_ATOMIC)
+    // persistent: mini-PointNet convs and the decoder-sized GEMMs
+    ACT_SPEC(1, 256, 0, E_PLAIN) ACT_SPEC(1, 128, 0, E_PLAIN) ACT_SPEC(1, 256, 1, E_PLAIN) ACT_SPEC(1, 128, 1, E_PLAIN)
+    ACT_SPEC(1, 256, 0, E_RESID) ACT_SPEC(1, 128, 0, E_RESID)
+    ACT_SPEC(1, 256, 1, E_MULRELU) ACT_SPEC(1, 128, 1, E_MULRELU)
+    ACT_SPEC(1, 256, 1, E_MULGELU) ACT_SPEC(1, 128, 0, E_GELU) ACT_SPEC(1, 256, 0, E_GELU)
+    ACT_SPEC(1, 128, 0, E_GMAX)
+    ACT_SPEC(1, 128, 3, E_ATOMIC) ACT_SPEC(1, 256, 3, E_ATOMIC)
+#undef ACT_SPEC
 #define ACT_GEMM_DISPATCH(BN_)                                                                         \
     do {                                                                                               \
         if (!a_mn_major && !b_mn_major) return launch_gemm<BN_, false, false>(ta, tb, epi, M, N, K, splits, st); \
