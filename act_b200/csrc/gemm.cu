@@ -186,7 +186,9 @@ struct EpiPre {
 template <int MODE>
 __device__ __forceinline__ void epi_prefetch(const GemmEpi &epi, EpiPre &pre, int row, bool row_ok, int n, int N) {
     constexpr bool G = MODE == E_GENERIC;
-    if (!G && MODE != E_MULGELU && MODE != E_MULRELU && MODE != E_RESID) return;
+    // E_RESID: the specialised kernels run 16 epilogue warps under a 96-register cap; 32 staged fp32 values x 2
+    // buffers would spill, so the residual row is loaded in place (the extra warps hide the latency instead)
+    if (!G && MODE != E_MULGELU && MODE != E_MULRELU) return;
     if (!row_ok || n >= N) return;
     const int ncols = min(32, N - n);
     const bool has_mul = G ? (epi.mul_mode != 0) : (MODE == E_MULGELU || MODE == E_MULRELU);
@@ -199,13 +201,19 @@ __device__ __forceinline__ void epi_prefetch(const GemmEpi &epi, EpiPre &pre, in
     } else if (has_resid) {
         const uint4 *rp =
             reinterpret_cast<const uint4 *>(epi.resid + (size_t)(row / epi.resid_row_div) * epi.ldr + n);
+        if (epi.resid_row_div != 1) {                     // broadcast row (never aliases out): read-only path
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (j * 4 < ncols) pre.r[j] = rp[j];          // plain load: resid may alias out
+            for (int j = 0; j < 8; ++j)
+                if (j * 4 < ncols) pre.r[j] = __ldg(rp + j);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j * 4 < ncols) pre.r[j] = rp[j];      // plain load: resid may alias out
+        }
     }
 }
 
-// gscratch: per-warp shared scratch [32][33] floats for the transposed group max (nullable -> redux path)
+// gscratch: per-warp shared scratch [32][32] floats (XOR-swizzled) for the transposed group max (nullable -> redux path)
 // stage (nullable): per-warp shared tile [32 rows][32 cols] (bf16: 64 B rows, fp32: 128 B rows) that the caller
 // hands to a TMA store; when given, the final result goes there instead of straight to global memory.
 template <int MODE>
@@ -247,17 +255,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_
         int barg;
         const bool any_ok = __any_sync(0xffffffffu, row_ok);
         if (gscratch) {
-            // transpose through shared memory: lane = row writes its 32 columns (pitch 33: conflict-free), then
-            // lane = column scans the 32 rows
+            // transpose through shared memory: lane = row writes its 32 columns (XOR-swizzled: conflict-free both
+            // ways), then lane = column scans the 32 rows
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) gscratch[lane * 33 + j] = row_ok ? f[j] : -INFINITY;
+            for (int j = 0; j < 32; ++j) gscratch[lane * 32 + (j ^ lane)] = row_ok ? f[j] : -INFINITY;
             __syncwarp();
-            best = gscratch[lane];
+            best = gscratch[lane];            // row 0: column index lane ^ 0
             barg = 0;
 #pragma unroll
             for (int r = 1; r < 32; ++r) {
-                const float x = gscratch[r * 33 + lane];
+                const float x = gscratch[r * 32 + (lane ^ r)];
                 if (x > best) { best = x; barg = r; }
             }
         } else {
@@ -326,7 +334,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_
         for (int j = 0; j < 32; ++j) f[j] *= rsc;
     }
     if (has_resid) {
-        if (!mul_mode) {
+        if (G && !mul_mode) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 if (j < ncols) {
@@ -336,7 +344,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_
                 }
             }
         } else {
-            // the rare resid + mul_in combination: direct loads
+            // E_RESID (no staging registers), or the rare resid + mul_in combination: direct loads
             const float *r = epi.resid + (size_t)(row / epi.resid_row_div) * epi.ldr + n;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -519,10 +527,22 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_co
 // accumulator is double-buffered in TMEM (2 x BN columns) so the 8 epilogue warps drain tile i while the TMA
 // producer and the MMA issuer already work on tile i+1; barrier setup and the TMEM allocation are paid once
 // per SM instead of once per tile.
-constexpr int GEMM_P_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quadrant)
+// warp 0 TMA, warp 1 MMA, warps 2.. epilogue: EW = 8 (generic epilogue, register-heavy) or 16 (specialised
+// epilogues fit 96 registers, so twice the warps hide the epilogue's dependent-instruction latency)
+template <int MODE>
+struct PersistCfg {
+    static constexpr int EW = MODE == E_GENERIC ? 8 : 16;
+    static constexpr int THREADS = (2 + EW) * 32;
+    static constexpr int STAGES = 3;
+    static constexpr bool HAS_GS = MODE == E_GENERIC || MODE == E_GMAX;    // [32][33] fp32 scratch per epilogue warp
+    static constexpr size_t smem(int BN) {
+        return (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024 +
+               ((HAS_GS && BN == 128) ? (size_t)EW * 32 * 32 * 4 : 0) + (size_t)EW * 4096;
+    }
+};
 
 template <int BN, bool A_MN, bool B_MN, int STAGES, int MODE>
-__global__ void __launch_bounds__(GEMM_P_THREADS, 1) gemm_bf16_persistent_kernel(
+__global__ void __launch_bounds__(PersistCfg<MODE>::THREADS, 1) gemm_bf16_persistent_kernel(
     const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
     const __grid_constant__ CUtensorMap tma_out, int use_tma_store, const GemmEpi epi, int M, int N, int K,
     int kb_per_split, int tiles_m, int tiles_n, int total_tiles) {
@@ -546,7 +566,7 @@ __global__ void __launch_bounds__(GEMM_P_THREADS, 1) gemm_bf16_persistent_kernel
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull_bar[b], 1);
-            mbar_init(&tempty_bar[b], 8);
+            mbar_init(&tempty_bar[b], PersistCfg<MODE>::EW);
         }
         fence_mbar_init();
     }
@@ -618,15 +638,22 @@ __global__ void __launch_bounds__(GEMM_P_THREADS, 1) gemm_bf16_persistent_kernel
             }
         }
     } else {
+        constexpr int EW = PersistCfg<MODE>::EW;
+        constexpr int WCOLS = BN / (EW / 4);                        // columns of the tile owned by one epilogue warp
         const int e = warp - 2;
-        const int quad = warp & 3, half = e >> 2;
+        const int quad = warp & 3, part = e >> 2;
         // per-warp [32][33] fp32 scratch for the transposed group max, carved after the pipeline stages
+        constexpr bool HAS_GS = PersistCfg<MODE>::HAS_GS && BN == 128;      // the fused group max only runs with BN = 128
         const bool gm = MODE == E_GENERIC ? (epi.gmax_f32 || epi.gmax_bf16 || epi.garg) : (MODE == E_GMAX);
-        float *gscratch = gm ? reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES) + e * (32 * 33) : nullptr;
-        // output staging for the TMA store: 2 x 4 KB per warp (double-buffered against the in-flight bulk store)
-        constexpr uint32_t GS_BYTES = BN == 256 ? 0 : 8 * 32 * 33 * 4;      // the fused group max only runs with BN = 128
-        uint8_t *stage_base = smem + STAGES * STAGE_BYTES + GS_BYTES + e * 8192;
+        float *gscratch = (gm && HAS_GS) ? reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES) + e * (32 * 32) : nullptr;
+        // output staging for the TMA store, 4 KB per warp: two 2 KB bf16 tiles (double-buffered against the bulk
+        // store in flight) or one 4 KB fp32 tile
+        constexpr uint32_t GS_BYTES = HAS_GS ? EW * 32 * 32 * 4 : 0;
+        uint8_t *stage_base = smem + STAGES * STAGE_BYTES + GS_BYTES + e * 4096;
+        const bool st_fp32 = MODE == E_ATOMIC ? true : (epi.out_fp32 != 0);
         uint32_t nstore = 0;
+        EpiPre cur, nxt;
+        bool have_pre = false;
         if (use_tma_store && warp == 2 && lane == 0) tma_prefetch_desc(&tma_out);
         uint32_t lt = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
@@ -634,23 +661,36 @@ __global__ void __launch_bounds__(GEMM_P_THREADS, 1) gemm_bf16_persistent_kernel
             const uint32_t buf = lt & 1;
             const int row = m0 + quad * 32 + lane;
             const bool row_ok = row < M;
-            constexpr int NCH = BN / 64;                              // 32-column chunks per epilogue warp
-            const int cbase = n0 + half * (BN / 2);
-            EpiPre cur, nxt;
-            epi_prefetch<MODE>(epi, cur, row, row_ok, cbase, N);      // before the accumulator is waited for
+            constexpr int NCH = WCOLS / 32;                           // 32-column chunks per epilogue warp
+            const int cbase = n0 + part * WCOLS;
+            // epilogue operands (residual / mul_in rows) are prefetched one chunk ahead ACROSS tiles: the first
+            // chunk of the next tile is requested while the last chunk of this one is processed
+            if (!have_pre) epi_prefetch<MODE>(epi, cur, row, row_ok, cbase, N);
             mbar_wait(&tfull_bar[buf], (lt >> 1) & 1);
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + buf * BN + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * (BN / 2));
+            const uint32_t tmem_d = tmem_base + buf * BN + ((uint32_t)(quad * 32) << 16) + (uint32_t)(part * WCOLS);
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
-                if (c + 1 < NCH) epi_prefetch<MODE>(epi, nxt, row, row_ok, cbase + (c + 1) * 32, N);
+                if (c + 1 < NCH) {
+                    epi_prefetch<MODE>(epi, nxt, row, row_ok, cbase + (c + 1) * 32, N);
+                } else {
+                    const int t2 = t + gridDim.x;
+                    have_pre = t2 < total_tiles;
+                    if (have_pre) {
+                        const int row2 = ((t2 / tiles_n) % tiles_m) * GEMM_BM + quad * 32 + lane;
+                        epi_prefetch<MODE>(epi, nxt, row2, row2 < M, (t2 % tiles_n) * BN + part * WCOLS, N);
+                    }
+                }
                 uint32_t v[32];
                 __syncwarp();
                 tmem_ld32(tmem_d + (uint32_t)(c * 32), v);
                 const int n = cbase + c * 32;
                 if (use_tma_store && n < N) {
-                    uint8_t *stage = stage_base + (nstore & 1) * 4096;
-                    if (lane == 0) bulk_wait_read<1>();      // the store issued two chunks ago has read its tile
+                    uint8_t *stage = st_fp32 ? stage_base : stage_base + (nstore & 1) * 2048;
+                    if (lane == 0) {                         // the bulk store that last used this tile has read it
+                        if (st_fp32) bulk_wait_read<0>();
+                        else bulk_wait_read<1>();
+                    }
                     __syncwarp();
                     epilogue_chunk<MODE>(epi, v, cur, row, row_ok, n, N, lane, gscratch, stage);
                     fence_proxy_async();                     // generic-proxy smem writes -> visible to the TMA engine
@@ -742,9 +782,8 @@ static int make_out_map(CUtensorMap *map, const void *ptr, long long rows, long 
 template <int BN, bool A_MN, bool B_MN, int MODE = E_GENERIC>
 static int launch_gemm_persistent(const CUtensorMap &ta, const CUtensorMap &tb, const GemmEpi &epi, int M, int N, int K,
                                   int splits, cudaStream_t st) {
-    constexpr int STAGES = 3;
-    constexpr size_t smem =
-        (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024 + (BN == 256 ? 0 : 8 * 32 * 33 * 4) + 8 * 8192;
+    constexpr int STAGES = PersistCfg<MODE>::STAGES;
+    constexpr size_t smem = PersistCfg<MODE>::smem(BN);
     // results leave through smem + TMA bulk stores (full-line writes, no per-thread store wavefronts) whenever the
     // epilogue has a plain tile output: not for split-K atomics, not with the pre-activation side output
     CUtensorMap tout;
@@ -762,7 +801,7 @@ static int launch_gemm_persistent(const CUtensorMap &ta, const CUtensorMap &tb, 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = (int)(total < sms ? total : sms);
-    ACT_CUDA(launch_k(kern, dim3(grid), dim3(GEMM_P_THREADS), smem, st, true, ta, tb, tout, use_tma_store, epi, M, N, K,
+    ACT_CUDA(launch_k(kern, dim3(grid), dim3(PersistCfg<MODE>::THREADS), smem, st, true, ta, tb, tout, use_tma_store, epi, M, N, K,
                       kbps, tiles_m, tiles_n, (int)total));
     return ACT_OK;
 }
@@ -833,8 +872,10 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
     const int lay = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);     // 0 = K/K, 1 = K/MN (dgrad), 3 = MN/MN (wgrad)
 #define ACT_SPEC(P_, BN_, LAY_, MODE_)                                                                             \
     if (persistent == P_ && BN == BN_ && lay == LAY_ && mode == MODE_) {                                           \
-        if (P_) return launch_gemm_persistent<BN_, (LAY_ & 2) != 0, (LAY_ & 1) != 0, MODE_>(ta, tb, epi, M, N, K, splits, st); \
-        return launch_gemm<BN_, (LAY_ & 2) != 0, (LAY_ & 1) != 0, MODE_>(ta, tb, epi, M, N, K, splits, st);           \
+        if constexpr (P_ != 0)                                                                                     \
+            return launch_gemm_persistent<BN_, (LAY_ & 2) != 0, (LAY_ & 1) != 0, MODE_>(ta, tb, epi, M, N, K, splits, st); \
+        else                                                                                                       \
+            return launch_gemm<BN_, (LAY_ & 2) != 0, (LAY_ & 1) != 0, MODE_>(ta, tb, epi, M, N, K, splits, st);       \
     }
     // one tile per CTA: transformer forward / dgrad / wgrad
     ACT_SPEC(0, 128, 0, E_PLAIN) ACT_SPEC(0, 192, 0, E_PLAIN) ACT_SPEC(0, 64, 0, E_PLAIN)
