@@ -91,8 +91,12 @@ class FlatParams:
     1-D tensors, `.bias`, and names containing `token`).  Each tensor is padded to a multiple of 8 elements so
     every bf16 shadow starts 16-byte aligned (TMA requirement)."""
 
-    def __init__(self, module, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05):
-        named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+    def __init__(self, module, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05, exclude=()):
+        """exclude: name prefixes of parameters that never receive a gradient on this path (the student's unused
+        `lm_head` / `cls_head`).  torch.optim.AdamW skips parameters whose .grad is None -- no
+        moment update and NO weight decay -- so they are left out of the flat buffers and stay untouched."""
+        named = [(n, p) for n, p in module.named_parameters()
+                 if p.requires_grad and not any(n.startswith(e) for e in exclude)]
         if not named:
             raise ValueError("no trainable parameters")
         dev = named[0][1].device

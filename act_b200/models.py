@@ -90,6 +90,10 @@ class ACT_PointDistillation(nn.Module):
         else:
             raise NotImplementedError("mask_ratio 0 (no decoder) is not part of the hot path")
 
+    # trainable parameters that never get a gradient in the distillation step (act.py:187-196: token-classification
+    # and contrast heads of the Point-BERT lineage); pass to layers.FlatParams(exclude=...)
+    UNUSED_PARAMETERS = ("ACT_encoder.lm_head.", "ACT_encoder.cls_head.")
+
     def _apply(self, fn, *a, **k):
         super()._apply(fn, *a, **k)
         if isinstance(self.teacher, nn.Module):

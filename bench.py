@@ -126,7 +126,7 @@ def run_ours(args):
     cfg = models.default_config(mask_ratio=MASK_RATIO, drop_path_rate=DROP_PATH, num_group=N_GROUP,
                                 group_size=GROUP_SIZE)
     model = models.ACT_PointDistillation(cfg).to(dev).train()
-    fp = layers.FlatParams(model, lr=1e-3, weight_decay=0.05)
+    fp = layers.FlatParams(model, lr=1e-3, weight_decay=0.05, exclude=model.UNUSED_PARAMETERS)
     dp.broadcast_params(fp)
 
     n_batches = 4

@@ -63,7 +63,7 @@ def build_student(seed=4, flat=False, **kw):
     model = models.ACT_PointDistillation(cfg)
     ref_model.fill_params(model, seed=seed)
     model = model.cuda().train()
-    fp = layers.FlatParams(model) if flat else None
+    fp = layers.FlatParams(model, exclude=model.UNUSED_PARAMETERS) if flat else None
     return model, fp
 
 
@@ -129,7 +129,7 @@ def test_full_size_step_properties():
     np.random.seed(0)
     cfg = models.default_config(mask_ratio=0.6, drop_path_rate=0.1)
     model = models.ACT_PointDistillation(cfg).cuda().train()
-    fp = layers.FlatParams(model)
+    fp = layers.FlatParams(model, exclude=model.UNUSED_PARAMETERS)
     pts = ref_model.synthetic_clouds(128, 1024).cuda()
     loss = model(pts)
     loss.backward()
@@ -137,10 +137,10 @@ def test_full_size_step_properties():
     for n, p in zip(fp.names, fp.params):
         gmax = p.grad.abs().max().item()
         assert np.isfinite(gmax), n
-        if "lm_head" in n or "cls_head" in n:
-            assert gmax == 0.0, n
-        elif not (n.endswith("first_conv.0.bias") or n.endswith("second_conv.0.bias")):
+        assert "lm_head" not in n and "cls_head" not in n        # excluded: torch AdamW would skip them too
+        if not (n.endswith("first_conv.0.bias") or n.endswith("second_conv.0.bias")):
             assert gmax > 0.0, n
+    assert model.ACT_encoder.lm_head.weight.grad is None
     assert model.ACT_encoder.encoder.first_conv[1].num_batches_tracked.item() == 1
 
 
@@ -154,7 +154,7 @@ def test_engine_graph_replay_matches_eager():
         np.random.seed(0)
         cfg = models.default_config(mask_ratio=0.6, drop_path_rate=0.0)
         model = ref_model.fill_params(models.ACT_PointDistillation(cfg), seed=3).cuda().train()
-        fp = layers.FlatParams(model, lr=1e-3)
+        fp = layers.FlatParams(model, lr=1e-3, exclude=model.UNUSED_PARAMETERS)
         eng = PretrainStep(model, fp, 8, 1024, use_graph=use_graph).capture()
         pts = ref_model.synthetic_clouds(8, 1024, seed=1)
         out = []
