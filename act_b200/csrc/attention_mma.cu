@@ -357,6 +357,7 @@ static int launch_fwd(const __nv_bfloat16 *qkv, int B, int T, int H, float scale
                       cudaStream_t st) {
     constexpr size_t smem = (size_t)(2 * TP * MA_PITCH + MA_D * (TP + 8)) * 2;
     auto kern = attn_mma_fwd_kernel<TP>;
+    if (smem > 48 * 1024) ACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int npairs = B * H;
     ACT_CUDA(launch_k(kern, dim3(npairs), dim3((TP / 16) * 32), smem, st, true, qkv, T, H, npairs, scale, o, lse));
     return ACT_OK;
@@ -383,7 +384,8 @@ int attention_mma_fwd(const void *qkv, int B, int T, int H, float scale, void *o
     const __nv_bfloat16 *p = reinterpret_cast<const __nv_bfloat16 *>(qkv);
     __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(o);
     if (T <= 32) return launch_fwd<32>(p, B, T, H, scale, op, lse, st);
-    return launch_fwd<64>(p, B, T, H, scale, op, lse, st);
+    if (T <= 64) return launch_fwd<64>(p, B, T, H, scale, op, lse, st);
+    return launch_fwd<128>(p, B, T, H, scale, op, lse, st);     // the teacher's ViT: 64 prompts + 64 tokens
 }
 
 int attention_mma_bwd(const void *qkv, const void *o, const void *dO, const float *lse, int B, int T, int H, float scale,

@@ -566,12 +566,12 @@ namespace act {
 int attention_mma_fwd(const void *qkv, int B, int T, int H, float scale, void *o, float *lse, cudaStream_t st);
 int attention_mma_bwd(const void *qkv, const void *o, const void *dO, const float *lse, int B, int T, int H, float scale,
                       void *dqkv, float *delta, cudaStream_t st);
-inline bool attn_use_mma(int T) {
+inline bool attn_use_mma(int T, bool backward) {
     static const int on = [] {
         const char *e = std::getenv("ACT_B200_ATTN_MMA");
         return (e && e[0] == '0') ? 0 : 1;
     }();
-    return on && T <= 64;
+    return on && T <= (backward ? 64 : 128);      // forward-only T <= 128: the frozen teacher's ViT blocks
 }
 }  // namespace act
 
@@ -582,7 +582,7 @@ extern "C" int act_attention_fwd(const void *qkv, int B, int T, int H, int head_
     if (head_dim != AT_D) return ACT_EUNSUPPORTED;
     if (B == 0) return ACT_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (attn_use_mma(T) && lse) return attention_mma_fwd(qkv, B, T, H, scale, o, lse, st);
+    if (attn_use_mma(T, false)) return attention_mma_fwd(qkv, B, T, H, scale, o, lse, st);
     const __nv_bfloat16 *p = reinterpret_cast<const __nv_bfloat16 *>(qkv);
     __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(o);
     if (T <= 16) {
@@ -602,7 +602,7 @@ extern "C" int act_attention_bwd(const void *qkv, const void *o, const void *dO,
     if (head_dim != AT_D) return ACT_EUNSUPPORTED;
     if (B == 0) return ACT_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (attn_use_mma(T)) return attention_mma_bwd(qkv, o, dO, lse, B, T, H, scale, dqkv, delta, st);
+    if (attn_use_mma(T, true)) return attention_mma_bwd(qkv, o, dO, lse, B, T, H, scale, dqkv, delta, st);
     const __nv_bfloat16 *p = reinterpret_cast<const __nv_bfloat16 *>(qkv);
     const __nv_bfloat16 *op = reinterpret_cast<const __nv_bfloat16 *>(o);
     const __nv_bfloat16 *gp = reinterpret_cast<const __nv_bfloat16 *>(dO);

@@ -77,6 +77,14 @@ class ACT_PointDistillation(nn.Module):
         self.decoder_depth, self.decoder_num_heads = tc.decoder_depth, tc.decoder_num_heads
         # teacher: not registered as a submodule -> not in state_dict / not trained (the reference keeps its frozen
         # teacher under `dvae_tokenizer.*`; loading such a checkpoint needs strict=False)
+        if teacher == "native":
+            # the frozen Stage-I teacher on act_b200 kernels, under the reference's attribute name, so a Stage-II
+            # state_dict has the reference's `dvae_tokenizer.*` keys (act.py:1151-1160); frozen like the reference
+            from .teacher import ACTPromptedDiscreteVAEwithVIT
+            self.dvae_tokenizer = ACTPromptedDiscreteVAEwithVIT(dc)
+            for p in self.dvae_tokenizer.parameters():
+                p.requires_grad = False
+            teacher = self.dvae_tokenizer.forward_tokenizer_features
         object.__setattr__(self, "teacher", teacher if teacher is not None else SyntheticTeacher(dc.tokens_dims))
         self.group_divider = Group(num_group=self.num_group, group_size=self.group_size)
         self.proj_head = nn.Linear(self.embed_dim, dc.tokens_dims)

@@ -377,3 +377,30 @@ def bn_finalize(s1, s2, M, gamma, beta, eps, momentum, rmean, rvar, nbt):
               nbt, o[0], o[1], o[2], o[3])
     _count()
     return o[0], o[1], o[2], o[3]
+
+
+# ------------------------------------------------------------------------------ frozen teacher (DGCNN) pieces
+def dgcnn_edge_gn(pq, idx4, gamma, beta, B, G, Cp, eps, slope, out_view):
+    """out_view: bf16 [B*G, Cp] view (row pitch = stride(0)) receiving max_k LeakyReLU(GroupNorm(P[nbr] + Q[self]))."""
+    assert pq.dtype == torch.float32 and pq.is_contiguous() and pq.shape == (B * G, 2 * Cp)
+    assert out_view.dtype == torch.bfloat16 and out_view.stride(1) == 1
+    _lib.call("act_dgcnn_edge_gn", pq, idx4, gamma, beta, B, G, Cp, idx4.shape[-1], 4, float(eps), float(slope),
+              _p(out_view), out_view.stride(0))
+    _count()
+    return out_view
+
+
+def gn_rows(x, gamma, beta, B, R, eps, slope, noise=None):
+    """GroupNorm(4)+LeakyReLU over x bf16 [B*R, C].  noise None -> activations f32 [B*R, C];
+    noise f32 [B*R, C] -> labels i32 [B*R] = argmax(activation + noise)."""
+    C = x.shape[1]
+    stats = torch.empty(B, 4, 2, dtype=torch.float32, device=x.device)
+    if noise is None:
+        out = torch.empty(B * R, C, dtype=torch.float32, device=x.device)
+        _lib.call("act_gn_rows", x, gamma, beta, B, R, C, 4, float(eps), float(slope), stats, out, None, None)
+        _count(2)
+        return out
+    label = torch.empty(B * R, dtype=torch.int32, device=x.device)
+    _lib.call("act_gn_rows", x, gamma, beta, B, R, C, 4, float(eps), float(slope), stats, None, noise, label)
+    _count(2)
+    return label

@@ -189,6 +189,23 @@ int act_pn_conv1_bwd(const void *dz_bf16, const float *points, const float *W, c
                      const float *rstd, const float *gamma, long long M, float *s1, float *s2, float *dW, float *db,
                      void *stream);
 
+/* ---- Frozen teacher: DGCNN edge-conv layers, /root/reference/models/dvae.py:26-117 -------- */
+
+/* One DGCNN layer after its GEMM.  pq f32 [B*G, 2*Cp] = (P | Q) with P = x.Wa^T, Q = x.(Wb-Wa)^T (the 1x1 conv over
+ * the edge feature cat(x_k - x_q, x_q) split by linearity); idx i64 [B,G,kn] = kNN of each centre among the centres
+ * (kn must be 4).  Forms y = P[neighbour] + Q[self], GroupNorm(groups) over (G x kn x Cp/groups) per sample,
+ * LeakyReLU(slope), max over the kn neighbours -> out bf16 [B*G, Cp] written with row pitch ldo (a column slot of the
+ * concatenated feature buffer layer5 reads). */
+int act_dgcnn_edge_gn(const float *pq, const long long *idx, const float *gamma, const float *beta, int B, int G,
+                      int Cp, int kn, int groups, float eps, float slope, void *out_bf16, int ldo, void *stream);
+
+/* GroupNorm(groups) + LeakyReLU over x bf16 [B*R, C] (statistics per sample and channel group over R rows; DGCNN
+ * layer5, dvae.py:53-56).  stats f32 [B,groups,2] is scratch (mean, rstd).  out_f32 (nullable) [B*R, C] receives the
+ * activations; noise + label (nullable pair): label[row] = argmax_c(activation + noise[row,c]) -- the forward value of
+ * F.gumbel_softmax(hard=True) (dvae.py:587) without materialising the one-hot. */
+int act_gn_rows(const void *x_bf16, const float *gamma, const float *beta, int B, int R, int C, int groups, float eps,
+                float slope, float *stats, float *out_f32, const float *noise, int *label, void *stream);
+
 /* ---- Loss and optimizer ------------------------------------------------------------------------------ */
 
 /* Cosine distillation loss of ACT_PointDistillation.forward (/root/reference/models/act.py:1243-1254):

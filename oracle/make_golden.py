@@ -161,6 +161,63 @@ def gen_student_step():
     print("student_step.npz loss", loss.item(), "n grads", len(names))
 
 
+def teacher_noise(B, G, num_tokens, depth, P, seed=31):
+    """Fixed gumbel noise and prompt-dropout keep masks shared by the golden run, the oracle and the GPU tests."""
+    rng = np.random.default_rng(seed)
+    gumbel = torch.from_numpy(rng.gumbel(size=(B, G, num_tokens)).astype(np.float32))
+    keeps = [torch.from_numpy((rng.random((B, P, 768)) >= 0.1).astype(np.float32)) for _ in range(depth)]
+    return gumbel, keeps
+
+
+def run_reference_teacher(nb, center, seed=6):
+    """The UNMODIFIED ACTPromptedDiscreteVAEwithVIT.forward_tokenizer_features (dvae.py:584-592) in train mode, with
+    its two RNG consumers (F.gumbel_softmax, prompt_dropout) replaced by the fixed noise of teacher_noise()."""
+    import models.dvae as dvae
+    cfg = shims.easydict(dict(group_size=32, num_group=64, encoder_dims=384, tokens_dims=384, decoder_dims=384,
+                              num_tokens=8192, visual_embed_type="vit_base_patch16_384", visual_embed_dim=768,
+                              freeze_visual_embed=True, num_prompt_token=64, use_deep_prompt=True))
+    model = dvae.ACTPromptedDiscreteVAEwithVIT(cfg)
+    fill_params(model, seed=seed)
+    model.train()
+    B, G = center.shape[:2]
+    gumbel, keeps = teacher_noise(B, G, 8192, 12, 64)
+    calls = {"i": 0}
+
+    class FixedDrop(torch.nn.Module):
+        def forward(self, t):
+            k = keeps[calls["i"]]
+            calls["i"] += 1
+            return t * k / 0.9
+
+    model.prompt_dropout = FixedDrop()
+    orig = dvae.F.gumbel_softmax
+    labels = {}
+
+    def fixed_gumbel(logits, tau=1.0, hard=False, dim=-1):
+        idx = (logits + gumbel).argmax(dim)
+        labels["idx"], labels["logits"] = idx, logits
+        return torch.nn.functional.one_hot(idx, logits.shape[dim]).to(logits.dtype)
+
+    dvae.F.gumbel_softmax = fixed_gumbel
+    try:
+        with torch.no_grad():
+            feat = model.forward_tokenizer_features(nb, center, return_global=True)
+    finally:
+        dvae.F.gumbel_softmax = orig
+    return model, feat, labels
+
+
+def gen_teacher():
+    g = np.load(os.path.join(GOLD, "group.npz"))
+    nb = torch.from_numpy(g["shapenet/neighborhood"][:2])
+    center = torch.from_numpy(g["shapenet/center"][:2])
+    _, feat, labels = run_reference_teacher(nb, center)
+    lg = labels["logits"]
+    np.savez_compressed(os.path.join(GOLD, "teacher.npz"), feature=feat.numpy(), labels=labels["idx"].numpy().astype(np.int32),
+                        logits_sample=lg[:, ::8, ::64].numpy(), logits_absmean=np.float32(lg.abs().mean().item()))
+    print("teacher.npz", feat.abs().mean().item(), labels["idx"][0, :6].tolist())
+
+
 def main():
     if not os.path.isdir(shims.REFERENCE_ROOT):
         sys.exit("needs /root/reference (authoring container only)")
@@ -171,6 +228,7 @@ def main():
     gen_block_cfg1()
     gen_encoder()
     gen_student_step()
+    gen_teacher()
 
 
 if __name__ == "__main__":

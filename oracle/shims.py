@@ -151,7 +151,12 @@ def install():
     timm.models.layers.trunc_normal_ = _trunc_normal_
     timm.scheduler = _mod("timm.scheduler")
     timm.scheduler.CosineLRScheduler = object
-    timm.create_model = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("no timm teacher offline"))
+    def _create_model(name, pretrained=False, **k):
+        # stand-in for timm.create_model('vit_base_patch16_384'): random-weight ViT-B blocks (no pretrained weights
+        # offline); the reference only touches .blocks / .norm / .embed_dim (models/dvae.py:405-411)
+        from .ref_teacher import FakeTimmViT
+        return FakeTimmViT(768, 12, 12)
+    timm.create_model = _create_model
     lightly = _mod("lightly")
     lightly.loss = _mod("lightly.loss")
     lightly.loss.NegativeCosineSimilarity = _NegCos
