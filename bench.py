@@ -2,10 +2,12 @@
 """bench.py -- ACT Stage-II masked-point-modeling training step on B200 (BASELINE.json configs[1]/[3]).
 
 One "step" = Group tokenizer (FPS + kNN) -> mini-PointNet embed -> 12-block student encoder -> 2-block decoder
--> proj head -> cosine distillation loss -> backward -> (N>1: one NCCL all-reduce of the flat gradient) ->
-fused AdamW, on B=128 synthetic ShapeNet-shaped clouds per GPU (N=1024, G=64, k=32, d=384, mask 0.6,
-drop_path 0.1), bf16 tensor-core operands / fp32 accumulation and master weights.  The frozen teacher is replaced
-by a synthetic target (the teacher is row f1, "next").
+-> frozen teacher forward (mini-PointNet + DGCNN x2 + gumbel/codebook + prompted ViT-B, no grad) -> proj head ->
+cosine distillation loss -> backward -> (N>1: one NCCL all-reduce of the flat gradient) -> fused AdamW, on B=128
+synthetic ShapeNet-shaped clouds per GPU (N=1024, G=64, k=32, d=384, mask 0.6, drop_path 0.1), bf16 tensor-core
+operands / fp32 accumulation and master weights.  `--teacher synthetic` times the student-only step (SURVEY.md 8d
+config 2(i)); the default includes the teacher with random weights (config 2(ii): pretrained weights are not
+obtainable offline), and the line carries the student-only number as `student_only`.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
   N>1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -34,9 +36,12 @@ UNIT = "clouds/s"
 N_POINTS, N_GROUP, GROUP_SIZE, MASK_RATIO, DROP_PATH = 1024, 64, 32, 0.6, 0.1
 
 
-def workload_cfg(batch, n_gpus):
-    return {"workload": "ACT Stage-II student step: N=1024, G=64 x k=32, 12L d=384 + 2L decoder, mask 0.6, "
-                        "drop_path 0.1, cosine loss, fwd+bwd+AdamW; synthetic teacher target (teacher fwd = row f1)",
+def workload_cfg(batch, n_gpus, teacher="native"):
+    t = ("frozen teacher forward included (mini-PointNet + DGCNN x2 + gumbel/codebook + VPT-deep ViT-B x12 on 128 tokens, "
+         "random weights: pretrained ones are not obtainable offline)") if teacher == "native" else \
+        "synthetic teacher target (student-only step)"
+    return {"workload": "ACT Stage-II step: N=1024, G=64 x k=32, 12L d=384 + 2L decoder, mask 0.6, drop_path 0.1, "
+                        "cosine loss, fwd+bwd+AdamW; " + t, "teacher": teacher,
             "batch_per_gpu": batch, "global_batch": batch * n_gpus, "n_points": N_POINTS, "num_group": N_GROUP,
             "group_size": GROUP_SIZE, "depth": 12, "embed_dim": 384, "mask_ratio": MASK_RATIO,
             "parallelism": f"dp{n_gpus}",
@@ -125,7 +130,7 @@ def run_ours(args):
     np.random.seed(1234 + rank)
     cfg = models.default_config(mask_ratio=MASK_RATIO, drop_path_rate=DROP_PATH, num_group=N_GROUP,
                                 group_size=GROUP_SIZE)
-    model = models.ACT_PointDistillation(cfg).to(dev).train()
+    model = models.ACT_PointDistillation(cfg, teacher="native" if args.teacher == "native" else None).to(dev).train()
     fp = layers.FlatParams(model, lr=1e-3, weight_decay=0.05, exclude=model.UNUSED_PARAMETERS)
     dp.broadcast_params(fp)
 
@@ -187,6 +192,15 @@ def run_ours(args):
     _log("timed regions done")
     clocks = sampler.stop() if sampler else None
     last_loss = float(loss_host.item())
+    # the same step without the frozen teacher's forward (synthetic target): what the trainable path alone costs
+    ms_student = None
+    if args.teacher == "native":
+        object.__setattr__(model, "teacher", models.SyntheticTeacher(384).to(dev))
+        eng_s = PretrainStep(model, fp, B, N_POINTS, use_graph=not args.no_graph, device=dev).capture()
+        for i in range(3):
+            eng_s.run(resident[i % n_batches])
+        ms_student, _ = timed(lambda i: eng_s.run(resident[i % n_batches]), args.steps)
+        object.__setattr__(model, "teacher", model.dvae_tokenizer.forward_tokenizer_features)
 
     # ---- roofline of the dominant kernel: every launch of the tcgen05 GEMM kernels inside one step.
     # One eager step records each distinct GEMM call (shape, layouts, epilogue, its real operands); each distinct
@@ -261,14 +275,19 @@ def run_ours(args):
         dist.barrier()
 
     if rank == 0:
-        cpu = cpu_baseline(sample_batch=8, steps=1) if world == 1 and not args.no_cpu_baseline else None
+        cpu = (cpu_baseline(sample_batch=8, steps=1, teacher=args.teacher)
+               if world == 1 and not args.no_cpu_baseline else None)
         clouds = B * world
         line = {"metric": METRIC, "value": round(clouds / (ms_step * 1e-3), 1), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-                "data": "synthetic", "config": workload_cfg(B, world), "impl": "ours",
+                "data": "synthetic", "config": workload_cfg(B, world, args.teacher), "impl": "ours",
                 "e2e": {"value": round(clouds / (ms_e2e * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms_e2e, 4),
                         "h2d_bytes_per_step": int(host[0].numel() * 4 + B * N_GROUP + 32), "d2h_bytes_per_step": 4},
+                "student_only": (None if ms_student is None else
+                                 {"value": round(clouds / (ms_student * 1e-3), 1), "unit": UNIT,
+                                  "ms_per_step": round(ms_student, 4),
+                                  "what": "same step with a synthetic teacher target (no teacher forward)"}),
                 "gpu_launches": int(launches), "cuda_graph": not args.no_graph, "loss": last_loss,
                 "wall_s_timed": round(wall, 3),
                 "clocks": clocks, "roofline": roof}
@@ -280,7 +299,7 @@ def run_ours(args):
 
 
 # --------------------------------------------------------------------------- CPU baseline / reference arm
-def cpu_student_step_time(batch, steps, warmup, threads):
+def cpu_student_step_time(batch, steps, warmup, threads, teacher="native"):
     """The reference's path restated for the host (oracle/): Group on the C oracle, fp32 PyTorch modules,
     torch.optim.AdamW with the reference's two parameter groups (tools/builder.py:37-55)."""
     from oracle import ref_model
@@ -293,12 +312,22 @@ def cpu_student_step_time(batch, steps, warmup, threads):
     opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.05}, {"params": nodecay, "weight_decay": 0.0}],
                             lr=1e-3)
     pts = ref_model.synthetic_clouds(batch, N_POINTS)
-    teacher = torch.randn(batch, N_GROUP, 384)
+    tnet = None
+    if teacher == "native":
+        from oracle import ref_teacher
+        tnet = ref_teacher.TeacherFeatures().train()      # frozen, train mode like the reference (act.py:1151-1160)
+        for p in tnet.parameters():
+            p.requires_grad = False
+    tfeat = torch.randn(batch, N_GROUP, 384)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
-        loss = model(pts, teacher)
+        if tnet is not None:
+            with torch.no_grad():
+                nb, center = model.group_divider(pts)
+                tfeat = tnet.forward_tokenizer_features(nb, center, return_global=True)
+        loss = model(pts, tfeat)
         loss.backward()
         opt.step()
         dt = time.perf_counter() - t0
@@ -307,9 +336,9 @@ def cpu_student_step_time(batch, steps, warmup, threads):
     return sum(times) / len(times)
 
 
-def cpu_baseline(sample_batch=8, steps=1):
+def cpu_baseline(sample_batch=8, steps=1, teacher="native"):
     threads = os.cpu_count() or 1
-    t = cpu_student_step_time(sample_batch, steps, 1, threads)
+    t = cpu_student_step_time(sample_batch, steps, 1, threads, teacher)
     return {"value": round(sample_batch / t, 3), "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{steps} timed step(s) after 1 warm-up of the oracle restatement (fp32 PyTorch + C FPS/kNN) "
                       f"at batch {sample_batch} (same per-cloud workload; the full batch of 128 would take minutes)"}
@@ -323,12 +352,13 @@ def run_reference(args):
     sample = 8
     steps = max(1, min(args.steps, 3))
     warm = max(1, min(args.warmup, 1))
-    t = cpu_student_step_time(sample, steps, warm, threads)
+    t = cpu_student_step_time(sample, steps, warm, threads, args.teacher)
     world = max(1, args.gpus)
     val = round(sample / t, 3)
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(t * 1e3, 2), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_cfg(args.batch, world),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_cfg(args.batch, world, args.teacher),
             "impl": "reference",
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{steps} timed step(s) at batch {sample} per step (bounded sample of the "
@@ -345,6 +375,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="clouds per GPU")
+    ap.add_argument("--teacher", default="native", choices=["native", "synthetic"],
+                    help="native: the frozen teacher's forward is part of the step (the reference's full Stage-II step); "
+                         "synthetic: student-only step with a synthetic target")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

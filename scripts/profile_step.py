@@ -1,6 +1,6 @@
 """One profiled Stage-II step for ncu: warm up, then bracket ONE step (or N) with cudaProfilerStart/Stop.
   ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
-      --log-file gpurun_out/launches.csv python scripts/profile_step.py [steps] [batch]"""
+      --log-file gpurun_out/launches.csv python scripts/profile_step.py [steps] [batch] [native|synthetic]"""
 import os
 import sys
 
@@ -15,7 +15,8 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 torch.manual_seed(0)
 np.random.seed(0)
-model = models.ACT_PointDistillation(models.default_config(0.6, 0.1)).cuda().train()
+TEACHER = sys.argv[3] if len(sys.argv) > 3 else "native"
+model = models.ACT_PointDistillation(models.default_config(0.6, 0.1), teacher="native" if TEACHER == "native" else None).cuda().train()
 fp = layers.FlatParams(model, exclude=model.UNUSED_PARAMETERS)
 pts = synthetic_clouds(B, 1024).cuda()
 
