@@ -28,6 +28,27 @@ __device__ __forceinline__ float block_sum_256(float v, float *red) {
     return t;
 }
 
+
+// ---- counter-based RNG (Philox4x32-10, Salmon et al. 2011): the teacher's two random draws (gumbel noise of the hard
+// gumbel-softmax, dvae.py:587; prompt-token dropout, dvae.py:545-560) are generated inside the consuming kernel from a
+// per-step 64-bit seed held in device memory, instead of materialising [B*G, 8192] noise / [B,P,D] masks in HBM.
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                               uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+// uniform in (0,1): 23 random bits + 1/2 ulp, exactly representable, never 0 or 1
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 9) + 0.5f) * (1.f / 8388608.f); }
+// standard Gumbel sample -log(-log(u)) == -log(Exp(1)) (what F.gumbel_softmax draws)
+__device__ __forceinline__ float gumbel_from(uint32_t x) { return -__logf(-logf(u01(x))); }
+
 // pq: f32 [B*G, 2*Cp] (P | Q);  idx: i64 [B, G, KN] neighbour indices within the sample;  out: bf16, row pitch ldo.
 // grid (groups, B), 256 threads: warp w handles token rows g = w, w+8, ...; lanes stride the group's channels.
 template <int KN>
@@ -120,15 +141,23 @@ __global__ void __launch_bounds__(256) gn_rows_apply_kernel(const __nv_bfloat16 
                                                             const float *__restrict__ gamma,
                                                             const float *__restrict__ beta, int rows, int R, int C,
                                                             int groups, float slope, float *__restrict__ out,
-                                                            const float *__restrict__ noise, int *__restrict__ label) {
+                                                            const float *__restrict__ noise, int *__restrict__ label,
+                                                            const unsigned long long *__restrict__ seed) {
     pdl_wait();
     pdl_trigger();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
+    uint32_t k0 = 0, k1 = 0;
+    if (MODE == 2) {
+        const unsigned long long sd = __ldg(seed);
+        k0 = (uint32_t)sd;
+        k1 = (uint32_t)(sd >> 32);
+    }
     const int b = row / R, Cg = C / groups;
     const __nv_bfloat16 *p = x + (size_t)row * C;
     float best = -INFINITY;
     int bi = 0;
+    uint4 rnd = make_uint4(0, 0, 0, 0);
     for (int c = lane * 2; c < C; c += 64) {
         const int cg = c / Cg;
         const float mean = __ldg(stats + ((size_t)b * groups + cg) * 2), rstd = __ldg(stats + ((size_t)b * groups + cg) * 2 + 1);
@@ -140,14 +169,22 @@ __global__ void __launch_bounds__(256) gn_rows_apply_kernel(const __nv_bfloat16 
         if (MODE == 0) {
             *reinterpret_cast<float2 *>(out + (size_t)row * C + c) = make_float2(y0, y1);
         } else {
-            const float2 nz = __ldg(reinterpret_cast<const float2 *>(noise + (size_t)row * C + c));
-            y0 += nz.x;
-            y1 += nz.y;
+            if (MODE == 1) {
+                const float2 nz = __ldg(reinterpret_cast<const float2 *>(noise + (size_t)row * C + c));
+                y0 += nz.x;
+                y1 += nz.y;
+            } else {
+                // one Philox call per 4 elements: the lane pair (c, c + 64) shares a counter block
+                const int it = c >> 6;                       // this lane's it-th element pair
+                if ((it & 1) == 0) rnd = philox4x32_10((uint32_t)row, (uint32_t)(lane + 32 * (it >> 1)), 0x47554d42u, 0u, k0, k1);
+                y0 += gumbel_from((it & 1) ? rnd.z : rnd.x);
+                y1 += gumbel_from((it & 1) ? rnd.w : rnd.y);
+            }
             if (y0 > best) { best = y0; bi = c; }
             if (y1 > best) { best = y1; bi = c + 1; }
         }
     }
-    if (MODE == 1) {
+    if (MODE != 0) {
         // arg-max across lanes, lowest index on ties (torch.argmax returns the first maximum)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -159,7 +196,124 @@ __global__ void __launch_bounds__(256) gn_rows_apply_kernel(const __nv_bfloat16 
     }
 }
 
+
+// ---- VPT-deep prompted ViT block entry (visual_embedding_deep_prompt, dvae.py:536-576) ---------------------------
+// The reference rebuilds the sequence before every block: x = cat(dropout(prompt_tokens_i).expand(B), x[:, P:]),
+// pos = cat(prompt_pos_i.expand(B), pos_tok), then blk(x + pos) starts with LayerNorm.  This kernel is that whole
+// prologue fused with norm1: row r = b*T + t reads either the block's prompt token t (broadcast over the batch,
+// dropout drawn in-kernel or injected through `keep`) or the running token row, adds the matching position row,
+// writes the fp32 residual stream xs = x + pos and the bf16 LayerNorm output -- no cat / expand / dropout / copy
+// kernels and no [B,T,D] pos tensor.   xin row of token (b, t >= P) = b*xT + (t - P) + xoff: block 0 reads the
+// [B*G, D] proj_pre output (xT = G, xoff = 0), later blocks the previous block's [B*T, D] output (xT = T, xoff = P).
+template <int VPL>
+__global__ void __launch_bounds__(256) vit_ln1_kernel(const float *__restrict__ xin, int xT, int xoff,
+                                                      const float *__restrict__ pos_tok,
+                                                      const float *__restrict__ tok, const float *__restrict__ ppos,
+                                                      const float *__restrict__ keep,
+                                                      const unsigned long long *__restrict__ seed, uint32_t draw_id,
+                                                      float p_drop, const float *__restrict__ gamma,
+                                                      const float *__restrict__ beta, float eps, int rows, int T, int P,
+                                                      float *__restrict__ xs, __nv_bfloat16 *__restrict__ h) {
+    constexpr int C = 128 * VPL;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    pdl_wait();
+    pdl_trigger();
+    if (row >= rows) return;
+    const int b = row / T, t = row - b * T, G = T - P;
+    float4 v[VPL];
+    float s = 0.f;
+    if (t < P) {
+        const float4 *tr = reinterpret_cast<const float4 *>(tok + (size_t)t * C);
+        const float4 *pr = reinterpret_cast<const float4 *>(ppos + (size_t)t * C);
+        const float inv = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+        uint32_t k0 = 0, k1 = 0;
+        if (!keep && p_drop > 0.f) {
+            const unsigned long long sd = __ldg(seed);
+            k0 = (uint32_t)sd;
+            k1 = (uint32_t)(sd >> 32);
+        }
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            float4 x = __ldg(tr + lane + 32 * i);
+            const float4 p = __ldg(pr + lane + 32 * i);
+            if (keep) {
+                const float4 k = __ldg(reinterpret_cast<const float4 *>(keep + ((size_t)b * P + t) * C) + lane + 32 * i);
+                x.x *= k.x * inv; x.y *= k.y * inv; x.z *= k.z * inv; x.w *= k.w * inv;
+            } else if (p_drop > 0.f) {
+                const uint4 r = philox4x32_10((uint32_t)(b * P + t), (uint32_t)(lane + 32 * i), 0x44524f50u, draw_id, k0, k1);
+                x.x = u01(r.x) >= p_drop ? x.x * inv : 0.f;
+                x.y = u01(r.y) >= p_drop ? x.y * inv : 0.f;
+                x.z = u01(r.z) >= p_drop ? x.z * inv : 0.f;
+                x.w = u01(r.w) >= p_drop ? x.w * inv : 0.f;
+            }
+            v[i] = make_float4(x.x + p.x, x.y + p.y, x.z + p.z, x.w + p.w);
+            s += v[i].x + v[i].y + v[i].z + v[i].w;
+        }
+    } else {
+        const float4 *xr = reinterpret_cast<const float4 *>(xin + ((size_t)b * xT + (t - P) + xoff) * C);
+        const float4 *pr = reinterpret_cast<const float4 *>(pos_tok + ((size_t)b * G + (t - P)) * C);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const float4 x = xr[lane + 32 * i];
+            const float4 p = __ldg(pr + lane + 32 * i);
+            v[i] = make_float4(x.x + p.x, x.y + p.y, x.z + p.z, x.w + p.w);
+            s += v[i].x + v[i].y + v[i].z + v[i].w;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) reinterpret_cast<float4 *>(xs + (size_t)row * C)[lane + 32 * i] = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += a * a + bb * bb + c * c + d * d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.f / C) + eps);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma) + lane + 32 * i);
+        const float4 be = __ldg(reinterpret_cast<const float4 *>(beta) + lane + 32 * i);
+        uint2 pk;
+        *reinterpret_cast<__nv_bfloat162 *>(&pk.x) =
+            __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + be.x, (v[i].y - mean) * rstd * g.y + be.y);
+        *reinterpret_cast<__nv_bfloat162 *>(&pk.y) =
+            __floats2bfloat162_rn((v[i].z - mean) * rstd * g.z + be.z, (v[i].w - mean) * rstd * g.w + be.w);
+        reinterpret_cast<uint2 *>(h + (size_t)row * C)[lane + 32 * i] = pk;
+    }
+}
+
 }  // namespace act
+
+extern "C" int act_vit_ln1_fwd(const float *xin, int xT, int xoff, const float *pos_tok, const float *tok,
+                               const float *ppos, const float *keep, const unsigned long long *seed, int draw_id,
+                               float p_drop, const float *gamma, const float *beta, float eps, int B, int T, int P,
+                               int C, float *xs, void *h_bf16, void *stream) {
+    using namespace act;
+    if (!xin || !pos_tok || !tok || !ppos || !gamma || !beta || !xs || !h_bf16) return ACT_EINVAL;
+    if (B <= 0 || T <= 0 || P < 0 || P > T || xT < T - P || xoff < 0) return ACT_EINVAL;
+    if (p_drop < 0.f || p_drop >= 1.f || (p_drop > 0.f && !keep && !seed)) return ACT_EINVAL;
+    if (C % 128 || C > 1024) return ACT_EUNSUPPORTED;
+    const int rows = B * T;
+    cudaStream_t st = (cudaStream_t)stream;
+#define VLN_CASE(V)                                                                                                    \
+    case V:                                                                                                            \
+        ACT_CUDA(launch_k(vit_ln1_kernel<V>, dim3((rows + 7) / 8), dim3(256), 0, st, true, xin, xT, xoff, pos_tok, tok,  \
+                          ppos, keep, seed, (uint32_t)draw_id, p_drop, gamma, beta, eps, rows, T, P, xs,               \
+                          reinterpret_cast<__nv_bfloat16 *>(h_bf16)));                                                 \
+        break;
+    switch (C / 128) {
+        VLN_CASE(1) VLN_CASE(2) VLN_CASE(3) VLN_CASE(4) VLN_CASE(6) VLN_CASE(8)
+        default: return ACT_EUNSUPPORTED;
+    }
+#undef VLN_CASE
+    return ACT_OK;
+}
 
 extern "C" int act_dgcnn_edge_gn(const float *pq, const long long *idx, const float *gamma, const float *beta, int B,
                                  int G, int Cp, int kn, int groups, float eps, float slope, void *out_bf16, int ldo,
@@ -173,20 +327,25 @@ extern "C" int act_dgcnn_edge_gn(const float *pq, const long long *idx, const fl
 }
 
 extern "C" int act_gn_rows(const void *x_bf16, const float *gamma, const float *beta, int B, int R, int C, int groups,
-                           float eps, float slope, float *stats, float *out_f32, const float *noise, int *label,
-                           void *stream) {
+                           float eps, float slope, float *stats, float *out_f32, const float *noise,
+                           const unsigned long long *seed, int *label, void *stream) {
     using namespace act;
     if (!x_bf16 || !gamma || !beta || !stats || B <= 0 || R <= 0 || C <= 0 || groups <= 0) return ACT_EINVAL;
-    if (C % (2 * groups) || (!out_f32 && !(noise && label))) return ACT_EINVAL;
+    if (C % (2 * groups) || (!out_f32 && !((noise || seed) && label))) return ACT_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     const __nv_bfloat16 *x = reinterpret_cast<const __nv_bfloat16 *>(x_bf16);
     ACT_CUDA(launch_k(gn_rows_stats_kernel, dim3(groups, B), dim3(256), 0, st, true, x, R, C, groups, eps, stats));
     const int rows = B * R;
     if (out_f32)
         ACT_CUDA(launch_k(gn_rows_apply_kernel<0>, dim3((rows + 7) / 8), dim3(256), 0, st, true, x, (const float *)stats,
-                          gamma, beta, rows, R, C, groups, slope, out_f32, (const float *)nullptr, (int *)nullptr));
+                          gamma, beta, rows, R, C, groups, slope, out_f32, (const float *)nullptr, (int *)nullptr,
+                          (const unsigned long long *)nullptr));
     if (noise && label)
         ACT_CUDA(launch_k(gn_rows_apply_kernel<1>, dim3((rows + 7) / 8), dim3(256), 0, st, true, x, (const float *)stats,
-                          gamma, beta, rows, R, C, groups, slope, (float *)nullptr, noise, label));
+                          gamma, beta, rows, R, C, groups, slope, (float *)nullptr, noise, label,
+                          (const unsigned long long *)nullptr));
+    else if (seed && label)
+        ACT_CUDA(launch_k(gn_rows_apply_kernel<2>, dim3((rows + 7) / 8), dim3(256), 0, st, true, x, (const float *)stats,
+                          gamma, beta, rows, R, C, groups, slope, (float *)nullptr, (const float *)nullptr, label, seed));
     return ACT_OK;
 }

@@ -32,11 +32,11 @@ class _SideStream:
     _streams = {}
     enabled = os.environ.get("ACT_B200_SIDE_STREAM", "1") != "0"
 
-    def __init__(self, device):
+    def __init__(self, device, tag="wgrad"):
         self.main = torch.cuda.current_stream(device)
         self.side = None
         if _SideStream.enabled:
-            key = (device.index, self.main.cuda_stream)
+            key = (device.index, self.main.cuda_stream, tag)
             if key not in _SideStream._streams:
                 _SideStream._streams[key] = torch.cuda.Stream(device=device)
             self.side = _SideStream._streams[key]

@@ -117,19 +117,34 @@ class ACT_PointDistillation(nn.Module):
         if noaug:
             return self.forward_eval(pts)
         neighborhood, center = self.group_divider(pts)
+        # The frozen teacher's forward (act.py:1216-1217) depends only on the tokenizer's output, and the student's
+        # encoder/decoder forward is a chain of small latency-bound kernels that leave most SMs idle: fork the teacher
+        # onto a second stream right after the Group tokenizer and join before the loss, so inside the captured graph
+        # the two branches run concurrently.
+        fork = None
+        if teacher_feat is None:
+            fork = layers._SideStream(pts.device, tag="teacher")
+            box = []
+
+            def run_teacher():
+                with torch.no_grad():
+                    box.append(self.teacher(neighborhood, center))
+            fork.run(run_teacher, neighborhood, center)
         x_vis, mask = self.ACT_encoder(neighborhood, center, mask=mask)
         B, n_vis, C = x_vis.shape
         G = center.shape[1]
         num_mask = G - n_vis
-        if teacher_feat is None:
-            with torch.no_grad():
-                teacher_feat = self.teacher(neighborhood, center)
         order = self.ACT_encoder._order                       # visible groups first, then masked, original order
         centers_sorted = torch.gather(center, 1, order[..., None].expand(-1, -1, 3))
         pos_full = pos_mlp(self.decoder_pos_embed, centers_sorted)            # [pos(vis) | pos(mask)]
         x_full = torch.cat([x_vis, self.mask_token.expand(B, num_mask, -1)], dim=1)
         x_dec = self.ACT_decoder(x_full, pos_full, num_mask)
         student = layers.linear(x_dec, self.proj_head.weight, self.proj_head.bias)
+        if fork is not None:
+            fork.join()
+            teacher_feat = box[0]
+            if fork.side is not None:
+                teacher_feat.record_stream(fork.main)
         teacher = torch.gather(teacher_feat, 1, order[:, n_vis:, None].expand(-1, -1, student.shape[-1]))
         return layers.cosine_loss(student, teacher)
 

@@ -390,17 +390,35 @@ def dgcnn_edge_gn(pq, idx4, gamma, beta, B, G, Cp, eps, slope, out_view):
     return out_view
 
 
-def gn_rows(x, gamma, beta, B, R, eps, slope, noise=None):
-    """GroupNorm(4)+LeakyReLU over x bf16 [B*R, C].  noise None -> activations f32 [B*R, C];
-    noise f32 [B*R, C] -> labels i32 [B*R] = argmax(activation + noise)."""
+def gn_rows(x, gamma, beta, B, R, eps, slope, noise=None, seed=None):
+    """GroupNorm(4)+LeakyReLU over x bf16 [B*R, C].  noise/seed None -> activations f32 [B*R, C];
+    noise f32 [B*R, C] -> labels i32 [B*R] = argmax(activation + noise);  seed (device int64 [1]) -> the same with the
+    gumbel noise drawn inside the kernel (nothing [B*R, C]-sized is materialised)."""
     C = x.shape[1]
     stats = torch.empty(B, 4, 2, dtype=torch.float32, device=x.device)
-    if noise is None:
+    if noise is None and seed is None:
         out = torch.empty(B * R, C, dtype=torch.float32, device=x.device)
-        _lib.call("act_gn_rows", x, gamma, beta, B, R, C, 4, float(eps), float(slope), stats, out, None, None)
+        _lib.call("act_gn_rows", x, gamma, beta, B, R, C, 4, float(eps), float(slope), stats, out, None, None, None)
         _count(2)
         return out
     label = torch.empty(B * R, dtype=torch.int32, device=x.device)
-    _lib.call("act_gn_rows", x, gamma, beta, B, R, C, 4, float(eps), float(slope), stats, None, noise, label)
+    if noise is not None:
+        seed = None
+    else:
+        assert seed.dtype == torch.int64 and seed.is_cuda
+    _lib.call("act_gn_rows", x, gamma, beta, B, R, C, 4, float(eps), float(slope), stats, None, noise, seed, label)
     _count(2)
     return label
+
+
+def vit_ln1_fwd(xin, xT, xoff, pos_tok, tok, ppos, gamma, beta, eps, B, T, P, keep=None, seed=None, draw_id=0,
+                p_drop=0.0):
+    """Entry of a VPT-deep prompted ViT block: (prompt rows | token rows) + positions -> (xs f32 [B*T,C] residual
+    stream, h bf16 [B*T,C] = norm1(xs)).  See include/act_b200.h: act_vit_ln1_fwd."""
+    C = pos_tok.shape[-1]
+    xs = torch.empty(B * T, C, dtype=torch.float32, device=pos_tok.device)
+    h = torch.empty(B * T, C, dtype=torch.bfloat16, device=pos_tok.device)
+    _lib.call("act_vit_ln1_fwd", xin, xT, xoff, pos_tok, tok, ppos, keep, seed, draw_id, float(p_drop), gamma, beta,
+              float(eps), B, T, P, C, xs, _p(h))
+    _count()
+    return xs, h

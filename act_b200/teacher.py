@@ -149,7 +149,7 @@ class ACTPromptedDiscreteVAEwithVIT(nn.Module):
         return c
 
     # ---- pieces ----------------------------------------------------------------------------------------------
-    def _dgcnn(self, m, c, x, idx4, B, G, noise=None):
+    def _dgcnn(self, m, c, x, idx4, B, G, noise=None, seed=None, want_labels=False):
         """x f32 [B*G, Cin] -> layer5 activations f32 [B*G, Cout], or (noise given) arg-max labels i32 [B*G]."""
         dev = x.device
         f = ops.gemm(x.to(torch.bfloat16), c["it_w"], bias=c["it_b"])                       # [BG,128]
@@ -162,48 +162,48 @@ class ACTPromptedDiscreteVAEwithVIT(nn.Module):
             ops.dgcnn_edge_gn(pq, idx4, c[f"g{i}"], c[f"b{i}"], B, G, Cp, layer[1].eps, 0.2, f)
             off += Cp
         h5 = ops.gemm(feats, c["w5"])                                                       # [BG, Cout] bf16
-        return ops.gn_rows(h5, c["g5"], c["b5"], B, G, m.layer5[1].eps, 0.2, noise=noise)
+        if not want_labels:
+            return ops.gn_rows(h5, c["g5"], c["b5"], B, G, m.layer5[1].eps, 0.2)
+        return ops.gn_rows(h5, c["g5"], c["b5"], B, G, m.layer5[1].eps, 0.2, noise=noise, seed=seed)
 
-    def _drop(self, t, B, keep):
-        t = t.expand(B, -1, -1)
-        if keep is not None:
-            return t * keep / 0.9
-        return F.dropout(t, 0.1, self.training)
-
-    def _vit_block(self, x2, pos2, blk, w, B, T):
+    def _vit_block(self, xin, xT, xoff, pos_tok, tok, ppos, blk, w, B, T, keep, seed, draw_id):
+        """One prompted block: fused (prompt rebuild + pos add + norm1) -> qkv -> attention -> proj(+resid) -> norm2 ->
+        fc1(GELU) -> fc2(+resid).  Returns the block output f32 [B*T, D] (its prompt rows are dead: the next block
+        overwrites them with its own prompts, dvae.py:556-566)."""
         H = blk.attn.num_heads
         eps = blk.norm1.eps
-        h1, xs, _, _ = ops.layernorm_fwd(x2, blk.norm1.weight, blk.norm1.bias, eps, pos=pos2, save_stats=False)
+        P = self.num_prompt_token
+        p_drop = 0.1 if (self.training or keep is not None) else 0.0
+        xs, h1 = ops.vit_ln1_fwd(xin, xT, xoff, pos_tok, tok, ppos, blk.norm1.weight, blk.norm1.bias, eps, B, T, P,
+                                 keep=keep, seed=seed, draw_id=draw_id, p_drop=p_drop)
         qkv = ops.gemm(h1, w["qkv"], bias=blk.attn.qkv.bias)
-        o, _ = ops.attention_fwd(qkv, B, T, H, (x2.shape[1] // H) ** -0.5)
+        o, _ = ops.attention_fwd(qkv, B, T, H, (xs.shape[1] // H) ** -0.5)
         xmid = ops.gemm(o, w["proj"], bias=blk.attn.proj.bias, resid=xs, out_dtype=torch.float32)
         h2, _, _, _ = ops.layernorm_fwd(xmid, blk.norm2.weight, blk.norm2.bias, eps, save_stats=False)
         a = ops.gemm(h2, w["fc1"], bias=blk.mlp.fc1.bias, act=ops.ACT_GELU)
         return ops.gemm(a, w["fc2"], bias=blk.mlp.fc2.bias, resid=xmid, out_dtype=torch.float32)
 
-    def _visual(self, c, sampled, center, B, G, keeps):
+    def _visual(self, c, sampled, center, B, G, keeps, seed=None):
         """visual_embedding_deep_prompt (dvae.py:536-576)."""
         D, P = self.visual_embed_dim, self.num_prompt_token
         T = P + G
-        dev = sampled.device
         pe = self.visual_pos_embed
         pos_tok = ops.gemm(F.gelu(F.linear(center.reshape(B * G, 3), pe[0].weight, pe[0].bias)).to(torch.bfloat16),
                            c["pos2_w"], bias=pe[2].bias, out_dtype=torch.float32)
-        x_tok = ops.gemm(sampled.to(torch.bfloat16), c["pre_w"], bias=self.proj_pre.bias, out_dtype=torch.float32)
-        x = torch.empty(B, T, D, dtype=torch.float32, device=dev)
-        pos = torch.empty(B, T, D, dtype=torch.float32, device=dev)
-        x[:, :P] = self._drop(self.visual_prompt_token, B, None if keeps is None else keeps[0])
-        x[:, P:] = x_tok.view(B, G, D)
-        pos[:, :P] = self.visual_prompt_pos
-        pos[:, P:] = pos_tok.view(B, G, D)
+        x = ops.gemm(sampled.to(torch.bfloat16), c["pre_w"], bias=self.proj_pre.bias, out_dtype=torch.float32)
+        xT, xoff = G, 0
         blocks = self.visual_embed[0]
         for i, blk in enumerate(blocks):
-            if 0 < i <= self.deep_prompt_tokens.shape[0]:
-                x[:, :P] = self._drop(self.deep_prompt_tokens[i - 1:i], B, None if keeps is None else keeps[i])
-                pos[:, :P] = self.deep_prompt_pos[i - 1]
-            x = self._vit_block(x.view(B * T, D), pos.view(B * T, D), blk, c["blocks"][i], B, T).view(B, T, D)
+            if i == 0:
+                tok, ppos = self.visual_prompt_token[0], self.visual_prompt_pos[0]
+            elif i <= self.deep_prompt_tokens.shape[0]:
+                tok, ppos = self.deep_prompt_tokens[i - 1], self.deep_prompt_pos[i - 1]
+            keep = None if keeps is None else keeps[i].float().contiguous()
+            x = self._vit_block(x, xT, xoff, pos_tok, tok.detach(), ppos.detach(), blk, c["blocks"][i], B, T, keep, seed, i)
+            xT, xoff = T, P
         norm = self.visual_embed[1]
-        y, _, _, _ = ops.layernorm_fwd(x[:, P:].reshape(B * G, D), norm.weight, norm.bias, norm.eps, save_stats=False)
+        y, _, _, _ = ops.layernorm_fwd(x.view(B, T, D)[:, P:].reshape(B * G, D), norm.weight, norm.bias, norm.eps,
+                                       save_stats=False)
         return ops.gemm(y, c["post_w"], bias=self.proj_post.bias, out_dtype=torch.float32)  # [BG, tokens_dims]
 
     @torch.no_grad()
@@ -214,13 +214,16 @@ class ACTPromptedDiscreteVAEwithVIT(nn.Module):
         B, G, _ = center.shape
         tokens = self.encoder(neighborhood).reshape(B * G, -1)
         _, idx4, _ = ops.knn(center, center, 4, want_dist=False)                            # [B,G,4] i64
-        if gumbel is None:      # same construction as F.gumbel_softmax: -log(Exp(1))
-            gumbel = -torch.empty(B * G, self.num_tokens, device=center.device).exponential_().log()
-        labels = self._dgcnn(self.dgcnn_1, c["d1"], tokens, idx4, B, G,
-                             noise=gumbel.reshape(B * G, self.num_tokens).float().contiguous())
+        # one graph-safe draw per call (torch's Philox state advances on every CUDA-graph replay); the kernels derive
+        # the gumbel noise and the prompt-dropout masks from it on the fly
+        seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=center.device)
+        if gumbel is not None:
+            gumbel = gumbel.reshape(B * G, self.num_tokens).float().contiguous()
+        labels = self._dgcnn(self.dgcnn_1, c["d1"], tokens, idx4, B, G, noise=gumbel,
+                             seed=seed if gumbel is None else None, want_labels=True)
         self.last_labels = labels
         sampled = self.codebook.detach()[labels.long()]                                     # one-hot @ codebook
-        feature = self._visual(c, sampled, center.float(), B, G, keeps)
+        feature = self._visual(c, sampled, center.float(), B, G, keeps, seed)
         if return_global:
             feature = self._dgcnn(self.dgcnn_2, c["d2"], feature, idx4, B, G)
         return feature.view(B, G, -1)

@@ -202,9 +202,22 @@ int act_dgcnn_edge_gn(const float *pq, const long long *idx, const float *gamma,
 /* GroupNorm(groups) + LeakyReLU over x bf16 [B*R, C] (statistics per sample and channel group over R rows; DGCNN
  * layer5, dvae.py:53-56).  stats f32 [B,groups,2] is scratch (mean, rstd).  out_f32 (nullable) [B*R, C] receives the
  * activations; noise + label (nullable pair): label[row] = argmax_c(activation + noise[row,c]) -- the forward value of
- * F.gumbel_softmax(hard=True) (dvae.py:587) without materialising the one-hot. */
+ * F.gumbel_softmax(hard=True) (dvae.py:587) without materialising the one-hot.
+ * seed (alternative to noise): the gumbel noise -log(-log(u)) is drawn inside the kernel (Philox4x32-10 keyed by *seed,
+ * a 64-bit value in DEVICE memory so that a replayed CUDA graph draws fresh noise every step). */
 int act_gn_rows(const void *x_bf16, const float *gamma, const float *beta, int B, int R, int C, int groups, float eps,
-                float slope, float *stats, float *out_f32, const float *noise, int *label, void *stream);
+                float slope, float *stats, float *out_f32, const float *noise, const unsigned long long *seed,
+                int *label, void *stream);
+
+/* Entry of one VPT-deep prompted ViT block (visual_embedding_deep_prompt, /root/reference/models/dvae.py:536-576):
+ * the reference's per-block  x = cat(dropout(prompt_i).expand(B), x[:, P:]);  pos = cat(prompt_pos_i.expand(B), pos);
+ * blk(x + pos) -> norm1  fused into one pass.  Row r = b*T + t:  t < P: x = tok[t,:] (dropout p_drop: mask injected
+ * through keep f32 [B,P,C] of 0/1, or drawn in-kernel from *seed (device memory) and draw_id), pos = ppos[t,:];
+ * t >= P: x = xin[b*xT + (t-P) + xoff, :], pos = pos_tok[b*(T-P) + (t-P), :].  Writes xs f32 [B*T, C] = x + pos (the
+ * residual stream) and h bf16 [B*T, C] = LayerNorm(xs; gamma, beta, eps). */
+int act_vit_ln1_fwd(const float *xin, int xT, int xoff, const float *pos_tok, const float *tok, const float *ppos,
+                    const float *keep, const unsigned long long *seed, int draw_id, float p_drop, const float *gamma,
+                    const float *beta, float eps, int B, int T, int P, int C, float *xs, void *h_bf16, void *stream);
 
 /* ---- Loss and optimizer ------------------------------------------------------------------------------ */
 

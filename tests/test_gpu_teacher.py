@@ -108,3 +108,49 @@ def test_teacher_features_vs_oracle_and_reference_golden(golden):
         f = model._dgcnn(model.dgcnn_2, c["d2"], f, idx4, 2, 64).view(2, 64, -1)
     assert rel(f, want) < 2e-2, rel(f, want)
     assert rel(want, g["feature"]) < 1e-3                        # the oracle itself reproduces the reference golden
+
+
+def test_in_kernel_gumbel_and_prompt_dropout_draws():
+    """The product path draws the gumbel noise and the prompt-dropout masks inside the kernels (Philox keyed by a
+    device seed).  Distributional checks: P(argmax = c) follows softmax(logits); dropout keeps 90 % and rescales."""
+    B, R, C = 8, 64, 8192
+    h = torch.zeros(B * R, C, device="cuda", dtype=torch.bfloat16)           # GroupNorm(const) = 0 -> act = leaky(beta)
+    gam = torch.ones(C, device="cuda")
+    bet = torch.zeros(C, device="cuda")
+    bet[5] = float(np.log(C - 1))                                            # softmax prob of class 5 = 1/2
+    s1 = torch.tensor([12345], dtype=torch.int64, device="cuda")
+    s2 = torch.tensor([99], dtype=torch.int64, device="cuda")
+    l1 = ops.gn_rows(h, gam, bet, B, R, 1e-5, 0.2, seed=s1)
+    l1b = ops.gn_rows(h, gam, bet, B, R, 1e-5, 0.2, seed=s1)
+    l2 = ops.gn_rows(h, gam, bet, B, R, 1e-5, 0.2, seed=s2)
+    assert torch.equal(l1, l1b) and not torch.equal(l1, l2)
+    p5 = torch.cat([l1, l2]).eq(5).float().mean().item()
+    assert abs(p5 - 0.5) < 0.08, p5                                          # 1024 draws: sigma = 0.016
+    rest = torch.cat([l1, l2])
+    rest = rest[rest != 5]
+    assert rest.unique().numel() > 0.9 * rest.numel()                        # the other half spreads over 8191 classes
+    assert 0 <= int(rest.min()) and int(rest.max()) < C
+    # prompt dropout: tok = 1, ppos = 0 -> prompt rows of xs are keep / 0.9
+    Bv, T, P, D = 16, 128, 64, 768
+    xin = torch.randn(Bv * 64, D, device="cuda")
+    pos_tok = torch.randn(Bv * 64, D, device="cuda")
+    tok, ppos = torch.ones(P, D, device="cuda"), torch.zeros(P, D, device="cuda")
+    g, b = torch.ones(D, device="cuda"), torch.zeros(D, device="cuda")
+    xs, hh = ops.vit_ln1_fwd(xin, 64, 0, pos_tok, tok, ppos, g, b, 1e-6, Bv, T, P, seed=s1, draw_id=3, p_drop=0.1)
+    xs = xs.view(Bv, T, D)
+    pr = xs[:, :P]
+    assert ((pr == 0) | ((pr - 1 / 0.9).abs() < 1e-6)).all()
+    keep = (pr != 0).float().mean().item()
+    assert abs(keep - 0.9) < 5e-3, keep
+    assert (pr != 0).float().mean((1, 2)).std().item() < 5e-3               # every cloud gets its own mask
+    assert not torch.equal(pr[0], pr[1])
+    torch.testing.assert_close(xs[:, P:].reshape(Bv * 64, D), xin + pos_tok)
+    want_h = torch.nn.functional.layer_norm(xs, (D,), g, b, 1e-6)
+    assert rel(hh.view(Bv, T, D), want_h) < 4e-3
+    xs2, _ = ops.vit_ln1_fwd(xin, 64, 0, pos_tok, tok, ppos, g, b, 1e-6, Bv, T, P, seed=s1, draw_id=4, p_drop=0.1)
+    assert not torch.equal(xs2.view(Bv, T, D)[:, :P], pr)                    # another block, another mask
+    # later blocks read the previous block's [B*T, D] output, skipping its (dead) prompt rows
+    prev = torch.randn(Bv * T, D, device="cuda")
+    xs3, _ = ops.vit_ln1_fwd(prev, T, P, pos_tok, tok, ppos, g, b, 1e-6, Bv, T, P, p_drop=0.0)
+    torch.testing.assert_close(xs3.view(Bv, T, D)[:, P:], prev.view(Bv, T, D)[:, P:] + pos_tok.view(Bv, 64, D))
+    assert (xs3.view(Bv, T, D)[:, :P] == 1).all()
