@@ -31,29 +31,26 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 __device__ __forceinline__ uint32_t lds32(const __nv_bfloat16 *p) { return *reinterpret_cast<const uint32_t *>(p); }
 
-// rows [0,T) of a [T x 64] bf16 matrix with row pitch ld -> smem [TP][MA_PITCH] (rows >= T zero), one warp
+// rows [0,T) of a [T x 64] bf16 matrix with row pitch ld -> smem [TP][MA_PITCH] (rows >= T zero-filled), whole CTA.
+// Asynchronous 16-byte copies (cp.async / LDGSTS, zero-fill form for the padding rows): every thread puts all of its
+// copies for ALL staged matrices in flight before anyone waits (stage_wait), instead of one dependent
+// LDG -> STS round trip after another -- the staging latency, not the MMAs, bounded these kernels.
 template <int TP>
 __device__ __forceinline__ void stage_rowmajor(__nv_bfloat16 *dst, const __nv_bfloat16 *src, int ld, int T, int tid) {
+#pragma unroll
     for (int i = tid; i < TP * 8; i += (TP / 16) * 32) {
         const int r = i >> 3, c = i & 7;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (r < T) v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * ld) + c);
-        *reinterpret_cast<uint4 *>(dst + r * MA_PITCH + c * 8) = v;
+        const bool ok = r < T;
+        const __nv_bfloat16 *g = src + (size_t)(ok ? r : 0) * ld + c * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst + r * MA_PITCH + c * 8)), "l"(g),
+                     "r"(ok ? 16 : 0)
+                     : "memory");
     }
 }
-// same source, stored TRANSPOSED: dst[dim][row], pitch TP + 8 (cols >= T zero)
-// (lanes take consecutive ROWS of one 8-dim chunk, so each of the 8 scattered 2-byte stores of a warp lands in
-// 64 contiguous bytes of one transposed row: conflict-free)
-template <int TP>
-__device__ __forceinline__ void stage_transposed(__nv_bfloat16 *dst, const __nv_bfloat16 *src, int ld, int T, int tid) {
-    for (int i = tid; i < TP * 8; i += (TP / 16) * 32) {
-        const int r = i % TP, c = i / TP;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (r < T) v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * ld) + c);
-        const __nv_bfloat16 *e = reinterpret_cast<const __nv_bfloat16 *>(&v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dst[(c * 8 + j) * (TP + 8) + r] = e[j];
-    }
+__device__ __forceinline__ void stage_wait() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
 }
 // A fragments (16 rows x 64 k) of a row-major tile, rows r0..r0+15
 __device__ __forceinline__ void load_a_frags(uint32_t (&a)[4][4], const __nv_bfloat16 *tile, int r0, int g, int t) {
@@ -77,17 +74,28 @@ __device__ __forceinline__ void mma_rows_t(float (&acc)[TP / 8][4], const uint32
         }
     }
 }
-// out[nd] (16 x 8 tile nd of a 16 x 64 product) += A(16 x TP, fragments fa) . B, B given TRANSPOSED in smem:
-// bt[dim][k] with pitch TP + 8
+// out[nd] (16 x 8 tile nd of a 16 x 64 product) += A(16 x TP, fragments fa) . B, with B = the ROW-MAJOR smem tile
+// [k = token][n = dim] (pitch MA_PITCH): the B fragments (two consecutive k per register) come from
+// ldmatrix.x4.trans -- matrices (k-half 0/1) x (nd, nd+1) per instruction -- so no transposed copy of V / K / Q / dO
+// is ever built.
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const __nv_bfloat16 *p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_u32(p)));
+}
 template <int TP>
-__device__ __forceinline__ void mma_kt(float (&out)[8][4], const uint32_t (&fa)[TP / 16][4], const __nv_bfloat16 *bt, int g,
-                                       int t) {
+__device__ __forceinline__ void mma_kt(float (&out)[8][4], const uint32_t (&fa)[TP / 16][4], const __nv_bfloat16 *tile,
+                                       int lane) {
+    const int mi = lane >> 3, mr = lane & 7;
+    const __nv_bfloat16 *base = tile + ((mi & 1) * 8 + mr) * MA_PITCH + (mi >> 1) * 8;
 #pragma unroll
-    for (int nd = 0; nd < 8; ++nd) {
+    for (int kk = 0; kk < TP / 16; ++kk) {
 #pragma unroll
-        for (int kk = 0; kk < TP / 16; ++kk) {
-            const __nv_bfloat16 *p = bt + (nd * 8 + g) * (TP + 8) + kk * 16 + 2 * t;
-            mma16816(out[nd], fa[kk], lds32(p), lds32(p + 8));
+        for (int nd = 0; nd < 8; nd += 2) {
+            uint32_t b[4];
+            ldsm_x4_trans(b, base + kk * 16 * MA_PITCH + nd * 8);
+            mma16816(out[nd], fa[kk], b[0], b[1]);
+            mma16816(out[nd + 1], fa[kk], b[2], b[3]);
         }
     }
 }
@@ -135,13 +143,13 @@ __global__ void __launch_bounds__((TP / 16) * 32) attn_mma_fwd_kernel(const __nv
     pdl_trigger();
     const int b = pair / H, h = pair % H;
     __nv_bfloat16 *sQ = reinterpret_cast<__nv_bfloat16 *>(ma_smem);
-    __nv_bfloat16 *sK = sQ + TP * MA_PITCH, *sVt = sK + TP * MA_PITCH;
+    __nv_bfloat16 *sK = sQ + TP * MA_PITCH, *sV = sK + TP * MA_PITCH;
     const int ld = 3 * H * MA_D;
     const __nv_bfloat16 *base = qkv + (size_t)b * T * ld + h * MA_D;
     stage_rowmajor<TP>(sQ, base, ld, T, tid);
     stage_rowmajor<TP>(sK, base + H * MA_D, ld, T, tid);
-    stage_transposed<TP>(sVt, base + 2 * H * MA_D, ld, T, tid);
-    __syncthreads();
+    stage_rowmajor<TP>(sV, base + 2 * H * MA_D, ld, T, tid);
+    stage_wait();
     const float sl2 = scale * 1.4426950408889634f;
     __nv_bfloat16 *orow = o + (size_t)b * T * (H * MA_D) + h * MA_D;
     for (int mt = warp; mt * 16 < T; mt += TP / 16) {
@@ -177,7 +185,7 @@ __global__ void __launch_bounds__((TP / 16) * 32) attn_mma_fwd_kernel(const __nv
         float oacc[8][4];
 #pragma unroll
         for (int nd = 0; nd < 8; ++nd) oacc[nd][0] = oacc[nd][1] = oacc[nd][2] = oacc[nd][3] = 0.f;
-        mma_kt<TP>(oacc, pa, sVt, g, t);
+        mma_kt<TP>(oacc, pa, sV, lane);
         store_c_rows(orow, H * MA_D, oacc, mt * 16, T, g, t, 1.f / l0, 1.f / l1);
         if (t == 0 && lse) {
             float *L = lse + ((size_t)b * H + h) * T;
@@ -204,8 +212,7 @@ __global__ void __launch_bounds__((TP / 16) * 32) attn_mma_bwd_dq_kernel(const _
     const int b = pair / H, h = pair % H;
     __nv_bfloat16 *sQ = reinterpret_cast<__nv_bfloat16 *>(ma_smem);
     __nv_bfloat16 *sK = sQ + TP * MA_PITCH, *sV = sK + TP * MA_PITCH, *sG = sV + TP * MA_PITCH;
-    __nv_bfloat16 *sKt = sG + TP * MA_PITCH;
-    float *sD = reinterpret_cast<float *>(sKt + MA_D * (TP + 8));
+    float *sD = reinterpret_cast<float *>(sG + TP * MA_PITCH);
     const int ld = 3 * H * MA_D, ldo = H * MA_D;
     const __nv_bfloat16 *base = qkv + (size_t)b * T * ld + h * MA_D;
     const __nv_bfloat16 *gbase = dO + (size_t)b * T * ldo + h * MA_D, *obase = o + (size_t)b * T * ldo + h * MA_D;
@@ -213,7 +220,6 @@ __global__ void __launch_bounds__((TP / 16) * 32) attn_mma_bwd_dq_kernel(const _
     stage_rowmajor<TP>(sK, base + H * MA_D, ld, T, tid);
     stage_rowmajor<TP>(sV, base + 2 * H * MA_D, ld, T, tid);
     stage_rowmajor<TP>(sG, gbase, ldo, T, tid);
-    stage_transposed<TP>(sKt, base + H * MA_D, ld, T, tid);
     // D_i = dO_i . O_i  (rows lane, lane + 32)
     for (int r = tid; r < TP; r += (TP / 16) * 32) {
         float D = 0.f;
@@ -235,7 +241,7 @@ __global__ void __launch_bounds__((TP / 16) * 32) attn_mma_bwd_dq_kernel(const _
         }
         sD[r] = D;
     }
-    __syncthreads();
+    stage_wait();
     const float sl2 = scale * 1.4426950408889634f;
     const float *L = lse + ((size_t)b * H + h) * T;
     __nv_bfloat16 *dq = dqkv + (size_t)b * T * ld + h * MA_D;
@@ -269,7 +275,7 @@ __global__ void __launch_bounds__((TP / 16) * 32) attn_mma_bwd_dq_kernel(const _
         float acc[8][4];
 #pragma unroll
         for (int nd = 0; nd < 8; ++nd) acc[nd][0] = acc[nd][1] = acc[nd][2] = acc[nd][3] = 0.f;
-        mma_kt<TP>(acc, dsa, sKt, g, t);
+        mma_kt<TP>(acc, dsa, sK, lane);
         store_c_rows(dq, ld, acc, mt * 16, T, g, t, 1.f, 1.f);
     }
 }
@@ -292,8 +298,7 @@ __global__ void __launch_bounds__((TP / 16) * 32) attn_mma_bwd_dkv_kernel(const 
     const int b = pair / H, h = pair % H;
     __nv_bfloat16 *sQ = reinterpret_cast<__nv_bfloat16 *>(ma_smem);
     __nv_bfloat16 *sK = sQ + TP * MA_PITCH, *sV = sK + TP * MA_PITCH, *sG = sV + TP * MA_PITCH;
-    __nv_bfloat16 *sQt = sG + TP * MA_PITCH, *sGt = sQt + MA_D * (TP + 8);
-    float *sL = reinterpret_cast<float *>(sGt + MA_D * (TP + 8)), *sD = sL + TP;
+    float *sL = reinterpret_cast<float *>(sG + TP * MA_PITCH), *sD = sL + TP;
     const int ld = 3 * H * MA_D, ldo = H * MA_D;
     const __nv_bfloat16 *base = qkv + (size_t)b * T * ld + h * MA_D;
     const __nv_bfloat16 *gbase = dO + (size_t)b * T * ldo + h * MA_D;
@@ -301,13 +306,11 @@ __global__ void __launch_bounds__((TP / 16) * 32) attn_mma_bwd_dkv_kernel(const 
     stage_rowmajor<TP>(sK, base + H * MA_D, ld, T, tid);
     stage_rowmajor<TP>(sV, base + 2 * H * MA_D, ld, T, tid);
     stage_rowmajor<TP>(sG, gbase, ldo, T, tid);
-    stage_transposed<TP>(sQt, base, ld, T, tid);
-    stage_transposed<TP>(sGt, gbase, ldo, T, tid);
     for (int r = tid; r < TP; r += (TP / 16) * 32) {
         sL[r] = r < T ? __ldg(lse + ((size_t)b * H + h) * T + r) * 1.4426950408889634f : 0.f;
         sD[r] = r < T ? __ldg(delta + ((size_t)b * H + h) * T + r) : 0.f;
     }
-    __syncthreads();
+    stage_wait();
     const float sl2 = scale * 1.4426950408889634f;
     __nv_bfloat16 *dk = dqkv + (size_t)b * T * ld + H * MA_D + h * MA_D, *dv = dk + H * MA_D;
     for (int mt = warp; mt * 16 < T; mt += TP / 16) {
@@ -342,12 +345,12 @@ __global__ void __launch_bounds__((TP / 16) * 32) attn_mma_bwd_dkv_kernel(const 
         c_to_a<TP>(fa, pt);
 #pragma unroll
         for (int nd = 0; nd < 8; ++nd) acc[nd][0] = acc[nd][1] = acc[nd][2] = acc[nd][3] = 0.f;
-        mma_kt<TP>(acc, fa, sGt, g, t);          // dV = P^T dO
+        mma_kt<TP>(acc, fa, sG, lane);           // dV = P^T dO
         store_c_rows(dv, ld, acc, mt * 16, T, g, t, 1.f, 1.f);
         c_to_a<TP>(fa, st);
 #pragma unroll
         for (int nd = 0; nd < 8; ++nd) acc[nd][0] = acc[nd][1] = acc[nd][2] = acc[nd][3] = 0.f;
-        mma_kt<TP>(acc, fa, sQt, g, t);          // dK = dS^T Q
+        mma_kt<TP>(acc, fa, sQ, lane);           // dK = dS^T Q
         store_c_rows(dk, ld, acc, mt * 16, T, g, t, 1.f, 1.f);
     }
 }
@@ -355,7 +358,7 @@ __global__ void __launch_bounds__((TP / 16) * 32) attn_mma_bwd_dkv_kernel(const 
 template <int TP>
 static int launch_fwd(const __nv_bfloat16 *qkv, int B, int T, int H, float scale, __nv_bfloat16 *o, float *lse,
                       cudaStream_t st) {
-    constexpr size_t smem = (size_t)(2 * TP * MA_PITCH + MA_D * (TP + 8)) * 2;
+    constexpr size_t smem = (size_t)(3 * TP * MA_PITCH) * 2;
     auto kern = attn_mma_fwd_kernel<TP>;
     if (smem > 48 * 1024) ACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int npairs = B * H;
@@ -366,8 +369,8 @@ static int launch_fwd(const __nv_bfloat16 *qkv, int B, int T, int H, float scale
 template <int TP>
 static int launch_bwd(const __nv_bfloat16 *qkv, const __nv_bfloat16 *o, const __nv_bfloat16 *dO, const float *lse, int B,
                       int T, int H, float scale, __nv_bfloat16 *dqkv, float *delta, cudaStream_t st) {
-    constexpr size_t smem1 = (size_t)(4 * TP * MA_PITCH + MA_D * (TP + 8)) * 2 + TP * 4;
-    constexpr size_t smem2 = (size_t)(4 * TP * MA_PITCH + 2 * MA_D * (TP + 8)) * 2 + 2 * TP * 4;
+    constexpr size_t smem1 = (size_t)(4 * TP * MA_PITCH) * 2 + TP * 4;
+    constexpr size_t smem2 = (size_t)(4 * TP * MA_PITCH) * 2 + 2 * TP * 4;
     auto k1 = attn_mma_bwd_dq_kernel<TP>;
     auto k2 = attn_mma_bwd_dkv_kernel<TP>;
     if (smem1 > 48 * 1024) ACT_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));

@@ -62,17 +62,6 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *ba
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
-                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-template <int N_PENDING>
-__device__ __forceinline__ void bulk_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N_PENDING) : "memory");
-}
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -169,243 +158,277 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 }
 
 // ------------------------------------------------------------------------------------------ epilogue
-// One 32-column chunk of one accumulator row per thread (lane = row within the warp's 32-row slab).
-// Operands that do not depend on the accumulator (the residual row / the mul_in row) are PREFETCHED into
-// registers by epi_prefetch() before the accumulator is waited for -- for the next chunk while the current one
-// is processed -- because with one row per thread every such load is a full L2 round trip on the critical path.
-// Epilogue specialisation: MODE is a compile-time hint that fixes which optional parts exist, so that the hot
-// instantiations carry no flag tests, no dead register arrays and ~half the instructions per chunk (the epilogue
-// runs on 4-8 warps per SM: it is bound by its own dependent-instruction chains, not by memory).  E_GENERIC keeps
-// every part a runtime decision (any combination, used for the cold layouts).
+// tcgen05.ld hands every thread ONE accumulator row (lane = row of the warp's 32-row slab).  Storing from that layout
+// makes each warp-wide 16-byte store touch 32 different cache lines (32 LSU wavefronts per instruction, every
+// residual / mul_in load likewise) -- measured: the epilogue, not the MMA, bounded every GEMM of the step.  So a 32-row
+// x 32-column chunk takes two phases:
+//   A  (row layout)       raw fp32 accumulators -> per-warp shared tile [32][32] f32, 16-byte pieces XOR-swizzled by
+//                         (row & 7): conflict-free for the row-per-thread writes AND the row-contiguous reads;
+//   B  (coalesced layout) lane = (row group, CW consecutive columns): 8 (CW = 4, fp32 / no output) or 4 (CW = 8, bf16
+//                         output) iterations, each a warp-wide access of full 128-byte (fp32) / 64-byte (bf16) row
+//                         segments.  ALL element-wise work happens here: + bias (one vector per lane per chunk, not
+//                         32 scalars per thread), pre-activation side output, GELU / ReLU, x GELU'(mul_in) / ReLU
+//                         mask, DropPath row gate, + residual, fp32 / bf16 / atomic output, and the fused
+//                         max-over-32-rows (per-lane running max + 2-3 shuffles instead of a shared-memory transpose).
+// Operands that do not depend on the accumulator (residual / mul_in pieces) are PREFETCHED into registers by
+// epi_prefetch() before the accumulator is waited for.  MODE is a compile-time hint that fixes which optional parts
+// exist (no flag tests, no dead register arrays); E_GENERIC keeps every part a runtime decision (cold layouts).
 enum : int { E_GENERIC = 0, E_PLAIN, E_GELU, E_MULGELU, E_MULRELU, E_RESID, E_ATOMIC, E_GMAX };
 
 struct EpiPre {
-    uint4 r[8];   // 128 B: either 32 f32 of the residual row or 32 bf16 of mul_in in r[0..3]
+    uint4 r[8];   // residual: 32 f32 of this lane's pieces;  mul_in: 32 bf16 (CW = 8: r[0..3]; CW = 4: 8-byte halves)
 };
 
 template <int MODE>
-__device__ __forceinline__ void epi_prefetch(const GemmEpi &epi, EpiPre &pre, int row, bool row_ok, int n, int N) {
-    constexpr bool G = MODE == E_GENERIC;
-    // E_RESID: the specialised kernels run 16 epilogue warps under a 96-register cap; 32 staged fp32 values x 2
-    // buffers would spill, so the residual row is loaded in place (the extra warps hide the latency instead)
-    if (!G && MODE != E_MULGELU && MODE != E_MULRELU) return;
-    if (!row_ok || n >= N) return;
-    const int ncols = min(32, N - n);
-    const bool has_mul = G ? (epi.mul_mode != 0) : (MODE == E_MULGELU || MODE == E_MULRELU);
-    const bool has_resid = G ? (epi.resid != nullptr) : (MODE == E_RESID);
-    if (has_mul) {
-        const uint4 *mi = reinterpret_cast<const uint4 *>(epi.mul_in + (size_t)row * epi.ldm + n);
+struct EpiTraits {
+    static constexpr bool G = MODE == E_GENERIC;
+    __device__ static __forceinline__ bool has_mul(const GemmEpi &e) {
+        return G ? (e.mul_mode != 0) : (MODE == E_MULGELU || MODE == E_MULRELU);
+    }
+    __device__ static __forceinline__ bool has_resid(const GemmEpi &e) { return G ? (e.resid != nullptr) : (MODE == E_RESID); }
+    // column width of a lane in phase B: 4 for fp32 / atomic / absent output, 8 for bf16 output
+    __device__ static __forceinline__ bool wide(const GemmEpi &e) {
+        if (MODE == E_ATOMIC) return false;
+        if (MODE == E_GELU) return true;
+        return e.out != nullptr && e.out_fp32 == 0;
+    }
+};
+
+// row0: first row of the warp's 32-row slab; n: first column of the chunk
+template <int MODE, int CW>
+__device__ __forceinline__ void epi_prefetch_cw(const GemmEpi &epi, EpiPre &pre, int row0, int M, int n, int N, int lane) {
+    using TR = EpiTraits<MODE>;
+    constexpr int NIT = CW == 4 ? 8 : 4, RPI = 32 / NIT;
+    const int rq = CW == 4 ? (lane >> 3) : (lane >> 2), cq = CW == 4 ? (lane & 7) : (lane & 3);
+    const int col = n + cq * CW;
+    if (col >= N) return;
+    if (TR::has_mul(epi)) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (j * 8 < ncols) pre.r[j] = __ldg(mi + j);
-    } else if (has_resid) {
-        const uint4 *rp =
-            reinterpret_cast<const uint4 *>(epi.resid + (size_t)(row / epi.resid_row_div) * epi.ldr + n);
-        if (epi.resid_row_div != 1) {                     // broadcast row (never aliases out): read-only path
+        for (int i = 0; i < NIT; ++i) {
+            const int row = row0 + i * RPI + rq;
+            if (row < M) {
+                const __nv_bfloat16 *mp = epi.mul_in + (size_t)row * epi.ldm + col;
+                if (CW == 8) {
+                    pre.r[i] = __ldg(reinterpret_cast<const uint4 *>(mp));
+                } else {
+                    const uint2 u = __ldg(reinterpret_cast<const uint2 *>(mp));
+                    if (i & 1) { pre.r[i >> 1].z = u.x; pre.r[i >> 1].w = u.y; }
+                    else { pre.r[i >> 1].x = u.x; pre.r[i >> 1].y = u.y; }
+                }
+            }
+        }
+    } else if (TR::has_resid(epi)) {
+        const bool bcast = epi.resid_row_div != 1;        // broadcast row never aliases out: read-only path
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j * 4 < ncols) pre.r[j] = __ldg(rp + j);
-        } else {
+        for (int i = 0; i < NIT; ++i) {
+            const int row = row0 + i * RPI + rq;
+            if (row < M) {
+                const uint4 *rp = reinterpret_cast<const uint4 *>(epi.resid + (size_t)(row / epi.resid_row_div) * epi.ldr + col);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j * 4 < ncols) pre.r[j] = rp[j];      // plain load: resid may alias out
+                for (int q = 0; q < CW / 4; ++q)          // plain load when resid may alias out (in-place residual)
+                    pre.r[i * (CW / 4) + q] = bcast ? __ldg(rp + q) : rp[q];
+            }
         }
     }
 }
-
-// gscratch: per-warp shared scratch [32][32] floats (XOR-swizzled) for the transposed group max (nullable -> redux path)
-// stage (nullable): per-warp shared tile [32 rows][32 cols] (bf16: 64 B rows, fp32: 128 B rows) that the caller
-// hands to a TMA store; when given, the final result goes there instead of straight to global memory.
 template <int MODE>
-__device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_t (&v)[32], const EpiPre &pre, int row,
-                                               bool row_ok, int n, int N, int lane, float *gscratch,
-                                               uint8_t *stage = nullptr) {
+__device__ __forceinline__ void epi_prefetch(const GemmEpi &epi, EpiPre &pre, int row0, int M, int n, int N, int lane) {
+    using TR = EpiTraits<MODE>;
+    if (MODE == E_PLAIN || MODE == E_GELU || MODE == E_ATOMIC || MODE == E_GMAX) return;
+    if (row0 >= M || n >= N) return;
+    if (TR::wide(epi)) epi_prefetch_cw<MODE, 8>(epi, pre, row0, M, n, N, lane);
+    else epi_prefetch_cw<MODE, 4>(epi, pre, row0, M, n, N, lane);
+}
+
+template <int MODE, int CW>
+__device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPre &pre, int row0, int M, int n, int N,
+                                                 int lane, const float *stage) {
+    using TR = EpiTraits<MODE>;
     constexpr bool G = MODE == E_GENERIC;
-    if (n >= N) return;                       // warp-uniform
+    constexpr int NIT = CW == 4 ? 8 : 4, RPI = 32 / NIT;
     const bool gmode = G ? (epi.gmax_f32 || epi.gmax_bf16 || epi.garg) : (MODE == E_GMAX);
     const int act_kind = G ? epi.act : (MODE == E_GELU ? 1 : 0);
     const int mul_mode = G ? epi.mul_mode : (MODE == E_MULGELU ? 1 : (MODE == E_MULRELU ? 2 : 0));
-    const bool has_resid = G ? (epi.resid != nullptr) : (MODE == E_RESID);
+    const bool has_resid = TR::has_resid(epi);
     const bool has_rscale = (G || MODE == E_RESID) ? (epi.row_scale != nullptr) : false;
     const bool has_preact = (G || MODE == E_GELU) ? (epi.preact_out != nullptr) : false;
     const bool atomic = G ? (epi.atomic != 0) : (MODE == E_ATOMIC);
     const bool has_bias = (MODE == E_ATOMIC || MODE == E_MULGELU || MODE == E_MULRELU) ? false : (epi.bias != nullptr);
-    const bool out_fp32 = MODE == E_ATOMIC ? true : (epi.out_fp32 != 0);
-    if (!row_ok && !gmode) return;
-    float f[32];
+    const int rq = CW == 4 ? (lane >> 3) : (lane >> 2), cq = CW == 4 ? (lane & 7) : (lane & 3);
+    const int col = n + cq * CW;
+    const bool col_ok = col < N;                      // N % 8 == 0 (host): a lane's CW columns are all in or all out
+    float bias[CW];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-    if (G && epi.alpha != 1.f) {
+    for (int j = 0; j < CW; ++j) bias[j] = 0.f;
+    if (has_bias && col_ok) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] *= epi.alpha;
+        for (int q = 0; q < CW / 4; ++q) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(epi.bias + col) + q);
+            bias[4 * q] = b4.x; bias[4 * q + 1] = b4.y; bias[4 * q + 2] = b4.z; bias[4 * q + 3] = b4.w;
+        }
     }
-    const int ncols = min(32, N - n);   // N % 8 == 0 guaranteed by the host
-    if (has_bias) {
+    float rs[NIT];
+    if (has_rscale) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            if (j < ncols) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(epi.bias + n + j));
-                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+        for (int i = 0; i < NIT; ++i) {
+            const int row = row0 + i * RPI + rq;
+            rs[i] = row < M ? __ldg(epi.row_scale + row / epi.rows_per_scale) : 0.f;
+        }
+    }
+    float best[CW];
+    int barg[CW];
+    if (gmode) {
+#pragma unroll
+        for (int j = 0; j < CW; ++j) { best[j] = -INFINITY; barg[j] = 0; }
+    }
+    const float4 *st4 = reinterpret_cast<const float4 *>(stage);
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+        const int r = i * RPI + rq, row = row0 + r;
+        const bool ok = col_ok && row < M;
+        float f[CW];
+#pragma unroll
+        for (int q = 0; q < CW / 4; ++q) {
+            const float4 x = st4[r * 8 + ((cq * (CW / 4) + q) ^ (r & 7))];
+            f[4 * q] = x.x; f[4 * q + 1] = x.y; f[4 * q + 2] = x.z; f[4 * q + 3] = x.w;
+        }
+#pragma unroll
+        for (int j = 0; j < CW; ++j) f[j] += bias[j];
+        if (gmode) {
+            // max over the slab's 32 rows of (acc + bias) per column; rows >= M never win; the first row wins ties
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+                const float x = row < M ? f[j] : -INFINITY;
+                if (x > best[j]) { best[j] = x; barg[j] = r; }
             }
+        }
+        if (!ok || (gmode && !epi.out)) continue;
+        if (has_preact) {
+            __nv_bfloat16 *po = reinterpret_cast<__nv_bfloat16 *>(epi.preact_out) + (size_t)row * epi.ldo + col;
+            uint32_t pk[CW / 2];
+#pragma unroll
+            for (int j = 0; j < CW / 2; ++j) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t *>(&h2);
+            }
+            if (CW == 8) *reinterpret_cast<uint4 *>(po) = make_uint4(pk[0], pk[1], pk[CW / 2 - 2], pk[CW / 2 - 1]);
+            else *reinterpret_cast<uint2 *>(po) = make_uint2(pk[0], pk[1]);
+        }
+        if (act_kind == 1) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) f[j] = gelu_erf(f[j]);
+        } else if (act_kind == 2) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (mul_mode) {
+            uint32_t mw[CW / 2];
+            if (CW == 8) {
+                mw[0] = pre.r[i].x; mw[1] = pre.r[i].y; mw[CW / 2 - 2] = pre.r[i].z; mw[CW / 2 - 1] = pre.r[i].w;
+            } else {
+                mw[0] = (i & 1) ? pre.r[i >> 1].z : pre.r[i >> 1].x;
+                mw[1] = (i & 1) ? pre.r[i >> 1].w : pre.r[i >> 1].y;
+            }
+#pragma unroll
+            for (int j = 0; j < CW / 2; ++j) {
+                const float2 u = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&mw[j]));
+                if (mul_mode == 1) {
+                    f[2 * j] *= gelu_erf_grad(u.x);
+                    f[2 * j + 1] *= gelu_erf_grad(u.y);
+                } else {
+                    f[2 * j] = u.x > 0.f ? f[2 * j] : 0.f;
+                    f[2 * j + 1] = u.y > 0.f ? f[2 * j + 1] : 0.f;
+                }
+            }
+        }
+        if (has_rscale) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) f[j] *= rs[i];
+        }
+        if (has_resid) {
+            if (!mul_mode) {
+#pragma unroll
+                for (int q = 0; q < CW / 4; ++q) {
+                    const uint4 r4 = pre.r[i * (CW / 4) + q];
+                    f[4 * q] += __uint_as_float(r4.x); f[4 * q + 1] += __uint_as_float(r4.y);
+                    f[4 * q + 2] += __uint_as_float(r4.z); f[4 * q + 3] += __uint_as_float(r4.w);
+                }
+            } else {      // the rare resid + mul_in combination (generic mode): the registers hold mul_in
+                const float4 *rp = reinterpret_cast<const float4 *>(epi.resid + (size_t)(row / epi.resid_row_div) * epi.ldr + col);
+#pragma unroll
+                for (int q = 0; q < CW / 4; ++q) {
+                    const float4 r4 = rp[q];
+                    f[4 * q] += r4.x; f[4 * q + 1] += r4.y; f[4 * q + 2] += r4.z; f[4 * q + 3] += r4.w;
+                }
+            }
+        }
+        if (CW == 4) {
+            if (epi.out) {
+                float *o = reinterpret_cast<float *>(epi.out) + (size_t)row * epi.ldo + col;
+                if (atomic)
+                    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(f[0]),
+                                 "f"(f[1]), "f"(f[2]), "f"(f[3])
+                                 : "memory");
+                else
+                    *reinterpret_cast<float4 *>(o) = make_float4(f[0], f[1], f[2], f[3]);
+            }
+        } else {
+            __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(epi.out) + (size_t)row * epi.ldo + col;
+            uint32_t pk[CW / 2];
+#pragma unroll
+            for (int j = 0; j < CW / 2; ++j) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                pk[j] = *reinterpret_cast<uint32_t *>(&h2);
+            }
+            *reinterpret_cast<uint4 *>(o) = make_uint4(pk[0], pk[1], pk[CW / 2 - 2], pk[CW / 2 - 1]);
         }
     }
     if (gmode) {
-        // max over the warp's 32 rows of (acc + bias), per column; rows >= M never win; first row wins ties
-        float best;
-        int barg;
-        const bool any_ok = __any_sync(0xffffffffu, row_ok);
-        if (gscratch) {
-            // transpose through shared memory: lane = row writes its 32 columns (XOR-swizzled: conflict-free both
-            // ways), then lane = column scans the 32 rows
-            __syncwarp();
+        // combine the row groups held by different lanes (same columns): lanes differ in rq
 #pragma unroll
-            for (int j = 0; j < 32; ++j) gscratch[lane * 32 + (j ^ lane)] = row_ok ? f[j] : -INFINITY;
-            __syncwarp();
-            best = gscratch[lane];            // row 0: column index lane ^ 0
-            barg = 0;
+        for (int off = (CW == 4 ? 8 : 4); off < 32; off <<= 1) {
 #pragma unroll
-            for (int r = 1; r < 32; ++r) {
-                const float x = gscratch[r * 32 + (lane ^ r)];
-                if (x > best) { best = x; barg = r; }
-            }
-        } else {
-            uint32_t my_max = 0, my_arg = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const uint32_t bb = __float_as_uint(f[j]);
-                const uint32_t u = row_ok ? ((bb & 0x80000000u) ? ~bb : (bb | 0x80000000u)) : 0u;
-                const uint32_t mx = __reduce_max_sync(0xffffffffu, u);
-                const uint32_t ar = __reduce_min_sync(0xffffffffu, u == mx ? (uint32_t)lane : 32u);
-                if (lane == j) { my_max = mx; my_arg = ar; }
-            }
-            best = __uint_as_float((my_max & 0x80000000u) ? (my_max & 0x7fffffffu) : ~my_max);
-            barg = (int)my_arg;
-        }
-        if (lane < ncols && any_ok) {
-            const size_t o = (size_t)(row >> 5) * epi.ldg + n + lane;
-            if (epi.gmax_f32) epi.gmax_f32[o] = best;
-            if (epi.gmax_bf16) epi.gmax_bf16[o] = __float2bfloat16_rn(best);
-            if (epi.garg) epi.garg[o] = (uint8_t)barg;
-        }
-        if (!epi.out || !row_ok) return;
-    }
-    if (has_preact) {
-        __nv_bfloat16 *po = reinterpret_cast<__nv_bfloat16 *>(epi.preact_out) + (size_t)row * epi.ldo + n;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-            if (j < ncols) {
-                uint4 pk;
-                __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
-                *reinterpret_cast<uint4 *>(po + j) = pk;
+            for (int j = 0; j < CW; ++j) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best[j], off);
+                const int oa = __shfl_xor_sync(0xffffffffu, barg[j], off);
+                if (ob > best[j] || (ob == best[j] && oa < barg[j])) { best[j] = ob; barg[j] = oa; }
             }
         }
-    }
-    if (act_kind == 1) {
+        if (rq == 0 && col_ok && row0 < M) {
+            const size_t o = (size_t)(row0 >> 5) * epi.ldg + col;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-    } else if (act_kind == 2) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-    }
-    if (mul_mode) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-            if (j < ncols) {
-                const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&pre.r[j >> 3]);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const float2 u = __bfloat1622float2(h[t]);
-                    if (mul_mode == 1) {
-                        f[j + 2 * t] *= gelu_erf_grad(u.x);
-                        f[j + 2 * t + 1] *= gelu_erf_grad(u.y);
-                    } else {
-                        f[j + 2 * t] = u.x > 0.f ? f[j + 2 * t] : 0.f;
-                        f[j + 2 * t + 1] = u.y > 0.f ? f[j + 2 * t + 1] : 0.f;
-                    }
-                }
-            }
-        }
-    }
-    if (has_rscale) {
-        const float rsc = __ldg(epi.row_scale + row / epi.rows_per_scale);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] *= rsc;
-    }
-    if (has_resid) {
-        if (G && !mul_mode) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                if (j < ncols) {
-                    const uint4 r4 = pre.r[j >> 2];
-                    f[j] += __uint_as_float(r4.x); f[j + 1] += __uint_as_float(r4.y);
-                    f[j + 2] += __uint_as_float(r4.z); f[j + 3] += __uint_as_float(r4.w);
-                }
-            }
-        } else {
-            // E_RESID (no staging registers), or the rare resid + mul_in combination: direct loads
-            const float *r = epi.resid + (size_t)(row / epi.resid_row_div) * epi.ldr + n;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                if (j < ncols) {
-                    const float4 r4 = *reinterpret_cast<const float4 *>(r + j);
-                    f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
-                }
-            }
-        }
-    }
-    if (stage) {
-        // row-per-thread writes into the staging tile; columns past N are clipped by the TMA store
-        if (out_fp32) {
-            float4 *o = reinterpret_cast<float4 *>(stage + lane * 128);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        } else {
-            uint4 *o = reinterpret_cast<uint4 *>(stage + lane * 64);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                uint4 pk;
-                __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(f[8 * j + 2 * t], f[8 * j + 2 * t + 1]);
-                o[j] = pk;
-            }
-        }
-        return;
-    }
-    if (out_fp32) {
-        float *o = reinterpret_cast<float *>(epi.out) + (size_t)row * epi.ldo + n;
-        if (atomic) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                if (j < ncols)
-                    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j),
-                                 "f"(f[j]), "f"(f[j + 1]), "f"(f[j + 2]), "f"(f[j + 3])
-                                 : "memory");
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                if (j < ncols) *reinterpret_cast<float4 *>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-        }
-    } else {
-        __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(epi.out) + (size_t)row * epi.ldo + n;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-            if (j < ncols) {
-                uint4 pk;
-                __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) h[t] = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
-                *reinterpret_cast<uint4 *>(o + j) = pk;
+            for (int j = 0; j < CW; ++j) {
+                if (epi.gmax_f32) epi.gmax_f32[o + j] = best[j];
+                if (epi.gmax_bf16) epi.gmax_bf16[o + j] = __float2bfloat16_rn(best[j]);
+                if (epi.garg) epi.garg[o + j] = (uint8_t)barg[j];
             }
         }
     }
 }
 
+// stage: this warp's private shared tile, 4 KB, 16-byte aligned.  v: the chunk's raw accumulators (row = lane).
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_t (&v)[32], const EpiPre &pre, int row0,
+                                               int M, int n, int N, int lane, float *stage) {
+    using TR = EpiTraits<MODE>;
+    if (n >= N || row0 >= M) return;                  // warp-uniform
+    __syncwarp();                                     // the previous chunk's phase-B reads of `stage` are done
+    {
+        float4 *st = reinterpret_cast<float4 *>(stage) + lane * 8;
+        const float a = (MODE == E_GENERIC) ? epi.alpha : 1.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            st[c ^ (lane & 7)] = make_float4(__uint_as_float(v[4 * c]) * a, __uint_as_float(v[4 * c + 1]) * a,
+                                             __uint_as_float(v[4 * c + 2]) * a, __uint_as_float(v[4 * c + 3]) * a);
+    }
+    __syncwarp();
+    if (TR::wide(epi)) epilogue_phase_b<MODE, 8>(epi, pre, row0, M, n, N, lane, stage);
+    else epilogue_phase_b<MODE, 4>(epi, pre, row0, M, n, N, lane, stage);
+}
+
 // ------------------------------------------------------------------------------------- the kernel
 template <int BN, bool A_MN, bool B_MN, int STAGES, int MODE>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a,
+__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                                  const __grid_constant__ CUtensorMap tma_b,
                                                                  const GemmEpi epi, int M, int N, int K,
                                                                  int kb_per_split) {
@@ -491,15 +514,17 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_co
     } else {
         // epilogue warps 2..5 -> TMEM lane quadrant warp % 4
         const int quad = warp & 3;
-        const int row = m0 + quad * 32 + lane;
-        const bool row_ok = row < M;
+        const int row0 = m0 + quad * 32;
         EpiPre cur, nxt;
-        epi_prefetch<MODE>(epi, cur, row, row_ok, n0, N);       // overlaps the whole main loop
+        epi_prefetch<MODE>(epi, cur, row0, M, n0, N, lane);       // overlaps the whole main loop
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
+        // every MMA has completed (tcgen05.commit), so the pipeline stages are dead: their memory becomes the four
+        // per-warp 4 KB epilogue tiles
+        float *stage = reinterpret_cast<float *>(smem) + quad * 1024;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
-            if (c0 + 32 < BN) epi_prefetch<MODE>(epi, nxt, row, row_ok, n0 + c0 + 32, N);
+            if (c0 + 32 < BN) epi_prefetch<MODE>(epi, nxt, row0, M, n0 + c0 + 32, N, lane);
             uint32_t v[32];
             __syncwarp();
             if (nkb > 0) {
@@ -508,7 +533,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_kernel(const __grid_co
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0u;
             }
-            epilogue_chunk<MODE>(epi, v, cur, row, row_ok, n0 + c0, N, lane, nullptr);
+            epilogue_chunk<MODE>(epi, v, cur, row0, M, n0 + c0, N, lane, stage);
             cur = nxt;
         }
     }
@@ -534,18 +559,15 @@ struct PersistCfg {
     static constexpr int EW = MODE == E_GENERIC ? 8 : 16;
     static constexpr int THREADS = (2 + EW) * 32;
     static constexpr int STAGES = 3;
-    static constexpr bool HAS_GS = MODE == E_GENERIC || MODE == E_GMAX;    // [32][33] fp32 scratch per epilogue warp
     static constexpr size_t smem(int BN) {
-        return (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024 +
-               ((HAS_GS && BN == 128) ? (size_t)EW * 32 * 32 * 4 : 0) + (size_t)EW * 4096;
+        return (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024 + (size_t)EW * 4096;
     }
 };
 
 template <int BN, bool A_MN, bool B_MN, int STAGES, int MODE>
 __global__ void __launch_bounds__(PersistCfg<MODE>::THREADS, 1) gemm_bf16_persistent_kernel(
-    const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-    const __grid_constant__ CUtensorMap tma_out, int use_tma_store, const GemmEpi epi, int M, int N, int K,
-    int kb_per_split, int tiles_m, int tiles_n, int total_tiles) {
+    const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmEpi epi, int M, int N,
+    int K, int kb_per_split, int tiles_m, int tiles_n, int total_tiles) {
     constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
     constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -642,71 +664,39 @@ __global__ void __launch_bounds__(PersistCfg<MODE>::THREADS, 1) gemm_bf16_persis
         constexpr int WCOLS = BN / (EW / 4);                        // columns of the tile owned by one epilogue warp
         const int e = warp - 2;
         const int quad = warp & 3, part = e >> 2;
-        // per-warp [32][33] fp32 scratch for the transposed group max, carved after the pipeline stages
-        constexpr bool HAS_GS = PersistCfg<MODE>::HAS_GS && BN == 128;      // the fused group max only runs with BN = 128
-        const bool gm = MODE == E_GENERIC ? (epi.gmax_f32 || epi.gmax_bf16 || epi.garg) : (MODE == E_GMAX);
-        float *gscratch = (gm && HAS_GS) ? reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES) + e * (32 * 32) : nullptr;
-        // output staging for the TMA store, 4 KB per warp: two 2 KB bf16 tiles (double-buffered against the bulk
-        // store in flight) or one 4 KB fp32 tile
-        constexpr uint32_t GS_BYTES = HAS_GS ? EW * 32 * 32 * 4 : 0;
-        uint8_t *stage_base = smem + STAGES * STAGE_BYTES + GS_BYTES + e * 4096;
-        const bool st_fp32 = MODE == E_ATOMIC ? true : (epi.out_fp32 != 0);
-        uint32_t nstore = 0;
-        EpiPre cur, nxt;
-        bool have_pre = false;
-        if (use_tma_store && warp == 2 && lane == 0) tma_prefetch_desc(&tma_out);
+        // this warp's 4 KB epilogue tile, carved after the pipeline stages
+        float *stage = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES) + e * 1024;
+        // Operand prefetch is single-buffered here: each chunk's residual / mul_in pieces are requested right before the
+        // accumulator is waited for / loaded; with 8-16 epilogue warps per SM the other warps cover that latency, and
+        // a second register buffer would not fit the 96-register budget of the 16-warp configuration.
+        EpiPre cur;
         uint32_t lt = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
             const int n0 = (t % tiles_n) * BN, m0 = ((t / tiles_n) % tiles_m) * GEMM_BM;
             const uint32_t buf = lt & 1;
-            const int row = m0 + quad * 32 + lane;
-            const bool row_ok = row < M;
+            const int row0 = m0 + quad * 32;
             constexpr int NCH = WCOLS / 32;                           // 32-column chunks per epilogue warp
             const int cbase = n0 + part * WCOLS;
-            // epilogue operands (residual / mul_in rows) are prefetched one chunk ahead ACROSS tiles: the first
-            // chunk of the next tile is requested while the last chunk of this one is processed
-            if (!have_pre) epi_prefetch<MODE>(epi, cur, row, row_ok, cbase, N);
+            epi_prefetch<MODE>(epi, cur, row0, M, cbase, N, lane);    // overlaps the wait for the tile's MMAs
             mbar_wait(&tfull_bar[buf], (lt >> 1) & 1);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + buf * BN + ((uint32_t)(quad * 32) << 16) + (uint32_t)(part * WCOLS);
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
-                if (c + 1 < NCH) {
-                    epi_prefetch<MODE>(epi, nxt, row, row_ok, cbase + (c + 1) * 32, N);
-                } else {
-                    const int t2 = t + gridDim.x;
-                    have_pre = t2 < total_tiles;
-                    if (have_pre) {
-                        const int row2 = ((t2 / tiles_n) % tiles_m) * GEMM_BM + quad * 32 + lane;
-                        epi_prefetch<MODE>(epi, nxt, row2, row2 < M, (t2 % tiles_n) * BN + part * WCOLS, N);
-                    }
-                }
+                if (c > 0) epi_prefetch<MODE>(epi, cur, row0, M, cbase + c * 32, N, lane);
                 uint32_t v[32];
                 __syncwarp();
                 tmem_ld32(tmem_d + (uint32_t)(c * 32), v);
-                const int n = cbase + c * 32;
-                if (use_tma_store && n < N) {
-                    uint8_t *stage = st_fp32 ? stage_base : stage_base + (nstore & 1) * 2048;
-                    if (lane == 0) {                         // the bulk store that last used this tile has read it
-                        if (st_fp32) bulk_wait_read<0>();
-                        else bulk_wait_read<1>();
-                    }
+                if (c + 1 == NCH) {
+                    // the accumulator buffer is fully in registers: hand it back to the MMA warp before the
+                    // (long) phase B of the last chunk
+                    tc_fence_before();
                     __syncwarp();
-                    epilogue_chunk<MODE>(epi, v, cur, row, row_ok, n, N, lane, gscratch, stage);
-                    fence_proxy_async();                     // generic-proxy smem writes -> visible to the TMA engine
-                    __syncwarp();
-                    if (lane == 0) tma_store_2d(&tma_out, stage, n, m0 + quad * 32);
-                    ++nstore;
-                } else {
-                    epilogue_chunk<MODE>(epi, v, cur, row, row_ok, n, N, lane, gscratch);
+                    if (lane == 0) mbar_arrive(&tempty_bar[buf]);
                 }
-                cur = nxt;
+                epilogue_chunk<MODE>(epi, v, cur, row0, M, cbase + c * 32, N, lane, stage);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[buf]);
         }
-        if (use_tma_store && lane == 0) bulk_wait_all();     // all bulk stores of this warp have completed
     }
     tc_fence_before();
     __syncthreads();
@@ -763,33 +753,11 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmE
     return ACT_OK;
 }
 
-// 2-D row-major output [rows, cols] (bf16 or fp32), box = 32 rows x 32 cols, no swizzle: the epilogue's TMA store
-static int make_out_map(CUtensorMap *map, const void *ptr, long long rows, long long cols, long long ld, bool fp32) {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) return ACT_EUNSUPPORTED;
-    const int es = fp32 ? 4 : 2;
-    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * es) % 16) return ACT_EALIGN;
-    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * es};
-    cuuint32_t box[2] = {32, 32};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                     const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? ACT_OK : ACT_EINVAL;
-}
-
 template <int BN, bool A_MN, bool B_MN, int MODE = E_GENERIC>
 static int launch_gemm_persistent(const CUtensorMap &ta, const CUtensorMap &tb, const GemmEpi &epi, int M, int N, int K,
                                   int splits, cudaStream_t st) {
     constexpr int STAGES = PersistCfg<MODE>::STAGES;
     constexpr size_t smem = PersistCfg<MODE>::smem(BN);
-    // results leave through smem + TMA bulk stores (full-line writes, no per-thread store wavefronts) whenever the
-    // epilogue has a plain tile output: not for split-K atomics, not with the pre-activation side output
-    CUtensorMap tout;
-    int use_tma_store = (epi.out && !epi.atomic && !epi.preact_out) ? 1 : 0;
-    if (use_tma_store && make_out_map(&tout, epi.out, M, N, epi.ldo, epi.out_fp32 != 0) != ACT_OK) use_tma_store = 0;
-    if (!use_tma_store) tout = ta;
     auto kern = gemm_bf16_persistent_kernel<BN, A_MN, B_MN, STAGES, MODE>;
     ACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int total_kb = (K + GEMM_BK - 1) / GEMM_BK;
@@ -801,7 +769,7 @@ static int launch_gemm_persistent(const CUtensorMap &ta, const CUtensorMap &tb, 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = (int)(total < sms ? total : sms);
-    ACT_CUDA(launch_k(kern, dim3(grid), dim3(PersistCfg<MODE>::THREADS), smem, st, true, ta, tb, tout, use_tma_store, epi, M, N, K,
+    ACT_CUDA(launch_k(kern, dim3(grid), dim3(PersistCfg<MODE>::THREADS), smem, st, true, ta, tb, epi, M, N, K,
                       kbps, tiles_m, tiles_n, (int)total));
     return ACT_OK;
 }
