@@ -157,6 +157,21 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
     return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 
+// explicit shared-window accesses for the epilogue tile (a generic pointer derived from the aligned dynamic-smem
+// base compiles to generic LD/ST, which are slower than LDS/STS)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&h2);
+}
+
 // ------------------------------------------------------------------------------------------ epilogue
 // tcgen05.ld hands every thread ONE accumulator row (lane = row of the warp's 32-row slab).  Storing from that layout
 // makes each warp-wide 16-byte store touch 32 different cache lines (32 LSU wavefronts per instruction, every
@@ -194,20 +209,22 @@ struct EpiTraits {
     }
 };
 
-// row0: first row of the warp's 32-row slab; n: first column of the chunk
-template <int MODE, int CW>
+// row0: first row of the warp's 32-row slab; n: first column of the chunk.  Row indices advance by pointer stepping
+// (one 64-bit add per iteration): the epilogue is instruction-issue bound, so no per-element index arithmetic.
+template <int MODE, int CW, bool FULL>
 __device__ __forceinline__ void epi_prefetch_cw(const GemmEpi &epi, EpiPre &pre, int row0, int M, int n, int N, int lane) {
     using TR = EpiTraits<MODE>;
     constexpr int NIT = CW == 4 ? 8 : 4, RPI = 32 / NIT;
     const int rq = CW == 4 ? (lane >> 3) : (lane >> 2), cq = CW == 4 ? (lane & 7) : (lane & 3);
     const int col = n + cq * CW;
-    if (col >= N) return;
+    if (!FULL && col >= N) return;
+    const int rows_left = FULL ? 32 : M - (row0 + rq);   // iteration i is in range iff i * RPI < rows_left
     if (TR::has_mul(epi)) {
+        const __nv_bfloat16 *mp = epi.mul_in + (size_t)(row0 + rq) * epi.ldm + col;
+        const size_t step = (size_t)RPI * epi.ldm;
 #pragma unroll
-        for (int i = 0; i < NIT; ++i) {
-            const int row = row0 + i * RPI + rq;
-            if (row < M) {
-                const __nv_bfloat16 *mp = epi.mul_in + (size_t)row * epi.ldm + col;
+        for (int i = 0; i < NIT; ++i, mp += step) {
+            if (i * RPI < rows_left) {
                 if (CW == 8) {
                     pre.r[i] = __ldg(reinterpret_cast<const uint4 *>(mp));
                 } else {
@@ -218,15 +235,22 @@ __device__ __forceinline__ void epi_prefetch_cw(const GemmEpi &epi, EpiPre &pre,
             }
         }
     } else if (TR::has_resid(epi)) {
-        const bool bcast = epi.resid_row_div != 1;        // broadcast row never aliases out: read-only path
+        if (epi.resid_row_div != 1) {
+            // per-group broadcast row (resid_row_div % 32 == 0, host-checked): the whole slab reads ONE residual row,
+            // which never aliases out -> read-only path, one address
+            const uint4 *rp = reinterpret_cast<const uint4 *>(epi.resid + (size_t)(row0 / epi.resid_row_div) * epi.ldr + col);
 #pragma unroll
-        for (int i = 0; i < NIT; ++i) {
-            const int row = row0 + i * RPI + rq;
-            if (row < M) {
-                const uint4 *rp = reinterpret_cast<const uint4 *>(epi.resid + (size_t)(row / epi.resid_row_div) * epi.ldr + col);
+            for (int q = 0; q < CW / 4; ++q) pre.r[q] = __ldg(rp + q);
+        } else {
+            const float *rp = epi.resid + (size_t)(row0 + rq) * epi.ldr + col;
+            const size_t step = (size_t)RPI * epi.ldr;
 #pragma unroll
-                for (int q = 0; q < CW / 4; ++q)          // plain load when resid may alias out (in-place residual)
-                    pre.r[i * (CW / 4) + q] = bcast ? __ldg(rp + q) : rp[q];
+            for (int i = 0; i < NIT; ++i, rp += step) {
+                if (i * RPI < rows_left) {
+#pragma unroll
+                    for (int q = 0; q < CW / 4; ++q)      // plain load: resid may alias out (in-place residual stream)
+                        pre.r[i * (CW / 4) + q] = reinterpret_cast<const uint4 *>(rp)[q];
+                }
             }
         }
     }
@@ -236,13 +260,20 @@ __device__ __forceinline__ void epi_prefetch(const GemmEpi &epi, EpiPre &pre, in
     using TR = EpiTraits<MODE>;
     if (MODE == E_PLAIN || MODE == E_GELU || MODE == E_ATOMIC || MODE == E_GMAX) return;
     if (row0 >= M || n >= N) return;
-    if (TR::wide(epi)) epi_prefetch_cw<MODE, 8>(epi, pre, row0, M, n, N, lane);
-    else epi_prefetch_cw<MODE, 4>(epi, pre, row0, M, n, N, lane);
+    // FULL: the chunk lies entirely inside the matrix (the common case) -> no per-row / per-column predicates
+    const bool full = row0 + 32 <= M && n + 32 <= N;
+    if (TR::wide(epi)) {
+        if (full) epi_prefetch_cw<MODE, 8, true>(epi, pre, row0, M, n, N, lane);
+        else epi_prefetch_cw<MODE, 8, false>(epi, pre, row0, M, n, N, lane);
+    } else {
+        if (full) epi_prefetch_cw<MODE, 4, true>(epi, pre, row0, M, n, N, lane);
+        else epi_prefetch_cw<MODE, 4, false>(epi, pre, row0, M, n, N, lane);
+    }
 }
 
-template <int MODE, int CW>
+template <int MODE, int CW, bool FULL>
 __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPre &pre, int row0, int M, int n, int N,
-                                                 int lane, const float *stage) {
+                                                 int lane, uint32_t stage) {
     using TR = EpiTraits<MODE>;
     constexpr bool G = MODE == E_GENERIC;
     constexpr int NIT = CW == 4 ? 8 : 4, RPI = 32 / NIT;
@@ -250,29 +281,34 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
     const int act_kind = G ? epi.act : (MODE == E_GELU ? 1 : 0);
     const int mul_mode = G ? epi.mul_mode : (MODE == E_MULGELU ? 1 : (MODE == E_MULRELU ? 2 : 0));
     const bool has_resid = TR::has_resid(epi);
+    const bool bcast_resid = has_resid && epi.resid_row_div != 1;
     const bool has_rscale = (G || MODE == E_RESID) ? (epi.row_scale != nullptr) : false;
     const bool has_preact = (G || MODE == E_GELU) ? (epi.preact_out != nullptr) : false;
     const bool atomic = G ? (epi.atomic != 0) : (MODE == E_ATOMIC);
     const bool has_bias = (MODE == E_ATOMIC || MODE == E_MULGELU || MODE == E_MULRELU) ? false : (epi.bias != nullptr);
+    const bool has_out = (MODE == E_GMAX || G) ? (epi.out != nullptr) : true;
     const int rq = CW == 4 ? (lane >> 3) : (lane >> 2), cq = CW == 4 ? (lane & 7) : (lane & 3);
     const int col = n + cq * CW;
-    const bool col_ok = col < N;                      // N % 8 == 0 (host): a lane's CW columns are all in or all out
+    const bool col_ok = FULL || col < N;              // N % 8 == 0 (host): a lane's CW columns are all in or all out
+    const int rfirst = row0 + rq;
+    const int rows_left = FULL ? 32 : (col_ok ? M - rfirst : 0);    // iteration i stores iff i * RPI < rows_left
     float bias[CW];
-#pragma unroll
-    for (int j = 0; j < CW; ++j) bias[j] = 0.f;
-    if (has_bias && col_ok) {
+    if (has_bias) {
 #pragma unroll
         for (int q = 0; q < CW / 4; ++q) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(epi.bias + col) + q);
+            const float4 b4 = col_ok ? __ldg(reinterpret_cast<const float4 *>(epi.bias + col) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
             bias[4 * q] = b4.x; bias[4 * q + 1] = b4.y; bias[4 * q + 2] = b4.z; bias[4 * q + 3] = b4.w;
         }
     }
     float rs[NIT];
     if (has_rscale) {
+        // one division per chunk; the scale index then advances incrementally (rows_per_scale >= 8 >= RPI, host-checked)
+        int sq = rfirst / epi.rows_per_scale, srem = rfirst - sq * epi.rows_per_scale;
 #pragma unroll
         for (int i = 0; i < NIT; ++i) {
-            const int row = row0 + i * RPI + rq;
-            rs[i] = row < M ? __ldg(epi.row_scale + row / epi.rows_per_scale) : 0.f;
+            rs[i] = i * RPI < rows_left ? __ldg(epi.row_scale + sq) : 0.f;
+            srem += RPI;
+            if (srem >= epi.rows_per_scale) { srem -= epi.rows_per_scale; ++sq; }
         }
     }
     float best[CW];
@@ -281,107 +317,117 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
 #pragma unroll
         for (int j = 0; j < CW; ++j) { best[j] = -INFINITY; barg[j] = 0; }
     }
-    const float4 *st4 = reinterpret_cast<const float4 *>(stage);
+    // byte pointers stepped by RPI rows per iteration
+    const size_t osz = CW == 4 ? 4 : 2;
+    char *op = has_out ? reinterpret_cast<char *>(epi.out) + ((size_t)rfirst * epi.ldo + col) * osz : nullptr;
+    const size_t ostep = (size_t)RPI * epi.ldo * osz;
+    char *pp = has_preact ? reinterpret_cast<char *>(epi.preact_out) + ((size_t)rfirst * epi.ldo + col) * 2 : nullptr;
+    const size_t pstep = (size_t)RPI * epi.ldo * 2;
+    const uint32_t st4 = stage + rq * 128;            // byte address of row rq of the tile
 #pragma unroll
     for (int i = 0; i < NIT; ++i) {
-        const int r = i * RPI + rq, row = row0 + r;
-        const bool ok = col_ok && row < M;
+        const int r = i * RPI + rq;
         float f[CW];
 #pragma unroll
         for (int q = 0; q < CW / 4; ++q) {
-            const float4 x = st4[r * 8 + ((cq * (CW / 4) + q) ^ (r & 7))];
+            // (r & 7) == (rq & 7) for CW = 8 (RPI = 8); for CW = 4 it alternates with i: ((i * 4 + rq) & 7)
+            const float4 x = lds128(st4 + (i * RPI * 8 + ((cq * (CW / 4) + q) ^ (r & 7))) * 16);
             f[4 * q] = x.x; f[4 * q + 1] = x.y; f[4 * q + 2] = x.z; f[4 * q + 3] = x.w;
         }
+        if (has_bias) {
 #pragma unroll
-        for (int j = 0; j < CW; ++j) f[j] += bias[j];
+            for (int j = 0; j < CW; ++j) f[j] += bias[j];
+        }
         if (gmode) {
-            // max over the slab's 32 rows of (acc + bias) per column; rows >= M never win; the first row wins ties
+            // max over the slab's 32 rows of (acc + bias) per column; the first row wins ties.  M % 32 == 0 in this
+            // mode (host-checked), so every row of a live slab is in range.
 #pragma unroll
-            for (int j = 0; j < CW; ++j) {
-                const float x = row < M ? f[j] : -INFINITY;
-                if (x > best[j]) { best[j] = x; barg[j] = r; }
-            }
+            for (int j = 0; j < CW; ++j)
+                if (f[j] > best[j]) { best[j] = f[j]; barg[j] = r; }
         }
-        if (!ok || (gmode && !epi.out)) continue;
-        if (has_preact) {
-            __nv_bfloat16 *po = reinterpret_cast<__nv_bfloat16 *>(epi.preact_out) + (size_t)row * epi.ldo + col;
-            uint32_t pk[CW / 2];
+        if (i * RPI < rows_left && has_out) {
+            if (has_preact) {
+                uint32_t pk[CW / 2];
 #pragma unroll
-            for (int j = 0; j < CW / 2; ++j) {
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                pk[j] = *reinterpret_cast<uint32_t *>(&h2);
+                for (int j = 0; j < CW / 2; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                if (CW == 8) *reinterpret_cast<uint4 *>(pp) = make_uint4(pk[0], pk[1], pk[CW / 2 - 2], pk[CW / 2 - 1]);
+                else *reinterpret_cast<uint2 *>(pp) = make_uint2(pk[0], pk[1]);
             }
-            if (CW == 8) *reinterpret_cast<uint4 *>(po) = make_uint4(pk[0], pk[1], pk[CW / 2 - 2], pk[CW / 2 - 1]);
-            else *reinterpret_cast<uint2 *>(po) = make_uint2(pk[0], pk[1]);
-        }
-        if (act_kind == 1) {
+            if (act_kind == 1) {
 #pragma unroll
-            for (int j = 0; j < CW; ++j) f[j] = gelu_erf(f[j]);
-        } else if (act_kind == 2) {
+                for (int j = 0; j < CW; ++j) f[j] = gelu_erf(f[j]);
+            } else if (act_kind == 2) {
 #pragma unroll
-            for (int j = 0; j < CW; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        if (mul_mode) {
-            uint32_t mw[CW / 2];
-            if (CW == 8) {
-                mw[0] = pre.r[i].x; mw[1] = pre.r[i].y; mw[CW / 2 - 2] = pre.r[i].z; mw[CW / 2 - 1] = pre.r[i].w;
-            } else {
-                mw[0] = (i & 1) ? pre.r[i >> 1].z : pre.r[i >> 1].x;
-                mw[1] = (i & 1) ? pre.r[i >> 1].w : pre.r[i >> 1].y;
+                for (int j = 0; j < CW; ++j) f[j] = fmaxf(f[j], 0.f);
             }
-#pragma unroll
-            for (int j = 0; j < CW / 2; ++j) {
-                const float2 u = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&mw[j]));
-                if (mul_mode == 1) {
-                    f[2 * j] *= gelu_erf_grad(u.x);
-                    f[2 * j + 1] *= gelu_erf_grad(u.y);
+            if (mul_mode) {
+                uint32_t mw[CW / 2];
+                if (CW == 8) {
+                    mw[0] = pre.r[i].x; mw[1] = pre.r[i].y; mw[CW / 2 - 2] = pre.r[i].z; mw[CW / 2 - 1] = pre.r[i].w;
                 } else {
-                    f[2 * j] = u.x > 0.f ? f[2 * j] : 0.f;
-                    f[2 * j + 1] = u.y > 0.f ? f[2 * j + 1] : 0.f;
+                    mw[0] = (i & 1) ? pre.r[i >> 1].z : pre.r[i >> 1].x;
+                    mw[1] = (i & 1) ? pre.r[i >> 1].w : pre.r[i >> 1].y;
+                }
+#pragma unroll
+                for (int j = 0; j < CW / 2; ++j) {
+                    const float2 u = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&mw[j]));
+                    if (mul_mode == 1) {
+                        f[2 * j] *= gelu_erf_grad(u.x);
+                        f[2 * j + 1] *= gelu_erf_grad(u.y);
+                    } else {
+                        f[2 * j] = u.x > 0.f ? f[2 * j] : 0.f;
+                        f[2 * j + 1] = u.y > 0.f ? f[2 * j + 1] : 0.f;
+                    }
                 }
             }
-        }
-        if (has_rscale) {
+            if (has_rscale) {
 #pragma unroll
-            for (int j = 0; j < CW; ++j) f[j] *= rs[i];
-        }
-        if (has_resid) {
-            if (!mul_mode) {
+                for (int j = 0; j < CW; ++j) f[j] *= rs[i];
+            }
+            if (has_resid) {
+                if (!mul_mode) {
+                    // two branches with STATIC register indices (a selected index would push `pre` to local memory)
+                    if (bcast_resid) {
 #pragma unroll
-                for (int q = 0; q < CW / 4; ++q) {
-                    const uint4 r4 = pre.r[i * (CW / 4) + q];
-                    f[4 * q] += __uint_as_float(r4.x); f[4 * q + 1] += __uint_as_float(r4.y);
-                    f[4 * q + 2] += __uint_as_float(r4.z); f[4 * q + 3] += __uint_as_float(r4.w);
-                }
-            } else {      // the rare resid + mul_in combination (generic mode): the registers hold mul_in
-                const float4 *rp = reinterpret_cast<const float4 *>(epi.resid + (size_t)(row / epi.resid_row_div) * epi.ldr + col);
+                        for (int q = 0; q < CW / 4; ++q) {
+                            const uint4 r4 = pre.r[q];
+                            f[4 * q] += __uint_as_float(r4.x); f[4 * q + 1] += __uint_as_float(r4.y);
+                            f[4 * q + 2] += __uint_as_float(r4.z); f[4 * q + 3] += __uint_as_float(r4.w);
+                        }
+                    } else {
 #pragma unroll
-                for (int q = 0; q < CW / 4; ++q) {
-                    const float4 r4 = rp[q];
-                    f[4 * q] += r4.x; f[4 * q + 1] += r4.y; f[4 * q + 2] += r4.z; f[4 * q + 3] += r4.w;
+                        for (int q = 0; q < CW / 4; ++q) {
+                            const uint4 r4 = pre.r[i * (CW / 4) + q];
+                            f[4 * q] += __uint_as_float(r4.x); f[4 * q + 1] += __uint_as_float(r4.y);
+                            f[4 * q + 2] += __uint_as_float(r4.z); f[4 * q + 3] += __uint_as_float(r4.w);
+                        }
+                    }
+                } else {      // the rare resid + mul_in combination (generic mode): the registers hold mul_in
+                    const float4 *rp = reinterpret_cast<const float4 *>(
+                        epi.resid + (size_t)((rfirst + i * RPI) / epi.resid_row_div) * epi.ldr + col);
+#pragma unroll
+                    for (int q = 0; q < CW / 4; ++q) {
+                        const float4 r4 = rp[q];
+                        f[4 * q] += r4.x; f[4 * q + 1] += r4.y; f[4 * q + 2] += r4.z; f[4 * q + 3] += r4.w;
+                    }
                 }
             }
-        }
-        if (CW == 4) {
-            if (epi.out) {
-                float *o = reinterpret_cast<float *>(epi.out) + (size_t)row * epi.ldo + col;
+            if (CW == 4) {
                 if (atomic)
-                    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(f[0]),
+                    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(op), "f"(f[0]),
                                  "f"(f[1]), "f"(f[2]), "f"(f[3])
                                  : "memory");
                 else
-                    *reinterpret_cast<float4 *>(o) = make_float4(f[0], f[1], f[2], f[3]);
-            }
-        } else {
-            __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(epi.out) + (size_t)row * epi.ldo + col;
-            uint32_t pk[CW / 2];
+                    *reinterpret_cast<float4 *>(op) = make_float4(f[0], f[1], f[2], f[3]);
+            } else {
+                uint32_t pk[CW / 2];
 #pragma unroll
-            for (int j = 0; j < CW / 2; ++j) {
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                pk[j] = *reinterpret_cast<uint32_t *>(&h2);
+                for (int j = 0; j < CW / 2; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                *reinterpret_cast<uint4 *>(op) = make_uint4(pk[0], pk[1], pk[CW / 2 - 2], pk[CW / 2 - 1]);
             }
-            *reinterpret_cast<uint4 *>(o) = make_uint4(pk[0], pk[1], pk[CW / 2 - 2], pk[CW / 2 - 1]);
         }
+        op += ostep;
+        pp += pstep;
     }
     if (gmode) {
         // combine the row groups held by different lanes (same columns): lanes differ in rq
@@ -394,7 +440,7 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
                 if (ob > best[j] || (ob == best[j] && oa < barg[j])) { best[j] = ob; barg[j] = oa; }
             }
         }
-        if (rq == 0 && col_ok && row0 < M) {
+        if (rq == 0 && col_ok) {
             const size_t o = (size_t)(row0 >> 5) * epi.ldg + col;
 #pragma unroll
             for (int j = 0; j < CW; ++j) {
@@ -406,24 +452,55 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
     }
 }
 
-// stage: this warp's private shared tile, 4 KB, 16-byte aligned.  v: the chunk's raw accumulators (row = lane).
-template <int MODE>
-__device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_t (&v)[32], const EpiPre &pre, int row0,
-                                               int M, int n, int N, int lane, float *stage) {
+// stage: shared-window byte address of this warp's private 4 KB tile (16-byte aligned).  v: the chunk's raw
+// accumulators (row = lane).
+// LATE: request the chunk's residual / mul_in pieces only after the accumulators have left the registers (phase A), so
+// the two 32-register sets are never live together -- the 16-warp persistent configuration has 96 registers per
+// thread, and its spills went to L2 (the L1 is almost entirely carved out as shared memory there).
+template <int MODE, bool LATE = false>
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_t (&v)[32], EpiPre &pre, int row0,
+                                               int M, int n, int N, int lane, uint32_t stage) {
     using TR = EpiTraits<MODE>;
     if (n >= N || row0 >= M) return;                  // warp-uniform
-    __syncwarp();                                     // the previous chunk's phase-B reads of `stage` are done
+    __syncwarp();                                     // the previous chunk's phase-B reads of the tile are done
     {
-        float4 *st = reinterpret_cast<float4 *>(stage) + lane * 8;
+        const uint32_t st = stage + lane * 128;
         const float a = (MODE == E_GENERIC) ? epi.alpha : 1.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-            st[c ^ (lane & 7)] = make_float4(__uint_as_float(v[4 * c]) * a, __uint_as_float(v[4 * c + 1]) * a,
-                                             __uint_as_float(v[4 * c + 2]) * a, __uint_as_float(v[4 * c + 3]) * a);
+            sts128(st + ((c ^ (lane & 7)) << 4), __uint_as_float(v[4 * c]) * a, __uint_as_float(v[4 * c + 1]) * a,
+                   __uint_as_float(v[4 * c + 2]) * a, __uint_as_float(v[4 * c + 3]) * a);
     }
+    if (LATE) epi_prefetch<MODE>(epi, pre, row0, M, n, N, lane);
     __syncwarp();
-    if (TR::wide(epi)) epilogue_phase_b<MODE, 8>(epi, pre, row0, M, n, N, lane, stage);
-    else epilogue_phase_b<MODE, 4>(epi, pre, row0, M, n, N, lane, stage);
+    const bool full = row0 + 32 <= M && n + 32 <= N;
+    if (TR::wide(epi)) {
+        if (full) epilogue_phase_b<MODE, 8, true>(epi, pre, row0, M, n, N, lane, stage);
+        else epilogue_phase_b<MODE, 8, false>(epi, pre, row0, M, n, N, lane, stage);
+    } else {
+        if (full) epilogue_phase_b<MODE, 4, true>(epi, pre, row0, M, n, N, lane, stage);
+        else epilogue_phase_b<MODE, 4, false>(epi, pre, row0, M, n, N, lane, stage);
+    }
+}
+
+// One chunk: TMEM -> registers, (optionally) hand the accumulator buffer back, then the two epilogue phases.
+template <int MODE, bool LATE = false>
+__device__ __forceinline__ void epi_do_chunk(const GemmEpi &epi, uint32_t taddr, bool have_acc, uint64_t *release_bar,
+                                             EpiPre &pre, int row0, int M, int n, int N, int lane, uint32_t stage) {
+    uint32_t v[32];
+    __syncwarp();
+    if (have_acc) {
+        tmem_ld32(taddr, v);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+    }
+    if (release_bar) {        // last chunk of a tile: the accumulator is in registers, free the TMEM buffer now
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(release_bar);
+    }
+    epilogue_chunk<MODE, LATE>(epi, v, pre, row0, M, n, N, lane, stage);
 }
 
 // ------------------------------------------------------------------------------------- the kernel
@@ -515,26 +592,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const __grid
         // epilogue warps 2..5 -> TMEM lane quadrant warp % 4
         const int quad = warp & 3;
         const int row0 = m0 + quad * 32;
-        EpiPre cur, nxt;
-        epi_prefetch<MODE>(epi, cur, row0, M, n0, N, lane);       // overlaps the whole main loop
+        // two operand buffers used in ping-pong (chunks 2j -> pa, 2j+1 -> pb; BN / 32 is even): a `cur = nxt` copy
+        // would make every prefetch synchronous (the register move waits for the load)
+        EpiPre pa, pb;
+        epi_prefetch<MODE>(epi, pa, row0, M, n0, N, lane);        // overlaps the whole main loop
         mbar_wait(&tmem_full_bar, 0);
         tc_fence_after();
         // every MMA has completed (tcgen05.commit), so the pipeline stages are dead: their memory becomes the four
         // per-warp 4 KB epilogue tiles
-        float *stage = reinterpret_cast<float *>(smem) + quad * 1024;
+        const uint32_t stage = smem_u32(smem) + quad * 4096;
+        const uint32_t tbase = tmem_d + ((uint32_t)(quad * 32) << 16);
+        static_assert((BN / 32) % 2 == 0, "chunk count must be even");
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            if (c0 + 32 < BN) epi_prefetch<MODE>(epi, nxt, row0, M, n0 + c0 + 32, N, lane);
-            uint32_t v[32];
-            __syncwarp();
-            if (nkb > 0) {
-                tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = 0u;
-            }
-            epilogue_chunk<MODE>(epi, v, cur, row0, M, n0 + c0, N, lane, stage);
-            cur = nxt;
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+            epi_prefetch<MODE>(epi, pb, row0, M, n0 + c0 + 32, N, lane);
+            epi_do_chunk<MODE>(epi, tbase + (uint32_t)c0, nkb > 0, nullptr, pa, row0, M, n0 + c0, N, lane, stage);
+            if (c0 + 64 < BN) epi_prefetch<MODE>(epi, pa, row0, M, n0 + c0 + 64, N, lane);
+            epi_do_chunk<MODE>(epi, tbase + (uint32_t)(c0 + 32), nkb > 0, nullptr, pb, row0, M, n0 + c0 + 32, N, lane, stage);
         }
     }
     tc_fence_before();
@@ -556,7 +630,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const __grid
 // epilogues fit 96 registers, so twice the warps hide the epilogue's dependent-instruction latency)
 template <int MODE>
 struct PersistCfg {
-    static constexpr int EW = MODE == E_GENERIC ? 8 : 16;
+    static constexpr int EW = (MODE == E_GENERIC) ? 8 : 16;
     static constexpr int THREADS = (2 + EW) * 32;
     static constexpr int STAGES = 3;
     static constexpr size_t smem(int BN) {
@@ -665,36 +739,48 @@ __global__ void __launch_bounds__(PersistCfg<MODE>::THREADS, 1) gemm_bf16_persis
         const int e = warp - 2;
         const int quad = warp & 3, part = e >> 2;
         // this warp's 4 KB epilogue tile, carved after the pipeline stages
-        float *stage = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES) + e * 1024;
-        // Operand prefetch is single-buffered here: each chunk's residual / mul_in pieces are requested right before the
-        // accumulator is waited for / loaded; with 8-16 epilogue warps per SM the other warps cover that latency, and
-        // a second register buffer would not fit the 96-register budget of the 16-warp configuration.
-        EpiPre cur;
+        const uint32_t stage = smem_u32(smem + STAGES * STAGE_BYTES) + e * 4096;
+        // Operand prefetch: with 16 epilogue warps (96-register budget) each chunk's residual / mul_in pieces are
+        // requested after its accumulators left the registers and the other warps cover the latency (DB = false); the
+        // 8-warp configurations have the registers for two buffers used in ping-pong, one chunk AHEAD, across tiles
+        // too (DB = true; never `cur = nxt`: the register copy would wait for the loads).
+        constexpr bool DB = EW == 8;
+        constexpr int NCH = WCOLS / 32;                               // 32-column chunks per epilogue warp
+        static_assert(!DB || NCH % 2 == 0, "ping-pong needs an even chunk count");
+        EpiPre pa, pb;
+        bool have_pre = false;
         uint32_t lt = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
             const int n0 = (t % tiles_n) * BN, m0 = ((t / tiles_n) % tiles_m) * GEMM_BM;
             const uint32_t buf = lt & 1;
             const int row0 = m0 + quad * 32;
-            constexpr int NCH = WCOLS / 32;                           // 32-column chunks per epilogue warp
             const int cbase = n0 + part * WCOLS;
-            epi_prefetch<MODE>(epi, cur, row0, M, cbase, N, lane);    // overlaps the wait for the tile's MMAs
+            if (DB && !have_pre) epi_prefetch<MODE>(epi, pa, row0, M, cbase, N, lane);    // overlaps the wait below
             mbar_wait(&tfull_bar[buf], (lt >> 1) & 1);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + buf * BN + ((uint32_t)(quad * 32) << 16) + (uint32_t)(part * WCOLS);
+            if (DB) {
 #pragma unroll 1
-            for (int c = 0; c < NCH; ++c) {
-                if (c > 0) epi_prefetch<MODE>(epi, cur, row0, M, cbase + c * 32, N, lane);
-                uint32_t v[32];
-                __syncwarp();
-                tmem_ld32(tmem_d + (uint32_t)(c * 32), v);
-                if (c + 1 == NCH) {
-                    // the accumulator buffer is fully in registers: hand it back to the MMA warp before the
-                    // (long) phase B of the last chunk
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+                for (int c = 0; c < NCH; c += 2) {
+                    epi_prefetch<MODE>(epi, pb, row0, M, cbase + (c + 1) * 32, N, lane);
+                    epi_do_chunk<MODE>(epi, tmem_d + (uint32_t)(c * 32), true, nullptr, pa, row0, M, cbase + c * 32, N, lane, stage);
+                    if (c + 2 < NCH) {
+                        epi_prefetch<MODE>(epi, pa, row0, M, cbase + (c + 2) * 32, N, lane);
+                    } else {
+                        const int t2 = t + gridDim.x;
+                        have_pre = t2 < total_tiles;
+                        if (have_pre)
+                            epi_prefetch<MODE>(epi, pa, ((t2 / tiles_n) % tiles_m) * GEMM_BM + quad * 32, M,
+                                               (t2 % tiles_n) * BN + part * WCOLS, N, lane);
+                    }
+                    epi_do_chunk<MODE>(epi, tmem_d + (uint32_t)((c + 1) * 32), true, c + 2 >= NCH ? &tempty_bar[buf] : nullptr,
+                                       pb, row0, M, cbase + (c + 1) * 32, N, lane, stage);
                 }
-                epilogue_chunk<MODE>(epi, v, cur, row0, M, cbase + c * 32, N, lane, stage);
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < NCH; ++c)
+                    epi_do_chunk<MODE, true>(epi, tmem_d + (uint32_t)(c * 32), true, c + 1 == NCH ? &tempty_bar[buf] : nullptr,
+                                             pa, row0, M, cbase + c * 32, N, lane, stage);
             }
         }
     }
@@ -795,6 +881,8 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
     if (splits > 1 && !out_fp32) return ACT_EINVAL;
     if (splits > 1 && (bias || act_kind || mul_mode || resid || preact_out || row_scale)) return ACT_EINVAL;
     if (row_scale && rows_per_scale <= 0) return ACT_EINVAL;
+    if (row_scale && rows_per_scale < 8) return ACT_EUNSUPPORTED;      // the epilogue steps the gate index 4/8 rows at a time
+    if (resid && resid_row_div > 1 && (resid_row_div % 32)) return ACT_EUNSUPPORTED;   // broadcast rows: whole 32-row slabs
     const long long tiles128 = (long long)((M + 127) / 128) * ((N + 127) / 128) * splits;
     if (persistent < 0) persistent = tiles128 > 592 ? 1 : 0;     // > 2 waves of the one-tile-per-CTA kernel
     int BN;

@@ -262,6 +262,11 @@ def run_ours(args):
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
         top = [{"gemm": k, "launches_per_step": c, "us": round(t * 1e3, 1), "tflops": round(f / (t * 1e-3) / 1e12, 1)}
                for k, c, f, t in sorted(rows, key=lambda r: -r[1] * r[3])[:8]]
+        if os.environ.get("ACT_BENCH_GEMM_TABLE"):
+            with open(os.environ["ACT_BENCH_GEMM_TABLE"], "w") as f:
+                json.dump([{"gemm": k, "launches_per_step": c, "us": round(t * 1e3, 2),
+                            "tflops": round(fl / (t * 1e-3) / 1e12, 1)} for k, c, fl, t in
+                           sorted(rows, key=lambda r: -r[1] * r[3])], f, indent=1)
         roof = {"kernel": "gemm_bf16_kernel + gemm_bf16_persistent_kernel (tcgen05/TMA GEMM, all launches of a step)",
                 "bound": "tensor", "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s",
                 "frac": round(ach / peak, 4), "peak_src": pk["src"] + " bf16 sustained", "launches_per_step": n,

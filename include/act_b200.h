@@ -85,7 +85,7 @@ int act_chamfer_backward(const float *xyz1, const float *xyz2, const int32_t *id
  * A / B are bf16, row-major: K-major = [MN, K] with pitch lda/ldb (elements), MN-major = [K, MN].
  * Epilogue, in order, each part optional: + bias[N] (f32);  preact_out (bf16 [M,ldo]) <- value;
  * act_kind 1 = GELU(erf) / 2 = ReLU;  mul_mode 1: *= GELU'(mul_in) / 2: *= (mul_in > 0)  (mul_in bf16 [M,ldm]);
- * *= row_scale[m / rows_per_scale] (nullable f32: the per-sample DropPath gate of timm, models/act.py:88-89);
+ * *= row_scale[m / rows_per_scale] (nullable f32: the per-sample DropPath gate of timm, models/act.py:88-89; rows_per_scale >= 8);
  * + resid[m / resid_row_div, ldr] (f32; may alias out when resid_row_div == 1; resid_row_div = group_size
  * broadcasts a per-group term over the group's points: the hoisted "global feature" half of the mini-PointNet's
  * third conv, models/dvae.py:211-213);  out bf16 (out_fp32 = 0) or f32 (1), pitch ldo.
