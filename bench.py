@@ -59,6 +59,16 @@ def peaks():
     return p
 
 
+def gemm_traffic():
+    """DRAM bytes (read + write) per GEMM launch, averaged over the 256 launches of one step: from the committed ncu
+    capture of the same step (profiles/r1_gemm_traffic.json, `dram__bytes_read.sum + dram__bytes_write.sum`); None
+    when the capture is absent.  A profiler number, reported beside -- never instead of -- the timed ones."""
+    try:
+        return round(json.load(open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")))["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -275,7 +285,7 @@ def run_ours(args):
                 "note": "per-launch durations: each distinct GEMM call of the step replayed 10x from a CUDA graph on its "
                         "real operands, CUDA events; in the timed step the weight-gradient GEMMs additionally overlap "
                         "the dgrad chain on a second stream",
-                "top_launches": top, "traffic": None}
+                "top_launches": top, "traffic": gemm_traffic()}
     if world > 1:
         dist.barrier()
 
