@@ -35,6 +35,9 @@ __device__ __forceinline__ uint32_t lds32(const __nv_bfloat16 *p) { return *rein
 // Asynchronous 16-byte copies (cp.async / LDGSTS, zero-fill form for the padding rows): every thread puts all of its
 // copies for ALL staged matrices in flight before anyone waits (stage_wait), instead of one dependent
 // LDG -> STS round trip after another -- the staging latency, not the MMAs, bounded these kernels.
+__device__ __forceinline__ void cp_async16(__nv_bfloat16 *dst, const __nv_bfloat16 *src, bool ok) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+}
 template <int TP>
 __device__ __forceinline__ void stage_rowmajor(__nv_bfloat16 *dst, const __nv_bfloat16 *src, int ld, int T, int tid) {
 #pragma unroll
@@ -355,6 +358,84 @@ __global__ void __launch_bounds__((TP / 16) * 32) attn_mma_bwd_dkv_kernel(const 
     }
 }
 
+// ------------------------------------------------- forward with a key/value PREFIX (the prompted teacher ViT)
+// VPT-deep (dvae.py:536-576) rebuilds the P prompt rows of the sequence before every block and discards them after it,
+// so only the G token rows ever need queries / outputs; the prompts matter as KEYS and VALUES only.  One CTA per
+// (cloud, head): Q = the G token rows, K / V = [P prompt rows (from kv_p) ; G token rows (from qkv_t)], TQ <= 64 query
+// rows (4 warps x 16), TK <= 128 keys.   qkv_t: bf16 [B*G, 3*H*64] (q | k | v);  kv_p: bf16 [B*P, 2*H*64] (k | v);
+// o: bf16 [B*G, H*64].
+template <int TQ, int TK>
+__global__ void __launch_bounds__((TQ / 16) * 32) attn_prefix_fwd_kernel(const __nv_bfloat16 *__restrict__ qkv_t,
+                                                                         const __nv_bfloat16 *__restrict__ kv_p, int G, int P,
+                                                                         int H, float scale, __nv_bfloat16 *__restrict__ o) {
+    extern __shared__ __align__(16) uint8_t ma_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int pair = blockIdx.x, tid = threadIdx.x;
+    constexpr int NT = (TQ / 16) * 32;
+    pdl_wait();
+    pdl_trigger();
+    const int b = pair / H, h = pair % H;
+    __nv_bfloat16 *sQ = reinterpret_cast<__nv_bfloat16 *>(ma_smem);
+    __nv_bfloat16 *sK = sQ + TQ * MA_PITCH, *sV = sK + TK * MA_PITCH;
+    const int ldt = 3 * H * MA_D, ldp = 2 * H * MA_D;
+    const __nv_bfloat16 *tb = qkv_t + (size_t)b * G * ldt + h * MA_D;
+    const __nv_bfloat16 *pb = kv_p + (size_t)b * P * ldp + h * MA_D;
+    const int T = P + G;
+    // all copies in flight before anyone waits (see stage_rowmajor); rows >= their source's count are zero-filled
+    for (int i = tid; i < TQ * 8; i += NT) {
+        const int r = i >> 3, c = i & 7;
+        const bool ok = r < G;
+        cp_async16(sQ + r * MA_PITCH + c * 8, tb + (size_t)(ok ? r : 0) * ldt + c * 8, ok);
+    }
+    for (int i = tid; i < TK * 8; i += NT) {
+        const int r = i >> 3, c = i & 7;
+        const bool ok = r < T;
+        const __nv_bfloat16 *ksrc = r < P ? pb + (size_t)r * ldp : tb + (size_t)(ok ? r - P : 0) * ldt + H * MA_D;
+        const __nv_bfloat16 *vsrc = r < P ? pb + (size_t)r * ldp + H * MA_D : tb + (size_t)(ok ? r - P : 0) * ldt + 2 * H * MA_D;
+        cp_async16(sK + r * MA_PITCH + c * 8, ksrc + c * 8, ok);
+        cp_async16(sV + r * MA_PITCH + c * 8, vsrc + c * 8, ok);
+    }
+    stage_wait();
+    const float sl2 = scale * 1.4426950408889634f;
+    __nv_bfloat16 *orow = o + (size_t)b * G * (H * MA_D) + h * MA_D;
+    for (int mt = warp; mt * 16 < G; mt += TQ / 16) {
+        uint32_t a[4][4];
+        load_a_frags(a, sQ, mt * 16, g, t);
+        float s[TK / 8][4];
+#pragma unroll
+        for (int nt = 0; nt < TK / 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        mma_rows_t<TK>(s, a, sK, g, t);
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < TK / 8; ++nt) {
+            const int c = nt * 8 + 2 * t;
+            if (c >= T) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+            if (c + 1 >= T) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+            m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+            m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        m0 = quad_max(m0);
+        m1 = quad_max(m1);
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < TK / 8; ++nt) {
+            s[nt][0] = exp2f((s[nt][0] - m0) * sl2); s[nt][1] = exp2f((s[nt][1] - m0) * sl2);
+            s[nt][2] = exp2f((s[nt][2] - m1) * sl2); s[nt][3] = exp2f((s[nt][3] - m1) * sl2);
+            l0 += s[nt][0] + s[nt][1];
+            l1 += s[nt][2] + s[nt][3];
+        }
+        l0 = quad_sum(l0);
+        l1 = quad_sum(l1);
+        uint32_t pa[TK / 16][4];
+        c_to_a<TK>(pa, s);
+        float oacc[8][4];
+#pragma unroll
+        for (int nd = 0; nd < 8; ++nd) oacc[nd][0] = oacc[nd][1] = oacc[nd][2] = oacc[nd][3] = 0.f;
+        mma_kt<TK>(oacc, pa, sV, lane);
+        store_c_rows(orow, H * MA_D, oacc, mt * 16, G, g, t, 1.f / l0, 1.f / l1);
+    }
+}
+
 template <int TP>
 static int launch_fwd(const __nv_bfloat16 *qkv, int B, int T, int H, float scale, __nv_bfloat16 *o, float *lse,
                       cudaStream_t st) {
@@ -379,6 +460,18 @@ static int launch_bwd(const __nv_bfloat16 *qkv, const __nv_bfloat16 *o, const __
     const dim3 grid(npairs), block((TP / 16) * 32);
     ACT_CUDA(launch_k(k1, grid, block, smem1, st, true, qkv, o, dO, lse, T, H, npairs, scale, dqkv, delta));
     ACT_CUDA(launch_k(k2, grid, block, smem2, st, true, qkv, dO, lse, delta, T, H, npairs, scale, dqkv));
+    return ACT_OK;
+}
+
+int attention_prefix_fwd(const void *qkv_t, const void *kv_p, int B, int G, int P, int H, float scale, void *o,
+                         cudaStream_t st) {
+    constexpr int TQ = 64, TK = 128;
+    if (G > TQ || P + G > TK) return ACT_EUNSUPPORTED;
+    constexpr size_t smem = (size_t)(TQ + 2 * TK) * MA_PITCH * 2;
+    auto kern = attn_prefix_fwd_kernel<TQ, TK>;
+    ACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ACT_CUDA(launch_k(kern, dim3(B * H), dim3((TQ / 16) * 32), smem, st, true, reinterpret_cast<const __nv_bfloat16 *>(qkv_t),
+                      reinterpret_cast<const __nv_bfloat16 *>(kv_p), G, P, H, scale, reinterpret_cast<__nv_bfloat16 *>(o)));
     return ACT_OK;
 }
 

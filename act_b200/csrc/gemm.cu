@@ -884,10 +884,14 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
     if (row_scale && rows_per_scale < 8) return ACT_EUNSUPPORTED;      // the epilogue steps the gate index 4/8 rows at a time
     if (resid && resid_row_div > 1 && (resid_row_div % 32)) return ACT_EUNSUPPORTED;   // broadcast rows: whole 32-row slabs
     const long long tiles128 = (long long)((M + 127) / 128) * ((N + 127) / 128) * splits;
-    if (persistent < 0) persistent = tiles128 > 592 ? 1 : 0;     // > 2 waves of the one-tile-per-CTA kernel
+    // persistent: more than two waves of the one-tile-per-CTA kernel (2 CTAs / SM), or more than one wave of long-K
+    // tiles on a tall matrix (the teacher-ViT token GEMMs: the 2-stage 128x192 one-tile variant starves there)
+    if (persistent < 0) persistent = (tiles128 > 592 || (tiles128 > 296 && M >= 8192 && K >= 768)) ? 1 : 0;
     int BN;
     if (persistent) {
-        BN = (block_n == 256 || (block_n == 0 && N % 256 == 0 && !gmode)) ? 256 : 128;
+        // 128 x 256 tiles when there are at least two rounds of them per SM, else 128 x 128 (finer load balance)
+        const long long tiles256 = (long long)((M + 127) / 128) * ((N + 255) / 256) * splits;
+        BN = (block_n == 256 || (block_n == 0 && N % 256 == 0 && !gmode && tiles256 >= 296)) ? 256 : 128;
     } else if (block_n == 64 || block_n == 128 || block_n == 192) {
         BN = block_n;
     } else {

@@ -199,30 +199,35 @@ __global__ void __launch_bounds__(256) gn_rows_apply_kernel(const __nv_bfloat16 
 
 // ---- VPT-deep prompted ViT block entry (visual_embedding_deep_prompt, dvae.py:536-576) ---------------------------
 // The reference rebuilds the sequence before every block: x = cat(dropout(prompt_tokens_i).expand(B), x[:, P:]),
-// pos = cat(prompt_pos_i.expand(B), pos_tok), then blk(x + pos) starts with LayerNorm.  This kernel is that whole
-// prologue fused with norm1: row r = b*T + t reads either the block's prompt token t (broadcast over the batch,
-// dropout drawn in-kernel or injected through `keep`) or the running token row, adds the matching position row,
-// writes the fp32 residual stream xs = x + pos and the bf16 LayerNorm output -- no cat / expand / dropout / copy
-// kernels and no [B,T,D] pos tensor.   xin row of token (b, t >= P) = b*xT + (t - P) + xoff: block 0 reads the
-// [B*G, D] proj_pre output (xT = G, xoff = 0), later blocks the previous block's [B*T, D] output (xT = T, xoff = P).
+// pos = cat(prompt_pos_i.expand(B), pos_tok), then blk(x + pos).  Two consequences this kernel exploits:
+//   * the block's prologue (cat / expand / dropout / pos add) and norm1 fuse into one pass over the rows;
+//   * the block OUTPUT at the P prompt rows is dead -- the next block overwrites those rows with its own prompts and the
+//     final feature keeps only x[:, P:] -- so prompts only ever act as keys / values of the block's attention.  The
+//     residual stream therefore holds the G token rows only, and prompt rows get nothing but their norm1 output:
+//       token row (b, j):  xs[b*G + j] = x[b*G + j] + pos_tok[b*G + j]  (f32),   h_tok[b*G + j] = norm1(xs) (bf16)
+//       prompt row (b, p): h_prm[b*P + p] = norm1(dropout(tok[p]) + ppos[p])      (bf16; feeds the K/V projection only)
+//   dropout: mask injected through `keep` (f32 [B,P,C] of 0/1), or drawn in-kernel from *seed and draw_id.
+// grid over B*(P+G) rows, one warp per row.
 template <int VPL>
-__global__ void __launch_bounds__(256) vit_ln1_kernel(const float *__restrict__ xin, int xT, int xoff,
-                                                      const float *__restrict__ pos_tok,
+__global__ void __launch_bounds__(256) vit_ln1_kernel(const float *__restrict__ x, const float *__restrict__ pos_tok,
                                                       const float *__restrict__ tok, const float *__restrict__ ppos,
                                                       const float *__restrict__ keep,
                                                       const unsigned long long *__restrict__ seed, uint32_t draw_id,
                                                       float p_drop, const float *__restrict__ gamma,
-                                                      const float *__restrict__ beta, float eps, int rows, int T, int P,
-                                                      float *__restrict__ xs, __nv_bfloat16 *__restrict__ h) {
+                                                      const float *__restrict__ beta, float eps, int rows, int G, int P,
+                                                      float *__restrict__ xs, __nv_bfloat16 *__restrict__ h_tok,
+                                                      __nv_bfloat16 *__restrict__ h_prm) {
     constexpr int C = 128 * VPL;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     pdl_wait();
     pdl_trigger();
     if (row >= rows) return;
-    const int b = row / T, t = row - b * T, G = T - P;
+    const int T = P + G;
+    const int b = row / T, t = row - b * T;
     float4 v[VPL];
     float s = 0.f;
+    __nv_bfloat16 *hout;
     if (t < P) {
         const float4 *tr = reinterpret_cast<const float4 *>(tok + (size_t)t * C);
         const float4 *pr = reinterpret_cast<const float4 *>(ppos + (size_t)t * C);
@@ -235,34 +240,37 @@ __global__ void __launch_bounds__(256) vit_ln1_kernel(const float *__restrict__ 
         }
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
-            float4 x = __ldg(tr + lane + 32 * i);
+            float4 xv = __ldg(tr + lane + 32 * i);
             const float4 p = __ldg(pr + lane + 32 * i);
             if (keep) {
                 const float4 k = __ldg(reinterpret_cast<const float4 *>(keep + ((size_t)b * P + t) * C) + lane + 32 * i);
-                x.x *= k.x * inv; x.y *= k.y * inv; x.z *= k.z * inv; x.w *= k.w * inv;
+                xv.x *= k.x * inv; xv.y *= k.y * inv; xv.z *= k.z * inv; xv.w *= k.w * inv;
             } else if (p_drop > 0.f) {
                 const uint4 r = philox4x32_10((uint32_t)(b * P + t), (uint32_t)(lane + 32 * i), 0x44524f50u, draw_id, k0, k1);
-                x.x = u01(r.x) >= p_drop ? x.x * inv : 0.f;
-                x.y = u01(r.y) >= p_drop ? x.y * inv : 0.f;
-                x.z = u01(r.z) >= p_drop ? x.z * inv : 0.f;
-                x.w = u01(r.w) >= p_drop ? x.w * inv : 0.f;
+                xv.x = u01(r.x) >= p_drop ? xv.x * inv : 0.f;
+                xv.y = u01(r.y) >= p_drop ? xv.y * inv : 0.f;
+                xv.z = u01(r.z) >= p_drop ? xv.z * inv : 0.f;
+                xv.w = u01(r.w) >= p_drop ? xv.w * inv : 0.f;
             }
-            v[i] = make_float4(x.x + p.x, x.y + p.y, x.z + p.z, x.w + p.w);
+            v[i] = make_float4(xv.x + p.x, xv.y + p.y, xv.z + p.z, xv.w + p.w);
             s += v[i].x + v[i].y + v[i].z + v[i].w;
         }
+        hout = h_prm + ((size_t)b * P + t) * C;
     } else {
-        const float4 *xr = reinterpret_cast<const float4 *>(xin + ((size_t)b * xT + (t - P) + xoff) * C);
-        const float4 *pr = reinterpret_cast<const float4 *>(pos_tok + ((size_t)b * G + (t - P)) * C);
+        const size_t tr = (size_t)b * G + (t - P);
+        const float4 *xr = reinterpret_cast<const float4 *>(x + tr * C);
+        const float4 *pr = reinterpret_cast<const float4 *>(pos_tok + tr * C);
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
-            const float4 x = xr[lane + 32 * i];
+            const float4 xv = xr[lane + 32 * i];
             const float4 p = __ldg(pr + lane + 32 * i);
-            v[i] = make_float4(x.x + p.x, x.y + p.y, x.z + p.z, x.w + p.w);
+            v[i] = make_float4(xv.x + p.x, xv.y + p.y, xv.z + p.z, xv.w + p.w);
             s += v[i].x + v[i].y + v[i].z + v[i].w;
         }
-    }
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) reinterpret_cast<float4 *>(xs + (size_t)row * C)[lane + 32 * i] = v[i];
+        for (int i = 0; i < VPL; ++i) reinterpret_cast<float4 *>(xs + tr * C)[lane + 32 * i] = v[i];
+        hout = h_tok + tr * C;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = s * (1.f / C);
@@ -284,28 +292,28 @@ __global__ void __launch_bounds__(256) vit_ln1_kernel(const float *__restrict__ 
             __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + be.x, (v[i].y - mean) * rstd * g.y + be.y);
         *reinterpret_cast<__nv_bfloat162 *>(&pk.y) =
             __floats2bfloat162_rn((v[i].z - mean) * rstd * g.z + be.z, (v[i].w - mean) * rstd * g.w + be.w);
-        reinterpret_cast<uint2 *>(h + (size_t)row * C)[lane + 32 * i] = pk;
+        reinterpret_cast<uint2 *>(hout)[lane + 32 * i] = pk;
     }
 }
 
 }  // namespace act
 
-extern "C" int act_vit_ln1_fwd(const float *xin, int xT, int xoff, const float *pos_tok, const float *tok,
-                               const float *ppos, const float *keep, const unsigned long long *seed, int draw_id,
-                               float p_drop, const float *gamma, const float *beta, float eps, int B, int T, int P,
-                               int C, float *xs, void *h_bf16, void *stream) {
+extern "C" int act_vit_ln1_fwd(const float *x, const float *pos_tok, const float *tok, const float *ppos, const float *keep,
+                               const unsigned long long *seed, int draw_id, float p_drop, const float *gamma,
+                               const float *beta, float eps, int B, int G, int P, int C, float *xs, void *h_tok_bf16,
+                               void *h_prm_bf16, void *stream) {
     using namespace act;
-    if (!xin || !pos_tok || !tok || !ppos || !gamma || !beta || !xs || !h_bf16) return ACT_EINVAL;
-    if (B <= 0 || T <= 0 || P < 0 || P > T || xT < T - P || xoff < 0) return ACT_EINVAL;
-    if (p_drop < 0.f || p_drop >= 1.f || (p_drop > 0.f && !keep && !seed)) return ACT_EINVAL;
+    if (!x || !pos_tok || !gamma || !beta || !xs || !h_tok_bf16) return ACT_EINVAL;
+    if (B <= 0 || G <= 0 || P < 0 || (P > 0 && (!tok || !ppos || !h_prm_bf16))) return ACT_EINVAL;
+    if (p_drop < 0.f || p_drop >= 1.f || (P > 0 && p_drop > 0.f && !keep && !seed)) return ACT_EINVAL;
     if (C % 128 || C > 1024) return ACT_EUNSUPPORTED;
-    const int rows = B * T;
+    const int rows = B * (G + P);
     cudaStream_t st = (cudaStream_t)stream;
 #define VLN_CASE(V)                                                                                                    \
     case V:                                                                                                            \
-        ACT_CUDA(launch_k(vit_ln1_kernel<V>, dim3((rows + 7) / 8), dim3(256), 0, st, true, xin, xT, xoff, pos_tok, tok,  \
-                          ppos, keep, seed, (uint32_t)draw_id, p_drop, gamma, beta, eps, rows, T, P, xs,               \
-                          reinterpret_cast<__nv_bfloat16 *>(h_bf16)));                                                 \
+        ACT_CUDA(launch_k(vit_ln1_kernel<V>, dim3((rows + 7) / 8), dim3(256), 0, st, true, x, pos_tok, tok, ppos, keep,  \
+                          seed, (uint32_t)draw_id, p_drop, gamma, beta, eps, rows, G, P, xs,                           \
+                          reinterpret_cast<__nv_bfloat16 *>(h_tok_bf16), reinterpret_cast<__nv_bfloat16 *>(h_prm_bf16))); \
         break;
     switch (C / 128) {
         VLN_CASE(1) VLN_CASE(2) VLN_CASE(3) VLN_CASE(4) VLN_CASE(6) VLN_CASE(8)

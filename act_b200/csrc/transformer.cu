@@ -595,6 +595,19 @@ extern "C" int act_attention_fwd(const void *qkv, int B, int T, int H, int head_
     return ACT_OK;
 }
 
+namespace act {
+int attention_prefix_fwd(const void *qkv_t, const void *kv_p, int B, int G, int P, int H, float scale, void *o,
+                         cudaStream_t st);
+}
+extern "C" int act_attention_prefix_fwd(const void *qkv_t, const void *kv_p, int B, int G, int P, int H, int head_dim,
+                                        float scale, void *o, void *stream) {
+    using namespace act;
+    if (!qkv_t || !kv_p || !o || B < 0 || G <= 0 || P < 0 || H <= 0) return ACT_EINVAL;
+    if (head_dim != AT_D) return ACT_EUNSUPPORTED;
+    if (B == 0) return ACT_OK;
+    return attention_prefix_fwd(qkv_t, kv_p, B, G, P, H, scale, o, (cudaStream_t)stream);
+}
+
 extern "C" int act_attention_bwd(const void *qkv, const void *o, const void *dO, const float *lse, int B, int T, int H,
                                  int head_dim, float scale, void *dqkv, float *delta, void *stream) {
     using namespace act;

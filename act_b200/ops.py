@@ -411,14 +411,24 @@ def gn_rows(x, gamma, beta, B, R, eps, slope, noise=None, seed=None):
     return label
 
 
-def vit_ln1_fwd(xin, xT, xoff, pos_tok, tok, ppos, gamma, beta, eps, B, T, P, keep=None, seed=None, draw_id=0,
-                p_drop=0.0):
-    """Entry of a VPT-deep prompted ViT block: (prompt rows | token rows) + positions -> (xs f32 [B*T,C] residual
-    stream, h bf16 [B*T,C] = norm1(xs)).  See include/act_b200.h: act_vit_ln1_fwd."""
+def vit_ln1_fwd(x, pos_tok, tok, ppos, gamma, beta, eps, B, G, P, keep=None, seed=None, draw_id=0, p_drop=0.0):
+    """Entry of a VPT-deep prompted ViT block (include/act_b200.h: act_vit_ln1_fwd) ->
+    (xs f32 [B*G,C] token residual stream, h_tok bf16 [B*G,C], h_prm bf16 [B*P,C])."""
     C = pos_tok.shape[-1]
-    xs = torch.empty(B * T, C, dtype=torch.float32, device=pos_tok.device)
-    h = torch.empty(B * T, C, dtype=torch.bfloat16, device=pos_tok.device)
-    _lib.call("act_vit_ln1_fwd", xin, xT, xoff, pos_tok, tok, ppos, keep, seed, draw_id, float(p_drop), gamma, beta,
-              float(eps), B, T, P, C, xs, _p(h))
+    dev = pos_tok.device
+    xs = torch.empty(B * G, C, dtype=torch.float32, device=dev)
+    h_tok = torch.empty(B * G, C, dtype=torch.bfloat16, device=dev)
+    h_prm = torch.empty(B * P, C, dtype=torch.bfloat16, device=dev)
+    _lib.call("act_vit_ln1_fwd", x, pos_tok, tok, ppos, keep, seed, draw_id, float(p_drop), gamma, beta, float(eps), B, G,
+              P, C, xs, _p(h_tok), _p(h_prm))
     _count()
-    return xs, h
+    return xs, h_tok, h_prm
+
+
+def attention_prefix_fwd(qkv_t, kv_p, B, G, P, H, scale):
+    """Queries = the G token rows of qkv_t [B*G, 3*H*64]; keys/values = P prompt rows of kv_p [B*P, 2*H*64] + the
+    token rows -> o bf16 [B*G, H*64]."""
+    o = torch.empty(B * G, H * 64, dtype=torch.bfloat16, device=qkv_t.device)
+    _lib.call("act_attention_prefix_fwd", qkv_t, kv_p, B, G, P, H, 64, float(scale), o)
+    _count()
+    return o

@@ -10,7 +10,7 @@ deep_prompt_tokens/pos), so a reference teacher checkpoint loads unchanged; only
     mini-PointNet (train-mode BatchNorm, as the reference runs it)  -> layers.PointNetEncoderFn
     DGCNN x2 (dvae.py:26-117)                                        -> one tcgen05 GEMM + one fused kernel per layer
     hard gumbel-softmax + codebook (dvae.py:587-588)                 -> fused GroupNorm/LeakyReLU/+noise/arg-max, gather
-    VPT-deep prompted ViT-B, 12 blocks, T = 64 prompts + 64 tokens   -> tcgen05 GEMMs, LayerNorm, mma.sync attention
+    VPT-deep prompted ViT-B, 12 blocks, 64 prompts (keys/values only) + 64 tokens -> tcgen05 GEMMs, LayerNorm, mma.sync attention
 
 The pretrained ViT / dVAE weights are not obtainable offline; the module is exercised with deterministic weights.
 """
@@ -166,18 +166,20 @@ class ACTPromptedDiscreteVAEwithVIT(nn.Module):
             return ops.gn_rows(h5, c["g5"], c["b5"], B, G, m.layer5[1].eps, 0.2)
         return ops.gn_rows(h5, c["g5"], c["b5"], B, G, m.layer5[1].eps, 0.2, noise=noise, seed=seed)
 
-    def _vit_block(self, xin, xT, xoff, pos_tok, tok, ppos, blk, w, B, T, keep, seed, draw_id):
-        """One prompted block: fused (prompt rebuild + pos add + norm1) -> qkv -> attention -> proj(+resid) -> norm2 ->
-        fc1(GELU) -> fc2(+resid).  Returns the block output f32 [B*T, D] (its prompt rows are dead: the next block
-        overwrites them with its own prompts, dvae.py:556-566)."""
+    def _vit_block(self, x, pos_tok, tok, ppos, blk, w, B, G, keep, seed, draw_id):
+        """One prompted block on the G token rows (the prompt rows' block output is dead in the reference -- the next
+        block overwrites them, dvae.py:556-566 -- so prompts only supply keys / values): fused (prompt rebuild + pos add +
+        norm1) -> q,k,v of the tokens / k,v of the prompts -> prefix attention -> proj(+resid) -> norm2 -> fc1(GELU) ->
+        fc2(+resid).  x, returned value: f32 [B*G, D]."""
         H = blk.attn.num_heads
         eps = blk.norm1.eps
-        P = self.num_prompt_token
+        P, D = self.num_prompt_token, self.visual_embed_dim
         p_drop = 0.1 if (self.training or keep is not None) else 0.0
-        xs, h1 = ops.vit_ln1_fwd(xin, xT, xoff, pos_tok, tok, ppos, blk.norm1.weight, blk.norm1.bias, eps, B, T, P,
-                                 keep=keep, seed=seed, draw_id=draw_id, p_drop=p_drop)
-        qkv = ops.gemm(h1, w["qkv"], bias=blk.attn.qkv.bias)
-        o, _ = ops.attention_fwd(qkv, B, T, H, (xs.shape[1] // H) ** -0.5)
+        xs, h_tok, h_prm = ops.vit_ln1_fwd(x, pos_tok, tok, ppos, blk.norm1.weight, blk.norm1.bias, eps, B, G, P,
+                                           keep=keep, seed=seed, draw_id=draw_id, p_drop=p_drop)
+        qkv_t = ops.gemm(h_tok, w["qkv"], bias=blk.attn.qkv.bias)
+        kv_p = ops.gemm(h_prm, w["qkv"][D:], bias=blk.attn.qkv.bias[D:])
+        o = ops.attention_prefix_fwd(qkv_t, kv_p, B, G, P, H, (D // H) ** -0.5)
         xmid = ops.gemm(o, w["proj"], bias=blk.attn.proj.bias, resid=xs, out_dtype=torch.float32)
         h2, _, _, _ = ops.layernorm_fwd(xmid, blk.norm2.weight, blk.norm2.bias, eps, save_stats=False)
         a = ops.gemm(h2, w["fc1"], bias=blk.mlp.fc1.bias, act=ops.ACT_GELU)
@@ -185,25 +187,22 @@ class ACTPromptedDiscreteVAEwithVIT(nn.Module):
 
     def _visual(self, c, sampled, center, B, G, keeps, seed=None):
         """visual_embedding_deep_prompt (dvae.py:536-576)."""
-        D, P = self.visual_embed_dim, self.num_prompt_token
-        T = P + G
         pe = self.visual_pos_embed
         pos_tok = ops.gemm(F.gelu(F.linear(center.reshape(B * G, 3), pe[0].weight, pe[0].bias)).to(torch.bfloat16),
                            c["pos2_w"], bias=pe[2].bias, out_dtype=torch.float32)
         x = ops.gemm(sampled.to(torch.bfloat16), c["pre_w"], bias=self.proj_pre.bias, out_dtype=torch.float32)
-        xT, xoff = G, 0
         blocks = self.visual_embed[0]
         for i, blk in enumerate(blocks):
             if i == 0:
                 tok, ppos = self.visual_prompt_token[0], self.visual_prompt_pos[0]
             elif i <= self.deep_prompt_tokens.shape[0]:
                 tok, ppos = self.deep_prompt_tokens[i - 1], self.deep_prompt_pos[i - 1]
+            else:
+                raise NotImplementedError("act_b200 teacher: one deep prompt per block after the first (the shipped config)")
             keep = None if keeps is None else keeps[i].float().contiguous()
-            x = self._vit_block(x, xT, xoff, pos_tok, tok.detach(), ppos.detach(), blk, c["blocks"][i], B, T, keep, seed, i)
-            xT, xoff = T, P
+            x = self._vit_block(x, pos_tok, tok.detach(), ppos.detach(), blk, c["blocks"][i], B, G, keep, seed, i)
         norm = self.visual_embed[1]
-        y, _, _, _ = ops.layernorm_fwd(x.view(B, T, D)[:, P:].reshape(B * G, D), norm.weight, norm.bias, norm.eps,
-                                       save_stats=False)
+        y, _, _, _ = ops.layernorm_fwd(x, norm.weight, norm.bias, norm.eps, save_stats=False)
         return ops.gemm(y, c["post_w"], bias=self.proj_post.bias, out_dtype=torch.float32)  # [BG, tokens_dims]
 
     @torch.no_grad()

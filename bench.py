@@ -308,7 +308,7 @@ def run_ours(args):
                 "clocks": clocks, "roofline": roof}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -380,7 +380,28 @@ def run_reference(args):
                                        f"batch-128 workload), oracle restatement of the reference path on all host "
                                        f"threads; the reference's own native ops are CUDA-only"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """stdout carries exactly ONE JSON line: anything else written to fd 1 (NCCL prints its version banner there from
+    C code) is sent to stderr instead; emit() writes the line to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -397,6 +418,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    _guard_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

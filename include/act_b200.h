@@ -211,13 +211,20 @@ int act_gn_rows(const void *x_bf16, const float *gamma, const float *beta, int B
 
 /* Entry of one VPT-deep prompted ViT block (visual_embedding_deep_prompt, /root/reference/models/dvae.py:536-576):
  * the reference's per-block  x = cat(dropout(prompt_i).expand(B), x[:, P:]);  pos = cat(prompt_pos_i.expand(B), pos);
- * blk(x + pos) -> norm1  fused into one pass.  Row r = b*T + t:  t < P: x = tok[t,:] (dropout p_drop: mask injected
- * through keep f32 [B,P,C] of 0/1, or drawn in-kernel from *seed (device memory) and draw_id), pos = ppos[t,:];
- * t >= P: x = xin[b*xT + (t-P) + xoff, :], pos = pos_tok[b*(T-P) + (t-P), :].  Writes xs f32 [B*T, C] = x + pos (the
- * residual stream) and h bf16 [B*T, C] = LayerNorm(xs; gamma, beta, eps). */
-int act_vit_ln1_fwd(const float *xin, int xT, int xoff, const float *pos_tok, const float *tok, const float *ppos,
-                    const float *keep, const unsigned long long *seed, int draw_id, float p_drop, const float *gamma,
-                    const float *beta, float eps, int B, int T, int P, int C, float *xs, void *h_bf16, void *stream);
+ * blk(x + pos) -> norm1  fused into one pass.  The block output at the P prompt rows is dead in the reference (the next
+ * block overwrites them, the final feature keeps x[:, P:]), so the residual stream holds the G token rows only:
+ *   x, pos_tok f32 [B*G, C] -> xs f32 [B*G, C] = x + pos_tok,  h_tok bf16 [B*G, C] = LayerNorm(xs);
+ *   tok, ppos f32 [P, C]    -> h_prm bf16 [B*P, C] = LayerNorm(dropout(tok[p]) + ppos[p])   (per cloud: the dropout mask
+ *   is per sample; injected through keep f32 [B,P,C] of 0/1, or drawn in-kernel from *seed (device memory) and draw_id). */
+int act_vit_ln1_fwd(const float *x, const float *pos_tok, const float *tok, const float *ppos, const float *keep,
+                    const unsigned long long *seed, int draw_id, float p_drop, const float *gamma, const float *beta,
+                    float eps, int B, int G, int P, int C, float *xs, void *h_tok_bf16, void *h_prm_bf16, void *stream);
+
+/* softmax(q k^T * scale) v with a key/value PREFIX: queries are the G token rows of qkv_t bf16 [B*G, 3*H*64] (q | k | v),
+ * keys / values are the P prompt rows of kv_p bf16 [B*P, 2*H*64] (k | v) followed by the token rows; o bf16 [B*G, H*64].
+ * (The prompted ViT block: prompts act as keys / values only.)  G <= 64, P + G <= 128, head_dim 64. */
+int act_attention_prefix_fwd(const void *qkv_t, const void *kv_p, int B, int G, int P, int H, int head_dim, float scale,
+                             void *o, void *stream);
 
 /* ---- Loss and optimizer ------------------------------------------------------------------------------ */
 

@@ -26,7 +26,13 @@ out32 = torch.empty(M, D, device=dev)
 outb = torch.empty(M, 4 * D, device=dev, dtype=torch.bfloat16)
 outq = torch.empty(M, 3 * D, device=dev, dtype=torch.bfloat16)
 cases = {
-    "vit_ln1_fused(prompt+pos+norm1)": (lambda: ops.vit_ln1_fwd(x, T, P, pos_tok, tok, ppos, g, be, 1e-6, B, T, P, seed=seed, draw_id=1, p_drop=0.1), None),
+    "vit_ln1_fused(prompt+pos+norm1)": (lambda: ops.vit_ln1_fwd(x[:B * 64], pos_tok, tok, ppos, g, be, 1e-6, B, 64, P, seed=seed, draw_id=1, p_drop=0.1), None),
+    "vit_attn_prefix 64q x 128kv H=12": (lambda: ops.attention_prefix_fwd(qkv[:B * 64], qkv[B * 64:, :2 * D].contiguous(), B, 64, P, H, 0.125), 4.0 * B * H * 64 * T * 64),
+    "vit_qkv_tok 8192x2304x768+bias": (lambda: ops.gemm(h[:B * 64], wqkv, bias=b3), 2.0 * B * 64 * 3 * D * D),
+    "vit_kv_prm 8192x1536x768+bias": (lambda: ops.gemm(h[:B * 64], wqkv[D:], bias=b3[D:]), 2.0 * B * 64 * 2 * D * D),
+    "vit_proj 8192x768x768+bias+resid": (lambda: ops.gemm(o[:B * 64], wproj, bias=b1, resid=x[:B * 64], out=out32[:B * 64]), 2.0 * B * 64 * D * D),
+    "vit_fc1 8192x3072x768+bias+gelu": (lambda: ops.gemm(h[:B * 64], wfc1, bias=b4, act=ops.ACT_GELU, out=outb[:B * 64]), 2.0 * B * 64 * 4 * D * D),
+    "vit_fc2 8192x768x3072+bias+resid": (lambda: ops.gemm(a4[:B * 64], wfc2, bias=b1, resid=x[:B * 64], out=out32[:B * 64]), 2.0 * B * 64 * 4 * D * D),
     "vit_qkv 16384x2304x768+bias": (lambda: ops.gemm(h, wqkv, bias=b3, out=outq), 2.0 * M * 3 * D * D),
     "vit_attn_fwd T=128 H=12": (lambda: ops.attention_fwd(qkv, B, T, H, 0.125), 4.0 * B * H * T * T * 64),
     "vit_proj 16384x768x768+bias+resid": (lambda: ops.gemm(o, wproj, bias=b1, resid=x, out=out32), 2.0 * M * D * D),

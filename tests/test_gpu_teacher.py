@@ -130,27 +130,50 @@ def test_in_kernel_gumbel_and_prompt_dropout_draws():
     rest = rest[rest != 5]
     assert rest.unique().numel() > 0.9 * rest.numel()                        # the other half spreads over 8191 classes
     assert 0 <= int(rest.min()) and int(rest.max()) < C
-    # prompt dropout: tok = 1, ppos = 0 -> prompt rows of xs are keep / 0.9
-    Bv, T, P, D = 16, 128, 64, 768
-    xin = torch.randn(Bv * 64, D, device="cuda")
-    pos_tok = torch.randn(Bv * 64, D, device="cuda")
-    tok, ppos = torch.ones(P, D, device="cuda"), torch.zeros(P, D, device="cuda")
+    # prompt dropout: ppos = 0, gamma = 1, beta = 0 -> h_prm = LayerNorm(keep * tok / 0.9): a dropped element of a row is
+    # the row's minimum (tok > 0), so the mask is recoverable from the output
+    Bv, G, P, D = 16, 64, 64, 768
+    x = torch.randn(Bv * G, D, device="cuda")
+    pos_tok = torch.randn(Bv * G, D, device="cuda")
+    tok, ppos = torch.rand(P, D, device="cuda") + 0.5, torch.zeros(P, D, device="cuda")
     g, b = torch.ones(D, device="cuda"), torch.zeros(D, device="cuda")
-    xs, hh = ops.vit_ln1_fwd(xin, 64, 0, pos_tok, tok, ppos, g, b, 1e-6, Bv, T, P, seed=s1, draw_id=3, p_drop=0.1)
-    xs = xs.view(Bv, T, D)
-    pr = xs[:, :P]
-    assert ((pr == 0) | ((pr - 1 / 0.9).abs() < 1e-6)).all()
-    keep = (pr != 0).float().mean().item()
-    assert abs(keep - 0.9) < 5e-3, keep
-    assert (pr != 0).float().mean((1, 2)).std().item() < 5e-3               # every cloud gets its own mask
-    assert not torch.equal(pr[0], pr[1])
-    torch.testing.assert_close(xs[:, P:].reshape(Bv * 64, D), xin + pos_tok)
-    want_h = torch.nn.functional.layer_norm(xs, (D,), g, b, 1e-6)
-    assert rel(hh.view(Bv, T, D), want_h) < 4e-3
-    xs2, _ = ops.vit_ln1_fwd(xin, 64, 0, pos_tok, tok, ppos, g, b, 1e-6, Bv, T, P, seed=s1, draw_id=4, p_drop=0.1)
-    assert not torch.equal(xs2.view(Bv, T, D)[:, :P], pr)                    # another block, another mask
-    # later blocks read the previous block's [B*T, D] output, skipping its (dead) prompt rows
-    prev = torch.randn(Bv * T, D, device="cuda")
-    xs3, _ = ops.vit_ln1_fwd(prev, T, P, pos_tok, tok, ppos, g, b, 1e-6, Bv, T, P, p_drop=0.0)
-    torch.testing.assert_close(xs3.view(Bv, T, D)[:, P:], prev.view(Bv, T, D)[:, P:] + pos_tok.view(Bv, 64, D))
-    assert (xs3.view(Bv, T, D)[:, :P] == 1).all()
+    xs, h_tok, h_prm = ops.vit_ln1_fwd(x, pos_tok, tok, ppos, g, b, 1e-6, Bv, G, P, seed=s1, draw_id=3, p_drop=0.1)
+    torch.testing.assert_close(xs, x + pos_tok)
+    assert rel(h_tok, torch.nn.functional.layer_norm(xs, (D,), g, b, 1e-6)) < 4e-3
+    hp = h_prm.float().view(Bv, P, D)
+    dropped = hp <= hp.min(-1, keepdim=True)[0] + 1e-3
+    keep = (~dropped).float()
+    rate = keep.mean().item()
+    assert abs(rate - 0.9) < 5e-3, rate
+    assert keep.mean((1, 2)).std().item() < 5e-3 and not torch.equal(keep[0], keep[1])   # every cloud its own mask
+    want = torch.nn.functional.layer_norm(keep * tok / 0.9, (D,), g, b, 1e-6)
+    assert rel(hp, want) < 4e-3                                           # the recovered mask reproduces the output
+    _, _, h2 = ops.vit_ln1_fwd(x, pos_tok, tok, ppos, g, b, 1e-6, Bv, G, P, seed=s1, draw_id=4, p_drop=0.1)
+    assert not torch.equal(h2, h_prm)                                     # another block, another mask
+    # injected mask (the parity path) and no dropout (eval mode)
+    kin = (torch.rand(Bv, P, D, device="cuda") >= 0.1).float()
+    _, _, h3 = ops.vit_ln1_fwd(x, pos_tok, tok, ppos, g, b, 1e-6, Bv, G, P, keep=kin, p_drop=0.1)
+    assert rel(h3.view(Bv, P, D), torch.nn.functional.layer_norm(kin * tok / 0.9, (D,), g, b, 1e-6)) < 4e-3
+    _, _, h4 = ops.vit_ln1_fwd(x, pos_tok, tok, ppos, g, b, 1e-6, Bv, G, P, p_drop=0.0)
+    assert rel(h4.view(Bv, P, D), torch.nn.functional.layer_norm(tok, (D,), g, b, 1e-6).expand(Bv, -1, -1)) < 4e-3
+
+
+def test_prefix_attention_equals_full_attention_on_token_rows():
+    """Prompts act as keys / values only: the token rows of full attention over [prompts ; tokens] == prefix attention."""
+    torch.manual_seed(3)
+    B, G, P, H = 5, 64, 64, 12
+    C = H * 64
+    qkv_t = (torch.randn(B * G, 3 * C, device="cuda") * 0.7).bfloat16()
+    kv_p = (torch.randn(B * P, 2 * C, device="cuda") * 0.7).bfloat16()
+    q = qkv_t.float().view(B, G, 3, H, 64)[:, :, 0].permute(0, 2, 1, 3)                      # B H G 64
+    k = torch.cat([kv_p.float().view(B, P, 2, H, 64)[:, :, 0], qkv_t.float().view(B, G, 3, H, 64)[:, :, 1]], 1).permute(0, 2, 1, 3)
+    v = torch.cat([kv_p.float().view(B, P, 2, H, 64)[:, :, 1], qkv_t.float().view(B, G, 3, H, 64)[:, :, 2]], 1).permute(0, 2, 1, 3)
+    want = ((q @ k.transpose(-2, -1) * 0.125).softmax(-1) @ v).transpose(1, 2).reshape(B * G, C)
+    got = ops.attention_prefix_fwd(qkv_t, kv_p, B, G, P, H, 0.125)
+    assert rel(got, want) < 4e-3
+    # and against the square kernel on the assembled [prompts ; tokens] sequence
+    full = torch.zeros(B, P + G, 3 * C, device="cuda", dtype=torch.bfloat16)
+    full[:, :P, C:] = kv_p.view(B, P, 2 * C)
+    full[:, P:] = qkv_t.view(B, G, 3 * C)
+    o_full, _ = ops.attention_fwd(full.view(B * (P + G), 3 * C), B, P + G, H, 0.125)
+    assert rel(got, o_full.view(B, P + G, C)[:, P:].reshape(B * G, C)) < 2e-3
