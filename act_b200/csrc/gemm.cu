@@ -40,7 +40,11 @@ struct GemmEpi {
     const __nv_bfloat16 *mul_in;  // nullable, bf16 [M, ldm]
     const float *row_scale;       // nullable, f32 [ceil(M / rows_per_scale)]: DropPath gate of the branch
     int rows_per_scale;
-    int resid_row_div;            // residual row = m / resid_row_div (broadcast of a per-group term over its points)
+    int resid_row_div;            // residual row = m / resid_row_div (1 here: broadcast rows travel as slab_bias)
+    // per-group broadcast term (resid with resid_row_div % 32 == 0: every 32-row epilogue slab reads ONE row of it):
+    // handled like a bias vector whose base depends on the slab -- one vector per lane per chunk, no operand registers
+    const float *slab_bias;
+    int slab_div, ld_slab;
     // fused max over each group of 32 consecutive rows (= one epilogue warp): torch.max(feature, dim=2) of the
     // mini-PointNet taken on the fp32 accumulators; any of the three outputs may be null.  [M/32, ldg]
     float *gmax_f32;
@@ -235,13 +239,7 @@ __device__ __forceinline__ void epi_prefetch_cw(const GemmEpi &epi, EpiPre &pre,
             }
         }
     } else if (TR::has_resid(epi)) {
-        if (epi.resid_row_div != 1) {
-            // per-group broadcast row (resid_row_div % 32 == 0, host-checked): the whole slab reads ONE residual row,
-            // which never aliases out -> read-only path, one address
-            const uint4 *rp = reinterpret_cast<const uint4 *>(epi.resid + (size_t)(row0 / epi.resid_row_div) * epi.ldr + col);
-#pragma unroll
-            for (int q = 0; q < CW / 4; ++q) pre.r[q] = __ldg(rp + q);
-        } else {
+        {
             const float *rp = epi.resid + (size_t)(row0 + rq) * epi.ldr + col;
             const size_t step = (size_t)RPI * epi.ldr;
 #pragma unroll
@@ -281,7 +279,6 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
     const int act_kind = G ? epi.act : (MODE == E_GELU ? 1 : 0);
     const int mul_mode = G ? epi.mul_mode : (MODE == E_MULGELU ? 1 : (MODE == E_MULRELU ? 2 : 0));
     const bool has_resid = TR::has_resid(epi);
-    const bool bcast_resid = has_resid && epi.resid_row_div != 1;
     const bool has_rscale = (G || MODE == E_RESID) ? (epi.row_scale != nullptr) : false;
     const bool has_preact = (G || MODE == E_GELU) ? (epi.preact_out != nullptr) : false;
     const bool atomic = G ? (epi.atomic != 0) : (MODE == E_ATOMIC);
@@ -292,12 +289,25 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
     const bool col_ok = FULL || col < N;              // N % 8 == 0 (host): a lane's CW columns are all in or all out
     const int rfirst = row0 + rq;
     const int rows_left = FULL ? 32 : (col_ok ? M - rfirst : 0);    // iteration i stores iff i * RPI < rows_left
+    const bool has_slab = (MODE == E_PLAIN || MODE == E_GENERIC) ? (epi.slab_bias != nullptr) : false;
     float bias[CW];
-    if (has_bias) {
+    if (has_bias || has_slab) {
 #pragma unroll
-        for (int q = 0; q < CW / 4; ++q) {
-            const float4 b4 = col_ok ? __ldg(reinterpret_cast<const float4 *>(epi.bias + col) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            bias[4 * q] = b4.x; bias[4 * q + 1] = b4.y; bias[4 * q + 2] = b4.z; bias[4 * q + 3] = b4.w;
+        for (int j = 0; j < CW; ++j) bias[j] = 0.f;
+        if (has_bias && col_ok) {
+#pragma unroll
+            for (int q = 0; q < CW / 4; ++q) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(epi.bias + col) + q);
+                bias[4 * q] = b4.x; bias[4 * q + 1] = b4.y; bias[4 * q + 2] = b4.z; bias[4 * q + 3] = b4.w;
+            }
+        }
+        if (has_slab && col_ok) {
+            const float4 *sp = reinterpret_cast<const float4 *>(epi.slab_bias + (size_t)(row0 / epi.slab_div) * epi.ld_slab + col);
+#pragma unroll
+            for (int q = 0; q < CW / 4; ++q) {
+                const float4 b4 = __ldg(sp + q);
+                bias[4 * q] += b4.x; bias[4 * q + 1] += b4.y; bias[4 * q + 2] += b4.z; bias[4 * q + 3] += b4.w;
+            }
         }
     }
     float rs[NIT];
@@ -313,6 +323,7 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
     }
     float best[CW];
     int barg[CW];
+    const bool want_arg = gmode && epi.garg != nullptr;      // the arg-max costs a second shuffle per value: only on demand
     if (gmode) {
 #pragma unroll
         for (int j = 0; j < CW; ++j) { best[j] = -INFINITY; barg[j] = 0; }
@@ -334,16 +345,21 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
             const float4 x = lds128(st4 + (i * RPI * 8 + ((cq * (CW / 4) + q) ^ (r & 7))) * 16);
             f[4 * q] = x.x; f[4 * q + 1] = x.y; f[4 * q + 2] = x.z; f[4 * q + 3] = x.w;
         }
-        if (has_bias) {
+        if (has_bias || has_slab) {
 #pragma unroll
             for (int j = 0; j < CW; ++j) f[j] += bias[j];
         }
         if (gmode) {
             // max over the slab's 32 rows of (acc + bias) per column; the first row wins ties.  M % 32 == 0 in this
             // mode (host-checked), so every row of a live slab is in range.
+            if (want_arg) {
 #pragma unroll
-            for (int j = 0; j < CW; ++j)
-                if (f[j] > best[j]) { best[j] = f[j]; barg[j] = r; }
+                for (int j = 0; j < CW; ++j)
+                    if (f[j] > best[j]) { best[j] = f[j]; barg[j] = r; }
+            } else {
+#pragma unroll
+                for (int j = 0; j < CW; ++j) best[j] = fmaxf(best[j], f[j]);
+            }
         }
         if (i * RPI < rows_left && has_out) {
             if (has_preact) {
@@ -386,25 +402,15 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
             }
             if (has_resid) {
                 if (!mul_mode) {
-                    // two branches with STATIC register indices (a selected index would push `pre` to local memory)
-                    if (bcast_resid) {
 #pragma unroll
-                        for (int q = 0; q < CW / 4; ++q) {
-                            const uint4 r4 = pre.r[q];
-                            f[4 * q] += __uint_as_float(r4.x); f[4 * q + 1] += __uint_as_float(r4.y);
-                            f[4 * q + 2] += __uint_as_float(r4.z); f[4 * q + 3] += __uint_as_float(r4.w);
-                        }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < CW / 4; ++q) {
-                            const uint4 r4 = pre.r[i * (CW / 4) + q];
-                            f[4 * q] += __uint_as_float(r4.x); f[4 * q + 1] += __uint_as_float(r4.y);
-                            f[4 * q + 2] += __uint_as_float(r4.z); f[4 * q + 3] += __uint_as_float(r4.w);
-                        }
+                    for (int q = 0; q < CW / 4; ++q) {
+                        const uint4 r4 = pre.r[i * (CW / 4) + q];
+                        f[4 * q] += __uint_as_float(r4.x); f[4 * q + 1] += __uint_as_float(r4.y);
+                        f[4 * q + 2] += __uint_as_float(r4.z); f[4 * q + 3] += __uint_as_float(r4.w);
                     }
                 } else {      // the rare resid + mul_in combination (generic mode): the registers hold mul_in
                     const float4 *rp = reinterpret_cast<const float4 *>(
-                        epi.resid + (size_t)((rfirst + i * RPI) / epi.resid_row_div) * epi.ldr + col);
+                        epi.resid + (size_t)(rfirst + i * RPI) * epi.ldr + col);
 #pragma unroll
                     for (int q = 0; q < CW / 4; ++q) {
                         const float4 r4 = rp[q];
@@ -436,8 +442,12 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
 #pragma unroll
             for (int j = 0; j < CW; ++j) {
                 const float ob = __shfl_xor_sync(0xffffffffu, best[j], off);
-                const int oa = __shfl_xor_sync(0xffffffffu, barg[j], off);
-                if (ob > best[j] || (ob == best[j] && oa < barg[j])) { best[j] = ob; barg[j] = oa; }
+                if (want_arg) {
+                    const int oa = __shfl_xor_sync(0xffffffffu, barg[j], off);
+                    if (ob > best[j] || (ob == best[j] && oa < barg[j])) { best[j] = ob; barg[j] = oa; }
+                } else {
+                    best[j] = fmaxf(best[j], ob);
+                }
             }
         }
         if (rq == 0 && col_ok) {
@@ -907,7 +917,13 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
     epi.ldo = ldo; epi.ldr = ldr; epi.ldm = ldm; epi.out_fp32 = out_fp32; epi.atomic = splits > 1 ? 1 : 0;
     epi.act = act_kind; epi.mul_mode = mul_in ? mul_mode : 0; epi.alpha = alpha;
     epi.row_scale = row_scale; epi.rows_per_scale = rows_per_scale;
-    epi.resid_row_div = resid_row_div > 0 ? resid_row_div : 1;
+    epi.resid_row_div = 1;
+    epi.slab_bias = nullptr; epi.slab_div = 1; epi.ld_slab = 0;
+    if (resid && resid_row_div > 1) {        // broadcast rows: a per-slab bias, not a residual operand
+        epi.slab_bias = resid; epi.slab_div = resid_row_div; epi.ld_slab = ldr;
+        epi.resid = nullptr;
+        resid = nullptr;
+    }
     epi.gmax_f32 = gmax_f32; epi.gmax_bf16 = reinterpret_cast<__nv_bfloat16 *>(gmax_bf16); epi.garg = garg; epi.ldg = ldg;
     CUtensorMap ta, tb;
     int rc;
@@ -929,6 +945,7 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
         else if (epi.atomic && !bias && !act_kind) mode = E_ATOMIC;
         else if (gmode && !act_kind && !preact_out && !epi.mul_mode && !resid && !row_scale) mode = E_GMAX;
     }
+    if (epi.slab_bias && mode != E_PLAIN) mode = E_GENERIC;        // only the plain / generic epilogues add the slab term
     const int lay = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);     // 0 = K/K, 1 = K/MN (dgrad), 3 = MN/MN (wgrad)
 #define ACT_SPEC(P_, BN_, LAY_, MODE_)                                                                             \
     if (persistent == P_ && BN == BN_ && lay == LAY_ && mode == MODE_) {                                           \

@@ -113,8 +113,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void *__restri
 
     for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
         const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
-        float4 xh[VPL], d[VPL];
+        float4 xh[VPL], d[VPL], rres[VPL];
         float s1 = 0.f, s2 = 0.f;
+        if (dres) {        // requested with the other operands: one memory latency per row, not two
+#pragma unroll
+            for (int i = 0; i < VPL; ++i)
+                rres[i] = __ldg(reinterpret_cast<const float4 *>(dres + (size_t)row * C) + lane + 32 * i);
+        }
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
             const float4 xv = __ldg(reinterpret_cast<const float4 *>(x + (size_t)row * C) + lane + 32 * i);
@@ -145,7 +150,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void *__restri
             o.z = rs * (d[i].z - m1 - xh[i].z * m2);
             o.w = rs * (d[i].w - m1 - xh[i].w * m2);
             if (dres) {
-                const float4 r = __ldg(reinterpret_cast<const float4 *>(dres + (size_t)row * C) + lane + 32 * i);
+                const float4 r = rres[i];
                 o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
             }
             reinterpret_cast<float4 *>(dx_out + (size_t)row * C)[lane + 32 * i] = o;
@@ -523,7 +528,7 @@ extern "C" int act_layernorm_bwd(const void *dy, int dy_fp32, const float *x, co
     if (M == 0) return ACT_OK;
     if (C % 128 || C > 1024) return ACT_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = (M + 7) / 8 < 148 ? (M + 7) / 8 : 148;
+    const int grid = (M + 7) / 8 < 296 ? (M + 7) / 8 : 296;     // <= 2 CTAs per SM: 1-2 rows per warp at M = 3456
 #define LN_CASE(V)                                                                                                \
     case V:                                                                                                       \
         ACT_CUDA(launch_k(layernorm_bwd_kernel<V>, dim3(grid), dim3(256), 0, st, true, dy, dy_fp32, x, mean, rstd,  \

@@ -192,3 +192,26 @@ def test_dense_regime_step_runs():
     assert np.isfinite(loss.item()) and 0 < loss.item() < 2
     g = model.ACT_encoder.blocks.blocks[0].attn.qkv.weight.grad
     assert torch.isfinite(g).all() and g.abs().max() > 0
+
+
+def test_full_step_with_native_teacher_graph_replay():
+    """The whole Stage-II step with the frozen teacher on the act_b200 kernels (forked stream inside the captured graph):
+    finite loss in the cosine range, the teacher gets no gradient and does not change, the student does."""
+    from act_b200.engine import PretrainStep
+    torch.manual_seed(0)
+    np.random.seed(0)
+    B = 8
+    model = models.ACT_PointDistillation(models.default_config(0.6, 0.1), teacher="native").cuda().train()
+    fp = layers.FlatParams(model, lr=1e-3, weight_decay=0.05, exclude=model.UNUSED_PARAMETERS)
+    t_before = {k: v.clone() for k, v in model.dvae_tokenizer.state_dict().items()}
+    w_before = model.proj_head.weight.detach().clone()
+    eng = PretrainStep(model, fp, B, 1024).capture()
+    pts = ref_model.synthetic_clouds(B, 1024, seed=5).cuda()
+    losses = [eng.run(pts).item() for _ in range(4)]
+    assert all(np.isfinite(l) and 0.0 < l < 2.0 for l in losses), losses
+    assert len(set(losses)) > 1                                   # fresh mask / gumbel / dropout draws every replay
+    assert not torch.equal(model.proj_head.weight.detach(), w_before)
+    for k, v in model.dvae_tokenizer.state_dict().items():
+        if v.dtype.is_floating_point and "running_" not in k and "num_batches" not in k:
+            assert torch.equal(v, t_before[k]), k                 # frozen (BatchNorm running stats move: train mode)
+    assert all(p.grad is None for p in model.dvae_tokenizer.parameters())
