@@ -643,18 +643,28 @@ struct PersistCfg {
     static constexpr int EW = (MODE == E_GENERIC) ? 8 : 16;
     static constexpr int THREADS = (2 + EW) * 32;
     static constexpr int STAGES = 3;
-    static constexpr size_t smem(int BN) {
-        return (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024 + (size_t)EW * 4096;
+    static constexpr size_t smem(int BN, int NB = 1, int stages = STAGES) {
+        return (size_t)stages * (GEMM_BM * GEMM_BK * 2 + NB * BN * GEMM_BK * 2) + 1024 + (size_t)EW * 4096;
     }
 };
 
-template <int BN, bool A_MN, bool B_MN, int STAGES, int MODE>
+// NB = 2: one CTA computes a 128 x (2*BN) tile as two BN-wide MMAs per k-step that share the A tile -- for GEMMs with a
+// narrow output and a long K (the teacher ViT's fc2 / proj on 8192 token rows: N = 768) a 128 x 384 tile gives 128
+// tiles = ONE round on 148 SMs and 64 KB of operands per k-block for 768 MMA cycles, where 128 x 128 tiles need three
+// rounds at twice the operand traffic per FLOP.  2 * 384 accumulator columns do not fit TMEM, so that configuration
+// runs a single accumulator buffer (nothing to overlap with in a one-round grid).
+
+template <int BN, bool A_MN, bool B_MN, int STAGES, int MODE, int NB = 1>
 __global__ void __launch_bounds__(PersistCfg<MODE>::THREADS, 1) gemm_bf16_persistent_kernel(
     const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmEpi epi, int M, int N,
     int K, int kb_per_split, int tiles_m, int tiles_n, int total_tiles) {
     constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;
     constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
-    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t STAGE_BYTES = A_BYTES + NB * B_BYTES;
+    constexpr int TILE_N = NB * BN;                                   // output columns of one tile
+    constexpr int NBUF = 2 * TILE_N <= 512 ? 2 : 1;                   // accumulator buffers in TMEM
+    constexpr uint32_t TMEM_COLS = NBUF * TILE_N <= 256 ? 256 : 512;
+    static_assert(TILE_N <= 512 && (NB == 1 || !B_MN), "unsupported tile");
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_slot;
@@ -676,7 +686,7 @@ __global__ void __launch_bounds__(PersistCfg<MODE>::THREADS, 1) gemm_bf16_persis
         }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(&tmem_slot, 2 * BN);
+    if (warp == 1) tmem_alloc(&tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -688,7 +698,7 @@ __global__ void __launch_bounds__(PersistCfg<MODE>::THREADS, 1) gemm_bf16_persis
         if (lane == 0) {
             uint32_t it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int n0 = (t % tiles_n) * BN, m0 = ((t / tiles_n) % tiles_m) * GEMM_BM;
+                const int n0 = (t % tiles_n) * TILE_N, m0 = ((t / tiles_n) % tiles_m) * GEMM_BM;
                 const int kb0 = (t / (tiles_n * tiles_m)) * kb_per_split;
                 const int nkb = min(kb_per_split, total_kb - kb0);
                 for (int i = 0; i < nkb; ++i, ++it) {
@@ -705,7 +715,8 @@ __global__ void __launch_bounds__(PersistCfg<MODE>::THREADS, 1) gemm_bf16_persis
                             tma_load_2d(&tma_a, &full_bar[s], sa + j * (GEMM_BK * 128), m0 + j * 64, k);
                     }
                     if (!B_MN) {
-                        if (BN <= 256) tma_load_2d(&tma_b, &full_bar[s], sb, k, n0);
+#pragma unroll
+                        for (int j = 0; j < NB; ++j) tma_load_2d(&tma_b, &full_bar[s], sb + j * B_BYTES, k, n0 + j * BN);
                     } else {
 #pragma unroll
                         for (int j = 0; j < BN / 64; ++j)
@@ -721,10 +732,10 @@ __global__ void __launch_bounds__(PersistCfg<MODE>::THREADS, 1) gemm_bf16_persis
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
                 const int kb0 = (t / (tiles_n * tiles_m)) * kb_per_split;
                 const int nkb = min(kb_per_split, total_kb - kb0);
-                const uint32_t buf = lt & 1;
-                mbar_wait(&tempty_bar[buf], ((lt >> 1) & 1) ^ 1);
+                const uint32_t buf = lt % NBUF;
+                mbar_wait(&tempty_bar[buf], ((lt / NBUF) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + buf * BN;
+                const uint32_t tmem_d = tmem_base + buf * TILE_N;
                 for (int i = 0; i < nkb; ++i, ++it) {
                     const int s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(&full_bar[s], ph);
@@ -734,9 +745,12 @@ __global__ void __launch_bounds__(PersistCfg<MODE>::THREADS, 1) gemm_bf16_persis
                     for (int k = 0; k < GEMM_BK / 16; ++k) {
                         const uint64_t ad = A_MN ? make_smem_desc(sa + k * 2048, GEMM_BK * 128, 1024)
                                                  : make_smem_desc(sa + k * 32, 0, 1024);
-                        const uint64_t bd = B_MN ? make_smem_desc(sb + k * 2048, GEMM_BK * 128, 1024)
-                                                 : make_smem_desc(sb + k * 32, 0, 1024);
-                        umma_bf16(tmem_d, ad, bd, idesc, (i | k) != 0);
+#pragma unroll
+                        for (int j = 0; j < NB; ++j) {
+                            const uint64_t bd = B_MN ? make_smem_desc(sb + k * 2048, GEMM_BK * 128, 1024)
+                                                     : make_smem_desc(sb + j * B_BYTES + k * 32, 0, 1024);
+                            umma_bf16(tmem_d + j * BN, ad, bd, idesc, (i | k) != 0);
+                        }
                     }
                     umma_commit(&empty_bar[s]);
                 }
@@ -745,7 +759,8 @@ __global__ void __launch_bounds__(PersistCfg<MODE>::THREADS, 1) gemm_bf16_persis
         }
     } else {
         constexpr int EW = PersistCfg<MODE>::EW;
-        constexpr int WCOLS = BN / (EW / 4);                        // columns of the tile owned by one epilogue warp
+        constexpr int WCOLS = TILE_N / (EW / 4);                    // columns of the tile owned by one epilogue warp
+        static_assert(WCOLS % 32 == 0, "epilogue warps own whole 32-column chunks");
         const int e = warp - 2;
         const int quad = warp & 3, part = e >> 2;
         // this warp's 4 KB epilogue tile, carved after the pipeline stages
@@ -761,14 +776,14 @@ __global__ void __launch_bounds__(PersistCfg<MODE>::THREADS, 1) gemm_bf16_persis
         bool have_pre = false;
         uint32_t lt = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
-            const int n0 = (t % tiles_n) * BN, m0 = ((t / tiles_n) % tiles_m) * GEMM_BM;
-            const uint32_t buf = lt & 1;
+            const int n0 = (t % tiles_n) * TILE_N, m0 = ((t / tiles_n) % tiles_m) * GEMM_BM;
+            const uint32_t buf = lt % NBUF;
             const int row0 = m0 + quad * 32;
             const int cbase = n0 + part * WCOLS;
             if (DB && !have_pre) epi_prefetch<MODE>(epi, pa, row0, M, cbase, N, lane);    // overlaps the wait below
-            mbar_wait(&tfull_bar[buf], (lt >> 1) & 1);
+            mbar_wait(&tfull_bar[buf], (lt / NBUF) & 1);
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + buf * BN + ((uint32_t)(quad * 32) << 16) + (uint32_t)(part * WCOLS);
+            const uint32_t tmem_d = tmem_base + buf * TILE_N + ((uint32_t)(quad * 32) << 16) + (uint32_t)(part * WCOLS);
             if (DB) {
 #pragma unroll 1
                 for (int c = 0; c < NCH; c += 2) {
@@ -781,7 +796,7 @@ __global__ void __launch_bounds__(PersistCfg<MODE>::THREADS, 1) gemm_bf16_persis
                         have_pre = t2 < total_tiles;
                         if (have_pre)
                             epi_prefetch<MODE>(epi, pa, ((t2 / tiles_n) % tiles_m) * GEMM_BM + quad * 32, M,
-                                               (t2 % tiles_n) * BN + part * WCOLS, N, lane);
+                                               (t2 % tiles_n) * TILE_N + part * WCOLS, N, lane);
                     }
                     epi_do_chunk<MODE>(epi, tmem_d + (uint32_t)((c + 1) * 32), true, c + 2 >= NCH ? &tempty_bar[buf] : nullptr,
                                        pb, row0, M, cbase + (c + 1) * 32, N, lane, stage);
@@ -798,7 +813,7 @@ __global__ void __launch_bounds__(PersistCfg<MODE>::THREADS, 1) gemm_bf16_persis
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * BN);
+        tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -849,17 +864,18 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmE
     return ACT_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, int MODE = E_GENERIC>
+template <int BN, bool A_MN, bool B_MN, int MODE = E_GENERIC, int NB = 1>
 static int launch_gemm_persistent(const CUtensorMap &ta, const CUtensorMap &tb, const GemmEpi &epi, int M, int N, int K,
                                   int splits, cudaStream_t st) {
-    constexpr int STAGES = PersistCfg<MODE>::STAGES;
-    constexpr size_t smem = PersistCfg<MODE>::smem(BN);
-    auto kern = gemm_bf16_persistent_kernel<BN, A_MN, B_MN, STAGES, MODE>;
+    constexpr int STAGES = NB == 1 ? PersistCfg<MODE>::STAGES : 2;
+    constexpr size_t smem = PersistCfg<MODE>::smem(BN, NB, STAGES);
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    auto kern = gemm_bf16_persistent_kernel<BN, A_MN, B_MN, STAGES, MODE, NB>;
     ACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int total_kb = (K + GEMM_BK - 1) / GEMM_BK;
     const int kbps = (total_kb + splits - 1) / splits;
     const int nsplit = (total_kb + kbps - 1) / kbps;
-    const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM, tiles_n = (N + BN - 1) / BN;
+    const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM, tiles_n = (N + NB * BN - 1) / (NB * BN);
     const long long total = (long long)tiles_m * tiles_n * nsplit;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -898,7 +914,12 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
     // tiles on a tall matrix (the teacher-ViT token GEMMs: the 2-stage 128x192 one-tile variant starves there)
     if (persistent < 0) persistent = (tiles128 > 592 || (tiles128 > 296 && M >= 8192 && K >= 768)) ? 1 : 0;
     int BN;
-    if (persistent) {
+    bool wide384 = false;        // 128 x 384 tiles (two 192-wide MMAs sharing A): narrow outputs with a long K, one round
+    if (persistent && block_n == 0 && !a_mn_major && !b_mn_major && !gmode && splits == 1 && N % 384 == 0 && K >= 512 &&
+        (long long)((M + 127) / 128) * (N / 384) <= 148 && (long long)((M + 127) / 128) * (N / 384) >= 96) {
+        wide384 = true;
+        BN = 192;
+    } else if (persistent) {
         // 128 x 256 tiles when there are at least two rounds of them per SM, else 128 x 128 (finer load balance)
         const long long tiles256 = (long long)((M + 127) / 128) * ((N + 255) / 256) * splits;
         BN = (block_n == 256 || (block_n == 0 && N % 256 == 0 && !gmode && tiles256 >= 296)) ? 256 : 128;
@@ -953,6 +974,15 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
             return launch_gemm_persistent<BN_, (LAY_ & 2) != 0, (LAY_ & 1) != 0, MODE_>(ta, tb, epi, M, N, K, splits, st); \
         else                                                                                                       \
             return launch_gemm<BN_, (LAY_ & 2) != 0, (LAY_ & 1) != 0, MODE_>(ta, tb, epi, M, N, K, splits, st);       \
+    }
+    if (wide384 && (mode == E_RESID || mode == E_PLAIN)) {
+        if (mode == E_RESID) return launch_gemm_persistent<192, false, false, E_RESID, 2>(ta, tb, epi, M, N, K, splits, st);
+        return launch_gemm_persistent<192, false, false, E_PLAIN, 2>(ta, tb, epi, M, N, K, splits, st);
+    }
+    if (wide384) {       // other epilogues: back to the regular persistent tiles
+        BN = 128;
+        rc = make_map(&tb, B, N, K, ldb, BN);
+        if (rc) return rc;
     }
     // one tile per CTA: transformer forward / dgrad / wgrad
     ACT_SPEC(0, 128, 0, E_PLAIN) ACT_SPEC(0, 192, 0, E_PLAIN) ACT_SPEC(0, 64, 0, E_PLAIN)

@@ -162,3 +162,24 @@ def test_gemm_bn192(a_mn, b_mn):
     check(got, a.float() @ b.float().t(), False)
     auto = ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32)
     assert torch.equal(got, auto)          # the heuristic picks the 192-wide tile here
+
+
+@pytest.mark.parametrize("M,K", [(8192, 768), (8192, 3072), (8100, 768), (6200, 1024)])
+def test_gemm_wide384_tiles(M, K):
+    """Narrow output, long K, ~one round of 128 x 384 tiles (two 192-wide MMAs sharing the A tile): the teacher ViT's
+    proj / fc2 on the token rows.  Plain and bias + residual (fp32, in place) epilogues, bf16 output, ragged M."""
+    torch.manual_seed(M + K)
+    N = 768
+    a, w = rnd(M, K), rnd(N, K, scale=0.05)
+    bias = torch.randn(N, device="cuda")
+    lin = a.float() @ w.float().t()
+    check(ops.gemm(a, w, out_dtype=torch.float32), lin, False)
+    check(ops.gemm(a, w, bias=bias), lin + bias, True)
+    x = torch.randn(M, N, device="cuda")
+    want = x + lin + bias
+    got = ops.gemm(a, w, bias=bias, resid=x, out_dtype=torch.float32)
+    check(got, want, False)
+    ops.gemm(a, w, bias=bias, resid=x, out=x)          # in place on the residual stream
+    check(x, want, False)
+    # an epilogue the wide configuration does not instantiate falls back to the regular tiles
+    check(ops.gemm(a, w, bias=bias, act=ops.ACT_GELU), F.gelu(lin + bias), True)
