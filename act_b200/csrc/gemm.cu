@@ -817,6 +817,192 @@ __global__ void __launch_bounds__(PersistCfg<MODE>::THREADS, 1) gemm_bf16_persis
     }
 }
 
+// ------------------------------------------------------------------ the CTA-pair (cta_group::2) kernel
+// L2 -> SM operand delivery (~43 B/clk/SM measured) bounds a 128 x 256 single-CTA tile at ~45 % of the MMA rate:
+// bytes per FLOP scale with (1/BM + 1/BN).  Two CTAs of a cluster (one TPC) therefore compute ONE 256 x 256 tile
+// with tcgen05.mma.cta_group::2: each CTA loads its 128 rows of A and its 128 columns' worth of B (32 KB per k-block
+// instead of 48 KB for the same 128 x 256 outputs per CTA), the leader CTA's single MMA thread issues M = 256 x N = 256
+// instructions that read both CTAs' shared memory and write both CTAs' TMEM, and every CTA runs the epilogue of its own
+// 128 accumulator rows.  Barriers: TMA (cta_group::2 form) of BOTH CTAs completes on the LEADER's full barrier;
+// tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both CTAs; the peer's epilogue warps
+// arrive on the leader's "accumulator drained" barrier through the cluster shared window.  K-major operands only.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr` in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    // relaxed: the hand-off it signals (TMEM reads done) is ordered by tcgen05.fence::before_thread_sync; a .release at
+    // cluster scope compiles to MEMBAR.ALL.GPU, a microsecond-class fence, once per warp per tile
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta(const CUtensorMap *map, uint32_t leader_bar_cluster_addr, void *dst, int c0,
+                                                 int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t *slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint64_t *bar) {       // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+constexpr int PAIR_EW = 16;                               // epilogue warps per CTA
+constexpr int PAIR_THREADS = (2 + PAIR_EW) * 32;
+constexpr int PAIR_STAGES = 4;
+constexpr int PAIR_N = 256;                               // tile columns (each CTA loads 128 of them as B rows)
+constexpr size_t PAIR_SMEM = (size_t)PAIR_STAGES * (2 * GEMM_BM * GEMM_BK * 2) + 1024 + (size_t)PAIR_EW * 4096;
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) gemm_bf16_pair_kernel(
+    const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmEpi epi, int M, int N,
+    int K, int tiles_m, int tiles_n, int total_tiles) {
+    constexpr int STAGES = PAIR_STAGES;
+    constexpr uint32_t HALF_BYTES = GEMM_BM * GEMM_BK * 2;             // 16 KB: this CTA's A rows / B rows of one k-block
+    constexpr uint32_t STAGE_BYTES = 2 * HALF_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_slot;
+
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int total_kb = (K + GEMM_BK - 1) / GEMM_BK;
+    const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);          // leader's: its producer's arrive.expect_tx (+ both CTAs' TMA bytes)
+            mbar_init(&empty_bar[s], 1);         // one multicast tcgen05.commit
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull_bar[b], 1);
+            mbar_init(&tempty_bar[b], 2 * PAIR_EW);    // leader's: the epilogue warps of BOTH CTAs
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc_2cta(&tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync_all();                           // barrier inits + TMEM allocation visible pair-wide
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    pdl_wait();
+    pdl_trigger();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = pair_id; t < total_tiles; t += num_pairs) {
+                const int n0 = (t % tiles_n) * PAIR_N + (int)rank * (PAIR_N / 2);
+                const int m0 = (t / tiles_n) * (2 * GEMM_BM) + (int)rank * GEMM_BM;
+                for (int i = 0; i < total_kb; ++i, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    if (leader) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);      // both CTAs' bytes land on this barrier
+                    const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
+                    uint8_t *sa = smem + s * STAGE_BYTES, *sb = sa + HALF_BYTES;
+                    tma_load_2d_2cta(&tma_a, lbar, sa, i * GEMM_BK, m0);
+                    tma_load_2d_2cta(&tma_b, lbar, sb, i * GEMM_BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc(2 * GEMM_BM, PAIR_N, false, false);
+            uint32_t it = 0, lt = 0;
+            for (int t = pair_id; t < total_tiles; t += num_pairs, ++lt) {
+                const uint32_t buf = lt & 1;
+                mbar_wait(&tempty_bar[buf], ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + buf * PAIR_N;
+                for (int i = 0; i < total_kb; ++i, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + HALF_BYTES;
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k)
+                        umma_bf16_2cta(tmem_d, make_smem_desc(sa + k * 32, 0, 1024), make_smem_desc(sb + k * 32, 0, 1024), idesc,
+                                       (i | k) != 0);
+                    umma_commit_2cta(&empty_bar[s]);
+                }
+                umma_commit_2cta(&tfull_bar[buf]);
+            }
+        }
+    } else {
+        constexpr int WCOLS = PAIR_N / (PAIR_EW / 4);
+        constexpr int NCH = WCOLS / 32;
+        const int e = warp - 2;
+        const int quad = warp & 3, part = e >> 2;
+        const uint32_t stage = smem_u32(smem + STAGES * STAGE_BYTES) + e * 4096;
+        EpiPre pa;
+        uint32_t lt = 0;
+        for (int t = pair_id; t < total_tiles; t += num_pairs, ++lt) {
+            const int n0 = (t % tiles_n) * PAIR_N, m0 = (t / tiles_n) * (2 * GEMM_BM) + (int)rank * GEMM_BM;
+            const uint32_t buf = lt & 1;
+            const int row0 = m0 + quad * 32;
+            const int cbase = n0 + part * WCOLS;
+            mbar_wait(&tfull_bar[buf], (lt >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + buf * PAIR_N + ((uint32_t)(quad * 32) << 16) + (uint32_t)(part * WCOLS);
+            const uint32_t lempty = mapa_u32(smem_u32(&tempty_bar[buf]), 0);
+#pragma unroll 1
+            for (int c = 0; c < NCH; ++c) {
+                uint32_t v[32];
+                __syncwarp();
+                tmem_ld32(tmem_d + (uint32_t)(c * 32), v);
+                if (c + 1 == NCH) {              // accumulator buffer drained: tell the leader's MMA thread
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(lempty);
+                }
+                epilogue_chunk<MODE, true>(epi, v, pa, row0, M, cbase + c * 32, N, lane, stage);
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                           // nobody leaves (or frees TMEM) while the peer may still touch it
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2cta(tmem_base, 512);
+    }
+}
+
 // -------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -886,6 +1072,30 @@ static int launch_gemm_persistent(const CUtensorMap &ta, const CUtensorMap &tb, 
     return ACT_OK;
 }
 
+inline bool pair_enabled() {       // ACT_B200_PAIR=0 keeps every GEMM on the single-CTA kernels (A/B timing)
+    static const int on = [] {
+        const char *e = std::getenv("ACT_B200_PAIR");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    return on != 0;
+}
+
+template <int MODE>
+static int launch_gemm_pair(const CUtensorMap &ta, const CUtensorMap &tb, const GemmEpi &epi, int M, int N, int K,
+                            cudaStream_t st) {
+    auto kern = gemm_bf16_pair_kernel<MODE>;
+    ACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM));
+    const int tiles_m = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM), tiles_n = (N + PAIR_N - 1) / PAIR_N;
+    const long long total = (long long)tiles_m * tiles_n;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int pairs = (int)(total < sms / 2 ? total : sms / 2);
+    ACT_CUDA(launch_k(kern, dim3(2 * pairs), dim3(PAIR_THREADS), PAIR_SMEM, st, true, ta, tb, epi, M, N, K, tiles_m, tiles_n,
+                      (int)total));
+    return ACT_OK;
+}
+
 }  // namespace act
 
 extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, int a_mn_major, int b_mn_major,
@@ -909,13 +1119,51 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
     if (row_scale && rows_per_scale <= 0) return ACT_EINVAL;
     if (row_scale && rows_per_scale < 8) return ACT_EUNSUPPORTED;      // the epilogue steps the gate index 4/8 rows at a time
     if (resid && resid_row_div > 1 && (resid_row_div % 32)) return ACT_EUNSUPPORTED;   // broadcast rows: whole 32-row slabs
+    GemmEpi epi;
+    epi.out = out; epi.preact_out = preact_out; epi.bias = bias; epi.resid = resid;
+    epi.mul_in = reinterpret_cast<const __nv_bfloat16 *>(mul_in);
+    epi.ldo = ldo; epi.ldr = ldr; epi.ldm = ldm; epi.out_fp32 = out_fp32; epi.atomic = splits > 1 ? 1 : 0;
+    epi.act = act_kind; epi.mul_mode = mul_in ? mul_mode : 0; epi.alpha = alpha;
+    epi.row_scale = row_scale; epi.rows_per_scale = rows_per_scale;
+    epi.resid_row_div = 1;
+    epi.slab_bias = nullptr; epi.slab_div = 1; epi.ld_slab = 0;
+    if (resid && resid_row_div > 1) {        // broadcast rows: a per-slab bias, not a residual operand
+        epi.slab_bias = resid; epi.slab_div = resid_row_div; epi.ld_slab = ldr;
+        epi.resid = nullptr;
+        resid = nullptr;
+    }
+    epi.gmax_f32 = gmax_f32; epi.gmax_bf16 = reinterpret_cast<__nv_bfloat16 *>(gmax_bf16); epi.garg = garg; epi.ldg = ldg;
+    int mode = E_GENERIC;
+    if (alpha == 1.f) {
+        const bool simple_out = !preact_out && !epi.mul_mode && !resid && !row_scale && !gmode && !epi.atomic;
+        if (simple_out && !act_kind) mode = E_PLAIN;
+        else if (act_kind == 1 && !epi.mul_mode && !resid && !row_scale && !gmode && !epi.atomic && !out_fp32) mode = E_GELU;
+        else if (epi.mul_mode && !bias && !act_kind && !preact_out && !resid && !row_scale && !gmode && !epi.atomic)
+            mode = epi.mul_mode == 1 ? E_MULGELU : E_MULRELU;
+        else if (resid && !act_kind && !preact_out && !epi.mul_mode && !gmode && !epi.atomic) mode = E_RESID;
+        else if (epi.atomic && !bias && !act_kind) mode = E_ATOMIC;
+        else if (gmode && !act_kind && !preact_out && !epi.mul_mode && !resid && !row_scale) mode = E_GMAX;
+    }
+    if (epi.slab_bias && mode != E_PLAIN) mode = E_GENERIC;        // only the plain / generic epilogues add the slab term
     const long long tiles128 = (long long)((M + 127) / 128) * ((N + 127) / 128) * splits;
     // persistent: more than two waves of the one-tile-per-CTA kernel (2 CTAs / SM), or more than one wave of long-K
     // tiles on a tall matrix (the teacher-ViT token GEMMs: the 2-stage 128x192 one-tile variant starves there)
+    const bool auto_persist = persistent < 0;
     if (persistent < 0) persistent = (tiles128 > 592 || (tiles128 > 296 && M >= 8192 && K >= 768)) ? 1 : 0;
+    // persistent == 2: the CTA-pair (cta_group::2, 256 x 256 tile) kernel.  Chosen automatically for K-major GEMMs with
+    // a plain / residual epilogue and at least one full round of pair tiles (measured +5..20 % over the single-CTA
+    // tiles there; the GELU epilogue is compute-heavy enough that the pair's doubled tile does not pay at K = 768).
+    const long long pair_tiles = (long long)((M + 255) / 256) * ((N + 255) / 256);
+    if (persistent == 1 && auto_persist && block_n == 0 && !a_mn_major && !b_mn_major && !gmode && splits == 1 &&
+        (mode == E_PLAIN || mode == E_RESID) && pair_tiles >= 74 && act::pair_enabled())
+        persistent = 2;
+    const bool pair = persistent == 2;
+    if (pair && (a_mn_major || b_mn_major || gmode || splits != 1 || block_n != 0)) return ACT_EUNSUPPORTED;
     int BN;
     bool wide384 = false;        // 128 x 384 tiles (two 192-wide MMAs sharing A): narrow outputs with a long K, one round
-    if (persistent && block_n == 0 && !a_mn_major && !b_mn_major && !gmode && splits == 1 && N % 384 == 0 && K >= 512 &&
+    if (pair) {
+        BN = 128;                // each CTA of the pair loads 128 B rows (tile columns)
+    } else if (persistent && block_n == 0 && !a_mn_major && !b_mn_major && !gmode && splits == 1 && N % 384 == 0 && K >= 512 &&
         (long long)((M + 127) / 128) * (N / 384) <= 148 && (long long)((M + 127) / 128) * (N / 384) >= 96) {
         wide384 = true;
         BN = 192;
@@ -932,20 +1180,6 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
         if (N % 192 == 0 && rows * ((N + 127) / 128) * splits > 296 && rows * (N / 192) * splits <= 296) BN = 192;
         else if (rows * ((N + 127) / 128) * splits < 148) BN = 64;     // fewer tiles than SMs: halve them
     }
-    GemmEpi epi;
-    epi.out = out; epi.preact_out = preact_out; epi.bias = bias; epi.resid = resid;
-    epi.mul_in = reinterpret_cast<const __nv_bfloat16 *>(mul_in);
-    epi.ldo = ldo; epi.ldr = ldr; epi.ldm = ldm; epi.out_fp32 = out_fp32; epi.atomic = splits > 1 ? 1 : 0;
-    epi.act = act_kind; epi.mul_mode = mul_in ? mul_mode : 0; epi.alpha = alpha;
-    epi.row_scale = row_scale; epi.rows_per_scale = rows_per_scale;
-    epi.resid_row_div = 1;
-    epi.slab_bias = nullptr; epi.slab_div = 1; epi.ld_slab = 0;
-    if (resid && resid_row_div > 1) {        // broadcast rows: a per-slab bias, not a residual operand
-        epi.slab_bias = resid; epi.slab_div = resid_row_div; epi.ld_slab = ldr;
-        epi.resid = nullptr;
-        resid = nullptr;
-    }
-    epi.gmax_f32 = gmax_f32; epi.gmax_bf16 = reinterpret_cast<__nv_bfloat16 *>(gmax_bf16); epi.garg = garg; epi.ldg = ldg;
     CUtensorMap ta, tb;
     int rc;
     // K-major operand: global [MN, K], box [BLOCK_MN rows, 64].  MN-major: global [K, MN], box [64 k-rows, 64].
@@ -955,18 +1189,6 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     // epilogue mode (see the enum): the specialised instantiations below cover the hot layouts of the ACT step
-    int mode = E_GENERIC;
-    if (alpha == 1.f) {
-        const bool simple_out = !preact_out && !epi.mul_mode && !resid && !row_scale && !gmode && !epi.atomic;
-        if (simple_out && !act_kind) mode = E_PLAIN;
-        else if (act_kind == 1 && !epi.mul_mode && !resid && !row_scale && !gmode && !epi.atomic && !out_fp32) mode = E_GELU;
-        else if (epi.mul_mode && !bias && !act_kind && !preact_out && !resid && !row_scale && !gmode && !epi.atomic)
-            mode = epi.mul_mode == 1 ? E_MULGELU : E_MULRELU;
-        else if (resid && !act_kind && !preact_out && !epi.mul_mode && !gmode && !epi.atomic) mode = E_RESID;
-        else if (epi.atomic && !bias && !act_kind) mode = E_ATOMIC;
-        else if (gmode && !act_kind && !preact_out && !epi.mul_mode && !resid && !row_scale) mode = E_GMAX;
-    }
-    if (epi.slab_bias && mode != E_PLAIN) mode = E_GENERIC;        // only the plain / generic epilogues add the slab term
     const int lay = (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);     // 0 = K/K, 1 = K/MN (dgrad), 3 = MN/MN (wgrad)
 #define ACT_SPEC(P_, BN_, LAY_, MODE_)                                                                             \
     if (persistent == P_ && BN == BN_ && lay == LAY_ && mode == MODE_) {                                           \
@@ -974,6 +1196,12 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
             return launch_gemm_persistent<BN_, (LAY_ & 2) != 0, (LAY_ & 1) != 0, MODE_>(ta, tb, epi, M, N, K, splits, st); \
         else                                                                                                       \
             return launch_gemm<BN_, (LAY_ & 2) != 0, (LAY_ & 1) != 0, MODE_>(ta, tb, epi, M, N, K, splits, st);       \
+    }
+    if (pair) {
+        if (mode == E_PLAIN) return launch_gemm_pair<E_PLAIN>(ta, tb, epi, M, N, K, st);
+        if (mode == E_GELU) return launch_gemm_pair<E_GELU>(ta, tb, epi, M, N, K, st);
+        if (mode == E_RESID) return launch_gemm_pair<E_RESID>(ta, tb, epi, M, N, K, st);
+        return ACT_EUNSUPPORTED;
     }
     if (wide384 && (mode == E_RESID || mode == E_PLAIN)) {
         if (mode == E_RESID) return launch_gemm_persistent<192, false, false, E_RESID, 2>(ta, tb, epi, M, N, K, splits, st);

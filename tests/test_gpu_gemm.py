@@ -183,3 +183,24 @@ def test_gemm_wide384_tiles(M, K):
     check(x, want, False)
     # an epilogue the wide configuration does not instantiate falls back to the regular tiles
     check(ops.gemm(a, w, bias=bias, act=ops.ACT_GELU), F.gelu(lin + bias), True)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (8192, 768, 768), (8100, 2304, 768), (300, 264, 200), (4096, 512, 1024)])
+def test_gemm_cta_pair(M, N, K):
+    """The cta_group::2 kernel (two CTAs of a cluster on one 256 x 256 tile), forced with persistent=2: plain, GELU and
+    bias + residual epilogues, ragged M / N, against fp32 torch on the same bf16 operands."""
+    torch.manual_seed(M + N + K)
+    a, w = rnd(M, K), rnd(N, K, scale=0.05)
+    bias = torch.randn(N, device="cuda")
+    lin = a.float() @ w.float().t()
+    check(ops.gemm(a, w, out_dtype=torch.float32, persistent=2), lin, False)
+    check(ops.gemm(a, w, bias=bias, persistent=2), lin + bias, True)
+    check(ops.gemm(a, w, bias=bias, act=ops.ACT_GELU, persistent=2), F.gelu(lin + bias), True)
+    x = torch.randn(M, N, device="cuda")
+    want = x + lin + bias
+    ops.gemm(a, w, bias=bias, resid=x, out=x, persistent=2)          # in place on the residual stream
+    check(x, want, False)
+    res = torch.randn((M + 31) // 32, N, device="cuda")              # per-group broadcast term (mini-PointNet conv3)
+    if M % 32 == 0:
+        got = ops.gemm(a, w, resid=res, resid_row_div=32, persistent=2)
+        check(got, lin + res.repeat_interleave(32, 0), True)
