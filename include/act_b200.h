@@ -94,8 +94,11 @@ int act_chamfer_backward(const float *xyz1, const float *xyz2, const int32_t *id
  * fp32 accumulators, and the winning row (first on ties); `out` may then be NULL (conv4: only the max is kept).
  * splits > 1: split-K, fp32 atomic accumulation into out (caller zeroes it; no other epilogue parts).
  * persistent: 1 = one CTA per SM looping over tiles with a double-buffered TMEM accumulator (many-tile GEMMs),
- * 0 = one tile per CTA, -1 = choose.
- * block_n: 64 / 128 output-tile width (0 = choose).  Requirements: N % 8 == 0, K % 8 == 0 pitches,
+ * 2 = the CTA-pair kernel (clusters of two CTAs computing 256 x 256 tiles with tcgen05.mma.cta_group::2; K-major
+ * operands, plain / GELU / residual epilogues, no split-K, block_n = 0; ACT_EUNSUPPORTED otherwise), 0 = one tile per
+ * CTA, -1 = choose (the pair kernel for K-major plain / residual GEMMs with at least 74 pair tiles).
+ * block_n: 64 / 128 / 192 / 256 output-tile width (0 = choose).  resid_row_div: 1, or a multiple of 32 (the broadcast
+ * term then enters as a per-32-row-slab bias).  rows_per_scale >= 8.  Requirements: N % 8 == 0, K % 8 == 0 pitches,
  * 16-byte aligned pointers. */
 int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, int a_mn_major, int b_mn_major, int lda, int ldb,
                   void *out, int ldo, int out_fp32, const float *bias, int act_kind, void *preact_out,
