@@ -213,6 +213,65 @@ struct EpiTraits {
     }
 };
 
+// Per-chunk vectors that do not depend on the accumulator: this lane's bias (+ per-slab broadcast term) columns and its
+// rows' DropPath gates.  Requested BEFORE the TMEM load so their L2 round trip overlaps it instead of sitting between
+// the two epilogue phases.
+struct EpiBias {
+    float b[8];
+    float rs[8];
+};
+template <int MODE>
+__device__ __forceinline__ void epi_load_bias(const GemmEpi &epi, EpiBias &eb, int row0, int M, int n, int N, int lane) {
+    using TR = EpiTraits<MODE>;
+    constexpr bool G = MODE == E_GENERIC;
+    const bool has_bias = (MODE == E_ATOMIC || MODE == E_MULGELU || MODE == E_MULRELU) ? false : (epi.bias != nullptr);
+    const bool has_slab = (MODE == E_PLAIN || G) ? (epi.slab_bias != nullptr) : false;
+    const bool has_rscale = (G || MODE == E_RESID) ? (epi.row_scale != nullptr) : false;
+    if (!(has_bias || has_slab || has_rscale) || row0 >= M || n >= N) return;
+    const bool wide = TR::wide(epi);
+    const int cw = wide ? 8 : 4;
+    const int rq = wide ? (lane >> 2) : (lane >> 3), cq = wide ? (lane & 3) : (lane & 7);
+    const int col = n + cq * cw;
+    if (has_bias || has_slab) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) eb.b[j] = 0.f;
+        if (col < N) {
+            if (has_bias) {
+                const float4 *bp = reinterpret_cast<const float4 *>(epi.bias + col);
+                const float4 b0 = __ldg(bp);
+                eb.b[0] = b0.x; eb.b[1] = b0.y; eb.b[2] = b0.z; eb.b[3] = b0.w;
+                if (wide) {
+                    const float4 b1 = __ldg(bp + 1);
+                    eb.b[4] = b1.x; eb.b[5] = b1.y; eb.b[6] = b1.z; eb.b[7] = b1.w;
+                }
+            }
+            if (has_slab) {
+                const float4 *sp = reinterpret_cast<const float4 *>(epi.slab_bias + (size_t)(row0 / epi.slab_div) * epi.ld_slab + col);
+                const float4 b0 = __ldg(sp);
+                eb.b[0] += b0.x; eb.b[1] += b0.y; eb.b[2] += b0.z; eb.b[3] += b0.w;
+                if (wide) {
+                    const float4 b1 = __ldg(sp + 1);
+                    eb.b[4] += b1.x; eb.b[5] += b1.y; eb.b[6] += b1.z; eb.b[7] += b1.w;
+                }
+            }
+        }
+    }
+    if (has_rscale) {
+        // one division per chunk; the gate index then advances incrementally (rows_per_scale >= 8 >= rows per iteration)
+        const int rpi = wide ? 8 : 4, nit = wide ? 4 : 8;
+        const int rfirst = row0 + rq;
+        int sq = rfirst / epi.rows_per_scale, srem = rfirst - sq * epi.rows_per_scale;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < nit) {
+                eb.rs[i] = rfirst + i * rpi < M ? __ldg(epi.row_scale + sq) : 0.f;
+                srem += rpi;
+                if (srem >= epi.rows_per_scale) { srem -= epi.rows_per_scale; ++sq; }
+            }
+        }
+    }
+}
+
 // row0: first row of the warp's 32-row slab; n: first column of the chunk.  Row indices advance by pointer stepping
 // (one 64-bit add per iteration): the epilogue is instruction-issue bound, so no per-element index arithmetic.
 template <int MODE, int CW, bool FULL>
@@ -270,8 +329,8 @@ __device__ __forceinline__ void epi_prefetch(const GemmEpi &epi, EpiPre &pre, in
 }
 
 template <int MODE, int CW, bool FULL>
-__device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPre &pre, int row0, int M, int n, int N,
-                                                 int lane, uint32_t stage) {
+__device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPre &pre, const EpiBias &eb, int row0, int M,
+                                                 int n, int N, int lane, uint32_t stage) {
     using TR = EpiTraits<MODE>;
     constexpr bool G = MODE == E_GENERIC;
     constexpr int NIT = CW == 4 ? 8 : 4, RPI = 32 / NIT;
@@ -290,37 +349,6 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
     const int rfirst = row0 + rq;
     const int rows_left = FULL ? 32 : (col_ok ? M - rfirst : 0);    // iteration i stores iff i * RPI < rows_left
     const bool has_slab = (MODE == E_PLAIN || MODE == E_GENERIC) ? (epi.slab_bias != nullptr) : false;
-    float bias[CW];
-    if (has_bias || has_slab) {
-#pragma unroll
-        for (int j = 0; j < CW; ++j) bias[j] = 0.f;
-        if (has_bias && col_ok) {
-#pragma unroll
-            for (int q = 0; q < CW / 4; ++q) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(epi.bias + col) + q);
-                bias[4 * q] = b4.x; bias[4 * q + 1] = b4.y; bias[4 * q + 2] = b4.z; bias[4 * q + 3] = b4.w;
-            }
-        }
-        if (has_slab && col_ok) {
-            const float4 *sp = reinterpret_cast<const float4 *>(epi.slab_bias + (size_t)(row0 / epi.slab_div) * epi.ld_slab + col);
-#pragma unroll
-            for (int q = 0; q < CW / 4; ++q) {
-                const float4 b4 = __ldg(sp + q);
-                bias[4 * q] += b4.x; bias[4 * q + 1] += b4.y; bias[4 * q + 2] += b4.z; bias[4 * q + 3] += b4.w;
-            }
-        }
-    }
-    float rs[NIT];
-    if (has_rscale) {
-        // one division per chunk; the scale index then advances incrementally (rows_per_scale >= 8 >= RPI, host-checked)
-        int sq = rfirst / epi.rows_per_scale, srem = rfirst - sq * epi.rows_per_scale;
-#pragma unroll
-        for (int i = 0; i < NIT; ++i) {
-            rs[i] = i * RPI < rows_left ? __ldg(epi.row_scale + sq) : 0.f;
-            srem += RPI;
-            if (srem >= epi.rows_per_scale) { srem -= epi.rows_per_scale; ++sq; }
-        }
-    }
     float best[CW];
     int barg[CW];
     const bool want_arg = gmode && epi.garg != nullptr;      // the arg-max costs a second shuffle per value: only on demand
@@ -347,7 +375,7 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
         }
         if (has_bias || has_slab) {
 #pragma unroll
-            for (int j = 0; j < CW; ++j) f[j] += bias[j];
+            for (int j = 0; j < CW; ++j) f[j] += eb.b[j];
         }
         if (gmode) {
             // max over the slab's 32 rows of (acc + bias) per column; the first row wins ties.  M % 32 == 0 in this
@@ -398,7 +426,7 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
             }
             if (has_rscale) {
 #pragma unroll
-                for (int j = 0; j < CW; ++j) f[j] *= rs[i];
+                for (int j = 0; j < CW; ++j) f[j] *= eb.rs[i];
             }
             if (has_resid) {
                 if (!mul_mode) {
@@ -468,8 +496,8 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
 // the two 32-register sets are never live together -- the 16-warp persistent configuration has 96 registers per
 // thread, and its spills went to L2 (the L1 is almost entirely carved out as shared memory there).
 template <int MODE, bool LATE = false>
-__device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_t (&v)[32], EpiPre &pre, int row0,
-                                               int M, int n, int N, int lane, uint32_t stage) {
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_t (&v)[32], EpiPre &pre, const EpiBias &eb,
+                                               int row0, int M, int n, int N, int lane, uint32_t stage) {
     using TR = EpiTraits<MODE>;
     if (n >= N || row0 >= M) return;                  // warp-uniform
     __syncwarp();                                     // the previous chunk's phase-B reads of the tile are done
@@ -485,11 +513,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_
     __syncwarp();
     const bool full = row0 + 32 <= M && n + 32 <= N;
     if (TR::wide(epi)) {
-        if (full) epilogue_phase_b<MODE, 8, true>(epi, pre, row0, M, n, N, lane, stage);
-        else epilogue_phase_b<MODE, 8, false>(epi, pre, row0, M, n, N, lane, stage);
+        if (full) epilogue_phase_b<MODE, 8, true>(epi, pre, eb, row0, M, n, N, lane, stage);
+        else epilogue_phase_b<MODE, 8, false>(epi, pre, eb, row0, M, n, N, lane, stage);
     } else {
-        if (full) epilogue_phase_b<MODE, 4, true>(epi, pre, row0, M, n, N, lane, stage);
-        else epilogue_phase_b<MODE, 4, false>(epi, pre, row0, M, n, N, lane, stage);
+        if (full) epilogue_phase_b<MODE, 4, true>(epi, pre, eb, row0, M, n, N, lane, stage);
+        else epilogue_phase_b<MODE, 4, false>(epi, pre, eb, row0, M, n, N, lane, stage);
     }
 }
 
@@ -497,6 +525,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_
 template <int MODE, bool LATE = false>
 __device__ __forceinline__ void epi_do_chunk(const GemmEpi &epi, uint32_t taddr, bool have_acc, uint64_t *release_bar,
                                              EpiPre &pre, int row0, int M, int n, int N, int lane, uint32_t stage) {
+    EpiBias eb;
+    epi_load_bias<MODE>(epi, eb, row0, M, n, N, lane);
     uint32_t v[32];
     __syncwarp();
     if (have_acc) {
@@ -510,7 +540,7 @@ __device__ __forceinline__ void epi_do_chunk(const GemmEpi &epi, uint32_t taddr,
         __syncwarp();
         if (lane == 0) mbar_arrive(release_bar);
     }
-    epilogue_chunk<MODE, LATE>(epi, v, pre, row0, M, n, N, lane, stage);
+    epilogue_chunk<MODE, LATE>(epi, v, pre, eb, row0, M, n, N, lane, stage);
 }
 
 // ------------------------------------------------------------------------------------- the kernel
@@ -983,6 +1013,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) gem
             const uint32_t lempty = mapa_u32(smem_u32(&tempty_bar[buf]), 0);
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
+                EpiBias eb;
+                epi_load_bias<MODE>(epi, eb, row0, M, cbase + c * 32, N, lane);
                 uint32_t v[32];
                 __syncwarp();
                 tmem_ld32(tmem_d + (uint32_t)(c * 32), v);
@@ -991,7 +1023,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) gem
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(lempty);
                 }
-                epilogue_chunk<MODE, true>(epi, v, pa, row0, M, cbase + c * 32, N, lane, stage);
+                epilogue_chunk<MODE, true>(epi, v, pa, eb, row0, M, cbase + c * 32, N, lane, stage);
             }
         }
     }
