@@ -218,6 +218,69 @@ def gen_teacher():
     print("teacher.npz", feat.abs().mean().item(), labels["idx"][0, :6].tolist())
 
 
+def dvae_noise(B, G, num_tokens, seed=41):
+    """Fixed gumbel noise shared by the golden run, the oracle and the GPU tests of the Stage-I step."""
+    return torch.from_numpy(np.random.default_rng(seed).gumbel(size=(B, G, num_tokens)).astype(np.float32))
+
+
+DVAE_KLD_WEIGHT = 0.05      # a mid-schedule value (runner_autoencoder.py:18-41), so the KL gradient is exercised too
+
+
+def run_reference_dvae(pts, temperature=1.0, seed=8):
+    """One Stage-I training step of the UNMODIFIED reference DiscreteVAE (dvae.py:278-357) as
+    tools/runner_autoencoder.py:137-146 drives it (forward, get_loss, loss_1 + kld_weight * loss_2, backward), with
+    F.gumbel_softmax's internal noise replaced by dvae_noise()."""
+    import models.dvae as dvae
+    from .ref_dvae import gumbel_softmax_with_noise
+    cfg = shims.easydict(dict(NAME="DiscreteVAE", group_size=32, num_group=64, num_tokens=8192, encoder_dims=256,
+                              tokens_dims=256, decoder_dims=256))      # cfgs/autoencoder/pointbert_dvae.yaml:41-48
+    model = dvae.DiscreteVAE(cfg)
+    fill_params(model, seed=seed)
+    model.train()
+    B = pts.shape[0]
+    gumbel = dvae_noise(B, 64, 8192)
+    orig = dvae.F.gumbel_softmax
+    dvae.F.gumbel_softmax = lambda logits, tau=1.0, hard=False, dim=-1: gumbel_softmax_with_noise(logits, gumbel, tau, hard)
+    try:
+        ret = model(pts, temperature=temperature, hard=False)
+        loss_recon, loss_klv = model.get_loss(ret, pts)
+        loss = loss_recon + DVAE_KLD_WEIGHT * loss_klv
+        loss.backward()
+    finally:
+        dvae.F.gumbel_softmax = orig
+    return model, ret, loss_recon, loss_klv, loss
+
+
+def gen_dvae_step():
+    """BASELINE config 3 (Stage-I autoencoder step) at B=2: outputs, both losses and parameter gradients."""
+    pts = synthetic_clouds(2, 1024, seed=23)
+    model, ret, l1, l2, loss = run_reference_dvae(pts)
+    whole_coarse, whole_fine, coarse, fine, nb, logits = ret
+    res = {"pts": pts.numpy(), "coarse": coarse.detach().numpy(), "fine": fine.detach().numpy(),
+           "whole_fine": whole_fine.numpy(), "logits_sample": logits.detach()[:, ::8, ::64].numpy(),
+           "logits_absmean": np.float32(logits.abs().mean().item()),
+           "loss_recon": np.float32(l1.item()), "loss_klv": np.float32(l2.item()), "loss": np.float32(loss.item())}
+    keep_full = ("decoder.mlp.4.bias", "decoder.final_conv.6.weight", "decoder.final_conv.0.weight",
+                 "dgcnn_2.layer5.1.weight", "dgcnn_2.input_trans.bias", "dgcnn_1.layer1.1.bias",
+                 "encoder.second_conv.3.bias", "encoder.first_conv.0.weight")
+    names, norms = [], []
+    for k, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        names.append(k)
+        norms.append(p.grad.norm().item())
+        if k in keep_full:
+            res["grad/" + k] = p.grad.numpy()
+    res["grad/codebook_rows"] = model.codebook.grad[::512].numpy()
+    res["grad_names"] = np.array(names)
+    res["grad_norms"] = np.array(norms, np.float64)
+    for k, b in model.named_buffers():
+        if "running" in k:
+            res["buf/" + k] = b.numpy()
+    np.savez_compressed(os.path.join(GOLD, "dvae_step.npz"), **res)
+    print("dvae_step.npz recon", l1.item(), "klv", l2.item(), "n grads", len(names))
+
+
 def main():
     if not os.path.isdir(shims.REFERENCE_ROOT):
         sys.exit("needs /root/reference (authoring container only)")
@@ -229,6 +292,7 @@ def main():
     gen_encoder()
     gen_student_step()
     gen_teacher()
+    gen_dvae_step()
 
 
 if __name__ == "__main__":
