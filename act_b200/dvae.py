@@ -10,8 +10,8 @@ What runs where (forward AND backward):
     mini-PointNet Encoder, train-mode BatchNorm             -> layers.PointNetEncoderFn (tcgen05 GEMMs + pointnet.cu)
     DGCNN x2 (dvae.py:26-117): kNN k=4 among the centres    -> csrc/knn.cu;  every 1x1 conv as ONE token-level tcgen05
         GEMM per layer -- W.[x_k - x_q ; x_q] = Wa.x_k + (Wb - Wa).x_q, so the [B,2C,G,4] edge tensor is never built --
-        with forward, dgrad and wgrad on layers.LinearFn; GroupNorm / LeakyReLU / max-over-k are ATen element-wise ops
-        (library calls; the fused forward kernels of csrc/teacher.cu have no backward yet)
+        with forward, dgrad and wgrad on layers.LinearFn; GroupNorm + LeakyReLU + max-over-k fused into one forward and
+        two backward kernels per layer (csrc/dgcnn_train.cu, layers.DgcnnEdgeFn / GroupNormRowsFn)
     soft gumbel-softmax (dvae.py:346)                       -> ATen softmax; the [BG,8192] x [8192,C] codebook einsum
                                                                (dvae.py:347) on the tcgen05 GEMM
     FoldingNet Decoder (dvae.py:217-275)                    -> Linear / 1x1-conv layers on the tcgen05 GEMM; the K=5
@@ -68,35 +68,22 @@ class ChamferDistanceL1(ChamferDistanceL2):
 
 
 # ------------------------------------------------------------------------------------------------- DGCNN
-def _group_norm_rows(e, gamma, beta, eps, B):
-    """nn.GroupNorm(4, C) of the reference's [B, C, ...] tensor held rows-major: e [B, R, C] (R = every position of
-    one cloud); statistics per (cloud, channel group) over R x C/4 values, biased variance."""
-    R, C = e.shape[1], e.shape[2]
-    v = e.view(B, R, 4, C // 4)
-    var, mean = torch.var_mean(v, dim=(1, 3), keepdim=True, unbiased=False)
-    y = (v - mean) * torch.rsqrt(var + eps)
-    return y.view(B, R, C) * gamma + beta
-
-
 def dgcnn_forward(m, x, idx4, B, G):
-    """DGCNN.forward (dvae.py:81-117) for x f32 [B*G, Cin], idx4 i64 [B,G,4] -> f32 [B, G, Cout]; differentiable."""
+    """DGCNN.forward (dvae.py:81-117) for x f32 [B*G, Cin], idx4 i64 [B,G,4] -> f32 [B, G, Cout]; differentiable.
+    Per edge layer: one tcgen05 GEMM (P | Q) + one fused GroupNorm / LeakyReLU / max-over-k kernel, each with its backward."""
     f = layers.linear(x, m.input_trans.weight.squeeze(-1), m.input_trans.bias)            # [BG,128]
     feats = []
     for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
         conv, gn = layer[0], layer[1]
         W = conv.weight.flatten(1)                                                         # [Cp, 2*Cin]
-        Cp, cin = W.shape[0], W.shape[1] // 2
+        cin = W.shape[1] // 2
         Wa, Wb = W[:, :cin], W[:, cin:]
-        pq = layers.linear(f, torch.cat([Wa, Wb - Wa], dim=0))                             # [BG, 2*Cp]
-        P, Q = pq[:, :Cp].view(B, G, Cp), pq[:, Cp:].view(B, G, Cp)
-        nb = torch.gather(P, 1, idx4.reshape(B, G * 4, 1).expand(-1, -1, Cp)).view(B, G, 4, Cp)
-        e = (nb + Q[:, :, None]).view(B, G * 4, Cp)
-        y = F.leaky_relu(_group_norm_rows(e, gn.weight, gn.bias, gn.eps, B), 0.2)
-        f = y.view(B, G, 4, Cp).amax(dim=2).reshape(B * G, Cp)
+        pq = layers.linear(f, torch.cat([Wa, Wb - Wa], dim=0))                             # [BG, 2*Cp] = (P | Q)
+        f = layers.DgcnnEdgeFn.apply(pq, idx4, gn.weight, gn.bias, B, G, gn.eps, 0.2)      # [BG, Cp]
         feats.append(f)
     h5 = layers.linear(torch.cat(feats, dim=1), m.layer5[0].weight.squeeze(-1))            # [BG, Cout]
     gn = m.layer5[1]
-    return F.leaky_relu(_group_norm_rows(h5.view(B, G, -1), gn.weight, gn.bias, gn.eps, B), 0.2)
+    return layers.GroupNormRowsFn.apply(h5, gn.weight, gn.bias, B, G, gn.eps, 0.2).view(B, G, -1)
 
 
 # ----------------------------------------------------------------------------------------------- Decoder
@@ -131,7 +118,9 @@ class Decoder(nn.Module):
         c0, bn0, _, c1, bn1, _, c2 = self.final_conv
         W0 = c0.weight.squeeze(-1)
         z_g = layers.linear(fg, W0[:, :c].contiguous(), c0.bias)                                        # [BG,512]
-        seed = self.folding_seed.to(fg.device)[0].t()                                      # [S,2]
+        if self.folding_seed.device != fg.device:          # a plain attribute in the reference: moved once, kept
+            self.folding_seed = self.folding_seed.to(fg.device)
+        seed = self.folding_seed[0].t()                                                    # [S,2]
         z_s = seed @ W0[:, c:c + 2].t()                                                    # [S,512]
         z_p = coarse @ W0[:, c + 2:].t()                                                   # [BG,M,512]
         z = (z_g[:, None, None, :] + z_p[:, :, None, :] + z_s[None, None]).reshape(BG * N, 512)

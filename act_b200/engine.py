@@ -97,3 +97,89 @@ class PretrainStep:
             dp.sync_gradients(self.fp)
             self.graph_b.replay()
         return self.loss
+
+
+class AutoencoderStep:
+    """The Stage-I dVAE training step (tools/runner_autoencoder.py:130-146: temp = get_temp(n_itr); ret = model(points,
+    temperature=temp, hard=False); loss_1, loss_2 = get_loss(ret, points); loss_1 + kld_weight * loss_2; backward;
+    optimizer.step; zero_grad) as one replayable CUDA graph.  The two schedules are evaluated on the host exactly like
+    the reference (dvae.get_temp / dvae.get_kld_weight) and staged into a 2-element device tensor the graph reads."""
+
+    def __init__(self, model, flat_params, batch, n_points, use_graph=True, device=None, temp_cfg=None, kld_cfg=None):
+        from . import dvae
+        self._dvae = dvae
+        self.model, self.fp = model, flat_params
+        self.dev = device or flat_params.flat.device
+        self.B, self.N = batch, n_points
+        self.points = torch.zeros(batch, n_points, 3, dtype=torch.float32, device=self.dev)
+        self.sched = torch.ones(2, dtype=torch.float32, device=self.dev)          # [temperature, kld_weight]
+        self._sched_host = torch.ones(2, dtype=torch.float32).pin_memory()
+        self.losses = torch.zeros(3, dtype=torch.float32, device=self.dev)         # [recon, klv, total]
+        self.temp_cfg = temp_cfg or dict(start=1.0, target=0.0625, ntime=100000)   # pointbert_dvae.yaml:27-30
+        self.kld_cfg = kld_cfg or dict(start=0.0, target=0.1, ntime=100000)        # pointbert_dvae.yaml:33-36
+        self.use_graph = use_graph
+        self.graph = self.graph_b = None
+        self.n_itr = 0
+        self.launches_per_step = None
+
+    def _body_a(self):
+        self.fp.zero_grad()
+        ret = self.model(self.points, temperature=self.sched[0], hard=False)
+        l1, l2 = self.model.get_loss(ret, self.points)
+        loss = l1 + self.sched[1] * l2
+        loss.backward()
+        self.losses.copy_(torch.stack([l1.detach(), l2.detach(), loss.detach()]))
+
+    def _body_b(self):
+        self.fp.step()
+
+    def _body(self):
+        self._body_a()
+        dp.sync_gradients(self.fp)
+        self._body_b()
+
+    def _host_prologue(self, points):
+        self._sched_host[0] = self._dvae.get_temp(self.n_itr, **self.temp_cfg)
+        self._sched_host[1] = self._dvae.get_kld_weight(self.n_itr, **self.kld_cfg)
+        self.sched.copy_(self._sched_host, non_blocking=True)
+        self.fp.set_hyper(grad_scale=1.0 / dp.world_size())
+        if points is not None and points.data_ptr() != self.points.data_ptr():
+            self.points.copy_(points, non_blocking=True)
+
+    def capture(self):
+        l0 = ops.LAUNCHES
+        self._host_prologue(None)
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._body()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self.launches_per_step = (ops.LAUNCHES - l0) // 2
+        if self.use_graph:
+            self.graph = torch.cuda.CUDAGraph()
+            if dp.world_size() == 1:
+                with torch.cuda.graph(self.graph):
+                    self._body()
+            else:
+                with torch.cuda.graph(self.graph):
+                    self._body_a()
+                self.graph_b = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_b, pool=self.graph.pool()):
+                    self._body_b()
+        return self
+
+    def run(self, points):
+        """One Stage-I step on `points`; returns the device tensor [loss_recon, loss_klv, loss] of this step."""
+        self._host_prologue(points)
+        self.n_itr += 1
+        if self.graph is None:
+            self._body()
+        elif self.graph_b is None:
+            self.graph.replay()
+        else:
+            self.graph.replay()
+            dp.sync_gradients(self.fp)
+            self.graph_b.replay()
+        return self.losses

@@ -477,3 +477,47 @@ class CosineLossFn(torch.autograd.Function):
 
 def cosine_loss(student, teacher):
     return CosineLossFn.apply(student, teacher)
+
+
+# ------------------------------------------------------------------------ Stage-I dVAE: trainable DGCNN layers
+class DgcnnEdgeFn(torch.autograd.Function):
+    """One DGCNN edge-conv layer after its token-level GEMM (models/dvae.py:91-93: GroupNorm(4) -> LeakyReLU(0.2) -> max
+    over the k = 4 neighbours of the conv over cat(x_k - x_q, x_q)), forward and backward fused (csrc/dgcnn_train.cu)."""
+
+    @staticmethod
+    def forward(ctx, pq, idx4, gamma, beta, B, G, eps, slope):
+        Cp = pq.shape[1] // 2
+        pq = pq.contiguous()
+        out, argj, stats = ops.dgcnn_edge_gn_train_fwd(pq, idx4, gamma, beta, B, G, Cp, eps, slope)
+        ctx.save_for_backward(pq, idx4, argj, stats, gamma, beta)
+        ctx.meta = (B, G, Cp, slope)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        pq, idx4, argj, stats, gamma, beta = ctx.saved_tensors
+        B, G, Cp, slope = ctx.meta
+        sink = _GradSink()
+        dpq = ops.dgcnn_edge_gn_train_bwd(pq, idx4, argj, stats, gamma, beta, dout, B, G, Cp, slope,
+                                          sink.get(gamma, "g"), sink.get(beta, "b"))
+        return dpq, None, sink.result("g"), sink.result("b"), None, None, None, None
+
+
+class GroupNormRowsFn(torch.autograd.Function):
+    """LeakyReLU(GroupNorm(4)(x)) over the rows of each cloud (DGCNN layer5, models/dvae.py:53-56), x f32 [B*R, C]."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, B, R, eps, slope):
+        x = x.contiguous()
+        out, stats = ops.gn_rows_train_fwd(x, gamma, beta, B, R, eps, slope)
+        ctx.save_for_backward(x, stats, gamma, beta)
+        ctx.meta = (B, R, slope)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stats, gamma, beta = ctx.saved_tensors
+        B, R, slope = ctx.meta
+        sink = _GradSink()
+        dx = ops.gn_rows_train_bwd(x, stats, gamma, beta, dy, B, R, slope, sink.get(gamma, "g"), sink.get(beta, "b"))
+        return dx, sink.result("g"), sink.result("b"), None, None, None, None

@@ -432,3 +432,49 @@ def attention_prefix_fwd(qkv_t, kv_p, B, G, P, H, scale):
     _lib.call("act_attention_prefix_fwd", qkv_t, kv_p, B, G, P, H, 64, float(scale), o)
     _count()
     return o
+
+
+# ------------------------------------------------------------------ Stage-I dVAE: trainable DGCNN layers (csrc/dgcnn_train.cu)
+def dgcnn_edge_gn_train_fwd(pq, idx4, gamma, beta, B, G, Cp, eps, slope):
+    """max_k LeakyReLU(GroupNorm(P[nbr] + Q[self])) -> (out f32 [B*G, Cp], argj u8 [B*G, Cp], stats f32 [B,4,2])."""
+    assert pq.dtype == torch.float32 and pq.is_contiguous() and pq.shape == (B * G, 2 * Cp)
+    out = torch.empty(B * G, Cp, dtype=torch.float32, device=pq.device)
+    argj = torch.empty(B * G, Cp, dtype=torch.uint8, device=pq.device)
+    stats = torch.empty(B, 4, 2, dtype=torch.float32, device=pq.device)
+    _lib.call("act_dgcnn_edge_gn_train_fwd", pq, idx4, _f32c(gamma), _f32c(beta), B, G, Cp, idx4.shape[-1], 4, float(eps),
+              float(slope), out, Cp, argj, stats)
+    _count()
+    return out, argj, stats
+
+
+def dgcnn_edge_gn_train_bwd(pq, idx4, argj, stats, gamma, beta, dout, B, G, Cp, slope, dgamma, dbeta):
+    """-> dpq f32 [B*G, 2*Cp]; dgamma / dbeta (f32 [Cp]) are accumulated into."""
+    dout = _f32c(dout)
+    dpq = torch.empty(B * G, 2 * Cp, dtype=torch.float32, device=pq.device)
+    sums = torch.empty(B, 4, 2, dtype=torch.float32, device=pq.device)
+    _lib.call("act_dgcnn_edge_gn_train_bwd", pq, idx4, argj, stats, _f32c(gamma), _f32c(beta), dout, Cp, B, G, Cp,
+              idx4.shape[-1], 4, float(slope), sums, dpq, dgamma, dbeta)
+    _count(2)
+    return dpq
+
+
+def gn_rows_train_fwd(x, gamma, beta, B, R, eps, slope):
+    """LeakyReLU(GroupNorm(4)(x)) for x f32 [B*R, C] -> (out f32, stats f32 [B,4,2])."""
+    x = _f32c(x)
+    C = x.shape[1]
+    out = torch.empty_like(x)
+    stats = torch.empty(B, 4, 2, dtype=torch.float32, device=x.device)
+    _lib.call("act_gn_rows_train_fwd", x, _f32c(gamma), _f32c(beta), B, R, C, 4, float(eps), float(slope), stats, out)
+    _count(2)
+    return out, stats
+
+
+def gn_rows_train_bwd(x, stats, gamma, beta, dy, B, R, slope, dgamma, dbeta):
+    dy = _f32c(dy)
+    C = x.shape[1]
+    dx = torch.empty_like(x)
+    sums = torch.empty(B, 4, 2, dtype=torch.float32, device=x.device)
+    _lib.call("act_gn_rows_train_bwd", x, stats, _f32c(gamma), _f32c(beta), dy, B, R, C, 4, float(slope), sums, dx,
+              dgamma, dbeta)
+    _count(2)
+    return dx

@@ -229,6 +229,35 @@ int act_vit_ln1_fwd(const float *x, const float *pos_tok, const float *tok, cons
 int act_attention_prefix_fwd(const void *qkv_t, const void *kv_p, int B, int G, int P, int H, int head_dim, float scale,
                              void *o, void *stream);
 
+/* ---- Stage-I dVAE training: trainable DGCNN layers, /root/reference/models/dvae.py:26-117 ------------
+ * The reference differentiates Conv2d 1x1 -> GroupNorm(4) -> LeakyReLU(0.2) -> max over k with autograd; these four entry
+ * points are the forward-with-saved-state and the backward of everything after the token-level GEMM. */
+
+/* act_dgcnn_edge_gn with f32 output (row pitch ldo) and the state its backward needs: argj u8 [B*G, Cp] = winning
+ * neighbour (first maximum), stats f32 [B, groups, 2] = GroupNorm (mean, rstd). */
+int act_dgcnn_edge_gn_train_fwd(const float *pq, const long long *idx, const float *gamma, const float *beta, int B,
+                                int G, int Cp, int kn, int groups, float eps, float slope, float *out, int ldo,
+                                unsigned char *argj, float *stats, void *stream);
+
+/* Backward of the above.  dout f32 [B*G, Cp] (row pitch ldd, 16-byte aligned rows) -> dpq f32 [B*G, 2*Cp] (overwritten);
+ * dgamma / dbeta f32 [Cp] are ACCUMULATED INTO (atomics); sums f32 [B, groups, 2] is scratch.
+ * Needs Cp/groups <= 256 and a multiple of 32. */
+int act_dgcnn_edge_gn_train_bwd(const float *pq, const long long *idx, const unsigned char *argj, const float *stats,
+                                const float *gamma, const float *beta, const float *dout, int ldd, int B, int G, int Cp,
+                                int kn, int groups, float slope, float *sums, float *dpq, float *dgamma, float *dbeta,
+                                void *stream);
+
+/* GroupNorm(groups) + LeakyReLU over x f32 [B*R, C] (statistics per cloud and channel group over its R rows; DGCNN layer5,
+ * dvae.py:53-56) -> out f32 [B*R, C]; stats f32 [B, groups, 2] (mean, rstd) is kept for the backward. */
+int act_gn_rows_train_fwd(const float *x, const float *gamma, const float *beta, int B, int R, int C, int groups,
+                          float eps, float slope, float *stats, float *out, void *stream);
+
+/* Backward of the above: dy f32 [B*R, C] -> dx f32 [B*R, C]; dgamma / dbeta f32 [C] are ACCUMULATED INTO; sums f32
+ * [B, groups, 2] is scratch.  C/groups must be a multiple of 128, or 64 / 32 / 16. */
+int act_gn_rows_train_bwd(const float *x, const float *stats, const float *gamma, const float *beta, const float *dy,
+                          int B, int R, int C, int groups, float slope, float *sums, float *dx, float *dgamma,
+                          float *dbeta, void *stream);
+
 /* ---- Loss and optimizer ------------------------------------------------------------------------------ */
 
 /* Cosine distillation loss of ACT_PointDistillation.forward (/root/reference/models/act.py:1243-1254):

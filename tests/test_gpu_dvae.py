@@ -173,3 +173,55 @@ def test_schedules_match_oracle():
     for n in (0, 5000, 10000, 40000, 100000, 110000, 200000):
         assert dvae.get_temp(n) == ref_dvae.temperature_schedule(n)
         assert dvae.get_kld_weight(n) == ref_dvae.kld_weight_schedule(n)
+
+
+def _torch_edge_layer(pq, idx4, gamma, beta, B, G, eps):
+    """The ATen formulation of one edge layer after its GEMM (fp32): gather, GroupNorm(4), LeakyReLU, max over k."""
+    Cp = pq.shape[1] // 2
+    P, Q = pq[:, :Cp].view(B, G, Cp), pq[:, Cp:].view(B, G, Cp)
+    nb = torch.gather(P, 1, idx4.reshape(B, G * 4, 1).expand(-1, -1, Cp)).view(B, G, 4, Cp)
+    e = (nb + Q[:, :, None]).permute(0, 3, 1, 2)                                       # B Cp G 4 (the reference layout)
+    y = torch.nn.functional.leaky_relu(torch.nn.functional.group_norm(e, 4, gamma, beta, eps), 0.2)
+    return y.max(dim=-1)[0].permute(0, 2, 1).reshape(B * G, Cp)
+
+
+@pytest.mark.parametrize("Cp", [256, 512, 1024])
+def test_dgcnn_edge_kernels_fwd_bwd_fp32(Cp):
+    """csrc/dgcnn_train.cu against the same math in ATen fp32 ops on the GPU (tight: no bf16 anywhere)."""
+    from act_b200 import layers
+    torch.manual_seed(Cp)
+    B, G = 5, 64
+    pq = torch.randn(B * G, 2 * Cp, device="cuda")
+    idx4 = torch.stack([torch.randperm(G, device="cuda")[:4] for _ in range(B * G)]).view(B, G, 4)
+    gamma, beta = 1 + 0.1 * torch.randn(Cp, device="cuda"), 0.1 * torch.randn(Cp, device="cuda")
+    w = torch.randn(B * G, Cp, device="cuda")
+    a = [t.clone().requires_grad_(True) for t in (pq, gamma, beta)]
+    want = _torch_edge_layer(a[0], idx4, a[1], a[2], B, G, 1e-5)
+    (want * w).sum().backward()
+    b = [t.clone().requires_grad_(True) for t in (pq, gamma, beta)]
+    got = layers.DgcnnEdgeFn.apply(b[0], idx4, b[1], b[2], B, G, 1e-5, 0.2)
+    (got * w).sum().backward()
+    assert rel(got, want.detach()) < 1e-5
+    for x, y in zip(b, a):
+        assert rel(x.grad, y.grad) < 2e-4, rel(x.grad, y.grad)
+
+
+@pytest.mark.parametrize("C", [256, 512, 8192])
+def test_group_norm_rows_kernels_fwd_bwd_fp32(C):
+    from act_b200 import layers
+    torch.manual_seed(C)
+    B, R = 5, 64
+    x = torch.randn(B * R, C, device="cuda") * 1.3 + 0.2
+    gamma, beta = 1 + 0.1 * torch.randn(C, device="cuda"), 0.1 * torch.randn(C, device="cuda")
+    w = torch.randn(B * R, C, device="cuda")
+    a = [t.clone().requires_grad_(True) for t in (x, gamma, beta)]
+    xr = a[0].view(B, R, C).permute(0, 2, 1)                                            # B C R (the reference layout)
+    want = torch.nn.functional.leaky_relu(torch.nn.functional.group_norm(xr, 4, a[1], a[2], 1e-5), 0.2)
+    want = want.permute(0, 2, 1).reshape(B * R, C)
+    (want * w).sum().backward()
+    b = [t.clone().requires_grad_(True) for t in (x, gamma, beta)]
+    got = layers.GroupNormRowsFn.apply(b[0], b[1], b[2], B, R, 1e-5, 0.2)
+    (got * w).sum().backward()
+    assert rel(got, want.detach()) < 1e-5
+    for p, q in zip(b, a):
+        assert rel(p.grad, q.grad) < 2e-4, rel(p.grad, q.grad)
