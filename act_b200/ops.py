@@ -478,3 +478,13 @@ def gn_rows_train_bwd(x, stats, gamma, beta, dy, B, R, slope, dgamma, dbeta):
               dgamma, dbeta)
     _count(2)
     return dx
+
+
+# ------------------------------------------------------------------------------------- input augmentation
+def scale_translate_(pc, st):
+    """In place: pc[b,n,:] = pc[b,n,:] * st[b,:3] + st[b,3:]  (data_transforms.py:20-34); pc f32 [B,N,3], st f32 [B,6]."""
+    assert pc.dtype == torch.float32 and pc.is_contiguous() and pc.dim() == 3 and pc.shape[2] == 3
+    assert st.dtype == torch.float32 and st.is_contiguous() and st.shape == (pc.shape[0], 6)
+    _lib.call("act_scale_translate", pc, st, pc.shape[0], pc.shape[1])
+    _count()
+    return pc

@@ -123,7 +123,7 @@ def _log(msg):
 def run_ours(args):
     import torch.distributed as dist
     from act_b200 import _lib, dp, layers, models, ops
-    from oracle.ref_model import synthetic_clouds          # synthetic input generator only
+    from act_b200.data import synthetic_clouds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -258,6 +258,13 @@ int act_gn_rows_train_bwd(const float *x, const float *stats, const float *gamma
                           int B, int R, int C, int groups, float slope, float *sums, float *dx, float *dgamma,
                           float *dbeta, void *stream);
 
+/* ---- Input augmentation -------------------------------------------------------------- */
+
+/* PointcloudScaleAndTranslate.__call__ (/root/reference/datasets/data_transforms.py:20-34) on the whole batch in one
+ * launch, in place: pc f32 [B,N,3];  scale_translate f32 [B,6] = per-cloud (scale xyz, translate xyz) as the reference
+ * draws them;  pc[b,n,c] = fl(fl(pc * scale[b,c]) + translate[b,c])  (bit-identical to the reference's mul then add). */
+int act_scale_translate(float *pc, const float *scale_translate, int B, int N, void *stream);
+
 /* ---- Loss and optimizer ------------------------------------------------------------------------------ */
 
 /* Cosine distillation loss of ACT_PointDistillation.forward (/root/reference/models/act.py:1243-1254):

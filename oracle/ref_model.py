@@ -256,3 +256,14 @@ def synthetic_clouds(B, N, seed=20231017):
     scale = 2.0 / 3.0 + (1.5 - 2.0 / 3.0) * torch.rand(B, 1, 3, generator=g)
     trans = -0.2 + 0.4 * torch.rand(B, 1, 3, generator=g)
     return (p * scale + trans).contiguous().float()
+
+
+def scale_and_translate(pc, scale_low=2. / 3., scale_high=3. / 2., translate_range=0.2):
+    """PointcloudScaleAndTranslate.__call__ (datasets/data_transforms.py:20-34) restated for the CPU: per cloud, numpy's
+    GLOBAL RNG draws uniform(size=3) scale then uniform(size=3) translation (float64 -> float32), and
+    pc[i] = pc[i] * scale + translation in fp32 (multiply, then add).  In place, returns pc."""
+    for i in range(pc.shape[0]):
+        xyz1 = np.random.uniform(low=scale_low, high=scale_high, size=[3])
+        xyz2 = np.random.uniform(low=-translate_range, high=translate_range, size=[3])
+        pc[i, :, 0:3] = torch.mul(pc[i, :, 0:3], torch.from_numpy(xyz1).float()) + torch.from_numpy(xyz2).float()
+    return pc
