@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import layers
-from .modules import Group, TransformerDecoder, VisableOnlyMaskTransformer, pos_mlp
+from .modules import Encoder, Group, TransformerDecoder, TransformerEncoder, VisableOnlyMaskTransformer, pos_mlp
 
 MODELS = {}
 
@@ -147,6 +147,86 @@ class ACT_PointDistillation(nn.Module):
                 teacher_feat.record_stream(fork.main)
         teacher = torch.gather(teacher_feat, 1, order[:, n_vis:, None].expand(-1, -1, student.shape[-1]))
         return layers.cosine_loss(student, teacher)
+
+
+@register
+class PointTransformer(nn.Module):
+    """models/act.py:727-910: the fine-tune / inference classifier on the hot-path kernels -- Group ->
+    mini-PointNet -> cls token + all G tokens through the Blocks -> LayerNorm -> cat(cls, max over tokens) -> head.  Same
+    constructor contract (`cls(config)` with embed_dim, depth, drop_path_rate, cls_dim, num_heads, group_size, num_group,
+    encoder_dims, transfer_type), attribute names (=> state_dict keys) and transfer-type freezing rules; trainable
+    (every piece has its backward).  The tiny [B, 2C] classification head stays on PyTorch ops."""
+
+    def __init__(self, config, **kwargs):
+        super().__init__()
+        self.config = config
+        self.embed_dim, self.depth = config.embed_dim, config.depth
+        self.drop_path_rate, self.cls_dim, self.num_heads = config.drop_path_rate, config.cls_dim, config.num_heads
+        self.group_size, self.num_group, self.encoder_dims = config.group_size, config.num_group, config.encoder_dims
+        self.group_divider = Group(num_group=self.num_group, group_size=self.group_size)
+        self.encoder = Encoder(encoder_channel=self.encoder_dims)
+        self.reduce_dim = (nn.Linear(self.encoder_dims, self.embed_dim) if self.encoder_dims != self.embed_dim
+                           else nn.Identity())
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, self.embed_dim))
+        self.cls_pos = nn.Parameter(torch.randn(1, 1, self.embed_dim))
+        self.pos_embed = nn.Sequential(nn.Linear(3, 128), nn.GELU(), nn.Linear(128, self.embed_dim))
+        dpr = [x.item() for x in torch.linspace(0, self.drop_path_rate, self.depth)]
+        self.blocks = TransformerEncoder(embed_dim=self.embed_dim, depth=self.depth, drop_path_rate=dpr,
+                                         num_heads=self.num_heads)
+        self.norm = nn.LayerNorm(self.embed_dim)
+        tt = config.transfer_type
+        if tt == 'linear':
+            self.cls_head_finetune = nn.Sequential(nn.Linear(self.embed_dim * 2, self.cls_dim))
+        else:
+            self.cls_head_finetune = nn.Sequential(
+                nn.Linear(self.embed_dim * 2, 256), nn.BatchNorm1d(256), nn.ReLU(inplace=True), nn.Dropout(0.5),
+                nn.Linear(256, 256), nn.BatchNorm1d(256), nn.ReLU(inplace=True), nn.Dropout(0.5),
+                nn.Linear(256, self.cls_dim))
+        self.loss_ce = nn.CrossEntropyLoss()
+        self.side = None
+        if tt == "side":                                            # act.py:808-814
+            self.side_alpha = nn.Parameter(torch.Tensor([0.0]))
+            self.side = Encoder(encoder_channel=self.embed_dim)
+            self.side_projection = nn.Linear(self.embed_dim, self.embed_dim, bias=False)
+        nn.init.trunc_normal_(self.cls_token, std=.02)
+        nn.init.trunc_normal_(self.cls_pos, std=.02)
+        if tt != 'full':                                            # act.py:795-806
+            for name, param in self.named_parameters():
+                if tt in ('mlp-3', 'linear'):
+                    keep = 'cls' in name
+                elif tt == 'side':
+                    keep = 'side' in name or 'cls' in name
+                elif tt == 'bit-fit':
+                    keep = 'bias' in name or 'cls' in name
+                else:
+                    keep = True
+                if not keep:
+                    param.requires_grad = False
+
+    def get_loss_acc(self, ret, gt):
+        loss = self.loss_ce(ret, gt.long())
+        pred = ret.argmax(-1)
+        acc = (pred == gt).sum() / float(gt.size(0))
+        return loss, acc * 100
+
+    def forward(self, pts):
+        neighborhood, center = self.group_divider(pts)
+        tokens = self.encoder(neighborhood)                                    # B G C
+        if not isinstance(self.reduce_dim, nn.Identity):
+            tokens = layers.linear(tokens, self.reduce_dim.weight, self.reduce_dim.bias)
+        B = tokens.shape[0]
+        x = torch.cat((self.cls_token.expand(B, -1, -1), tokens), dim=1)
+        pos = torch.cat((self.cls_pos.expand(B, -1, -1), pos_mlp(self.pos_embed, center)), dim=1)
+        x = self.blocks(x, pos)
+        x = layers.layer_norm(x, self.norm.weight, self.norm.bias, self.norm.eps)
+        if self.side is not None:
+            side = layers.linear(self.side(neighborhood), self.side_projection.weight)
+            a = torch.sigmoid(self.side_alpha)
+            side = a * x[:, 1:] + (1 - a) * side
+            concat_f = torch.cat([x[:, 0], side.max(1)[0]], dim=-1)
+        else:
+            concat_f = torch.cat([x[:, 0], x[:, 1:].max(1)[0]], dim=-1)
+        return self.cls_head_finetune(concat_f)
 
 
 def build_model_from_cfg(cfg, **kwargs):

@@ -281,6 +281,52 @@ def gen_dvae_step():
     print("dvae_step.npz recon", l1.item(), "klv", l2.item(), "n grads", len(names))
 
 
+def gen_point_transformer():
+    """the unmodified reference PointTransformer (act.py:727-910), transfer_type 'full' (mlp-3 head) and
+    'side': eval logits, and one train-mode forward/backward with cross-entropy (head dropout p set to 0 so that the run
+    is deterministic; everything else as constructed)."""
+    import models.act as act
+    res = {}
+    pts = synthetic_clouds(4, 1024, seed=29)
+    gt = torch.tensor([3, 17, 0, 39])
+    res["pts"], res["gt"] = pts.numpy(), gt.numpy()
+    for tt in ("full", "side", "linear"):
+        cfg = shims.easydict(dict(NAME="PointTransformer", embed_dim=384, depth=12, drop_path_rate=0.0, cls_dim=40,
+                                  num_heads=6, group_size=32, num_group=64, encoder_dims=384, transfer_type=tt))
+        model = fill_params(act.PointTransformer(cfg), seed=9)
+        if tt == "linear":       # the linear head has no 4-sample BatchNorm in front of the loss: a well-conditioned
+            for p_ in model.parameters():      # gradient check of the whole backbone -> un-freeze it for this run
+                p_.requires_grad = True
+        for m in model.cls_head_finetune:
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        model.eval()
+        with torch.no_grad():
+            res[tt + "/logits_eval"] = model(pts).numpy()
+        model.train()
+        ret = model(pts)
+        loss, acc = model.get_loss_acc(ret, gt)
+        loss.backward()
+        res[tt + "/logits_train"] = ret.detach().numpy()
+        res[tt + "/loss"] = np.float32(loss.item())
+        names, norms = [], []
+        for k, p in model.named_parameters():
+            if p.grad is not None:
+                names.append(k)
+                norms.append(p.grad.norm().item())
+        res[tt + "/grad_names"] = np.array(names)
+        res[tt + "/grad_norms"] = np.array(norms, np.float64)
+        last = len(model.cls_head_finetune) - 1
+        res[tt + f"/grad/cls_head_finetune.{last}.weight"] = model.cls_head_finetune[last].weight.grad.numpy()
+        res[tt + "/grad/cls_token"] = model.cls_token.grad.numpy()
+        if tt != "side":          # 'side' freezes everything without 'side' / 'cls' in its name (act.py:797-806)
+            res[tt + "/grad/blocks.blocks.0.attn.qkv.weight"] = model.blocks.blocks[0].attn.qkv.weight.grad[::16, ::8].numpy()
+        else:
+            res[tt + "/grad/side_projection.weight"] = model.side_projection.weight.grad.numpy()
+    np.savez_compressed(os.path.join(GOLD, "point_transformer.npz"), **res)
+    print("point_transformer.npz", {k: float(res[k + "/loss"]) for k in ("full", "side", "linear")})
+
+
 def main():
     if not os.path.isdir(shims.REFERENCE_ROOT):
         sys.exit("needs /root/reference (authoring container only)")
@@ -293,6 +339,7 @@ def main():
     gen_student_step()
     gen_teacher()
     gen_dvae_step()
+    gen_point_transformer()
 
 
 if __name__ == "__main__":

@@ -267,3 +267,54 @@ def scale_and_translate(pc, scale_low=2. / 3., scale_high=3. / 2., translate_ran
         xyz2 = np.random.uniform(low=-translate_range, high=translate_range, size=[3])
         pc[i, :, 0:3] = torch.mul(pc[i, :, 0:3], torch.from_numpy(xyz1).float()) + torch.from_numpy(xyz2).float()
     return pc
+
+
+class PointTransformer(nn.Module):
+    """models/act.py:727-910 (the fine-tune / inference classifier): Group -> Encoder -> cls token + all G
+    tokens through the Blocks -> LayerNorm -> cat(cls, max over tokens) -> head.  transfer_type 'linear' uses the linear
+    head, every other type the mlp-3 head (act.py:771-789); 'side' adds the side Encoder (act.py:808-814, 899-903)."""
+
+    def __init__(self, embed_dim=384, depth=12, num_heads=6, cls_dim=40, group_size=32, num_group=64, encoder_dims=384,
+                 transfer_type="full"):
+        super().__init__()
+        self.group_divider = Group(num_group, group_size)
+        self.encoder = Encoder(encoder_dims)
+        self.reduce_dim = nn.Linear(encoder_dims, embed_dim) if encoder_dims != embed_dim else nn.Identity()
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.cls_pos = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.pos_embed = nn.Sequential(nn.Linear(3, 128), nn.GELU(), nn.Linear(128, embed_dim))
+        self.blocks = TransformerEncoder(embed_dim, depth, num_heads)
+        self.norm = nn.LayerNorm(embed_dim)
+        if transfer_type == "linear":
+            self.cls_head_finetune = nn.Sequential(nn.Linear(embed_dim * 2, cls_dim))
+        else:
+            self.cls_head_finetune = nn.Sequential(
+                nn.Linear(embed_dim * 2, 256), nn.BatchNorm1d(256), nn.ReLU(inplace=True), nn.Dropout(0.5),
+                nn.Linear(256, 256), nn.BatchNorm1d(256), nn.ReLU(inplace=True), nn.Dropout(0.5), nn.Linear(256, cls_dim))
+        self.side = None
+        if transfer_type == "side":
+            self.side_alpha = nn.Parameter(torch.Tensor([0.0]))
+            self.side = Encoder(embed_dim)
+            self.side_projection = nn.Linear(embed_dim, embed_dim, bias=False)
+
+    def forward(self, pts):
+        neighborhood, center = self.group_divider(pts)
+        tokens = self.reduce_dim(self.encoder(neighborhood))
+        B = tokens.shape[0]
+        x = torch.cat((self.cls_token.expand(B, -1, -1), tokens), dim=1)
+        pos = torch.cat((self.cls_pos.expand(B, -1, -1), self.pos_embed(center)), dim=1)
+        x = self.norm(self.blocks(x, pos))
+        if self.side is not None:
+            a = torch.sigmoid(self.side_alpha)
+            side = a * x[:, 1:] + (1 - a) * self.side_projection(self.side(neighborhood))
+            f = torch.cat([x[:, 0], side.max(1)[0]], dim=-1)
+        else:
+            f = torch.cat([x[:, 0], x[:, 1:].max(1)[0]], dim=-1)
+        return self.cls_head_finetune(f)
+
+    @staticmethod
+    def get_loss_acc(ret, gt):
+        """act.py:820-824."""
+        loss = F.cross_entropy(ret, gt.long())
+        acc = (ret.argmax(-1) == gt).sum() / float(gt.size(0))
+        return loss, acc * 100
