@@ -127,6 +127,137 @@ static int launch_fps(const float *xyz, int B, int N, int G, int log2_bs, int32_
     return ACT_OK;
 }
 
+// ---- cluster-cooperative FPS: few, large clouds (the dense regime: N = 8192, G = 512, B = 16 per GPU) ----------------
+// One CTA per cloud leaves 132 of the 148 SMs idle when B = 16 and makes every one of the G-1 dependent rounds scan
+// N / T points per thread.  Here a thread-block CLUSTER of CL CTAs owns one cloud: every CTA stages the whole cloud
+// (coordinates of the last selected point are then a local shared-memory read), keeps 1/CL of the points and their
+// running min-distances in registers, and per round publishes its warps' (distance, tie-key) maxima into EVERY CTA's
+// shared memory with st.shared::cluster (distributed shared memory); one barrier.cluster arrive/wait per round (which
+// also orders the CTA's own warps) and each CTA reduces the CL * T/32 candidates with one LDS + two redux.sync.  Slots
+// are double-buffered by round parity, so one cluster barrier per round suffices.  Same tie key as above => same result
+// bit for bit, whatever the partition.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_u64(uint32_t local_addr, uint32_t cta, uint32_t lo, uint32_t hi) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(cta));
+    asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(remote), "r"(lo), "r"(hi) : "memory");
+}
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int T, int PPT, int CL>
+__global__ void __launch_bounds__(T) fps_cluster_kernel(const float *__restrict__ xyz, int N, int G, int log2_bs,
+                                                        int32_t *__restrict__ idx, float *__restrict__ center) {
+    static_assert(CL * (T / 32) <= 32, "one candidate per lane in the final reduction");
+    extern __shared__ __align__(16) float s_xyz[];  // [N][3]
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(8) uint2 s_red[2][32];     // [parity][cta * (T/32) + warp]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t rank = cluster_ctarank();
+    const int b = blockIdx.x / CL;
+    const float *p = xyz + (size_t)b * N * 3;
+    if (tid < 64) reinterpret_cast<uint2 *>(s_red)[tid] = make_uint2(0u, 0u);     // unused slots: "no candidate"
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    stage_cloud(s_xyz, p, N * 3, &s_bar, 0);
+
+    const uint32_t bs_mask = (1u << log2_bs) - 1u;
+    const int chunk = (N + CL - 1) / CL, k0 = (int)rank * chunk, k1 = min(N, k0 + chunk);
+    float px[PPT], py[PPT], pz[PPT], tmp[PPT];
+    uint32_t valid = 0;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int k = k0 + tid + j * T;
+        tmp[j] = 1e10f;
+        px[j] = py[j] = pz[j] = 0.f;
+        if (k < k1) {
+            const float x = s_xyz[k * 3 + 0], y = s_xyz[k * 3 + 1], z = s_xyz[k * 3 + 2];
+            px[j] = x; py[j] = y; pz[j] = z;
+            const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
+            if (!((double)mag <= 1e-3)) valid |= 1u << j;
+        }
+    }
+    cluster_barrier();                              // every CTA's slots are initialised before anyone stores into them
+
+    int old = 0;
+    if (rank == 0 && tid == 0) {
+        idx[(size_t)b * G] = 0;
+        if (center) {
+            float *c = center + (size_t)b * G * 3;
+            c[0] = s_xyz[0]; c[1] = s_xyz[1]; c[2] = s_xyz[2];
+        }
+    }
+    for (int g = 1; g < G; ++g) {
+        const float x1 = s_xyz[old * 3 + 0], y1 = s_xyz[old * 3 + 1], z1 = s_xyz[old * 3 + 2];
+        uint32_t bv = 0, bt = 0;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            if (valid & (1u << j)) {
+                const int k = k0 + tid + j * T;
+                const float dx = px[j] - x1, dy = py[j] - y1, dz = pz[j] - z1;
+                const float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+                const float d2 = fminf(d, tmp[j]);
+                tmp[j] = d2;
+                const uint32_t vk = __float_as_uint(d2) + 1u;
+                const uint32_t it = 0xffffffffu - ((brev_bs((uint32_t)k & bs_mask, log2_bs) << 16) | ((uint32_t)k >> log2_bs));
+                const bool better = (vk > bv) || (vk == bv && it > bt);
+                bv = better ? vk : bv;
+                bt = better ? it : bt;
+            }
+        }
+        const uint32_t wv = redux_max(bv);
+        const uint32_t wt = redux_max(bv == wv ? bt : 0u);
+        const int par = g & 1;
+        if (lane < CL)                              // lane c publishes this warp's maximum into CTA c's slot array
+            st_cluster_u64(smem_u32(&s_red[par][rank * (T / 32) + warp]), (uint32_t)lane, wv, wt);
+        cluster_barrier();
+        const uint2 r = s_red[par][lane];
+        const uint32_t mv = redux_max(r.x);
+        const uint32_t mt = redux_max(r.x == mv ? r.y : 0u);
+        const uint32_t tk = 0xffffffffu - mt;
+        old = (mv == 0) ? 0 : (int)(brev_bs(tk >> 16, log2_bs) + ((tk & 0xffffu) << log2_bs));
+        if (rank == 0 && tid == 0) {
+            idx[(size_t)b * G + g] = old;
+            if (center) {
+                float *c = center + ((size_t)b * G + g) * 3;
+                c[0] = s_xyz[old * 3 + 0]; c[1] = s_xyz[old * 3 + 1]; c[2] = s_xyz[old * 3 + 2];
+            }
+        }
+    }
+    cluster_barrier();                              // no CTA exits while a peer may still store into its shared memory
+}
+
+template <int T, int PPT, int CL>
+static int launch_fps_cluster(const float *xyz, int B, int N, int G, int log2_bs, int32_t *idx, float *center,
+                              cudaStream_t st) {
+    const size_t smem = (size_t)N * 12;
+    auto kern = fps_cluster_kernel<T, PPT, CL>;
+    if (smem > 40 * 1024) ACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B * CL);
+    cfg.blockDim = dim3(T);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ACT_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, G, log2_bs, idx, center));
+    return ACT_OK;
+}
+
 // out[b,c,m] = in[b,c,idx[b,m]]
 __global__ void gather_points_kernel(const float *__restrict__ feat, const int32_t *__restrict__ idx, int C, int N,
                                      int M, float *__restrict__ out, size_t total) {
@@ -150,6 +281,14 @@ __global__ void gather_points_grad_kernel(const float *__restrict__ gout, const 
 
 }  // namespace act
 
+static int act_fps_cluster_mode() {
+    static const int mode = [] {
+        const char *e = std::getenv("ACT_B200_FPS_CLUSTER");      // 0: one CTA per cloud everywhere; 4 / 8: cluster size (A/B)
+        return e ? std::atoi(e) : 8;
+    }();
+    return mode;
+}
+
 extern "C" int act_fps(const float *xyz, int B, int N, int G, int32_t *idx, float *center, void *stream) {
     using namespace act;
     if (!xyz || !idx || B < 0 || N <= 0 || G <= 0) return ACT_EINVAL;
@@ -158,6 +297,17 @@ extern "C" int act_fps(const float *xyz, int B, int N, int G, int32_t *idx, floa
     cudaStream_t st = (cudaStream_t)stream;
     int log2_bs = 0;
     while ((2 << log2_bs) <= N && log2_bs < 9) ++log2_bs;  // upstream opt_n_threads(N): min(512, 2^floor(log2 N))
+    // few large clouds: a cluster of 8 CTAs per cloud (distributed shared memory) instead of one CTA on one SM
+    if (act_fps_cluster_mode() == 4 && N >= 2048 && N <= 4 * 256 * 16 && B * 4 <= 148 && (N * 3) % 4 == 0) {
+        if (N <= 4 * 256 * 4) return launch_fps_cluster<256, 4, 4>(xyz, B, N, G, log2_bs, idx, center, st);
+        if (N <= 4 * 256 * 8) return launch_fps_cluster<256, 8, 4>(xyz, B, N, G, log2_bs, idx, center, st);
+        return launch_fps_cluster<256, 16, 4>(xyz, B, N, G, log2_bs, idx, center, st);
+    }
+    if (act_fps_cluster_mode() == 8 && N >= 2048 && N <= 8 * 128 * 16 && B * 8 <= 148 && (N * 3) % 4 == 0) {
+        if (N <= 8 * 128 * 4) return launch_fps_cluster<128, 4, 8>(xyz, B, N, G, log2_bs, idx, center, st);
+        if (N <= 8 * 128 * 8) return launch_fps_cluster<128, 8, 8>(xyz, B, N, G, log2_bs, idx, center, st);
+        return launch_fps_cluster<128, 16, 8>(xyz, B, N, G, log2_bs, idx, center, st);
+    }
     if (N <= 128 * 4) return launch_fps<128, 4, true>(xyz, B, N, G, log2_bs, idx, center, st);
     if (N <= 128 * 8) return launch_fps<128, 8, true>(xyz, B, N, G, log2_bs, idx, center, st);
     if (N <= 256 * 8) return launch_fps<256, 8, true>(xyz, B, N, G, log2_bs, idx, center, st);

@@ -148,3 +148,24 @@ def test_group_full_size_properties():
     d = nb.pow(2).sum(-1)
     assert (d[:, :, 1:] >= d[:, :, :-1] - 1e-6).all()
     assert all(len(set(r.tolist())) == 64 for r in fps_idx[:4].cpu())
+
+
+@pytest.mark.parametrize("B,N,G", [(16, 8192, 512), (3, 2048, 64), (18, 4096, 256), (2, 5000, 100), (1, 16384, 128)])
+def test_fps_cluster_kernel_vs_oracle(B, N, G):
+    """Few large clouds take the cluster-cooperative kernel (8 CTAs per cloud, distributed shared memory)."""
+    xyz = ref_model.synthetic_clouds(B, N, seed=N + G + B).numpy()
+    idx, center = ops.furthest_point_sample(dev(xyz), G, return_center=True)
+    want = cpu_ref.fps(xyz, G)
+    assert np.array_equal(idx.cpu().numpy(), want)
+    assert np.array_equal(center.cpu().numpy(), np.take_along_axis(xyz, want[..., None].astype(np.int64), 1))
+
+
+def test_fps_cluster_kernel_ties_and_skipped_points():
+    """Quantised coordinates (many exactly equal distances across the 8 CTAs' slices) and points within the |p|^2 <= 1e-3
+    ball (never selected, App. A.1) on the cluster path; an all-identical cloud."""
+    rng = np.random.default_rng(9)
+    xyz = (rng.integers(-6, 7, size=(3, 4096, 3)) * 0.125).astype(np.float32)
+    xyz[:, 100:140] = (rng.standard_normal((3, 40, 3)) * 0.01).astype(np.float32)
+    assert np.array_equal(ops.furthest_point_sample(dev(xyz), 200).cpu().numpy(), cpu_ref.fps(xyz, 200))
+    same = np.full((2, 2048, 3), 0.25, np.float32)
+    assert np.array_equal(ops.furthest_point_sample(dev(same), 16).cpu().numpy(), cpu_ref.fps(same, 16))
