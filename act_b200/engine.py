@@ -16,8 +16,27 @@ from .modules import mask_center_rand
 
 
 class PretrainStep:
-    def __init__(self, model, flat_params, batch, n_points, use_graph=True, device=None):
+    """pipeline (default: on when world > 1): the tokenizer and the FROZEN teacher's forward do not depend on the student's
+    weights, so step i's gradient all-reduce and AdamW are deferred to the start of step i+1, where the all-reduce runs on
+    its own stream UNDER the tokenizer and the first part of the teacher's forward -- the teacher branch (about 4 ms) is
+    longer than all-reduce + AdamW + student forward, so the collective leaves the critical path:
+        S_n : all-reduce(grad i)
+        main: [G0 Group(i+1)] ........ wait(S_n) [G3 AdamW(i)] [G2a student forward(i+1)] wait(T) [G2b loss + backward(i+1)]
+        T   :      wait(G0) [G1 teacher forward(i+1) ...................................]
+    Five graphs (forward and backward of the student are captured separately, the autograd graph spanning both); G1 has
+    its own memory pool because it replays concurrently with G3 / G2a.  Same arithmetic as the serial order (every student
+    forward sees the weights updated by all earlier steps); call flush() to apply the last pending update (before reading
+    parameters, saving a checkpoint, or switching engines)."""
+
+    def __init__(self, model, flat_params, batch, n_points, use_graph=True, device=None, pipeline=None):
+        import os
         self.model, self.fp = model, flat_params
+        if pipeline is None:
+            env = os.environ.get("ACT_B200_PIPELINE")
+            pipeline = (dp.world_size() > 1) if env is None else env == "1"
+        self.pipeline = bool(pipeline) and use_graph
+        self._pending = False
+        self._nccl_stream = None
         self.dev = device or flat_params.flat.device
         self.B, self.N = batch, n_points
         self.G = model.num_group
@@ -48,16 +67,107 @@ class PretrainStep:
         dp.sync_gradients(self.fp)                  # N>1: flat fp32 gradient all-reduce (NCCL over NVLink)
         self._body_b()
 
-    def _host_prologue(self, points):
+    # pipelined mode: the step in five graphs
+    def _body_group(self):                           # G0
+        with torch.no_grad():
+            self._nb, self._center = self.model.group_divider(self.points)
+
+    def _body_teacher(self):                         # G1: frozen teacher on G0's outputs
+        with torch.no_grad():
+            self._tfeat = self.model.teacher(self._nb, self._center)
+
+    def _body_fwd(self):                             # G2a: student forward (autograd graph kept for G2b)
+        self.fp.zero_grad()
+        self._student, self._order, self._nvis = self.model.forward_student(self._nb, self._center, self.mask)
+
+    def _body_bwd(self):                             # G2b: loss against the teacher's features + backward
+        loss = self.model.distill_loss(self._student, self._tfeat, self._order, self._nvis)
+        loss.backward()
+        self.loss.copy_(loss.detach())
+        self._student = None
+
+    def _host_prologue(self, points, hyper=True):
         m = mask_center_rand(self.B, self.G, self.mask_ratio, "cpu")
         self._mask_host.copy_(m)
         self.mask.copy_(self._mask_host, non_blocking=True)
-        self.fp.set_hyper(grad_scale=1.0 / dp.world_size())
+        if hyper:
+            self.fp.set_hyper(grad_scale=1.0 / dp.world_size())
         if points is not None and points.data_ptr() != self.points.data_ptr():
             self.points.copy_(points, non_blocking=True)       # H2D when `points` is a pinned host batch
 
+    def _capture_pipeline(self):
+        l0 = ops.LAUNCHES
+        self._host_prologue(None)
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._body_group()
+                self._body_teacher()
+                self._body_fwd()
+                self._body_bwd()
+                dp.sync_gradients(self.fp)
+                self._body_b()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self.launches_per_step = (ops.LAUNCHES - l0) // 2
+        self.graph = torch.cuda.CUDAGraph()                  # G0
+        with torch.cuda.graph(self.graph):
+            self._body_group()
+        self.graph_t = torch.cuda.CUDAGraph()                # G1: its own pool (replays concurrently with G3 / G2a)
+        with torch.cuda.graph(self.graph_t):
+            self._body_teacher()
+        self.graph_f = torch.cuda.CUDAGraph()                # G2a
+        with torch.cuda.graph(self.graph_f, pool=self.graph.pool()):
+            self._body_fwd()
+        self.graph_s = torch.cuda.CUDAGraph()                # G2b
+        with torch.cuda.graph(self.graph_s, pool=self.graph.pool()):
+            self._body_bwd()
+        self.graph_b = torch.cuda.CUDAGraph()                # G3 (replayed BEFORE G2a: not in the shared pool's order)
+        with torch.cuda.graph(self.graph_b):
+            self._body_b()
+        self._teacher_stream = torch.cuda.Stream(device=self.dev)
+        self._ev_group, self._ev_teacher = torch.cuda.Event(), torch.cuda.Event()
+        if dp.world_size() > 1:
+            self._nccl_stream = torch.cuda.Stream(device=self.dev)
+        return self
+
+    def _run_pipeline(self, points):
+        main = torch.cuda.current_stream(self.dev)
+        if self._pending and self._nccl_stream is not None:
+            self._nccl_stream.wait_stream(main)              # the previous step's backward (G2b) is complete
+            with torch.cuda.stream(self._nccl_stream):
+                dp.sync_gradients(self.fp)
+        self._host_prologue(points, hyper=False)
+        self.graph.replay()                                  # G0: tokenizer of THIS step
+        self._ev_group.record(main)
+        self._teacher_stream.wait_event(self._ev_group)
+        with torch.cuda.stream(self._teacher_stream):
+            self.graph_t.replay()                            # G1: teacher forward, beside everything up to the loss
+            self._ev_teacher.record(self._teacher_stream)
+        if self._pending:
+            if self._nccl_stream is not None:
+                main.wait_stream(self._nccl_stream)
+            self.fp.set_hyper(grad_scale=1.0 / dp.world_size())
+            self.graph_b.replay()                            # G3: AdamW of the previous step
+        self.graph_f.replay()                                # G2a
+        main.wait_event(self._ev_teacher)
+        self.graph_s.replay()                                # G2b
+        self._pending = True
+        return self.loss
+
+    def flush(self):
+        """Apply the pending update of the last step (pipelined mode); a no-op otherwise."""
+        if self._pending:
+            dp.sync_gradients(self.fp)
+            self.fp.set_hyper(grad_scale=1.0 / dp.world_size())
+            self.graph_b.replay()
+            self._pending = False
+
     def capture(self):
         """Warm up on a side stream (allocator + autotuned state), then capture the step."""
+        if self.pipeline:
+            return self._capture_pipeline()
         l0 = ops.LAUNCHES
         self._host_prologue(None)
         s = torch.cuda.Stream(device=self.dev)
@@ -87,6 +197,8 @@ class PretrainStep:
     def run(self, points):
         """One training step on `points` ([B,N,3] f32: device tensor, or pinned host tensor).  Returns the (device,
         asynchronous) loss scalar of this step."""
+        if self.pipeline:
+            return self._run_pipeline(points)
         self._host_prologue(points)
         if self.graph is None:
             self._body()

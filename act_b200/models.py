@@ -113,10 +113,12 @@ class ACT_PointDistillation(nn.Module):
             neighborhood, center = self.group_divider(pts)
             return self.ACT_encoder(neighborhood, center, only_cls_tokens=True, noaug=True)
 
-    def forward(self, pts, noaug=False, mask=None, teacher_feat=None, **kwargs):
+    def forward(self, pts, noaug=False, mask=None, teacher_feat=None, group=None, **kwargs):
+        """group (optional): a precomputed (neighborhood, center) of `pts` -- engine.PretrainStep's pipelined mode runs the
+        tokenizer and the frozen teacher ahead of the student (they do not depend on the student's weights)."""
         if noaug:
             return self.forward_eval(pts)
-        neighborhood, center = self.group_divider(pts)
+        neighborhood, center = self.group_divider(pts) if group is None else group
         # The frozen teacher's forward (act.py:1216-1217) depends only on the tokenizer's output, and the student's
         # encoder/decoder forward is a chain of small latency-bound kernels that leave most SMs idle: fork the teacher
         # onto a second stream right after the Group tokenizer and join before the loss, so inside the captured graph
@@ -130,6 +132,17 @@ class ACT_PointDistillation(nn.Module):
                 with torch.no_grad():
                     box.append(self.teacher(neighborhood, center))
             fork.run(run_teacher, neighborhood, center)
+        student, order, n_vis = self.forward_student(neighborhood, center, mask)
+        if fork is not None:
+            fork.join()
+            teacher_feat = box[0]
+            if fork.side is not None:
+                teacher_feat.record_stream(fork.main)
+        return self.distill_loss(student, teacher_feat, order, n_vis)
+
+    def forward_student(self, neighborhood, center, mask=None):
+        """The trainable half of forward() up to the projection head (act.py:1212-1228): -> (student [B,num_mask,C],
+        order [B,G] = visible groups first, n_vis).  Does not need the teacher's features."""
         x_vis, mask = self.ACT_encoder(neighborhood, center, mask=mask)
         B, n_vis, C = x_vis.shape
         G = center.shape[1]
@@ -140,11 +153,10 @@ class ACT_PointDistillation(nn.Module):
         x_full = torch.cat([x_vis, self.mask_token.expand(B, num_mask, -1)], dim=1)
         x_dec = self.ACT_decoder(x_full, pos_full, num_mask)
         student = layers.linear(x_dec, self.proj_head.weight, self.proj_head.bias)
-        if fork is not None:
-            fork.join()
-            teacher_feat = box[0]
-            if fork.side is not None:
-                teacher_feat.record_stream(fork.main)
+        return student, order, n_vis
+
+    def distill_loss(self, student, teacher_feat, order, n_vis):
+        """act.py:1229-1254: the teacher's features at the masked groups against the student's predictions."""
         teacher = torch.gather(teacher_feat, 1, order[:, n_vis:, None].expand(-1, -1, student.shape[-1]))
         return layers.cosine_loss(student, teacher)
 

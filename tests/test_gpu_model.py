@@ -215,3 +215,46 @@ def test_full_step_with_native_teacher_graph_replay():
         if v.dtype.is_floating_point and "running_" not in k and "num_batches" not in k:
             assert torch.equal(v, t_before[k]), k                 # frozen (BatchNorm running stats move: train mode)
     assert all(p.grad is None for p in model.dvae_tokenizer.parameters())
+
+
+def test_engine_pipelined_mode_matches_serial():
+    """engine.PretrainStep(pipeline=True) -- tokenizer + teacher ahead of the student, the previous step's all-reduce /
+    AdamW deferred under them (the N>1 schedule) -- computes the same losses as the serial single-graph step, and flush()
+    applies the last pending update."""
+    from act_b200.engine import PretrainStep
+
+    def run(pipeline):
+        torch.manual_seed(0)
+        np.random.seed(0)
+        cfg = models.default_config(mask_ratio=0.6, drop_path_rate=0.0)
+        model = ref_model.fill_params(models.ACT_PointDistillation(cfg), seed=3).cuda().train()
+        fp = layers.FlatParams(model, lr=1e-3, exclude=model.UNUSED_PARAMETERS)
+        eng = PretrainStep(model, fp, 8, 1024, pipeline=pipeline).capture()
+        assert eng.pipeline == pipeline
+        pts = ref_model.synthetic_clouds(8, 1024, seed=1)
+        out = [eng.run(pts.pin_memory() if i % 2 else pts.cuda()).item() for i in range(6)]
+        eng.flush()
+        torch.cuda.synchronize()
+        return out, fp.flat.clone(), fp.step_count
+
+    serial, w_s, n_s = run(False)
+    piped, w_p, n_p = run(True)
+    assert n_s == n_p                                               # as many AdamW updates (warm-up included)
+    np.testing.assert_allclose(piped[:2], serial[:2], rtol=1e-3)
+    np.testing.assert_allclose(piped, serial, rtol=0.15)            # float-atomic noise amplified by Adam, as above
+    assert ((w_p - w_s).norm() / w_s.norm()).item() < 2e-2
+
+
+def test_engine_pipelined_mode_with_native_teacher():
+    from act_b200.engine import PretrainStep
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = models.ACT_PointDistillation(models.default_config(0.6, 0.1), teacher="native").cuda().train()
+    fp = layers.FlatParams(model, lr=1e-3, weight_decay=0.05, exclude=model.UNUSED_PARAMETERS)
+    eng = PretrainStep(model, fp, 8, 1024, pipeline=True).capture()
+    pts = ref_model.synthetic_clouds(8, 1024, seed=5).cuda()
+    w_before = model.proj_head.weight.detach().clone()
+    losses = [eng.run(pts).item() for _ in range(4)]
+    eng.flush()
+    assert all(np.isfinite(l) and 0.0 < l < 2.0 for l in losses), losses
+    assert len(set(losses)) > 1 and not torch.equal(model.proj_head.weight.detach(), w_before)
