@@ -8,7 +8,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from act_b200 import ops  # noqa: E402
-from oracle.ref_model import synthetic_clouds  # noqa: E402  (bench harness only)
+from act_b200.data import synthetic_clouds  # noqa: E402
 
 PEAKS = {"hbm_gbs": 6541.5, "bf16_tflops": 1639.0}
 try:

@@ -3,15 +3,15 @@ import os, sys
 import torch
 from torch.profiler import profile, ProfilerActivity
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from act_b200 import dvae, engine, layers
+from act_b200 import data, dvae, engine, layers
 from act_b200.models import Cfg
-from oracle import ref_model
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 cfg = Cfg(NAME="DiscreteVAE", group_size=32, num_group=64, num_tokens=8192, encoder_dims=256, tokens_dims=256, decoder_dims=256)
-model = ref_model.fill_params(dvae.DiscreteVAE(cfg), seed=8).cuda().train()
+torch.manual_seed(0)
+model = dvae.DiscreteVAE(cfg).cuda().train()
 fp = layers.FlatParams(model, lr=5e-4, weight_decay=5e-4)
 step = engine.AutoencoderStep(model, fp, B, 1024, use_graph=False).capture()
-pts = ref_model.synthetic_clouds(B, 1024, seed=1).cuda()
+pts = data.synthetic_clouds(B, 1024, seed=1).cuda()
 for _ in range(2):
     step.run(pts)
 torch.cuda.synchronize()

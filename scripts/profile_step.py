@@ -9,7 +9,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from act_b200 import layers, models  # noqa: E402
-from oracle.ref_model import synthetic_clouds  # noqa: E402  (input generator)
+from act_b200.data import synthetic_clouds  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 128
