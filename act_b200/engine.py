@@ -17,16 +17,19 @@ from .modules import mask_center_rand
 
 class PretrainStep:
     """pipeline (default: on when world > 1): the tokenizer and the FROZEN teacher's forward do not depend on the student's
-    weights, so step i's gradient all-reduce and AdamW are deferred to the start of step i+1, where the all-reduce runs on
-    its own stream UNDER the tokenizer and the first part of the teacher's forward -- the teacher branch (about 4 ms) is
-    longer than all-reduce + AdamW + student forward, so the collective leaves the critical path:
-        S_n : all-reduce(grad i)
-        main: [G0 Group(i+1)] ........ wait(S_n) [G3 AdamW(i)] [G2a student forward(i+1)] wait(T) [G2b loss + backward(i+1)]
-        T   :      wait(G0) [G1 teacher forward(i+1) ...................................]
-    Five graphs (forward and backward of the student are captured separately, the autograd graph spanning both); G1 has
-    its own memory pool because it replays concurrently with G3 / G2a.  Same arithmetic as the serial order (every student
-    forward sees the weights updated by all earlier steps); call flush() to apply the last pending update (before reading
-    parameters, saving a checkpoint, or switching engines)."""
+    weights, so (1) step i's gradient all-reduce and AdamW are deferred to the start of step i+1, where the all-reduce runs
+    on its own stream beside the teacher branch, and (2) with `run(points, next_points=...)` the tokenizer + teacher forward
+    of step i+1 are issued on the teacher stream at the START of step i (software pipelining across steps: the teacher's
+    large GEMMs fill the SMs that the student's small latency-bound kernels -- forward AND backward -- leave idle):
+        S_n : all-reduce(grad i-1)
+        main: copy(nb, center, tfeat <- next) . wait(S_n) [G3 AdamW(i-1)] [G2a student forward(i)] [G2b loss + backward(i)]
+        T   :   wait(copy) [H2D points(i+1)] [G0 Group(i+1)] [G1 teacher forward(i+1) ........................]
+    Without next_points the teacher of step i is issued at the start of step i and joined before the loss (G2a overlaps it).
+    Five graphs (forward and backward of the student are captured separately, the autograd graph spanning both); G0 / G1
+    write a "next" buffer set from their own memory pool because they replay concurrently with G3 / G2a / G2b, which read
+    the "current" set.  Same arithmetic as the serial order (every student forward sees the weights updated by all earlier
+    steps, every loss the teacher features of its own batch); call flush() to apply the last pending update (before
+    reading parameters, saving a checkpoint, or switching engines)."""
 
     def __init__(self, model, flat_params, batch, n_points, use_graph=True, device=None, pipeline=None):
         import os
@@ -36,6 +39,7 @@ class PretrainStep:
             pipeline = (dp.world_size() > 1) if env is None else env == "1"
         self.pipeline = bool(pipeline) and use_graph
         self._pending = False
+        self._prefetched = None                              # data_ptr of the batch whose teacher forward is in flight
         self._nccl_stream = None
         self.dev = device or flat_params.flat.device
         self.B, self.N = batch, n_points
@@ -68,13 +72,13 @@ class PretrainStep:
         self._body_b()
 
     # pipelined mode: the step in five graphs
-    def _body_group(self):                           # G0
+    def _body_group(self):                           # G0 -> the "next" neighbourhoods / centres
         with torch.no_grad():
-            self._nb, self._center = self.model.group_divider(self.points)
+            self._nb_n, self._center_n = self.model.group_divider(self.points)
 
-    def _body_teacher(self):                         # G1: frozen teacher on G0's outputs
+    def _body_teacher(self):                         # G1: frozen teacher on G0's outputs -> the "next" features
         with torch.no_grad():
-            self._tfeat = self.model.teacher(self._nb, self._center)
+            self._tfeat_n = self.model.teacher(self._nb_n, self._center_n)
 
     def _body_fwd(self):                             # G2a: student forward (autograd graph kept for G2b)
         self.fp.zero_grad()
@@ -104,6 +108,7 @@ class PretrainStep:
             for _ in range(2):
                 self._body_group()
                 self._body_teacher()
+                self._nb, self._center, self._tfeat = self._nb_n.clone(), self._center_n.clone(), self._tfeat_n.clone()
                 self._body_fwd()
                 self._body_bwd()
                 dp.sync_gradients(self.fp)
@@ -111,47 +116,73 @@ class PretrainStep:
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
         self.launches_per_step = (ops.LAUNCHES - l0) // 2
-        self.graph = torch.cuda.CUDAGraph()                  # G0
-        with torch.cuda.graph(self.graph):
+        self.graph = torch.cuda.CUDAGraph()                  # G0 \ the teacher stream's graphs share one pool of their own:
+        with torch.cuda.graph(self.graph):                   #    } they replay concurrently with the main stream's
             self._body_group()
-        self.graph_t = torch.cuda.CUDAGraph()                # G1: its own pool (replays concurrently with G3 / G2a)
-        with torch.cuda.graph(self.graph_t):
+        self.graph_t = torch.cuda.CUDAGraph()                # G1 /
+        with torch.cuda.graph(self.graph_t, pool=self.graph.pool()):
             self._body_teacher()
         self.graph_f = torch.cuda.CUDAGraph()                # G2a
-        with torch.cuda.graph(self.graph_f, pool=self.graph.pool()):
+        with torch.cuda.graph(self.graph_f):
             self._body_fwd()
         self.graph_s = torch.cuda.CUDAGraph()                # G2b
-        with torch.cuda.graph(self.graph_s, pool=self.graph.pool()):
+        with torch.cuda.graph(self.graph_s, pool=self.graph_f.pool()):
             self._body_bwd()
         self.graph_b = torch.cuda.CUDAGraph()                # G3 (replayed BEFORE G2a: not in the shared pool's order)
         with torch.cuda.graph(self.graph_b):
             self._body_b()
         self._teacher_stream = torch.cuda.Stream(device=self.dev)
-        self._ev_group, self._ev_teacher = torch.cuda.Event(), torch.cuda.Event()
+        self._ev_group, self._ev_teacher, self._ev_copied = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        self._ev_copied.record(torch.cuda.current_stream(self.dev))
         if dp.world_size() > 1:
             self._nccl_stream = torch.cuda.Stream(device=self.dev)
         return self
 
-    def _run_pipeline(self, points):
+    def _enqueue_teacher(self, points):
+        """Tokenizer + frozen teacher of `points` on the teacher stream, into the "next" buffer set."""
+        T = self._teacher_stream
+        T.wait_event(self._ev_copied)                        # the previous contents have been copied out
+        with torch.cuda.stream(T):
+            if points.data_ptr() != self.points.data_ptr():
+                self.points.copy_(points, non_blocking=True)  # H2D when `points` is a pinned host batch
+            self.graph.replay()                              # G0
+            self._ev_group.record(T)
+            self.graph_t.replay()                            # G1
+            self._ev_teacher.record(T)
+
+    def _run_pipeline(self, points, next_points=None):
         main = torch.cuda.current_stream(self.dev)
         if self._pending and self._nccl_stream is not None:
             self._nccl_stream.wait_stream(main)              # the previous step's backward (G2b) is complete
             with torch.cuda.stream(self._nccl_stream):
                 dp.sync_gradients(self.fp)
-        self._host_prologue(points, hyper=False)
-        self.graph.replay()                                  # G0: tokenizer of THIS step
-        self._ev_group.record(main)
-        self._teacher_stream.wait_event(self._ev_group)
-        with torch.cuda.stream(self._teacher_stream):
-            self.graph_t.replay()                            # G1: teacher forward, beside everything up to the loss
-            self._ev_teacher.record(self._teacher_stream)
+        self._host_prologue(None, hyper=False)               # this step's mask
+        # tokenizer + teacher of THIS batch were issued a step ago (a different batch than announced: start over)
+        ahead = self._prefetched is not None and self._prefetched == points.data_ptr()
+        if not ahead:
+            self._enqueue_teacher(points)
+        main.wait_event(self._ev_group)
+        self._nb.copy_(self._nb_n)
+        self._center.copy_(self._center_n)
+        if ahead:
+            main.wait_event(self._ev_teacher)
+            self._tfeat.copy_(self._tfeat_n)
+            self._ev_copied.record(main)
+            if next_points is not None:
+                self._enqueue_teacher(next_points)           # runs beside this step's AdamW / forward / backward
         if self._pending:
             if self._nccl_stream is not None:
                 main.wait_stream(self._nccl_stream)
             self.fp.set_hyper(grad_scale=1.0 / dp.world_size())
             self.graph_b.replay()                            # G3: AdamW of the previous step
         self.graph_f.replay()                                # G2a
-        main.wait_event(self._ev_teacher)
+        if not ahead:
+            main.wait_event(self._ev_teacher)                # teacher of this step: joined only before the loss
+            self._tfeat.copy_(self._tfeat_n)
+            self._ev_copied.record(main)
+            if next_points is not None:
+                self._enqueue_teacher(next_points)
+        self._prefetched = next_points.data_ptr() if next_points is not None else None
         self.graph_s.replay()                                # G2b
         self._pending = True
         return self.loss
@@ -194,11 +225,12 @@ class PretrainStep:
                     self._body_b()
         return self
 
-    def run(self, points):
+    def run(self, points, next_points=None):
         """One training step on `points` ([B,N,3] f32: device tensor, or pinned host tensor).  Returns the (device,
-        asynchronous) loss scalar of this step."""
+        asynchronous) loss scalar of this step.  next_points (pipelined mode): the batch of the NEXT call -- its tokenizer
+        and teacher forward are issued now, beside this step's student work; the next call must then pass that batch."""
         if self.pipeline:
-            return self._run_pipeline(points)
+            return self._run_pipeline(points, next_points)
         self._host_prologue(points)
         if self.graph is None:
             self._body()

@@ -155,8 +155,8 @@ def run_ours(args):
     eng = PretrainStep(model, fp, B, N_POINTS, use_graph=not args.no_graph, device=dev).capture()
     _log("captured")
 
-    def step(points):                                        # batch already resident in HBM
-        return eng.run(points)
+    def step(i):                                             # batch already resident in HBM
+        return eng.run(resident[i % n_batches])
 
     def step_e2e(i):
         loss = eng.run(host[i % n_batches])                  # pinned HOST batch: H2D inside the timed region
@@ -188,7 +188,7 @@ def run_ours(args):
         return t.item() / K, wall
 
     for i in range(args.warmup):
-        step(resident[i % n_batches])
+        step(i)
     for i in range(max(1, args.warmup // 2)):
         step_e2e(i)
     barrier()
@@ -196,7 +196,7 @@ def run_ours(args):
     _log("warm-up done")
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = ops.LAUNCHES
-    ms_step, wall = timed(lambda i: step(resident[i % n_batches]), args.steps)
+    ms_step, wall = timed(step, args.steps)
     launches = eng.launches_per_step
     ms_e2e, _ = timed(step_e2e, args.steps)
     _log("timed regions done")

@@ -223,7 +223,7 @@ def test_engine_pipelined_mode_matches_serial():
     applies the last pending update."""
     from act_b200.engine import PretrainStep
 
-    def run(pipeline):
+    def run(pipeline, lookahead=False):
         torch.manual_seed(0)
         np.random.seed(0)
         cfg = models.default_config(mask_ratio=0.6, drop_path_rate=0.0)
@@ -231,18 +231,21 @@ def test_engine_pipelined_mode_matches_serial():
         fp = layers.FlatParams(model, lr=1e-3, exclude=model.UNUSED_PARAMETERS)
         eng = PretrainStep(model, fp, 8, 1024, pipeline=pipeline).capture()
         assert eng.pipeline == pipeline
-        pts = ref_model.synthetic_clouds(8, 1024, seed=1)
-        out = [eng.run(pts.pin_memory() if i % 2 else pts.cuda()).item() for i in range(6)]
+        # two DIFFERENT batches, alternating device / pinned host: a loss must belong to its own batch's teacher features
+        b0, b1 = ref_model.synthetic_clouds(8, 1024, seed=1).cuda(), ref_model.synthetic_clouds(8, 1024, seed=2).pin_memory()
+        seq = [b0, b1, b0, b1, b0, b1, b0]
+        out = [eng.run(seq[i], next_points=seq[i + 1] if lookahead else None).item() for i in range(6)]
         eng.flush()
         torch.cuda.synchronize()
         return out, fp.flat.clone(), fp.step_count
 
     serial, w_s, n_s = run(False)
-    piped, w_p, n_p = run(True)
-    assert n_s == n_p                                               # as many AdamW updates (warm-up included)
-    np.testing.assert_allclose(piped[:2], serial[:2], rtol=1e-3)
-    np.testing.assert_allclose(piped, serial, rtol=0.15)            # float-atomic noise amplified by Adam, as above
-    assert ((w_p - w_s).norm() / w_s.norm()).item() < 2e-2
+    for look in (False, True):
+        piped, w_p, n_p = run(True, look)
+        assert n_s == n_p                                           # as many AdamW updates (warm-up included)
+        np.testing.assert_allclose(piped[:2], serial[:2], rtol=1e-3)
+        np.testing.assert_allclose(piped, serial, rtol=0.15)        # float-atomic noise amplified by Adam, as above
+        assert ((w_p - w_s).norm() / w_s.norm()).item() < 2e-2
 
 
 def test_engine_pipelined_mode_with_native_teacher():
@@ -254,7 +257,7 @@ def test_engine_pipelined_mode_with_native_teacher():
     eng = PretrainStep(model, fp, 8, 1024, pipeline=True).capture()
     pts = ref_model.synthetic_clouds(8, 1024, seed=5).cuda()
     w_before = model.proj_head.weight.detach().clone()
-    losses = [eng.run(pts).item() for _ in range(4)]
+    losses = [eng.run(pts, next_points=pts).item() for _ in range(4)]
     eng.flush()
     assert all(np.isfinite(l) and 0.0 < l < 2.0 for l in losses), losses
     assert len(set(losses)) > 1 and not torch.equal(model.proj_head.weight.detach(), w_before)
