@@ -8,7 +8,6 @@ graph (two graphs around the NCCL gradient all-reduce when N>1) (CUDA streams an
 random mask exactly as the reference does (numpy RNG, act.py:244-267) into a pinned buffer, (b) stages the AdamW
 scalars, (c) copies the batch into the graph's static input, (d) launches the graph.  Nothing synchronises.
 """
-import numpy as np
 import torch
 
 from . import dp, ops

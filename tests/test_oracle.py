@@ -147,3 +147,31 @@ def test_state_dict_keys_match_real_reference():
     te = act.TransformerEncoder(embed_dim=384, depth=2, num_heads=6, drop_path_rate=[0.0, 0.0])
     assert {k: tuple(v.shape) for k, v in te.state_dict().items()} == \
         {k: tuple(v.shape) for k, v in ref_model.TransformerEncoder(384, 2, 6).state_dict().items()}
+
+
+def test_product_stage1_and_finetune_modules_have_the_oracle_state_dict():
+    """act_b200.dvae.DiscreteVAE / act_b200.models.PointTransformer (constructed on the CPU: parameters only) carry the
+    same state_dict keys and shapes as the oracle restatements, which tests/test_oracle_dvae.py and
+    tests/test_point_transformer.py pin to the unmodified reference classes."""
+    from act_b200 import dvae, models
+    from oracle import ref_dvae, ref_model
+
+    def shapes(m):
+        return {k: tuple(v.shape) for k, v in m.state_dict().items()}
+
+    cfg = models.Cfg(NAME="DiscreteVAE", group_size=32, num_group=64, num_tokens=8192, encoder_dims=256, tokens_dims=256,
+                     decoder_dims=256)
+    assert shapes(dvae.DiscreteVAE(cfg)) == shapes(ref_dvae.DiscreteVAE())
+    assert models.MODELS["DiscreteVAE"] is dvae.DiscreteVAE
+    for tt in ("full", "linear", "side"):
+        pc = models.Cfg(NAME="PointTransformer", embed_dim=384, depth=12, drop_path_rate=0.1, cls_dim=40, num_heads=6,
+                        group_size=32, num_group=64, encoder_dims=384, transfer_type=tt)
+        assert shapes(models.PointTransformer(pc)) == shapes(ref_model.PointTransformer(transfer_type=tt))
+
+
+def test_stage1_schedules_product_equals_oracle():
+    from act_b200 import dvae
+    from oracle import ref_dvae
+    for n in (0, 1, 9999, 10000, 10001, 55000, 100000, 100001, 110000, 110001, 10 ** 6):
+        assert dvae.get_temp(n) == ref_dvae.temperature_schedule(n)
+        assert dvae.get_kld_weight(n) == ref_dvae.kld_weight_schedule(n)
