@@ -18,7 +18,6 @@ class PointcloudScaleAndTranslate(object):
         self.scale_low = scale_low
         self.scale_high = scale_high
         self.translate_range = translate_range
-        self._host = None
 
     def draw(self, bsize):
         """The reference's RNG consumption (data_transforms.py:28-30) -> float32 [B,6] (scale xyz | translate xyz)."""
@@ -30,10 +29,8 @@ class PointcloudScaleAndTranslate(object):
 
     def __call__(self, pc):
         bsize = pc.size()[0]
-        if self._host is None or self._host.shape[0] != bsize:
-            self._host = torch.empty(bsize, 6, dtype=torch.float32).pin_memory()
-        self._host.copy_(torch.from_numpy(self.draw(bsize)))
-        st = self._host.to(pc.device, non_blocking=True)
+        # fresh pinned staging per call (recycled by torch's host allocator only after the async copy has completed)
+        st = torch.from_numpy(self.draw(bsize)).pin_memory().to(pc.device, non_blocking=True)
         if pc.shape[2] == 3 and pc.is_contiguous():
             return ops.scale_translate_(pc, st)
         xyz = pc[:, :, 0:3].contiguous()                      # clouds with extra channels: transform the xyz columns

@@ -46,7 +46,6 @@ class PretrainStep:
         self.mask_ratio = model.mask_ratio
         self.points = torch.zeros(batch, n_points, 3, dtype=torch.float32, device=self.dev)
         self.mask = torch.zeros(batch, self.G, dtype=torch.bool, device=self.dev)
-        self._mask_host = torch.zeros(batch, self.G, dtype=torch.bool).pin_memory()
         self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
         self.use_graph = use_graph
         self.graph = None
@@ -91,8 +90,10 @@ class PretrainStep:
 
     def _host_prologue(self, points, hyper=True):
         m = mask_center_rand(self.B, self.G, self.mask_ratio, "cpu")
-        self._mask_host.copy_(m)
-        self.mask.copy_(self._mask_host, non_blocking=True)
+        # a FRESH pinned staging tensor per step: the host runs many replays ahead of the GPU, and a reused staging buffer
+        # would be overwritten before its asynchronous copy has executed (torch's caching host allocator recycles a
+        # pinned block only after the copies recorded on it have completed)
+        self.mask.copy_(m.pin_memory(), non_blocking=True)
         if hyper:
             self.fp.set_hyper(grad_scale=1.0 / dp.world_size())
         if points is not None and points.data_ptr() != self.points.data_ptr():
@@ -256,7 +257,6 @@ class AutoencoderStep:
         self.B, self.N = batch, n_points
         self.points = torch.zeros(batch, n_points, 3, dtype=torch.float32, device=self.dev)
         self.sched = torch.ones(2, dtype=torch.float32, device=self.dev)          # [temperature, kld_weight]
-        self._sched_host = torch.ones(2, dtype=torch.float32).pin_memory()
         self.losses = torch.zeros(3, dtype=torch.float32, device=self.dev)         # [recon, klv, total]
         self.temp_cfg = temp_cfg or dict(start=1.0, target=0.0625, ntime=100000)   # pointbert_dvae.yaml:27-30
         self.kld_cfg = kld_cfg or dict(start=0.0, target=0.1, ntime=100000)        # pointbert_dvae.yaml:33-36
@@ -282,9 +282,9 @@ class AutoencoderStep:
         self._body_b()
 
     def _host_prologue(self, points):
-        self._sched_host[0] = self._dvae.get_temp(self.n_itr, **self.temp_cfg)
-        self._sched_host[1] = self._dvae.get_kld_weight(self.n_itr, **self.kld_cfg)
-        self.sched.copy_(self._sched_host, non_blocking=True)
+        sched = torch.tensor([self._dvae.get_temp(self.n_itr, **self.temp_cfg),
+                              self._dvae.get_kld_weight(self.n_itr, **self.kld_cfg)], dtype=torch.float32)
+        self.sched.copy_(sched.pin_memory(), non_blocking=True)      # fresh pinned staging per step (see PretrainStep)
         self.fp.set_hyper(grad_scale=1.0 / dp.world_size())
         if points is not None and points.data_ptr() != self.points.data_ptr():
             self.points.copy_(points, non_blocking=True)

@@ -134,7 +134,6 @@ class FlatParams:
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.step_count = 0
         self.hyper = torch.zeros(8, dtype=torch.float32, device=dev)
-        self._hyper_host = torch.zeros(8, dtype=torch.float32).pin_memory() if dev.type == "cuda" else None
 
     def refresh_shadow(self):
         """After loading a state_dict (which writes through the fp32 views)."""
@@ -149,8 +148,10 @@ class FlatParams:
         t = self.step_count
         vals = [self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 - self.betas[0] ** t,
                 1.0 - self.betas[1] ** t, grad_scale]
-        self._hyper_host.copy_(torch.tensor(vals, dtype=torch.float32))
-        self.hyper.copy_(self._hyper_host, non_blocking=True)
+        host = torch.tensor(vals, dtype=torch.float32)
+        if self.hyper.is_cuda:       # fresh pinned staging per step: the host may run many steps ahead of the GPU
+            host = host.pin_memory()
+        self.hyper.copy_(host, non_blocking=True)
 
     def step(self):
         """One fused AdamW launch over the flat buffers (hyper-parameters read from device memory)."""
