@@ -76,3 +76,30 @@ def test_dvae_state_dict_keys_match_real_reference():
     a = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
     b = {k: tuple(v.shape) for k, v in ref_dvae.DiscreteVAE().state_dict().items()}
     assert a == b, (set(a) ^ set(b))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="authoring container only")
+def test_dvae_restatement_eval_hard_path_matches_real_reference():
+    """runner_autoencoder.py:240 (`base_model(inp=points, hard=True, eval=True)`): eval-mode BatchNorm, straight-through
+    one-hot.  The oracle restatement against the unmodified reference class on other clouds and another temperature."""
+    from oracle import shims
+    shims.install()
+    import models.dvae as dvae
+    cfg = shims.easydict(dict(NAME="DiscreteVAE", group_size=32, num_group=64, num_tokens=8192, encoder_dims=256,
+                              tokens_dims=256, decoder_dims=256))
+    torch.set_num_threads(8)
+    ref = ref_model.fill_params(dvae.DiscreteVAE(cfg), seed=3).eval()
+    mine = ref_model.fill_params(ref_dvae.DiscreteVAE(), seed=3).eval()
+    pts = ref_model.synthetic_clouds(2, 1024, seed=77)
+    gum = torch.from_numpy(np.random.default_rng(5).gumbel(size=(2, 64, 8192)).astype(np.float32))
+    orig = dvae.F.gumbel_softmax
+    dvae.F.gumbel_softmax = lambda logits, tau=1.0, hard=False, dim=-1: ref_dvae.gumbel_softmax_with_noise(logits, gum, tau, hard)
+    try:
+        with torch.no_grad():
+            want = ref(inp=pts, temperature=0.5, hard=True, eval=True)
+    finally:
+        dvae.F.gumbel_softmax = orig
+    with torch.no_grad():
+        got = mine(pts, temperature=0.5, hard=True, gumbel=gum, eval=True)
+    for a, b in zip(got, want):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-3, atol=1e-4)
