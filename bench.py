@@ -337,7 +337,7 @@ def cpu_student_step_time(batch, steps, warmup, threads, teacher="native"):
         for p in tnet.parameters():
             p.requires_grad = False
     tfeat = torch.randn(batch, N_GROUP, 384)
-    times = []
+    times, phases = [], {"group_teacher": 0.0, "student_forward": 0.0, "backward": 0.0, "adamw": 0.0}
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
@@ -345,12 +345,18 @@ def cpu_student_step_time(batch, steps, warmup, threads, teacher="native"):
             with torch.no_grad():
                 nb, center = model.group_divider(pts)
                 tfeat = tnet.forward_tokenizer_features(nb, center, return_global=True)
+        t1 = time.perf_counter()
         loss = model(pts, tfeat)
+        t2 = time.perf_counter()
         loss.backward()
+        t3 = time.perf_counter()
         opt.step()
-        dt = time.perf_counter() - t0
+        t4 = time.perf_counter()
         if i >= warmup:
-            times.append(dt)
+            times.append(t4 - t0)
+            for k, v in zip(phases, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+                phases[k] += v * 1e3 / steps
+    cpu_student_step_time.last_phases_ms = {k: round(v, 1) for k, v in phases.items()}
     return sum(times) / len(times)
 
 
@@ -358,6 +364,7 @@ def cpu_baseline(sample_batch=8, steps=1, teacher="native"):
     threads = os.cpu_count() or 1
     t = cpu_student_step_time(sample_batch, steps, 1, threads, teacher)
     return {"value": round(sample_batch / t, 3), "unit": UNIT, "cores": threads, "kind": "port",
+            "phases_ms": getattr(cpu_student_step_time, "last_phases_ms", None),
             "sample": f"{steps} timed step(s) after 1 warm-up of the oracle restatement (fp32 PyTorch + C FPS/kNN) "
                       f"at batch {sample_batch} (same per-cloud workload; the full batch of 128 would take minutes)"}
 
@@ -379,6 +386,7 @@ def run_reference(args):
             "config": workload_cfg(args.batch, world, args.teacher),
             "impl": "reference",
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "phases_ms": getattr(cpu_student_step_time, "last_phases_ms", None),
                              "sample": f"{steps} timed step(s) at batch {sample} per step (bounded sample of the "
                                        f"batch-128 workload), oracle restatement of the reference path on all host "
                                        f"threads; the reference's own native ops are CUDA-only"},
