@@ -179,17 +179,19 @@ def _compiled_reference_chamfer():
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "chamfer_ref.so")
     if not os.path.exists(path):
         pytest.skip("oracle/_ref/chamfer_ref.so not built")
-    spec = importlib.util.spec_from_file_location("chamfer_ref", path)
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
+    try:
+        spec = importlib.util.spec_from_file_location("chamfer_ref", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    except (ImportError, OSError) as e:      # built against another torch / CUDA runtime than this box has
+        pytest.skip(f"oracle/_ref/chamfer_ref.so does not load here: {e}")
     return mod
 
 
-@pytest.mark.skipif(__import__("os").environ.get("ACT_TEST_REF_CHAMFER") != "1",
-                    reason="opt-in (ACT_TEST_REF_CHAMFER=1): the compiled reference kernel was built after this round's "
-                           "GPU budget was spent; it has not run on a GPU box yet")
 @pytest.mark.parametrize("B,n,m", [(4096, 8, 32), (4096, 32, 32), (1, 2048, 1024), (3, 600, 1000)])
 def test_chamfer_against_compiled_reference(B, n, m):
+    """Default-on whenever oracle/_ref/chamfer_ref.so exists (it travels with the gpurun snapshot): row a12's parity is
+    pinned against the reference's own kernel, not only against the C restatement."""
     ref = _compiled_reference_chamfer()
     rng = np.random.default_rng(B + n)
     a, b = dev(rng.standard_normal((B, n, 3)).astype(np.float32)), dev(rng.standard_normal((B, m, 3)).astype(np.float32))
