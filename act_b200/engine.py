@@ -14,6 +14,51 @@ from . import dp, ops
 from .modules import mask_center_rand
 
 
+class _StateSnapshot:
+    """Everything a warm-up step mutates, so capture() can leave the model exactly as it found it (a loaded checkpoint
+    must not be perturbed by the two eager warm-up steps the allocator / lazy initialisers need before a graph capture):
+    master weights, AdamW moments and step count, every module buffer (BatchNorm running statistics and counters of the
+    student AND of the frozen teacher), the numpy global RNG (the mask draw) and the torch CPU / CUDA generators
+    (DropPath gates, gumbel seed)."""
+
+    def __init__(self, model, fp, dev):
+        import numpy as np
+        self.np = np
+        self.model, self.fp, self.dev = model, fp, dev
+        self.flat = fp.flat.clone()
+        self.exp_avg, self.exp_avg_sq = fp.exp_avg.clone(), fp.exp_avg_sq.clone()
+        self.step_count = fp.step_count
+        mods = [model]
+        t = getattr(model, "teacher", None)
+        t = getattr(t, "__self__", t)                          # bound method of the (registered or external) teacher module
+        if isinstance(t, torch.nn.Module):
+            mods.append(t)
+        self.bufs, seen = [], set()
+        for m in mods:
+            for b in m.buffers():
+                if b.data_ptr() not in seen:
+                    seen.add(b.data_ptr())
+                    self.bufs.append((b, b.clone()))
+        self.np_state = np.random.get_state()
+        self.cpu_rng = torch.get_rng_state()
+        self.cuda_rng = torch.cuda.get_rng_state(dev)
+
+    def restore(self):
+        fp = self.fp
+        with torch.no_grad():
+            fp.flat.copy_(self.flat)
+            fp.exp_avg.copy_(self.exp_avg)
+            fp.exp_avg_sq.copy_(self.exp_avg_sq)
+            fp.step_count = self.step_count
+            fp.refresh_shadow()
+            fp.zero_grad()
+            for b, saved in self.bufs:
+                b.copy_(saved)
+        self.np.random.set_state(self.np_state)
+        torch.set_rng_state(self.cpu_rng)
+        torch.cuda.set_rng_state(self.cuda_rng, self.dev)
+
+
 class PretrainStep:
     """pipeline (default: on when world > 1): the tokenizer and the FROZEN teacher's forward do not depend on the student's
     weights, so (1) step i's gradient all-reduce and AdamW are deferred to the start of step i+1, where the all-reduce runs
@@ -38,7 +83,8 @@ class PretrainStep:
             pipeline = (dp.world_size() > 1) if env is None else env == "1"
         self.pipeline = bool(pipeline) and use_graph
         self._pending = False
-        self._prefetched = None                              # data_ptr of the batch whose teacher forward is in flight
+        self._prefetched = None                              # the announced batch (the tensor itself, kept alive) whose
+                                                             # tokenizer + teacher forward are in flight
         self._nccl_stream = None
         self.dev = device or flat_params.flat.device
         self.B, self.N = batch, n_points
@@ -101,6 +147,14 @@ class PretrainStep:
 
     def _capture_pipeline(self):
         l0 = ops.LAUNCHES
+        snap = _StateSnapshot(self.model, self.fp, self.dev)
+        # G1 replays concurrently with G3 / G2a, which draw the DropPath gates from torch's default CUDA generator: the
+        # teacher's per-call seed is therefore staged from the host (like the mask and the AdamW scalars), not drawn in G1
+        tmod = getattr(getattr(self.model, "teacher", None), "__self__", None)
+        self._tseed = None
+        if tmod is not None and hasattr(tmod, "seed_buffer"):
+            self._tseed = torch.zeros(1, dtype=torch.int64, device=self.dev)
+            tmod.seed_buffer = self._tseed
         self._host_prologue(None)
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
@@ -115,6 +169,7 @@ class PretrainStep:
                 self._body_b()
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
+        snap.restore()                                       # the warm-up leaves no trace (see capture())
         self.launches_per_step = (ops.LAUNCHES - l0) // 2
         self.graph = torch.cuda.CUDAGraph()                  # G0 \ the teacher stream's graphs share one pool of their own:
         with torch.cuda.graph(self.graph):                   #    } they replay concurrently with the main stream's
@@ -145,6 +200,8 @@ class PretrainStep:
         with torch.cuda.stream(T):
             if points.data_ptr() != self.points.data_ptr():
                 self.points.copy_(points, non_blocking=True)  # H2D when `points` is a pinned host batch
+            if self._tseed is not None:                      # fresh pinned staging per step (see _host_prologue)
+                self._tseed.copy_(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).pin_memory(), non_blocking=True)
             self.graph.replay()                              # G0
             self._ev_group.record(T)
             self.graph_t.replay()                            # G1
@@ -158,7 +215,9 @@ class PretrainStep:
                 dp.sync_gradients(self.fp)
         self._host_prologue(None, hyper=False)               # this step's mask
         # tokenizer + teacher of THIS batch were issued a step ago (a different batch than announced: start over)
-        ahead = self._prefetched is not None and self._prefetched == points.data_ptr()
+        # identity of the tensor object, not its address: the caching allocators recycle addresses, so a freed batch and a
+        # later one can share a data_ptr; the reference held in _prefetched keeps the announced batch alive meanwhile
+        ahead = self._prefetched is not None and self._prefetched is points
         if not ahead:
             self._enqueue_teacher(points)
         main.wait_event(self._ev_group)
@@ -182,7 +241,7 @@ class PretrainStep:
             self._ev_copied.record(main)
             if next_points is not None:
                 self._enqueue_teacher(next_points)
-        self._prefetched = next_points.data_ptr() if next_points is not None else None
+        self._prefetched = next_points
         self.graph_s.replay()                                # G2b
         self._pending = True
         return self.loss
@@ -195,11 +254,31 @@ class PretrainStep:
             self.graph_b.replay()
             self._pending = False
 
+
+    def checkpoint(self, epoch=0, metrics=None, best_metrics=None):
+        """The dict tools/builder.py:132-144 saves ({'base_model', 'optimizer', 'epoch', 'metrics', 'best_metrics'}), with
+        any pending pipelined update applied first (flush()), so that nothing is lost between the last step and the save;
+        `optimizer` is FlatParams.state_dict() = torch.optim.AdamW's layout."""
+        self.flush()
+        torch.cuda.synchronize(self.dev)
+        return {"base_model": self.model.state_dict(), "optimizer": self.fp.state_dict(), "epoch": epoch,
+                "metrics": metrics if metrics is not None else {}, "best_metrics": best_metrics if best_metrics is not None else {}}
+
+    def save_checkpoint(self, path, **kw):
+        torch.save(self.checkpoint(**kw), path)
+
     def capture(self):
-        """Warm up on a side stream (allocator + autotuned state), then capture the step."""
+        """Warm up on a side stream (allocator + lazily initialised state), then capture the step.  capture() leaves the
+        model, the optimizer state, every BatchNorm buffer and the RNG streams exactly as it found them: the two eager
+        warm-up steps run on the all-zero static batch and are undone (snapshot before, restore after), so a loaded
+        checkpoint is not perturbed and step counts / bias corrections start where the caller left them."""
         if self.pipeline:
             return self._capture_pipeline()
+        tmod = getattr(getattr(self.model, "teacher", None), "__self__", None)
+        if tmod is not None and hasattr(tmod, "seed_buffer"):
+            tmod.seed_buffer = None                          # single graph: the teacher's seed is drawn inside it
         l0 = ops.LAUNCHES
+        snap = _StateSnapshot(self.model, self.fp, self.dev)
         self._host_prologue(None)
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
@@ -208,8 +287,7 @@ class PretrainStep:
                 self._body()
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
-        # undo the warm-up's parameter updates? No: they are ordinary training steps on a zero batch-independent
-        # path; callers that need exact step counts capture before training starts (bench, tests do).
+        snap.restore()
         l1 = ops.LAUNCHES
         self.launches_per_step = (l1 - l0) // 2
         if self.use_graph:
@@ -289,8 +367,16 @@ class AutoencoderStep:
         if points is not None and points.data_ptr() != self.points.data_ptr():
             self.points.copy_(points, non_blocking=True)
 
+    def flush(self):
+        """Serial schedule: nothing is ever pending (kept for interface parity with PretrainStep)."""
+
+    checkpoint = PretrainStep.checkpoint
+    save_checkpoint = PretrainStep.save_checkpoint
+
     def capture(self):
+        """Same contract as PretrainStep.capture(): the warm-up steps are undone."""
         l0 = ops.LAUNCHES
+        snap = _StateSnapshot(self.model, self.fp, self.dev)
         self._host_prologue(None)
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
@@ -299,6 +385,7 @@ class AutoencoderStep:
                 self._body()
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
+        snap.restore()
         self.launches_per_step = (ops.LAUNCHES - l0) // 2
         if self.use_graph:
             self.graph = torch.cuda.CUDAGraph()

@@ -131,9 +131,80 @@ class FlatParams:
             self.params.append(p)
             self.names.append(n)
         self.shadow.copy_(self.flat)
-        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.betas, self.eps = betas, eps
         self.step_count = 0
         self.hyper = torch.zeros(8, dtype=torch.float32, device=dev)
+        self._offs = dict(zip(self.names, offs))
+        # torch.optim.AdamW's view of the same parameters, in the reference's order (tools/builder.py:38-55: group 0 =
+        # no-decay, group 1 = decay, each in named_parameters() order, every requires_grad parameter listed -- the ones
+        # excluded above included: torch keeps them in the groups and simply never creates state for them)
+        all_named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+        g_nd = [n for n, p in all_named if no_decay(n, p)]
+        g_d = [n for n, p in all_named if not no_decay(n, p)]
+        self._opt_index = {n: i for i, n in enumerate(g_nd + g_d)}
+        common = dict(lr=lr, betas=tuple(betas), eps=eps, amsgrad=False, maximize=False, foreach=None, capturable=False,
+                      differentiable=False, fused=None)
+        self.param_groups = [dict(common, weight_decay=0.0, params=[self._opt_index[n] for n in g_nd]),
+                             dict(common, weight_decay=weight_decay, params=[self._opt_index[n] for n in g_d])]
+
+    # lr / weight_decay live in param_groups, like torch.optim: an LR scheduler that writes group['lr'] (timm's
+    # CosineLRScheduler, torch.optim.lr_scheduler.*: the reference's build_opti_sche) drives this object unchanged.  The
+    # fused kernel takes ONE learning rate: both groups must carry the same one (they do in the reference).
+    @property
+    def lr(self):
+        return self.param_groups[1]["lr"]
+
+    @lr.setter
+    def lr(self, v):
+        for g in self.param_groups:
+            g["lr"] = v
+
+    @property
+    def weight_decay(self):
+        return self.param_groups[1]["weight_decay"]
+
+    @weight_decay.setter
+    def weight_decay(self, v):
+        self.param_groups[1]["weight_decay"] = v
+
+    def state_dict(self):
+        """torch.optim.AdamW.state_dict() layout ({'state': {index: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_groups':
+        [...]}) with the reference's parameter indexing, so `ckpt['optimizer']` written by tools/builder.py:132-144
+        round-trips: a reference run resumes from it and vice versa.  Call the engine's flush() first when training in
+        pipelined mode (engine.PretrainStep.save_checkpoint does)."""
+        state = {}
+        if self.step_count > 0:
+            for n, p in zip(self.names, self.params):
+                o, k = self._offs[n], p.numel()
+                state[self._opt_index[n]] = {"step": torch.tensor(float(self.step_count)),
+                                             "exp_avg": self.exp_avg[o:o + k].view(p.shape).clone(),
+                                             "exp_avg_sq": self.exp_avg_sq[o:o + k].view(p.shape).clone()}
+        return {"state": state, "param_groups": [dict(g, params=list(g["params"])) for g in self.param_groups]}
+
+    def load_state_dict(self, sd):
+        """Inverse of state_dict(); also accepts a torch.optim.AdamW state_dict of the reference's optimizer."""
+        by_index = {i: n for n, i in self._opt_index.items()}
+        steps = []
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        for idx, st in sd["state"].items():
+            n = by_index.get(int(idx))
+            if n is None or n not in self._offs:
+                continue                      # state of a parameter that is excluded here (never had a gradient)
+            o = self._offs[n]
+            k = st["exp_avg"].numel()
+            self.exp_avg[o:o + k].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.append(int(float(st["step"])))
+        if len(set(steps)) > 1:
+            raise ValueError("FlatParams keeps one step count; the loaded per-parameter steps differ")
+        self.step_count = steps[0] if steps else 0
+        for g, src in zip(self.param_groups, sd["param_groups"]):
+            for k in ("lr", "betas", "eps", "weight_decay"):
+                if k in src:
+                    g[k] = src[k]
+        self.betas, self.eps = tuple(self.param_groups[1]["betas"]), self.param_groups[1]["eps"]
+        self.refresh_shadow()
 
     def refresh_shadow(self):
         """After loading a state_dict (which writes through the fp32 views)."""
@@ -146,6 +217,8 @@ class FlatParams:
         """Stage this step's AdamW scalars (lr from the scheduler, bias corrections) into device memory."""
         self.step_count += 1
         t = self.step_count
+        if self.param_groups[0]["lr"] != self.param_groups[1]["lr"]:
+            raise ValueError("FlatParams: the fused AdamW kernel applies one learning rate to both parameter groups")
         vals = [self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, 1.0 - self.betas[0] ** t,
                 1.0 - self.betas[1] ** t, grad_scale]
         host = torch.tensor(vals, dtype=torch.float32)

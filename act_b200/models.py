@@ -2,11 +2,11 @@
 state_dict keys as the reference: /root/reference/models/act.py:1099-1258, utils/registry.py:272-285).
 
 `ACT_PointDistillation` is the Stage-II model that tools/runner_pretrain.py:139 calls as
-`loss = base_model(points)`.  The frozen Stage-I teacher (`dvae_tokenizer`, act.py:1151-1160, 1216-1217 --
-a prompt-tuned ViT-B whose pretrained weights are not obtainable offline) is SURVEY.md row f1 ("next"): it is
-pluggable here through `teacher` (any callable (neighborhood, center) -> [B,G,C] features, e.g. the reference's
-own ACTPromptedDiscreteVAEwithVIT module); the default is a deterministic synthetic target so that the student
-path can be trained / timed / parity-checked stand-alone.
+`loss = base_model(points)`.  Like the reference (act.py:1151-1160) `cls(cfg)` builds the frozen Stage-I teacher
+`dvae_tokenizer` (ACTPromptedDiscreteVAEwithVIT on the act_b200 kernels, act_b200/teacher.py), strict-loads
+`cfg.dvae_config.ckpt` into it and freezes it.  Only on explicit request is something else used: `teacher="synthetic"`
+(a deterministic parameter-free target: student-only timing / parity runs) or any callable
+(neighborhood, center) -> [B,G,C] features.
 """
 import torch
 import torch.nn as nn
@@ -75,17 +75,28 @@ class ACT_PointDistillation(nn.Module):
         self.group_size, self.num_group = dc.group_size, dc.num_group
         self.drop_path_rate = tc.drop_path_rate
         self.decoder_depth, self.decoder_num_heads = tc.decoder_depth, tc.decoder_num_heads
-        # teacher: not registered as a submodule -> not in state_dict / not trained (the reference keeps its frozen
-        # teacher under `dvae_tokenizer.*`; loading such a checkpoint needs strict=False)
-        if teacher == "native":
-            # the frozen Stage-I teacher on act_b200 kernels, under the reference's attribute name, so a Stage-II
-            # state_dict has the reference's `dvae_tokenizer.*` keys (act.py:1151-1160); frozen like the reference
+        # The tokenizer contract of the reference (act.py:1151-1160, build_tokenizer): construct the prompted dVAE + ViT
+        # teacher under the attribute name `dvae_tokenizer` (so a Stage-II state_dict has the reference's
+        # `dvae_tokenizer.*` keys), strict-load `dvae_config.ckpt`, freeze every parameter.  `teacher=None` / "native"
+        # is that default.  The reference cannot be constructed without the checkpoint file; here a missing `ckpt`
+        # (None) leaves the teacher at its initialisation -- the offline situation of the benchmark and the tests --
+        # while a path that is set but unreadable raises, as torch.load does in the reference.
+        if teacher is None or teacher == "native":
             from .teacher import ACTPromptedDiscreteVAEwithVIT
             self.dvae_tokenizer = ACTPromptedDiscreteVAEwithVIT(dc)
+            ckpt_path = dc.get("ckpt") if isinstance(dc, dict) else getattr(dc, "ckpt", None)
+            if ckpt_path:
+                ckpt = torch.load(ckpt_path, map_location="cpu")
+                base_ckpt = {k.replace("module.", ""): v for k, v in ckpt["base_model"].items()}
+                self.dvae_tokenizer.load_state_dict(base_ckpt, strict=True)
             for p in self.dvae_tokenizer.parameters():
                 p.requires_grad = False
             teacher = self.dvae_tokenizer.forward_tokenizer_features
-        object.__setattr__(self, "teacher", teacher if teacher is not None else SyntheticTeacher(dc.tokens_dims))
+        elif teacher == "synthetic":
+            teacher = SyntheticTeacher(dc.tokens_dims)
+        elif not callable(teacher):
+            raise ValueError("teacher: None / 'native' (the reference's frozen dvae_tokenizer), 'synthetic', or a callable")
+        object.__setattr__(self, "teacher", teacher)      # not a registered submodule (dvae_tokenizer above already is)
         self.group_divider = Group(num_group=self.num_group, group_size=self.group_size)
         self.proj_head = nn.Linear(self.embed_dim, dc.tokens_dims)
         if self.mask_ratio > 0.:
@@ -214,6 +225,40 @@ class PointTransformer(nn.Module):
                     keep = True
                 if not keep:
                     param.requires_grad = False
+
+    def load_model_from_ckpt(self, bert_ckpt_path, custom_loading=False):
+        """models/act.py:829-867 (what tools/runner_finetune.py calls): load a Stage-II checkpoint into the classifier --
+        strip `module.`, map `ACT_encoder.*` / `base_model.*` onto this module's keys, load non-strictly; returns the
+        incompatible-keys record the reference logs.  `None` re-initialises like the reference ("training from scratch")."""
+        if bert_ckpt_path is None:
+            self.apply(self._init_weights)
+            return None
+        ckpt = torch.load(bert_ckpt_path, map_location="cpu")
+        if custom_loading:
+            base_ckpt = {k.replace("module.point_encoder.", ""): v for k, v in ckpt['state_dict'].items()}
+            base_ckpt = {k.replace("encoder", "blocks"): v for k, v in base_ckpt.items()}
+            base_ckpt = {k.replace("patch_embed", "encoder"): v for k, v in base_ckpt.items()}
+        else:
+            base_ckpt = {k.replace("module.", ""): v for k, v in ckpt['base_model'].items()}
+        for k in list(base_ckpt.keys()):
+            if k.startswith('ACT_encoder'):
+                base_ckpt[k[len('ACT_encoder.'):]] = base_ckpt[k]
+                del base_ckpt[k]
+            elif k.startswith('base_model'):
+                base_ckpt[k[len('base_model.'):]] = base_ckpt[k]
+                del base_ckpt[k]
+        incompatible = self.load_state_dict(base_ckpt, strict=False)
+        self.last_incompatible_keys = incompatible
+        return incompatible
+
+    def _init_weights(self, m):
+        if isinstance(m, (nn.Linear, nn.Conv1d)):
+            nn.init.trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
 
     def get_loss_acc(self, ret, gt):
         loss = self.loss_ce(ret, gt.long())

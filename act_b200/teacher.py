@@ -114,6 +114,10 @@ class ACTPromptedDiscreteVAEwithVIT(nn.Module):
         for t in (self.visual_prompt_token, self.visual_prompt_pos, self.deep_prompt_tokens, self.deep_prompt_pos):
             nn.init.trunc_normal_(t, std=.02)
         self._cache = None
+        # optional device int64 [1] the caller refreshes before every call (engine.PretrainStep's pipelined mode stages it
+        # from the host): the per-call seed of the in-kernel gumbel / prompt-dropout draws is then read from it instead of
+        # being drawn from torch's default CUDA generator, whose state a CONCURRENTLY replaying graph also advances
+        self.seed_buffer = None
 
     # ---- frozen bf16 operand cache (weights never change: built once, dropped on load / device move) ----------
     def _apply(self, fn, *a, **k):
@@ -215,7 +219,9 @@ class ACTPromptedDiscreteVAEwithVIT(nn.Module):
         _, idx4, _ = ops.knn(center, center, 4, want_dist=False)                            # [B,G,4] i64
         # one graph-safe draw per call (torch's Philox state advances on every CUDA-graph replay); the kernels derive
         # the gumbel noise and the prompt-dropout masks from it on the fly
-        seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=center.device)
+        seed = self.seed_buffer
+        if seed is None:
+            seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=center.device)
         if gumbel is not None:
             gumbel = gumbel.reshape(B * G, self.num_tokens).float().contiguous()
         labels = self._dgcnn(self.dgcnn_1, c["d1"], tokens, idx4, B, G, noise=gumbel,

@@ -1,21 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- ACT Stage-II masked-point-modeling training step on B200 (BASELINE.json configs[1]/[3]).
+"""bench.py -- ACT masked-point-modeling training steps on B200 (BASELINE.json configs[1..4]).
 
-One "step" = Group tokenizer (FPS + kNN) -> mini-PointNet embed -> 12-block student encoder -> 2-block decoder
--> frozen teacher forward (mini-PointNet + DGCNN x2 + gumbel/codebook + prompted ViT-B, no grad) -> proj head ->
-cosine distillation loss -> backward -> (N>1: one NCCL all-reduce of the flat gradient) -> fused AdamW, on B=128
-synthetic ShapeNet-shaped clouds per GPU (N=1024, G=64, k=32, d=384, mask 0.6, drop_path 0.1), bf16 tensor-core
-operands / fp32 accumulation and master weights.  `--teacher synthetic` times the student-only step (SURVEY.md 8d
-config 2(i)); the default includes the teacher with random weights (config 2(ii): pretrained weights are not
-obtainable offline), and the line carries the student-only number as `student_only`.
+Headline (config 2 / 4, `--config stage2`): one "step" = Group tokenizer (FPS + kNN) -> mini-PointNet embed -> 12-block
+student encoder -> 2-block decoder -> frozen teacher forward (mini-PointNet + DGCNN x2 + gumbel/codebook + prompted
+ViT-B, no grad) -> proj head -> cosine distillation loss -> backward -> (N>1: one NCCL all-reduce of the flat gradient)
+-> fused AdamW, on B=128 synthetic ShapeNet-shaped clouds per GPU (N=1024, G=64, k=32, d=384, mask 0.6, drop_path 0.1),
+bf16 tensor-core operands / fp32 accumulation and master weights.  The same line carries, under `configs`, the other two
+GPU configs of BASELINE.json measured in the same process: `dvae` (config 3: Stage-I autoencoder step, B=64) and `dense`
+(config 5: N=8192, G=512 x k=32, T_enc=206 / T_dec=512, B=16 per GPU; student step with a synthetic target -- the
+teacher's ViT is defined for 64 tokens), and `sustained`: the headline step replayed back to back for >= 3 s.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config all|stage2|dvae|dense]
   N>1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Prints ONE JSON line (rank 0).  `value`: clouds/s with the batch already resident in HBM; `e2e`: the same step
-called with a pinned HOST batch (H2D inside the timed region, D2H of the loss).  `--impl reference` times the
-reference's path restated for the host CPU (oracle/ref_model.py + oracle/cpu_ref.c: the reference itself is
-Python + CUDA-only extensions and cannot run on the box without a GPU build), all host threads.
+Prints ONE JSON line (rank 0).  `value`: clouds/s with the batch already resident in HBM (device-timed; the wall clock
+of the same loop is reported beside it and the slower of the two is the value); `e2e`: the same step called with a pinned
+HOST batch (H2D inside the timed region, D2H of the loss).  `--impl reference` times the reference's path restated for
+the host CPU (oracle/ref_model.py + ref_teacher.py + cpu_ref.c, pinned against the unmodified reference modules in the
+authoring container): the reference itself is Python over CUDA-only extensions and its sources cannot travel to the GPU
+box, so `kind` is "port".
 """
 import argparse
 import json
@@ -33,18 +36,22 @@ sys.path.insert(0, ROOT)
 
 METRIC = "clouds_per_sec_act_stage2_step"
 UNIT = "clouds/s"
-N_POINTS, N_GROUP, GROUP_SIZE, MASK_RATIO, DROP_PATH = 1024, 64, 32, 0.6, 0.1
+MASK_RATIO, DROP_PATH = 0.6, 0.1
+SHAPES = {"stage2": dict(n_points=1024, num_group=64, group_size=32, batch=128),
+          "dense": dict(n_points=8192, num_group=512, group_size=32, batch=16),
+          "dvae": dict(n_points=1024, num_group=64, group_size=32, batch=64)}
 
 
-def workload_cfg(batch, n_gpus, teacher="native"):
+def workload_cfg(batch, n_gpus, teacher="native", shape="stage2"):
+    sh = SHAPES[shape]
     t = ("frozen teacher forward included (mini-PointNet + DGCNN x2 + gumbel/codebook + VPT-deep ViT-B x12 on 128 tokens, "
          "random weights: pretrained ones are not obtainable offline)") if teacher == "native" else \
         "synthetic teacher target (student-only step)"
-    return {"workload": "ACT Stage-II step: N=1024, G=64 x k=32, 12L d=384 + 2L decoder, mask 0.6, drop_path 0.1, "
-                        "cosine loss, fwd+bwd+AdamW; " + t, "teacher": teacher,
-            "batch_per_gpu": batch, "global_batch": batch * n_gpus, "n_points": N_POINTS, "num_group": N_GROUP,
-            "group_size": GROUP_SIZE, "depth": 12, "embed_dim": 384, "mask_ratio": MASK_RATIO,
-            "parallelism": f"dp{n_gpus}",
+    return {"workload": f"ACT Stage-II step: N={sh['n_points']}, G={sh['num_group']} x k={sh['group_size']}, 12L d=384 + "
+                        f"2L decoder, mask 0.6, drop_path 0.1, cosine loss, fwd+bwd+AdamW; " + t, "teacher": teacher,
+            "batch_per_gpu": batch, "global_batch": batch * n_gpus, "n_points": sh["n_points"],
+            "num_group": sh["num_group"], "group_size": sh["group_size"], "depth": 12, "embed_dim": 384,
+            "mask_ratio": MASK_RATIO, "parallelism": f"dp{n_gpus}",
             "l2": "per-step activation working set (~3 GB) >> 126 MB L2; an extra 256 MB L2-flush write runs "
                   "between timed steps, outside the per-step event pairs"}
 
@@ -60,13 +67,14 @@ def peaks():
 
 
 def gemm_traffic():
-    """DRAM bytes (read + write) per GEMM launch, averaged over the 256 launches of one step: from the committed ncu
-    capture of the same step (profiles/r1_gemm_traffic.json, `dram__bytes_read.sum + dram__bytes_write.sum`); None
-    when the capture is absent.  A profiler number, reported beside -- never instead of -- the timed ones."""
-    try:
-        return round(json.load(open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")))["dram_bytes_per_launch"])
-    except Exception:
-        return None
+    """DRAM bytes (read + write) per GEMM launch from the committed ncu capture of the same step (newest round first);
+    None when absent.  A profiler number, reported beside -- never instead of -- the timed ones."""
+    for name in ("r2_gemm_traffic.json", "r1_gemm_traffic.json"):
+        try:
+            return round(json.load(open(os.path.join(ROOT, "profiles", name)))["dram_bytes_per_launch"])
+        except Exception:
+            continue
+    return None
 
 
 class ClockSampler:
@@ -120,40 +128,196 @@ def _log(msg):
         print(f"[bench rank {os.environ.get('RANK', '0')} {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
 
-def run_ours(args):
-    import torch.distributed as dist
-    from act_b200 import _lib, dp, layers, models, ops
-    from act_b200.data import synthetic_clouds
+class Harness:
+    """Process-wide pieces shared by every config: ranks, barrier, the L2 flush buffer and the two timers."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py (impl=ours) needs a CUDA device: the act_b200 path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    _log("process group up")
-    B = args.batch
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py (impl=ours) needs a CUDA device: the act_b200 path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+        self.args = args
+        self._flush_ms = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def flush_ms(self):
+        """Device time of one L2-flush write, measured alone (subtracted from the wall clock of a timed loop)."""
+        if self._flush_ms is None:
+            for _ in range(2):
+                self.flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                self.flush.zero_()
+            b.record()
+            torch.cuda.synchronize()
+            self._flush_ms = a.elapsed_time(b) / 5
+        return self._flush_ms
+
+    def timed(self, fn, K):
+        """K steps, an L2 flush before each (outside the per-step event pair), barrier + synchronize on both sides.
+        -> (device ms/step = sum of the per-step CUDA-event intervals, max over ranks;
+            wall ms/step = host wall clock of the loop minus K flush writes, max over ranks).
+        The second is what a training loop sees when the host (graph launches, mask loop, staging) is the limiter."""
+        evs = []
+        fl = self.flush_ms()
+        self.barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            self.flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn(i)
+            b.record()
+            evs.append((a, b))
+        self.barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms, wall_ms], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t[0].item() / K, max(0.0, t[1].item() / K - fl)
+
+    def sustained(self, fn, seconds):
+        """fn(i) back to back for >= `seconds` of device time (no flush: consecutive steps use different batches and a
+        multi-GB working set), one event pair around the whole run, clocks sampled meanwhile."""
+        sampler = ClockSampler(self.local) if self.rank == 0 else None
+        self.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n, t0 = 0, time.perf_counter()
+        a.record()
+        # the same step count on every rank (N>1: each step holds a collective): sized from a 10-step probe on rank 0
+        for _ in range(10):
+            fn(n)
+            n += 1
+        torch.cuda.synchronize()
+        per = (time.perf_counter() - t0) / n
+        more = torch.tensor([max(20, int(seconds / per) - n)], dtype=torch.int64, device=self.dev)
+        if self.world > 1:
+            self.dist.broadcast(more, 0)
+        for _ in range(int(more.item())):
+            fn(n)
+            n += 1
+        b.record()
+        self.barrier()
+        ms = a.elapsed_time(b)
+        t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        clocks = sampler.stop() if sampler else None
+        return {"seconds": round(t.item() * 1e-3, 2), "steps": n, "ms_per_step": round(t.item() / n, 4),
+                "sm_mhz_median": clocks["sm_mhz"] if clocks else None, "clock_reasons": clocks["reasons"] if clocks else None}
+
+
+def gemm_roofline(record_step, pk, want_table=None):
+    """Roofline of the dominant kernel family: every launch of the tcgen05 GEMM kernels inside one step.  One eager step
+    (`record_step`) records each distinct GEMM call (shape, layouts, epilogue, its real operands); each distinct call is
+    replayed 10x back to back from a CUDA graph and timed with CUDA events on the launching stream (steady-state launch
+    duration without host gaps, at burst clocks: the denominator is therefore the BURST bf16 peak);
+    achieved = sum(count * 2MNK) / sum(count * time)."""
+    from act_b200 import ops
+    calls = {}
+    orig = ops.gemm
+
+    def rec_gemm(a, b, **kw):
+        out = orig(a, b, **kw)
+        K_, M_ = (a.shape if kw.get("a_mn") else a.shape[::-1])
+        N_ = b.shape[1] if kw.get("b_mn") else b.shape[0]
+        epi = [k for k in ("bias", "preact_out", "mul_in", "resid", "row_scale", "gmax_f32", "gmax_bf16", "colstats")
+               if kw.get(k) is not None]
+        if kw.get("act", 0):
+            epi.append("gelu" if kw["act"] == 1 else "relu")
+        key = (f"{M_}x{N_}x{K_}{'/Amn' if kw.get('a_mn') else ''}{'/Bmn' if kw.get('b_mn') else ''}"
+               f"{'/splitK' + str(kw['splits']) if kw.get('splits', 1) > 1 else ''}"
+               f"{'+' + '+'.join(epi) if epi else ''}")
+        c = calls.setdefault(key, [0, 2.0 * M_ * N_ * K_, a, b, dict(kw, out=kw.get("out", out) if not kw.get("no_out") else None)])
+        c[0] += 1
+        return out
+
+    ops.gemm = rec_gemm
+    try:
+        record_step()
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm = orig
+    rows = []
+    for key, (cnt, fl, a, b, kw) in calls.items():
+        g = torch.cuda.CUDAGraph()
+        s_ = torch.cuda.Stream()
+        s_.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s_):
+            orig(a, b, **kw)
+        torch.cuda.current_stream().wait_stream(s_)
+        with torch.cuda.graph(g):
+            for _ in range(10):
+                orig(a, b, **kw)
+        best = 1e9
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) / 10)
+        rows.append((key, cnt, fl, best))
+    tot_ms = sum(c * t for _, c, _, t in rows)
+    tot_fl = sum(c * f for _, c, f, _ in rows)
+    n = sum(c for _, c, _, _ in rows)
+    ach = tot_fl / (tot_ms * 1e-3) / 1e12
+    peak = pk["bf16_tflops"]
+    srt = sorted(rows, key=lambda r: -r[1] * r[3])
+    top = [{"gemm": k, "launches_per_step": c, "us": round(t * 1e3, 1), "tflops": round(f / (t * 1e-3) / 1e12, 1)}
+           for k, c, f, t in srt[:8]]
+    if want_table:
+        with open(want_table, "w") as f:
+            json.dump([{"gemm": k, "launches_per_step": c, "us": round(t * 1e3, 2),
+                        "tflops": round(fl / (t * 1e-3) / 1e12, 1)} for k, c, fl, t in srt], f, indent=1)
+    return {"kernel": "gemm_bf16_kernel + gemm_bf16_persistent_kernel + gemm_bf16_pair_kernel (tcgen05/TMA GEMM, all launches "
+                      "of a step)",
+            "bound": "tensor", "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s",
+            "frac": round(ach / peak, 4), "peak_src": pk["src"] + " bf16 burst (isolated-replay timings run at burst clocks)",
+            "launches_per_step": n, "flops_per_launch": tot_fl / n, "flops_per_step": tot_fl,
+            "avg_launch_us": round(tot_ms * 1e3 / n, 2), "gemm_ms_per_step_serialised": round(tot_ms, 3),
+            "note": "per-launch durations: each distinct GEMM call of the step replayed 10x from a CUDA graph on its "
+                    "real operands, CUDA events; in the timed step the weight-gradient GEMMs additionally overlap "
+                    "the dgrad chain on a second stream",
+            "top_launches": top, "traffic": gemm_traffic()}
+
+
+def bench_stage2(h, shape, teacher, steps, warmup, want_roofline, want_student_only, want_sustained, no_graph=False):
+    """The Stage-II step at one of SHAPES on this rank's GPU -> result dict (timings are max over ranks)."""
+    from act_b200 import dp, layers, models, ops
+    from act_b200.data import synthetic_clouds
+    from act_b200.engine import PretrainStep
+    sh = SHAPES[shape]
+    B, NP = h.args.batch if (shape == "stage2" and h.args.batch) else sh["batch"], sh["n_points"]
+    dev = h.dev
     torch.manual_seed(0)
-    np.random.seed(1234 + rank)
-    cfg = models.default_config(mask_ratio=MASK_RATIO, drop_path_rate=DROP_PATH, num_group=N_GROUP,
-                                group_size=GROUP_SIZE)
-    model = models.ACT_PointDistillation(cfg, teacher="native" if args.teacher == "native" else None).to(dev).train()
+    np.random.seed(1234 + h.rank)
+    cfg = models.default_config(mask_ratio=MASK_RATIO, drop_path_rate=DROP_PATH, num_group=sh["num_group"],
+                                group_size=sh["group_size"])
+    model = models.ACT_PointDistillation(cfg, teacher="native" if teacher == "native" else "synthetic").to(dev).train()
     fp = layers.FlatParams(model, lr=1e-3, weight_decay=0.05, exclude=model.UNUSED_PARAMETERS)
     dp.broadcast_params(fp)
-
     n_batches = 4
-    host = [synthetic_clouds(B, N_POINTS, seed=dp.shard_seed(20231017, rank, i)).pin_memory() for i in range(n_batches)]
-    resident = [h.to(dev) for h in host]
+    host = [synthetic_clouds(B, NP, seed=dp.shard_seed(20231017, h.rank, i)).pin_memory() for i in range(n_batches)]
+    resident = [x.to(dev) for x in host]
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    from act_b200.engine import PretrainStep
-    _log("model + flat params built; capturing")
-    eng = PretrainStep(model, fp, B, N_POINTS, use_graph=not args.no_graph, device=dev).capture()
-    _log("captured")
+    _log(f"{shape}: model + flat params built; capturing")
+    eng = PretrainStep(model, fp, B, NP, use_graph=not no_graph, device=dev).capture()
+    _log(f"{shape}: captured")
 
     def step(i):                                             # batch already resident in HBM
         return eng.run(resident[i % n_batches])
@@ -163,163 +327,220 @@ def run_ours(args):
         loss_host.copy_(loss, non_blocking=True)             # D2H of the step's result
         return loss
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, K):
-        evs = []
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(K):
-            flush.zero_()                                     # L2 flush, outside the event pair
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            fn(i)
-            b.record()
-            evs.append((a, b))
-        barrier()
-        wall = time.perf_counter() - t0
-        ms = sum(a.elapsed_time(b) for a, b in evs)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item() / K, wall
-
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(i)
-    for i in range(max(1, args.warmup // 2)):
+    for i in range(max(1, warmup // 2)):
         step_e2e(i)
-    barrier()
-
-    _log("warm-up done")
-    sampler = ClockSampler(local) if rank == 0 else None
-    l0 = ops.LAUNCHES
-    ms_step, wall = timed(step, args.steps)
-    launches = eng.launches_per_step
-    ms_e2e, _ = timed(step_e2e, args.steps)
-    _log("timed regions done")
+    h.barrier()
+    sampler = ClockSampler(h.local) if h.rank == 0 else None
+    ms_step, wall_step = h.timed(step, steps)
+    ms_e2e, wall_e2e = h.timed(step_e2e, steps)
     clocks = sampler.stop() if sampler else None
+    sustained = h.sustained(step, h.args.sustain_seconds) if want_sustained else None
     eng.flush()                                              # pipelined mode (N>1): the last step's pending update
-    last_loss = float(loss_host.item())
+    torch.cuda.synchronize()
+    res = {"batch": B, "ms_step": ms_step, "wall_step": wall_step, "ms_e2e": ms_e2e, "wall_e2e": wall_e2e,
+           "clocks": clocks, "sustained": sustained, "launches": int(eng.launches_per_step),
+           "pipelined": bool(eng.pipeline), "loss": float(loss_host.item()),
+           "h2d": int(host[0].numel() * 4 + B * sh["num_group"] + 32)}
     # the same step without the frozen teacher's forward (synthetic target): what the trainable path alone costs
-    ms_student = None
-    if args.teacher == "native":
+    if want_student_only and teacher == "native":
         object.__setattr__(model, "teacher", models.SyntheticTeacher(384).to(dev))
-        eng_s = PretrainStep(model, fp, B, N_POINTS, use_graph=not args.no_graph, device=dev).capture()
+        eng_s = PretrainStep(model, fp, B, NP, use_graph=not no_graph, device=dev).capture()
         for i in range(3):
             eng_s.run(resident[i % n_batches])
-        ms_student, _ = timed(lambda i: eng_s.run(resident[i % n_batches]), args.steps)
+        res["ms_student"], _ = h.timed(lambda i: eng_s.run(resident[i % n_batches]), steps)
+        res["launches_student"] = int(eng_s.launches_per_step)
         eng_s.flush()
+        del eng_s
         object.__setattr__(model, "teacher", model.dvae_tokenizer.forward_tokenizer_features)
-
-    # ---- roofline of the dominant kernel: every launch of the tcgen05 GEMM kernels inside one step.
-    # One eager step records each distinct GEMM call (shape, layouts, epilogue, its real operands); each distinct
-    # call is then replayed 10x back to back from a CUDA graph and timed with CUDA events on the launching stream
-    # (steady-state launch duration without host launch gaps); achieved = sum(count * 2MNK) / sum(count * time).
-    pk = peaks()
-    roof = None
-    if rank == 0:
-        calls = {}
-        orig = ops.gemm
-
-        def rec_gemm(a, b, **kw):
-            out = orig(a, b, **kw)
-            K_, M_ = (a.shape if kw.get("a_mn") else a.shape[::-1])
-            N_ = b.shape[1] if kw.get("b_mn") else b.shape[0]
-            epi = [k for k in ("bias", "preact_out", "mul_in", "resid", "row_scale", "gmax_f32", "gmax_bf16")
-                   if kw.get(k) is not None]
-            if kw.get("act", 0):
-                epi.append("gelu" if kw["act"] == 1 else "relu")
-            key = (f"{M_}x{N_}x{K_}{'/Amn' if kw.get('a_mn') else ''}{'/Bmn' if kw.get('b_mn') else ''}"
-                   f"{'/splitK' + str(kw['splits']) if kw.get('splits', 1) > 1 else ''}"
-                   f"{'+' + '+'.join(epi) if epi else ''}")
-            c = calls.setdefault(key, [0, 2.0 * M_ * N_ * K_, a, b, dict(kw, out=kw.get("out", out) if not kw.get("no_out") else None)])
-            c[0] += 1
-            return out
-
-        ops.gemm = rec_gemm
-        try:
+    # tokenizer alone (FPS + kNN/gather): the latency-bound front of the step, first-order in the dense regime
+    if h.rank == 0:
+        ops.group(resident[0], sh["num_group"], sh["group_size"])
+        evs = []
+        for i in range(5):
+            h.flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ops.group(resident[i % n_batches], sh["num_group"], sh["group_size"])
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        res["tokenizer_us"] = round(1e3 * statistics.median(a.elapsed_time(b) for a, b in evs), 1)
+    if want_roofline and h.rank == 0:
+        def record():
             eng._host_prologue(resident[0])
             eng._body_a()
-            eng._body_b()
-            torch.cuda.synchronize()
-        finally:
-            ops.gemm = orig
-        rows = []
-        for key, (cnt, fl, a, b, kw) in calls.items():
-            g = torch.cuda.CUDAGraph()
-            s_ = torch.cuda.Stream()
-            s_.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s_):
-                orig(a, b, **kw)
-            torch.cuda.current_stream().wait_stream(s_)
-            with torch.cuda.graph(g):
-                for _ in range(10):
-                    orig(a, b, **kw)
-            best = 1e9
-            for _ in range(3):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                g.replay()
-                e1.record()
-                torch.cuda.synchronize()
-                best = min(best, e0.elapsed_time(e1) / 10)
-            rows.append((key, cnt, fl, best))
-        tot_ms = sum(c * t for _, c, _, t in rows)
-        tot_fl = sum(c * f for _, c, f, _ in rows)
-        n = sum(c for _, c, _, _ in rows)
-        ach = tot_fl / (tot_ms * 1e-3) / 1e12
-        peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
-        top = [{"gemm": k, "launches_per_step": c, "us": round(t * 1e3, 1), "tflops": round(f / (t * 1e-3) / 1e12, 1)}
-               for k, c, f, t in sorted(rows, key=lambda r: -r[1] * r[3])[:8]]
-        if os.environ.get("ACT_BENCH_GEMM_TABLE"):
-            with open(os.environ["ACT_BENCH_GEMM_TABLE"], "w") as f:
-                json.dump([{"gemm": k, "launches_per_step": c, "us": round(t * 1e3, 2),
-                            "tflops": round(fl / (t * 1e-3) / 1e12, 1)} for k, c, fl, t in
-                           sorted(rows, key=lambda r: -r[1] * r[3])], f, indent=1)
-        roof = {"kernel": "gemm_bf16_kernel + gemm_bf16_persistent_kernel (tcgen05/TMA GEMM, all launches of a step)",
-                "bound": "tensor", "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s",
-                "frac": round(ach / peak, 4), "peak_src": pk["src"] + " bf16 sustained", "launches_per_step": n,
-                "flops_per_launch": tot_fl / n, "avg_launch_us": round(tot_ms * 1e3 / n, 2),
-                "gemm_ms_per_step_serialised": round(tot_ms, 3),
-                "note": "per-launch durations: each distinct GEMM call of the step replayed 10x from a CUDA graph on its "
-                        "real operands, CUDA events; in the timed step the weight-gradient GEMMs additionally overlap "
-                        "the dgrad chain on a second stream",
-                "top_launches": top, "traffic": gemm_traffic()}
-    if world > 1:
-        dist.barrier()
+            eng._body_b()                 # one extra AdamW update outside the timed regions (recording only)
+        res["roofline"] = gemm_roofline(record, peaks(), os.environ.get("ACT_BENCH_GEMM_TABLE") if shape == "stage2" else
+                                        os.environ.get("ACT_BENCH_GEMM_TABLE_" + shape.upper()))
+    if h.world > 1:
+        h.dist.barrier()
+    del eng, fp, model
+    torch.cuda.empty_cache()
+    return res
 
+
+def bench_dvae(h, steps, warmup):
+    """BASELINE config 3: the Stage-I dVAE step (tools/runner_autoencoder.py:130-146), B=64 per GPU."""
+    from act_b200 import dp, dvae, engine, layers
+    from act_b200.data import synthetic_clouds
+    from act_b200.models import Cfg
+    sh = SHAPES["dvae"]
+    B = sh["batch"]
+    cfg = Cfg(NAME="DiscreteVAE", group_size=32, num_group=64, num_tokens=8192, encoder_dims=256, tokens_dims=256,
+              decoder_dims=256)
+    torch.manual_seed(0)
+    model = dvae.DiscreteVAE(cfg).to(h.dev).train()
+    fp = layers.FlatParams(model, lr=5e-4, weight_decay=5e-4)
+    dp.broadcast_params(fp)
+    eng = engine.AutoencoderStep(model, fp, B, sh["n_points"], device=h.dev).capture()
+    host = [synthetic_clouds(B, sh["n_points"], seed=dp.shard_seed(777, h.rank, i)).pin_memory() for i in range(4)]
+    resident = [x.to(h.dev) for x in host]
+    lh = torch.zeros(3, dtype=torch.float32).pin_memory()
+    for i in range(warmup):
+        eng.run(resident[i % 4])
+
+    def e2e(i):
+        lh.copy_(eng.run(host[i % 4]), non_blocking=True)
+
+    e2e(0)
+    ms, wall = h.timed(lambda i: eng.run(resident[i % 4]), steps)
+    ms_e, wall_e = h.timed(e2e, steps)
+    torch.cuda.synchronize()
+    res = {"batch": B, "ms_step": ms, "wall_step": wall, "ms_e2e": ms_e, "wall_e2e": wall_e,
+           "launches": int(eng.launches_per_step), "losses": [round(x, 5) for x in lh.tolist()],
+           "h2d": int(host[0].numel() * 4 + 8 + 32)}
+    if h.rank == 0:
+        def record():
+            eng._host_prologue(resident[0])
+            eng._body_a()
+        res["roofline"] = gemm_roofline(record, peaks(), os.environ.get("ACT_BENCH_GEMM_TABLE_DVAE"))
+    if h.world > 1:
+        h.dist.barrier()
+    del eng, fp, model
+    torch.cuda.empty_cache()
+    return res
+
+
+def _summ(res, world, unit=UNIT):
+    """value = clouds/s from the slower of (device-event time, wall clock) -- see Harness.timed."""
+    clouds = res["batch"] * world
+    ms = max(res["ms_step"], res["wall_step"])
+    ms_e = max(res["ms_e2e"], res["wall_e2e"])
+    return {"value": round(clouds / (ms * 1e-3), 1), "unit": unit, "ms_per_step": round(ms, 4),
+            "ms_per_step_device": round(res["ms_step"], 4), "ms_per_step_wall": round(res["wall_step"], 4),
+            "batch_per_gpu": res["batch"],
+            "e2e": {"value": round(clouds / (ms_e * 1e-3), 1), "unit": unit, "ms_per_step": round(ms_e, 4),
+                    "ms_per_step_device": round(res["ms_e2e"], 4), "ms_per_step_wall": round(res["wall_e2e"], 4),
+                    "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": 4 if "losses" not in res else 12},
+            "gpu_launches": res["launches"]}
+
+
+def _dense_line(res, world, pk):
+    s = _summ(res, world)
+    sh = SHAPES["dense"]
+    s["config"] = workload_cfg(res["batch"], world, "synthetic", "dense")
+    s["metric"] = "clouds_per_sec_act_stage2_step_dense"
+    if "tokenizer_us" in res:
+        B, N, G, k = res["batch"], sh["n_points"], sh["num_group"], sh["group_size"]
+        nbytes = B * (12 * N + 16 * G) + B * (12 * N + 12 * G + 20 * G * k)       # SURVEY 8(d): FPS + kNN/gather
+        s["tokenizer"] = {"us": res["tokenizer_us"], "share_of_step": round(res["tokenizer_us"] * 1e-3 / res["ms_step"], 4),
+                          "algorithmic_bytes": nbytes,
+                          "hbm_gbs": round(nbytes / (res["tokenizer_us"] * 1e-6) / 1e9, 1),
+                          "frac_of_hbm_peak": round(nbytes / (res["tokenizer_us"] * 1e-6) / 1e9 / pk["hbm_gbs"], 5),
+                          "note": "latency-bound (G-1 dependent arg-max rounds), not bandwidth-bound"}
+    if "roofline" in res:
+        s["roofline"] = res["roofline"]
+    s["loss"] = res.get("loss")
+    return s
+
+
+def _dvae_line(res, world):
+    s = _summ(res, world)
+    s["metric"] = "clouds_per_sec_dvae_stage1_step"
+    s["config"] = {"workload": "dVAE Stage-I step (BASELINE config 3): N=1024, G=64 x k=32, dims 256, 8192 tokens, "
+                               "fwd + ChamferL1 x2 + KL + bwd + AdamW", "batch_per_gpu": res["batch"],
+                   "global_batch": res["batch"] * world, "parallelism": f"dp{world}",
+                   "l2": "256 MB L2-flush write between timed steps, outside the event pairs"}
+    s["losses_recon_kl_total"] = res.get("losses")
+    if "roofline" in res:
+        s["roofline"] = res["roofline"]
+    return s
+
+
+def run_ours(args):
+    h = Harness(args)
+    _log("process group up")
+    pk = peaks()
+    world, rank = h.world, h.rank
+    which = args.config
+    line = None
+    extra = {}
+    if which in ("all", "stage2"):
+        res = bench_stage2(h, "stage2", args.teacher, args.steps, args.warmup, want_roofline=True,
+                           want_student_only=True, want_sustained=args.sustain_seconds > 0, no_graph=args.no_graph)
+        s = _summ(res, world)
+        if rank == 0:
+            clouds = res["batch"] * world
+            roof = res.get("roofline")
+            sus = res["sustained"]
+            if sus is not None and roof is not None:
+                # step-level tensor throughput of the seconds-long run against the SUSTAINED cuBLAS figure
+                tf = roof["flops_per_step"] / (sus["ms_per_step"] * 1e-3) / 1e12
+                sus.update({"value": round(clouds / (sus["ms_per_step"] * 1e-3), 1), "unit": UNIT,
+                            "gemm_tflops_step_level": round(tf, 1), "peak_sustained": pk["bf16_tflops_sustained"],
+                            "frac_of_sustained_peak": round(tf / pk["bf16_tflops_sustained"], 4)})
+            line = {"metric": METRIC, "value": s["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": s["ms_per_step"], "ms_per_step_device": s["ms_per_step_device"],
+                    "ms_per_step_wall": s["ms_per_step_wall"],
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                    "data": "synthetic", "config": workload_cfg(res["batch"], world, args.teacher), "impl": "ours",
+                    "e2e": s["e2e"],
+                    "student_only": (None if "ms_student" not in res else
+                                     {"value": round(clouds / (res["ms_student"] * 1e-3), 1), "unit": UNIT,
+                                      "ms_per_step": round(res["ms_student"], 4), "gpu_launches": res["launches_student"],
+                                      "what": "same step with a synthetic teacher target (no teacher forward)"}),
+                    "sustained": sus,
+                    "gpu_launches": res["launches"], "cuda_graph": not args.no_graph, "pipelined": res["pipelined"],
+                    "loss": res["loss"], "clocks": res["clocks"], "roofline": roof,
+                    "tokenizer_us": res.get("tokenizer_us")}
+    for name in ("dvae", "dense"):
+        if which not in ("all", name):
+            continue
+        try:
+            if name == "dvae":
+                r = bench_dvae(h, args.steps, args.warmup)
+                extra[name] = _dvae_line(r, world) if rank == 0 else None
+            else:
+                r = bench_stage2(h, "dense", "synthetic", max(5, args.steps // 2), args.warmup, want_roofline=True,
+                                 want_student_only=False, want_sustained=False)
+                extra[name] = _dense_line(r, world, pk) if rank == 0 else None
+        except Exception as e:                          # a secondary config must never take the headline line down
+            if which != "all" or world > 1:             # (N>1: ranks must fail together, not diverge)
+                raise
+            extra[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0:
-        cpu = (cpu_baseline(sample_batch=8, steps=1, teacher=args.teacher)
-               if world == 1 and not args.no_cpu_baseline else None)
-        clouds = B * world
-        line = {"metric": METRIC, "value": round(clouds / (ms_step * 1e-3), 1), "unit": UNIT, "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-                "data": "synthetic", "config": workload_cfg(B, world, args.teacher), "impl": "ours",
-                "e2e": {"value": round(clouds / (ms_e2e * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms_e2e, 4),
-                        "h2d_bytes_per_step": int(host[0].numel() * 4 + B * N_GROUP + 32), "d2h_bytes_per_step": 4},
-                "student_only": (None if ms_student is None else
-                                 {"value": round(clouds / (ms_student * 1e-3), 1), "unit": UNIT,
-                                  "ms_per_step": round(ms_student, 4),
-                                  "what": "same step with a synthetic teacher target (no teacher forward)"}),
-                "gpu_launches": int(launches), "cuda_graph": not args.no_graph, "pipelined": bool(eng.pipeline),
-                "loss": last_loss,
-                "wall_s_timed": round(wall, 3),
-                "clocks": clocks, "roofline": roof}
-        if cpu is not None:
-            line["cpu_baseline"] = cpu
+        if line is None:                                   # --config dvae / dense: that config IS the line
+            name = which
+            s = extra[name]
+            line = {"metric": s.pop("metric"), "value": s["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": s["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "ours"}
+            line.update({k: v for k, v in s.items() if k not in ("value", "unit", "ms_per_step")})
+        else:
+            line["configs"] = extra
+            if world == 1 and not args.no_cpu_baseline:
+                line["cpu_baseline"] = cpu_baseline(sample_batch=16, steps=1, teacher=args.teacher)
         emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        h.dist.destroy_process_group()
 
 
 # --------------------------------------------------------------------------- CPU baseline / reference arm
 def cpu_student_step_time(batch, steps, warmup, threads, teacher="native"):
     """The reference's path restated for the host (oracle/): Group on the C oracle, fp32 PyTorch modules,
-    torch.optim.AdamW with the reference's two parameter groups (tools/builder.py:37-55)."""
+    torch.optim.AdamW with the reference's two parameter groups (tools/builder.py:37-55).  -> median step time (s)."""
     from oracle import ref_model
     torch.set_num_threads(threads)
     torch.manual_seed(0)
@@ -329,14 +550,14 @@ def cpu_student_step_time(batch, steps, warmup, threads, teacher="native"):
     nodecay = [p for n, p in model.named_parameters() if (p.dim() <= 1 or n.endswith(".bias") or "token" in n)]
     opt = torch.optim.AdamW([{"params": decay, "weight_decay": 0.05}, {"params": nodecay, "weight_decay": 0.0}],
                             lr=1e-3)
-    pts = ref_model.synthetic_clouds(batch, N_POINTS)
+    pts = ref_model.synthetic_clouds(batch, SHAPES["stage2"]["n_points"])
     tnet = None
     if teacher == "native":
         from oracle import ref_teacher
         tnet = ref_teacher.TeacherFeatures().train()      # frozen, train mode like the reference (act.py:1151-1160)
         for p in tnet.parameters():
             p.requires_grad = False
-    tfeat = torch.randn(batch, N_GROUP, 384)
+    tfeat = torch.randn(batch, SHAPES["stage2"]["num_group"], 384)
     times, phases = [], {"group_teacher": 0.0, "student_forward": 0.0, "backward": 0.0, "adamw": 0.0}
     for i in range(warmup + steps):
         t0 = time.perf_counter()
@@ -357,10 +578,10 @@ def cpu_student_step_time(batch, steps, warmup, threads, teacher="native"):
             for k, v in zip(phases, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
                 phases[k] += v * 1e3 / steps
     cpu_student_step_time.last_phases_ms = {k: round(v, 1) for k, v in phases.items()}
-    return sum(times) / len(times)
+    return statistics.median(times)
 
 
-def cpu_baseline(sample_batch=8, steps=1, teacher="native"):
+def cpu_baseline(sample_batch=16, steps=1, teacher="native"):
     threads = os.cpu_count() or 1
     t = cpu_student_step_time(sample_batch, steps, 1, threads, teacher)
     return {"value": round(sample_batch / t, 3), "unit": UNIT, "cores": threads, "kind": "port",
@@ -370,26 +591,32 @@ def cpu_baseline(sample_batch=8, steps=1, teacher="native"):
 
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU implementation of the path on the box's host cores.  What runs is the
+    oracle PORT (oracle/ref_model.py + ref_teacher.py + cpu_ref.c) -- pinned against the UNMODIFIED reference modules in
+    the authoring container (tests/test_oracle*.py; scripts/ref_cpu_here.py times the two side by side there) -- because
+    the reference's sources may not be copied into this repo and /root/reference does not exist on the GPU box.
+    SURVEY 8(d): B=16 per step, 1 warm-up + 3 timed steps, median; the line states the steps / batch it REALLY ran."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = 8
-    steps = max(1, min(args.steps, 3))
-    warm = max(1, min(args.warmup, 1))
+    sample, steps, warm = 16, 3, 1
     t = cpu_student_step_time(sample, steps, warm, threads, args.teacher)
     world = max(1, args.gpus)
     val = round(sample / t, 3)
-    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(t * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+    cfg = workload_cfg(sample, 1, args.teacher)
+    cfg["parallelism"] = f"host cpu, {threads} threads (one host: the arm does not scale with --gpus)"
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": warm, "ms_per_step": round(t * 1e3, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_cfg(args.batch, world, args.teacher),
+            "config": cfg, "requested": {"steps": args.steps, "warmup": args.warmup},
             "impl": "reference",
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                              "phases_ms": getattr(cpu_student_step_time, "last_phases_ms", None),
-                             "sample": f"{steps} timed step(s) at batch {sample} per step (bounded sample of the "
-                                       f"batch-128 workload), oracle restatement of the reference path on all host "
-                                       f"threads; the reference's own native ops are CUDA-only"},
+                             "sample": f"median of {steps} timed steps after {warm} warm-up at batch {sample} per step "
+                                       f"(bounded sample of the batch-128 workload), oracle restatement of the reference "
+                                       f"path on all host threads; the reference's own native ops are CUDA-only and its "
+                                       f"sources cannot travel to this box"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -421,10 +648,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=128, help="clouds per GPU")
+    ap.add_argument("--config", default="all", choices=["all", "stage2", "dvae", "dense"],
+                    help="all: the Stage-II headline line with `configs.{dvae,dense}` attached; else that config alone")
+    ap.add_argument("--batch", type=int, default=0, help="clouds per GPU of the stage2 config (default 128)")
     ap.add_argument("--teacher", default="native", choices=["native", "synthetic"],
                     help="native: the frozen teacher's forward is part of the step (the reference's full Stage-II step); "
                          "synthetic: student-only step with a synthetic target")
+    ap.add_argument("--sustain-seconds", type=float, default=3.0, help="length of the back-to-back `sustained` run (0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

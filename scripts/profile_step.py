@@ -16,7 +16,7 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 torch.manual_seed(0)
 np.random.seed(0)
 TEACHER = sys.argv[3] if len(sys.argv) > 3 else "native"
-model = models.ACT_PointDistillation(models.default_config(0.6, 0.1), teacher="native" if TEACHER == "native" else None).cuda().train()
+model = models.ACT_PointDistillation(models.default_config(0.6, 0.1), teacher="native" if TEACHER == "native" else "synthetic").cuda().train()
 fp = layers.FlatParams(model, exclude=model.UNUSED_PARAMETERS)
 pts = synthetic_clouds(B, 1024).cuda()
 

@@ -60,7 +60,7 @@ def test_encoder_vs_reference_golden(golden):
 
 def build_student(seed=4, flat=False, **kw):
     cfg = models.default_config(mask_ratio=0.6, drop_path_rate=0.0, **kw)
-    model = models.ACT_PointDistillation(cfg)
+    model = models.ACT_PointDistillation(cfg, teacher="synthetic")
     ref_model.fill_params(model, seed=seed)
     model = model.cuda().train()
     fp = layers.FlatParams(model, exclude=model.UNUSED_PARAMETERS) if flat else None
@@ -128,7 +128,7 @@ def test_full_size_step_properties():
     torch.manual_seed(0)
     np.random.seed(0)
     cfg = models.default_config(mask_ratio=0.6, drop_path_rate=0.1)
-    model = models.ACT_PointDistillation(cfg).cuda().train()
+    model = models.ACT_PointDistillation(cfg, teacher="synthetic").cuda().train()
     fp = layers.FlatParams(model, exclude=model.UNUSED_PARAMETERS)
     pts = ref_model.synthetic_clouds(128, 1024).cuda()
     loss = model(pts)
@@ -153,7 +153,7 @@ def test_engine_graph_replay_matches_eager():
         torch.manual_seed(0)
         np.random.seed(0)
         cfg = models.default_config(mask_ratio=0.6, drop_path_rate=0.0)
-        model = ref_model.fill_params(models.ACT_PointDistillation(cfg), seed=3).cuda().train()
+        model = ref_model.fill_params(models.ACT_PointDistillation(cfg, teacher="synthetic"), seed=3).cuda().train()
         fp = layers.FlatParams(model, lr=1e-3, exclude=model.UNUSED_PARAMETERS)
         eng = PretrainStep(model, fp, 8, 1024, use_graph=use_graph).capture()
         pts = ref_model.synthetic_clouds(8, 1024, seed=1)
@@ -181,7 +181,7 @@ def test_dense_regime_step_runs():
     B = 2
     pts = ref_model.synthetic_clouds(B, 8192, seed=8)
     cfg = models.default_config(mask_ratio=0.6, drop_path_rate=0.0, num_group=512, group_size=32, depth=2)
-    model = models.ACT_PointDistillation(cfg).cuda().train()
+    model = models.ACT_PointDistillation(cfg, teacher="synthetic").cuda().train()
     nb, center = model.group_divider(pts.cuda())
     onb, ocenter, oidx, ofps = cpu_ref.group(pts.numpy(), 512, 32)
     assert np.array_equal(model.group_divider.last_fps_idx.cpu().numpy(), ofps)
@@ -227,7 +227,7 @@ def test_engine_pipelined_mode_matches_serial():
         torch.manual_seed(0)
         np.random.seed(0)
         cfg = models.default_config(mask_ratio=0.6, drop_path_rate=0.0)
-        model = ref_model.fill_params(models.ACT_PointDistillation(cfg), seed=3).cuda().train()
+        model = ref_model.fill_params(models.ACT_PointDistillation(cfg, teacher="synthetic"), seed=3).cuda().train()
         fp = layers.FlatParams(model, lr=1e-3, exclude=model.UNUSED_PARAMETERS)
         eng = PretrainStep(model, fp, 8, 1024, pipeline=pipeline).capture()
         assert eng.pipeline == pipeline
@@ -261,3 +261,67 @@ def test_engine_pipelined_mode_with_native_teacher():
     eng.flush()
     assert all(np.isfinite(l) and 0.0 < l < 2.0 for l in losses), losses
     assert len(set(losses)) > 1 and not torch.equal(model.proj_head.weight.detach(), w_before)
+
+
+def test_capture_leaves_model_optimizer_buffers_and_rng_unchanged():
+    """engine.PretrainStep.capture(): the two eager warm-up steps (needed before a CUDA-graph capture) are undone -- master
+    weights, AdamW moments + step count, every BatchNorm buffer of student and frozen teacher, numpy / torch RNG streams --
+    so a loaded checkpoint is not perturbed and the first real step is step 1."""
+    from act_b200.engine import PretrainStep
+    torch.manual_seed(0)
+    np.random.seed(0)
+    for pipeline in (False, True):
+        model = models.ACT_PointDistillation(models.default_config(0.6, 0.1)).cuda().train()
+        fp = layers.FlatParams(model, lr=1e-3, weight_decay=0.05, exclude=model.UNUSED_PARAMETERS)
+        fp.exp_avg.normal_()                                     # pretend a resumed optimizer state
+        fp.exp_avg_sq.uniform_()
+        fp.step_count = 41
+        before = (fp.flat.clone(), fp.exp_avg.clone(), fp.exp_avg_sq.clone(), fp.shadow.clone())
+        bufs = {k: v.clone() for k, v in model.state_dict().items()}
+        np_state, cpu_state = np.random.get_state()[1].copy(), torch.get_rng_state().clone()
+        cuda_state = torch.cuda.get_rng_state().clone()
+        eng = PretrainStep(model, fp, 8, 1024, pipeline=pipeline).capture()
+        torch.cuda.synchronize()
+        for a, b in zip(before, (fp.flat, fp.exp_avg, fp.exp_avg_sq, fp.shadow)):
+            assert torch.equal(a, b)
+        assert fp.step_count == 41 and not fp.grad.any()
+        for k, v in model.state_dict().items():
+            assert torch.equal(v, bufs[k]), k                    # incl. running_mean / running_var / num_batches_tracked
+        assert np.array_equal(np.random.get_state()[1], np_state)
+        assert torch.equal(torch.get_rng_state(), cpu_state) and torch.equal(torch.cuda.get_rng_state(), cuda_state)
+        loss = eng.run(ref_model.synthetic_clouds(8, 1024, seed=5).cuda())
+        eng.flush()
+        assert np.isfinite(loss.item()) and fp.step_count == 42
+
+
+def test_checkpoint_round_trip_resumes_the_optimizer(tmp_path):
+    """engine.checkpoint(): the reference's ckpt dict (tools/builder.py:132-144) with FlatParams.state_dict() as
+    `optimizer`; a fresh model + FlatParams restored from it holds identical weights, moments and step count, and
+    torch.optim.AdamW (the reference's optimizer) accepts the optimizer part."""
+    from act_b200.engine import PretrainStep
+    torch.manual_seed(0)
+    np.random.seed(0)
+    cfg = models.default_config(0.6, 0.0)
+    model = models.ACT_PointDistillation(cfg, teacher="synthetic").cuda().train()
+    fp = layers.FlatParams(model, lr=1e-3, exclude=model.UNUSED_PARAMETERS)
+    eng = PretrainStep(model, fp, 8, 1024, pipeline=True).capture()
+    pts = ref_model.synthetic_clouds(8, 1024, seed=1).cuda()
+    for _ in range(3):
+        eng.run(pts)
+    path = str(tmp_path / "ckpt-last.pth")
+    eng.save_checkpoint(path, epoch=3)                           # flush()es the pending pipelined update first
+    assert fp.step_count == 3
+    ck = torch.load(path, map_location="cpu")
+    assert set(ck) == {"base_model", "optimizer", "epoch", "metrics", "best_metrics"}
+    model2 = models.ACT_PointDistillation(cfg, teacher="synthetic")
+    model2.load_state_dict(ck["base_model"], strict=True)
+    model2 = model2.cuda().train()
+    fp2 = layers.FlatParams(model2, lr=1e-3, exclude=model2.UNUSED_PARAMETERS)
+    fp2.load_state_dict(ck["optimizer"])
+    assert torch.equal(fp2.flat, fp.flat) and torch.equal(fp2.exp_avg, fp.exp_avg)
+    assert torch.equal(fp2.exp_avg_sq, fp.exp_avg_sq) and fp2.step_count == 3 and torch.equal(fp2.shadow, fp.shadow)
+    named = [(n, p) for n, p in model2.named_parameters() if p.requires_grad]
+    nd = lambda n, p: p.dim() <= 1 or n.endswith(".bias") or "token" in n  # noqa: E731
+    opt = torch.optim.AdamW([{"params": [p for n, p in named if nd(n, p)], "weight_decay": 0.0},
+                             {"params": [p for n, p in named if not nd(n, p)], "weight_decay": 0.05}], lr=1e-3)
+    opt.load_state_dict(ck["optimizer"])
