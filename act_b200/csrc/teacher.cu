@@ -29,23 +29,7 @@ __device__ __forceinline__ float block_sum_256(float v, float *red) {
 }
 
 
-// ---- counter-based RNG (Philox4x32-10, Salmon et al. 2011): the teacher's two random draws (gumbel noise of the hard
-// gumbel-softmax, dvae.py:587; prompt-token dropout, dvae.py:545-560) are generated inside the consuming kernel from a
-// per-step 64-bit seed held in device memory, instead of materialising [B*G, 8192] noise / [B,P,D] masks in HBM.
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                               uint32_t k1) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    return make_uint4(c0, c1, c2, c3);
-}
-// uniform in (0,1): 23 random bits + 1/2 ulp, exactly representable, never 0 or 1
-__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 9) + 0.5f) * (1.f / 8388608.f); }
+// (philox4x32_10 / u01: common.cuh)
 // standard Gumbel sample -log(-log(u)) == -log(Exp(1)) (what F.gumbel_softmax draws).  Two MUFU.LG2 per sample;
 // the inner logarithm switches to the accurate log1p form near u = 1, where lg2.approx loses its relative accuracy
 // (that upper tail is exactly where the arg-max winners come from; below 0.9999 the relative error is < 2e-3).

@@ -96,7 +96,46 @@ __global__ void __launch_bounds__(256) adamw_kernel(float *__restrict__ p, const
     }
 }
 
+// dst[i] += src[i]  (tiny per-channel gradient pieces: BatchNorm dgamma / dbeta into the flat gradient buffer)
+__global__ void __launch_bounds__(256) accumulate_kernel(float *__restrict__ dst, const float *__restrict__ src, long long n) {
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) dst[i] += __ldg(src + i);
+}
+// x[i] *= *scalar  (the incoming d(loss) of the loss node: a device scalar, 1.0 in the training step)
+__global__ void __launch_bounds__(256) scale_by_kernel(float *__restrict__ x, const float *__restrict__ scalar, long long n) {
+    const float s = __ldg(scalar);
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) x[i] *= s;
+}
+
 }  // namespace act
+
+extern "C" int act_zero(void *ptr, long long nbytes, void *stream) {
+    if (!ptr || nbytes < 0) return ACT_EINVAL;
+    if (nbytes == 0) return ACT_OK;
+    ACT_CUDA(cudaMemsetAsync(ptr, 0, (size_t)nbytes, (cudaStream_t)stream));
+    return ACT_OK;
+}
+
+extern "C" int act_accumulate(float *dst, const float *src, long long n, void *stream) {
+    using namespace act;
+    if (!dst || !src || n < 0) return ACT_EINVAL;
+    if (n == 0) return ACT_OK;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    accumulate_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(dst, src, n);
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}
+
+extern "C" int act_scale_by(float *x, const float *scalar, long long n, void *stream) {
+    using namespace act;
+    if (!x || !scalar || n < 0) return ACT_EINVAL;
+    if (n == 0) return ACT_OK;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    scale_by_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, scalar, n);
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}
 
 extern "C" int act_cosine_loss(const float *student, const float *teacher, int R, int C, float eps, float *loss,
                                float *grad_student, void *stream) {

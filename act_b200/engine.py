@@ -10,7 +10,7 @@ scalars, (c) copies the batch into the graph's static input, (d) launches the gr
 """
 import torch
 
-from . import dp, ops
+from . import dp, layers, ops
 from .modules import mask_center_rand
 
 
@@ -93,6 +93,9 @@ class PretrainStep:
         self.points = torch.zeros(batch, n_points, 3, dtype=torch.float32, device=self.dev)
         self.mask = torch.zeros(batch, self.G, dtype=torch.bool, device=self.dev)
         self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
+        # per-step 64-bit seeds staged from the host like the mask: [0] DropPath gates, [1] the teacher's gumbel / prompt
+        # dropout draws (single-graph mode) -- the captured step then contains no library RNG kernel
+        self._seeds = torch.zeros(2, dtype=torch.int64, device=self.dev)
         self.use_graph = use_graph
         self.graph = None
         self.graph_b = None
@@ -103,7 +106,8 @@ class PretrainStep:
     # the all-reduce is one eager launch on the same stream, ordered after graph A and before graph B)
     def _body_a(self):
         self.fp.zero_grad()
-        loss = self.model(self.points, mask=self.mask)
+        with layers.drop_path_seed(self._seeds[:1]):
+            loss = self.model(self.points, mask=self.mask)
         loss.backward()
         self.loss.copy_(loss.detach())
 
@@ -126,7 +130,8 @@ class PretrainStep:
 
     def _body_fwd(self):                             # G2a: student forward (autograd graph kept for G2b)
         self.fp.zero_grad()
-        self._student, self._order, self._nvis = self.model.forward_student(self._nb, self._center, self.mask)
+        with layers.drop_path_seed(self._seeds[:1]):
+            self._student, self._order, self._nvis = self.model.forward_student(self._nb, self._center, self.mask)
 
     def _body_bwd(self):                             # G2b: loss against the teacher's features + backward
         loss = self.model.distill_loss(self._student, self._tfeat, self._order, self._nvis)
@@ -140,6 +145,7 @@ class PretrainStep:
         # would be overwritten before its asynchronous copy has executed (torch's caching host allocator recycles a
         # pinned block only after the copies recorded on it have completed)
         self.mask.copy_(m.pin_memory(), non_blocking=True)
+        self._seeds.copy_(torch.randint(0, 2 ** 62, (2,), dtype=torch.int64).pin_memory(), non_blocking=True)
         if hyper:
             self.fp.set_hyper(grad_scale=1.0 / dp.world_size())
         if points is not None and points.data_ptr() != self.points.data_ptr():
@@ -276,7 +282,7 @@ class PretrainStep:
             return self._capture_pipeline()
         tmod = getattr(getattr(self.model, "teacher", None), "__self__", None)
         if tmod is not None and hasattr(tmod, "seed_buffer"):
-            tmod.seed_buffer = None                          # single graph: the teacher's seed is drawn inside it
+            tmod.seed_buffer = self._seeds[1:]               # single graph: the teacher's seed is staged with the mask
         l0 = ops.LAUNCHES
         snap = _StateSnapshot(self.model, self.fp, self.dev)
         self._host_prologue(None)

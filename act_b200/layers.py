@@ -211,7 +211,10 @@ class FlatParams:
         self.shadow.copy_(self.flat)
 
     def zero_grad(self):
-        self.grad.zero_()
+        if self.grad.is_cuda:
+            ops.zero_(self.grad)          # a memset node in the captured step
+        else:
+            self.grad.zero_()
 
     def set_hyper(self, grad_scale=1.0):
         """Stage this step's AdamW scalars (lr from the scheduler, bias corrections) into device memory."""
@@ -286,7 +289,7 @@ class TransformerStack(torch.autograd.Function):
         sink = _GradSink()
         side = _SideStream(dy.device)
         dx = dy.reshape(M, C).contiguous().float()
-        dpos = torch.zeros(M, C, dtype=torch.float32, device=dy.device) if has_pos else None
+        dpos = ops.zero_(torch.empty(M, C, dtype=torch.float32, device=dy.device)) if has_pos else None
         g = None
         NS = 13
         for l in reversed(range(depth)):
@@ -333,6 +336,24 @@ def transformer_stack(x, pos, blocks, num_heads, eps=1e-5, gates=None):
 
 
 _KEEP_CACHE = {}
+_DP = {"seed": None, "calls": 0}
+
+
+class drop_path_seed:
+    """Context manager: inside it, DropPath gates are drawn by the act_b200 kernel from `seed` (a device int64 [1] the
+    caller refreshes before every step -- engine.PretrainStep stages it from the host next to the mask and the AdamW
+    scalars), so a captured step contains no library RNG kernel.  Outside it the seed comes from torch.randint on the
+    device (one library kernel; graph-safe too)."""
+
+    def __init__(self, seed):
+        self.seed = seed
+
+    def __enter__(self):
+        self.prev = _DP["seed"]
+        _DP["seed"] = self.seed
+
+    def __exit__(self, *a):
+        _DP["seed"] = self.prev
 
 
 def drop_path_gates(rates, batch, device, training):
@@ -343,10 +364,13 @@ def drop_path_gates(rates, batch, device, training):
     key = (tuple(rates), str(device))
     keep = _KEEP_CACHE.get(key)
     if keep is None:       # built once, outside any CUDA-graph capture (the engine warms up eagerly first)
-        keep = torch.tensor([1.0 - r for r in rates for _ in (0, 1)], dtype=torch.float32).view(-1, 1).to(device)
+        keep = torch.tensor([1.0 - r for r in rates for _ in (0, 1)], dtype=torch.float32).to(device)
         _KEEP_CACHE[key] = keep
-    u = torch.rand(2 * len(rates), batch, dtype=torch.float32, device=device)
-    return (torch.floor(keep + u) / keep).contiguous()
+    seed = _DP["seed"]
+    if seed is None:
+        seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=device)
+    _DP["calls"] += 1      # distinct stream per call site of a step (baked into a captured graph; the seed changes per step)
+    return ops.drop_path_gates(seed, keep, batch, draw_id=_DP["calls"] & 0x7fffffff)
 
 
 # ------------------------------------------------------------------------------------------- LayerNorm
@@ -379,7 +403,11 @@ class LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, gelu):
         shp = x.shape
-        xb = x.reshape(-1, shp[-1]).to(torch.bfloat16).contiguous()
+        x2 = x.reshape(-1, shp[-1])
+        if x2.dtype == torch.float32 and x2.is_contiguous() and shp[-1] % 128 == 0 and shp[-1] <= 1024:
+            xb = ops.cast_rows(x2)                               # our cast kernel (no library launch in the step)
+        else:
+            xb = x2.to(torch.bfloat16).contiguous()
         u = None
         if gelu:
             u = torch.empty(xb.shape[0], weight.shape[0], dtype=torch.bfloat16, device=x.device)
@@ -415,6 +443,114 @@ class LinearFn(torch.autograd.Function):
 
 def linear(x, weight, bias=None, gelu=False):
     return LinearFn.apply(x, weight, bias, gelu)
+
+
+
+# --------------------------------------------------------------------------------------- pos-embed MLP
+class PosMlpFn(torch.autograd.Function):
+    """nn.Sequential(Linear(3,128), GELU, Linear(128,C)) on group centres (act.py:173-177, 1166-1170): the K = 3 layer +
+    GELU on CUDA cores (csrc/tokens.cu) writing the bf16 operand of the 128 -> C tcgen05 GEMM; backward: cast + bias
+    gradient, wgrad, dgrad, and the first layer's parameter gradients with the pre-activation recomputed from the centres
+    (which carry no gradient: they come from FPS)."""
+
+    @staticmethod
+    def forward(ctx, x, w0, b0, w2, b2):
+        shp = x.shape
+        x2 = x.reshape(-1, 3).contiguous().float()
+        a = ops.pos_mlp1_fwd(x2, w0, b0, out_dtype=ops.act_dtype())
+        y = ops.gemm(a, shadow(w2), bias=b2, out_dtype=torch.float32)
+        ctx.save_for_backward(x2, a, w0, b0, w2, b2)
+        return y.view(*shp[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, a, w0, b0, w2, b2 = ctx.saved_tensors
+        sink = _GradSink()
+        C = w2.shape[0]
+        g = ops.cast_rows(dy.reshape(-1, C).contiguous().float(), dbias=sink.get(b2, "b2"))
+        ops.wgrad(g, a, sink.get(w2, "w2"))
+        da = ops.gemm(g, shadow(w2), b_mn=True, out_dtype=ops.act_dtype())
+        ops.pos_mlp1_bwd(da, x2, w0, b0, sink.get(w0, "w0"), sink.get(b0, "b0"))
+        r = sink.result
+        return None, r("w0"), r("b0"), r("w2"), r("b2")
+
+
+def pos_mlp(seq, x):
+    return PosMlpFn.apply(x, seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias)
+
+
+# ----------------------------------------------------------------------------- cls / mask-token rows
+class AssembleRowsFn(torch.autograd.Function):
+    """cat(fill.expand(B,T-n,C), src) (fill_first: cls token / cls pos, act.py:287-290) or cat(src, fill.expand(B,T-n,C))
+    (mask tokens, act.py:1222-1224) in one launch.  src: f32 [B, src_T, C] contiguous, of which every cloud's rows
+    [src_off, src_off+n) are used (the decoder input reads the encoder output past its cls row without a slice copy).
+    Backward: the src rows (zeros elsewhere) and the parameter row's accumulated gradient."""
+
+    @staticmethod
+    def forward(ctx, src, fill, B, n, T, fill_first, src_off):
+        C = fill.numel()
+        src = src.reshape(B, -1, C).contiguous().float()
+        out = ops.assemble_rows(src, fill, B, n, T, fill_first, src.shape[1], src_off)
+        ctx.save_for_backward(fill)
+        ctx.meta = (B, n, T, fill_first, src.shape[1], src_off)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (fill,) = ctx.saved_tensors
+        B, n, T, fill_first, src_T, src_off = ctx.meta
+        sink = _GradSink()
+        need_src = ctx.needs_input_grad[0]
+        dsrc = ops.assemble_rows_bwd(dout.contiguous().float(), B, n, T, fill_first, need_src, sink.get(fill, "f"), src_T,
+                                     src_off)
+        return dsrc, sink.result("f"), None, None, None, None, None
+
+
+def assemble_rows(src, fill, B, n, T, fill_first, src_off=0):
+    """-> f32 [B,T,C]; src may be [B*n, C] / [B, n, C] (src_off 0) or [B, src_T, C] with src_off."""
+    return AssembleRowsFn.apply(src, fill, B, n, T, fill_first, src_off)
+
+
+class LayerNormRowsFn(torch.autograd.Function):
+    """nn.LayerNorm on x[:, j0:j0+cnt] of x f32 [B,T,C] (TransformerDecoder.forward, act.py:144: the last
+    return_token_num tokens) without the slice copy of the library path: one row-gather launch feeds the LayerNorm kernel;
+    the backward scatters into a zero-padded [B,T,C] gradient with the assemble kernel."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, j0, cnt):
+        B, T, C = x.shape
+        xs = ops.gather_rows(x.contiguous().float(), None, j0, cnt).view(B * cnt, C)
+        y, _, mean, rstd = ops.layernorm_fwd(xs, weight, bias, eps, out_dtype=torch.float32)
+        ctx.save_for_backward(xs, mean, rstd, weight, bias)
+        ctx.meta = (B, T, C, j0, cnt)
+        return y.view(B, cnt, C)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs, mean, rstd, weight, bias = ctx.saved_tensors
+        B, T, C, j0, cnt = ctx.meta
+        if j0 + cnt != T:
+            raise NotImplementedError("LayerNormRowsFn backward: the selected rows must be the last ones")
+        sink = _GradSink()
+        dxs, _ = ops.layernorm_bwd(dy.reshape(B * cnt, C).contiguous().float(), xs, mean, rstd, weight,
+                                   sink.get(weight, "w"), sink.get(bias, "b"))
+        zero = _zero_row(C, dy.device)
+        dx = ops.assemble_rows(dxs, zero, B, cnt, T, True, cnt, 0)
+        return dx, sink.result("w"), sink.result("b"), None, None, None
+
+
+_ZERO_ROWS = {}
+
+
+def _zero_row(C, device):
+    key = (C, str(device))
+    if key not in _ZERO_ROWS:        # created during the eager warm-up, before any capture
+        _ZERO_ROWS[key] = torch.zeros(C, dtype=torch.float32, device=device)
+    return _ZERO_ROWS[key]
+
+
+def layer_norm_rows(x, weight, bias, eps, j0, cnt):
+    return LayerNormRowsFn.apply(x, weight, bias, eps, j0, cnt)
 
 
 # --------------------------------------------------------------------------------- mini-PointNet Encoder
@@ -504,12 +640,12 @@ class PointNetEncoderFn(torch.autograd.Function):
             dZ3 = torch.empty(M, 512, dtype=torch.bfloat16, device=d.device)
             ops.gemm(dF4, shadow(w4).view(C, 512), b_mn=True, mul_in=a3k, mul_mode=ops.MUL_RELU_MASK,
                      out=dZ3[:GK * k])
-            dZ3[GK * k:].zero_()
+            ops.zero_(dZ3[GK * k:])
         dH3, dbe2, dg2 = ops.bn_bwd(dZ3, h3, mean2, rstd2, g2)
-        sink.get(g2, "g2").add_(dg2)
-        sink.get(be2, "be2").add_(dbe2)
+        ops.accumulate_(sink.get(g2, "g2"), dg2)
+        ops.accumulate_(sink.get(be2, "be2"), dbe2)
         dGp_b, dGp_f = ops.group_sum(dH3, k, want_bf16=True, want_f32=True)       # [BG,512]
-        sink.get(b3, "b3").add_(dGp_f.sum(0))
+        ops.colsum(dGp_f, sink.get(b3, "b3"))
         gw3 = sink.get(w3, "w3").view(512, 512)
         side.run(lambda: (ops.wgrad(dH3, f2, gw3[:, 256:]), ops.wgrad(dGp_b, gmax, gw3[:, :256])), dH3, dGp_b)
         w3s = shadow(w3).view(512, 512)
@@ -521,8 +657,8 @@ class PointNetEncoderFn(torch.autograd.Function):
         dZ1 = ops.gemm(dF2, shadow(w2).view(256, 128), b_mn=True, mul_in=a1, mul_mode=ops.MUL_RELU_MASK)
         dbe1, dg1 = ops.pn_conv1_bwd(dZ1, p, w1.view(128, 3).contiguous(), b1, mean1, rstd1, g1,
                                      sink.get(w1, "w1").view(128, 3), sink.get(b1, "b1"))
-        sink.get(g1, "g1").add_(dg1)
-        sink.get(be1, "be1").add_(dbe1)
+        ops.accumulate_(sink.get(g1, "g1"), dg1)
+        ops.accumulate_(sink.get(be1, "be1"), dbe1)
         side.join()
         r = sink.result
         return (None, None, None, None, None, None, r("w1"), r("b1"), r("g1"), r("be1"), r("w2"), r("b2"), r("w3"), r("b3"),
@@ -546,7 +682,8 @@ class CosineLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dloss):
         (grad,) = ctx.saved_tensors
-        return (grad * dloss).view(ctx.shape), None
+        # the saved gradient is consumed once: scale it in place by the incoming d(loss) (1.0 in the training step)
+        return ops.scale_by_(grad, dloss.reshape(1)).view(ctx.shape), None
 
 
 def cosine_loss(student, teacher):

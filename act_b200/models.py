@@ -11,7 +11,7 @@ state_dict keys as the reference: /root/reference/models/act.py:1099-1258, utils
 import torch
 import torch.nn as nn
 
-from . import layers
+from . import layers, ops
 from .modules import Encoder, Group, TransformerDecoder, TransformerEncoder, VisableOnlyMaskTransformer, pos_mlp
 
 MODELS = {}
@@ -158,17 +158,19 @@ class ACT_PointDistillation(nn.Module):
         B, n_vis, C = x_vis.shape
         G = center.shape[1]
         num_mask = G - n_vis
-        order = self.ACT_encoder._order                       # visible groups first, then masked, original order
-        centers_sorted = torch.gather(center, 1, order[..., None].expand(-1, -1, 3))
-        pos_full = pos_mlp(self.decoder_pos_embed, centers_sorted)            # [pos(vis) | pos(mask)]
-        x_full = torch.cat([x_vis, self.mask_token.expand(B, num_mask, -1)], dim=1)
+        enc = self.ACT_encoder
+        order = enc._order                                     # visible groups first, then masked, original order
+        pos_full = pos_mlp(self.decoder_pos_embed, enc._centers_sorted)           # [pos(vis) | pos(mask)]  [B,G,C]
+        # cat([x_vis, mask_token.expand]) read straight from the encoder output past its cls row (no slice copy)
+        x_full = layers.assemble_rows(enc._encoded, self.mask_token, B, n_vis, G, False, src_off=1)
         x_dec = self.ACT_decoder(x_full, pos_full, num_mask)
         student = layers.linear(x_dec, self.proj_head.weight, self.proj_head.bias)
         return student, order, n_vis
 
     def distill_loss(self, student, teacher_feat, order, n_vis):
         """act.py:1229-1254: the teacher's features at the masked groups against the student's predictions."""
-        teacher = torch.gather(teacher_feat, 1, order[:, n_vis:, None].expand(-1, -1, student.shape[-1]))
+        G = order.shape[1]
+        teacher = ops.gather_rows(teacher_feat.detach(), order, n_vis, G - n_vis)  # teacher_feat[mask], original order
         return layers.cosine_loss(student, teacher)
 
 
@@ -271,9 +273,9 @@ class PointTransformer(nn.Module):
         tokens = self.encoder(neighborhood)                                    # B G C
         if not isinstance(self.reduce_dim, nn.Identity):
             tokens = layers.linear(tokens, self.reduce_dim.weight, self.reduce_dim.bias)
-        B = tokens.shape[0]
-        x = torch.cat((self.cls_token.expand(B, -1, -1), tokens), dim=1)
-        pos = torch.cat((self.cls_pos.expand(B, -1, -1), pos_mlp(self.pos_embed, center)), dim=1)
+        B, G = tokens.shape[:2]
+        x = layers.assemble_rows(tokens, self.cls_token, B, G, G + 1, True)               # cat(cls_token, tokens)
+        pos = layers.assemble_rows(pos_mlp(self.pos_embed, center), self.cls_pos, B, G, G + 1, True)
         x = self.blocks(x, pos)
         x = layers.layer_norm(x, self.norm.weight, self.norm.bias, self.norm.eps)
         if self.side is not None:

@@ -153,7 +153,9 @@ class TransformerDecoder(nn.Module):
 
     def forward(self, x, pos, return_token_num):
         x = run_blocks(list(self.blocks), x, pos, self.training)
-        return layers.layer_norm(x[:, -return_token_num:], self.norm.weight, self.norm.bias, self.norm.eps)
+        T = x.shape[1]
+        return layers.layer_norm_rows(x, self.norm.weight, self.norm.bias, self.norm.eps, T - return_token_num,
+                                      return_token_num)
 
 
 def mask_center_rand(B, G, mask_ratio, device):
@@ -169,10 +171,9 @@ def mask_center_rand(B, G, mask_ratio, device):
 
 
 def pos_mlp(seq, x):
-    """nn.Sequential(Linear(3,128), GELU, Linear(128,C)) (act.py:173-177, 1166-1170).  The 3->128 layer is
-    K=3 (0.4 MFLOP per cloud) and stays a PyTorch op; the 128->C layer runs on the tcgen05 GEMM."""
-    h = F.gelu(F.linear(x, seq[0].weight, seq[0].bias))
-    return layers.linear(h, seq[2].weight, seq[2].bias)
+    """nn.Sequential(Linear(3,128), GELU, Linear(128,C)) (act.py:173-177, 1166-1170): K = 3 layer + GELU on CUDA cores, the
+    128 -> C layer on the tcgen05 GEMM (layers.PosMlpFn, forward and backward)."""
+    return layers.pos_mlp(seq, x)
 
 
 class VisableOnlyMaskTransformer(nn.Module):
@@ -231,34 +232,29 @@ class VisableOnlyMaskTransformer(nn.Module):
         if mask is None:
             mask = self._mask_center_rand(center, noaug=noaug)
         num_mask = 0 if (noaug or self.mask_ratio == 0) else int(self.mask_ratio * G)
-        # visible groups in original order == tokens[~mask].reshape(B,-1,C), via a stable argsort (no host sync)
-        order = torch.argsort(mask.to(torch.uint8), dim=1, stable=True)
         n_vis = G - num_mask
-        vis_idx = order[:, :n_vis]
-        k = neighborhood.shape[2]
+        # the permutation "visible groups first" (original order inside each part) replaces the reference's boolean
+        # indexing tokens[~mask] / center[~mask] (act.py:281-284: nonzero + a host sync each); one kernel, no sync
+        order = ops.mask_order(mask)
         if num_mask > 0 and isinstance(self.reduce_dim, nn.Identity):
             # The reference embeds all G groups and then throws the masked ones away (act.py:276-281).  Both
             # BatchNorms need every point, but the last conv + max-pool only matter for visible groups: reorder
             # the groups (all clouds' visible groups first) so that those rows are one contiguous prefix.
-            nb_sorted = torch.gather(neighborhood, 1, order[:, :, None, None].expand(-1, -1, k, 3))
-            nb_perm = torch.cat([nb_sorted[:, :n_vis].reshape(B * n_vis, k, 3),
-                                 nb_sorted[:, n_vis:].reshape(B * num_mask, k, 3)], dim=0)
-            x_vis = self.encoder(nb_perm, n_keep=B * n_vis).view(B, n_vis, -1)
-            C = x_vis.shape[-1]
+            nb_perm, centers_sorted, vis_center = ops.permute_groups(neighborhood, center, order, n_vis)
+            x_vis = self.encoder(nb_perm, n_keep=B * n_vis)                       # [B*n_vis, C]
         else:
             tokens = self.encoder(neighborhood)
             if not isinstance(self.reduce_dim, nn.Identity):
                 tokens = layers.linear(tokens, self.reduce_dim.weight, self.reduce_dim.bias)
-            C = tokens.shape[-1]
-            x_vis = torch.gather(tokens, 1, vis_idx[..., None].expand(-1, -1, C))
-        vis_center = torch.gather(center, 1, vis_idx[..., None].expand(-1, -1, 3))
-        pos = pos_mlp(self.pos_embed, vis_center)
-        x_vis = torch.cat((self.cls_token.expand(B, -1, -1), x_vis), dim=1)
-        pos = torch.cat((self.cls_pos.expand(B, -1, -1), pos), dim=1)
-        x_vis = self.blocks(x_vis, pos)
-        x_vis = layers.layer_norm(x_vis, self.norm.weight, self.norm.bias, self.norm.eps)
+            _, centers_sorted, vis_center = ops.permute_groups(None, center, order, n_vis, want_nb=False)
+            x_vis = tokens if num_mask == 0 else torch.gather(tokens, 1, order[:, :n_vis, None].expand(-1, -1, tokens.shape[-1]))
+        pos = pos_mlp(self.pos_embed, vis_center)                                  # [B*n_vis, C]
+        x = layers.assemble_rows(x_vis, self.cls_token, B, n_vis, n_vis + 1, True)  # cat(cls_token, x_vis)
+        pos = layers.assemble_rows(pos, self.cls_pos, B, n_vis, n_vis + 1, True)    # cat(cls_pos, pos)
+        x = self.blocks(x, pos)
+        x = layers.layer_norm(x, self.norm.weight, self.norm.bias, self.norm.eps)
         if only_cls_tokens:
-            h = layers.linear(x_vis[:, 0], self.cls_head[0].weight, self.cls_head[0].bias, gelu=True)
+            h = layers.linear(x[:, 0], self.cls_head[0].weight, self.cls_head[0].bias, gelu=True)
             return layers.linear(h, self.cls_head[2].weight, self.cls_head[2].bias)
-        self._order = order
-        return x_vis[:, 1:], mask
+        self._order, self._centers_sorted, self._encoded = order, centers_sorted, x
+        return x[:, 1:], mask

@@ -5,6 +5,12 @@ import torch
 from . import _lib
 
 LAUNCHES = 0  # number of libact_b200 kernel launches issued through this module (bench.py reads it)
+_ACT_DTYPE = torch.bfloat16
+
+
+def act_dtype():
+    """Storage dtype of the activations that feed GEMMs: bf16 (the speed mode and default)."""
+    return _ACT_DTYPE
 
 
 def _count(n=1):
@@ -267,10 +273,128 @@ def cosine_loss(student, teacher, eps=1e-8, want_grad=True):
     return loss, grad
 
 
+def zero_(t):
+    """cudaMemsetAsync on the current stream (a memset node inside a captured graph, not a fill kernel)."""
+    assert t.is_contiguous()
+    _lib.call("act_zero", t, _lib.ctypes.c_int64(t.numel() * t.element_size()))
+    return t
+
+
+def accumulate_(dst, src):
+    """dst += src (f32, same numel, contiguous)."""
+    assert dst.dtype == torch.float32 and src.dtype == torch.float32 and dst.numel() == src.numel()
+    _lib.call("act_accumulate", dst, src.contiguous(), _lib.ctypes.c_int64(dst.numel()))
+    _count()
+    return dst
+
+
+def scale_by_(x, scalar):
+    """x *= scalar, scalar a device f32 tensor with one element."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and scalar.numel() == 1
+    _lib.call("act_scale_by", x, scalar.float(), _lib.ctypes.c_int64(x.numel()))
+    _count()
+    return x
+
+
 def adamw(param, grad, exp_avg, exp_avg_sq, shadow, n_decay, hyper):
     _lib.call("act_adamw", param, grad, exp_avg, exp_avg_sq, shadow, _lib.ctypes.c_int64(param.numel()),
               _lib.ctypes.c_int64(n_decay), hyper)
     _count()
+
+
+
+# ------------------------------------------------------------------------------ token plumbing (csrc/tokens.cu)
+def pos_mlp1_fwd(x, W, b, out_dtype=torch.bfloat16):
+    """GELU(Linear(3,128)(x)): x f32 [R,3] -> [R,128] bf16 (GEMM operand) or f32."""
+    x = _f32c(x)
+    R = x.shape[0]
+    out = torch.empty(R, 128, dtype=out_dtype, device=x.device)
+    _lib.call("act_pos_mlp1_fwd", x, W, b, R, _p(out), int(out_dtype == torch.float32))
+    _count()
+    return out
+
+
+def pos_mlp1_bwd(da, x, W, b, dW, db):
+    """Accumulates dW [128,3], db [128] from da [R,128] (bf16 or f32); the pre-activation is recomputed from x."""
+    R = x.shape[0]
+    _lib.call("act_pos_mlp1_bwd", _p(da), int(da.dtype == torch.float32), x, W, b, R, dW, db)
+    _count()
+
+
+def mask_order(mask):
+    """bool / u8 [B,G] -> i64 [B,G]: visible (mask == 0) group indices in original order, then the masked ones."""
+    B, G = mask.shape
+    m = mask.contiguous()
+    if m.dtype == torch.bool:
+        m = m.view(torch.uint8)
+    order = torch.empty(B, G, dtype=torch.int64, device=mask.device)
+    _lib.call("act_mask_order", m, B, G, order)
+    _count()
+    return order
+
+
+def permute_groups(nb, center, order, n_vis, want_nb=True):
+    """-> (nb_perm [B*G, k, 3] visible rows of all clouds first | None, center_sorted [B,G,3], vis_center [B*n_vis,3])."""
+    B, G, _ = center.shape
+    center = _f32c(center)
+    dev = center.device
+    nb_perm = None
+    rf = 0
+    if want_nb:
+        nb = _f32c(nb)
+        rf = nb[0, 0].numel()
+        nb_perm = torch.empty((B * G,) + tuple(nb.shape[2:]), dtype=torch.float32, device=dev)
+    cs = torch.empty(B, G, 3, dtype=torch.float32, device=dev)
+    vc = torch.empty(B * n_vis, 3, dtype=torch.float32, device=dev)
+    _lib.call("act_permute_groups", nb if want_nb else None, center, order, B, G, rf, n_vis, nb_perm, cs, vc)
+    _count()
+    return nb_perm, cs, vc
+
+
+def assemble_rows(src, fill, B, n, T, fill_first, src_T=None, src_off=0):
+    """src f32 [B, src_T, C] (rows [src_off, src_off+n) of every cloud) + the parameter row `fill` -> out f32 [B,T,C]."""
+    C = fill.numel()
+    out = torch.empty(B, T, C, dtype=torch.float32, device=fill.device)
+    _lib.call("act_assemble_rows", src, fill, B, n, T, C, int(fill_first), n if src_T is None else src_T, src_off, out)
+    _count()
+    return out
+
+
+def assemble_rows_bwd(dout, B, n, T, fill_first, want_dsrc, dfill, src_T=None, src_off=0):
+    C = dout.shape[-1]
+    src_T = n if src_T is None else src_T
+    dsrc = torch.empty(B, src_T, C, dtype=torch.float32, device=dout.device) if want_dsrc else None
+    _lib.call("act_assemble_rows_bwd", dout, B, n, T, C, int(fill_first), src_T, src_off, dsrc, dfill)
+    _count()
+    return dsrc
+
+
+def gather_rows(src, order, j0, cnt):
+    """src f32 [B,G,C] -> [B, cnt, C] = src[b, order[b, j0:j0+cnt]] (order None: the contiguous slice)."""
+    B, G, C = src.shape
+    out = torch.empty(B, cnt, C, dtype=torch.float32, device=src.device)
+    _lib.call("act_gather_rows", _f32c(src), order, B, G, C, int(j0), int(cnt), out)
+    _count()
+    return out
+
+
+def embedding_bf16(table, label):
+    """table bf16 [V,C], label i32 [R] -> bf16 [R,C]."""
+    V, C = table.shape
+    R = label.numel()
+    out = torch.empty(R, C, dtype=torch.bfloat16, device=table.device)
+    _lib.call("act_embedding_bf16", table, label.contiguous(), R, V, C, out)
+    _count()
+    return out
+
+
+def drop_path_gates(seed, keep, B, draw_id=0):
+    """seed: device int64 [1]; keep f32 [L] -> gates f32 [L,B] = floor(keep + U) / keep."""
+    L = keep.numel()
+    gates = torch.empty(L, B, dtype=torch.float32, device=keep.device)
+    _lib.call("act_drop_path_gates", seed, keep, L, B, int(draw_id), gates)
+    _count()
+    return gates
 
 
 # ------------------------------------------------------------------------------ mini-PointNet pieces

@@ -16,7 +16,6 @@ The pretrained ViT / dVAE weights are not obtainable offline; the module is exer
 """
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import layers, ops
 from .modules import Encoder
@@ -145,7 +144,7 @@ class ACTPromptedDiscreteVAEwithVIT(nn.Module):
             return self._cache
         c = {"d1": self._dgcnn_cache(self.dgcnn_1), "d2": self._dgcnn_cache(self.dgcnn_2),
              "pre_w": _bf(self.proj_pre.weight), "post_w": _bf(self.proj_post.weight),
-             "pos2_w": _bf(self.visual_pos_embed[2].weight), "blocks": []}
+             "pos2_w": _bf(self.visual_pos_embed[2].weight), "codebook": _bf(self.codebook), "blocks": []}
         for blk in self.visual_embed[0]:
             c["blocks"].append({"qkv": _bf(blk.attn.qkv.weight), "proj": _bf(blk.attn.proj.weight),
                                 "fc1": _bf(blk.mlp.fc1.weight), "fc2": _bf(blk.mlp.fc2.weight)})
@@ -156,7 +155,8 @@ class ACTPromptedDiscreteVAEwithVIT(nn.Module):
     def _dgcnn(self, m, c, x, idx4, B, G, noise=None, seed=None, want_labels=False):
         """x f32 [B*G, Cin] -> layer5 activations f32 [B*G, Cout], or (noise given) arg-max labels i32 [B*G]."""
         dev = x.device
-        f = ops.gemm(x.to(torch.bfloat16), c["it_w"], bias=c["it_b"])                       # [BG,128]
+        xb = x if x.dtype == torch.bfloat16 else ops.cast_rows(x.contiguous())              # C % 128 == 0
+        f = ops.gemm(xb, c["it_w"], bias=c["it_b"])                                         # [BG,128]
         feats = torch.empty(B * G, 2304, dtype=torch.bfloat16, device=dev)
         off = 0
         for i, layer in enumerate((m.layer1, m.layer2, m.layer3, m.layer4)):
@@ -189,12 +189,14 @@ class ACTPromptedDiscreteVAEwithVIT(nn.Module):
         a = ops.gemm(h2, w["fc1"], bias=blk.mlp.fc1.bias, act=ops.ACT_GELU)
         return ops.gemm(a, w["fc2"], bias=blk.mlp.fc2.bias, resid=xmid, out_dtype=torch.float32)
 
-    def _visual(self, c, sampled, center, B, G, keeps, seed=None):
+    def _visual(self, c, sampled, center, B, G, keeps, seed=None, out_dtype=torch.float32):
         """visual_embedding_deep_prompt (dvae.py:536-576)."""
         pe = self.visual_pos_embed
-        pos_tok = ops.gemm(F.gelu(F.linear(center.reshape(B * G, 3), pe[0].weight, pe[0].bias)).to(torch.bfloat16),
-                           c["pos2_w"], bias=pe[2].bias, out_dtype=torch.float32)
-        x = ops.gemm(sampled.to(torch.bfloat16), c["pre_w"], bias=self.proj_pre.bias, out_dtype=torch.float32)
+        pos_tok = ops.gemm(ops.pos_mlp1_fwd(center.reshape(B * G, 3), pe[0].weight, pe[0].bias), c["pos2_w"],
+                           bias=pe[2].bias, out_dtype=torch.float32)
+        if sampled.dtype != torch.bfloat16:
+            sampled = ops.cast_rows(sampled.float().contiguous())
+        x = ops.gemm(sampled, c["pre_w"], bias=self.proj_pre.bias, out_dtype=torch.float32)
         blocks = self.visual_embed[0]
         for i, blk in enumerate(blocks):
             if i == 0:
@@ -207,7 +209,7 @@ class ACTPromptedDiscreteVAEwithVIT(nn.Module):
             x = self._vit_block(x, pos_tok, tok.detach(), ppos.detach(), blk, c["blocks"][i], B, G, keep, seed, i)
         norm = self.visual_embed[1]
         y, _, _, _ = ops.layernorm_fwd(x, norm.weight, norm.bias, norm.eps, save_stats=False)
-        return ops.gemm(y, c["post_w"], bias=self.proj_post.bias, out_dtype=torch.float32)  # [BG, tokens_dims]
+        return ops.gemm(y, c["post_w"], bias=self.proj_post.bias, out_dtype=out_dtype)      # [BG, tokens_dims]
 
     @torch.no_grad()
     def forward_tokenizer_features(self, neighborhood, center, return_global=True, gumbel=None, keeps=None):
@@ -227,8 +229,10 @@ class ACTPromptedDiscreteVAEwithVIT(nn.Module):
         labels = self._dgcnn(self.dgcnn_1, c["d1"], tokens, idx4, B, G, noise=gumbel,
                              seed=seed if gumbel is None else None, want_labels=True)
         self.last_labels = labels
-        sampled = self.codebook.detach()[labels.long()]                                     # one-hot @ codebook
-        feature = self._visual(c, sampled, center.float(), B, G, keeps, seed)
+        sampled = ops.embedding_bf16(c["codebook"], labels)                                 # one-hot @ codebook, bf16
+        # the ViT's output feeds only dgcnn_2's first GEMM when return_global: emit its bf16 operand directly
+        feature = self._visual(c, sampled, center.float(), B, G, keeps, seed,
+                               out_dtype=torch.bfloat16 if return_global else torch.float32)
         if return_global:
             feature = self._dgcnn(self.dgcnn_2, c["d2"], feature, idx4, B, G)
         return feature.view(B, G, -1)

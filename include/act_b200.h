@@ -143,6 +143,53 @@ int act_attention_bwd(const void *qkv, const void *o, const void *dO, const floa
 /* out[N] += column sums of x[M, ld] (bf16 or f32): bias gradients. */
 int act_colsum(const void *x, int x_fp32, int M, int N, int ld, float *out, void *stream);
 
+/* ---- Token plumbing of the masked student path (models/act.py:244-290, 1219-1229) -------------------------------- */
+
+/* pos_embed[0] + pos_embed[1] = nn.Linear(3,128) + nn.GELU (act.py:173-177, 1166-1170; the teacher's visual_pos_embed,
+ * dvae.py:412-416): x f32 [R,3] -> out [R,128] = GELU(x W^T + b), bf16 (out_fp32 = 0: the A operand of the 128 -> C GEMM)
+ * or f32.  K = 3 is CUDA-core work. */
+int act_pos_mlp1_fwd(const float *x, const float *W, const float *b, int R, void *out, int out_fp32, void *stream);
+/* its backward w.r.t. the parameters (the centres carry no gradient): da [R,128] (bf16, or f32 if da_fp32) = gradient of
+ * the GELU output; the pre-activation is recomputed from x.  dW [128,3] and db [128] are ACCUMULATED INTO (atomics). */
+int act_pos_mlp1_bwd(const void *da, int da_fp32, const float *x, const float *W, const float *b, int R, float *dW,
+                     float *db, void *stream);
+
+/* bool_masked_pos -> the permutation "visible groups first" the whole student path indexes through: order i64 [B,G] =
+ * indices with mask == 0 in original order, then those with mask != 0 (== argsort(mask, stable); replaces the boolean
+ * indexing of act.py:281-284 and its host synchronisation).  mask u8 / bool [B,G]. */
+int act_mask_order(const uint8_t *mask, int B, int G, long long *order, void *stream);
+
+/* nb f32 [B,G,row_floats], center f32 [B,G,3] re-ordered through order:  nb_perm (nullable) [B*G, row_floats] = every
+ * cloud's first n_vis ordered groups (cloud-major) followed by all the remaining ones -- the mini-PointNet then computes
+ * tokens for a contiguous row prefix only;  center_sorted (nullable) [B,G,3];  vis_center (nullable) [B*n_vis,3]. */
+int act_permute_groups(const float *nb, const float *center, const long long *order, int B, int G, int row_floats,
+                       int n_vis, float *nb_perm, float *center_sorted, float *vis_center, void *stream);
+
+/* out f32 [B,T,C]: n rows per cloud taken from src f32 [B,src_T,C] (cloud b: rows [src_off, src_off+n)) and T - n copies
+ * of the parameter row fill [C]:  fill_first = 1 -> cat(fill.expand, src) (cls token / cls pos, act.py:287-290; with a
+ * zero fill: the zero-padded scatter that is the backward of x[:, -n:]); 0 -> cat(src, fill.expand) (mask tokens,
+ * act.py:1222-1224, reading the encoder output past its cls row: src_off = 1).
+ * Backward: dsrc (nullable) [B,src_T,C] = the src rows of dout, every other row zero; dfill [C] (nullable) ACCUMULATED. */
+int act_assemble_rows(const float *src, const float *fill, int B, int n, int T, int C, int fill_first, int src_T,
+                      int src_off, float *out, void *stream);
+int act_assemble_rows_bwd(const float *dout, int B, int n, int T, int C, int fill_first, int src_T, int src_off,
+                          float *dsrc, float *dfill, void *stream);
+
+/* out f32 [B*cnt, C] = src[b, order[b, j0 + i], :] (src f32 [B,G,C]; order nullable = identity): teacher_feat[mask]
+ * (act.py:1229) with j0 = n_vis, cnt = num_mask; the decoder's x[:, -return_token_num:] with order = NULL. */
+int act_gather_rows(const float *src, const long long *order, int B, int G, int C, int j0, int cnt, float *out,
+                    void *stream);
+
+/* out bf16 [R,C] = table[label[r], :] (table bf16 [V,C], label i32 [R]): the forward value of
+ * einsum(one_hot, codebook) after F.gumbel_softmax(hard=True) (dvae.py:587-588). */
+int act_embedding_bf16(const void *table, const int *label, int R, int V, int C, void *out, void *stream);
+
+/* timm DropPath (act.py:88-89): gates f32 [L,B] = floor(keep[l] + U) / keep[l], U ~ U(0,1) drawn in the kernel
+ * (Philox4x32-10) from the 64-bit *seed in DEVICE memory (a replayed CUDA graph draws fresh gates every step) and
+ * draw_id (distinguishes the Block stacks that draw from the same per-step seed). */
+int act_drop_path_gates(const unsigned long long *seed, const float *keep, int L, int B, int draw_id, float *gates,
+                        void *stream);
+
 /* ---- mini-PointNet (Encoder, models/dvae.py:185-215): everything between the four 1x1-conv GEMMs ------- */
 /* Rows are points: M = B*G*k, row m belongs to group m / k.  Activations are bf16 [M, C]. */
 
@@ -273,6 +320,14 @@ int act_scale_translate(float *pc, const float *scale_translate, int B, int N, v
  * d loss / d student. */
 int act_cosine_loss(const float *student, const float *teacher, int R, int C, float eps, float *loss,
                     float *grad_student, void *stream);
+
+/* Small pieces of the step that would otherwise be library launches inside the captured graph:
+ * act_zero: cudaMemsetAsync (optimizer.zero_grad() of the flat gradient buffer, runner_pretrain.py:157; scratch);
+ * act_accumulate: dst[i] += src[i] (per-channel BatchNorm gradients into the flat buffer);
+ * act_scale_by: x[i] *= *scalar with the scalar in device memory (the loss node's incoming gradient). */
+int act_zero(void *ptr, long long nbytes, void *stream);
+int act_accumulate(float *dst, const float *src, long long n, void *stream);
+int act_scale_by(float *x, const float *scalar, long long n, void *stream);
 
 /* torch.optim.AdamW over flat buffers (/root/reference/tools/builder.py:37-55 builds it with a decay and a
  * no-decay group): elements [0, n_decay) get weight decay, [n_decay, n) do not.  hyper (device, f32[8]) =
