@@ -56,6 +56,7 @@ struct GemmEpi {
     int atomic;            // 1: fp32 atomicAdd into out (split-K)
     int act;               // 0 none, 1 GELU(erf), 2 ReLU
     int mul_mode;          // 0 none, 1: *= GELU'(mul_in), 2: *= (mul_in > 0)
+    int aux_fp32;          // preact_out / mul_in are f32 (the fp32-grade parity mode; generic epilogue only)
     float alpha;           // scales the accumulator first
 };
 
@@ -282,7 +283,7 @@ __device__ __forceinline__ void epi_prefetch_cw(const GemmEpi &epi, EpiPre &pre,
     const int col = n + cq * CW;
     if (!FULL && col >= N) return;
     const int rows_left = FULL ? 32 : M - (row0 + rq);   // iteration i is in range iff i * RPI < rows_left
-    if (TR::has_mul(epi)) {
+    if (TR::has_mul(epi) && !(MODE == E_GENERIC && epi.aux_fp32)) {
         const __nv_bfloat16 *mp = epi.mul_in + (size_t)(row0 + rq) * epi.ldm + col;
         const size_t step = (size_t)RPI * epi.ldm;
 #pragma unroll
@@ -360,8 +361,10 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
     const size_t osz = CW == 4 ? 4 : 2;
     char *op = has_out ? reinterpret_cast<char *>(epi.out) + ((size_t)rfirst * epi.ldo + col) * osz : nullptr;
     const size_t ostep = (size_t)RPI * epi.ldo * osz;
-    char *pp = has_preact ? reinterpret_cast<char *>(epi.preact_out) + ((size_t)rfirst * epi.ldo + col) * 2 : nullptr;
-    const size_t pstep = (size_t)RPI * epi.ldo * 2;
+    const bool aux32 = G ? (epi.aux_fp32 != 0) : false;
+    const size_t psz = aux32 ? 4 : 2;
+    char *pp = has_preact ? reinterpret_cast<char *>(epi.preact_out) + ((size_t)rfirst * epi.ldo + col) * psz : nullptr;
+    const size_t pstep = (size_t)RPI * epi.ldo * psz;
     const uint32_t st4 = stage + rq * 128;            // byte address of row rq of the tile
 #pragma unroll
     for (int i = 0; i < NIT; ++i) {
@@ -391,11 +394,17 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
         }
         if (i * RPI < rows_left && has_out) {
             if (has_preact) {
-                uint32_t pk[CW / 2];
+                if (aux32) {
 #pragma unroll
-                for (int j = 0; j < CW / 2; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-                if (CW == 8) *reinterpret_cast<uint4 *>(pp) = make_uint4(pk[0], pk[1], pk[CW / 2 - 2], pk[CW / 2 - 1]);
-                else *reinterpret_cast<uint2 *>(pp) = make_uint2(pk[0], pk[1]);
+                    for (int q = 0; q < CW / 4; ++q)
+                        reinterpret_cast<float4 *>(pp)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                } else {
+                    uint32_t pk[CW / 2];
+#pragma unroll
+                    for (int j = 0; j < CW / 2; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+                    if (CW == 8) *reinterpret_cast<uint4 *>(pp) = make_uint4(pk[0], pk[1], pk[CW / 2 - 2], pk[CW / 2 - 1]);
+                    else *reinterpret_cast<uint2 *>(pp) = make_uint2(pk[0], pk[1]);
+                }
             }
             if (act_kind == 1) {
 #pragma unroll
@@ -404,7 +413,19 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
 #pragma unroll
                 for (int j = 0; j < CW; ++j) f[j] = fmaxf(f[j], 0.f);
             }
-            if (mul_mode) {
+            if (mul_mode && aux32) {      // f32 operand of the activation's derivative: read here (cold path)
+                const float *mp = reinterpret_cast<const float *>(epi.mul_in) + (size_t)(rfirst + i * RPI) * epi.ldm + col;
+#pragma unroll
+                for (int q = 0; q < CW / 4; ++q) {
+                    const float4 u = __ldg(reinterpret_cast<const float4 *>(mp) + q);
+                    const float uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (mul_mode == 1) f[4 * q + j] *= gelu_erf_grad(uu[j]);
+                        else f[4 * q + j] = uu[j] > 0.f ? f[4 * q + j] : 0.f;
+                    }
+                }
+            } else if (mul_mode) {
                 uint32_t mw[CW / 2];
                 if (CW == 8) {
                     mw[0] = pre.r[i].x; mw[1] = pre.r[i].y; mw[CW / 2 - 2] = pre.r[i].z; mw[CW / 2 - 1] = pre.r[i].w;
@@ -1135,7 +1156,7 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
                              void *preact_out, const void *mul_in, int ldm, int mul_mode, const float *resid, int ldr,
                              int resid_row_div, const float *row_scale, int rows_per_scale, float *gmax_f32,
                              void *gmax_bf16, uint8_t *garg, int ldg, float alpha, int splits, int block_n,
-                             int persistent, void *stream) {
+                             int persistent, int aux_fp32, void *stream) {
     using namespace act;
     const bool gmode = gmax_f32 || gmax_bf16 || garg;
     if (!A || !B || (!out && !gmode) || M <= 0 || N <= 0 || K <= 0) return ACT_EINVAL;
@@ -1143,7 +1164,7 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
     if ((N % 8) || (out && ((ldo % 8) || (reinterpret_cast<uintptr_t>(out) & 15)))) return ACT_EALIGN;
     if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) return ACT_EALIGN;
     if (resid && ((reinterpret_cast<uintptr_t>(resid) & 15) || (ldr % 4))) return ACT_EALIGN;
-    if (mul_in && ((reinterpret_cast<uintptr_t>(mul_in) & 15) || (ldm % 8))) return ACT_EALIGN;
+    if (mul_in && ((reinterpret_cast<uintptr_t>(mul_in) & 15) || (ldm % (aux_fp32 ? 4 : 8)))) return ACT_EALIGN;
     if (preact_out && (reinterpret_cast<uintptr_t>(preact_out) & 15)) return ACT_EALIGN;
     if (splits < 1) splits = 1;
     if (splits > 1 && !out_fp32) return ACT_EINVAL;
@@ -1156,6 +1177,7 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
     epi.mul_in = reinterpret_cast<const __nv_bfloat16 *>(mul_in);
     epi.ldo = ldo; epi.ldr = ldr; epi.ldm = ldm; epi.out_fp32 = out_fp32; epi.atomic = splits > 1 ? 1 : 0;
     epi.act = act_kind; epi.mul_mode = mul_in ? mul_mode : 0; epi.alpha = alpha;
+    epi.aux_fp32 = (aux_fp32 && (preact_out || mul_in)) ? 1 : 0;
     epi.row_scale = row_scale; epi.rows_per_scale = rows_per_scale;
     epi.resid_row_div = 1;
     epi.slab_bias = nullptr; epi.slab_div = 1; epi.ld_slab = 0;
@@ -1166,7 +1188,7 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
     }
     epi.gmax_f32 = gmax_f32; epi.gmax_bf16 = reinterpret_cast<__nv_bfloat16 *>(gmax_bf16); epi.garg = garg; epi.ldg = ldg;
     int mode = E_GENERIC;
-    if (alpha == 1.f) {
+    if (alpha == 1.f && !epi.aux_fp32) {
         const bool simple_out = !preact_out && !epi.mul_mode && !resid && !row_scale && !gmode && !epi.atomic;
         if (simple_out && !act_kind) mode = E_PLAIN;
         else if (act_kind == 1 && !epi.mul_mode && !resid && !row_scale && !gmode && !epi.atomic && !out_fp32) mode = E_GELU;

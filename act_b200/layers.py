@@ -489,21 +489,22 @@ class AssembleRowsFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, src, fill, B, n, T, fill_first, src_off):
         C = fill.numel()
+        shp = src.shape
         src = src.reshape(B, -1, C).contiguous().float()
         out = ops.assemble_rows(src, fill, B, n, T, fill_first, src.shape[1], src_off)
         ctx.save_for_backward(fill)
-        ctx.meta = (B, n, T, fill_first, src.shape[1], src_off)
+        ctx.meta = (B, n, T, fill_first, src.shape[1], src_off, shp)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         (fill,) = ctx.saved_tensors
-        B, n, T, fill_first, src_T, src_off = ctx.meta
+        B, n, T, fill_first, src_T, src_off, shp = ctx.meta
         sink = _GradSink()
         need_src = ctx.needs_input_grad[0]
         dsrc = ops.assemble_rows_bwd(dout.contiguous().float(), B, n, T, fill_first, need_src, sink.get(fill, "f"), src_T,
                                      src_off)
-        return dsrc, sink.result("f"), None, None, None, None, None
+        return (dsrc.view(shp) if need_src else None), sink.result("f"), None, None, None, None, None
 
 
 def assemble_rows(src, fill, B, n, T, fill_first, src_off=0):

@@ -154,15 +154,14 @@ class ACT_PointDistillation(nn.Module):
     def forward_student(self, neighborhood, center, mask=None):
         """The trainable half of forward() up to the projection head (act.py:1212-1228): -> (student [B,num_mask,C],
         order [B,G] = visible groups first, n_vis).  Does not need the teacher's features."""
-        x_vis, mask = self.ACT_encoder(neighborhood, center, mask=mask)
+        x_vis, mask, ex = self.ACT_encoder(neighborhood, center, mask=mask, return_extras=True)
         B, n_vis, C = x_vis.shape
         G = center.shape[1]
         num_mask = G - n_vis
-        enc = self.ACT_encoder
-        order = enc._order                                     # visible groups first, then masked, original order
-        pos_full = pos_mlp(self.decoder_pos_embed, enc._centers_sorted)           # [pos(vis) | pos(mask)]  [B,G,C]
+        order = ex["order"]                                    # visible groups first, then masked, original order
+        pos_full = pos_mlp(self.decoder_pos_embed, ex["centers_sorted"])          # [pos(vis) | pos(mask)]  [B,G,C]
         # cat([x_vis, mask_token.expand]) read straight from the encoder output past its cls row (no slice copy)
-        x_full = layers.assemble_rows(enc._encoded, self.mask_token, B, n_vis, G, False, src_off=1)
+        x_full = layers.assemble_rows(ex["encoded"], self.mask_token, B, n_vis, G, False, src_off=1)
         x_dec = self.ACT_decoder(x_full, pos_full, num_mask)
         student = layers.linear(x_dec, self.proj_head.weight, self.proj_head.bias)
         return student, order, n_vis

@@ -225,7 +225,10 @@ class VisableOnlyMaskTransformer(nn.Module):
         self.num_mask = int(self.mask_ratio * G)
         return mask_center_rand(B, G, self.mask_ratio, center.device)
 
-    def forward(self, neighborhood, center, only_cls_tokens=False, noaug=False, mask=None):
+    def forward(self, neighborhood, center, only_cls_tokens=False, noaug=False, mask=None, return_extras=False):
+        """-> (x_vis, mask) like the reference; with return_extras also the dict {order, centers_sorted, encoded} the Stage-II
+        model consumes (returned, never kept on the module: a tensor with a grad_fn stored on a module would keep the previous
+        step's autograd graph alive and release it in the middle of the next step -- e.g. inside a CUDA-graph capture)."""
         if self.mask_type != 'rand':
             raise NotImplementedError("act_b200: only mask_type 'rand' (the shipped config) is implemented")
         B, G, _ = center.shape
@@ -256,5 +259,6 @@ class VisableOnlyMaskTransformer(nn.Module):
         if only_cls_tokens:
             h = layers.linear(x[:, 0], self.cls_head[0].weight, self.cls_head[0].bias, gelu=True)
             return layers.linear(h, self.cls_head[2].weight, self.cls_head[2].bias)
-        self._order, self._centers_sorted, self._encoded = order, centers_sorted, x
+        if return_extras:
+            return x[:, 1:], mask, {"order": order, "centers_sorted": centers_sorted, "encoded": x}
         return x[:, 1:], mask

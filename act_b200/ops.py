@@ -179,7 +179,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bi
               int(act), preact_out, _p(mul_in), mul_in.stride(0) if mul_in is not None else 0, int(mul_mode),
               _p(resid), resid.stride(0) if resid is not None else 0, int(resid_row_div), row_scale,
               int(rows_per_scale), gmax_f32, gmax_bf16, garg, int(ldg), float(alpha), int(splits), int(block_n),
-              int(persistent))
+              int(persistent), 0)
     _count()
     return out
 

@@ -99,12 +99,14 @@ int act_chamfer_backward(const float *xyz1, const float *xyz2, const int32_t *id
  * CTA, -1 = choose (the pair kernel for K-major plain / residual GEMMs with at least 74 pair tiles).
  * block_n: 64 / 128 / 192 / 256 output-tile width (0 = choose).  resid_row_div: 1, or a multiple of 32 (the broadcast
  * term then enters as a per-32-row-slab bias).  rows_per_scale >= 8.  Requirements: N % 8 == 0, K % 8 == 0 pitches,
- * 16-byte aligned pointers. */
+ * 16-byte aligned pointers.
+ * aux_fp32 = 1: preact_out / mul_in are f32 instead of bf16 -- the fp32-grade parity mode, in which activations are
+ * stored in f32 and every operand reaches this GEMM as a three-way bf16 split (act_split3_bf16) with K tripled. */
 int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, int a_mn_major, int b_mn_major, int lda, int ldb,
                   void *out, int ldo, int out_fp32, const float *bias, int act_kind, void *preact_out,
                   const void *mul_in, int ldm, int mul_mode, const float *resid, int ldr, int resid_row_div,
                   const float *row_scale, int rows_per_scale, float *gmax_f32, void *gmax_bf16, uint8_t *garg, int ldg,
-                  float alpha, int splits, int block_n, int persistent, void *stream);
+                  float alpha, int splits, int block_n, int persistent, int aux_fp32, void *stream);
 
 /* ---- Transformer Block pieces (models/act.py:45-90, 109-112) ------------------------------------------ */
 
