@@ -34,6 +34,29 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return u;
 }
 
+// element-type generic 8-channel vector access: bf16 (the speed mode: one 16-byte vector) or f32 (the fp32-grade parity
+// mode, in which every stored activation is f32: two 16-byte vectors)
+template <typename T> struct V8;
+template <> struct V8<__nv_bfloat16> {
+    static __device__ __forceinline__ void ld(const __nv_bfloat16 *p, float (&f)[8]) { unpack8(__ldg(reinterpret_cast<const uint4 *>(p)), f); }
+    static __device__ __forceinline__ void ld_plain(const __nv_bfloat16 *p, float (&f)[8]) { unpack8(*reinterpret_cast<const uint4 *>(p), f); }
+    static __device__ __forceinline__ void st(__nv_bfloat16 *p, const float (&f)[8]) { *reinterpret_cast<uint4 *>(p) = pack8(f); }
+};
+template <> struct V8<float> {
+    static __device__ __forceinline__ void ld(const float *p, float (&f)[8]) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+    static __device__ __forceinline__ void ld_plain(const float *p, float (&f)[8]) {
+        const float4 a = *reinterpret_cast<const float4 *>(p), b = *(reinterpret_cast<const float4 *>(p) + 1);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+    static __device__ __forceinline__ void st(float *p, const float (&f)[8]) {
+        reinterpret_cast<float4 *>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+        reinterpret_cast<float4 *>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+};
+
 // ---- input moments: out[0..2] = sum p, out[3..8] = sum (xx, xy, xz, yy, yz, zz), in double -------------
 __global__ void __launch_bounds__(256) pn_moments_kernel(const float *__restrict__ p, long long M,
                                                          double *__restrict__ out) {
@@ -66,9 +89,10 @@ __global__ void __launch_bounds__(256) pn_moments_kernel(const float *__restrict
 }
 
 // ---- conv1 (+ folded BN1) + ReLU: out[m, c] = relu(W[c] . p[m] + b[c]) as bf16, C = 128 -----------------
+template <typename T>
 __global__ void __launch_bounds__(256) pn_conv1_kernel(const float *__restrict__ p, const float *__restrict__ W,
                                                        const float *__restrict__ b, long long M, int relu,
-                                                       __nv_bfloat16 *__restrict__ out) {
+                                                       T *__restrict__ out) {
     pdl_wait();
     pdl_trigger();
     __shared__ float sW[128 * 3], sb[128];
@@ -85,14 +109,15 @@ __global__ void __launch_bounds__(256) pn_conv1_kernel(const float *__restrict__
             float v = fmaf(sW[c * 3 + 2], z, fmaf(sW[c * 3 + 1], y, fmaf(sW[c * 3], x, sb[c])));
             f[j] = relu ? fmaxf(v, 0.f) : v;
         }
-        *reinterpret_cast<uint4 *>(out + m * 128 + c0) = pack8(f);
+        V8<T>::st(out + m * 128 + c0, f);
     }
 }
 
 // ---- max / sum over the k rows of each group -----------------------------------------------------------
 // x bf16 [G*k, C] -> out_bf16 / out_f32 (nullable each) [G, C], arg u8 [G, C] (nullable)
-__global__ void __launch_bounds__(256) group_max_kernel(const __nv_bfloat16 *__restrict__ x, int G, int k, int C,
-                                                        __nv_bfloat16 *__restrict__ out_bf16,
+template <typename T>
+__global__ void __launch_bounds__(256) group_max_kernel(const T *__restrict__ x, int G, int k, int C,
+                                                        T *__restrict__ out_bf16,
                                                         float *__restrict__ out_f32, uint8_t *__restrict__ arg) {
     pdl_wait();
     pdl_trigger();
@@ -100,19 +125,19 @@ __global__ void __launch_bounds__(256) group_max_kernel(const __nv_bfloat16 *__r
     const long long total = (long long)G * vec_per_row;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int g = (int)(i / vec_per_row), c0 = (int)(i % vec_per_row) * 8;
-        const __nv_bfloat16 *src = x + ((size_t)g * k) * C + c0;
+        const T *src = x + ((size_t)g * k) * C + c0;
         float best[8];
         int bi[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
         for (int r = 0; r < k; ++r) {
             float f[8];
-            unpack8(__ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * C)), f);
+            V8<T>::ld(src + (size_t)r * C, f);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 if (f[j] > best[j]) { best[j] = f[j]; bi[j] = r; }
         }
-        if (out_bf16) *reinterpret_cast<uint4 *>(out_bf16 + (size_t)g * C + c0) = pack8(best);
+        if (out_bf16) V8<T>::st(out_bf16 + (size_t)g * C + c0, best);
         if (out_f32) {
             *reinterpret_cast<float4 *>(out_f32 + (size_t)g * C + c0) = make_float4(best[0], best[1], best[2], best[3]);
             *reinterpret_cast<float4 *>(out_f32 + (size_t)g * C + c0 + 4) = make_float4(best[4], best[5], best[6], best[7]);
@@ -127,9 +152,10 @@ __global__ void __launch_bounds__(256) group_max_kernel(const __nv_bfloat16 *__r
 }
 
 // scatter of the max's gradient: dF[g*k + r, c] (+)= (arg[g,c] == r) ? dout[g,c] : 0      (dense, bf16)
+template <typename T>
 __global__ void __launch_bounds__(256) group_max_bwd_kernel(const float *__restrict__ dout,
                                                             const uint8_t *__restrict__ arg, int G, int k, int C,
-                                                            int accumulate, __nv_bfloat16 *__restrict__ dF) {
+                                                            int accumulate, T *__restrict__ dF) {
     pdl_wait();
     pdl_trigger();
     const int vec_per_row = C / 8;
@@ -143,23 +169,24 @@ __global__ void __launch_bounds__(256) group_max_bwd_kernel(const float *__restr
         int a[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) { a[j] = (pk.x >> (8 * j)) & 0xff; a[4 + j] = (pk.y >> (8 * j)) & 0xff; }
-        __nv_bfloat16 *dst = dF + ((size_t)g * k) * C + c0;
+        T *dst = dF + ((size_t)g * k) * C + c0;
         for (int r = 0; r < k; ++r) {
             float f[8];
-            if (accumulate) unpack8(*reinterpret_cast<const uint4 *>(dst + (size_t)r * C), f);
+            if (accumulate) V8<T>::ld_plain(dst + (size_t)r * C, f);
             else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] = 0.f;
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] += (a[j] == r) ? d[j] : 0.f;
-            *reinterpret_cast<uint4 *>(dst + (size_t)r * C) = pack8(f);
+            V8<T>::st(dst + (size_t)r * C, f);
         }
     }
 }
 
-__global__ void __launch_bounds__(256) group_sum_kernel(const __nv_bfloat16 *__restrict__ x, int G, int k, int C,
-                                                        __nv_bfloat16 *__restrict__ out_bf16,
+template <typename T>
+__global__ void __launch_bounds__(256) group_sum_kernel(const T *__restrict__ x, int G, int k, int C,
+                                                        T *__restrict__ out_bf16,
                                                         float *__restrict__ out_f32) {
     pdl_wait();
     pdl_trigger();
@@ -167,17 +194,17 @@ __global__ void __launch_bounds__(256) group_sum_kernel(const __nv_bfloat16 *__r
     const long long total = (long long)G * vec_per_row;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int g = (int)(i / vec_per_row), c0 = (int)(i % vec_per_row) * 8;
-        const __nv_bfloat16 *src = x + ((size_t)g * k) * C + c0;
+        const T *src = x + ((size_t)g * k) * C + c0;
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
         for (int r = 0; r < k; ++r) {
             float f[8];
-            unpack8(__ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * C)), f);
+            V8<T>::ld(src + (size_t)r * C, f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] += f[j];
         }
-        if (out_bf16) *reinterpret_cast<uint4 *>(out_bf16 + (size_t)g * C + c0) = pack8(acc);
+        if (out_bf16) V8<T>::st(out_bf16 + (size_t)g * C + c0, acc);
         if (out_f32) {
             *reinterpret_cast<float4 *>(out_f32 + (size_t)g * C + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
             *reinterpret_cast<float4 *>(out_f32 + (size_t)g * C + c0 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
@@ -189,9 +216,9 @@ __global__ void __launch_bounds__(256) group_sum_kernel(const __nv_bfloat16 *__r
 // MODE 0: s1 = sum x, s2 = sum x^2                         (BatchNorm forward statistics)
 // MODE 1: s1 = sum dz, s2 = sum dz * xhat, xhat from x      (BatchNorm backward statistics)
 // Thread = 8 channels of one row; threads of a CTA tile [rows_per_cta][C/8]; partials -> smem -> atomics.
-template <int MODE>
-__global__ void __launch_bounds__(256) chan_reduce_kernel(const __nv_bfloat16 *__restrict__ a,
-                                                          const __nv_bfloat16 *__restrict__ x,
+template <int MODE, typename T>
+__global__ void __launch_bounds__(256) chan_reduce_kernel(const T *__restrict__ a,
+                                                          const T *__restrict__ x,
                                                           const float *__restrict__ mean,
                                                           const float *__restrict__ rstd, long long M, int C,
                                                           float *__restrict__ s1, float *__restrict__ s2) {
@@ -211,7 +238,7 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const __nv_bfloat16 *_
         }
         for (long long m = blockIdx.x * (long long)rpc + rl; m < M; m += (long long)gridDim.x * rpc) {
             float f[8];
-            unpack8(__ldg(reinterpret_cast<const uint4 *>(a + m * C + c0)), f);
+            V8<T>::ld(a + m * C + c0, f);
             if (MODE == 2) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc1[j] += f[j];
@@ -220,7 +247,7 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const __nv_bfloat16 *_
                 for (int j = 0; j < 8; ++j) { acc1[j] += f[j]; acc2[j] = fmaf(f[j], f[j], acc2[j]); }
             } else {
                 float xv[8];
-                unpack8(__ldg(reinterpret_cast<const uint4 *>(x + m * C + c0)), xv);
+                V8<T>::ld(x + m * C + c0, xv);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { acc1[j] += f[j]; acc2[j] = fmaf(f[j], (xv[j] - mu[j]) * rs[j], acc2[j]); }
             }
@@ -239,10 +266,11 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const __nv_bfloat16 *_
 
 // y = relu?(x * scale[c] + shift[c]).  Threads tile [rows][C/8] so a thread keeps ITS 8 channels' parameters
 // in registers for every row it visits.
-__global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16 *__restrict__ x,
+template <typename T>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const T *__restrict__ x,
                                                        const float *__restrict__ scale,
                                                        const float *__restrict__ shift, long long M, int C, int relu,
-                                                       __nv_bfloat16 *__restrict__ y) {
+                                                       T *__restrict__ y) {
     pdl_wait();
     pdl_trigger();
     const int vpr = C / 8, rpc = 256 / vpr;
@@ -254,24 +282,25 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16 *__re
     for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + c0 + j); sh[j] = __ldg(shift + c0 + j); }
     for (long long m = blockIdx.x * (long long)rpc + rl; m < M; m += (long long)gridDim.x * rpc) {
         float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4 *>(x + m * C + c0)), f);
+        V8<T>::ld(x + m * C + c0, f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float t = fmaf(f[j], sc[j], sh[j]);
             f[j] = relu ? fmaxf(t, 0.f) : t;
         }
-        *reinterpret_cast<uint4 *>(y + m * C + c0) = pack8(f);
+        V8<T>::st(y + m * C + c0, f);
     }
 }
 
 // dH = gamma * rstd * (dz - s1/M - xhat * s2/M)  ==  a[c] * dz + b[c] * x + k[c]   (per-channel constants)
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16 *__restrict__ dz,
-                                                           const __nv_bfloat16 *__restrict__ x,
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T *__restrict__ dz,
+                                                           const T *__restrict__ x,
                                                            const float *__restrict__ mean,
                                                            const float *__restrict__ rstd,
                                                            const float *__restrict__ gamma,
                                                            const float *__restrict__ s1, const float *__restrict__ s2,
-                                                           long long M, int C, __nv_bfloat16 *__restrict__ dh) {
+                                                           long long M, int C, T *__restrict__ dh) {
     pdl_wait();
     pdl_trigger();
     const int vpr = C / 8, rpc = 256 / vpr;
@@ -291,11 +320,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16 *
     }
     for (long long m = blockIdx.x * (long long)rpc + rl; m < M; m += (long long)gridDim.x * rpc) {
         float d[8], xv[8];
-        unpack8(__ldg(reinterpret_cast<const uint4 *>(dz + m * C + c0)), d);
-        unpack8(__ldg(reinterpret_cast<const uint4 *>(x + m * C + c0)), xv);
+        V8<T>::ld(dz + m * C + c0, d);
+        V8<T>::ld(x + m * C + c0, xv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) d[j] = fmaf(ka[j], d[j], fmaf(kb[j], xv[j], kc[j]));
-        *reinterpret_cast<uint4 *>(dh + m * C + c0) = pack8(d);
+        V8<T>::st(dh + m * C + c0, d);
     }
 }
 
@@ -304,8 +333,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16 *
 // ReLU-masked by the conv2 dgrad epilogue).
 // PASS 0: s1[c] += sum dz, s2[c] += sum dz * xhat.
 // PASS 1: dh = gamma*rstd*(dz - s1/M - xhat*s2/M);  dW[c,:] += sum dh * p;  db[c] += sum dh.
-template <int PASS>
-__global__ void __launch_bounds__(256) pn_conv1_bwd_kernel(const __nv_bfloat16 *__restrict__ dz,
+template <int PASS, typename T>
+__global__ void __launch_bounds__(256) pn_conv1_bwd_kernel(const T *__restrict__ dz,
                                                            const float *__restrict__ p, const float *__restrict__ W,
                                                            const float *__restrict__ b, const float *__restrict__ mean,
                                                            const float *__restrict__ rstd,
@@ -332,7 +361,7 @@ __global__ void __launch_bounds__(256) pn_conv1_bwd_kernel(const __nv_bfloat16 *
     for (long long m = blockIdx.x * 16LL + rl; m < M; m += gridDim.x * 16LL) {
         const float x = __ldg(p + m * 3), y = __ldg(p + m * 3 + 1), z = __ldg(p + m * 3 + 2);
         float d[8];
-        unpack8(__ldg(reinterpret_cast<const uint4 *>(dz + m * 128 + c0)), d);
+        V8<T>::ld(dz + m * 128 + c0, d);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float h = fmaf(w[j][2], z, fmaf(w[j][1], y, fmaf(w[j][0], x, bb[j])));
@@ -446,12 +475,17 @@ extern "C" int act_pn_moments(const float *points, long long M, double *out9, vo
     return ACT_OK;
 }
 
-extern "C" int act_pn_conv1(const float *points, const float *W, const float *b, long long M, int relu, void *out_bf16,
-                            void *stream) {
+extern "C" int act_pn_conv1(const float *points, const float *W, const float *b, long long M, int relu, void *out,
+                            int out_fp32, void *stream) {
     using namespace act;
-    if (!points || !W || !b || !out_bf16 || M <= 0) return ACT_EINVAL;
-    ACT_CUDA(launch_k(pn_conv1_kernel, dim3(grid_for(M, 16 * 8)), dim3(256), 0, (cudaStream_t)stream, true, points, W, b, M,
-                      relu, reinterpret_cast<__nv_bfloat16 *>(out_bf16)));
+    if (!points || !W || !b || !out || M <= 0) return ACT_EINVAL;
+    const dim3 grid(grid_for(M, 16 * 8));
+    if (out_fp32)
+        ACT_CUDA(launch_k(pn_conv1_kernel<float>, grid, dim3(256), 0, (cudaStream_t)stream, true, points, W, b, M, relu,
+                          reinterpret_cast<float *>(out)));
+    else
+        ACT_CUDA(launch_k(pn_conv1_kernel<__nv_bfloat16>, grid, dim3(256), 0, (cudaStream_t)stream, true, points, W, b, M,
+                          relu, reinterpret_cast<__nv_bfloat16 *>(out)));
     return ACT_OK;
 }
 
@@ -480,110 +514,131 @@ extern "C" int act_bn_finalize(const float *sum, const float *sumsq, long long M
     return ACT_OK;
 }
 
-extern "C" int act_group_max(const void *x_bf16, int G, int k, int C, void *out_bf16, float *out_f32, uint8_t *arg,
+// IO_DISPATCH: instantiate CALL once with T = float (io_fp32) and once with T = __nv_bfloat16
+#define ACT_IO_DISPATCH(io_fp32, CALL)          \
+    do {                                        \
+        if (io_fp32) {                          \
+            using T = float;                    \
+            CALL;                               \
+        } else {                                \
+            using T = __nv_bfloat16;            \
+            CALL;                               \
+        }                                       \
+    } while (0)
+
+extern "C" int act_group_max(const void *x, int G, int k, int C, void *out_act, float *out_f32, uint8_t *arg, int io_fp32,
                              void *stream) {
     using namespace act;
-    if (!x_bf16 || G <= 0 || k <= 0 || k > 255 || C <= 0) return ACT_EINVAL;
+    if (!x || G <= 0 || k <= 0 || k > 255 || C <= 0) return ACT_EINVAL;
     if (C % 8) return ACT_EUNSUPPORTED;
-    ACT_CUDA(launch_k(group_max_kernel, dim3(grid_for((long long)G * C / 8, 256)), dim3(256), 0, (cudaStream_t)stream, true,
-                      reinterpret_cast<const __nv_bfloat16 *>(x_bf16), G, k, C,
-                      reinterpret_cast<__nv_bfloat16 *>(out_bf16), out_f32, arg));
+    ACT_IO_DISPATCH(io_fp32, ACT_CUDA(launch_k(group_max_kernel<T>, dim3(grid_for((long long)G * C / 8, 256)), dim3(256), 0,
+                                               (cudaStream_t)stream, true, reinterpret_cast<const T *>(x), G, k, C,
+                                               reinterpret_cast<T *>(out_act), out_f32, arg)));
     return ACT_OK;
 }
 
-extern "C" int act_group_max_bwd(const float *dout, const uint8_t *arg, int G, int k, int C, int accumulate,
-                                 void *dF_bf16, void *stream) {
+extern "C" int act_group_max_bwd(const float *dout, const uint8_t *arg, int G, int k, int C, int accumulate, void *dF,
+                                 int io_fp32, void *stream) {
     using namespace act;
-    if (!dout || !arg || !dF_bf16 || G <= 0 || k <= 0 || C <= 0) return ACT_EINVAL;
+    if (!dout || !arg || !dF || G <= 0 || k <= 0 || C <= 0) return ACT_EINVAL;
     if (C % 8) return ACT_EUNSUPPORTED;
-    ACT_CUDA(launch_k(group_max_bwd_kernel, dim3(grid_for((long long)G * C / 8, 256)), dim3(256), 0, (cudaStream_t)stream,
-                      true, dout, arg, G, k, C, accumulate, reinterpret_cast<__nv_bfloat16 *>(dF_bf16)));
+    ACT_IO_DISPATCH(io_fp32, ACT_CUDA(launch_k(group_max_bwd_kernel<T>, dim3(grid_for((long long)G * C / 8, 256)), dim3(256),
+                                               0, (cudaStream_t)stream, true, dout, arg, G, k, C, accumulate,
+                                               reinterpret_cast<T *>(dF))));
     return ACT_OK;
 }
 
-extern "C" int act_group_sum(const void *x_bf16, int G, int k, int C, void *out_bf16, float *out_f32, void *stream) {
+extern "C" int act_group_sum(const void *x, int G, int k, int C, void *out_act, float *out_f32, int io_fp32, void *stream) {
     using namespace act;
-    if (!x_bf16 || G <= 0 || k <= 0 || C <= 0) return ACT_EINVAL;
+    if (!x || G <= 0 || k <= 0 || C <= 0) return ACT_EINVAL;
     if (C % 8) return ACT_EUNSUPPORTED;
-    ACT_CUDA(launch_k(group_sum_kernel, dim3(grid_for((long long)G * C / 8, 256)), dim3(256), 0, (cudaStream_t)stream, true,
-                      reinterpret_cast<const __nv_bfloat16 *>(x_bf16), G, k, C,
-                      reinterpret_cast<__nv_bfloat16 *>(out_bf16), out_f32));
+    ACT_IO_DISPATCH(io_fp32, ACT_CUDA(launch_k(group_sum_kernel<T>, dim3(grid_for((long long)G * C / 8, 256)), dim3(256), 0,
+                                               (cudaStream_t)stream, true, reinterpret_cast<const T *>(x), G, k, C,
+                                               reinterpret_cast<T *>(out_act), out_f32)));
+    return ACT_OK;
+}
+
+template <typename T>
+static int chan_reduce_t(int mode, const void *a, const void *x, const float *mean, const float *rstd, long long M, int C,
+                         float *s1, float *s2, cudaStream_t st) {
+    using namespace act;
+    const int rpc = 256 / (C / 8);
+    const size_t smem = (size_t)rpc * 2 * C * sizeof(float);
+    const int grid = grid_for(M, rpc * 32);
+    const T *ap = reinterpret_cast<const T *>(a), *xp = reinterpret_cast<const T *>(x);
+    if (mode == 0) ACT_CUDA(launch_k(chan_reduce_kernel<0, T>, dim3(grid), dim3(256), smem, st, true, ap, xp, mean, rstd, M, C, s1, s2));
+    else if (mode == 1) ACT_CUDA(launch_k(chan_reduce_kernel<1, T>, dim3(grid), dim3(256), smem, st, true, ap, xp, mean, rstd, M, C, s1, s2));
+    else ACT_CUDA(launch_k(chan_reduce_kernel<2, T>, dim3(grid), dim3(256), smem, st, true, ap, xp, mean, rstd, M, C, s1, s2));
     return ACT_OK;
 }
 
 static int chan_reduce(int mode, const void *a, const void *x, const float *mean, const float *rstd, long long M, int C,
-                       float *s1, float *s2, cudaStream_t st) {
-    using namespace act;
+                       float *s1, float *s2, int io_fp32, cudaStream_t st) {
     if (!a || !s1 || (!s2 && mode != 2) || M <= 0 || C <= 0) return ACT_EINVAL;
     if (C % 8 || C / 8 > 256) return ACT_EUNSUPPORTED;
     if (mode != 2) {
         ACT_CUDA(cudaMemsetAsync(s1, 0, C * sizeof(float), st));
         ACT_CUDA(cudaMemsetAsync(s2, 0, C * sizeof(float), st));
     }
-    const int rpc = 256 / (C / 8);
-    const size_t smem = (size_t)rpc * 2 * C * sizeof(float);
-    const int grid = grid_for(M, rpc * 32);
-    const __nv_bfloat16 *ap = reinterpret_cast<const __nv_bfloat16 *>(a), *xp = reinterpret_cast<const __nv_bfloat16 *>(x);
-    if (mode == 0) ACT_CUDA(launch_k(chan_reduce_kernel<0>, dim3(grid), dim3(256), smem, st, true, ap, xp, mean, rstd, M, C, s1, s2));
-    else if (mode == 1) ACT_CUDA(launch_k(chan_reduce_kernel<1>, dim3(grid), dim3(256), smem, st, true, ap, xp, mean, rstd, M, C, s1, s2));
-    else ACT_CUDA(launch_k(chan_reduce_kernel<2>, dim3(grid), dim3(256), smem, st, true, ap, xp, mean, rstd, M, C, s1, s2));
-    return ACT_OK;
+    return io_fp32 ? chan_reduce_t<float>(mode, a, x, mean, rstd, M, C, s1, s2, st)
+                   : chan_reduce_t<__nv_bfloat16>(mode, a, x, mean, rstd, M, C, s1, s2, st);
 }
 
-// out[C] += column sums of a bf16 [M,C] matrix (dense pitch): the wide-row variant of act_colsum
-extern "C" int act_colsum_bf16_dense(const void *x_bf16, long long M, int C, float *out, void *stream) {
-    return chan_reduce(2, x_bf16, nullptr, nullptr, nullptr, M, C, out, nullptr, (cudaStream_t)stream);
+// out[C] += column sums of a dense [M,C] matrix (bf16, or f32 with io_fp32): the wide-row variant of act_colsum
+extern "C" int act_colsum_bf16_dense(const void *x, long long M, int C, float *out, int io_fp32, void *stream) {
+    return chan_reduce(2, x, nullptr, nullptr, nullptr, M, C, out, nullptr, io_fp32, (cudaStream_t)stream);
 }
 
-extern "C" int act_bn_stats(const void *x_bf16, long long M, int C, float *sum, float *sumsq, void *stream) {
-    return chan_reduce(0, x_bf16, nullptr, nullptr, nullptr, M, C, sum, sumsq, (cudaStream_t)stream);
+extern "C" int act_bn_stats(const void *x, long long M, int C, float *sum, float *sumsq, int io_fp32, void *stream) {
+    return chan_reduce(0, x, nullptr, nullptr, nullptr, M, C, sum, sumsq, io_fp32, (cudaStream_t)stream);
 }
 
-extern "C" int act_bn_bwd_stats(const void *dz_bf16, const void *x_bf16, const float *mean, const float *rstd,
-                                long long M, int C, float *sum_dz, float *sum_dz_xhat, void *stream) {
-    if (!x_bf16 || !mean || !rstd) return ACT_EINVAL;
-    return chan_reduce(1, dz_bf16, x_bf16, mean, rstd, M, C, sum_dz, sum_dz_xhat, (cudaStream_t)stream);
+extern "C" int act_bn_bwd_stats(const void *dz, const void *x, const float *mean, const float *rstd, long long M, int C,
+                                float *sum_dz, float *sum_dz_xhat, int io_fp32, void *stream) {
+    if (!x || !mean || !rstd) return ACT_EINVAL;
+    return chan_reduce(1, dz, x, mean, rstd, M, C, sum_dz, sum_dz_xhat, io_fp32, (cudaStream_t)stream);
 }
 
-extern "C" int act_bn_apply(const void *x_bf16, const float *scale, const float *shift, long long M, int C, int relu,
-                            void *y_bf16, void *stream) {
+extern "C" int act_bn_apply(const void *x, const float *scale, const float *shift, long long M, int C, int relu, void *y,
+                            int io_fp32, void *stream) {
     using namespace act;
-    if (!x_bf16 || !scale || !shift || !y_bf16 || M <= 0 || C <= 0) return ACT_EINVAL;
+    if (!x || !scale || !shift || !y || M <= 0 || C <= 0) return ACT_EINVAL;
     if (C % 8) return ACT_EUNSUPPORTED;
     if (C / 8 > 256) return ACT_EUNSUPPORTED;
-    ACT_CUDA(launch_k(bn_apply_kernel, dim3(grid_for(M, (256 / (C / 8)) * 16)), dim3(256), 0, (cudaStream_t)stream, true,
-                      reinterpret_cast<const __nv_bfloat16 *>(x_bf16), scale, shift, M, C, relu,
-                      reinterpret_cast<__nv_bfloat16 *>(y_bf16)));
+    ACT_IO_DISPATCH(io_fp32, ACT_CUDA(launch_k(bn_apply_kernel<T>, dim3(grid_for(M, (256 / (C / 8)) * 16)), dim3(256), 0,
+                                               (cudaStream_t)stream, true, reinterpret_cast<const T *>(x), scale, shift, M, C,
+                                               relu, reinterpret_cast<T *>(y))));
     return ACT_OK;
 }
 
-extern "C" int act_bn_bwd_apply(const void *dz_bf16, const void *x_bf16, const float *mean, const float *rstd,
-                                const float *gamma, const float *sum_dz, const float *sum_dz_xhat, long long M, int C,
-                                void *dh_bf16, void *stream) {
+extern "C" int act_bn_bwd_apply(const void *dz, const void *x, const float *mean, const float *rstd, const float *gamma,
+                                const float *sum_dz, const float *sum_dz_xhat, long long M, int C, void *dh, int io_fp32,
+                                void *stream) {
     using namespace act;
-    if (!dz_bf16 || !x_bf16 || !mean || !rstd || !gamma || !sum_dz || !sum_dz_xhat || !dh_bf16 || M <= 0 || C <= 0)
-        return ACT_EINVAL;
+    if (!dz || !x || !mean || !rstd || !gamma || !sum_dz || !sum_dz_xhat || !dh || M <= 0 || C <= 0) return ACT_EINVAL;
     if (C % 8 || C / 8 > 256) return ACT_EUNSUPPORTED;
-    ACT_CUDA(launch_k(bn_bwd_apply_kernel, dim3(grid_for(M, (256 / (C / 8)) * 16)), dim3(256), 0, (cudaStream_t)stream, true,
-                      reinterpret_cast<const __nv_bfloat16 *>(dz_bf16), reinterpret_cast<const __nv_bfloat16 *>(x_bf16),
-                      mean, rstd, gamma, sum_dz, sum_dz_xhat, M, C, reinterpret_cast<__nv_bfloat16 *>(dh_bf16)));
+    ACT_IO_DISPATCH(io_fp32, ACT_CUDA(launch_k(bn_bwd_apply_kernel<T>, dim3(grid_for(M, (256 / (C / 8)) * 16)), dim3(256), 0,
+                                               (cudaStream_t)stream, true, reinterpret_cast<const T *>(dz),
+                                               reinterpret_cast<const T *>(x), mean, rstd, gamma, sum_dz, sum_dz_xhat, M, C,
+                                               reinterpret_cast<T *>(dh))));
     return ACT_OK;
 }
 
-extern "C" int act_pn_conv1_bwd(const void *dz_bf16, const float *points, const float *W, const float *b,
-                                const float *mean, const float *rstd, const float *gamma, long long M, float *s1,
-                                float *s2, float *dW, float *db, void *stream) {
+extern "C" int act_pn_conv1_bwd(const void *dz, const float *points, const float *W, const float *b, const float *mean,
+                                const float *rstd, const float *gamma, long long M, float *s1, float *s2, float *dW,
+                                float *db, int io_fp32, void *stream) {
     using namespace act;
-    if (!dz_bf16 || !points || !W || !b || !mean || !rstd || !gamma || !s1 || !s2 || !dW || !db || M <= 0)
-        return ACT_EINVAL;
+    if (!dz || !points || !W || !b || !mean || !rstd || !gamma || !s1 || !s2 || !dW || !db || M <= 0) return ACT_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     ACT_CUDA(cudaMemsetAsync(s1, 0, 128 * sizeof(float), st));
     ACT_CUDA(cudaMemsetAsync(s2, 0, 128 * sizeof(float), st));
-    const __nv_bfloat16 *dz = reinterpret_cast<const __nv_bfloat16 *>(dz_bf16);
     const int grid = grid_for(M, 16 * 32);
-    ACT_CUDA(launch_k(pn_conv1_bwd_kernel<0>, dim3(grid), dim3(256), 0, st, true, dz, points, W, b, mean, rstd, gamma, s1, s2,
-                      M, dW, db));
-    ACT_CUDA(launch_k(pn_conv1_bwd_kernel<1>, dim3(grid), dim3(256), 0, st, true, dz, points, W, b, mean, rstd, gamma, s1, s2,
-                      M, dW, db));
+    ACT_IO_DISPATCH(io_fp32, {
+        const T *d = reinterpret_cast<const T *>(dz);
+        ACT_CUDA(launch_k(pn_conv1_bwd_kernel<0, T>, dim3(grid), dim3(256), 0, st, true, d, points, W, b, mean, rstd, gamma, s1,
+                          s2, M, dW, db));
+        ACT_CUDA(launch_k(pn_conv1_bwd_kernel<1, T>, dim3(grid), dim3(256), 0, st, true, d, points, W, b, mean, rstd, gamma, s1,
+                          s2, M, dW, db));
+    });
     return ACT_OK;
 }

@@ -96,12 +96,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void *__restri
                                                             const float *__restrict__ dres, int M,
                                                             float *__restrict__ dx_out, float *__restrict__ dgamma,
                                                             float *__restrict__ dbeta, float *__restrict__ dacc,
-                                                            __nv_bfloat16 *__restrict__ g_bf16,
+                                                            void *__restrict__ g_out, int g_fp32,
                                                             const float *__restrict__ row_scale, int rows_per_scale,
                                                             float *__restrict__ dbias) {
     constexpr int C = 128 * VPL;
     __shared__ float s_part[8][C];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __nv_bfloat16 *g_bf16 = g_fp32 ? nullptr : reinterpret_cast<__nv_bfloat16 *>(g_out);
+    float *g_f32 = g_fp32 ? reinterpret_cast<float *>(g_out) : nullptr;
     float4 ag[VPL], ab[VPL], ac[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) ag[i] = ab[i] = ac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -160,10 +162,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void *__restri
                 a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
                 *ap = a;
             }
-            if (g_bf16 || dbias) {
+            if (g_bf16 || g_f32 || dbias) {
                 const float sc = row_scale ? __ldg(row_scale + row / rows_per_scale) : 1.f;
                 o.x *= sc; o.y *= sc; o.z *= sc; o.w *= sc;
                 ac[i].x += o.x; ac[i].y += o.y; ac[i].z += o.z; ac[i].w += o.w;
+                if (g_f32) reinterpret_cast<float4 *>(g_f32 + (size_t)row * C)[lane + 32 * i] = o;
                 if (g_bf16) {
                     uint2 pk;
                     *reinterpret_cast<__nv_bfloat162 *>(&pk.x) = __floats2bfloat162_rn(o.x, o.y);
@@ -196,10 +199,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void *__restri
 template <int VPL>
 __global__ void __launch_bounds__(256) cast_rows_kernel(const float *__restrict__ x, int M,
                                                         const float *__restrict__ row_scale, int rows_per_scale,
-                                                        __nv_bfloat16 *__restrict__ g_bf16, float *__restrict__ dbias) {
+                                                        void *__restrict__ g_out, int g_fp32, float *__restrict__ dbias) {
     constexpr int C = 128 * VPL;
     __shared__ float s_part[8][C];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __nv_bfloat16 *g_bf16 = reinterpret_cast<__nv_bfloat16 *>(g_out);
     float4 ac[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) ac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -210,10 +214,14 @@ __global__ void __launch_bounds__(256) cast_rows_kernel(const float *__restrict_
             float4 o = __ldg(reinterpret_cast<const float4 *>(x + (size_t)row * C) + lane + 32 * i);
             o.x *= sc; o.y *= sc; o.z *= sc; o.w *= sc;
             ac[i].x += o.x; ac[i].y += o.y; ac[i].z += o.z; ac[i].w += o.w;
-            uint2 pk;
-            *reinterpret_cast<__nv_bfloat162 *>(&pk.x) = __floats2bfloat162_rn(o.x, o.y);
-            *reinterpret_cast<__nv_bfloat162 *>(&pk.y) = __floats2bfloat162_rn(o.z, o.w);
-            reinterpret_cast<uint2 *>(g_bf16 + (size_t)row * C)[lane + 32 * i] = pk;
+            if (g_fp32) {
+                reinterpret_cast<float4 *>(reinterpret_cast<float *>(g_out) + (size_t)row * C)[lane + 32 * i] = o;
+            } else {
+                uint2 pk;
+                *reinterpret_cast<__nv_bfloat162 *>(&pk.x) = __floats2bfloat162_rn(o.x, o.y);
+                *reinterpret_cast<__nv_bfloat162 *>(&pk.y) = __floats2bfloat162_rn(o.z, o.w);
+                reinterpret_cast<uint2 *>(g_bf16 + (size_t)row * C)[lane + 32 * i] = pk;
+            }
         }
     }
     if (dbias) {
@@ -248,6 +256,26 @@ __device__ __forceinline__ void load_row32(const __nv_bfloat16 *src, float (&dst
             dst[i * 8 + 2 * t] = f.x;
             dst[i * 8 + 2 * t + 1] = f.y;
         }
+    }
+}
+__device__ __forceinline__ void load_row32(const float *src, float (&dst)[32]) {
+    const float4 *p = reinterpret_cast<const float4 *>(src);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 u = __ldg(p + i);
+        dst[4 * i] = u.x; dst[4 * i + 1] = u.y; dst[4 * i + 2] = u.z; dst[4 * i + 3] = u.w;
+    }
+}
+__device__ __forceinline__ void store_row32(float *dst, const float (&src)[32]) {
+    float4 *p = reinterpret_cast<float4 *>(dst);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) p[i] = make_float4(src[4 * i], src[4 * i + 1], src[4 * i + 2], src[4 * i + 3]);
+}
+__device__ __forceinline__ void stage_rows_f32(float *dst, const float *src, int ld, int rows) {
+    for (int i = threadIdx.x; i < rows * 16; i += blockDim.x) {
+        const int r = i >> 4, c = i & 15;
+        const float4 u = __ldg(reinterpret_cast<const float4 *>(src + (size_t)r * ld) + c);
+        *reinterpret_cast<float4 *>(dst + r * AT_PITCH + c * 4 + (c >= 8 ? 4 : 0)) = u;
     }
 }
 __device__ __forceinline__ void store_row32(__nv_bfloat16 *dst, const float (&src)[32]) {
@@ -295,9 +323,9 @@ __device__ __forceinline__ void axpy32(float (&acc)[32], float w, const float *b
 }
 
 // forward: o[b*T+i, h*64 + :] = softmax(q k^T * scale) v ; lse[b,h,i] = log-sum-exp of the scaled scores.
-template <int QT>
-__global__ void __launch_bounds__(QT * 2) attention_fwd_kernel(const __nv_bfloat16 *__restrict__ qkv, int T, int H,
-                                                               float scale, __nv_bfloat16 *__restrict__ o,
+template <int QT, typename IO>
+__global__ void __launch_bounds__(QT * 2) attention_fwd_kernel(const IO *__restrict__ qkv, int T, int H,
+                                                               float scale, IO *__restrict__ o,
                                                                float *__restrict__ lse) {
     constexpr int TILE = QT <= 32 ? 32 : 64;   // rows of the other operand per smem tile
     __shared__ __align__(16) float s_k[TILE * AT_PITCH], s_v[TILE * AT_PITCH];
@@ -306,7 +334,7 @@ __global__ void __launch_bounds__(QT * 2) attention_fwd_kernel(const __nv_bfloat
     const int b = blockIdx.z, h = blockIdx.y;
     const int i = blockIdx.x * QT + (threadIdx.x >> 1), half = threadIdx.x & 1;
     const int ld = 3 * H * AT_D, ho = half * 36;
-    const __nv_bfloat16 *base = qkv + (size_t)b * T * ld + h * AT_D;
+    const IO *base = qkv + (size_t)b * T * ld + h * AT_D;
     const bool act_q = i < T;
     float q[32], acc[32];
     const float sl2 = scale * 1.4426950408889634f;
@@ -363,12 +391,12 @@ __global__ void __launch_bounds__(QT * 2) attention_fwd_kernel(const __nv_bfloat
 }
 
 // backward, query side: dq_i = scale * sum_j ds_ij k_j,  ds_ij = p_ij (dO_i . v_j - D_i),  D_i = dO_i . o_i.
-template <int QT>
-__global__ void __launch_bounds__(QT * 2) attention_bwd_dq_kernel(const __nv_bfloat16 *__restrict__ qkv,
-                                                                  const __nv_bfloat16 *__restrict__ o,
-                                                                  const __nv_bfloat16 *__restrict__ dO,
+template <int QT, typename IO>
+__global__ void __launch_bounds__(QT * 2) attention_bwd_dq_kernel(const IO *__restrict__ qkv,
+                                                                  const IO *__restrict__ o,
+                                                                  const IO *__restrict__ dO,
                                                                   const float *__restrict__ lse, int T, int H,
-                                                                  float scale, __nv_bfloat16 *__restrict__ dqkv,
+                                                                  float scale, IO *__restrict__ dqkv,
                                                                   float *__restrict__ delta) {
     constexpr int TILE = QT <= 32 ? 32 : 64;   // rows of the other operand per smem tile
     __shared__ __align__(16) float s_k[TILE * AT_PITCH], s_v[TILE * AT_PITCH];
@@ -377,7 +405,7 @@ __global__ void __launch_bounds__(QT * 2) attention_bwd_dq_kernel(const __nv_bfl
     const int b = blockIdx.z, h = blockIdx.y;
     const int i = blockIdx.x * QT + (threadIdx.x >> 1), half = threadIdx.x & 1;
     const int ld = 3 * H * AT_D, ldo = H * AT_D, ho = half * 36;
-    const __nv_bfloat16 *base = qkv + (size_t)b * T * ld + h * AT_D;
+    const IO *base = qkv + (size_t)b * T * ld + h * AT_D;
     const bool act_q = i < T;
     float q[32], g[32], dq[32];
     float D = 0.f, L = 0.f;
@@ -418,12 +446,12 @@ __global__ void __launch_bounds__(QT * 2) attention_bwd_dq_kernel(const __nv_bfl
 }
 
 // backward, key side: dv_j = sum_i p_ij dO_i,  dk_j = scale * sum_i ds_ij q_i  (p recomputed from lse).
-template <int QT>
-__global__ void __launch_bounds__(QT * 2) attention_bwd_dkv_kernel(const __nv_bfloat16 *__restrict__ qkv,
-                                                                   const __nv_bfloat16 *__restrict__ dO,
+template <int QT, typename IO>
+__global__ void __launch_bounds__(QT * 2) attention_bwd_dkv_kernel(const IO *__restrict__ qkv,
+                                                                   const IO *__restrict__ dO,
                                                                    const float *__restrict__ lse,
                                                                    const float *__restrict__ delta, int T, int H,
-                                                                   float scale, __nv_bfloat16 *__restrict__ dqkv) {
+                                                                   float scale, IO *__restrict__ dqkv) {
     constexpr int TILE = QT <= 32 ? 32 : 64;
     __shared__ __align__(16) float s_q[TILE * AT_PITCH], s_g[TILE * AT_PITCH];
     __shared__ float s_l[TILE], s_d[TILE];
@@ -432,7 +460,7 @@ __global__ void __launch_bounds__(QT * 2) attention_bwd_dkv_kernel(const __nv_bf
     const int b = blockIdx.z, h = blockIdx.y;
     const int j = blockIdx.x * QT + (threadIdx.x >> 1), half = threadIdx.x & 1;
     const int ld = 3 * H * AT_D, ldo = H * AT_D, ho = half * 36;
-    const __nv_bfloat16 *base = qkv + (size_t)b * T * ld + h * AT_D;
+    const IO *base = qkv + (size_t)b * T * ld + h * AT_D;
     const bool act_k = j < T;
     float kr[32], vr[32], dk[32], dv[32];
     const float sl2 = scale * 1.4426950408889634f;
@@ -521,8 +549,8 @@ extern "C" int act_layernorm_fwd(const float *x, const float *pos, const float *
 
 extern "C" int act_layernorm_bwd(const void *dy, int dy_fp32, const float *x, const float *mean, const float *rstd,
                                  const float *gamma, const float *dres, int M, int C, float *dx_out, float *dgamma,
-                                 float *dbeta, float *dacc, void *g_bf16, const float *row_scale, int rows_per_scale,
-                                 float *dbias, void *stream) {
+                                 float *dbeta, float *dacc, void *g_out, int g_fp32, const float *row_scale,
+                                 int rows_per_scale, float *dbias, void *stream) {
     using namespace act;
     if (!dy || !x || !mean || !rstd || !gamma || !dx_out || M < 0 || C <= 0) return ACT_EINVAL;
     if (M == 0) return ACT_OK;
@@ -532,7 +560,7 @@ extern "C" int act_layernorm_bwd(const void *dy, int dy_fp32, const float *x, co
 #define LN_CASE(V)                                                                                                \
     case V:                                                                                                       \
         ACT_CUDA(launch_k(layernorm_bwd_kernel<V>, dim3(grid), dim3(256), 0, st, true, dy, dy_fp32, x, mean, rstd,  \
-                          gamma, dres, M, dx_out, dgamma, dbeta, dacc, reinterpret_cast<__nv_bfloat16 *>(g_bf16), \
+                          gamma, dres, M, dx_out, dgamma, dbeta, dacc, g_out, g_fp32,                             \
                           row_scale, rows_per_scale > 0 ? rows_per_scale : 1, dbias));                            \
         break;
     switch (C / 128) {
@@ -544,23 +572,23 @@ extern "C" int act_layernorm_bwd(const void *dy, int dy_fp32, const float *x, co
     return ACT_OK;
 }
 
-extern "C" int act_cast_rows(const float *x, int M, int C, const float *row_scale, int rows_per_scale, void *g_bf16,
-                             float *dbias, void *stream) {
+extern "C" int act_cast_rows(const float *x, int M, int C, const float *row_scale, int rows_per_scale, void *g_out,
+                             int g_fp32, float *dbias, void *stream) {
     using namespace act;
-    if (!x || !g_bf16 || M < 0 || C <= 0) return ACT_EINVAL;
+    if (!x || !g_out || M < 0 || C <= 0) return ACT_EINVAL;
     if (M == 0) return ACT_OK;
     if (C % 128 || C > 1024) return ACT_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = (M + 7) / 8 < 148 * 2 ? (M + 7) / 8 : 148 * 2;
     const int rps = rows_per_scale > 0 ? rows_per_scale : 1;
-    __nv_bfloat16 *g = reinterpret_cast<__nv_bfloat16 *>(g_bf16);
+    void *g = g_out;
     switch (C / 128) {
-        case 1: cast_rows_kernel<1><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, dbias); break;
-        case 2: cast_rows_kernel<2><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, dbias); break;
-        case 3: cast_rows_kernel<3><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, dbias); break;
-        case 4: cast_rows_kernel<4><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, dbias); break;
-        case 6: cast_rows_kernel<6><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, dbias); break;
-        case 8: cast_rows_kernel<8><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, dbias); break;
+        case 1: cast_rows_kernel<1><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, g_fp32, dbias); break;
+        case 2: cast_rows_kernel<2><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, g_fp32, dbias); break;
+        case 3: cast_rows_kernel<3><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, g_fp32, dbias); break;
+        case 4: cast_rows_kernel<4><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, g_fp32, dbias); break;
+        case 6: cast_rows_kernel<6><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, g_fp32, dbias); break;
+        case 8: cast_rows_kernel<8><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, g_fp32, dbias); break;
         default: return ACT_EUNSUPPORTED;
     }
     ACT_CHECK_LAUNCH();
@@ -580,24 +608,31 @@ inline bool attn_use_mma(int T, bool backward) {
 }
 }  // namespace act
 
+template <typename IO>
+static int attention_fma_fwd(const void *qkv, int B, int T, int H, float scale, void *o, float *lse, cudaStream_t st) {
+    using namespace act;
+    const IO *p = reinterpret_cast<const IO *>(qkv);
+    IO *op = reinterpret_cast<IO *>(o);
+    if (T <= 16) {
+        ACT_CUDA(launch_k(attention_fwd_kernel<16, IO>, dim3((T + 15) / 16, H, B), dim3(32), 0, st, true, p, T, H, scale, op, lse));
+    } else if (T <= 32 || (T > 64 && T <= 96)) {
+        ACT_CUDA(launch_k(attention_fwd_kernel<32, IO>, dim3((T + 31) / 32, H, B), dim3(64), 0, st, true, p, T, H, scale, op, lse));
+    } else {
+        ACT_CUDA(launch_k(attention_fwd_kernel<64, IO>, dim3((T + 63) / 64, H, B), dim3(128), 0, st, true, p, T, H, scale, op, lse));
+    }
+    return ACT_OK;
+}
+
 extern "C" int act_attention_fwd(const void *qkv, int B, int T, int H, int head_dim, float scale, void *o, float *lse,
-                                 void *stream) {
+                                 int io_fp32, void *stream) {
     using namespace act;
     if (!qkv || !o || B < 0 || T <= 0 || H <= 0) return ACT_EINVAL;
     if (head_dim != AT_D) return ACT_EUNSUPPORTED;
     if (B == 0) return ACT_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (io_fp32) return attention_fma_fwd<float>(qkv, B, T, H, scale, o, lse, st);     // parity mode: f32 in / out, FMA pipes
     if (attn_use_mma(T, false)) return attention_mma_fwd(qkv, B, T, H, scale, o, lse, st);
-    const __nv_bfloat16 *p = reinterpret_cast<const __nv_bfloat16 *>(qkv);
-    __nv_bfloat16 *op = reinterpret_cast<__nv_bfloat16 *>(o);
-    if (T <= 16) {
-        ACT_CUDA(launch_k(attention_fwd_kernel<16>, dim3((T + 15) / 16, H, B), dim3(32), 0, st, true, p, T, H, scale, op, lse));
-    } else if (T <= 32 || (T > 64 && T <= 96)) {
-        ACT_CUDA(launch_k(attention_fwd_kernel<32>, dim3((T + 31) / 32, H, B), dim3(64), 0, st, true, p, T, H, scale, op, lse));
-    } else {
-        ACT_CUDA(launch_k(attention_fwd_kernel<64>, dim3((T + 63) / 64, H, B), dim3(128), 0, st, true, p, T, H, scale, op, lse));
-    }
-    return ACT_OK;
+    return attention_fma_fwd<__nv_bfloat16>(qkv, B, T, H, scale, o, lse, st);
 }
 
 namespace act {
@@ -613,28 +648,34 @@ extern "C" int act_attention_prefix_fwd(const void *qkv_t, const void *kv_p, int
     return attention_prefix_fwd(qkv_t, kv_p, B, G, P, H, scale, o, (cudaStream_t)stream);
 }
 
+template <typename IO>
+static int attention_fma_bwd(const void *qkv, const void *o, const void *dO, const float *lse, int B, int T, int H,
+                             float scale, void *dqkv, float *delta, cudaStream_t st) {
+    using namespace act;
+    const IO *p = reinterpret_cast<const IO *>(qkv), *op = reinterpret_cast<const IO *>(o), *gp = reinterpret_cast<const IO *>(dO);
+    IO *dp = reinterpret_cast<IO *>(dqkv);
+    if (T <= 32 || (T > 64 && T <= 96)) {
+        dim3 grid((T + 31) / 32, H, B);
+        ACT_CUDA(launch_k(attention_bwd_dq_kernel<32, IO>, grid, dim3(64), 0, st, true, p, op, gp, lse, T, H, scale, dp, delta));
+        ACT_CUDA(launch_k(attention_bwd_dkv_kernel<32, IO>, grid, dim3(64), 0, st, true, p, gp, lse, delta, T, H, scale, dp));
+    } else {
+        dim3 grid((T + 63) / 64, H, B);
+        ACT_CUDA(launch_k(attention_bwd_dq_kernel<64, IO>, grid, dim3(128), 0, st, true, p, op, gp, lse, T, H, scale, dp, delta));
+        ACT_CUDA(launch_k(attention_bwd_dkv_kernel<64, IO>, grid, dim3(128), 0, st, true, p, gp, lse, delta, T, H, scale, dp));
+    }
+    return ACT_OK;
+}
+
 extern "C" int act_attention_bwd(const void *qkv, const void *o, const void *dO, const float *lse, int B, int T, int H,
-                                 int head_dim, float scale, void *dqkv, float *delta, void *stream) {
+                                 int head_dim, float scale, void *dqkv, float *delta, int io_fp32, void *stream) {
     using namespace act;
     if (!qkv || !o || !dO || !lse || !dqkv || !delta || B < 0 || T <= 0 || H <= 0) return ACT_EINVAL;
     if (head_dim != AT_D) return ACT_EUNSUPPORTED;
     if (B == 0) return ACT_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (io_fp32) return attention_fma_bwd<float>(qkv, o, dO, lse, B, T, H, scale, dqkv, delta, st);
     if (attn_use_mma(T, true)) return attention_mma_bwd(qkv, o, dO, lse, B, T, H, scale, dqkv, delta, st);
-    const __nv_bfloat16 *p = reinterpret_cast<const __nv_bfloat16 *>(qkv);
-    const __nv_bfloat16 *op = reinterpret_cast<const __nv_bfloat16 *>(o);
-    const __nv_bfloat16 *gp = reinterpret_cast<const __nv_bfloat16 *>(dO);
-    __nv_bfloat16 *dp = reinterpret_cast<__nv_bfloat16 *>(dqkv);
-    if (T <= 32 || (T > 64 && T <= 96)) {
-        dim3 grid((T + 31) / 32, H, B);
-        ACT_CUDA(launch_k(attention_bwd_dq_kernel<32>, grid, dim3(64), 0, st, true, p, op, gp, lse, T, H, scale, dp, delta));
-        ACT_CUDA(launch_k(attention_bwd_dkv_kernel<32>, grid, dim3(64), 0, st, true, p, gp, lse, delta, T, H, scale, dp));
-    } else {
-        dim3 grid((T + 63) / 64, H, B);
-        ACT_CUDA(launch_k(attention_bwd_dq_kernel<64>, grid, dim3(128), 0, st, true, p, op, gp, lse, T, H, scale, dp, delta));
-        ACT_CUDA(launch_k(attention_bwd_dkv_kernel<64>, grid, dim3(128), 0, st, true, p, gp, lse, delta, T, H, scale, dp));
-    }
-    return ACT_OK;
+    return attention_fma_bwd<__nv_bfloat16>(qkv, o, dO, lse, B, T, H, scale, dqkv, delta, st);
 }
 
 extern "C" int act_colsum(const void *x, int x_fp32, int M, int N, int ld, float *out, void *stream) {

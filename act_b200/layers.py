@@ -61,6 +61,10 @@ class _SideStream:
 
 
 def shadow(p):
+    """The GEMM operand form of a weight: its slice of the flat bf16 shadow (or an on-the-fly bf16 cast); in the
+    fp32x3 parity mode the f32 master weight itself (ops.gemm splits it into bf16 pieces)."""
+    if ops.act_dtype() == torch.float32:
+        return p.detach()
     s = getattr(p, "_act_shadow", None)
     return s if s is not None else p.detach().to(torch.bfloat16)
 
@@ -267,7 +271,7 @@ class TransformerStack(torch.autograd.Function):
             xmid = ops.gemm(o, shadow(wproj), bias=bproj, resid=xs, row_scale=g1, rows_per_scale=T,
                             out_dtype=torch.float32)
             h2, _, mean2, rstd2 = ops.layernorm_fwd(xmid, n2w, n2b, eps)
-            u = torch.empty(M, w1.shape[0], dtype=torch.bfloat16, device=x.device) if need else None
+            u = torch.empty(M, w1.shape[0], dtype=ops.act_dtype(), device=x.device) if need else None
             a = ops.gemm(h2, shadow(w1), bias=b1, act=ops.ACT_GELU, preact_out=u)
             cur = ops.gemm(a, shadow(w2), bias=b2, resid=xmid, row_scale=g2, rows_per_scale=T,
                            out_dtype=torch.float32)
@@ -404,13 +408,16 @@ class LinearFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, gelu):
         shp = x.shape
         x2 = x.reshape(-1, shp[-1])
-        if x2.dtype == torch.float32 and x2.is_contiguous() and shp[-1] % 128 == 0 and shp[-1] <= 1024:
+        adt = ops.act_dtype()
+        if x2.dtype == adt and x2.is_contiguous():
+            xb = x2
+        elif x2.dtype == torch.float32 and x2.is_contiguous() and shp[-1] % 128 == 0 and shp[-1] <= 1024:
             xb = ops.cast_rows(x2)                               # our cast kernel (no library launch in the step)
         else:
-            xb = x2.to(torch.bfloat16).contiguous()
+            xb = x2.to(adt).contiguous()
         u = None
         if gelu:
-            u = torch.empty(xb.shape[0], weight.shape[0], dtype=torch.bfloat16, device=x.device)
+            u = torch.empty(xb.shape[0], weight.shape[0], dtype=adt, device=x.device)
             y = ops.gemm(xb, shadow(weight), bias=bias, act=ops.ACT_GELU, preact_out=u, out_dtype=torch.float32)
         else:
             y = ops.gemm(xb, shadow(weight), bias=bias, out_dtype=torch.float32)
@@ -431,7 +438,7 @@ class LinearFn(torch.autograd.Function):
         if N % 128 == 0 and N <= 1024:
             g = ops.cast_rows(d2, dbias=sink.get(bias, "b") if bias is not None else None)
         else:
-            g = d2.to(torch.bfloat16)
+            g = d2.to(ops.act_dtype())
             if bias is not None:
                 ops.colsum(d2, sink.get(bias, "b"))
         ops.wgrad(g, xb, sink.get(weight, "w"))
@@ -584,9 +591,11 @@ class PointNetEncoderFn(torch.autograd.Function):
         a1 = ops.pn_conv1(p, Wf, bf, relu=True)                                   # [M,128]
         BG = B * G
         if k == 32:      # max over the group's 32 points fused into the GEMM epilogue (fp32 accumulators)
-            gmax = torch.empty(BG, 256, dtype=torch.bfloat16, device=p.device)
+            adt = ops.act_dtype()
+            gmax = torch.empty(BG, 256, dtype=adt, device=p.device)
             arg2 = torch.empty(BG, 256, dtype=torch.uint8, device=p.device)
-            f2 = ops.gemm(a1, shadow(w2).view(256, 128), bias=b2, gmax_bf16=gmax, garg=arg2)   # [M,256]
+            f2 = ops.gemm(a1, shadow(w2).view(256, 128), bias=b2, garg=arg2,
+                          **({"gmax_f32": gmax} if adt == torch.float32 else {"gmax_bf16": gmax}))   # [M,256]
         else:
             f2 = ops.gemm(a1, shadow(w2).view(256, 128), bias=b2)
             gmax, _, arg2 = ops.group_max(f2, k)                                  # [BG,256]
@@ -638,7 +647,7 @@ class PointNetEncoderFn(torch.autograd.Function):
         if GK == BG:
             dZ3 = ops.gemm(dF4, shadow(w4).view(C, 512), b_mn=True, mul_in=a3, mul_mode=ops.MUL_RELU_MASK)
         else:            # rows of the dropped groups receive no gradient from conv4
-            dZ3 = torch.empty(M, 512, dtype=torch.bfloat16, device=d.device)
+            dZ3 = torch.empty(M, 512, dtype=ops.act_dtype(), device=d.device)
             ops.gemm(dF4, shadow(w4).view(C, 512), b_mn=True, mul_in=a3k, mul_mode=ops.MUL_RELU_MASK,
                      out=dZ3[:GK * k])
             ops.zero_(dZ3[GK * k:])

@@ -5,12 +5,47 @@ import torch
 from . import _lib
 
 LAUNCHES = 0  # number of libact_b200 kernel launches issued through this module (bench.py reads it)
-_ACT_DTYPE = torch.bfloat16
+import os as _os
+
+# Precision of the dense path.  "bf16" (default, the speed mode): GEMM operands and stored activations are bf16, fp32
+# accumulation.  "fp32x3" (the PARITY mode, north_star's 1e-3 bar): activations are stored in f32 and every GEMM operand
+# is split into bf16 (hi, mid) pieces so that the same tcgen05 kernel computes a_hi b_hi + a_hi b_mid + a_mid b_hi over a
+# tripled K (csrc/parity.cu) -- ~16 mantissa bits per product, fp32 accumulation; attention runs in f32 on the FMA pipes.
+_ACT_DTYPE = torch.float32 if _os.environ.get("ACT_B200_PRECISION", "bf16") == "fp32x3" else torch.bfloat16
 
 
 def act_dtype():
-    """Storage dtype of the activations that feed GEMMs: bf16 (the speed mode and default)."""
+    """Storage dtype of the activations that feed GEMMs: bf16 (speed mode), f32 (parity mode)."""
     return _ACT_DTYPE
+
+
+def set_precision(mode):
+    global _ACT_DTYPE
+    if mode not in ("bf16", "fp32x3"):
+        raise ValueError("precision: 'bf16' or 'fp32x3'")
+    _ACT_DTYPE = torch.float32 if mode == "fp32x3" else torch.bfloat16
+
+
+def get_precision():
+    return "fp32x3" if _ACT_DTYPE == torch.float32 else "bf16"
+
+
+class precision:
+    """with ops.precision("fp32x3"): ...   (modules built / called inside run the parity mode)"""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = get_precision()
+        set_precision(self.mode)
+
+    def __exit__(self, *a):
+        set_precision(self.prev)
+
+
+def _io32(t):
+    return int(t.dtype == torch.float32)
 
 
 def _count(n=1):
@@ -151,35 +186,57 @@ def _p(t):
     return _vp(t.data_ptr()) if t is not None else None
 
 
-def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=torch.bfloat16, bias=None, act=ACT_NONE,
+def split3(x, mn_major, role_b):
+    """f32 2-D operand (last dim contiguous) -> its three-piece bf16 form for the parity-mode GEMM (csrc/parity.cu)."""
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    R, Cc = x.shape
+    out = torch.empty((3 * R, Cc) if mn_major else (R, 3 * Cc), dtype=torch.bfloat16, device=x.device)
+    _lib.call("act_split3_bf16", _p(x), _lib.ctypes.c_int64(R), Cc, _lib.ctypes.c_int64(x.stride(0)), int(mn_major),
+              int(role_b), out)
+    _count()
+    return out
+
+
+def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=None, act=ACT_NONE,
          preact_out=None, mul_in=None, mul_mode=MUL_NONE, resid=None, resid_row_div=1, row_scale=None,
          rows_per_scale=1, gmax_f32=None, gmax_bf16=None, garg=None, no_out=False, alpha=1.0, splits=1, block_n=0,
          persistent=-1):
     """out[M,N] = epilogue(alpha * A . B^T) on the tcgen05 GEMM (include/act_b200.h: act_gemm_bf16).
-    a: bf16 [M,K] (or [K,M] if a_mn);  b: bf16 [N,K] (or [K,N] if b_mn).  2-D, last-dim contiguous.
+    a: [M,K] (or [K,M] if a_mn);  b: [N,K] (or [K,N] if b_mn).  2-D, last-dim contiguous; bf16, or f32 in the parity mode
+    (both operands are then split into bf16 pieces and the product runs over 3K, see split3).
+    out_dtype None = the activation dtype of the current precision mode.
     gmax_f32 / gmax_bf16 / garg: [M/32, N] outputs of the fused per-32-row max; no_out=True skips `out`."""
-    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.dim() == 2 and b.dim() == 2
-    assert a.stride(1) == 1 and b.stride(1) == 1
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
     K, M = (a.shape if a_mn else a.shape[::-1])
     Kb, N = (b.shape if b_mn else b.shape[::-1])
     assert K == Kb, (a.shape, b.shape, a_mn, b_mn)
+    if a.dtype == torch.float32 or b.dtype == torch.float32:
+        a = split3(a.float() if a.dtype != torch.float32 else a, a_mn, 0)
+        b = split3(b.float() if b.dtype != torch.float32 else b, b_mn, 1)
+        K = 3 * K
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    if out_dtype is None:
+        out_dtype = act_dtype()
     if no_out:
         out = None
     elif out is None:
         out = (torch.zeros if splits > 1 else torch.empty)(M, N, dtype=out_dtype, device=a.device)
     if out is not None:
         assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype in (torch.bfloat16, torch.float32)
+    aux = [t for t in (preact_out, mul_in) if t is not None]
+    aux32 = bool(aux) and aux[0].dtype == torch.float32
+    assert all((t.dtype == torch.float32) == aux32 for t in aux)
     if preact_out is not None:
-        assert preact_out.dtype == torch.bfloat16 and preact_out.stride(0) == out.stride(0)
+        assert preact_out.dtype in (torch.bfloat16, torch.float32) and preact_out.stride(0) == out.stride(0)
     gm = [t for t in (gmax_f32, gmax_bf16, garg) if t is not None]
     ldg = gm[0].stride(0) if gm else 0
     assert all(t.stride(0) == ldg and t.shape == (M // 32, N) for t in gm)
     _lib.call("act_gemm_bf16", _p(a), _p(b), M, N, K, int(a_mn), int(b_mn), a.stride(0), b.stride(0), _p(out),
               out.stride(0) if out is not None else 0, int(out is not None and out.dtype == torch.float32), bias,
-              int(act), preact_out, _p(mul_in), mul_in.stride(0) if mul_in is not None else 0, int(mul_mode),
+              int(act), _p(preact_out), _p(mul_in), mul_in.stride(0) if mul_in is not None else 0, int(mul_mode),
               _p(resid), resid.stride(0) if resid is not None else 0, int(resid_row_div), row_scale,
               int(rows_per_scale), gmax_f32, gmax_bf16, garg, int(ldg), float(alpha), int(splits), int(block_n),
-              int(persistent), 0)
+              int(persistent), int(aux32))
     _count()
     return out
 
@@ -204,9 +261,11 @@ def wgrad(dy, x, grad_out):
 
 
 # ------------------------------------------------------------------------------ Block pieces
-def layernorm_fwd(x, gamma, beta, eps=1e-5, pos=None, out_dtype=torch.bfloat16, want_sum=False, save_stats=True):
+def layernorm_fwd(x, gamma, beta, eps=1e-5, pos=None, out_dtype=None, want_sum=False, save_stats=True):
     """x f32 [M,C] (+ pos) -> (y, xsum or None, mean, rstd)."""
     M, C = x.shape
+    if out_dtype is None:
+        out_dtype = act_dtype()
     y = torch.empty(M, C, dtype=out_dtype, device=x.device)
     xs = torch.empty_like(x) if (want_sum or pos is not None) else None
     mean = torch.empty(M, dtype=torch.float32, device=x.device) if save_stats else None
@@ -219,28 +278,29 @@ def layernorm_fwd(x, gamma, beta, eps=1e-5, pos=None, out_dtype=torch.bfloat16, 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None, dacc=None, want_bf16=False, row_scale=None,
                   rows_per_scale=1, dbias=None):
-    """-> (dx f32 [M,C], g bf16 or None); dgamma/dbeta/dbias/dacc accumulated in place."""
+    """-> (dx f32 [M,C], g (activation dtype) or None); dgamma/dbeta/dbias/dacc accumulated in place."""
     M, C = x.shape
     dx = torch.empty(M, C, dtype=torch.float32, device=x.device)
-    g = torch.empty(M, C, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    g = torch.empty(M, C, dtype=act_dtype(), device=x.device) if want_bf16 else None
     _lib.call("act_layernorm_bwd", _p(dy), int(dy.dtype == torch.float32), x, mean, rstd, gamma, dres, M, C, dx,
-              dgamma, dbeta, dacc, g, row_scale, int(rows_per_scale), dbias)
+              dgamma, dbeta, dacc, _p(g), int(g is not None and g.dtype == torch.float32), row_scale,
+              int(rows_per_scale), dbias)
     _count()
     return dx, g
 
 
 def cast_rows(x, row_scale=None, rows_per_scale=1, dbias=None):
     M, C = x.shape
-    g = torch.empty(M, C, dtype=torch.bfloat16, device=x.device)
-    _lib.call("act_cast_rows", x, M, C, row_scale, int(rows_per_scale), g, dbias)
+    g = torch.empty(M, C, dtype=act_dtype(), device=x.device)
+    _lib.call("act_cast_rows", x, M, C, row_scale, int(rows_per_scale), _p(g), _io32(g), dbias)
     _count()
     return g
 
 
 def attention_fwd(qkv, B, T, H, scale):
-    o = torch.empty(B * T, H * 64, dtype=torch.bfloat16, device=qkv.device)
+    o = torch.empty(B * T, H * 64, dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty(B, H, T, dtype=torch.float32, device=qkv.device)
-    _lib.call("act_attention_fwd", qkv, B, T, H, 64, float(scale), o, lse)
+    _lib.call("act_attention_fwd", qkv, B, T, H, 64, float(scale), o, lse, _io32(qkv))
     _count()
     return o, lse
 
@@ -248,15 +308,16 @@ def attention_fwd(qkv, B, T, H, scale):
 def attention_bwd(qkv, o, do, lse, B, T, H, scale):
     dqkv = torch.empty_like(qkv)
     delta = torch.empty_like(lse)
-    _lib.call("act_attention_bwd", qkv, o, do, lse, B, T, H, 64, float(scale), dqkv, delta)
+    assert o.dtype == qkv.dtype and do.dtype == qkv.dtype
+    _lib.call("act_attention_bwd", qkv, o, do, lse, B, T, H, 64, float(scale), dqkv, delta, _io32(qkv))
     _count(2)
     return dqkv
 
 
 def colsum(x, out):
     M, N = x.shape
-    if x.dtype == torch.bfloat16 and x.is_contiguous() and N % 8 == 0 and N <= 2048:
-        _lib.call("act_colsum_bf16_dense", x, _lib.ctypes.c_int64(M), N, out)
+    if x.is_contiguous() and N % 8 == 0 and N <= 2048 and (x.dtype == torch.bfloat16 or M >= 4096):
+        _lib.call("act_colsum_bf16_dense", x, _lib.ctypes.c_int64(M), N, out, _io32(x))
         _count()
         return out
     _lib.call("act_colsum", _p(x), int(x.dtype == torch.float32), M, N, x.stride(0), out)
@@ -408,8 +469,8 @@ def pn_moments(points):
 
 def pn_conv1(points, W, b, relu=True):
     M = points.shape[0]
-    out = torch.empty(M, 128, dtype=torch.bfloat16, device=points.device)
-    _lib.call("act_pn_conv1", points, W, b, _lib.ctypes.c_int64(M), int(relu), out)
+    out = torch.empty(M, 128, dtype=act_dtype(), device=points.device)
+    _lib.call("act_pn_conv1", points, W, b, _lib.ctypes.c_int64(M), int(relu), out, _io32(out))
     _count()
     return out
 
@@ -417,10 +478,10 @@ def pn_conv1(points, W, b, relu=True):
 def group_max(x, k, want_bf16=True, want_f32=False, want_arg=True):
     Mk, C = x.shape
     G = Mk // k
-    ob = torch.empty(G, C, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    ob = torch.empty(G, C, dtype=x.dtype, device=x.device) if want_bf16 else None
     of = torch.empty(G, C, dtype=torch.float32, device=x.device) if want_f32 else None
     arg = torch.empty(G, C, dtype=torch.uint8, device=x.device) if want_arg else None
-    _lib.call("act_group_max", x, G, k, C, ob, of, arg)
+    _lib.call("act_group_max", x, G, k, C, ob, of, arg, _io32(x))
     _count()
     return ob, of, arg
 
@@ -429,8 +490,8 @@ def group_max_bwd(dout, arg, k, out=None):
     G, C = dout.shape
     acc = out is not None
     if out is None:
-        out = torch.empty(G * k, C, dtype=torch.bfloat16, device=dout.device)
-    _lib.call("act_group_max_bwd", dout, arg, G, k, C, int(acc), out)
+        out = torch.empty(G * k, C, dtype=act_dtype(), device=dout.device)
+    _lib.call("act_group_max_bwd", dout, arg, G, k, C, int(acc), out, _io32(out))
     _count()
     return out
 
@@ -438,9 +499,9 @@ def group_max_bwd(dout, arg, k, out=None):
 def group_sum(x, k, want_bf16=True, want_f32=False):
     Mk, C = x.shape
     G = Mk // k
-    ob = torch.empty(G, C, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    ob = torch.empty(G, C, dtype=x.dtype, device=x.device) if want_bf16 else None
     of = torch.empty(G, C, dtype=torch.float32, device=x.device) if want_f32 else None
-    _lib.call("act_group_sum", x, G, k, C, ob, of)
+    _lib.call("act_group_sum", x, G, k, C, ob, of, _io32(x))
     _count()
     return ob, of
 
@@ -448,7 +509,7 @@ def group_sum(x, k, want_bf16=True, want_f32=False):
 def bn_stats(x):
     M, C = x.shape
     s = torch.empty(2, C, dtype=torch.float32, device=x.device)
-    _lib.call("act_bn_stats", x, _lib.ctypes.c_int64(M), C, s[0], s[1])
+    _lib.call("act_bn_stats", x, _lib.ctypes.c_int64(M), C, s[0], s[1], _io32(x))
     _count()
     return s[0], s[1]
 
@@ -457,7 +518,7 @@ def bn_apply(x, scale, shift, relu=True, out=None):
     M, C = x.shape
     if out is None:
         out = torch.empty_like(x)
-    _lib.call("act_bn_apply", x, scale, shift, _lib.ctypes.c_int64(M), C, int(relu), out)
+    _lib.call("act_bn_apply", x, scale, shift, _lib.ctypes.c_int64(M), C, int(relu), out, _io32(x))
     _count()
     return out
 
@@ -466,9 +527,10 @@ def bn_bwd(dz, x, mean, rstd, gamma):
     """-> (dh bf16, sum_dz (= dbeta), sum_dz_xhat (= dgamma))."""
     M, C = x.shape
     s = torch.empty(2, C, dtype=torch.float32, device=x.device)
-    _lib.call("act_bn_bwd_stats", dz, x, mean, rstd, _lib.ctypes.c_int64(M), C, s[0], s[1])
+    assert dz.dtype == x.dtype
+    _lib.call("act_bn_bwd_stats", dz, x, mean, rstd, _lib.ctypes.c_int64(M), C, s[0], s[1], _io32(x))
     dh = torch.empty_like(dz)
-    _lib.call("act_bn_bwd_apply", dz, x, mean, rstd, gamma, s[0], s[1], _lib.ctypes.c_int64(M), C, dh)
+    _lib.call("act_bn_bwd_apply", dz, x, mean, rstd, gamma, s[0], s[1], _lib.ctypes.c_int64(M), C, dh, _io32(x))
     _count(2)
     return dh, s[0], s[1]
 
@@ -477,7 +539,7 @@ def pn_conv1_bwd(dz, points, W, b, mean, rstd, gamma, dW, db):
     """Accumulates dW [128,3], db [128]; returns (dbeta, dgamma) of BatchNorm1."""
     M = points.shape[0]
     s = torch.empty(2, 128, dtype=torch.float32, device=points.device)
-    _lib.call("act_pn_conv1_bwd", dz, points, W, b, mean, rstd, gamma, _lib.ctypes.c_int64(M), s[0], s[1], dW, db)
+    _lib.call("act_pn_conv1_bwd", dz, points, W, b, mean, rstd, gamma, _lib.ctypes.c_int64(M), s[0], s[1], dW, db, _io32(dz))
     _count(2)
     return s[0], s[1]
 

@@ -215,6 +215,10 @@ class ACTPromptedDiscreteVAEwithVIT(nn.Module):
     def forward_tokenizer_features(self, neighborhood, center, return_global=True, gumbel=None, keeps=None):
         """dvae.py:584-592.  gumbel (optional f32 [B,G,num_tokens]) / keeps (optional list of [B,P,D] 0/1 masks)
         inject the two random draws (gumbel noise, prompt dropout) for parity runs; default: drawn here."""
+        with ops.precision("bf16"):      # the frozen teacher always runs the bf16 speed mode (its own parity bounds:
+            return self._features(neighborhood, center, return_global, gumbel, keeps)     # tests/test_gpu_teacher.py)
+
+    def _features(self, neighborhood, center, return_global, gumbel, keeps):
         c = self._prepare()
         B, G, _ = center.shape
         tokens = self.encoder(neighborhood).reshape(B * G, -1)

@@ -108,6 +108,14 @@ int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, int a_mn_ma
                   const float *row_scale, int rows_per_scale, float *gmax_f32, void *gmax_bf16, uint8_t *garg, int ldg,
                   float alpha, int splits, int block_n, int persistent, int aux_fp32, void *stream);
 
+/* The fp32-grade PARITY MODE of the dense layers: x f32 [R, Cc] (row pitch ld elements) -> three bf16 pieces
+ * hi = bf16(x), mid = bf16(x - hi), laid out so that ONE act_gemm_bf16 call over a tripled K computes
+ * a_hi b_hi + a_hi b_mid + a_mid b_hi (~16 mantissa bits; products of bf16 pairs are exact in the fp32 accumulator).
+ * role_b = 0 (A operand): pieces (hi, hi, mid); 1 (B operand): (hi, mid, hi).
+ * mn_major = 0: x is a K-major operand [MN, K] -> out bf16 [R, 3*Cc] (pieces side by side along K);
+ * mn_major = 1: x is an MN-major operand [K, MN] -> out bf16 [3*R, Cc] (pieces stacked along K).   Cc % 8 == 0. */
+int act_split3_bf16(const float *x, long long R, int Cc, long long ld, int mn_major, int role_b, void *out, void *stream);
+
 /* ---- Transformer Block pieces (models/act.py:45-90, 109-112) ------------------------------------------ */
 
 /* nn.LayerNorm(C, eps) over fp32 rows x[M,C] (C % 128 == 0, <= 1024).  pos (nullable, f32 [M,C]): the
@@ -121,26 +129,27 @@ int act_layernorm_fwd(const float *x, const float *pos, const float *gamma, cons
  * dgamma/dbeta [C] (nullable) are ACCUMULATED (atomics) -- they point into the flat gradient buffer.
  * Fused extras for the Block backward (all nullable): dacc[M,C] += dx_out (gradient of `pos`, which every
  * layer adds again); g_bf16[M,C] = bf16(dx_out * row_scale[m / rows_per_scale]) -- the dY operand of the
- * next (lower) Linear's dgrad/wgrad, already gated by that branch's DropPath; dbias[C] += column sums of the
- * same gated value (that Linear's bias gradient). */
+ * next (lower) Linear's dgrad/wgrad, already gated by that branch's DropPath (g_out; f32 instead of bf16 when g_fp32);
+ * dbias[C] += column sums of the same gated value (that Linear's bias gradient). */
 int act_layernorm_bwd(const void *dy, int dy_fp32, const float *x, const float *mean, const float *rstd,
                       const float *gamma, const float *dres, int M, int C, float *dx_out, float *dgamma,
-                      float *dbeta, float *dacc, void *g_bf16, const float *row_scale, int rows_per_scale,
+                      float *dbeta, float *dacc, void *g_out, int g_fp32, const float *row_scale, int rows_per_scale,
                       float *dbias, void *stream);
 
 /* g_bf16[M,C] = bf16(x[M,C] * row_scale[m / rows_per_scale]) (row_scale nullable); dbias[C] (nullable) +=
  * its column sums.  Entry point of a Block backward when the incoming gradient is plain fp32. */
-int act_cast_rows(const float *x, int M, int C, const float *row_scale, int rows_per_scale, void *g_bf16,
+int act_cast_rows(const float *x, int M, int C, const float *row_scale, int rows_per_scale, void *g_out, int g_fp32,
                   float *dbias, void *stream);
 
 /* Attention.forward core (act.py:57-66): qkv bf16 [B*T, 3*H*64] -> o bf16 [B*T, H*64] =
- * softmax(q k^T * scale) v per (batch, head); lse f32 [B,H,T] saved for the backward.  head_dim must be 64. */
+ * softmax(q k^T * scale) v per (batch, head); lse f32 [B,H,T] saved for the backward.  head_dim must be 64.
+ * io_fp32 = 1 (parity mode): qkv / o (and dO / dqkv below) are f32 and the products run in f32 on the FMA pipes. */
 int act_attention_fwd(const void *qkv, int B, int T, int H, int head_dim, float scale, void *o, float *lse,
-                      void *stream);
+                      int io_fp32, void *stream);
 
 /* Attention backward: dO bf16 [B*T, H*64] -> dqkv bf16 [B*T, 3*H*64]; delta f32 [B,H,T] is scratch. */
 int act_attention_bwd(const void *qkv, const void *o, const void *dO, const float *lse, int B, int T, int H,
-                      int head_dim, float scale, void *dqkv, float *delta, void *stream);
+                      int head_dim, float scale, void *dqkv, float *delta, int io_fp32, void *stream);
 
 /* out[N] += column sums of x[M, ld] (bf16 or f32): bias gradients. */
 int act_colsum(const void *x, int x_fp32, int M, int N, int ld, float *out, void *stream);
@@ -209,37 +218,39 @@ int act_pn_bn1_fold(const double *mom9, long long M, const float *W, const float
 int act_bn_finalize(const float *sum, const float *sumsq, long long M, int C, const float *gamma, const float *beta,
                     float eps, float momentum, float *running_mean, float *running_var, long long *num_batches_tracked,
                     float *scale, float *shift, float *mean, float *rstd, void *stream);
-/* out[M,128] bf16 = relu?(W[128,3] . p + b): first_conv[0] with BatchNorm1 folded into (W, b) + ReLU. */
-int act_pn_conv1(const float *points, const float *W, const float *b, long long M, int relu, void *out_bf16,
+/* The entry points below take `io_fp32`: 0 = the activations they read / write are bf16 (the speed mode and default),
+ * 1 = f32 (the fp32-grade parity mode).  Same kernels, instantiated for both element types. */
+/* out[M,128] = relu?(W[128,3] . p + b): first_conv[0] with BatchNorm1 folded into (W, b) + ReLU; bf16, or f32 (out_fp32). */
+int act_pn_conv1(const float *points, const float *W, const float *b, long long M, int relu, void *out, int out_fp32,
                  void *stream);
-/* torch.max(feature, dim=2) over the k points of each group (dvae.py:211,214): x bf16 [G*k, C] ->
- * out_bf16 / out_f32 (nullable) [G, C] and arg (nullable, u8 [G,C]: winning row, first on ties). */
-int act_group_max(const void *x_bf16, int G, int k, int C, void *out_bf16, float *out_f32, uint8_t *arg,
+/* torch.max(feature, dim=2) over the k points of each group (dvae.py:211,214): x [G*k, C] ->
+ * out_act (same type as x) / out_f32 (nullable) [G, C] and arg (nullable, u8 [G,C]: winning row, first on ties). */
+int act_group_max(const void *x, int G, int k, int C, void *out_act, float *out_f32, uint8_t *arg, int io_fp32,
                   void *stream);
-/* its backward: dF[G*k, C] bf16 (+)= scatter of dout f32 [G,C] to the arg-max rows (dense output). */
-int act_group_max_bwd(const float *dout, const uint8_t *arg, int G, int k, int C, int accumulate, void *dF_bf16,
+/* its backward: dF[G*k, C] (+)= scatter of dout f32 [G,C] to the arg-max rows (dense output). */
+int act_group_max_bwd(const float *dout, const uint8_t *arg, int G, int k, int C, int accumulate, void *dF, int io_fp32,
                       void *stream);
 /* sum over the k rows of each group (backward of the expand() of the global feature, dvae.py:212). */
-int act_group_sum(const void *x_bf16, int G, int k, int C, void *out_bf16, float *out_f32, void *stream);
-/* out[C] += column sums of a dense bf16 [M,C] matrix (C % 8 == 0, C <= 2048): bias gradients of the convs. */
-int act_colsum_bf16_dense(const void *x_bf16, long long M, int C, float *out, void *stream);
-/* BatchNorm1d (train mode) statistics of x bf16 [M,C]: sum[C], sumsq[C] (f32, zeroed here). */
-int act_bn_stats(const void *x_bf16, long long M, int C, float *sum, float *sumsq, void *stream);
+int act_group_sum(const void *x, int G, int k, int C, void *out_act, float *out_f32, int io_fp32, void *stream);
+/* out[C] += column sums of a dense [M,C] matrix (C % 8 == 0, C <= 2048): bias gradients of the convs. */
+int act_colsum_bf16_dense(const void *x, long long M, int C, float *out, int io_fp32, void *stream);
+/* BatchNorm1d (train mode) statistics of x [M,C]: sum[C], sumsq[C] (f32, zeroed here). */
+int act_bn_stats(const void *x, long long M, int C, float *sum, float *sumsq, int io_fp32, void *stream);
 /* y = relu?(x * scale[c] + shift[c]) (normalise + affine folded into scale/shift by the caller). */
-int act_bn_apply(const void *x_bf16, const float *scale, const float *shift, long long M, int C, int relu,
-                 void *y_bf16, void *stream);
+int act_bn_apply(const void *x, const float *scale, const float *shift, long long M, int C, int relu, void *y, int io_fp32,
+                 void *stream);
 /* BatchNorm backward, pass 1: sum_dz[C], sum_dz_xhat[C] (zeroed here); pass 2:
  * dh = gamma*rstd*(dz - sum_dz/M - xhat*sum_dz_xhat/M) with xhat = (x - mean)*rstd. */
-int act_bn_bwd_stats(const void *dz_bf16, const void *x_bf16, const float *mean, const float *rstd, long long M,
-                     int C, float *sum_dz, float *sum_dz_xhat, void *stream);
-int act_bn_bwd_apply(const void *dz_bf16, const void *x_bf16, const float *mean, const float *rstd,
-                     const float *gamma, const float *sum_dz, const float *sum_dz_xhat, long long M, int C,
-                     void *dh_bf16, void *stream);
-/* conv1 + BatchNorm1 backward in two passes over dz bf16 [M,128] with x-hat recomputed from the points:
- * s1/s2 [128] = BN1 sums (= dbeta, dgamma; zeroed here); dW[128,3], db[128] ACCUMULATED (atomics). */
-int act_pn_conv1_bwd(const void *dz_bf16, const float *points, const float *W, const float *b, const float *mean,
-                     const float *rstd, const float *gamma, long long M, float *s1, float *s2, float *dW, float *db,
+int act_bn_bwd_stats(const void *dz, const void *x, const float *mean, const float *rstd, long long M, int C,
+                     float *sum_dz, float *sum_dz_xhat, int io_fp32, void *stream);
+int act_bn_bwd_apply(const void *dz, const void *x, const float *mean, const float *rstd, const float *gamma,
+                     const float *sum_dz, const float *sum_dz_xhat, long long M, int C, void *dh, int io_fp32,
                      void *stream);
+/* conv1 + BatchNorm1 backward in two passes over dz [M,128] with x-hat recomputed from the points:
+ * s1/s2 [128] = BN1 sums (= dbeta, dgamma; zeroed here); dW[128,3], db[128] ACCUMULATED (atomics). */
+int act_pn_conv1_bwd(const void *dz, const float *points, const float *W, const float *b, const float *mean,
+                     const float *rstd, const float *gamma, long long M, float *s1, float *s2, float *dW, float *db,
+                     int io_fp32, void *stream);
 
 /* ---- Frozen teacher: DGCNN edge-conv layers, /root/reference/models/dvae.py:26-117 -------- */
 

@@ -1,0 +1,193 @@
+"""GPU: the fp32-grade PARITY MODE (ops.precision("fp32x3"): f32 stored activations, every GEMM operand split into bf16
+(hi, mid) pieces and multiplied by the unchanged tcgen05 kernel over a tripled K, f32 attention) against the golden
+fixtures written from the UNMODIFIED reference (oracle/make_golden.py) at north_star's bar:
+
+    features / losses   <= 1e-3 relative (Frobenius norm over the tensor; losses as scalars)
+    gradients           <= 1e-2 relative, gradient NORMS <= 1e-3   (the judge's bar for round 2)
+
+The default bf16 speed mode is held to its own (looser, documented) bounds in test_gpu_model.py / test_gpu_layers.py;
+this file is the proof that the same kernels reproduce the reference once operand precision is taken out of the picture,
+and that the schedule variants of the engine (eager / CUDA graph / pipelined) are the same arithmetic."""
+import numpy as np
+import pytest
+import torch
+
+from act_b200 import layers, models, modules, ops
+from oracle import ref_model
+
+pytestmark = pytest.mark.gpu
+FEAT, GRAD, NORM = 1e-3, 1e-2, 1e-3
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+@pytest.fixture(autouse=True)
+def parity_mode():
+    with ops.precision("fp32x3"):
+        yield
+    assert ops.get_precision() == "bf16"
+
+
+@pytest.mark.parametrize("M,N,K", [(3456, 1152, 384), (3456, 384, 1536), (1000, 256, 128), (262144 // 8, 512, 256)])
+def test_split_gemm_is_fp32_grade(M, N, K):
+    """All three operand layouts the step uses (forward K/K, dgrad K/MN, wgrad MN/MN) against float64."""
+    torch.manual_seed(M + N)
+    a = torch.randn(M, K, device="cuda") * (1 + torch.rand(M, 1, device="cuda") * 30)      # rows of very different scale
+    b = torch.randn(N, K, device="cuda")
+    want = a.double() @ b.double().t()
+    got = ops.gemm(a, b, out_dtype=torch.float32)
+    assert rel(got, want) < 2e-5, rel(got, want)
+    assert rel(ops.gemm(a.bfloat16(), b.bfloat16(), out_dtype=torch.float32), want) > 1e-3   # what the speed mode gives
+    bt = b.t().contiguous()                                                                  # [K, N]
+    assert rel(ops.gemm(a, bt, b_mn=True, out_dtype=torch.float32), want) < 2e-5
+    dy = torch.randn(M, N, device="cuda")
+    gw = torch.zeros(N, K, device="cuda")
+    ops.wgrad(dy, a, gw)                                                                     # dy^T a, split-K atomics
+    assert rel(gw, dy.double().t() @ a.double()) < 2e-5
+    # fused epilogue pieces with f32 side tensors: bias + GELU + pre-activation output, then x GELU'(u) on the way back
+    bias = torch.randn(N, device="cuda")
+    u = torch.empty(M, N, device="cuda")
+    y = ops.gemm(a * 0.02, b, bias=bias, act=ops.ACT_GELU, preact_out=u)
+    pre = (a.double() * 0.02) @ b.double().t() + bias.double()
+    assert y.dtype == torch.float32 and rel(u, pre) < 2e-5
+    assert rel(y, torch.nn.functional.gelu(pre)) < 2e-5
+    w2 = torch.randn(K, N, device="cuda")                                                    # Linear(N -> K).weight
+    dy2 = torch.randn(M, K, device="cuda")
+    du = ops.gemm(dy2, w2, b_mn=True, mul_in=u, mul_mode=ops.MUL_GELU_GRAD)
+    x64 = pre
+    gp = 0.5 * (1 + torch.erf(x64 / 2 ** 0.5)) + x64 * torch.exp(-0.5 * x64 * x64) / (2 * np.pi) ** 0.5
+    assert rel(du, (dy2.double() @ w2.double()) * gp) < 5e-5
+
+
+def test_block_stack_cfg1_features_1e3(golden):
+    """BASELINE config 1 (Block x12, d=384, 64 tokens, batch 2) against utils/transformer_layers.Block of the reference."""
+    g = golden("block12_cfg1.npz")
+    blocks = torch.nn.ModuleList([modules.Block(384, 6) for _ in range(12)])
+    ref_model.fill_params(blocks, seed=1)
+    blocks = blocks.cuda().eval()
+    with torch.no_grad():
+        y = modules.run_blocks(list(blocks), torch.from_numpy(g["x"]).cuda(), None, False)
+    assert rel(y, g["y"]) < FEAT, rel(y, g["y"])
+
+
+def test_encoder_features_and_gradients(golden):
+    """mini-PointNet Encoder (models/dvae.py:185-215), train-mode BatchNorm: tokens, running stats, every gradient."""
+    g, grp = golden("encoder.npz"), golden("group.npz")
+    nb = torch.from_numpy(grp["shapenet/neighborhood"][:2]).cuda()
+    enc = ref_model.fill_params(modules.Encoder(384), seed=2).cuda().train()
+    out = enc(nb)
+    (out * torch.from_numpy(g["wout"]).cuda()).sum().backward()
+    assert rel(out, g["out"]) < FEAT, rel(out, g["out"])
+    for k, b in enc.named_buffers():
+        if "num_batches" not in k:
+            assert rel(b, g["buf/" + k]) < FEAT, k
+    scale = np.abs(g["grad/second_conv.3.bias"]).max()
+    for k, p in enc.named_parameters():
+        want = g["grad/" + k]
+        if k in ("first_conv.0.bias", "first_conv.3.bias", "second_conv.0.bias"):
+            assert p.grad.abs().max().item() < 1e-2 * scale, k      # exact value 0 (constant in front of BatchNorm / max)
+            continue
+        assert rel(p.grad, want) < GRAD, (k, rel(p.grad, want))
+
+
+@pytest.mark.parametrize("flat", [False, True])
+def test_student_step_features_and_gradients(golden, flat):
+    """The full Stage-II student step (BASELINE config 2 at B=4) against the unmodified ACT_PointDistillation."""
+    g = golden("student_step.npz")
+    cfg = models.default_config(mask_ratio=0.6, drop_path_rate=0.0)
+    model = ref_model.fill_params(models.ACT_PointDistillation(cfg, teacher="synthetic"), seed=4).cuda().train()
+    if flat:
+        layers.FlatParams(model, exclude=model.UNUSED_PARAMETERS)
+    pts, teacher, mask = (torch.from_numpy(g[k]).cuda() for k in ("pts", "teacher", "mask"))
+    loss = model(pts, mask=mask, teacher_feat=teacher)
+    loss.backward()
+    want = float(g["loss"])
+    assert abs(loss.item() - want) <= 1e-4 * abs(want), (loss.item(), want)
+    norms = dict(zip(g["grad_names"].tolist(), g["grad_norms"].tolist()))
+    worst = {}
+    for k, p in model.named_parameters():
+        if k not in norms:
+            continue
+        gn = p.grad.norm().item()
+        if norms[k] > 1e-6:
+            worst[k] = abs(gn - norms[k]) / norms[k]
+        if "grad/" + k in g.files:
+            assert rel(p.grad, g["grad/" + k]) < GRAD, (k, rel(p.grad, g["grad/" + k]))
+    bad = {k: v for k, v in worst.items() if v > NORM and not k.endswith(("first_conv.0.bias", "first_conv.3.bias", "second_conv.0.bias"))}
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:8]
+    for k, b in model.named_buffers():
+        if "running" in k:
+            assert rel(b, g["buf/" + k]) < FEAT, k
+
+
+def test_schedule_variants_are_the_same_arithmetic():
+    """engine.PretrainStep eager vs CUDA-graph replay vs pipelined (look-ahead on and off): 6 AdamW steps, per-step losses
+    within 1e-3 and final weights within 1e-3 -- the only differences left are float-atomic summation orders, which the
+    parity mode does not amplify (in the bf16 mode a 1e-7 perturbation flips bf16 roundings and the trajectories separate)."""
+    from act_b200.engine import PretrainStep
+
+    def run(use_graph, pipeline, lookahead=False):
+        torch.manual_seed(0)
+        np.random.seed(0)
+        cfg = models.default_config(mask_ratio=0.6, drop_path_rate=0.0)
+        model = ref_model.fill_params(models.ACT_PointDistillation(cfg, teacher="synthetic"), seed=3).cuda().train()
+        fp = layers.FlatParams(model, lr=1e-3, exclude=model.UNUSED_PARAMETERS)
+        eng = PretrainStep(model, fp, 8, 1024, use_graph=use_graph, pipeline=pipeline).capture()
+        b0, b1 = ref_model.synthetic_clouds(8, 1024, seed=1).cuda(), ref_model.synthetic_clouds(8, 1024, seed=2).cuda()
+        seq = [b0, b1, b0, b1, b0, b1, b0]
+        out = [eng.run(seq[i], next_points=seq[i + 1] if lookahead else None).item() for i in range(6)]
+        eng.flush()
+        torch.cuda.synchronize()
+        return np.array(out), fp.flat.clone()
+
+    base, w0 = run(False, False)
+    for args in ((True, False), (True, True), (True, True, True)):
+        got, w = run(*args)
+        np.testing.assert_allclose(got, base, rtol=1e-3, err_msg=str(args))
+        assert rel(w, w0) < 1e-3, (args, rel(w, w0))
+
+
+def test_report_errors_of_both_modes(golden):
+    """Measures -- for the bf16 speed mode and the fp32x3 parity mode side by side -- the errors of the three golden
+    comparisons above and writes them to gpurun_out/parity_report.json (committed as profiles/r2_parity_report.json and
+    attached to the bench line as `parity`)."""
+    import json
+    import os
+    report = {}
+    for mode in ("bf16", "fp32x3"):
+        with ops.precision(mode):
+            r = {}
+            g = golden("block12_cfg1.npz")
+            blocks = ref_model.fill_params(torch.nn.ModuleList([modules.Block(384, 6) for _ in range(12)]), seed=1).cuda().eval()
+            with torch.no_grad():
+                r["block12_cfg1_feature_rel"] = rel(modules.run_blocks(list(blocks), torch.from_numpy(g["x"]).cuda(), None, False), g["y"])
+            g, grp = golden("encoder.npz"), golden("group.npz")
+            nb = torch.from_numpy(grp["shapenet/neighborhood"][:2]).cuda()
+            enc = ref_model.fill_params(modules.Encoder(384), seed=2).cuda().train()
+            out = enc(nb)
+            (out * torch.from_numpy(g["wout"]).cuda()).sum().backward()
+            r["encoder_feature_rel"] = rel(out, g["out"])
+            skip = ("first_conv.0.bias", "first_conv.3.bias", "second_conv.0.bias")
+            r["encoder_grad_rel_max"] = max(rel(p.grad, g["grad/" + k]) for k, p in enc.named_parameters() if k not in skip)
+            g = golden("student_step.npz")
+            cfg = models.default_config(mask_ratio=0.6, drop_path_rate=0.0)
+            model = ref_model.fill_params(models.ACT_PointDistillation(cfg, teacher="synthetic"), seed=4).cuda().train()
+            pts, teacher, mask = (torch.from_numpy(g[k]).cuda() for k in ("pts", "teacher", "mask"))
+            loss = model(pts, mask=mask, teacher_feat=teacher)
+            loss.backward()
+            r["student_step_loss_rel"] = abs(loss.item() - float(g["loss"])) / abs(float(g["loss"]))
+            norms = dict(zip(g["grad_names"].tolist(), g["grad_norms"].tolist()))
+            pg = dict(model.named_parameters())
+            r["student_step_grad_norm_rel_max"] = max(abs(pg[k].grad.norm().item() - n) / n for k, n in norms.items()
+                                                     if n > 1e-6 and not k.endswith(skip))
+            r["student_step_grad_rel_max"] = max(rel(pg[k[5:]].grad, g[k]) for k in g.files if k.startswith("grad/"))
+            report[mode] = {k: float(f"{v:.3e}") for k, v in r.items()}
+    report["what"] = ("relative Frobenius errors against the golden fixtures written from the unmodified reference "
+                      "(tests/golden/*.npz), measured by tests/test_gpu_parity.py::test_report_errors_of_both_modes on a B200")
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", "parity_report.json"), "w") as f:
+        json.dump(report, f, indent=1)
+    assert report["fp32x3"]["student_step_grad_rel_max"] < GRAD and report["fp32x3"]["encoder_feature_rel"] < FEAT
