@@ -66,6 +66,15 @@ def peaks():
     return p
 
 
+def parity_report():
+    """Errors of both precision modes against the reference goldens, as measured on a B200 by
+    tests/test_gpu_parity.py::test_report_errors_of_both_modes (committed copy; None when absent)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_parity_report.json")))
+    except Exception:
+        return None
+
+
 def gemm_traffic():
     """DRAM bytes (read + write) per GEMM launch from the committed ncu capture of the same step (newest round first);
     None when absent.  A profiler number, reported beside -- never instead of -- the timed ones."""
@@ -504,7 +513,9 @@ def run_ours(args):
                     "sustained": sus,
                     "gpu_launches": res["launches"], "cuda_graph": not args.no_graph, "pipelined": res["pipelined"],
                     "loss": res["loss"], "clocks": res["clocks"], "roofline": roof,
-                    "tokenizer_us": res.get("tokenizer_us")}
+                    "tokenizer_us": res.get("tokenizer_us"),
+                    "precision": "bf16 operands, fp32 accumulate (speed mode; ACT_B200_PRECISION=fp32x3 selects the parity mode)",
+                    "parity": parity_report()}
     for name in ("dvae", "dense"):
         if which not in ("all", name):
             continue
