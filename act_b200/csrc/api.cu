@@ -15,9 +15,18 @@ extern "C" const char *act_error_string(int code) {
     return "act_b200: unknown error";
 }
 
+namespace act {
+int &attn_tc_mode();
+}
+
 extern "C" int act_set_option(int key, int value) {
     if (key == ACT_OPT_PDL) {
         act::pdl_flag() = value ? 1 : 0;
+        return ACT_OK;
+    }
+    if (key == ACT_OPT_ATTN_TC) {
+        if (value < 0 || value > 2) return ACT_EINVAL;
+        act::attn_tc_mode() = value;
         return ACT_OK;
     }
     return ACT_EINVAL;

@@ -23,7 +23,7 @@
 //   S = Q K^T, dP = dO V^T into TMEM; threads form P = exp(S*scale - lse) and dS = P * (dP - D) * scale per row
 //   (D = dO . O), write both as bf16 K-major tiles; then dQ = dS K (A = dS K-major, B = K MN-major),
 //   dK = dS^T Q and dV = P^T dO (A = the SAME dS / P tiles read through an MN-major descriptor, B = Q / dO MN-major).
-// Longer sequences keep the two-kernel streaming backward of transformer.cu.
+// Longer sequences: the same products as two looped launches (query side: dQ; key side: dK, dV), see attn_tc_bwd_loop_kernel.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -424,6 +424,221 @@ __global__ void __launch_bounds__(TC_THREADS, 1) attn_tc_bwd_kernel(const __grid
     }
 }
 
+// ------------------------------------------------------------------------------------------------ backward (T > 128)
+// Two launches of one kernel, as in every flash-style backward:
+//   KV_SIDE = false (dQ): CTA = (cloud, 128 query rows, head); Q and dO tiles stay resident, the sequence's K / V tiles
+//       stream through a 2-stage TMA ring; per tile  S = Q K^T, dP = dO V^T -> threads -> dS -> dQ += dS K  (TMEM accumulate).
+//       Also writes delta[b,h,t] = dO . O for the second launch.
+//   KV_SIDE = true (dK, dV): CTA = (cloud, 128 key rows, head); K and V resident, Q / dO tiles stream;
+//       S = Q K^T, dP = dO V^T (rows = queries of the streamed tile) -> P, dS -> dV += P^T dO, dK += dS^T Q.
+// S / dP are single-buffered in TMEM (the MMA thread issues the next pair once the 128 threads have read the current one,
+// while the accumulation MMAs of the current tile are still in flight).
+template <bool KV_SIDE>
+__global__ void __launch_bounds__(TC_THREADS, 1) attn_tc_bwd_loop_kernel(const __grid_constant__ CUtensorMap tm_qkv,
+                                                                         const __grid_constant__ CUtensorMap tm_do,
+                                                                         const __nv_bfloat16 *__restrict__ o,
+                                                                         const __nv_bfloat16 *__restrict__ dO,
+                                                                         const float *__restrict__ lse,
+                                                                         float *__restrict__ delta, int T, int H, float scale,
+                                                                         __nv_bfloat16 *__restrict__ dqkv) {
+    constexpr uint32_t S_COL = 0, DP_COL = 128, A0_COL = 256, A1_COL = 320;       // A0 = dQ or dK, A1 = dV
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t f_full, x_full[2], x_empty[2], sdp_full, pds_ready, acc_done, out_full;
+    __shared__ uint32_t tmem_slot;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sF1 = smem, *sF2 = sF1 + TC_TILE_BYTES, *sX = sF2 + TC_TILE_BYTES;   // sX: 2 stages x (X1 | X2)
+    uint8_t *sS = sX + 4 * TC_TILE_BYTES, *sP = sS + TC_P_BYTES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.y;
+    const int tps = (T + TC_TILE - 1) / TC_TILE;
+    const int b = blockIdx.x / tps, jt = blockIdx.x % tps;
+    const int seq0 = b * T, f_m0 = seq0 + jt * TC_TILE;
+    const int f_rows = min(TC_TILE, T - jt * TC_TILE);              // valid rows of the resident tile
+    const int n_it = tps;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_qkv);
+        tma_prefetch_desc(&tm_do);
+        mbar_init(&f_full, 1);
+        for (int s2 = 0; s2 < 2; ++s2) {
+            mbar_init(&x_full[s2], 1);
+            mbar_init(&x_empty[s2], 1);
+        }
+        mbar_init(&sdp_full, 1);
+        mbar_init(&pds_ready, 4);
+        mbar_init(&acc_done, 1);
+        mbar_init(&out_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    pdl_wait();
+    pdl_trigger();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(&f_full, 2 * TC_TILE_BYTES);
+            if (!KV_SIDE) {
+                tma_load_2d(&tm_qkv, &f_full, sF1, h * TC_D, f_m0);                        // Q
+                tma_load_2d(&tm_do, &f_full, sF2, h * TC_D, f_m0);                         // dO
+            } else {
+                tma_load_2d(&tm_qkv, &f_full, sF1, (H + h) * TC_D, f_m0);                  // K
+                tma_load_2d(&tm_qkv, &f_full, sF2, (2 * H + h) * TC_D, f_m0);              // V
+            }
+            for (int it = 0; it < n_it; ++it) {
+                const int st = it & 1;
+                mbar_wait(&x_empty[st], ((it >> 1) & 1) ^ 1);
+                mbar_expect_tx(&x_full[st], 2 * TC_TILE_BYTES);
+                uint8_t *x1 = sX + st * 2 * TC_TILE_BYTES, *x2 = x1 + TC_TILE_BYTES;
+                const int xm = seq0 + it * TC_TILE;
+                if (!KV_SIDE) {
+                    tma_load_2d(&tm_qkv, &x_full[st], x1, (H + h) * TC_D, xm);             // K(it)
+                    tma_load_2d(&tm_qkv, &x_full[st], x2, (2 * H + h) * TC_D, xm);         // V(it)
+                } else {
+                    tma_load_2d(&tm_qkv, &x_full[st], x1, h * TC_D, xm);                   // Q(it)
+                    tma_load_2d(&tm_do, &x_full[st], x2, h * TC_D, xm);                    // dO(it)
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc(TC_TILE, TC_TILE, false, false);
+            constexpr uint32_t idesc_q = make_idesc(TC_TILE, TC_D, false, true);
+            constexpr uint32_t idesc_t = make_idesc(TC_TILE, TC_D, true, true);
+            const uint32_t f1 = smem_u32(sF1), f2 = smem_u32(sF2), as = smem_u32(sS), ap = smem_u32(sP);
+            auto issue_sdp = [&](int it) {
+                const int st = it & 1;
+                mbar_wait(&x_full[st], (it >> 1) & 1);
+                tc_fence_after();
+                const uint32_t x1 = smem_u32(sX + st * 2 * TC_TILE_BYTES), x2 = x1 + TC_TILE_BYTES;
+                // S = Q K^T, dP = dO V^T: A = the query-side tile, B = the key-side tile (both K-major)
+                const uint32_t sa = KV_SIDE ? x1 : f1, sb = KV_SIDE ? f1 : x1, da = KV_SIDE ? x2 : f2, db = KV_SIDE ? f2 : x2;
+#pragma unroll
+                for (int k = 0; k < TC_D / 16; ++k)
+                    umma_bf16(tmem + S_COL, make_smem_desc(sa + k * 32, 0, 1024), make_smem_desc(sb + k * 32, 0, 1024), idesc_s, k != 0);
+#pragma unroll
+                for (int k = 0; k < TC_D / 16; ++k)
+                    umma_bf16(tmem + DP_COL, make_smem_desc(da + k * 32, 0, 1024), make_smem_desc(db + k * 32, 0, 1024), idesc_s, k != 0);
+                umma_commit(&sdp_full);
+            };
+            mbar_wait(&f_full, 0);
+            issue_sdp(0);
+            for (int it = 0; it < n_it; ++it) {
+                const int st = it & 1;
+                mbar_wait(&pds_ready, it & 1);
+                tc_fence_after();
+                const uint32_t x1 = smem_u32(sX + st * 2 * TC_TILE_BYTES), x2 = x1 + TC_TILE_BYTES;
+#pragma unroll
+                for (int k = 0; k < TC_TILE / 16; ++k) {
+                    const uint32_t acc = (it | k) != 0;
+                    if (!KV_SIDE) {       // dQ += dS K(it): A = dS K-major, B = K tile MN-major
+                        umma_bf16(tmem + A0_COL, make_smem_desc(as + (k >> 2) * (TC_TILE * 128) + (k & 3) * 32, 0, 1024),
+                                  make_smem_desc(x1 + k * 2048, TC_TILE * 128, 1024), idesc_q, acc);
+                    } else {              // dK += dS^T Q(it), dV += P^T dO(it): A = dS / P through the MN-major view
+                        umma_bf16(tmem + A0_COL, make_smem_desc(as + k * 2048, TC_TILE * 128, 1024),
+                                  make_smem_desc(x1 + k * 2048, TC_TILE * 128, 1024), idesc_t, acc);
+                        umma_bf16(tmem + A1_COL, make_smem_desc(ap + k * 2048, TC_TILE * 128, 1024),
+                                  make_smem_desc(x2 + k * 2048, TC_TILE * 128, 1024), idesc_t, acc);
+                    }
+                }
+                umma_commit(&x_empty[st]);
+                umma_commit(&acc_done);
+                if (it + 1 < n_it) issue_sdp(it + 1);
+            }
+            umma_commit(&out_full);
+        }
+    } else {
+        const int quad = warp & 3, r = quad * 32 + lane;
+        const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
+        const float sl2 = scale * 1.4426950408889634f;
+        const int ldo = H * TC_D;
+        float D = 0.f, L2 = 0.f;
+        if (!KV_SIDE && r < f_rows) {      // resident query row: D = dO . O once (also published for the key-side launch)
+            const int m = f_m0 + r;
+            const uint4 *po = reinterpret_cast<const uint4 *>(o + (size_t)m * ldo + h * TC_D);
+            const uint4 *pg = reinterpret_cast<const uint4 *>(dO + (size_t)m * ldo + h * TC_D);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 uo = __ldg(po + c), ug = __ldg(pg + c);
+                const __nv_bfloat162 *ho = reinterpret_cast<const __nv_bfloat162 *>(&uo);
+                const __nv_bfloat162 *hg = reinterpret_cast<const __nv_bfloat162 *>(&ug);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 fo = __bfloat1622float2(ho[q]), fg = __bfloat1622float2(hg[q]);
+                    D = fmaf(fo.x, fg.x, fmaf(fo.y, fg.y, D));
+                }
+            }
+            const size_t si = ((size_t)b * H + h) * T + jt * TC_TILE + r;
+            delta[si] = D;
+            L2 = __ldg(lse + si) * 1.4426950408889634f;
+        }
+        for (int it = 0; it < n_it; ++it) {
+            const int x_rows = min(TC_TILE, T - it * TC_TILE);       // valid rows of the streamed tile
+            bool row_ok;
+            int hi;                                                  // valid key columns: [0, hi)
+            if (!KV_SIDE) {
+                row_ok = r < f_rows;
+                hi = x_rows;
+            } else {
+                row_ok = r < x_rows;
+                hi = f_rows;
+                if (row_ok) {
+                    const size_t si = ((size_t)b * H + h) * T + it * TC_TILE + r;
+                    D = __ldg(delta + si);
+                    L2 = __ldg(lse + si) * 1.4426950408889634f;
+                }
+            }
+            if (!row_ok) hi = 0;
+            mbar_wait(&sdp_full, it & 1);
+            tc_fence_after();
+            if (it > 0) mbar_wait(&acc_done, (it - 1) & 1);          // the previous tile's P / dS have been consumed
+#pragma unroll 1
+            for (int c = 0; c < TC_TILE; c += 32) {
+                uint32_t vs[32], vd[32];
+                tmem_ld32(trow + S_COL + c, vs);
+                tmem_ld32(trow + DP_COL + c, vd);
+                float p[32], ds[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    p[i] = (c + i < hi) ? ex2f(__uint_as_float(vs[i]) * sl2 - L2) : 0.f;
+                    ds[i] = p[i] * (__uint_as_float(vd[i]) - D) * scale;
+                }
+                if (KV_SIDE) store_p_chunk(smem_u32(sP), r, c, p);
+                store_p_chunk(smem_u32(sS), r, c, ds);
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&pds_ready);
+        }
+        mbar_wait(&out_full, 0);
+        tc_fence_after();
+        const int ld = 3 * H * TC_D;
+#pragma unroll 1
+        for (int which = 0; which < (KV_SIDE ? 2 : 1); ++which) {
+            float v64[64];
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(trow + (which == 0 ? A0_COL : A1_COL) + c, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v64[c + i] = __uint_as_float(v[i]);
+            }
+            const int part = KV_SIDE ? 1 + which : 0;               // 0 = dQ, 1 = dK, 2 = dV column block of dqkv
+            if (r < f_rows) store_row64(dqkv + (size_t)(f_m0 + r) * ld + (part * H + h) * TC_D, v64, 1.f);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
 static int n_tiles(int B, int T) {
     if (T <= TC_TILE) {
         const int spt = TC_TILE / T;
@@ -454,14 +669,27 @@ int attention_tc_fwd(const void *qkv, int B, int T, int H, float scale, void *o,
 }
 
 int attention_tc_bwd(const void *qkv, const void *o, const void *dO, const float *lse, int B, int T, int H, float scale,
-                     void *dqkv, cudaStream_t st) {
-    if (T > TC_TILE) return ACT_EUNSUPPORTED;
+                     void *dqkv, float *delta, cudaStream_t st) {
     const int Mtot = B * T;
     CUtensorMap tq, tg;
     int rc = make_map(&tq, qkv, Mtot, 3 * H * TC_D, 3 * H * TC_D, TC_TILE);
     if (rc) return rc;
     rc = make_map(&tg, dO, Mtot, H * TC_D, H * TC_D, TC_TILE);
     if (rc) return rc;
+    if (T > TC_TILE) {
+        if (!delta) return ACT_EINVAL;
+        constexpr size_t smem_l = 6 * TC_TILE_BYTES + 2 * TC_P_BYTES + 1024;
+        auto k1 = attn_tc_bwd_loop_kernel<false>;
+        auto k2 = attn_tc_bwd_loop_kernel<true>;
+        ACT_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+        ACT_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l));
+        const dim3 grid(n_tiles(B, T), H);
+        const __nv_bfloat16 *op = reinterpret_cast<const __nv_bfloat16 *>(o), *gp = reinterpret_cast<const __nv_bfloat16 *>(dO);
+        __nv_bfloat16 *dp = reinterpret_cast<__nv_bfloat16 *>(dqkv);
+        ACT_CUDA(launch_k(k1, grid, dim3(TC_THREADS), smem_l, st, true, tq, tg, op, gp, lse, delta, T, H, scale, dp));
+        ACT_CUDA(launch_k(k2, grid, dim3(TC_THREADS), smem_l, st, true, tq, tg, op, gp, lse, delta, T, H, scale, dp));
+        return ACT_OK;
+    }
     constexpr size_t smem = 4 * TC_TILE_BYTES + 2 * TC_P_BYTES + 1024;
     auto kern = attn_tc_bwd_kernel;
     ACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -480,9 +708,10 @@ int attention_tc_bwd(const void *qkv, const void *o, const void *dO, const float
 //            warp-MMA 12.7    27.6  (FMA)174  (FMA) 830         -            -
 // A 27-token problem is latency-bound: 768 tiny warp-MMA CTAs finish before one packed tcgen05 tile has allocated TMEM,
 // waited for its TMA loads and made two passes over S.  The tensor-core tiles win as soon as there is work per tile.
-// ACT_B200_ATTN_TC=2 forces the tcgen05 kernels wherever they are implemented (tests, A/B timing); 0 disables them.
-static int attn_tc_mode() {
-    static const int mode = [] {
+// ACT_B200_ATTN_TC / act_set_option(ACT_OPT_ATTN_TC, v): 1 = this measured dispatch (default), 2 = the tcgen05 kernels
+// wherever they are implemented (tests, A/B timing), 0 = never.
+int &attn_tc_mode() {            // process-wide option (act_set_option(ACT_OPT_ATTN_TC, v)); initialised from the environment
+    static int mode = [] {
         const char *e = std::getenv("ACT_B200_ATTN_TC");
         return e ? atoi(e) : 1;
     }();
@@ -491,7 +720,7 @@ static int attn_tc_mode() {
 bool attention_tc_usable(int T, bool backward) {
     const int mode = attn_tc_mode();
     if (mode == 0) return false;
-    if (backward) return T <= TC_TILE && (mode == 2 || T > 32);
+    if (backward) return mode == 2 || T > 32;
     return mode == 2 || T > TC_TILE;
 }
 

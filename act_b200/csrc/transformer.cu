@@ -599,7 +599,7 @@ namespace act {
 // attention_tc.cu: tcgen05 / TMEM attention (forward any T, backward T <= 128)
 int attention_tc_fwd(const void *qkv, int B, int T, int H, float scale, void *o, float *lse, cudaStream_t st);
 int attention_tc_bwd(const void *qkv, const void *o, const void *dO, const float *lse, int B, int T, int H, float scale,
-                     void *dqkv, cudaStream_t st);
+                     void *dqkv, float *delta, cudaStream_t st);
 bool attention_tc_usable(int T, bool backward);
 int attention_mma_fwd(const void *qkv, int B, int T, int H, float scale, void *o, float *lse, cudaStream_t st);
 int attention_mma_bwd(const void *qkv, const void *o, const void *dO, const float *lse, int B, int T, int H, float scale,
@@ -680,7 +680,7 @@ extern "C" int act_attention_bwd(const void *qkv, const void *o, const void *dO,
     if (B == 0) return ACT_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (io_fp32) return attention_fma_bwd<float>(qkv, o, dO, lse, B, T, H, scale, dqkv, delta, st);
-    if (attention_tc_usable(T, true)) return attention_tc_bwd(qkv, o, dO, lse, B, T, H, scale, dqkv, st);
+    if (attention_tc_usable(T, true)) return attention_tc_bwd(qkv, o, dO, lse, B, T, H, scale, dqkv, delta, st);
     if (attn_use_mma(T, true)) return attention_mma_bwd(qkv, o, dO, lse, B, T, H, scale, dqkv, delta, st);
     return attention_fma_bwd<__nv_bfloat16>(qkv, o, dO, lse, B, T, H, scale, dqkv, delta, st);
 }

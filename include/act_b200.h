@@ -31,6 +31,10 @@ const char *act_error_string(int code);
 /* Process-wide options.  ACT_OPT_PDL (default 1): launch the kernels of the dependent chain with programmatic
  * dependent launch (prologue overlaps the predecessor's tail); 0 serialises them (per-kernel timing). */
 #define ACT_OPT_PDL 1
+/* ACT_OPT_ATTN_TC (default 1): which attention kernels serve a sequence length -- 1 = the measured dispatch (tcgen05 / TMEM
+ * tiles where they win: forward T > 128, backward 32 < T <= 128; warp-MMA kernels for the latency-bound short sequences),
+ * 2 = the tcgen05 kernels wherever they are implemented, 0 = never. */
+#define ACT_OPT_ATTN_TC 2
 int act_set_option(int key, int value);
 
 /* ---- Group tokenizer ------------------------------------------------------------------------------ */

@@ -9,6 +9,16 @@ from act_b200 import ops
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def force_tcgen05_attention():
+    """act_set_option(ACT_OPT_ATTN_TC, 2): the tcgen05 kernels for every length they implement (the default dispatch sends
+    the latency-bound short sequences to the warp-MMA kernels, which tests/test_gpu_layers.py covers)."""
+    from act_b200 import _lib
+    assert _lib.lib().act_set_option(2, 2) == 0
+    yield
+    assert _lib.lib().act_set_option(2, 1) == 0
+
+
 def rel(a, b):
     a, b = a.float().cpu(), b.float().cpu()
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
@@ -33,7 +43,8 @@ def test_attention_tc_forward(B, T, H):
     torch.testing.assert_close(lse, wl, rtol=2e-4, atol=2e-4)
 
 
-@pytest.mark.parametrize("B,T,H", [(128, 27, 6), (7, 27, 6), (128, 64, 6), (5, 65, 6), (3, 128, 6), (9, 14, 6), (2, 1, 6)])
+@pytest.mark.parametrize("B,T,H", [(128, 27, 6), (7, 27, 6), (128, 64, 6), (5, 65, 6), (3, 128, 6), (9, 14, 6), (2, 1, 6),
+                                   (16, 206, 6), (4, 512, 6), (3, 300, 2), (2, 129, 6)])
 def test_attention_tc_backward(B, T, H):
     torch.manual_seed(B * 77 + T)
     qkv = (torch.randn(B * T, 3 * H * 64, device="cuda") * 0.8).bfloat16()
