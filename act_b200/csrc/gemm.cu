@@ -58,6 +58,10 @@ struct GemmEpi {
     int act;               // 0 none, 1 GELU(erf), 2 ReLU
     int mul_mode;          // 0 none, 1: *= GELU'(mul_in), 2: *= (mul_in > 0)
     int aux_fp32;          // preact_out / mul_in are f32 (the fp32-grade parity mode; generic epilogue only)
+    // fused per-column statistics of the stored value (E_STATS: plain + per-slab term): sum and sum of squares over all M
+    // rows -- the train-mode BatchNorm statistics of the mini-PointNet's third conv taken on the fp32 accumulators
+    // (models/dvae.py:196-197); accumulated per CTA in shared memory, flushed once per CTA with atomics.  N <= 512.
+    float *stat_sum, *stat_sq;
     float alpha;           // scales the accumulator first
 };
 
@@ -125,7 +129,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // Operands that do not depend on the accumulator (residual / mul_in pieces) are PREFETCHED into registers by
 // epi_prefetch() before the accumulator is waited for.  MODE is a compile-time hint that fixes which optional parts
 // exist (no flag tests, no dead register arrays); E_GENERIC keeps every part a runtime decision (cold layouts).
-enum : int { E_GENERIC = 0, E_PLAIN, E_GELU, E_MULGELU, E_MULRELU, E_RESID, E_ATOMIC, E_GMAX };
+enum : int { E_GENERIC = 0, E_PLAIN, E_GELU, E_MULGELU, E_MULRELU, E_RESID, E_ATOMIC, E_GMAX, E_STATS };
 
 struct EpiPre {
     uint4 r[8];   // residual: 32 f32 of this lane's pieces;  mul_in: 32 bf16 (CW = 8: r[0..3]; CW = 4: 8-byte halves)
@@ -158,7 +162,7 @@ __device__ __forceinline__ void epi_load_bias(const GemmEpi &epi, EpiBias &eb, i
     using TR = EpiTraits<MODE>;
     constexpr bool G = MODE == E_GENERIC;
     const bool has_bias = (MODE == E_ATOMIC || MODE == E_MULGELU || MODE == E_MULRELU) ? false : (epi.bias != nullptr);
-    const bool has_slab = (MODE == E_PLAIN || G) ? (epi.slab_bias != nullptr) : false;
+    const bool has_slab = (MODE == E_PLAIN || MODE == E_STATS || G) ? (epi.slab_bias != nullptr) : false;
     const bool has_rscale = (G || MODE == E_RESID) ? (epi.row_scale != nullptr) : false;
     if (!(has_bias || has_slab || has_rscale) || row0 >= M || n >= N) return;
     const bool wide = TR::wide(epi);
@@ -248,7 +252,7 @@ __device__ __forceinline__ void epi_prefetch_cw(const GemmEpi &epi, EpiPre &pre,
 template <int MODE>
 __device__ __forceinline__ void epi_prefetch(const GemmEpi &epi, EpiPre &pre, int row0, int M, int n, int N, int lane) {
     using TR = EpiTraits<MODE>;
-    if (MODE == E_PLAIN || MODE == E_GELU || MODE == E_ATOMIC || MODE == E_GMAX) return;
+    if (MODE == E_PLAIN || MODE == E_GELU || MODE == E_ATOMIC || MODE == E_GMAX || MODE == E_STATS) return;
     if (row0 >= M || n >= N) return;
     // FULL: the chunk lies entirely inside the matrix (the common case) -> no per-row / per-column predicates
     const bool full = row0 + 32 <= M && n + 32 <= N;
@@ -263,7 +267,7 @@ __device__ __forceinline__ void epi_prefetch(const GemmEpi &epi, EpiPre &pre, in
 
 template <int MODE, int CW, bool FULL>
 __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPre &pre, const EpiBias &eb, int row0, int M,
-                                                 int n, int N, int lane, uint32_t stage) {
+                                                 int n, int N, int lane, uint32_t stage, float *s_stats = nullptr) {
     using TR = EpiTraits<MODE>;
     constexpr bool G = MODE == E_GENERIC;
     constexpr int NIT = CW == 4 ? 8 : 4, RPI = 32 / NIT;
@@ -281,9 +285,14 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
     const bool col_ok = FULL || col < N;              // N % 8 == 0 (host): a lane's CW columns are all in or all out
     const int rfirst = row0 + rq;
     const int rows_left = FULL ? 32 : (col_ok ? M - rfirst : 0);    // iteration i stores iff i * RPI < rows_left
-    const bool has_slab = (MODE == E_PLAIN || MODE == E_GENERIC) ? (epi.slab_bias != nullptr) : false;
+    const bool has_slab = (MODE == E_PLAIN || MODE == E_STATS || MODE == E_GENERIC) ? (epi.slab_bias != nullptr) : false;
     float best[CW];
     int barg[CW];
+    float st1[CW], st2[CW];                                  // E_STATS: this lane's column sums over its rows of the chunk
+    if (MODE == E_STATS) {
+#pragma unroll
+        for (int j = 0; j < CW; ++j) st1[j] = st2[j] = 0.f;
+    }
     const bool want_arg = gmode && epi.garg != nullptr;      // the arg-max costs a second shuffle per value: only on demand
     if (gmode) {
 #pragma unroll
@@ -323,6 +332,10 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
 #pragma unroll
                 for (int j = 0; j < CW; ++j) best[j] = fmaxf(best[j], f[j]);
             }
+        }
+        if (MODE == E_STATS && i * RPI < rows_left) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) { st1[j] += f[j]; st2[j] = fmaf(f[j], f[j], st2[j]); }
         }
         if (i * RPI < rows_left && has_out) {
             if (has_preact) {
@@ -416,6 +429,24 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
         op += ostep;
         pp += pstep;
     }
+    if (MODE == E_STATS) {
+        // combine the row groups held by different lanes (same columns), then one shared-memory atomic per column and stat
+#pragma unroll
+        for (int off = (CW == 4 ? 8 : 4); off < 32; off <<= 1) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+                st1[j] += __shfl_xor_sync(0xffffffffu, st1[j], off);
+                st2[j] += __shfl_xor_sync(0xffffffffu, st2[j], off);
+            }
+        }
+        if (rq == 0 && col_ok && s_stats) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+                atomicAdd(s_stats + col + j, st1[j]);
+                atomicAdd(s_stats + 512 + col + j, st2[j]);
+            }
+        }
+    }
     if (gmode) {
         // combine the row groups held by different lanes (same columns): lanes differ in rq
 #pragma unroll
@@ -450,7 +481,8 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
 // thread, and its spills went to L2 (the L1 is almost entirely carved out as shared memory there).
 template <int MODE, bool LATE = false>
 __device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_t (&v)[32], EpiPre &pre, const EpiBias &eb,
-                                               int row0, int M, int n, int N, int lane, uint32_t stage) {
+                                               int row0, int M, int n, int N, int lane, uint32_t stage,
+                                               float *s_stats = nullptr) {
     using TR = EpiTraits<MODE>;
     if (n >= N || row0 >= M) return;                  // warp-uniform
     __syncwarp();                                     // the previous chunk's phase-B reads of the tile are done
@@ -466,18 +498,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_
     __syncwarp();
     const bool full = row0 + 32 <= M && n + 32 <= N;
     if (TR::wide(epi)) {
-        if (full) epilogue_phase_b<MODE, 8, true>(epi, pre, eb, row0, M, n, N, lane, stage);
-        else epilogue_phase_b<MODE, 8, false>(epi, pre, eb, row0, M, n, N, lane, stage);
+        if (full) epilogue_phase_b<MODE, 8, true>(epi, pre, eb, row0, M, n, N, lane, stage, s_stats);
+        else epilogue_phase_b<MODE, 8, false>(epi, pre, eb, row0, M, n, N, lane, stage, s_stats);
     } else {
-        if (full) epilogue_phase_b<MODE, 4, true>(epi, pre, eb, row0, M, n, N, lane, stage);
-        else epilogue_phase_b<MODE, 4, false>(epi, pre, eb, row0, M, n, N, lane, stage);
+        if (full) epilogue_phase_b<MODE, 4, true>(epi, pre, eb, row0, M, n, N, lane, stage, s_stats);
+        else epilogue_phase_b<MODE, 4, false>(epi, pre, eb, row0, M, n, N, lane, stage, s_stats);
     }
 }
 
 // One chunk: TMEM -> registers, (optionally) hand the accumulator buffer back, then the two epilogue phases.
 template <int MODE, bool LATE = false>
 __device__ __forceinline__ void epi_do_chunk(const GemmEpi &epi, uint32_t taddr, bool have_acc, uint64_t *release_bar,
-                                             EpiPre &pre, int row0, int M, int n, int N, int lane, uint32_t stage) {
+                                             EpiPre &pre, int row0, int M, int n, int N, int lane, uint32_t stage,
+                                             float *s_stats = nullptr) {
     EpiBias eb;
     epi_load_bias<MODE>(epi, eb, row0, M, n, N, lane);
     uint32_t v[32];
@@ -493,7 +526,7 @@ __device__ __forceinline__ void epi_do_chunk(const GemmEpi &epi, uint32_t taddr,
         __syncwarp();
         if (lane == 0) mbar_arrive(release_bar);
     }
-    epilogue_chunk<MODE, LATE>(epi, v, pre, eb, row0, M, n, N, lane, stage);
+    epilogue_chunk<MODE, LATE>(epi, v, pre, eb, row0, M, n, N, lane, stage, s_stats);
 }
 
 // ------------------------------------------------------------------------------------- the kernel
@@ -651,11 +684,15 @@ __global__ void __launch_bounds__(PersistCfg<MODE>::THREADS, 1) gemm_bf16_persis
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_slot;
+    __shared__ float s_stats_store[MODE == E_STATS ? 1024 : 1];      // [sum | sumsq] x 512 columns, this CTA's share
+    float *s_stats = MODE == E_STATS ? s_stats_store : nullptr;
 
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_kb = (K + GEMM_BK - 1) / GEMM_BK;
 
+    if (MODE == E_STATS)
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_stats_store[i] = 0.f;
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
@@ -788,12 +825,19 @@ __global__ void __launch_bounds__(PersistCfg<MODE>::THREADS, 1) gemm_bf16_persis
 #pragma unroll 1
                 for (int c = 0; c < NCH; ++c)
                     epi_do_chunk<MODE, true>(epi, tmem_d + (uint32_t)(c * 32), true, c + 1 == NCH ? &tempty_bar[buf] : nullptr,
-                                             pa, row0, M, cbase + c * 32, N, lane, stage);
+                                             pa, row0, M, cbase + c * 32, N, lane, stage, s_stats);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (MODE == E_STATS) {               // one flush per CTA: N <= 512 columns x 2 statistics
+        for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) {
+            const int which = i / N, c = i - which * N;
+            const float v = s_stats_store[which * 512 + c];
+            if (v != 0.f) atomicAdd((which ? epi.stat_sq : epi.stat_sum) + c, v);
+        }
+    }
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
@@ -878,6 +922,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) gem
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_slot;
+    __shared__ float s_stats_store[MODE == E_STATS ? 1024 : 1];
+    float *s_stats = MODE == E_STATS ? s_stats_store : nullptr;
+    if (MODE == E_STATS)
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) s_stats_store[i] = 0.f;
 
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -976,12 +1024,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) gem
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(lempty);
                 }
-                epilogue_chunk<MODE, true>(epi, v, pa, eb, row0, M, cbase + c * 32, N, lane, stage);
+                epilogue_chunk<MODE, true>(epi, v, pa, eb, row0, M, cbase + c * 32, N, lane, stage, s_stats);
             }
         }
     }
     tc_fence_before();
     cluster_sync_all();                           // nobody leaves (or frees TMEM) while the peer may still touch it
+    if (MODE == E_STATS) {
+        for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) {
+            const int which = i / N, c = i - which * N;
+            const float v = s_stats_store[which * 512 + c];
+            if (v != 0.f) atomicAdd((which ? epi.stat_sq : epi.stat_sum) + c, v);
+        }
+    }
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc_2cta(tmem_base, 512);
@@ -1056,7 +1111,7 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
                              void *preact_out, const void *mul_in, int ldm, int mul_mode, const float *resid, int ldr,
                              int resid_row_div, const float *row_scale, int rows_per_scale, float *gmax_f32,
                              void *gmax_bf16, uint8_t *garg, int ldg, float alpha, int splits, int block_n,
-                             int persistent, int aux_fp32, void *stream) {
+                             int persistent, int aux_fp32, float *colstat_sum, float *colstat_sq, void *stream) {
     using namespace act;
     const bool gmode = gmax_f32 || gmax_bf16 || garg;
     if (!A || !B || (!out && !gmode) || M <= 0 || N <= 0 || K <= 0) return ACT_EINVAL;
@@ -1087,6 +1142,16 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
         resid = nullptr;
     }
     epi.gmax_f32 = gmax_f32; epi.gmax_bf16 = reinterpret_cast<__nv_bfloat16 *>(gmax_bf16); epi.garg = garg; epi.ldg = ldg;
+    epi.stat_sum = colstat_sum; epi.stat_sq = colstat_sq;
+    const bool want_stats = colstat_sum != nullptr || colstat_sq != nullptr;
+    if (want_stats) {
+        // column statistics ride on the plain (+ per-slab term) epilogue of the many-tile K-major kernels only
+        if (!colstat_sum || !colstat_sq || N > 512 || a_mn_major || b_mn_major || splits != 1 || act_kind || preact_out ||
+            mul_in || resid || row_scale || gmode || alpha != 1.f || !out)
+            return ACT_EUNSUPPORTED;
+        ACT_CUDA(cudaMemsetAsync(colstat_sum, 0, N * sizeof(float), (cudaStream_t)stream));
+        ACT_CUDA(cudaMemsetAsync(colstat_sq, 0, N * sizeof(float), (cudaStream_t)stream));
+    }
     int mode = E_GENERIC;
     if (alpha == 1.f && !epi.aux_fp32) {
         const bool simple_out = !preact_out && !epi.mul_mode && !resid && !row_scale && !gmode && !epi.atomic;
@@ -1099,6 +1164,11 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
         else if (gmode && !act_kind && !preact_out && !epi.mul_mode && !resid && !row_scale) mode = E_GMAX;
     }
     if (epi.slab_bias && mode != E_PLAIN) mode = E_GENERIC;        // only the plain / generic epilogues add the slab term
+    if (want_stats) {
+        if (mode != E_PLAIN) return ACT_EUNSUPPORTED;
+        mode = E_STATS;
+        if (persistent <= 0) persistent = 1;                        // the per-CTA accumulation lives in the persistent kernels
+    }
     const long long tiles128 = (long long)((M + 127) / 128) * ((N + 127) / 128) * splits;
     // persistent: more than two waves of the one-tile-per-CTA kernel (2 CTAs / SM), or more than one wave of long-K
     // tiles on a tall matrix (the teacher-ViT token GEMMs: the 2-stage 128x192 one-tile variant starves there)
@@ -1109,7 +1179,7 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
     // tiles there; the GELU epilogue is compute-heavy enough that the pair's doubled tile does not pay at K = 768).
     const long long pair_tiles = (long long)((M + 255) / 256) * ((N + 255) / 256);
     if (persistent == 1 && auto_persist && block_n == 0 && !a_mn_major && !b_mn_major && !gmode && splits == 1 &&
-        (mode == E_PLAIN || mode == E_RESID) && pair_tiles >= 74 && act::pair_enabled())
+        (mode == E_PLAIN || mode == E_RESID || mode == E_STATS) && pair_tiles >= 74 && act::pair_enabled())
         persistent = 2;
     const bool pair = persistent == 2;
     if (pair && (a_mn_major || b_mn_major || gmode || splits != 1 || block_n != 0)) return ACT_EUNSUPPORTED;
@@ -1155,6 +1225,7 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
         if (mode == E_PLAIN) return launch_gemm_pair<E_PLAIN>(ta, tb, epi, M, N, K, st);
         if (mode == E_GELU) return launch_gemm_pair<E_GELU>(ta, tb, epi, M, N, K, st);
         if (mode == E_RESID) return launch_gemm_pair<E_RESID>(ta, tb, epi, M, N, K, st);
+        if (mode == E_STATS) return launch_gemm_pair<E_STATS>(ta, tb, epi, M, N, K, st);
         return ACT_EUNSUPPORTED;
     }
     if (wide384 && (mode == E_RESID || mode == E_PLAIN)) {
@@ -1179,8 +1250,10 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
     ACT_SPEC(1, 256, 1, E_MULRELU) ACT_SPEC(1, 128, 1, E_MULRELU)
     ACT_SPEC(1, 256, 1, E_MULGELU) ACT_SPEC(1, 128, 0, E_GELU) ACT_SPEC(1, 256, 0, E_GELU)
     ACT_SPEC(1, 128, 0, E_GMAX)
+    ACT_SPEC(1, 128, 0, E_STATS) ACT_SPEC(1, 256, 0, E_STATS)
     ACT_SPEC(1, 128, 3, E_ATOMIC) ACT_SPEC(1, 256, 3, E_ATOMIC)
 #undef ACT_SPEC
+    if (mode == E_STATS) return ACT_EUNSUPPORTED;
 #define ACT_GEMM_DISPATCH(BN_)                                                                         \
     do {                                                                                               \
         if (!a_mn_major && !b_mn_major) return launch_gemm<BN_, false, false>(ta, tb, epi, M, N, K, splits, st); \

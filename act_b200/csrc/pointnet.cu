@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T *__restrict__
                                                            const float *__restrict__ rstd,
                                                            const float *__restrict__ gamma,
                                                            const float *__restrict__ s1, const float *__restrict__ s2,
-                                                           long long M, int C, T *__restrict__ dh) {
+                                                           long long M, long long M_dz, int C, T *__restrict__ dh) {
     pdl_wait();
     pdl_trigger();
     const int vpr = C / 8, rpc = 256 / vpr;
@@ -320,7 +320,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T *__restrict__
     }
     for (long long m = blockIdx.x * (long long)rpc + rl; m < M; m += (long long)gridDim.x * rpc) {
         float d[8], xv[8];
-        V8<T>::ld(dz + m * C + c0, d);
+        if (m < M_dz) {
+            V8<T>::ld(dz + m * C + c0, d);
+        } else {                         // rows whose upstream gradient is zero by construction (never read, never stored)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d[j] = 0.f;
+        }
         V8<T>::ld(x + m * C + c0, xv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) d[j] = fmaf(ka[j], d[j], fmaf(kb[j], xv[j], kc[j]));
@@ -593,10 +598,10 @@ extern "C" int act_bn_stats(const void *x, long long M, int C, float *sum, float
     return chan_reduce(0, x, nullptr, nullptr, nullptr, M, C, sum, sumsq, io_fp32, (cudaStream_t)stream);
 }
 
-extern "C" int act_bn_bwd_stats(const void *dz, const void *x, const float *mean, const float *rstd, long long M, int C,
+extern "C" int act_bn_bwd_stats(const void *dz, const void *x, const float *mean, const float *rstd, long long M_dz, int C,
                                 float *sum_dz, float *sum_dz_xhat, int io_fp32, void *stream) {
     if (!x || !mean || !rstd) return ACT_EINVAL;
-    return chan_reduce(1, dz, x, mean, rstd, M, C, sum_dz, sum_dz_xhat, io_fp32, (cudaStream_t)stream);
+    return chan_reduce(1, dz, x, mean, rstd, M_dz, C, sum_dz, sum_dz_xhat, io_fp32, (cudaStream_t)stream);
 }
 
 extern "C" int act_bn_apply(const void *x, const float *scale, const float *shift, long long M, int C, int relu, void *y,
@@ -612,15 +617,16 @@ extern "C" int act_bn_apply(const void *x, const float *scale, const float *shif
 }
 
 extern "C" int act_bn_bwd_apply(const void *dz, const void *x, const float *mean, const float *rstd, const float *gamma,
-                                const float *sum_dz, const float *sum_dz_xhat, long long M, int C, void *dh, int io_fp32,
-                                void *stream) {
+                                const float *sum_dz, const float *sum_dz_xhat, long long M, long long M_dz, int C, void *dh,
+                                int io_fp32, void *stream) {
     using namespace act;
-    if (!dz || !x || !mean || !rstd || !gamma || !sum_dz || !sum_dz_xhat || !dh || M <= 0 || C <= 0) return ACT_EINVAL;
+    if (!dz || !x || !mean || !rstd || !gamma || !sum_dz || !sum_dz_xhat || !dh || M <= 0 || C <= 0 || M_dz < 0 || M_dz > M)
+        return ACT_EINVAL;
     if (C % 8 || C / 8 > 256) return ACT_EUNSUPPORTED;
     ACT_IO_DISPATCH(io_fp32, ACT_CUDA(launch_k(bn_bwd_apply_kernel<T>, dim3(grid_for(M, (256 / (C / 8)) * 16)), dim3(256), 0,
                                                (cudaStream_t)stream, true, reinterpret_cast<const T *>(dz),
-                                               reinterpret_cast<const T *>(x), mean, rstd, gamma, sum_dz, sum_dz_xhat, M, C,
-                                               reinterpret_cast<T *>(dh))));
+                                               reinterpret_cast<const T *>(x), mean, rstd, gamma, sum_dz, sum_dz_xhat, M, M_dz,
+                                               C, reinterpret_cast<T *>(dh))));
     return ACT_OK;
 }
 

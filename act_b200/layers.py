@@ -601,11 +601,12 @@ class PointNetEncoderFn(torch.autograd.Function):
             gmax, _, arg2 = ops.group_max(f2, k)                                  # [BG,256]
         w3s = shadow(w3).view(512, 512)
         gpart = ops.gemm(gmax, w3s[:, :256], bias=b3, out_dtype=torch.float32)    # [BG,512]
-        h3 = ops.gemm(f2, w3s[:, 256:], resid=gpart, resid_row_div=k)             # [M,512]
-        if training:
-            sm, sq = ops.bn_stats(h3)
-            sc2, sh2, mean2, rstd2 = ops.bn_finalize(sm, sq, M, g2, be2, eps, momentum, rm2, rv2, nbt2)
+        if training:     # BatchNorm2's batch statistics ride on conv3's epilogue (fp32 accumulators): h3 is not re-read
+            stats = torch.empty(2, 512, dtype=torch.float32, device=p.device)
+            h3 = ops.gemm(f2, w3s[:, 256:], resid=gpart, resid_row_div=k, colstats=stats)     # [M,512]
+            sc2, sh2, mean2, rstd2 = ops.bn_finalize(stats[0], stats[1], M, g2, be2, eps, momentum, rm2, rv2, nbt2)
         else:
+            h3 = ops.gemm(f2, w3s[:, 256:], resid=gpart, resid_row_div=k)         # [M,512]
             mean2, var2 = rm2.double(), rv2.double()
             rstd2 = torch.rsqrt(var2 + eps)
             sc2d = g2.double() * rstd2
@@ -646,11 +647,8 @@ class PointNetEncoderFn(torch.autograd.Function):
         side.run(lambda: ops.wgrad(dF4, a3k, gw4), dF4)
         if GK == BG:
             dZ3 = ops.gemm(dF4, shadow(w4).view(C, 512), b_mn=True, mul_in=a3, mul_mode=ops.MUL_RELU_MASK)
-        else:            # rows of the dropped groups receive no gradient from conv4
-            dZ3 = torch.empty(M, 512, dtype=ops.act_dtype(), device=d.device)
-            ops.gemm(dF4, shadow(w4).view(C, 512), b_mn=True, mul_in=a3k, mul_mode=ops.MUL_RELU_MASK,
-                     out=dZ3[:GK * k])
-            ops.zero_(dZ3[GK * k:])
+        else:            # rows of the dropped groups receive no gradient from conv4: dZ3 holds the first GK*k rows only
+            dZ3 = ops.gemm(dF4, shadow(w4).view(C, 512), b_mn=True, mul_in=a3k, mul_mode=ops.MUL_RELU_MASK)
         dH3, dbe2, dg2 = ops.bn_bwd(dZ3, h3, mean2, rstd2, g2)
         ops.accumulate_(sink.get(g2, "g2"), dg2)
         ops.accumulate_(sink.get(be2, "be2"), dbe2)

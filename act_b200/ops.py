@@ -200,8 +200,9 @@ def split3(x, mn_major, role_b):
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=None, act=ACT_NONE,
          preact_out=None, mul_in=None, mul_mode=MUL_NONE, resid=None, resid_row_div=1, row_scale=None,
          rows_per_scale=1, gmax_f32=None, gmax_bf16=None, garg=None, no_out=False, alpha=1.0, splits=1, block_n=0,
-         persistent=-1):
+         persistent=-1, colstats=None):
     """out[M,N] = epilogue(alpha * A . B^T) on the tcgen05 GEMM (include/act_b200.h: act_gemm_bf16).
+    colstats: f32 [2, N] receiving the per-column (sum, sum of squares) of the stored values (BatchNorm statistics).
     a: [M,K] (or [K,M] if a_mn);  b: [N,K] (or [K,N] if b_mn).  2-D, last-dim contiguous; bf16, or f32 in the parity mode
     (both operands are then split into bf16 pieces and the product runs over 3K, see split3).
     out_dtype None = the activation dtype of the current precision mode.
@@ -236,7 +237,8 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=None, a
               int(act), _p(preact_out), _p(mul_in), mul_in.stride(0) if mul_in is not None else 0, int(mul_mode),
               _p(resid), resid.stride(0) if resid is not None else 0, int(resid_row_div), row_scale,
               int(rows_per_scale), gmax_f32, gmax_bf16, garg, int(ldg), float(alpha), int(splits), int(block_n),
-              int(persistent), int(aux32))
+              int(persistent), int(aux32), colstats[0] if colstats is not None else None,
+              colstats[1] if colstats is not None else None)
     _count()
     return out
 
@@ -524,13 +526,16 @@ def bn_apply(x, scale, shift, relu=True, out=None):
 
 
 def bn_bwd(dz, x, mean, rstd, gamma):
-    """-> (dh bf16, sum_dz (= dbeta), sum_dz_xhat (= dgamma))."""
+    """-> (dh [M,C], sum_dz (= dbeta), sum_dz_xhat (= dgamma)).  dz may hold only the first M_dz <= M rows: the gradient of
+    the remaining rows is zero by construction and is neither stored nor read."""
     M, C = x.shape
+    M_dz = dz.shape[0]
     s = torch.empty(2, C, dtype=torch.float32, device=x.device)
-    assert dz.dtype == x.dtype
-    _lib.call("act_bn_bwd_stats", dz, x, mean, rstd, _lib.ctypes.c_int64(M), C, s[0], s[1], _io32(x))
-    dh = torch.empty_like(dz)
-    _lib.call("act_bn_bwd_apply", dz, x, mean, rstd, gamma, s[0], s[1], _lib.ctypes.c_int64(M), C, dh, _io32(x))
+    assert dz.dtype == x.dtype and M_dz <= M and dz.is_contiguous()
+    _lib.call("act_bn_bwd_stats", dz, x, mean, rstd, _lib.ctypes.c_int64(M_dz), C, s[0], s[1], _io32(x))
+    dh = torch.empty_like(x)
+    _lib.call("act_bn_bwd_apply", dz, x, mean, rstd, gamma, s[0], s[1], _lib.ctypes.c_int64(M), _lib.ctypes.c_int64(M_dz), C,
+              dh, _io32(x))
     _count(2)
     return dh, s[0], s[1]
 

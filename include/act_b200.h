@@ -104,13 +104,18 @@ int act_chamfer_backward(const float *xyz1, const float *xyz2, const int32_t *id
  * block_n: 64 / 128 / 192 / 256 output-tile width (0 = choose).  resid_row_div: 1, or a multiple of 32 (the broadcast
  * term then enters as a per-32-row-slab bias).  rows_per_scale >= 8.  Requirements: N % 8 == 0, K % 8 == 0 pitches,
  * 16-byte aligned pointers.
+ * colstat_sum / colstat_sq (nullable pair, f32 [N], zeroed here): sum and sum of squares of every output column over all
+ * M rows, taken on the fp32 values the epilogue stores (accumulator + bias + per-group term) -- the train-mode BatchNorm
+ * statistics of the mini-PointNet's second BatchNorm (models/dvae.py:196-197) without re-reading the [M,512] conv output.
+ * K-major operands, plain epilogue (bias / resid_row_div >= 32 term only), N <= 512.
  * aux_fp32 = 1: preact_out / mul_in are f32 instead of bf16 -- the fp32-grade parity mode, in which activations are
  * stored in f32 and every operand reaches this GEMM as a three-way bf16 split (act_split3_bf16) with K tripled. */
 int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, int a_mn_major, int b_mn_major, int lda, int ldb,
                   void *out, int ldo, int out_fp32, const float *bias, int act_kind, void *preact_out,
                   const void *mul_in, int ldm, int mul_mode, const float *resid, int ldr, int resid_row_div,
                   const float *row_scale, int rows_per_scale, float *gmax_f32, void *gmax_bf16, uint8_t *garg, int ldg,
-                  float alpha, int splits, int block_n, int persistent, int aux_fp32, void *stream);
+                  float alpha, int splits, int block_n, int persistent, int aux_fp32, float *colstat_sum,
+                  float *colstat_sq, void *stream);
 
 /* The fp32-grade PARITY MODE of the dense layers: x f32 [R, Cc] (row pitch ld elements) -> three bf16 pieces
  * hi = bf16(x), mid = bf16(x - hi), laid out so that ONE act_gemm_bf16 call over a tripled K computes
@@ -244,12 +249,14 @@ int act_bn_stats(const void *x, long long M, int C, float *sum, float *sumsq, in
 int act_bn_apply(const void *x, const float *scale, const float *shift, long long M, int C, int relu, void *y, int io_fp32,
                  void *stream);
 /* BatchNorm backward, pass 1: sum_dz[C], sum_dz_xhat[C] (zeroed here); pass 2:
- * dh = gamma*rstd*(dz - sum_dz/M - xhat*sum_dz_xhat/M) with xhat = (x - mean)*rstd. */
-int act_bn_bwd_stats(const void *dz, const void *x, const float *mean, const float *rstd, long long M, int C,
+ * dh = gamma*rstd*(dz - sum_dz/M - xhat*sum_dz_xhat/M) with xhat = (x - mean)*rstd.
+ * M_dz <= M: only the first M_dz rows of dz exist -- the gradient of the remaining rows is zero by construction (the masked
+ * groups of the student, whose tokens are never computed: models/act.py:276-281) and is neither stored nor read. */
+int act_bn_bwd_stats(const void *dz, const void *x, const float *mean, const float *rstd, long long M_dz, int C,
                      float *sum_dz, float *sum_dz_xhat, int io_fp32, void *stream);
 int act_bn_bwd_apply(const void *dz, const void *x, const float *mean, const float *rstd, const float *gamma,
-                     const float *sum_dz, const float *sum_dz_xhat, long long M, int C, void *dh, int io_fp32,
-                     void *stream);
+                     const float *sum_dz, const float *sum_dz_xhat, long long M, long long M_dz, int C, void *dh,
+                     int io_fp32, void *stream);
 /* conv1 + BatchNorm1 backward in two passes over dz [M,128] with x-hat recomputed from the points:
  * s1/s2 [128] = BN1 sums (= dbeta, dgamma; zeroed here); dW[128,3], db[128] ACCUMULATED (atomics). */
 int act_pn_conv1_bwd(const void *dz, const float *points, const float *W, const float *b, const float *mean,

@@ -204,3 +204,26 @@ def test_gemm_cta_pair(M, N, K):
     if M % 32 == 0:
         got = ops.gemm(a, w, resid=res, resid_row_div=32, persistent=2)
         check(got, lin + res.repeat_interleave(32, 0), True)
+
+
+@pytest.mark.parametrize("M,persist", [(32768, -1), (4096, -1), (262144, -1), (2048, 1)])
+def test_gemm_fused_column_statistics(M, persist):
+    """colstats: per-column sum / sum of squares of the stored values (accumulator + bias + per-group term), accumulated per
+    CTA in shared memory and flushed once -- the BatchNorm statistics of the mini-PointNet's conv3 (models/dvae.py:196-197)
+    without a second pass over the [M,512] output.  Pair kernel (large M) and persistent kernel (small M)."""
+    import torch
+    from act_b200 import ops
+    torch.manual_seed(M)
+    N, K, k = 512, 256, 32
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    gpart = torch.randn(M // k, N, device="cuda")
+    stats = torch.empty(2, N, device="cuda")
+    out = ops.gemm(a, w, resid=gpart, resid_row_div=k, colstats=stats, persistent=persist)
+    ref = a.float() @ w.float().t() + gpart.repeat_interleave(k, 0)
+    assert ((out.float() - ref).norm() / ref.norm()).item() < 5e-3
+    torch.testing.assert_close(stats[0], ref.sum(0), rtol=2e-3, atol=2e-2 * M ** 0.5)
+    torch.testing.assert_close(stats[1], (ref * ref).sum(0), rtol=2e-3, atol=1e-3)
+    mean, var = stats[0] / M, stats[1] / M - (stats[0] / M) ** 2
+    torch.testing.assert_close(mean, ref.mean(0), rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(var, ref.var(0, unbiased=False), rtol=2e-3, atol=1e-5)
