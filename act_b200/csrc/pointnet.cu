@@ -569,7 +569,9 @@ static int chan_reduce_t(int mode, const void *a, const void *x, const float *me
     using namespace act;
     const int rpc = 256 / (C / 8);
     const size_t smem = (size_t)rpc * 2 * C * sizeof(float);
-    const int grid = grid_for(M, rpc * 32);
+    // rows per CTA: 32 per row-lane for the big [B*G*k, C] activations, 8 for the token-sized ones (a few thousand rows:
+    // 32 would leave most SMs idle)
+    const int grid = grid_for(M, rpc * (M >= (1 << 16) ? 32 : 8));
     const T *ap = reinterpret_cast<const T *>(a), *xp = reinterpret_cast<const T *>(x);
     if (mode == 0) ACT_CUDA(launch_k(chan_reduce_kernel<0, T>, dim3(grid), dim3(256), smem, st, true, ap, xp, mean, rstd, M, C, s1, s2));
     else if (mode == 1) ACT_CUDA(launch_k(chan_reduce_kernel<1, T>, dim3(grid), dim3(256), smem, st, true, ap, xp, mean, rstd, M, C, s1, s2));

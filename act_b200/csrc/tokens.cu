@@ -197,39 +197,67 @@ __global__ void __launch_bounds__(256) assemble_rows_kernel(const float *__restr
 }
 
 // backward: dsrc [B, src_T, C]: rows [src_off, src_off + n) = the src rows of dout, the others zero;  dfill[C] += sum over
-// the fill rows.  CTA = 32 consecutive rows of dout (then of the uncovered dsrc rows), thread = one float4 column.
+// the fill rows.  One warp per row (lanes = float4 columns, C <= 1024), 4 rows per warp and 32 per CTA; the fill rows are
+// summed in registers, across the CTA's warps in shared memory, and leave as one atomic per column per CTA.
 __global__ void __launch_bounds__(256) assemble_rows_bwd_kernel(const float *__restrict__ dout, int B, int n, int T, int C,
                                                                 int fill_first, int src_T, int src_off,
                                                                 float *__restrict__ dsrc, float *__restrict__ dfill) {
     pdl_wait();
     pdl_trigger();
-    const int c4 = threadIdx.x;
-    if (c4 >= C / 4) return;
+    __shared__ float s_acc[8][1024];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int C4 = C / 4;
     const long long nout = (long long)B * T, extra = dsrc ? (long long)B * (src_T - n) : 0;
-    const long long r0 = blockIdx.x * 32LL, r1 = min(r0 + 32LL, nout + extra);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     bool any = false;
-    for (long long row = r0; row < r1; ++row) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const long long row = blockIdx.x * 32LL + it * 8 + warp;
+        if (row >= nout + extra) break;
         if (row < nout) {
             const int b = (int)(row / T), t = (int)(row % T);
             const int i = fill_first ? t - (T - n) : t;
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(dout + (size_t)row * C) + c4);
+            const float4 *src = reinterpret_cast<const float4 *>(dout + (size_t)row * C);
             if (i >= 0 && i < n) {
-                if (dsrc) reinterpret_cast<float4 *>(dsrc + ((size_t)b * src_T + src_off + i) * C)[c4] = v;
+                if (dsrc) {
+                    float4 *d = reinterpret_cast<float4 *>(dsrc + ((size_t)b * src_T + src_off + i) * C);
+                    for (int c = lane; c < C4; c += 32) d[c] = __ldg(src + c);
+                }
             } else {
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                 any = true;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int c = lane + 32 * q;
+                    if (c < C4) {
+                        const float4 v = __ldg(src + c);
+                        acc[q].x += v.x; acc[q].y += v.y; acc[q].z += v.z; acc[q].w += v.w;
+                    }
+                }
             }
         } else {                     // a dsrc row no output row came from (e.g. the cls row below the decoder): zero
             const long long e = row - nout;
             const int b = (int)(e / (src_T - n)), q = (int)(e % (src_T - n));
             const int sr = q < src_off ? q : q + n;
-            reinterpret_cast<float4 *>(dsrc + ((size_t)b * src_T + sr) * C)[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 *d = reinterpret_cast<float4 *>(dsrc + ((size_t)b * src_T + sr) * C);
+            for (int c = lane; c < C4; c += 32) d[c] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
-    if (any && dfill) {
-        atomicAdd(dfill + c4 * 4, acc.x); atomicAdd(dfill + c4 * 4 + 1, acc.y);
-        atomicAdd(dfill + c4 * 4 + 2, acc.z); atomicAdd(dfill + c4 * 4 + 3, acc.w);
+    if (!dfill) return;
+    const bool cta_any = __syncthreads_or(any ? 1 : 0) != 0;
+    if (!cta_any) return;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int c = lane + 32 * q;
+        if (c < C4) reinterpret_cast<float4 *>(s_acc[warp])[c] = acc[q];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_acc[w][c];
+        if (t != 0.f) atomicAdd(dfill + c, t);
     }
 }
 
@@ -297,7 +325,7 @@ extern "C" int act_pos_mlp1_bwd(const void *da, int da_fp32, const float *x, con
     using namespace act;
     if (!da || !x || !W || !b || !dW || !db || R < 0) return ACT_EINVAL;
     if (R == 0) return ACT_OK;
-    const int grid = (R + 511) / 512 < 148 ? (R + 511) / 512 : 148;
+    const int grid = (R + 63) / 64 < 148 * 4 ? (R + 63) / 64 : 148 * 4;      // 16 row-lanes x 4 rows per CTA
     if (da_fp32) ACT_CUDA(launch_k(pos_mlp1_bwd_kernel<true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, true, da, x, W, b, R, dW, db));
     else ACT_CUDA(launch_k(pos_mlp1_bwd_kernel<false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, true, da, x, W, b, R, dW, db));
     return ACT_OK;
@@ -344,7 +372,7 @@ extern "C" int act_assemble_rows_bwd(const float *dout, int B, int n, int T, int
                                      float *dsrc, float *dfill, void *stream) {
     using namespace act;
     if (!dout || B < 0 || n < 0 || T < n || C <= 0 || src_off < 0 || src_off + n > src_T) return ACT_EINVAL;
-    if (C % 4 || C / 4 > 256) return ACT_EUNSUPPORTED;
+    if (C % 4 || C > 1024) return ACT_EUNSUPPORTED;
     if (B == 0 || T == 0) return ACT_OK;
     const long long rows = (long long)B * T + (dsrc ? (long long)B * (src_T - n) : 0);
     ACT_CUDA(launch_k(assemble_rows_bwd_kernel, dim3((unsigned)((rows + 31) / 32)), dim3(256), 0, (cudaStream_t)stream, true,

@@ -148,6 +148,9 @@ class ACTPromptedDiscreteVAEwithVIT(nn.Module):
         for blk in self.visual_embed[0]:
             c["blocks"].append({"qkv": _bf(blk.attn.qkv.weight), "proj": _bf(blk.attn.proj.weight),
                                 "fc1": _bf(blk.mlp.fc1.weight), "fc2": _bf(blk.mlp.fc2.weight)})
+        for p in self.encoder.parameters():          # frozen: layers.shadow() finds the bf16 copy instead of casting per call
+            if p.dim() > 1:
+                p._act_shadow = _bf(p)
         self._cache = c
         return c
 

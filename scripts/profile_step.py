@@ -16,9 +16,12 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 torch.manual_seed(0)
 np.random.seed(0)
 TEACHER = sys.argv[3] if len(sys.argv) > 3 else "native"
-model = models.ACT_PointDistillation(models.default_config(0.6, 0.1), teacher="native" if TEACHER == "native" else "synthetic").cuda().train()
+NP = int(sys.argv[4]) if len(sys.argv) > 4 else 1024          # points per cloud (8192 = dense regime)
+G = int(sys.argv[5]) if len(sys.argv) > 5 else 64             # groups per cloud (512 = dense regime)
+model = models.ACT_PointDistillation(models.default_config(0.6, 0.1, num_group=G),
+                                     teacher="native" if TEACHER == "native" else "synthetic").cuda().train()
 fp = layers.FlatParams(model, exclude=model.UNUSED_PARAMETERS)
-pts = synthetic_clouds(B, 1024).cuda()
+pts = synthetic_clouds(B, NP).cuda()
 
 
 def step():
