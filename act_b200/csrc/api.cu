@@ -17,6 +17,7 @@ extern "C" const char *act_error_string(int code) {
 
 namespace act {
 int &attn_tc_mode();
+int &gemm_sm_cap();
 }
 
 extern "C" int act_set_option(int key, int value) {
@@ -27,6 +28,11 @@ extern "C" int act_set_option(int key, int value) {
     if (key == ACT_OPT_ATTN_TC) {
         if (value < 0 || value > 2) return ACT_EINVAL;
         act::attn_tc_mode() = value;
+        return ACT_OK;
+    }
+    if (key == ACT_OPT_GEMM_SM_CAP) {
+        if (value < 0) return ACT_EINVAL;
+        act::gemm_sm_cap() = value;
         return ACT_OK;
     }
     return ACT_EINVAL;

@@ -29,6 +29,13 @@
 
 namespace act {
 
+// ACT_OPT_GEMM_SM_CAP: upper bound on the SMs a persistent / CTA-pair GEMM occupies (0 = all).  The frozen teacher's large
+// GEMMs run beside the student's latency-bound chain on another stream; leaving a few SMs free keeps that chain moving.
+int &gemm_sm_cap() {
+    static int cap = 0;
+    return cap;
+}
+
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;          // 64 bf16 = 128 B = one swizzle row
 constexpr int GEMM_THREADS = 192;
@@ -267,7 +274,8 @@ __device__ __forceinline__ void epi_prefetch(const GemmEpi &epi, EpiPre &pre, in
 
 template <int MODE, int CW, bool FULL>
 __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPre &pre, const EpiBias &eb, int row0, int M,
-                                                 int n, int N, int lane, uint32_t stage, float *s_stats = nullptr) {
+                                                 int n, int N, int lane, uint32_t stage, float *s_stats = nullptr,
+                                                 float *racc = nullptr) {
     using TR = EpiTraits<MODE>;
     constexpr bool G = MODE == E_GENERIC;
     constexpr int NIT = CW == 4 ? 8 : 4, RPI = 32 / NIT;
@@ -429,7 +437,12 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
         op += ostep;
         pp += pstep;
     }
-    if (MODE == E_STATS) {
+    if (MODE == E_STATS && racc) {
+        // the caller keeps this lane's column sums in registers across tiles (same columns on every tile): no shuffle, no
+        // atomic per chunk -- the epilogue bounds these GEMMs, every instruction per chunk counts
+#pragma unroll
+        for (int j = 0; j < CW; ++j) { racc[j] += st1[j]; racc[8 + j] += st2[j]; }
+    } else if (MODE == E_STATS) {
         // combine the row groups held by different lanes (same columns), then one shared-memory atomic per column and stat
 #pragma unroll
         for (int off = (CW == 4 ? 8 : 4); off < 32; off <<= 1) {
@@ -482,7 +495,7 @@ __device__ __forceinline__ void epilogue_phase_b(const GemmEpi &epi, const EpiPr
 template <int MODE, bool LATE = false>
 __device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_t (&v)[32], EpiPre &pre, const EpiBias &eb,
                                                int row0, int M, int n, int N, int lane, uint32_t stage,
-                                               float *s_stats = nullptr) {
+                                               float *s_stats = nullptr, float *racc = nullptr) {
     using TR = EpiTraits<MODE>;
     if (n >= N || row0 >= M) return;                  // warp-uniform
     __syncwarp();                                     // the previous chunk's phase-B reads of the tile are done
@@ -498,11 +511,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi &epi, const uint32_
     __syncwarp();
     const bool full = row0 + 32 <= M && n + 32 <= N;
     if (TR::wide(epi)) {
-        if (full) epilogue_phase_b<MODE, 8, true>(epi, pre, eb, row0, M, n, N, lane, stage, s_stats);
-        else epilogue_phase_b<MODE, 8, false>(epi, pre, eb, row0, M, n, N, lane, stage, s_stats);
+        if (full) epilogue_phase_b<MODE, 8, true>(epi, pre, eb, row0, M, n, N, lane, stage, s_stats, racc);
+        else epilogue_phase_b<MODE, 8, false>(epi, pre, eb, row0, M, n, N, lane, stage, s_stats, racc);
     } else {
-        if (full) epilogue_phase_b<MODE, 4, true>(epi, pre, eb, row0, M, n, N, lane, stage, s_stats);
-        else epilogue_phase_b<MODE, 4, false>(epi, pre, eb, row0, M, n, N, lane, stage, s_stats);
+        if (full) epilogue_phase_b<MODE, 4, true>(epi, pre, eb, row0, M, n, N, lane, stage, s_stats, racc);
+        else epilogue_phase_b<MODE, 4, false>(epi, pre, eb, row0, M, n, N, lane, stage, s_stats, racc);
     }
 }
 
@@ -906,6 +919,26 @@ __device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t adesc, 
         : "memory");
 }
 
+// Publish a warp's register column statistics (see epilogue_phase_b, racc) into the CTA's shared accumulators and clear
+// them: lanes that share a column group (same cq, different rq) are combined by shuffles, one lane per group adds.
+// c0: first column of the warp's chunk 0; wide: the 8-columns-per-lane layout (bf16 output) or the 4-column one.
+template <int NCH>
+__device__ __forceinline__ void stats_flush(float *racc, float *s_stats, int c0, int N, int lane, bool wide) {
+    const int cw = wide ? 8 : 4;
+    const int rq = wide ? (lane >> 2) : (lane >> 3), cq = wide ? (lane & 3) : (lane & 7);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float v = racc[16 * c + j];
+            for (int off = wide ? 4 : 8; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            racc[16 * c + j] = 0.f;
+            const int jj = j & 7, col = c0 + c * 32 + cq * cw + jj;
+            if (rq == 0 && jj < cw && col < N && v != 0.f) atomicAdd(s_stats + (j >> 3) * 512 + col, v);
+        }
+    }
+}
+
 constexpr int PAIR_EW = 16;                               // epilogue warps per CTA
 constexpr int PAIR_THREADS = (2 + PAIR_EW) * 32;
 constexpr int PAIR_STAGES = 4;
@@ -1003,6 +1036,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) gem
         const uint32_t stage = smem_u32(smem + STAGES * STAGE_BYTES) + e * 4096;
         EpiPre pa;
         uint32_t lt = 0;
+        float racc[MODE == E_STATS ? 16 * NCH : 1];      // per chunk: [8 sums | 8 sums of squares] of this lane's columns
+        int stat_n0 = (pair_id % tiles_n) * PAIR_N;
+        if (MODE == E_STATS) {
+#pragma unroll
+            for (int i = 0; i < 16 * NCH; ++i) racc[i] = 0.f;
+        }
         for (int t = pair_id; t < total_tiles; t += num_pairs, ++lt) {
             const int n0 = (t % tiles_n) * PAIR_N, m0 = (t / tiles_n) * (2 * GEMM_BM) + (int)rank * GEMM_BM;
             const uint32_t buf = lt & 1;
@@ -1012,8 +1051,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) gem
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + buf * PAIR_N + ((uint32_t)(quad * 32) << 16) + (uint32_t)(part * WCOLS);
             const uint32_t lempty = mapa_u32(smem_u32(&tempty_bar[buf]), 0);
-#pragma unroll 1
-            for (int c = 0; c < NCH; ++c) {
+            if (MODE == E_STATS && n0 != stat_n0) {      // column block changed (odd pair count): publish, start over
+                stats_flush<NCH>(racc, s_stats, stat_n0 + part * WCOLS, N, lane, epi.out_fp32 == 0);
+                stat_n0 = n0;
+            }
+            auto do_chunk = [&](int c, float *ra) {
                 EpiBias eb;
                 epi_load_bias<MODE>(epi, eb, row0, M, cbase + c * 32, N, lane);
                 uint32_t v[32];
@@ -1024,9 +1066,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) gem
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(lempty);
                 }
-                epilogue_chunk<MODE, true>(epi, v, pa, eb, row0, M, cbase + c * 32, N, lane, stage, s_stats);
+                epilogue_chunk<MODE, true>(epi, v, pa, eb, row0, M, cbase + c * 32, N, lane, stage, s_stats, ra);
+            };
+            if (MODE == E_STATS) {               // unrolled: the register accumulators are indexed statically
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) do_chunk(c, racc + 16 * c);
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < NCH; ++c) do_chunk(c, nullptr);
             }
         }
+        if (MODE == E_STATS) stats_flush<NCH>(racc, s_stats, stat_n0 + part * WCOLS, N, lane, epi.out_fp32 == 0);
     }
     tc_fence_before();
     cluster_sync_all();                           // nobody leaves (or frees TMEM) while the peer may still touch it
@@ -1074,6 +1124,7 @@ static int launch_gemm_persistent(const CUtensorMap &ta, const CUtensorMap &tb, 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (gemm_sm_cap() > 0 && gemm_sm_cap() < sms) sms = gemm_sm_cap();
     const int grid = (int)(total < sms ? total : sms);
     ACT_CUDA(launch_k(kern, dim3(grid), dim3(PersistCfg<MODE>::THREADS), smem, st, true, ta, tb, epi, M, N, K,
                       kbps, tiles_m, tiles_n, (int)total));
@@ -1098,6 +1149,7 @@ static int launch_gemm_pair(const CUtensorMap &ta, const CUtensorMap &tb, const 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (gemm_sm_cap() > 1 && gemm_sm_cap() < sms) sms = gemm_sm_cap();
     const int pairs = (int)(total < sms / 2 ? total : sms / 2);
     ACT_CUDA(launch_k(kern, dim3(2 * pairs), dim3(PAIR_THREADS), PAIR_SMEM, st, true, ta, tb, epi, M, N, K, tiles_m, tiles_n,
                       (int)total));

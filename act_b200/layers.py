@@ -562,6 +562,13 @@ def layer_norm_rows(x, weight, bias, eps, j0, cnt):
 
 
 # --------------------------------------------------------------------------------- mini-PointNet Encoder
+# BatchNorm2's batch statistics can ride on conv3's GEMM epilogue (ops.gemm(colstats=...): no second pass over the
+# [B*G*k, 512] conv output, 268 MB less DRAM traffic per encoder).  MEASURED NEGATIVE on B200 (round 2): that GEMM is bound
+# by its epilogue, not by HBM -- the fused kernel takes 213 us against 102 us + 62 us for GEMM + separate statistics pass,
+# and the step is 0.05-0.1 ms slower (profiles/r2_fused_bn_stats_ab.txt).  Kept as a tested option, off by default.
+FUSED_BN_STATS = os.environ.get("ACT_B200_FUSED_BN_STATS", "0") == "1"
+
+
 class PointNetEncoderFn(torch.autograd.Function):
     """Encoder.forward (models/dvae.py:201-215) with train-mode BatchNorm1d: four tcgen05 GEMMs + the fused
     elementwise / reduction kernels of csrc/pointnet.cu.  The `cat([global, local])` + conv3 is computed
@@ -601,10 +608,14 @@ class PointNetEncoderFn(torch.autograd.Function):
             gmax, _, arg2 = ops.group_max(f2, k)                                  # [BG,256]
         w3s = shadow(w3).view(512, 512)
         gpart = ops.gemm(gmax, w3s[:, :256], bias=b3, out_dtype=torch.float32)    # [BG,512]
-        if training:     # BatchNorm2's batch statistics ride on conv3's epilogue (fp32 accumulators): h3 is not re-read
+        if training and FUSED_BN_STATS:   # BatchNorm2's batch statistics ride on conv3's epilogue: h3 is not re-read
             stats = torch.empty(2, 512, dtype=torch.float32, device=p.device)
             h3 = ops.gemm(f2, w3s[:, 256:], resid=gpart, resid_row_div=k, colstats=stats)     # [M,512]
             sc2, sh2, mean2, rstd2 = ops.bn_finalize(stats[0], stats[1], M, g2, be2, eps, momentum, rm2, rv2, nbt2)
+        elif training:
+            h3 = ops.gemm(f2, w3s[:, 256:], resid=gpart, resid_row_div=k)         # [M,512]
+            sm, sq = ops.bn_stats(h3)
+            sc2, sh2, mean2, rstd2 = ops.bn_finalize(sm, sq, M, g2, be2, eps, momentum, rm2, rv2, nbt2)
         else:
             h3 = ops.gemm(f2, w3s[:, 256:], resid=gpart, resid_row_div=k)         # [M,512]
             mean2, var2 = rm2.double(), rv2.double()

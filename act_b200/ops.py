@@ -44,6 +44,21 @@ class precision:
         set_precision(self.prev)
 
 
+class gemm_sm_cap:
+    """with ops.gemm_sm_cap(n): many-tile GEMMs ENQUEUED inside occupy at most n SMs (0 = all).  Launch-time host state."""
+
+    def __init__(self, n):
+        self.n = int(n or 0)
+
+    def __enter__(self):
+        if self.n:
+            _lib.check(_lib.lib().act_set_option(3, self.n), "act_set_option")
+
+    def __exit__(self, *a):
+        if self.n:
+            _lib.check(_lib.lib().act_set_option(3, 0), "act_set_option")
+
+
 def _io32(t):
     return int(t.dtype == torch.float32)
 

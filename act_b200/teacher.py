@@ -117,6 +117,8 @@ class ACTPromptedDiscreteVAEwithVIT(nn.Module):
         # from the host): the per-call seed of the in-kernel gumbel / prompt-dropout draws is then read from it instead of
         # being drawn from torch's default CUDA generator, whose state a CONCURRENTLY replaying graph also advances
         self.seed_buffer = None
+        import os
+        self.sm_cap = int(os.environ.get("ACT_B200_TEACHER_SM_CAP", "0"))
 
     # ---- frozen bf16 operand cache (weights never change: built once, dropped on load / device move) ----------
     def _apply(self, fn, *a, **k):
@@ -218,8 +220,10 @@ class ACTPromptedDiscreteVAEwithVIT(nn.Module):
     def forward_tokenizer_features(self, neighborhood, center, return_global=True, gumbel=None, keeps=None):
         """dvae.py:584-592.  gumbel (optional f32 [B,G,num_tokens]) / keeps (optional list of [B,P,D] 0/1 masks)
         inject the two random draws (gumbel noise, prompt dropout) for parity runs; default: drawn here."""
-        with ops.precision("bf16"):      # the frozen teacher always runs the bf16 speed mode (its own parity bounds:
-            return self._features(neighborhood, center, return_global, gumbel, keeps)     # tests/test_gpu_teacher.py)
+        # the frozen teacher always runs the bf16 speed mode (its own parity bounds: tests/test_gpu_teacher.py); sm_cap:
+        # see ops.gemm_sm_cap (0 = its GEMMs may take every SM)
+        with ops.precision("bf16"), ops.gemm_sm_cap(self.sm_cap):
+            return self._features(neighborhood, center, return_global, gumbel, keeps)
 
     def _features(self, neighborhood, center, return_global, gumbel, keeps):
         c = self._prepare()

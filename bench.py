@@ -328,7 +328,11 @@ def bench_stage2(h, shape, teacher, steps, warmup, want_roofline, want_student_o
     eng = PretrainStep(model, fp, B, NP, use_graph=not no_graph, device=dev).capture()
     _log(f"{shape}: captured")
 
+    look = os.environ.get("ACT_BENCH_LOOKAHEAD") == "1" and eng.pipeline     # experiment: software pipelining across steps
+
     def step(i):                                             # batch already resident in HBM
+        if look:
+            return eng.run(resident[i % n_batches], next_points=resident[(i + 1) % n_batches])
         return eng.run(resident[i % n_batches])
 
     def step_e2e(i):
@@ -376,7 +380,7 @@ def bench_stage2(h, shape, teacher, steps, warmup, want_roofline, want_student_o
             evs.append((a, b))
         torch.cuda.synchronize()
         res["tokenizer_us"] = round(1e3 * statistics.median(a.elapsed_time(b) for a, b in evs), 1)
-    if want_roofline and h.rank == 0:
+    if want_roofline and h.rank == 0 and os.environ.get("ACT_BENCH_QUICK") != "1":
         def record():
             eng._host_prologue(resident[0])
             eng._body_a()

@@ -35,6 +35,10 @@ const char *act_error_string(int code);
  * tiles where they win: forward T > 128, backward 32 < T <= 128; warp-MMA kernels for the latency-bound short sequences),
  * 2 = the tcgen05 kernels wherever they are implemented, 0 = never. */
 #define ACT_OPT_ATTN_TC 2
+/* ACT_OPT_GEMM_SM_CAP (default 0 = all): the many-tile (persistent / CTA-pair) GEMMs launched while it is set occupy at
+ * most this many SMs.  Host-side launch-time state: set it around the launches of one branch (the frozen teacher's
+ * forward, enqueued on its own stream) to leave SMs to a concurrent latency-bound branch. */
+#define ACT_OPT_GEMM_SM_CAP 3
 int act_set_option(int key, int value);
 
 /* ---- Group tokenizer ------------------------------------------------------------------------------ */
