@@ -128,12 +128,17 @@ def _chamfer_backward(xyz1, xyz2, idx1, idx2, g1, g2):
 _installed = False
 
 
-def install():
-    """Install the stand-ins and put the reference on sys.path.  Idempotent."""
-    global _installed
+def install(native="oracle", reference_root=None):
+    """Install the stand-ins and put the reference on sys.path.  Idempotent.
+    native = "oracle": knn_cuda / pointnet2_ops / chamfer are backed by the C oracle (CPU);
+    native = "dropin": those three import names are NOT stubbed -- the repo's dropin/ directory is put on sys.path instead,
+    so the unmodified reference runs on the act_b200 kernels (GPU; tests/test_gpu_dropin_reference.py)."""
+    global _installed, REFERENCE_ROOT
     if _installed:
         return
     _installed = True
+    if reference_root:
+        REFERENCE_ROOT = reference_root
     _mod("easydict").EasyDict = _EasyDict
     mmcv = _mod("mmcv")
     mmcv.utils = _mod("mmcv.utils")
@@ -160,13 +165,19 @@ def install():
     lightly = _mod("lightly")
     lightly.loss = _mod("lightly.loss")
     lightly.loss.NegativeCosineSimilarity = _NegCos
-    _mod("knn_cuda").KNN = _KNN
-    p2 = _mod("pointnet2_ops")
-    p2.pointnet2_utils = _mod("pointnet2_ops.pointnet2_utils")
-    p2.pointnet2_utils.furthest_point_sample = _fps
-    p2.pointnet2_utils.gather_operation = _Gather.apply
-    ch = _mod("chamfer")
-    ch.forward, ch.backward = _chamfer_forward, _chamfer_backward
+    if native == "dropin":
+        import os
+        dropin = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dropin")
+        if dropin not in sys.path:
+            sys.path.insert(0, dropin)
+    else:
+        _mod("knn_cuda").KNN = _KNN
+        p2 = _mod("pointnet2_ops")
+        p2.pointnet2_utils = _mod("pointnet2_ops.pointnet2_utils")
+        p2.pointnet2_utils.furthest_point_sample = _fps
+        p2.pointnet2_utils.gather_operation = _Gather.apply
+        ch = _mod("chamfer")
+        ch.forward, ch.backward = _chamfer_forward, _chamfer_backward
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     # act.py:1243 and dvae.py:300 call .cuda() unconditionally; neutralise on a CPU-only box.
