@@ -41,7 +41,100 @@ __global__ void __launch_bounds__(256) scale_translate_kernel(float *__restrict_
     }
 }
 
+// ---- ShapeNet.__getitem__ on the device (/root/reference/datasets/ShapeNet55Dataset.py:45-67): random_sample (keep the
+// `num` points the host-drawn permutation selects) + pc_norm (subtract the centroid, divide by the largest point norm).
+// raw f32 [B, Nraw, 3], sel i32 [B, num] (the first `num` entries of the shuffled permutation, drawn on the host from the
+// reference's numpy stream) -> out f32 [B, num, 3].  One CTA per cloud; the selected points live in registers (<= 8 per
+// thread at 256 threads: num <= 2048 -- larger clouds loop).  HBM: 12*num gathered bytes in, 12*num out per cloud.
+__device__ __forceinline__ float block_reduce_256(float v, float *red, bool is_max) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? fmaxf(v, w) : v + w;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t = is_max ? fmaxf(t, red[w]) : t + red[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(256) subsample_norm_kernel(const float *__restrict__ raw, const int *__restrict__ sel,
+                                                             int Nraw, int num, float *__restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ float red[8];
+    const int b = blockIdx.x;
+    const float *src = raw + (size_t)b * Nraw * 3;
+    const int *idx = sel + (size_t)b * num;
+    float *dst = out + (size_t)b * num * 3;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int i = threadIdx.x; i < num; i += 256) {
+        const int j = __ldg(idx + i);
+        sx += __ldg(src + 3 * j); sy += __ldg(src + 3 * j + 1); sz += __ldg(src + 3 * j + 2);
+    }
+    const float inv = 1.f / (float)num;
+    const float cx = block_reduce_256(sx, red, false) * inv;
+    const float cy = block_reduce_256(sy, red, false) * inv;
+    const float cz = block_reduce_256(sz, red, false) * inv;
+    float m2 = 0.f;
+    for (int i = threadIdx.x; i < num; i += 256) {
+        const int j = __ldg(idx + i);
+        const float x = __ldg(src + 3 * j) - cx, y = __ldg(src + 3 * j + 1) - cy, z = __ldg(src + 3 * j + 2) - cz;
+        m2 = fmaxf(m2, x * x + y * y + z * z);
+    }
+    const float m = sqrtf(block_reduce_256(m2, red, true));
+    for (int i = threadIdx.x; i < num; i += 256) {
+        const int j = __ldg(idx + i);
+        dst[3 * i] = (__ldg(src + 3 * j) - cx) / m;
+        dst[3 * i + 1] = (__ldg(src + 3 * j + 1) - cy) / m;
+        dst[3 * i + 2] = (__ldg(src + 3 * j + 2) - cz) / m;
+    }
+}
+
+// ---- random mask on the device: exactly num_mask of the G groups of every cloud, uniformly at random ---------------------
+// (the same distribution as VisableOnlyMaskTransformer._mask_center_rand, models/act.py:244-267, whose host loop
+// np.random.shuffle's one array per cloud; NOT the same random stream -- the default keeps the host draw for RNG parity).
+// Every group draws a 32-bit Philox key; the num_mask smallest (ties by index) are masked.  One warp per cloud.
+__global__ void __launch_bounds__(256) mask_rand_kernel(const unsigned long long *__restrict__ seed, int B, int G,
+                                                        int num_mask, uint8_t *__restrict__ mask) {
+    pdl_wait();
+    pdl_trigger();
+    extern __shared__ uint32_t s_key[];                       // [8 warps][G]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.x * 8 + warp;
+    if (b >= B) return;
+    uint32_t *key = s_key + warp * G;
+    const unsigned long long s = *seed;
+    for (int g = lane; g < G; g += 32)
+        key[g] = philox4x32_10((uint32_t)b, (uint32_t)g, 0x4d41534bu, 0u, (uint32_t)s, (uint32_t)(s >> 32)).x;
+    __syncwarp();
+    for (int g = lane; g < G; g += 32) {
+        const uint32_t k = key[g];
+        int rank = 0;
+        for (int j = 0; j < G; ++j) rank += (key[j] < k) || (key[j] == k && j < g);
+        mask[(size_t)b * G + g] = rank < num_mask ? 1 : 0;
+    }
+}
+
 }  // namespace act
+
+extern "C" int act_subsample_norm(const float *raw, const int *sel, int B, int Nraw, int num, float *out, void *stream) {
+    using namespace act;
+    if (!raw || !sel || !out || B <= 0 || Nraw <= 0 || num <= 0) return ACT_EINVAL;
+    ACT_CUDA(launch_k(subsample_norm_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, true, raw, sel, Nraw, num, out));
+    return ACT_OK;
+}
+
+extern "C" int act_mask_rand(const unsigned long long *seed, int B, int G, int num_mask, uint8_t *mask, void *stream) {
+    using namespace act;
+    if (!seed || !mask || B <= 0 || G <= 0 || num_mask < 0 || num_mask > G) return ACT_EINVAL;
+    if (G > 4096) return ACT_EUNSUPPORTED;
+    ACT_CUDA(launch_k(mask_rand_kernel, dim3((B + 7) / 8), dim3(256), (size_t)8 * G * sizeof(uint32_t), (cudaStream_t)stream,
+                      true, seed, B, G, num_mask, mask));
+    return ACT_OK;
+}
 
 extern "C" int act_scale_translate(float *pc, const float *scale_translate, int B, int N, void *stream) {
     using namespace act;

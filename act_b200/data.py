@@ -52,3 +52,28 @@ def synthetic_clouds(B, N, seed=20231017):
     scale = 2.0 / 3.0 + (1.5 - 2.0 / 3.0) * torch.rand(B, 1, 3, generator=g)
     trans = -0.2 + 0.4 * torch.rand(B, 1, 3, generator=g)
     return (p * scale + trans).contiguous().float()
+
+
+class ShapeNetOnDevice(object):
+    """ShapeNet.__getitem__ (/root/reference/datasets/ShapeNet55Dataset.py:45-67) for a whole batch on the GPU: the loader
+    workers only read the raw `.npy` clouds (8192 points); the per-item `random_sample` (np.random.shuffle of ONE persistent
+    permutation array, first `npoints` entries kept -- the same numpy stream and the same carried-over array state as the
+    reference) is drawn here on the host into one pinned [B, npoints] index buffer, and the gather + pc_norm (centroid,
+    largest norm) run as one launch (csrc/augment.cu).  Results equal the reference's to fp32 summation order."""
+
+    def __init__(self, n_raw=8192, npoints=1024):
+        self.permutation = np.arange(n_raw)
+        self.npoints = npoints
+
+    def draw(self, bsize):
+        sel = np.empty((bsize, self.npoints), np.int32)
+        for i in range(bsize):
+            np.random.shuffle(self.permutation)
+            sel[i] = self.permutation[:self.npoints]
+        return sel
+
+    def __call__(self, raw):
+        """raw: f32 [B, n_raw, 3] on the device (or pinned host memory) -> f32 [B, npoints, 3] on the device."""
+        dev = raw.device if raw.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        sel = torch.from_numpy(self.draw(raw.shape[0])).pin_memory().to(dev, non_blocking=True)
+        return ops.subsample_norm(raw.to(dev, non_blocking=True), sel)

@@ -75,7 +75,7 @@ class PretrainStep:
     steps, every loss the teacher features of its own batch); call flush() to apply the last pending update (before
     reading parameters, saving a checkpoint, or switching engines)."""
 
-    def __init__(self, model, flat_params, batch, n_points, use_graph=True, device=None, pipeline=None):
+    def __init__(self, model, flat_params, batch, n_points, use_graph=True, device=None, pipeline=None, device_mask=False):
         import os
         self.model, self.fp = model, flat_params
         if pipeline is None:
@@ -95,7 +95,11 @@ class PretrainStep:
         self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
         # per-step 64-bit seeds staged from the host like the mask: [0] DropPath gates, [1] the teacher's gumbel / prompt
         # dropout draws (single-graph mode) -- the captured step then contains no library RNG kernel
-        self._seeds = torch.zeros(2, dtype=torch.int64, device=self.dev)
+        self._seeds = torch.zeros(3, dtype=torch.int64, device=self.dev)
+        # device_mask: draw the random mask inside the captured step (csrc/augment.cu act_mask_rand, seed [2]) instead of the
+        # reference's host loop of B numpy shuffles (act.py:255-264).  Same distribution, not the reference's random stream:
+        # off by default, so that a seeded run masks the same groups as the reference does.
+        self.device_mask = bool(device_mask)
         self.use_graph = use_graph
         self.graph = None
         self.graph_b = None
@@ -107,9 +111,14 @@ class PretrainStep:
     def _body_a(self):
         self.fp.zero_grad()
         with layers.drop_path_seed(self._seeds[:1]):
-            loss = self.model(self.points, mask=self.mask)
+            loss = self.model(self.points, mask=self._mask())
         loss.backward()
         self.loss.copy_(loss.detach())
+
+    def _mask(self):
+        if self.device_mask:
+            return ops.mask_rand(self._seeds[2:], self.B, self.G, int(self.mask_ratio * self.G))
+        return self.mask
 
     def _body_b(self):
         self.fp.step()                              # fused AdamW (+ bf16 shadow refresh); scalars read from device
@@ -131,7 +140,7 @@ class PretrainStep:
     def _body_fwd(self):                             # G2a: student forward (autograd graph kept for G2b)
         self.fp.zero_grad()
         with layers.drop_path_seed(self._seeds[:1]):
-            self._student, self._order, self._nvis = self.model.forward_student(self._nb, self._center, self.mask)
+            self._student, self._order, self._nvis = self.model.forward_student(self._nb, self._center, self._mask())
 
     def _body_bwd(self):                             # G2b: loss against the teacher's features + backward
         loss = self.model.distill_loss(self._student, self._tfeat, self._order, self._nvis)
@@ -140,12 +149,13 @@ class PretrainStep:
         self._student = None
 
     def _host_prologue(self, points, hyper=True):
-        m = mask_center_rand(self.B, self.G, self.mask_ratio, "cpu")
+        m = None if self.device_mask else mask_center_rand(self.B, self.G, self.mask_ratio, "cpu")
         # a FRESH pinned staging tensor per step: the host runs many replays ahead of the GPU, and a reused staging buffer
         # would be overwritten before its asynchronous copy has executed (torch's caching host allocator recycles a
         # pinned block only after the copies recorded on it have completed)
-        self.mask.copy_(m.pin_memory(), non_blocking=True)
-        self._seeds.copy_(torch.randint(0, 2 ** 62, (2,), dtype=torch.int64).pin_memory(), non_blocking=True)
+        if m is not None:
+            self.mask.copy_(m.pin_memory(), non_blocking=True)
+        self._seeds.copy_(torch.randint(0, 2 ** 62, (3,), dtype=torch.int64).pin_memory(), non_blocking=True)
         if hyper:
             self.fp.set_hyper(grad_scale=1.0 / dp.world_size())
         if points is not None and points.data_ptr() != self.points.data_ptr():
@@ -282,7 +292,7 @@ class PretrainStep:
             return self._capture_pipeline()
         tmod = getattr(getattr(self.model, "teacher", None), "__self__", None)
         if tmod is not None and hasattr(tmod, "seed_buffer"):
-            tmod.seed_buffer = self._seeds[1:]               # single graph: the teacher's seed is staged with the mask
+            tmod.seed_buffer = self._seeds[1:2]              # single graph: the teacher's seed is staged with the mask
         l0 = ops.LAUNCHES
         snap = _StateSnapshot(self.model, self.fp, self.dev)
         self._host_prologue(None)

@@ -694,3 +694,22 @@ def scale_translate_(pc, st):
     _lib.call("act_scale_translate", pc, st, pc.shape[0], pc.shape[1])
     _count()
     return pc
+
+
+def subsample_norm(raw, sel):
+    """ShapeNet.__getitem__'s random_sample + pc_norm for a batch: raw f32 [B,Nraw,3], sel i32 [B,num] -> f32 [B,num,3]."""
+    raw = _f32c(raw)
+    B, Nraw, _ = raw.shape
+    num = sel.shape[1]
+    out = torch.empty(B, num, 3, dtype=torch.float32, device=raw.device)
+    _lib.call("act_subsample_norm", raw, sel.to(torch.int32).contiguous(), B, Nraw, num, out)
+    _count()
+    return out
+
+
+def mask_rand(seed, B, G, num_mask):
+    """Device-side random mask: bool [B,G] with exactly num_mask ones per row; seed = device int64 [1]."""
+    mask = torch.empty(B, G, dtype=torch.uint8, device=seed.device)
+    _lib.call("act_mask_rand", seed, B, G, int(num_mask), mask)
+    _count()
+    return mask.view(torch.bool)

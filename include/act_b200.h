@@ -340,6 +340,16 @@ int act_gn_rows_train_bwd(const float *x, const float *stats, const float *gamma
  * draws them;  pc[b,n,c] = fl(fl(pc * scale[b,c]) + translate[b,c])  (bit-identical to the reference's mul then add). */
 int act_scale_translate(float *pc, const float *scale_translate, int B, int N, void *stream);
 
+/* ShapeNet.__getitem__ on the device (/root/reference/datasets/ShapeNet55Dataset.py:45-67): out[b, i, :] =
+ * (raw[b, sel[b,i], :] - centroid) / max_norm over the `num` selected points -- random_sample with the host-drawn
+ * permutation prefix sel i32 [B,num] (the reference's numpy stream is kept) followed by pc_norm.  raw f32 [B,Nraw,3]. */
+int act_subsample_norm(const float *raw, const int *sel, int B, int Nraw, int num, float *out, void *stream);
+
+/* Device-side random mask (the distribution of _mask_center_rand, models/act.py:244-267: exactly num_mask of the G groups
+ * of every cloud, uniformly at random; keys from Philox4x32-10 keyed by the 64-bit *seed in device memory).  mask u8 [B,G].
+ * An option for loops that do not need the reference's numpy stream; the default mask stays the host draw. */
+int act_mask_rand(const unsigned long long *seed, int B, int G, int num_mask, uint8_t *mask, void *stream);
+
 /* ---- Loss and optimizer ------------------------------------------------------------------------------ */
 
 /* Cosine distillation loss of ACT_PointDistillation.forward (/root/reference/models/act.py:1243-1254):

@@ -67,3 +67,40 @@ def test_scale_translate_extra_channels():
     np.random.seed(1)
     got = data.PointcloudScaleAndTranslate()(pc.cuda())
     assert torch.equal(got.cpu(), want)
+
+
+@pytest.mark.gpu
+def test_shapenet_subsample_and_normalise_on_device():
+    """data.ShapeNetOnDevice == ShapeNet.__getitem__ of the reference (random_sample on the carried-over permutation array
+    + pc_norm), item by item, on the same numpy stream."""
+    from act_b200 import data
+    rng = np.random.default_rng(3)
+    raw = (rng.standard_normal((6, 8192, 3)) * np.array([1.0, 0.5, 2.0]) + 0.3).astype(np.float32)
+    np.random.seed(21)
+    perm = np.arange(8192)
+    want = []
+    for i in range(6):                                   # ShapeNet55Dataset.py:45-63 verbatim semantics
+        np.random.shuffle(perm)
+        pc = raw[i][perm[:1024]]
+        pc = pc - np.mean(pc, axis=0)
+        want.append(pc / np.max(np.sqrt(np.sum(pc ** 2, axis=1))))
+    np.random.seed(21)
+    got = data.ShapeNetOnDevice(8192, 1024)(torch.from_numpy(raw).cuda())
+    np.testing.assert_allclose(got.cpu().numpy(), np.stack(want), rtol=2e-5, atol=2e-6)
+    assert abs(got.norm(dim=-1).max(dim=1)[0] - 1).max().item() < 1e-5
+
+
+@pytest.mark.gpu
+def test_device_side_random_mask():
+    from act_b200 import ops
+    seed = torch.tensor([5], dtype=torch.int64, device="cuda")
+    for B, G, nm in [(128, 64, 38), (16, 512, 307), (3, 100, 0), (2, 64, 64)]:
+        m = ops.mask_rand(seed, B, G, nm)
+        assert m.dtype == torch.bool and m.shape == (B, G)
+        assert torch.all(m.sum(1) == nm)
+    a = ops.mask_rand(seed, 4096, 64, 38)
+    assert torch.equal(a, ops.mask_rand(seed, 4096, 64, 38))
+    assert not torch.equal(a, ops.mask_rand(torch.tensor([6], dtype=torch.int64, device="cuda"), 4096, 64, 38))
+    freq = a.float().mean(0)                                    # every group masked with probability 38/64
+    assert (freq - 38 / 64).abs().max().item() < 0.04           # sigma = 0.0077
+    assert not torch.equal(a[0], a[1])
