@@ -403,6 +403,21 @@ __global__ void __launch_bounds__(256) pn_conv1_bwd_kernel(const T *__restrict__
     }
 }
 
+// d[m, c] = (a[m, c] > 0) ? d[m, c] : 0, in place: the gradient through a ReLU whose OUTPUT a was kept.
+template <typename T>
+__global__ void __launch_bounds__(256) relu_mask_kernel(T *__restrict__ d, const T *__restrict__ a, long long n8) {
+    pdl_wait();
+    pdl_trigger();
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n8; i += gridDim.x * 256LL) {
+        float dv[8], av[8];
+        V8<T>::ld_plain(d + i * 8, dv);
+        V8<T>::ld(a + i * 8, av);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dv[j] = av[j] > 0.f ? dv[j] : 0.f;
+        V8<T>::st(d + i * 8, dv);
+    }
+}
+
 // ---- BatchNorm bookkeeping (O(C) work, one CTA): replaces ~25 tiny double-precision PyTorch kernels per step ----
 // BN1: statistics of h1 = W p + b follow from the input moments:  mean_c = W_c . mu + b_c,  var_c = W_c^T Cov W_c.
 // Outputs the folded conv1 (Wf, bf) = gamma * rstd * (W, b - mean) + (0, beta), mean, rstd, and updates the running
@@ -648,5 +663,16 @@ extern "C" int act_pn_conv1_bwd(const void *dz, const float *points, const float
         ACT_CUDA(launch_k(pn_conv1_bwd_kernel<1, T>, dim3(grid), dim3(256), 0, st, true, d, points, W, b, mean, rstd, gamma, s1,
                           s2, M, dW, db));
     });
+    return ACT_OK;
+}
+
+extern "C" int act_relu_mask(void *d, const void *a, long long n, int io_fp32, void *stream) {
+    using namespace act;
+    if (!d || !a || n < 0) return ACT_EINVAL;
+    if (n % 8) return ACT_EUNSUPPORTED;
+    if (n == 0) return ACT_OK;
+    ACT_IO_DISPATCH(io_fp32, ACT_CUDA(launch_k(relu_mask_kernel<T>, dim3(grid_for(n / 8, 256 * 4)), dim3(256), 0,
+                                               (cudaStream_t)stream, true, reinterpret_cast<T *>(d),
+                                               reinterpret_cast<const T *>(a), n / 8)));
     return ACT_OK;
 }

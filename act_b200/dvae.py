@@ -124,15 +124,14 @@ class Decoder(nn.Module):
         z_s = seed @ W0[:, c:c + 2].t()                                                    # [S,512]
         z_p = coarse @ W0[:, c + 2:].t()                                                   # [BG,M,512]
         z = (z_g[:, None, None, :] + z_p[:, :, None, :] + z_s[None, None]).reshape(BG * N, 512)
-        a = F.relu(F.batch_norm(z, bn0.running_mean, bn0.running_var, bn0.weight, bn0.bias, self.training,
-                                bn0.momentum, bn0.eps))
-        if self.training:
-            bn0.num_batches_tracked += 1
-        z = layers.linear(a, c1.weight.squeeze(-1), c1.bias)                               # [BG*N,512]
-        a = F.relu(F.batch_norm(z, bn1.running_mean, bn1.running_var, bn1.weight, bn1.bias, self.training,
-                                bn1.momentum, bn1.eps))
-        if self.training:
-            bn1.num_batches_tracked += 1
+        if self.training:      # BatchNorm1d + ReLU on the mini-PointNet's kernels, bf16 between the layers (layers.BnReluFn)
+            a = layers.bn_relu(z, bn0)
+            z = layers.linear(a, c1.weight.squeeze(-1), c1.bias, out_act=True)             # [BG*N,512]
+            a = layers.bn_relu(z, bn1)
+        else:
+            a = F.relu(F.batch_norm(z, bn0.running_mean, bn0.running_var, bn0.weight, bn0.bias, False, bn0.momentum, bn0.eps))
+            z = layers.linear(a, c1.weight.squeeze(-1), c1.bias)
+            a = F.relu(F.batch_norm(z, bn1.running_mean, bn1.running_var, bn1.weight, bn1.bias, False, bn1.momentum, bn1.eps))
         # 512 -> 3: the output dimension is padded to 8 columns for the tensor-core tile
         W2 = torch.cat([c2.weight.squeeze(-1), c2.weight.new_zeros(5, 512)], dim=0)
         b2 = torch.cat([c2.bias, c2.bias.new_zeros(5)])

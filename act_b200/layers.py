@@ -402,10 +402,14 @@ def layer_norm(x, weight, bias, eps=1e-5):
 
 # ---------------------------------------------------------------------------------------------- Linear
 class LinearFn(torch.autograd.Function):
-    """y = act(x W^T + b), fp32 in / fp32 out, bf16 tensor-core GEMM inside (K, N multiples of 8)."""
+    """y = act(x W^T + b) on the tensor-core GEMM (K, N multiples of 8).  x may be f32 (cast on the way in) or already in the
+    activation dtype (bf16 in the speed mode: no cast pass); out_act=True returns y in the activation dtype instead of f32, so
+    that a chain Linear -> BatchNorm/ReLU -> Linear never widens to f32 between kernels; the input gradient comes back in the
+    dtype the input had.  relu_mask (optional, activation dtype, the OUTPUT of a following ReLU): the incoming gradient is
+    first masked by (relu_mask > 0) -- not used by the layers themselves, see BnReluFn."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, gelu):
+    def forward(ctx, x, weight, bias, gelu, out_act):
         shp = x.shape
         x2 = x.reshape(-1, shp[-1])
         adt = ops.act_dtype()
@@ -415,14 +419,16 @@ class LinearFn(torch.autograd.Function):
             xb = ops.cast_rows(x2)                               # our cast kernel (no library launch in the step)
         else:
             xb = x2.to(adt).contiguous()
+        odt = adt if out_act else torch.float32
         u = None
         if gelu:
             u = torch.empty(xb.shape[0], weight.shape[0], dtype=adt, device=x.device)
-            y = ops.gemm(xb, shadow(weight), bias=bias, act=ops.ACT_GELU, preact_out=u, out_dtype=torch.float32)
+            y = ops.gemm(xb, shadow(weight), bias=bias, act=ops.ACT_GELU, preact_out=u, out_dtype=odt)
         else:
-            y = ops.gemm(xb, shadow(weight), bias=bias, out_dtype=torch.float32)
+            y = ops.gemm(xb, shadow(weight), bias=bias, out_dtype=odt)
         ctx.save_for_backward(xb, weight, bias, u)
         ctx.x_needs = x.requires_grad
+        ctx.x_dtype = x.dtype
         return y.view(*shp[:-1], weight.shape[0])
 
     @staticmethod
@@ -430,27 +436,78 @@ class LinearFn(torch.autograd.Function):
         xb, weight, bias, u = ctx.saved_tensors
         sink = _GradSink()
         N = weight.shape[0]
-        d2 = dy.reshape(-1, N).contiguous().float()
-        if u is not None:      # through the GELU first (needs its own pass: bias grad is of the pre-activation)
-            uu = u.float()
-            cdf = 0.5 * (1 + torch.erf(uu * 0.7071067811865476))
-            d2 = d2 * (cdf + uu * torch.exp(-0.5 * uu * uu) * 0.3989422804014327)
-        if N % 128 == 0 and N <= 1024:
-            g = ops.cast_rows(d2, dbias=sink.get(bias, "b") if bias is not None else None)
-        else:
-            g = d2.to(ops.act_dtype())
+        adt = ops.act_dtype()
+        d2 = dy.reshape(-1, N).contiguous()
+        if u is None and d2.dtype == adt and adt != torch.float32:
+            g = d2                                               # already the GEMM operand: no cast pass
             if bias is not None:
-                ops.colsum(d2, sink.get(bias, "b"))
+                ops.colsum(g, sink.get(bias, "b"))
+        else:
+            d2 = d2.float()
+            if u is not None:      # through the GELU first (needs its own pass: bias grad is of the pre-activation)
+                uu = u.float()
+                cdf = 0.5 * (1 + torch.erf(uu * 0.7071067811865476))
+                d2 = d2 * (cdf + uu * torch.exp(-0.5 * uu * uu) * 0.3989422804014327)
+            if N % 128 == 0 and N <= 1024:
+                g = ops.cast_rows(d2, dbias=sink.get(bias, "b") if bias is not None else None)
+            else:
+                g = d2.to(adt)
+                if bias is not None:
+                    ops.colsum(d2, sink.get(bias, "b"))
         ops.wgrad(g, xb, sink.get(weight, "w"))
         dx = None
         if ctx.x_needs:
-            dx = ops.gemm(g, shadow(weight), b_mn=True, out_dtype=torch.float32).view(*dy.shape[:-1], weight.shape[1])
-        return dx, sink.result("w"), sink.result("b") if bias is not None else None, None
+            dx = ops.gemm(g, shadow(weight), b_mn=True, out_dtype=ctx.x_dtype if ctx.x_dtype == adt else torch.float32)
+            dx = dx.view(*dy.shape[:-1], weight.shape[1])
+        return dx, sink.result("w"), sink.result("b") if bias is not None else None, None, None
 
 
-def linear(x, weight, bias=None, gelu=False):
-    return LinearFn.apply(x, weight, bias, gelu)
+def linear(x, weight, bias=None, gelu=False, out_act=False):
+    return LinearFn.apply(x, weight, bias, gelu, out_act)
 
+
+# ----------------------------------------------------------------------------- BatchNorm1d (train) + ReLU
+class BnReluFn(torch.autograd.Function):
+    """relu(BatchNorm1d(x)) over the rows of x [M, C] (channels last), train mode, on the kernels the mini-PointNet uses
+    (csrc/pointnet.cu: per-channel sum / sum of squares, finalize + running-statistics update, normalise + ReLU; backward:
+    ReLU mask folded into the two-pass BatchNorm backward).  x and the result are in the activation dtype (a following
+    LinearFn consumes the result without a cast).  The FoldingNet decoder's final_conv (models/dvae.py:234-240)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, momentum, eps):
+        M, C = x.shape
+        adt = ops.act_dtype()
+        xa = x if (x.dtype == adt and x.is_contiguous()) else (ops.cast_rows(x.contiguous().float()) if C % 128 == 0 and C <= 1024
+                                                                 else x.to(adt).contiguous())
+        sm, sq = ops.bn_stats(xa)
+        sc, sh, mean, rstd = ops.bn_finalize(sm, sq, M, gamma, beta, eps, momentum, running_mean, running_var, nbt)
+        a = ops.bn_apply(xa, sc, sh, relu=True)
+        ctx.save_for_backward(xa, a, mean, rstd, gamma, beta)
+        ctx.x_dtype = x.dtype
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        xa, a, mean, rstd, gamma, beta = ctx.saved_tensors
+        sink = _GradSink()
+        adt = ops.act_dtype()
+        d = da.contiguous()
+        if d.dtype != adt:
+            d = d.to(adt)
+        dz = ops.relu_mask_(d, a)                                # dz = da * (a > 0), in place on our own temporary
+        dx, dbeta, dgamma = ops.bn_bwd(dz, xa, mean, rstd, gamma)
+        ops.accumulate_(sink.get(gamma, "g"), dgamma)
+        ops.accumulate_(sink.get(beta, "b"), dbeta)
+        if ctx.x_dtype != adt:
+            dx = dx.to(ctx.x_dtype)
+        return dx, sink.result("g"), sink.result("b"), None, None, None, None, None
+
+
+def bn_relu(x, bn, training=True):
+    """x [M, C] -> relu(bn(x)) with bn an nn.BatchNorm1d (train mode: batch statistics + running-stat update)."""
+    if not training:
+        raise NotImplementedError("act_b200 BnReluFn: train-mode BatchNorm only (the Stage-I training step)")
+    return BnReluFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, bn.momentum, bn.eps)
 
 
 # --------------------------------------------------------------------------------------- pos-embed MLP

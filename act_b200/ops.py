@@ -555,6 +555,14 @@ def bn_bwd(dz, x, mean, rstd, gamma):
     return dh, s[0], s[1]
 
 
+def relu_mask_(d, a):
+    """d *= (a > 0), in place; d, a contiguous, same dtype (activation dtype)."""
+    assert d.dtype == a.dtype and d.is_contiguous() and a.is_contiguous() and d.numel() == a.numel()
+    _lib.call("act_relu_mask", d, a, _lib.ctypes.c_int64(d.numel()), _io32(d))
+    _count()
+    return d
+
+
 def pn_conv1_bwd(dz, points, W, b, mean, rstd, gamma, dW, db):
     """Accumulates dW [128,3], db [128]; returns (dbeta, dgamma) of BatchNorm1."""
     M = points.shape[0]

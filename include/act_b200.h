@@ -261,6 +261,9 @@ int act_bn_bwd_stats(const void *dz, const void *x, const float *mean, const flo
 int act_bn_bwd_apply(const void *dz, const void *x, const float *mean, const float *rstd, const float *gamma,
                      const float *sum_dz, const float *sum_dz_xhat, long long M, long long M_dz, int C, void *dh,
                      int io_fp32, void *stream);
+/* d[i] = a[i] > 0 ? d[i] : 0 in place (n elements, n % 8 == 0): the gradient through a ReLU whose output a was kept
+ * (the BatchNorm1d + ReLU pairs of the FoldingNet decoder, models/dvae.py:234-240). */
+int act_relu_mask(void *d, const void *a, long long n, int io_fp32, void *stream);
 /* conv1 + BatchNorm1 backward in two passes over dz [M,128] with x-hat recomputed from the points:
  * s1/s2 [128] = BN1 sums (= dbeta, dgamma; zeroed here); dW[128,3], db[128] ACCUMULATED (atomics). */
 int act_pn_conv1_bwd(const void *dz, const float *points, const float *W, const float *b, const float *mean,
