@@ -942,16 +942,33 @@ __device__ __forceinline__ void stats_flush(float *racc, float *s_stats, int c0,
 constexpr int PAIR_EW = 16;                               // epilogue warps per CTA
 constexpr int PAIR_THREADS = (2 + PAIR_EW) * 32;
 constexpr int PAIR_STAGES = 4;
-constexpr int PAIR_N = 256;                               // tile columns (each CTA loads 128 of them as B rows)
-constexpr size_t PAIR_SMEM = (size_t)PAIR_STAGES * (2 * GEMM_BM * GEMM_BK * 2) + 1024 + (size_t)PAIR_EW * 4096;
+// PN: N of one MMA instruction (each CTA loads PN / 2 of those columns as B rows); NB: MMAs per k-step sharing the A tile.
+// 256 x 256 tiles (PN = 256, NB = 1) are the default.  256 x 384 tiles (PN = 192, NB = 2) serve the narrow-output, long-K
+// GEMMs of the teacher ViT on 8192 token rows (proj / fc2: N = 768): 32 x 2 = 64 tiles = ONE round on 74 pairs where
+// 256 x 256 tiles quantise to two rounds at 65 % occupancy, and 40 KB of operands per CTA and k-block feed 256 x 384 x 64
+// MACs (154 FLOP per L2 byte against 128).  2 x 384 accumulator columns do not fit TMEM: single buffer (one round anyway).
+template <int PN, int NB>
+struct PairCfg {
+    static constexpr int TILE_N = PN * NB;
+    static constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;         // 16 KB: this CTA's A rows of one k-block
+    static constexpr uint32_t B_BYTES = (PN / 2) * GEMM_BK * 2;        // this CTA's B rows of one MMA of one k-block
+    static constexpr uint32_t STAGE_BYTES = A_BYTES + NB * B_BYTES;
+    static constexpr int NBUF = 2 * TILE_N <= 512 ? 2 : 1;
+    static constexpr size_t SMEM = (size_t)PAIR_STAGES * STAGE_BYTES + 1024 + (size_t)PAIR_EW * 4096;
+    static_assert(B_BYTES % 1024 == 0 && TILE_N <= 512 && (TILE_N / (PAIR_EW / 4)) % 32 == 0, "unsupported pair tile");
+};
 
-template <int MODE>
+template <int MODE, int PN = 256, int NB = 1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) gemm_bf16_pair_kernel(
     const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmEpi epi, int M, int N,
     int K, int tiles_m, int tiles_n, int total_tiles) {
+    using CFG = PairCfg<PN, NB>;
     constexpr int STAGES = PAIR_STAGES;
-    constexpr uint32_t HALF_BYTES = GEMM_BM * GEMM_BK * 2;             // 16 KB: this CTA's A rows / B rows of one k-block
-    constexpr uint32_t STAGE_BYTES = 2 * HALF_BYTES;
+    constexpr int PAIR_N = CFG::TILE_N;
+    constexpr int NBUF = CFG::NBUF;
+    constexpr uint32_t HALF_BYTES = CFG::A_BYTES;
+    constexpr uint32_t STAGE_BYTES = CFG::STAGE_BYTES;
+    static_assert(MODE != E_STATS || (PN == 256 && NB == 1), "column statistics: 256 x 256 tiles only");
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_slot;
@@ -992,7 +1009,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) gem
         if (lane == 0) {
             uint32_t it = 0;
             for (int t = pair_id; t < total_tiles; t += num_pairs) {
-                const int n0 = (t % tiles_n) * PAIR_N + (int)rank * (PAIR_N / 2);
+                const int n0 = (t % tiles_n) * PAIR_N + (int)rank * (PN / 2);
                 const int m0 = (t / tiles_n) * (2 * GEMM_BM) + (int)rank * GEMM_BM;
                 for (int i = 0; i < total_kb; ++i, ++it) {
                     const int s = it % STAGES, ph = (it / STAGES) & 1;
@@ -1001,17 +1018,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) gem
                     const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
                     uint8_t *sa = smem + s * STAGE_BYTES, *sb = sa + HALF_BYTES;
                     tma_load_2d_2cta(&tma_a, lbar, sa, i * GEMM_BK, m0);
-                    tma_load_2d_2cta(&tma_b, lbar, sb, i * GEMM_BK, n0);
+#pragma unroll
+                    for (int j = 0; j < NB; ++j)
+                        tma_load_2d_2cta(&tma_b, lbar, sb + j * CFG::B_BYTES, i * GEMM_BK, n0 + j * PN);
                 }
             }
         }
     } else if (warp == 1) {
         if (leader && lane == 0) {
-            constexpr uint32_t idesc = make_idesc(2 * GEMM_BM, PAIR_N, false, false);
+            constexpr uint32_t idesc = make_idesc(2 * GEMM_BM, PN, false, false);
             uint32_t it = 0, lt = 0;
             for (int t = pair_id; t < total_tiles; t += num_pairs, ++lt) {
-                const uint32_t buf = lt & 1;
-                mbar_wait(&tempty_bar[buf], ((lt >> 1) & 1) ^ 1);
+                const uint32_t buf = lt % NBUF;
+                mbar_wait(&tempty_bar[buf], ((lt / NBUF) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + buf * PAIR_N;
                 for (int i = 0; i < total_kb; ++i, ++it) {
@@ -1020,9 +1039,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) gem
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + HALF_BYTES;
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k)
-                        umma_bf16_2cta(tmem_d, make_smem_desc(sa + k * 32, 0, 1024), make_smem_desc(sb + k * 32, 0, 1024), idesc,
-                                       (i | k) != 0);
+                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                        const uint64_t ad = make_smem_desc(sa + k * 32, 0, 1024);
+#pragma unroll
+                        for (int j = 0; j < NB; ++j)
+                            umma_bf16_2cta(tmem_d + j * PN, ad, make_smem_desc(sb + j * CFG::B_BYTES + k * 32, 0, 1024), idesc,
+                                           (i | k) != 0);
+                    }
                     umma_commit_2cta(&empty_bar[s]);
                 }
                 umma_commit_2cta(&tfull_bar[buf]);
@@ -1044,10 +1067,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) gem
         }
         for (int t = pair_id; t < total_tiles; t += num_pairs, ++lt) {
             const int n0 = (t % tiles_n) * PAIR_N, m0 = (t / tiles_n) * (2 * GEMM_BM) + (int)rank * GEMM_BM;
-            const uint32_t buf = lt & 1;
+            const uint32_t buf = lt % NBUF;
             const int row0 = m0 + quad * 32;
             const int cbase = n0 + part * WCOLS;
-            mbar_wait(&tfull_bar[buf], (lt >> 1) & 1);
+            mbar_wait(&tfull_bar[buf], (lt / NBUF) & 1);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + buf * PAIR_N + ((uint32_t)(quad * 32) << 16) + (uint32_t)(part * WCOLS);
             const uint32_t lempty = mapa_u32(smem_u32(&tempty_bar[buf]), 0);
@@ -1131,18 +1154,22 @@ static int launch_gemm_persistent(const CUtensorMap &ta, const CUtensorMap &tb, 
     return ACT_OK;
 }
 
-inline bool pair_enabled() {       // ACT_B200_PAIR=0 keeps every GEMM on the single-CTA kernels (A/B timing)
+// ACT_B200_PAIR=0 keeps every GEMM on the single-CTA kernels, =1 keeps the pair kernel on 256 x 256 tiles only (A/B timing)
+inline int pair_enabled() {
     static const int on = [] {
         const char *e = std::getenv("ACT_B200_PAIR");
-        return (e && e[0] == '0') ? 0 : 1;
+        return (e && e[0] >= '0' && e[0] <= '9') ? (e[0] - '0') : 2;
     }();
-    return on != 0;
+    return on;
 }
 
-template <int MODE>
+template <int MODE, int PN = 256, int NB = 1>
 static int launch_gemm_pair(const CUtensorMap &ta, const CUtensorMap &tb, const GemmEpi &epi, int M, int N, int K,
                             cudaStream_t st) {
-    auto kern = gemm_bf16_pair_kernel<MODE>;
+    auto kern = gemm_bf16_pair_kernel<MODE, PN, NB>;
+    constexpr size_t PAIR_SMEM = PairCfg<PN, NB>::SMEM;
+    constexpr int PAIR_N = PairCfg<PN, NB>::TILE_N;
+    static_assert(PAIR_SMEM <= 227 * 1024, "shared memory budget");
     ACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PAIR_SMEM));
     const int tiles_m = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM), tiles_n = (N + PAIR_N - 1) / PAIR_N;
     const long long total = (long long)tiles_m * tiles_n;
@@ -1237,8 +1264,18 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
     if (pair && (a_mn_major || b_mn_major || gmode || splits != 1 || block_n != 0)) return ACT_EUNSUPPORTED;
     int BN;
     bool wide384 = false;        // 128 x 384 tiles (two 192-wide MMAs sharing A): narrow outputs with a long K, one round
+    bool pair384 = false;        // CTA-pair 256 x 384 tiles: narrow outputs with a long K that fit ONE round of pairs
     if (pair) {
         BN = 128;                // each CTA of the pair loads 128 B rows (tile columns)
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const long long t384 = (long long)((M + 255) / 256) * (N / 384);
+        if ((mode == E_PLAIN || mode == E_RESID) && !epi.slab_bias && N % 384 == 0 && K >= 512 && t384 <= sms / 2 &&
+            2 * t384 > sms / 2 && act::pair_enabled() >= 2) {
+            pair384 = true;
+            BN = 96;             // two 192-wide MMAs per k-step: 96 B rows per CTA and MMA
+        }
     } else if (persistent && block_n == 0 && !a_mn_major && !b_mn_major && !gmode && splits == 1 && N % 384 == 0 && K >= 512 &&
         (long long)((M + 127) / 128) * (N / 384) <= 148 && (long long)((M + 127) / 128) * (N / 384) >= 96) {
         wide384 = true;
@@ -1272,6 +1309,10 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
             return launch_gemm_persistent<BN_, (LAY_ & 2) != 0, (LAY_ & 1) != 0, MODE_>(ta, tb, epi, M, N, K, splits, st); \
         else                                                                                                       \
             return launch_gemm<BN_, (LAY_ & 2) != 0, (LAY_ & 1) != 0, MODE_>(ta, tb, epi, M, N, K, splits, st);       \
+    }
+    if (pair && pair384) {
+        if (mode == E_RESID) return launch_gemm_pair<E_RESID, 192, 2>(ta, tb, epi, M, N, K, st);
+        return launch_gemm_pair<E_PLAIN, 192, 2>(ta, tb, epi, M, N, K, st);
     }
     if (pair) {
         if (mode == E_PLAIN) return launch_gemm_pair<E_PLAIN>(ta, tb, epi, M, N, K, st);

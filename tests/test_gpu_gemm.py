@@ -118,11 +118,15 @@ def test_gemm_persistent_splitk_wgrad():
     torch.manual_seed(5)
     T, N, K = 262144, 384, 512
     dy, x = rnd(T, N, scale=0.05), rnd(T, K)
-    want = dy.float().t() @ x.float()
+    want = (dy.double().t() @ x.double()).float()
+    scale = want.abs().max().item()
     for persistent in (0, 1):
         got = ops.gemm(dy, x, a_mn=True, b_mn=True, out_dtype=torch.float32, splits=ops.wgrad_splits(N, K, T),
                        persistent=persistent)
-        check(got, want, False)
+        # fp32 accumulation of 262144 / splits exact products per accumulator: 2^-24 * sqrt(terms) ~ 2e-5 relative to the
+        # row scale, against an fp64 reference (one CTA per SM since round 2: fewer, longer chains than the 2e-5 of check())
+        err = (got - want).abs().max().item()
+        assert err <= 1e-4 * scale, (err, scale)
 
 
 @pytest.mark.parametrize("persistent", [0, 1])
