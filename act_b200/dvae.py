@@ -12,8 +12,8 @@ What runs where (forward AND backward):
         GEMM per layer -- W.[x_k - x_q ; x_q] = Wa.x_k + (Wb - Wa).x_q, so the [B,2C,G,4] edge tensor is never built --
         with forward, dgrad and wgrad on layers.LinearFn; GroupNorm + LeakyReLU + max-over-k fused into one forward and
         two backward kernels per layer (csrc/dgcnn_train.cu, layers.DgcnnEdgeFn / GroupNormRowsFn)
-    soft gumbel-softmax (dvae.py:346)                       -> ATen softmax; the [BG,8192] x [8192,C] codebook einsum
-                                                               (dvae.py:347) on the tcgen05 GEMM
+    soft gumbel-softmax (dvae.py:346) + KL term (:320-332)  -> csrc/gumbel.cu (layers.GumbelSoftmaxFn / KlUniformFn: one
+        pass per kernel, noise drawn in-kernel); the [BG,8192] x [8192,C] codebook einsum (dvae.py:347) on the tcgen05 GEMM
     FoldingNet Decoder (dvae.py:217-275)                    -> Linear / 1x1-conv layers on the tcgen05 GEMM; the K=5
         (seed, coarse-point) part of final_conv.0 is split off algebraically and its [BG,C] "global" part computed
         once per group instead of once per point; BatchNorm / ReLU are ATen ops
@@ -166,6 +166,10 @@ class DiscreteVAE(nn.Module):
         self.dgcnn_2 = DGCNN(encoder_channel=self.tokens_dims, output_channel=self.decoder_dims)
         self.decoder = Decoder(encoder_channel=self.decoder_dims, num_fine=self.group_size)
         self.build_loss_func()
+        # in-kernel gumbel noise: a device int64 [1] the engine refreshes before every step (AutoencoderStep stages it next
+        # to the schedules); None = one torch.randint draw on the device per forward
+        self.gumbel_seed = None
+        self._draws = 0
 
     def build_loss_func(self):
         self.loss_func_cdl1 = ChamferDistanceL1()
@@ -183,6 +187,9 @@ class DiscreteVAE(nn.Module):
     def get_loss(self, ret, gt):
         """dvae.py:320-332: (reconstruction, KL(mean softmax || uniform))."""
         loss_recon = self.recon_loss(ret, gt)
+        qbar = getattr(ret[-1], "_act_qbar", None)
+        if qbar is not None:                  # mean softmax already formed by the fused forward (layers.GumbelSoftmaxFn)
+            return loss_recon, layers.KlUniformFn.apply(qbar)
         log_qy = torch.log(F.softmax(ret[-1], dim=-1).mean(dim=1))
         log_uniform = torch.full_like(log_qy, math.log(1. / self.num_tokens))
         loss_klv = F.kl_div(log_qy, log_uniform, None, None, 'batchmean', log_target=True)
@@ -193,9 +200,25 @@ class DiscreteVAE(nn.Module):
         _, idx4, _ = ops.knn(center, center, 4, want_dist=False)                           # [B,G,4] i64, no grad
         tokens = self.encoder(neighborhood).reshape(B * G, -1)
         logits = dgcnn_forward(self.dgcnn_1, tokens, idx4, B, G)                           # [B,G,num_tokens]
-        soft_one_hot = gumbel_softmax(logits, temperature, hard, gumbel)
+        if self.training and not hard and self.num_tokens in ops.GUMBEL_V and logits.dtype == torch.float32:
+            # fused soft gumbel-softmax (+ the mean softmax get_loss needs): csrc/gumbel.cu
+            noise = None if gumbel is None else gumbel.reshape(B * G, -1).float().contiguous()
+            seed = None
+            if noise is None:
+                seed = self.gumbel_seed if self.gumbel_seed is not None else torch.randint(
+                    0, 2 ** 62, (1,), dtype=torch.int64, device=logits.device)
+                self._draws += 1
+            tau = temperature.reshape(1) if isinstance(temperature, torch.Tensor) else float(temperature)
+            soft_one_hot, qbar = layers.GumbelSoftmaxFn.apply(logits.view(B * G, -1), tau, noise, seed,
+                                                              self._draws & 0x7fffffff, B, G)
+            logits._act_qbar = qbar          # get_loss(ret, gt) receives this very tensor object as ret[-1]
+        else:
+            soft_one_hot = gumbel_softmax(logits, temperature, hard, gumbel)
         # einsum('b g n, n c -> b g c') == Linear with weight codebook^T
-        sampled = layers.linear(soft_one_hot.view(B * G, -1), self.codebook.t().contiguous())
+        if soft_one_hot.dtype == ops.act_dtype() and self.tokens_dims % 8 == 0:
+            sampled = layers.CodebookFn.apply(soft_one_hot.view(B * G, -1), self.codebook)
+        else:
+            sampled = layers.linear(soft_one_hot.view(B * G, -1), self.codebook.t().contiguous())
         feature = dgcnn_forward(self.dgcnn_2, sampled, idx4, B, G)
         return logits, feature
 

@@ -352,6 +352,11 @@ class AutoencoderStep:
         self.points = torch.zeros(batch, n_points, 3, dtype=torch.float32, device=self.dev)
         self.sched = torch.ones(2, dtype=torch.float32, device=self.dev)          # [temperature, kld_weight]
         self.losses = torch.zeros(3, dtype=torch.float32, device=self.dev)         # [recon, klv, total]
+        # seed of the in-kernel gumbel noise (csrc/gumbel.cu), drawn on the host from torch's CPU generator every step
+        self._seed = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        core = getattr(model, "module", model)
+        if hasattr(core, "gumbel_seed"):
+            core.gumbel_seed = self._seed
         self.temp_cfg = temp_cfg or dict(start=1.0, target=0.0625, ntime=100000)   # pointbert_dvae.yaml:27-30
         self.kld_cfg = kld_cfg or dict(start=0.0, target=0.1, ntime=100000)        # pointbert_dvae.yaml:33-36
         self.use_graph = use_graph
@@ -379,6 +384,7 @@ class AutoencoderStep:
         sched = torch.tensor([self._dvae.get_temp(self.n_itr, **self.temp_cfg),
                               self._dvae.get_kld_weight(self.n_itr, **self.kld_cfg)], dtype=torch.float32)
         self.sched.copy_(sched.pin_memory(), non_blocking=True)      # fresh pinned staging per step (see PretrainStep)
+        self._seed.copy_(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).pin_memory(), non_blocking=True)
         self.fp.set_hyper(grad_scale=1.0 / dp.world_size())
         if points is not None and points.data_ptr() != self.points.data_ptr():
             self.points.copy_(points, non_blocking=True)

@@ -510,6 +510,71 @@ def bn_relu(x, bn, training=True):
     return BnReluFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, bn.momentum, bn.eps)
 
 
+# ------------------------------------------------------------ Stage-I soft gumbel-softmax + KL(mean softmax || uniform)
+class GumbelSoftmaxFn(torch.autograd.Function):
+    """(y, qbar) = (softmax((logits + gumbel) / tau), mean over each cloud's G rows of softmax(logits)) for logits f32
+    [B*G, V] -- F.gumbel_softmax(logits, tau, hard=False) of DiscreteVAE.forward (models/dvae.py:346) and the mean softmax
+    get_loss needs (dvae.py:326), from ONE read of the logits per kernel (csrc/gumbel.cu).  y is in the activation dtype (the
+    codebook GEMM's A operand, no cast pass).  The backward takes both upstream gradients (dy from the reconstruction path,
+    dqbar from the KL term) and applies both softmax Jacobians in one pass.  tau: float or 1-element device tensor (no
+    gradient).  noise: f32 [B*G, V] gumbel noise (parity runs) or None = drawn in-kernel from `seed` (device int64 [1])."""
+
+    @staticmethod
+    def forward(ctx, logits, tau, noise, seed, draw_id, B, G):
+        logits = logits.contiguous()
+        y, lse = ops.gumbel_softmax_fwd(logits, tau, noise, seed, draw_id)
+        qbar = ops.softmax_colmean(logits, lse, B, G)
+        ctx.save_for_backward(logits, lse, y)
+        ctx.tau, ctx.G = tau, G
+        ctx.set_materialize_grads(False)
+        return y, qbar
+
+    @staticmethod
+    def backward(ctx, dy, dqbar):
+        logits, lse, y = ctx.saved_tensors
+        if dy is None and dqbar is None:
+            return (None,) * 7
+        dl = ops.gumbel_softmax_bwd(logits, lse, y, dy, ctx.tau, None if dqbar is None else dqbar.contiguous().float(), ctx.G)
+        return dl, None, None, None, None, None, None
+
+
+class KlUniformFn(torch.autograd.Function):
+    """F.kl_div(log(qbar), log(1/V), reduction='batchmean', log_target=True) for qbar f32 [B, V] (dvae.py:327-331)."""
+
+    @staticmethod
+    def forward(ctx, qbar):
+        qbar = qbar.contiguous()
+        ctx.save_for_backward(qbar)
+        return ops.kl_uniform_fwd(qbar)
+
+    @staticmethod
+    def backward(ctx, gout):
+        qbar, = ctx.saved_tensors
+        return ops.kl_uniform_bwd(qbar, gout.reshape(1))
+
+
+class CodebookFn(torch.autograd.Function):
+    """sampled = einsum('b g n, n c -> b g c', soft_one_hot, codebook) (dvae.py:347) for y [R, V] (activation dtype) and
+    codebook f32 [V, C], reading the codebook where it lies: forward = GEMM with an MN-major B operand, dgrad = the plain
+    K-major GEMM, wgrad = y^T . dout straight into the codebook's gradient -- no transposed or re-cast copies."""
+
+    @staticmethod
+    def forward(ctx, y, codebook):
+        ctx.save_for_backward(y, codebook)
+        return ops.gemm(y, shadow(codebook), b_mn=True, out_dtype=torch.float32)
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, codebook = ctx.saved_tensors
+        sink = _GradSink()
+        C = codebook.shape[1]
+        d2 = dout.contiguous().float()
+        g = ops.cast_rows(d2) if (C % 128 == 0 and C <= 1024) else d2.to(ops.act_dtype())
+        ops.wgrad(y, g, sink.get(codebook, "w"))
+        dy = ops.gemm(g, shadow(codebook), out_dtype=y.dtype) if ctx.needs_input_grad[0] else None
+        return dy, sink.result("w")
+
+
 # --------------------------------------------------------------------------------------- pos-embed MLP
 class PosMlpFn(torch.autograd.Function):
     """nn.Sequential(Linear(3,128), GELU, Linear(128,C)) on group centres (act.py:173-177, 1166-1170): the K = 3 layer +

@@ -9,8 +9,9 @@ import os as _os
 
 # Precision of the dense path.  "bf16" (default, the speed mode): GEMM operands and stored activations are bf16, fp32
 # accumulation.  "fp32x3" (the PARITY mode, north_star's 1e-3 bar): activations are stored in f32 and every GEMM operand
-# is split into bf16 (hi, mid) pieces so that the same tcgen05 kernel computes a_hi b_hi + a_hi b_mid + a_mid b_hi over a
-# tripled K (csrc/parity.cu) -- ~16 mantissa bits per product, fp32 accumulation; attention runs in f32 on the FMA pipes.
+# is split into bf16 (hi, mid, lo) pieces so that the same tcgen05 kernel computes hi hi + hi mid + mid hi (+ mid mid +
+# hi lo + lo hi, PARITY_TERMS = 6, the default) over a 3- / 6-fold K (csrc/parity.cu) -- ~16 / ~24 mantissa bits per
+# product, fp32 accumulation; attention runs in f32 on the FMA pipes.
 _ACT_DTYPE = torch.float32 if _os.environ.get("ACT_B200_PRECISION", "bf16") == "fp32x3" else torch.bfloat16
 
 
@@ -201,13 +202,19 @@ def _p(t):
     return _vp(t.data_ptr()) if t is not None else None
 
 
-def split3(x, mn_major, role_b):
-    """f32 2-D operand (last dim contiguous) -> its three-piece bf16 form for the parity-mode GEMM (csrc/parity.cu)."""
+# product terms of the parity-mode GEMM: 6 (hh + hm + mh + mm + hl + lh: ~24 mantissa bits, fp32 grade; default) or 3
+# (the first three: ~16 bits, half the work)
+PARITY_TERMS = int(_os.environ.get("ACT_B200_PARITY_TERMS", "6"))
+
+
+def split3(x, mn_major, role_b, pieces=None):
+    """f32 2-D operand (last dim contiguous) -> its multi-piece bf16 form for the parity-mode GEMM (csrc/parity.cu)."""
     assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    P = pieces or PARITY_TERMS
     R, Cc = x.shape
-    out = torch.empty((3 * R, Cc) if mn_major else (R, 3 * Cc), dtype=torch.bfloat16, device=x.device)
-    _lib.call("act_split3_bf16", _p(x), _lib.ctypes.c_int64(R), Cc, _lib.ctypes.c_int64(x.stride(0)), int(mn_major),
-              int(role_b), out)
+    out = torch.empty((P * R, Cc) if mn_major else (R, P * Cc), dtype=torch.bfloat16, device=x.device)
+    _lib.call("act_split_bf16", _p(x), _lib.ctypes.c_int64(R), Cc, _lib.ctypes.c_int64(x.stride(0)), int(mn_major),
+              int(role_b), P, out)
     _count()
     return out
 
@@ -229,7 +236,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=None, a
     if a.dtype == torch.float32 or b.dtype == torch.float32:
         a = split3(a.float() if a.dtype != torch.float32 else a, a_mn, 0)
         b = split3(b.float() if b.dtype != torch.float32 else b, b_mn, 1)
-        K = 3 * K
+        K = PARITY_TERMS * K
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     if out_dtype is None:
         out_dtype = act_dtype()
@@ -696,6 +703,76 @@ def gn_rows_train_bwd(x, stats, gamma, beta, dy, B, R, slope, dgamma, dbeta):
               dgamma, dbeta)
     _count(2)
     return dx
+
+
+# ------------------------------------------------------------ Stage-I gumbel-softmax + KL (csrc/gumbel.cu)
+GUMBEL_V = (1024, 2048, 4096, 8192, 16384)
+
+
+def _tau_args(tau):
+    """tau: python float, or a 0-dim / 1-element f32 device tensor (the engine's staged schedule) -> (ptr, value)."""
+    if isinstance(tau, torch.Tensor):
+        assert tau.is_cuda and tau.dtype == torch.float32 and tau.numel() == 1
+        return tau, 0.0
+    return None, float(tau)
+
+
+def gumbel_softmax_fwd(logits, tau, noise=None, seed=None, draw_id=0):
+    """logits f32 [R,V] -> (y [R,V] in the activation dtype = softmax((logits + gumbel) / tau), lse f32 [R])."""
+    R, V = logits.shape
+    y = torch.empty(R, V, dtype=act_dtype(), device=logits.device)
+    lse = torch.empty(R, dtype=torch.float32, device=logits.device)
+    tp, tv = _tau_args(tau)
+    _lib.call("act_gumbel_softmax_fwd", logits, noise, seed, int(draw_id), tp, tv, R, V, int(y.dtype == torch.bfloat16),
+              _p(y), lse)
+    _count()
+    return y, lse
+
+
+def softmax_colmean(logits, lse, B, G):
+    V = logits.shape[1]
+    qbar = torch.empty(B, V, dtype=torch.float32, device=logits.device)
+    _lib.call("act_softmax_colmean", logits, lse, B, G, V, qbar)
+    _count()
+    return qbar
+
+
+_KL_SCRATCH = {}
+
+
+def kl_uniform_fwd(qbar):
+    B, V = qbar.shape
+    key = (str(qbar.device), B)
+    sc = _KL_SCRATCH.get(key)
+    if sc is None:       # first use happens in the engine's eager warm-up, outside any capture
+        sc = (torch.empty(B, dtype=torch.float32, device=qbar.device), torch.zeros(1, dtype=torch.int32, device=qbar.device))
+        _KL_SCRATCH[key] = sc
+    loss = torch.empty((), dtype=torch.float32, device=qbar.device)
+    _lib.call("act_kl_uniform_fwd", qbar, B, V, sc[0], sc[1], loss)
+    _count()
+    return loss
+
+
+def kl_uniform_bwd(qbar, gout):
+    B, V = qbar.shape
+    dq = torch.empty_like(qbar)
+    _lib.call("act_kl_uniform_bwd", qbar, _f32c(gout), B, V, dq)
+    _count()
+    return dq
+
+
+def gumbel_softmax_bwd(logits, lse, y, dy, tau, dqbar, G):
+    R, V = logits.shape
+    dl = torch.empty_like(logits)
+    tp, tv = _tau_args(tau)
+    if dy is not None:
+        dy = dy.contiguous()
+        if dy.dtype != y.dtype:
+            dy = dy.to(y.dtype)
+    _lib.call("act_gumbel_softmax_bwd", logits, lse, _p(y) if dy is not None else None, _p(dy) if dy is not None else None,
+              int(y.dtype == torch.bfloat16), tp, tv if dy is not None else 1.0, dqbar, R, G, V, dl)
+    _count()
+    return dl
 
 
 # ------------------------------------------------------------------------------------- input augmentation

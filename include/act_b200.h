@@ -128,6 +128,10 @@ int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, int a_mn_ma
  * mn_major = 0: x is a K-major operand [MN, K] -> out bf16 [R, 3*Cc] (pieces side by side along K);
  * mn_major = 1: x is an MN-major operand [K, MN] -> out bf16 [3*R, Cc] (pieces stacked along K).   Cc % 8 == 0. */
 int act_split3_bf16(const float *x, long long R, int Cc, long long ld, int mn_major, int role_b, void *out, void *stream);
+/* The same with `pieces` = 3 (above) or 6: adds the products mid*mid + hi*lo + lo*hi (lo = bf16(x - hi - mid)), A role
+ * (hi hi mid mid hi lo), B role (hi mid hi mid lo hi) -- an fp32-grade (~24-bit) product over a six-fold K. */
+int act_split_bf16(const float *x, long long R, int Cc, long long ld, int mn_major, int role_b, int pieces, void *out,
+                   void *stream);
 
 /* ---- Transformer Block pieces (models/act.py:45-90, 109-112) ------------------------------------------ */
 
@@ -335,6 +339,31 @@ int act_gn_rows_train_fwd(const float *x, const float *gamma, const float *beta,
 int act_gn_rows_train_bwd(const float *x, const float *stats, const float *gamma, const float *beta, const float *dy,
                           int B, int R, int C, int groups, float slope, float *sums, float *dx, float *dgamma,
                           float *dbeta, void *stream);
+
+/* Soft gumbel-softmax over the codebook + KL(mean softmax || uniform), /root/reference/models/dvae.py:343-347 (forward:
+ * F.gumbel_softmax(logits, tau, dim=2, hard=False)) and :320-332 (get_loss: softmax -> mean over the groups -> log ->
+ * F.kl_div(., log uniform, 'batchmean', log_target=True)); the reference spends ~12 element-wise passes over
+ * logits [B*G, V] on these in each direction.  V in {1024, 2048, 4096, 8192, 16384}.
+ *
+ * act_gumbel_softmax_fwd: y[r,:] = softmax((logits[r,:] + g[r,:]) / tau) (bf16 if out_bf16 else f32) and
+ *   lse[r] = logsumexp(logits[r,:]).  g = noise f32 [R,V] when given, else drawn in-kernel (Philox keyed by *seed (device)
+ *   and draw_id; -log(-log(u))).  tau = *tau_ptr (device) when tau_ptr != NULL, else tau_val.
+ * act_softmax_colmean: qbar[b,v] = mean_g softmax(logits[b,g,:])[v] from logits and lse (deterministic, no atomics).
+ * act_kl_uniform_fwd: *loss = (1/B) sum_{b,v} (1/V)(log(1/V) - log qbar[b,v]); partial f32 [B] and counter u32 [1] (zero
+ *   before the first call; the kernel re-zeroes it) are scratch; the B partial sums are added in index order.
+ * act_kl_uniform_bwd: dqbar = *gout * d loss / d qbar.
+ * act_gumbel_softmax_bwd: dlogits[r,:] (overwritten) = y * (dy - <y,dy>) / tau  [when dy != NULL]
+ *                                                    + p * (c - <p,c>), p = softmax(logits[r,:]), c = dqbar[r / G,:] / G
+ *                                                      [when dqbar != NULL];  y / dy bf16 if act_bf16 else f32. */
+int act_gumbel_softmax_fwd(const float *logits, const float *noise, const unsigned long long *seed, int draw_id,
+                           const float *tau_ptr, float tau_val, int R, int V, int out_bf16, void *y, float *lse,
+                           void *stream);
+int act_softmax_colmean(const float *logits, const float *lse, int B, int G, int V, float *qbar, void *stream);
+int act_kl_uniform_fwd(const float *qbar, int B, int V, float *partial, unsigned int *counter, float *loss, void *stream);
+int act_kl_uniform_bwd(const float *qbar, const float *gout, int B, int V, float *dqbar, void *stream);
+int act_gumbel_softmax_bwd(const float *logits, const float *lse, const void *y, const void *dy, int act_bf16,
+                           const float *tau_ptr, float tau_val, const float *dqbar, int R, int G, int V, float *dlogits,
+                           void *stream);
 
 /* ---- Input augmentation -------------------------------------------------------------- */
 

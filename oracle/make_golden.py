@@ -281,6 +281,59 @@ def gen_dvae_step():
     print("dvae_step.npz recon", l1.item(), "klv", l2.item(), "n grads", len(names))
 
 
+def dvae_smooth_weights(coarse_shape, fine_shape, seed=43):
+    """Fixed weights of the smooth surrogate loss sum(coarse * Rc) + sum(fine * Rf) (shared with the GPU test)."""
+    rng = np.random.default_rng(seed)
+    rc = torch.from_numpy(rng.standard_normal(coarse_shape).astype(np.float32)) / float(np.prod(coarse_shape[:-1]))
+    rf = torch.from_numpy(rng.standard_normal(fine_shape).astype(np.float32)) / float(np.prod(fine_shape[:-1]))
+    return rc, rf
+
+
+def gen_dvae_step_smooth():
+    """The same Stage-I forward as gen_dvae_step, differentiated through a SMOOTH loss (a fixed random linear functional of
+    the coarse and fine reconstructions + kld_weight * KL) instead of Chamfer-L1.  Chamfer-L1's gradient is a sum of unit
+    vectors towards arg-min partners: piecewise constant in the forward values, so two fp32-grade forwards that differ in
+    the last bits re-assign a few partners and the parameter gradients move by a few per cent whatever the backward
+    arithmetic does.  This fixture isolates the backward arithmetic of the whole step from that discontinuity."""
+    import models.dvae as dvae
+    from .ref_dvae import gumbel_softmax_with_noise
+    pts = synthetic_clouds(2, 1024, seed=23)
+    cfg = shims.easydict(dict(NAME="DiscreteVAE", group_size=32, num_group=64, num_tokens=8192, encoder_dims=256,
+                              tokens_dims=256, decoder_dims=256))
+    model = dvae.DiscreteVAE(cfg)
+    fill_params(model, seed=8)
+    model.train()
+    gumbel = dvae_noise(2, 64, 8192)
+    orig = dvae.F.gumbel_softmax
+    dvae.F.gumbel_softmax = lambda logits, tau=1.0, hard=False, dim=-1: gumbel_softmax_with_noise(logits, gumbel, tau, hard)
+    try:
+        ret = model(pts, temperature=1.0, hard=False)
+        whole_coarse, whole_fine, coarse, fine, nb, logits = ret
+        _, loss_klv = model.get_loss(ret, pts)
+        rc, rf = dvae_smooth_weights(tuple(coarse.shape), tuple(fine.shape))
+        loss = (coarse * rc).sum() + (fine * rf).sum() + DVAE_KLD_WEIGHT * loss_klv
+        loss.backward()
+    finally:
+        dvae.F.gumbel_softmax = orig
+    keep_full = ("decoder.mlp.4.bias", "decoder.final_conv.6.weight", "decoder.final_conv.0.weight",
+                 "dgcnn_2.layer5.1.weight", "dgcnn_2.input_trans.bias", "dgcnn_1.layer1.1.bias",
+                 "encoder.second_conv.3.bias", "encoder.first_conv.0.weight")
+    res = {"loss": np.float32(loss.item())}
+    names, norms = [], []
+    for k, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        names.append(k)
+        norms.append(p.grad.norm().item())
+        if k in keep_full:
+            res["grad/" + k] = p.grad.numpy()
+    res["grad/codebook_rows"] = model.codebook.grad[::512].numpy()
+    res["grad_names"] = np.array(names)
+    res["grad_norms"] = np.array(norms, np.float64)
+    np.savez_compressed(os.path.join(GOLD, "dvae_step_smooth.npz"), **res)
+    print("dvae_step_smooth.npz loss", loss.item(), "n grads", len(names))
+
+
 def gen_point_transformer():
     """the unmodified reference PointTransformer (act.py:727-910), transfer_type 'full' (mlp-3 head) and
     'side': eval logits, and one train-mode forward/backward with cross-entropy (head dropout p set to 0 so that the run
@@ -333,13 +386,11 @@ def main():
     shims.install()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
-    gen_group()
-    gen_block_cfg1()
-    gen_encoder()
-    gen_student_step()
-    gen_teacher()
-    gen_dvae_step()
-    gen_point_transformer()
+    gens = {"group": gen_group, "block_cfg1": gen_block_cfg1, "encoder": gen_encoder, "student_step": gen_student_step,
+            "teacher": gen_teacher, "dvae_step": gen_dvae_step, "dvae_step_smooth": gen_dvae_step_smooth,
+            "point_transformer": gen_point_transformer}
+    for name in (sys.argv[1:] or list(gens)):      # `python -m oracle.make_golden [fixture ...]`: all by default
+        gens[name]()
 
 
 if __name__ == "__main__":

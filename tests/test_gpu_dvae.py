@@ -243,3 +243,68 @@ def test_autoencoder_step_graph_trains():
     assert h[-3:, 0].mean() < 0.9 * h[:3, 0].mean(), h[:, 0]
     assert step.n_itr == 12 and abs(step.sched[0].item() - dvae.get_temp(11)) < 1e-6 and step.sched[1].item() == 0.0
     assert step.launches_per_step > 100                       # the act_b200 kernels are what runs
+
+
+@pytest.mark.parametrize("mode,V", [("bf16", 8192), ("fp32x3", 8192), ("bf16", 1024)])
+def test_gumbel_softmax_kl_kernels_fwd_bwd(mode, V):
+    """csrc/gumbel.cu against torch autograd on the same f32 logits and injected gumbel noise: F.gumbel_softmax's soft
+    sample (dvae.py:346), get_loss's KL(mean softmax || uniform) (dvae.py:320-332) and the gradient of a loss that uses
+    both.  f32 outputs to 1e-5; the bf16 activation-dtype sample to its rounding (2^-8 relative per element)."""
+    import torch.nn.functional as F
+    from act_b200 import layers, ops
+    torch.manual_seed(3)
+    B, G, tau = 3, 64, 0.7
+    logits = (torch.randn(B * G, V, device="cuda") * 2.0).requires_grad_(True)
+    noise = torch.from_numpy(np.random.default_rng(5).gumbel(size=(B * G, V)).astype(np.float32)).cuda()
+    w = torch.randn(B * G, V, device="cuda")
+    tau_dev = torch.tensor([tau], device="cuda")
+    with ops.precision(mode):
+        y, qbar = layers.GumbelSoftmaxFn.apply(logits, tau_dev, noise, None, 0, B, G)
+        kl = layers.KlUniformFn.apply(qbar)
+        ((y.float() * w).sum() + 0.3 * kl).backward()
+    got = logits.grad.clone()
+    logits.grad = None
+    y_ref = ((logits + noise) / tau).softmax(-1)
+    q_ref = F.softmax(logits, dim=-1).view(B, G, V).mean(1)
+    log_qy = torch.log(q_ref)
+    kl_ref = F.kl_div(log_qy, torch.full_like(log_qy, float(np.log(1.0 / V))), None, None, "batchmean", log_target=True)
+    ((y_ref * w).sum() + 0.3 * kl_ref).backward()
+    assert y.dtype == (torch.bfloat16 if mode == "bf16" else torch.float32)
+    assert rel(qbar, q_ref) < 1e-5 and abs(kl.item() - kl_ref.item()) <= 1e-5 * abs(kl_ref.item()) + 1e-7
+    if mode == "bf16":
+        assert ((y.float() - y_ref).abs() <= 2 ** -8 * y_ref + 1e-12).all()
+    else:
+        assert rel(y, y_ref) < 1e-5
+    assert rel(got, logits.grad) < (2e-5 if mode != "bf16" else 8e-3), rel(got, logits.grad)
+    # each upstream gradient alone (the other one absent): dy only, dqbar only
+    with ops.precision(mode):
+        y2, q2 = layers.GumbelSoftmaxFn.apply(logits, tau, noise, None, 0, B, G)
+        logits.grad = None
+        layers.KlUniformFn.apply(q2).backward()
+    g_kl = logits.grad.clone()
+    logits.grad = None
+    kl_ref2 = F.kl_div(torch.log(F.softmax(logits, dim=-1).view(B, G, V).mean(1)),
+                       torch.full((B, V), float(np.log(1.0 / V)), device="cuda"), None, None, "batchmean", log_target=True)
+    kl_ref2.backward()
+    assert rel(g_kl, logits.grad) < 2e-5, rel(g_kl, logits.grad)
+
+
+def test_gumbel_softmax_in_kernel_noise_is_gumbel():
+    """Gumbel-max property of the in-kernel Philox noise: argmax(logits + g) ~ Categorical(softmax(logits)); different
+    seeds / draw ids give different samples, the same seed the same sample."""
+    from act_b200 import ops
+    V, R = 1024, 32768
+    base = torch.linspace(-2.0, 2.0, 16, device="cuda")
+    logits = (base.repeat_interleave(V // 16) - 20.0)
+    logits[::64] += 20.0                                   # 16 dominant classes with graded probabilities
+    L = logits[None].expand(R, V).contiguous()
+    seed = torch.tensor([1234567], dtype=torch.int64, device="cuda")
+    y, _ = ops.gumbel_softmax_fwd(L, 1.0, None, seed, 1)
+    y_again, _ = ops.gumbel_softmax_fwd(L, 1.0, None, seed, 1)
+    y_other, _ = ops.gumbel_softmax_fwd(L, 1.0, None, seed, 2)
+    assert torch.equal(y, y_again) and not torch.equal(y, y_other)
+    emp = torch.bincount(y.float().argmax(-1), minlength=V).float() / R
+    p = logits.softmax(-1)
+    top = p > 1e-3
+    assert (emp[top] - p[top]).abs().max().item() < 4 * (p.max() * (1 - p.max()) / R).sqrt().item() + 2e-3
+    assert abs(emp[~top].sum().item() - p[~top].sum().item()) < 5e-3

@@ -193,20 +193,28 @@ def test_report_errors_of_both_modes(golden):
     assert report["fp32x3"]["student_step_grad_rel_max"] < GRAD and report["fp32x3"]["encoder_feature_rel"] < FEAT
 
 
-def test_dvae_step_features_and_gradients(golden):
-    """BASELINE config 3 (Stage-I dVAE step, B=2) against the unmodified reference DiscreteVAE: outputs and both losses to
-    1e-3, gradient norms and the stored full gradients to 2e-2.  The loss is Chamfer-L1: its gradient is a sum of UNIT
-    vectors towards arg-min partners, i.e. discontinuous in the forward values -- an fp32-grade forward (1e-5) still
-    re-assigns a few partners of near-equidistant points, which moves upstream gradient norms by up to ~1.5 % (measured:
-    mini-PointNet BatchNorm1 bias 1.4 %), whatever the arithmetic of the backward."""
+def _dvae_parity_model():
     from act_b200 import dvae
     from act_b200.models import Cfg
-    g = golden("dvae_step.npz")
     cfg = Cfg(NAME="DiscreteVAE", group_size=32, num_group=64, num_tokens=8192, encoder_dims=256, tokens_dims=256,
               decoder_dims=256)
     model = ref_model.fill_params(dvae.DiscreteVAE(cfg), seed=8).cuda().train()
-    pts = torch.from_numpy(g["pts"]).cuda()
     gumbel = torch.from_numpy(np.random.default_rng(41).gumbel(size=(2, 64, 8192)).astype(np.float32)).cuda()
+    return model, gumbel
+
+
+def test_dvae_step_features_and_gradients(golden):
+    """BASELINE config 3 (Stage-I dVAE step, B=2) against the unmodified reference DiscreteVAE: outputs and both losses to
+    1e-3.  The training loss is Chamfer-L1: its gradient is a sum of UNIT vectors towards arg-min partners, i.e. piecewise
+    constant in the forward values -- two fp32-grade forwards that differ in the last bits (ours vs the reference's, or two
+    of our own runs: the split-K reductions use float atomics) re-assign a few partners of near-equidistant points, and the
+    upstream gradients then move by 1 % typically and up to ~5 % (measured over repeated runs on a B200: 0.9 - 4.5 % on
+    encoder.first_conv.0.weight), whatever the arithmetic of the backward.  So the Chamfer gradients are held to 2e-2 on the
+    norms / 1e-1 on the full tensors here, and the backward ARITHMETIC of the whole step is held to the 1e-2 / 1e-3 bar by
+    test_dvae_step_smooth_loss_gradients below, on a loss without that discontinuity."""
+    g = golden("dvae_step.npz")
+    model, gumbel = _dvae_parity_model()
+    pts = torch.from_numpy(g["pts"]).cuda()
     ret = model(pts, temperature=1.0, hard=False, gumbel=gumbel)
     l1, l2 = model.get_loss(ret, pts)
     (l1 + 0.05 * l2).backward()
@@ -224,4 +232,40 @@ def test_dvae_step_features_and_gradients(golden):
     assert not bad, bad
     worst = {k: rel(params[k[5:]].grad, g[k]) for k in g.files if k.startswith("grad/") and k != "grad/codebook_rows"}
     worst["codebook_rows"] = rel(model.codebook.grad[::512], g["grad/codebook_rows"])
-    assert all(v < 2e-2 for v in worst.values()), worst
+    assert all(v < 1e-1 for v in worst.values()), worst
+
+
+def test_dvae_step_smooth_loss_gradients(golden):
+    """The same Stage-I forward differentiated through a smooth loss (a fixed random linear functional of the coarse and
+    fine reconstructions + 0.05 * KL; oracle/make_golden.py:gen_dvae_step_smooth ran it on the unmodified reference): the
+    whole backward (FoldingNet decoder, codebook, gumbel-softmax, DGCNN x2, mini-PointNet, KL) without Chamfer's arg-min
+    discontinuity: gradient norms to 5e-3 (median 1e-3), full gradients to 2e-2 (median 1e-2); see the comment below."""
+    g, gs = golden("dvae_step.npz"), golden("dvae_step_smooth.npz")
+    model, gumbel = _dvae_parity_model()
+    pts = torch.from_numpy(g["pts"]).cuda()
+    ret = model(pts, temperature=1.0, hard=False, gumbel=gumbel)
+    whole_coarse, whole_fine, coarse, fine, nb, logits = ret
+    _, l2 = model.get_loss(ret, pts)
+    rng = np.random.default_rng(43)                      # == oracle.make_golden.dvae_smooth_weights
+    rc = torch.from_numpy(rng.standard_normal(tuple(coarse.shape)).astype(np.float32)) / float(np.prod(coarse.shape[:-1]))
+    rf = torch.from_numpy(rng.standard_normal(tuple(fine.shape)).astype(np.float32)) / float(np.prod(fine.shape[:-1]))
+    loss = (coarse * rc.cuda()).sum() + (fine * rf.cuda()).sum() + 0.05 * l2
+    loss.backward()
+    # the random linear functional nearly cancels the KL term (|loss| ~ 1e-3 from terms of ~2e-2): compare on that scale
+    assert abs(loss.item() - float(gs["loss"])) <= FEAT * 2e-2
+    params = dict(model.named_parameters())
+    norms = dict(zip(gs["grad_names"].tolist(), gs["grad_norms"].tolist()))
+    floor = 1e-5 * max(norms.values())
+    nerr = {k: abs(params[k].grad.norm().item() - w) / w for k, w in norms.items() if w > floor}
+    worst = {k: rel(params[k[5:]].grad, gs[k]) for k in gs.files if k.startswith("grad/") and k != "grad/codebook_rows"}
+    worst["codebook_rows"] = rel(model.codebook.grad[::512], gs["grad/codebook_rows"])
+    print("smooth-loss gradient errors: norms max", max(nerr.values()), "full", worst)
+    # Measured on a B200 (6-term parity GEMM): norms <= 3.4e-3 (median 4e-4), full gradients 5e-5 (decoder output layer)
+    # ... 6e-3 (decoder input, DGCNNs, codebook) ... 1.05e-2 (mini-PointNet first conv, the far end of the chain).  What is
+    # left is not arithmetic: a forward that agrees to ~1e-5 still decides a fraction f ~ 1e-5 of the ReLU / LeakyReLU /
+    # max-over-k / max-pool branches differently, and each flipped branch moves a gradient entry by its full value: relative
+    # error ~ sqrt(f) per layer, accumulating upstream (with the 3-term GEMM, forward 3e-5: 1 % ... 6 % on the same tensors).
+    assert all(v < 5 * NORM for v in nerr.values()), {k: v for k, v in nerr.items() if v >= 5 * NORM}
+    assert sorted(nerr.values())[len(nerr) // 2] < NORM
+    assert all(v < 2 * GRAD for v in worst.values()), worst
+    assert sorted(worst.values())[len(worst) // 2] < GRAD

@@ -53,6 +53,32 @@ def test_dvae_restatement_matches_reference_golden(golden):
             np.testing.assert_allclose(b.numpy(), g["buf/" + k], rtol=1e-4, atol=1e-5)
 
 
+def test_dvae_restatement_smooth_loss_gradients(golden):
+    """The step differentiated through the smooth surrogate loss (make_golden.gen_dvae_step_smooth): the fixture the GPU
+    parity test holds the whole Stage-I backward to, free of Chamfer-L1's arg-min discontinuity."""
+    g, gs = golden("dvae_step.npz"), golden("dvae_step_smooth.npz")
+    torch.set_num_threads(8)
+    model = ref_model.fill_params(ref_dvae.DiscreteVAE(), seed=8).train()
+    pts = torch.from_numpy(g["pts"])
+    ret = model(pts, temperature=1.0, hard=False, gumbel=_noise())
+    _, _, coarse, fine, _, _ = ret
+    _, l2 = model.get_loss(ret, pts)
+    rng = np.random.default_rng(43)
+    rc = torch.from_numpy(rng.standard_normal(tuple(coarse.shape)).astype(np.float32)) / float(np.prod(coarse.shape[:-1]))
+    rf = torch.from_numpy(rng.standard_normal(tuple(fine.shape)).astype(np.float32)) / float(np.prod(fine.shape[:-1]))
+    loss = (coarse * rc).sum() + (fine * rf).sum() + KLD_WEIGHT * l2
+    loss.backward()
+    assert abs(loss.item() - float(gs["loss"])) <= 1e-4 * abs(float(gs["loss"])) + 1e-8
+    grads = dict(model.named_parameters())
+    floor = 1e-5 * gs["grad_norms"].max()          # biases in front of a BatchNorm: analytically zero gradient, noise only
+    for k, want in zip(gs["grad_names"].tolist(), gs["grad_norms"].tolist()):
+        got = grads[k].grad.norm().item()
+        assert want < floor or abs(got - want) <= 1e-3 * want, (k, got, want)
+    for k in gs.files:
+        if k.startswith("grad/") and k != "grad/codebook_rows":
+            np.testing.assert_allclose(grads[k[5:]].grad.numpy(), gs[k], rtol=2e-3, atol=1e-3 * np.abs(gs[k]).max())
+
+
 def test_schedules():
     """tools/runner_autoencoder.py:18-53 with cfgs/autoencoder/pointbert_dvae.yaml:27-38."""
     assert ref_dvae.temperature_schedule(0) == 1.0
