@@ -14,6 +14,8 @@
 // d gamma / d beta; pass 2 (one warp per token row, float4 lanes) re-forms xh from P and Q, writes dQ = sum_j de and
 // scatters dP[nbr_j] += de_j with vector reductions (red.global.add.v4.f32) -- the neighbour lists have no fixed in-degree,
 // so a gather formulation would need a CSR transpose per step.  HBM-bound: pq is read twice, d pq written once.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace act {
@@ -446,5 +448,56 @@ extern "C" int act_gn_rows_train_bwd(const float *x, const float *stats, const f
     const int rows = B * R;
     ACT_CUDA(launch_k(gn_rows_train_apply_kernel<true>, dim3((rows + 7) / 8), dim3(256), 0, st, true, x, stats,
                       (const float *)sums, gamma, beta, dy, rows, R, C, groups, slope, dx));
+    return ACT_OK;
+}
+
+// ---- the edge conv's token-level weight -------------------------------------------------------------------------------
+// A DGCNN edge layer applies W [Cp, 2*Cin] to [x_k - x_q ; x_q] (dvae.py:63-79 get_graph_feature + Conv2d 1x1).  As ONE
+// token-level GEMM it is  P | Q = x . W'^T  with  W' = [Wa ; Wb - Wa]  ([2*Cp, Cin];  Wa = W[:, :Cin], Wb = W[:, Cin:]).
+// edge_weight_fwd builds W' directly in the GEMM operand dtype; edge_weight_bwd folds dW' back:
+//   dW[:, :Cin] += dW'_top - dW'_bot,   dW[:, Cin:] += dW'_bot.
+namespace act {
+__global__ void __launch_bounds__(256) edge_weight_fwd_kernel(const float *__restrict__ W, int Cp, int Cin, int out_bf16,
+                                                              void *__restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
+    const int n = 2 * Cp * Cin;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const int r = i / Cin, c = i - r * Cin;
+        const float v = r < Cp ? W[(size_t)r * 2 * Cin + c]
+                               : W[(size_t)(r - Cp) * 2 * Cin + Cin + c] - W[(size_t)(r - Cp) * 2 * Cin + c];
+        if (out_bf16) reinterpret_cast<__nv_bfloat16 *>(out)[i] = __float2bfloat16_rn(v);
+        else reinterpret_cast<float *>(out)[i] = v;
+    }
+}
+__global__ void __launch_bounds__(256) edge_weight_bwd_kernel(const float *__restrict__ dWp, int Cp, int Cin,
+                                                              float *__restrict__ dW) {
+    pdl_wait();
+    pdl_trigger();
+    const int n = Cp * Cin;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const int r = i / Cin, c = i - r * Cin;
+        const float top = dWp[(size_t)r * Cin + c], bot = dWp[(size_t)(r + Cp) * Cin + c];
+        dW[(size_t)r * 2 * Cin + c] += top - bot;
+        dW[(size_t)r * 2 * Cin + Cin + c] += bot;
+    }
+}
+}  // namespace act
+
+extern "C" int act_edge_weight_fwd(const float *W, int Cp, int Cin, int out_bf16, void *out, void *stream) {
+    using namespace act;
+    if (!W || !out || Cp <= 0 || Cin <= 0) return ACT_EINVAL;
+    const int n = 2 * Cp * Cin;
+    ACT_CUDA(launch_k(edge_weight_fwd_kernel, dim3((n + 255) / 256 < 592 ? (n + 255) / 256 : 592), dim3(256), 0,
+                      (cudaStream_t)stream, true, W, Cp, Cin, out_bf16, out));
+    return ACT_OK;
+}
+
+extern "C" int act_edge_weight_bwd(const float *dWp, int Cp, int Cin, float *dW, void *stream) {
+    using namespace act;
+    if (!dWp || !dW || Cp <= 0 || Cin <= 0) return ACT_EINVAL;
+    const int n = Cp * Cin;
+    ACT_CUDA(launch_k(edge_weight_bwd_kernel, dim3((n + 255) / 256 < 592 ? (n + 255) / 256 : 592), dim3(256), 0,
+                      (cudaStream_t)stream, true, dWp, Cp, Cin, dW));
     return ACT_OK;
 }

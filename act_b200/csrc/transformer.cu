@@ -237,6 +237,29 @@ __global__ void __launch_bounds__(256) cast_rows_kernel(const float *__restrict_
     }
 }
 
+// the same for any row width C % 4 == 0 (no column sums): plain grid-stride element-wise pass
+__global__ void __launch_bounds__(256) cast_any_kernel(const float *__restrict__ x, long long n4, int C4,
+                                                       const float *__restrict__ row_scale, int rows_per_scale,
+                                                       void *__restrict__ g_out, int g_fp32) {
+    pdl_wait();
+    pdl_trigger();
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += gridDim.x * 256LL) {
+        float4 o = __ldg(reinterpret_cast<const float4 *>(x) + i);
+        if (row_scale) {
+            const float sc = __ldg(row_scale + (i / C4) / rows_per_scale);
+            o.x *= sc; o.y *= sc; o.z *= sc; o.w *= sc;
+        }
+        if (g_fp32) {
+            reinterpret_cast<float4 *>(g_out)[i] = o;
+        } else {
+            uint2 pk;
+            *reinterpret_cast<__nv_bfloat162 *>(&pk.x) = __floats2bfloat162_rn(o.x, o.y);
+            *reinterpret_cast<__nv_bfloat162 *>(&pk.y) = __floats2bfloat162_rn(o.z, o.w);
+            reinterpret_cast<uint2 *>(g_out)[i] = pk;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------- attention
 // qkv: bf16 [B*T, 3*H*64] (q | k | v, head-major inside each third, as nn.Linear(dim, 3*dim) + the
 // reference's reshape(B,N,3,H,C/H) lays it out).  Two lanes own one query row (32 of the 64 head dims each).
@@ -577,19 +600,26 @@ extern "C" int act_cast_rows(const float *x, int M, int C, const float *row_scal
     using namespace act;
     if (!x || !g_out || M < 0 || C <= 0) return ACT_EINVAL;
     if (M == 0) return ACT_OK;
-    if (C % 128 || C > 1024) return ACT_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = (M + 7) / 8 < 148 * 2 ? (M + 7) / 8 : 148 * 2;
     const int rps = rows_per_scale > 0 ? rows_per_scale : 1;
     void *g = g_out;
-    switch (C / 128) {
+    switch ((C % 128 || C > 1024) ? 0 : C / 128) {
         case 1: cast_rows_kernel<1><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, g_fp32, dbias); break;
         case 2: cast_rows_kernel<2><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, g_fp32, dbias); break;
         case 3: cast_rows_kernel<3><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, g_fp32, dbias); break;
         case 4: cast_rows_kernel<4><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, g_fp32, dbias); break;
         case 6: cast_rows_kernel<6><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, g_fp32, dbias); break;
         case 8: cast_rows_kernel<8><<<grid, 256, 0, st>>>(x, M, row_scale, rps, g, g_fp32, dbias); break;
-        default: return ACT_EUNSUPPORTED;
+        default: {
+            if (dbias || (C % 4)) return ACT_EUNSUPPORTED;
+            const long long n4 = (long long)M * (C / 4);
+            long long blocks = (n4 + 255) / 256;
+            if (blocks > 148 * 16) blocks = 148 * 16;
+            ACT_CUDA(launch_k(cast_any_kernel, dim3((unsigned)blocks), dim3(256), 0, st, true, x, n4, C / 4, row_scale, rps, g,
+                              g_fp32));
+            return ACT_OK;
+        }
     }
     ACT_CHECK_LAUNCH();
     return ACT_OK;

@@ -75,10 +75,7 @@ def dgcnn_forward(m, x, idx4, B, G):
     feats = []
     for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
         conv, gn = layer[0], layer[1]
-        W = conv.weight.flatten(1)                                                         # [Cp, 2*Cin]
-        cin = W.shape[1] // 2
-        Wa, Wb = W[:, :cin], W[:, cin:]
-        pq = layers.linear(f, torch.cat([Wa, Wb - Wa], dim=0))                             # [BG, 2*Cp] = (P | Q)
+        pq = layers.EdgeLinearFn.apply(f, conv.weight.flatten(1))                          # [BG, 2*Cp] = (P | Q)
         f = layers.DgcnnEdgeFn.apply(pq, idx4, gn.weight, gn.bias, B, G, gn.eps, 0.2)      # [BG, Cp]
         feats.append(f)
     h5 = layers.linear(torch.cat(feats, dim=1), m.layer5[0].weight.squeeze(-1))            # [BG, Cout]
@@ -120,10 +117,13 @@ class Decoder(nn.Module):
         z_g = layers.linear(fg, W0[:, :c].contiguous(), c0.bias)                                        # [BG,512]
         if self.folding_seed.device != fg.device:          # a plain attribute in the reference: moved once, kept
             self.folding_seed = self.folding_seed.to(fg.device)
-        seed = self.folding_seed[0].t()                                                    # [S,2]
-        z_s = seed @ W0[:, c:c + 2].t()                                                    # [S,512]
-        z_p = coarse @ W0[:, c + 2:].t()                                                   # [BG,M,512]
-        z = (z_g[:, None, None, :] + z_p[:, :, None, :] + z_s[None, None]).reshape(BG * N, 512)
+        seed = self.folding_seed[0].t().contiguous()                                       # [S,2]
+        if self.training and M == 8 and S == 4:
+            z = layers.FoldInputFn.apply(z_g, coarse, W0, seed)                            # csrc/folding.cu, act dtype
+        else:
+            z_s = seed @ W0[:, c:c + 2].t()                                                # [S,512]
+            z_p = coarse @ W0[:, c + 2:].t()                                               # [BG,M,512]
+            z = (z_g[:, None, None, :] + z_p[:, :, None, :] + z_s[None, None]).reshape(BG * N, 512)
         if self.training:      # BatchNorm1d + ReLU on the mini-PointNet's kernels, bf16 between the layers (layers.BnReluFn)
             a = layers.bn_relu(z, bn0)
             z = layers.linear(a, c1.weight.squeeze(-1), c1.bias, out_act=True)             # [BG*N,512]

@@ -60,12 +60,28 @@ class _SideStream:
             self.main.wait_stream(self.side)
 
 
+def _flat_attr(p, name):
+    """The flat-buffer slice (`_act_shadow` / `_act_grad`, set by FlatParams) of parameter p -- or, when p is a pure reshape
+    of a parameter (conv.weight.squeeze(-1): same elements, same order, same address), the base parameter's slice viewed in
+    p's shape, so that 1x1-conv weights need no per-step cast / zero-fill / add passes either."""
+    v = getattr(p, name, None)
+    if v is not None:
+        return v
+    b = getattr(p, "_base", None)
+    if (b is not None and b.numel() == p.numel() and p.is_contiguous() and b.is_contiguous()
+            and p.data_ptr() == b.data_ptr()):
+        v = getattr(b, name, None)
+        if v is not None:
+            return v.view(p.shape)
+    return None
+
+
 def shadow(p):
     """The GEMM operand form of a weight: its slice of the flat bf16 shadow (or an on-the-fly bf16 cast); in the
     fp32x3 parity mode the f32 master weight itself (ops.gemm splits it into bf16 pieces)."""
     if ops.act_dtype() == torch.float32:
         return p.detach()
-    s = getattr(p, "_act_shadow", None)
+    s = _flat_attr(p, "_act_shadow")
     return s if s is not None else p.detach().to(torch.bfloat16)
 
 
@@ -77,7 +93,7 @@ class _GradSink:
         self.ret = {}
 
     def get(self, p, key):
-        g = getattr(p, "_act_grad", None)
+        g = _flat_attr(p, "_act_grad")
         if g is not None:
             self.ret[key] = None
             return g
@@ -413,12 +429,7 @@ class LinearFn(torch.autograd.Function):
         shp = x.shape
         x2 = x.reshape(-1, shp[-1])
         adt = ops.act_dtype()
-        if x2.dtype == adt and x2.is_contiguous():
-            xb = x2
-        elif x2.dtype == torch.float32 and x2.is_contiguous() and shp[-1] % 128 == 0 and shp[-1] <= 1024:
-            xb = ops.cast_rows(x2)                               # our cast kernel (no library launch in the step)
-        else:
-            xb = x2.to(adt).contiguous()
+        xb = ops.to_act(x2)                                      # our cast kernel (no library launch in the step)
         odt = adt if out_act else torch.float32
         u = None
         if gelu:
@@ -451,7 +462,7 @@ class LinearFn(torch.autograd.Function):
             if N % 128 == 0 and N <= 1024:
                 g = ops.cast_rows(d2, dbias=sink.get(bias, "b") if bias is not None else None)
             else:
-                g = d2.to(adt)
+                g = ops.to_act(d2)
                 if bias is not None:
                     ops.colsum(d2, sink.get(bias, "b"))
         ops.wgrad(g, xb, sink.get(weight, "w"))
@@ -477,8 +488,7 @@ class BnReluFn(torch.autograd.Function):
     def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, momentum, eps):
         M, C = x.shape
         adt = ops.act_dtype()
-        xa = x if (x.dtype == adt and x.is_contiguous()) else (ops.cast_rows(x.contiguous().float()) if C % 128 == 0 and C <= 1024
-                                                                 else x.to(adt).contiguous())
+        xa = ops.to_act(x.contiguous())
         sm, sq = ops.bn_stats(xa)
         sc, sh, mean, rstd = ops.bn_finalize(sm, sq, M, gamma, beta, eps, momentum, running_mean, running_var, nbt)
         a = ops.bn_apply(xa, sc, sh, relu=True)
@@ -491,9 +501,7 @@ class BnReluFn(torch.autograd.Function):
         xa, a, mean, rstd, gamma, beta = ctx.saved_tensors
         sink = _GradSink()
         adt = ops.act_dtype()
-        d = da.contiguous()
-        if d.dtype != adt:
-            d = d.to(adt)
+        d = ops.to_act(da.contiguous())
         dz = ops.relu_mask_(d, a)                                # dz = da * (a > 0), in place on our own temporary
         dx, dbeta, dgamma = ops.bn_bwd(dz, xa, mean, rstd, gamma)
         ops.accumulate_(sink.get(gamma, "g"), dgamma)
@@ -569,10 +577,61 @@ class CodebookFn(torch.autograd.Function):
         sink = _GradSink()
         C = codebook.shape[1]
         d2 = dout.contiguous().float()
-        g = ops.cast_rows(d2) if (C % 128 == 0 and C <= 1024) else d2.to(ops.act_dtype())
+        g = ops.to_act(d2)
         ops.wgrad(y, g, sink.get(codebook, "w"))
         dy = ops.gemm(g, shadow(codebook), out_dtype=y.dtype) if ctx.needs_input_grad[0] else None
         return dy, sink.result("w")
+
+
+class EdgeLinearFn(torch.autograd.Function):
+    """(P | Q) = x . [Wa ; Wb - Wa]^T for a DGCNN edge conv weight W [Cp, 2*Cin] (see dvae.dgcnn_forward): the token-level
+    weight is built by one small kernel in the GEMM operand dtype and its gradient folded back into W's by another -- no
+    slice / sub / cat / cast / zero-fill / add library passes per layer and step."""
+
+    @staticmethod
+    def forward(ctx, x, W):
+        W = W.contiguous()
+        xb = ops.to_act(x.reshape(-1, x.shape[-1]))
+        Wp = ops.edge_weight_fwd(W.detach())
+        ctx.save_for_backward(xb, W, Wp)
+        ctx.x_dtype, ctx.x_needs = x.dtype, x.requires_grad
+        return ops.gemm(xb, Wp, out_dtype=torch.float32)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, W, Wp = ctx.saved_tensors
+        sink = _GradSink()
+        g = ops.to_act(dy.contiguous())
+        dWp = ops.zero_(torch.empty(Wp.shape, dtype=torch.float32, device=Wp.device))
+        ops.wgrad(g, xb, dWp)
+        ops.edge_weight_bwd(dWp, sink.get(W, "w"))
+        dx = None
+        if ctx.x_needs:
+            dx = ops.gemm(g, Wp, b_mn=True, out_dtype=ctx.x_dtype if ctx.x_dtype == ops.act_dtype() else torch.float32)
+        return dx, sink.result("w")
+
+
+class FoldInputFn(torch.autograd.Function):
+    """FoldingNet final_conv.0 over cat([global, seed, point]) (dvae.py:259-266) as z_g (per group) + Ws.seed (per grid
+    cell) + Wp.coarse (per coarse point), csrc/folding.cu: one pass writes z in the activation dtype; the backward reduces
+    dz to dz_g / dcoarse / the 5 weight columns in one pass.  weight: the conv's full f32 weight [C, c_g + 5] (a view of the
+    parameter), only its last 5 columns take part here (the first c_g act through z_g)."""
+
+    @staticmethod
+    def forward(ctx, z_g, coarse, weight, seed):
+        z_g, coarse = z_g.contiguous().float(), coarse.contiguous().float()
+        c_g = weight.shape[1] - 5
+        ctx.save_for_backward(coarse, weight, seed)
+        return ops.fold_input_fwd(z_g, coarse, weight, c_g, seed)
+
+    @staticmethod
+    def backward(ctx, dz):
+        coarse, weight, seed = ctx.saved_tensors
+        sink = _GradSink()
+        dw = sink.get(weight, "w")
+        dz_g, dcoarse = ops.fold_input_bwd(ops.to_act(dz.contiguous()), coarse, weight, weight.shape[1] - 5, seed,
+                                           dw.view(weight.shape))
+        return dz_g, dcoarse, sink.result("w"), None
 
 
 # --------------------------------------------------------------------------------------- pos-embed MLP

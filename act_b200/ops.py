@@ -325,6 +325,17 @@ def cast_rows(x, row_scale=None, rows_per_scale=1, dbias=None):
     return g
 
 
+def to_act(x):
+    """x [M, C] -> the activation dtype, on our cast kernel whenever its layout allows (f32, contiguous, C % 4 == 0);
+    otherwise a library copy."""
+    adt = act_dtype()
+    if x.dtype == adt and x.is_contiguous():
+        return x
+    if x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous() and x.shape[1] % 4 == 0 and x.data_ptr() % 16 == 0:
+        return cast_rows(x)
+    return x.to(adt).contiguous()
+
+
 def attention_fwd(qkv, B, T, H, scale):
     o = torch.empty(B * T, H * 64, dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty(B, H, T, dtype=torch.float32, device=qkv.device)
@@ -773,6 +784,47 @@ def gumbel_softmax_bwd(logits, lse, y, dy, tau, dqbar, G):
               int(y.dtype == torch.bfloat16), tp, tv if dy is not None else 1.0, dqbar, R, G, V, dl)
     _count()
     return dl
+
+
+def edge_weight_fwd(W):
+    """W f32 [Cp, 2*Cin] -> [2*Cp, Cin] = [Wa ; Wb - Wa] in the activation dtype (the GEMM's B operand)."""
+    Cp, Cin = W.shape[0], W.shape[1] // 2
+    out = torch.empty(2 * Cp, Cin, dtype=act_dtype(), device=W.device)
+    _lib.call("act_edge_weight_fwd", W, Cp, Cin, int(out.dtype == torch.bfloat16), _p(out))
+    _count()
+    return out
+
+
+def edge_weight_bwd(dWp, dW):
+    Cp, Cin = dW.shape[0], dW.shape[1] // 2
+    assert dWp.shape == (2 * Cp, Cin) and dWp.dtype == torch.float32 and dW.is_contiguous()
+    _lib.call("act_edge_weight_bwd", dWp, Cp, Cin, dW)
+    _count()
+
+
+def fold_input_fwd(z_g, coarse, weight, c_g, seed):
+    """FoldingNet final_conv.0 as a broadcast sum (csrc/folding.cu): z_g f32 [BG,C], coarse f32 [BG,M,3], weight f32
+    [C, c_g + 5] (the full conv weight; only its last 5 columns are read), seed f32 [S,2] -> z [BG*M*S, C] (act dtype)."""
+    BG, C = z_g.shape
+    M, S = coarse.shape[1], seed.shape[0]
+    z = torch.empty(BG * M * S, C, dtype=act_dtype(), device=z_g.device)
+    _lib.call("act_fold_input_fwd", z_g, coarse, _vp(weight.data_ptr() + 4 * c_g), weight.stride(0), seed, BG, M, S, C,
+              int(z.dtype == torch.bfloat16), _p(z))
+    _count()
+    return z
+
+
+def fold_input_bwd(dz, coarse, weight, c_g, seed, dweight):
+    """-> (dz_g f32 [BG,C], dcoarse f32 [BG,M,3]); the last 5 columns of dweight f32 [C, c_g + 5] are accumulated into."""
+    BG, M = coarse.shape[:2]
+    C, S = weight.shape[0], seed.shape[0]
+    dz_g = torch.empty(BG, C, dtype=torch.float32, device=dz.device)
+    dcoarse = torch.empty(BG, M, 3, dtype=torch.float32, device=dz.device)
+    assert dweight.stride(0) == weight.stride(0) and dweight.dtype == torch.float32
+    _lib.call("act_fold_input_bwd", _p(dz), int(dz.dtype == torch.bfloat16), coarse, _vp(weight.data_ptr() + 4 * c_g),
+              weight.stride(0), seed, BG, M, S, C, dz_g, dcoarse, _vp(dweight.data_ptr() + 4 * c_g))
+    _count()
+    return dz_g, dcoarse
 
 
 # ------------------------------------------------------------------------------------- input augmentation

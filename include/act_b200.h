@@ -154,7 +154,8 @@ int act_layernorm_bwd(const void *dy, int dy_fp32, const float *x, const float *
                       float *dbias, void *stream);
 
 /* g_bf16[M,C] = bf16(x[M,C] * row_scale[m / rows_per_scale]) (row_scale nullable); dbias[C] (nullable) +=
- * its column sums.  Entry point of a Block backward when the incoming gradient is plain fp32. */
+ * its column sums.  Entry point of a Block backward when the incoming gradient is plain fp32.  C in {128, 256, 384, 512,
+ * 768, 1024}; any other C % 4 == 0 when dbias is NULL (plain element-wise pass). */
 int act_cast_rows(const float *x, int M, int C, const float *row_scale, int rows_per_scale, void *g_out, int g_fp32,
                   float *dbias, void *stream);
 
@@ -340,6 +341,12 @@ int act_gn_rows_train_bwd(const float *x, const float *stats, const float *gamma
                           int B, int R, int C, int groups, float slope, float *sums, float *dx, float *dgamma,
                           float *dbeta, void *stream);
 
+/* The DGCNN edge conv's weight W f32 [Cp, 2*Cin] (Conv2d 1x1 over [x_k - x_q ; x_q], dvae.py:63-79) in the token-level
+ * form the GEMM reads: out [2*Cp, Cin] = [W[:, :Cin] ; W[:, Cin:] - W[:, :Cin]] (bf16 if out_bf16 else f32); and the fold
+ * of the gradient dWp f32 [2*Cp, Cin] back: dW[:, :Cin] += top - bottom, dW[:, Cin:] += bottom (dW accumulated into). */
+int act_edge_weight_fwd(const float *W, int Cp, int Cin, int out_bf16, void *out, void *stream);
+int act_edge_weight_bwd(const float *dWp, int Cp, int Cin, float *dW, void *stream);
+
 /* Soft gumbel-softmax over the codebook + KL(mean softmax || uniform), /root/reference/models/dvae.py:343-347 (forward:
  * F.gumbel_softmax(logits, tau, dim=2, hard=False)) and :320-332 (get_loss: softmax -> mean over the groups -> log ->
  * F.kl_div(., log uniform, 'batchmean', log_target=True)); the reference spends ~12 element-wise passes over
@@ -364,6 +371,17 @@ int act_kl_uniform_bwd(const float *qbar, const float *gout, int B, int V, float
 int act_gumbel_softmax_bwd(const float *logits, const float *lse, const void *y, const void *dy, int act_bf16,
                            const float *tau_ptr, float tau_val, const float *dqbar, int R, int G, int V, float *dlogits,
                            void *stream);
+
+/* FoldingNet decoder input layer, /root/reference/models/dvae.py:259-266: final_conv.0 over cat([global, seed, point]) as a
+ * broadcast sum.  z[(bg*M + m)*S + s, :] = z_g[bg,:] + w_tail[:,0:2] . seed[s,:] + w_tail[:,2:5] . coarse[bg,m,:], with
+ * z_g f32 [BG,C] (the global part + bias, from the GEMM), coarse f32 [BG,M,3], seed f32 [S,2], w_tail = &weight[0][C_g]
+ * (f32, row pitch ldw, 5 columns), z [BG*M*S, C] bf16 if out_bf16 else f32.  M = 8, S = 4, C <= 512 and even.
+ * Backward: dz -> dz_g f32 [BG,C] and dcoarse f32 [BG,M,3] (overwritten), dw_tail (same layout as w_tail) ACCUMULATED
+ * INTO (atomics). */
+int act_fold_input_fwd(const float *z_g, const float *coarse, const float *w_tail, int ldw, const float *seed, int BG,
+                       int M, int S, int C, int out_bf16, void *z, void *stream);
+int act_fold_input_bwd(const void *dz, int in_bf16, const float *coarse, const float *w_tail, int ldw, const float *seed,
+                       int BG, int M, int S, int C, float *dz_g, float *dcoarse, float *dw_tail, void *stream);
 
 /* ---- Input augmentation -------------------------------------------------------------- */
 

@@ -308,3 +308,47 @@ def test_gumbel_softmax_in_kernel_noise_is_gumbel():
     top = p > 1e-3
     assert (emp[top] - p[top]).abs().max().item() < 4 * (p.max() * (1 - p.max()) / R).sqrt().item() + 2e-3
     assert abs(emp[~top].sum().item() - p[~top].sum().item()) < 5e-3
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32x3"])
+def test_fold_input_and_edge_weight_kernels(mode):
+    """csrc/folding.cu (FoldingNet final_conv.0 as a broadcast sum, dvae.py:259-266) and the DGCNN edge-conv weight
+    transform (dvae.py:63-79) against the plain torch composition, forward and backward."""
+    from act_b200 import layers, ops
+    torch.manual_seed(11)
+    BG, M, S, C, cg = 37, 8, 4, 512, 256
+    z_g = torch.randn(BG, C, device="cuda", requires_grad=True)
+    coarse = torch.randn(BG, M, 3, device="cuda", requires_grad=True)
+    W = torch.randn(C, cg + 5, device="cuda", requires_grad=True)
+    seed = torch.tensor([[-0.05, -0.05], [0.05, -0.05], [-0.05, 0.05], [0.05, 0.05]], device="cuda")
+    wgt = torch.randn(BG * M * S, C, device="cuda")
+    with ops.precision(mode):
+        z = layers.FoldInputFn.apply(z_g, coarse, W, seed)
+        assert z.dtype == ops.act_dtype()
+        (z.float() * wgt).sum().backward()
+    got = [t.grad.clone() for t in (z_g, coarse, W)]
+    for t in (z_g, coarse, W):
+        t.grad = None
+    z_ref = (z_g[:, None, None, :] + (coarse @ W[:, cg + 2:].t())[:, :, None, :] + (seed @ W[:, cg:cg + 2].t())[None, None])
+    z_ref = z_ref.reshape(BG * M * S, C)
+    wq = wgt.bfloat16().float() if mode == "bf16" else wgt        # the backward sees dz in the activation dtype
+    (z_ref * wq).sum().backward()
+    assert rel(z, z_ref) < (4e-3 if mode == "bf16" else 1e-6)
+    for a, b in zip(got, (z_g, coarse, W)):
+        assert rel(a, b.grad) < 1e-5, rel(a, b.grad)
+    assert got[2][:, :cg].abs().max().item() == 0.0               # only the 5 tail columns belong to this layer
+    # edge-conv weight: (P | Q) = x . [Wa ; Wb - Wa]^T and the gradient folded back into W
+    Cp, Cin, R = 64, 128, 200
+    We = (torch.randn(Cp, 2 * Cin, device="cuda") * 0.1).requires_grad_(True)
+    x = torch.randn(R, Cin, device="cuda", requires_grad=True)
+    w2 = torch.randn(R, 2 * Cp, device="cuda")
+    with ops.precision(mode):
+        pq = layers.EdgeLinearFn.apply(x, We)
+        (pq * w2).sum().backward()
+    gx, gw = x.grad.clone(), We.grad.clone()
+    x.grad = We.grad = None
+    Wa, Wb = We[:, :Cin], We[:, Cin:]
+    pq_ref = x @ torch.cat([Wa, Wb - Wa], 0).t()
+    (pq_ref * w2).sum().backward()
+    tol = 2e-2 if mode == "bf16" else 2e-5
+    assert rel(pq, pq_ref) < tol and rel(gx, x.grad) < tol and rel(gw, We.grad) < tol
