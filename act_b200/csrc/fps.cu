@@ -146,17 +146,30 @@ __device__ __forceinline__ void st_cluster_u64(uint32_t local_addr, uint32_t cta
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(cta));
     asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(remote), "r"(lo), "r"(hi) : "memory");
 }
+// 8-byte store into CTA `cta`'s shared memory that completes 8 bytes of transaction on that CTA's mbarrier (both given
+// as this CTA's addresses of the same variables): the round's exchange needs no barrier.cluster -- every CTA waits on its
+// OWN mbarrier for the CL * T/32 candidates of the round to land.
+__device__ __forceinline__ void st_async_cluster_u64(uint32_t local_addr, uint32_t local_bar, uint32_t cta, uint32_t lo,
+                                                     uint32_t hi) {
+    uint32_t remote, rbar;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(cta));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(local_bar), "r"(cta));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(remote),
+                 "r"(lo), "r"(hi), "r"(rbar)
+                 : "memory");
+}
 __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int T, int PPT, int CL>
+template <int T, int PPT, int CL, bool ASYNC>
 __global__ void __launch_bounds__(T) fps_cluster_kernel(const float *__restrict__ xyz, int N, int G, int log2_bs,
                                                         int32_t *__restrict__ idx, float *__restrict__ center) {
     static_assert(CL * (T / 32) <= 32, "one candidate per lane in the final reduction");
     extern __shared__ __align__(16) float s_xyz[];  // [N][3]
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(8) uint2 s_red[2][32];     // [parity][cta * (T/32) + warp]
+    __shared__ __align__(8) uint64_t s_xbar[2];     // ASYNC: per-parity mbarrier counting the round's incoming bytes
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t rank = cluster_ctarank();
@@ -165,6 +178,8 @@ __global__ void __launch_bounds__(T) fps_cluster_kernel(const float *__restrict_
     if (tid < 64) reinterpret_cast<uint2 *>(s_red)[tid] = make_uint2(0u, 0u);     // unused slots: "no candidate"
     if (tid == 0) {
         mbar_init(&s_bar, 1);
+        mbar_init(&s_xbar[0], 1);
+        mbar_init(&s_xbar[1], 1);
         fence_mbar_init();
     }
     __syncthreads();
@@ -217,9 +232,19 @@ __global__ void __launch_bounds__(T) fps_cluster_kernel(const float *__restrict_
         const uint32_t wv = redux_max(bv);
         const uint32_t wt = redux_max(bv == wv ? bt : 0u);
         const int par = g & 1;
-        if (lane < CL)                              // lane c publishes this warp's maximum into CTA c's slot array
-            st_cluster_u64(smem_u32(&s_red[par][rank * (T / 32) + warp]), (uint32_t)lane, wv, wt);
-        cluster_barrier();
+        if (ASYNC) {
+            // this round's CL * T/32 slots (8 bytes each) arrive asynchronously; the phase of s_xbar[par] completes when
+            // the one local arrival below and all their bytes are in (remote bytes may land first: the count goes negative)
+            if (tid == 0) mbar_expect_tx(&s_xbar[par], CL * (T / 32) * 8);
+            if (lane < CL)
+                st_async_cluster_u64(smem_u32(&s_red[par][rank * (T / 32) + warp]), smem_u32(&s_xbar[par]), (uint32_t)lane,
+                                     wv, wt);
+            mbar_wait(&s_xbar[par], (uint32_t)((g - 1) >> 1) & 1u);      // use number (g - 1) / 2 of this parity's barrier
+        } else {
+            if (lane < CL)                          // lane c publishes this warp's maximum into CTA c's slot array
+                st_cluster_u64(smem_u32(&s_red[par][rank * (T / 32) + warp]), (uint32_t)lane, wv, wt);
+            cluster_barrier();
+        }
         const uint2 r = s_red[par][lane];
         const uint32_t mv = redux_max(r.x);
         const uint32_t mt = redux_max(r.x == mv ? r.y : 0u);
@@ -236,11 +261,19 @@ __global__ void __launch_bounds__(T) fps_cluster_kernel(const float *__restrict_
     cluster_barrier();                              // no CTA exits while a peer may still store into its shared memory
 }
 
+static int act_fps_async_mode() {
+    static const int mode = [] {
+        const char *e = std::getenv("ACT_B200_FPS_ASYNC");        // 0: barrier.cluster per round (A/B); default st.async
+        return e ? std::atoi(e) : 1;
+    }();
+    return mode;
+}
+
 template <int T, int PPT, int CL>
 static int launch_fps_cluster(const float *xyz, int B, int N, int G, int log2_bs, int32_t *idx, float *center,
                               cudaStream_t st) {
     const size_t smem = (size_t)N * 12;
-    auto kern = fps_cluster_kernel<T, PPT, CL>;
+    auto kern = act_fps_async_mode() ? fps_cluster_kernel<T, PPT, CL, true> : fps_cluster_kernel<T, PPT, CL, false>;
     if (smem > 40 * 1024) ACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(B * CL);
