@@ -51,17 +51,29 @@ __global__ void __launch_bounds__(256) cosine_loss_kernel(const float *__restric
 
 // hp[0..7] = lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, grad_scale  (device memory, so a
 // captured CUDA graph sees the scheduler's new values on every replay)
-__global__ void __launch_bounds__(256) adamw_kernel(float *__restrict__ p, const float *__restrict__ g,
+// G16: the gradient is the bf16 buffer the N>1 all-reduce ran on (dp.sync_gradients), else the fp32 flat gradient
+template <bool G16>
+__global__ void __launch_bounds__(256) adamw_kernel(float *__restrict__ p, const void *__restrict__ g_any,
                                                     float *__restrict__ m, float *__restrict__ v,
                                                     __nv_bfloat16 *__restrict__ shadow, long long n,
                                                     long long n_decay, const float *__restrict__ hp) {
     const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], wd = hp[4], bc1 = hp[5], bc2 = hp[6], gs = hp[7];
     const float step = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+    const float *g = reinterpret_cast<const float *>(g_any);
+    const __nv_bfloat16 *g16 = reinterpret_cast<const __nv_bfloat16 *>(g_any);
     for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; i < n;
          i += (long long)gridDim.x * blockDim.x * 4) {
         if (i + 4 <= n) {
             float4 pv = *reinterpret_cast<float4 *>(p + i);
-            const float4 gv = *reinterpret_cast<const float4 *>(g + i);
+            float4 gv;
+            if (G16) {
+                const uint2 u = *reinterpret_cast<const uint2 *>(g16 + i);
+                const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u.x));
+                const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u.y));
+                gv = make_float4(a.x, a.y, b.x, b.y);
+            } else {
+                gv = *reinterpret_cast<const float4 *>(g + i);
+            }
             float4 mv = *reinterpret_cast<float4 *>(m + i), vv = *reinterpret_cast<float4 *>(v + i);
             float *pp = &pv.x, *mp = &mv.x, *vp = &vv.x;
             const float *gp = &gv.x;
@@ -84,7 +96,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float *__restrict__ p, const
             }
         } else {
             for (long long k = i; k < n; ++k) {
-                const float gr = g[k] * gs;
+                const float gr = (G16 ? __bfloat162float(g16[k]) : g[k]) * gs;
                 float pk = p[k];
                 if (k < n_decay) pk *= 1.f - lr * wd;
                 const float mk = b1 * m[k] + (1.f - b1) * gr, vk = b2 * v[k] + (1.f - b2) * gr * gr;
@@ -160,9 +172,26 @@ extern "C" int act_adamw(float *param, const float *grad, float *exp_avg, float 
     if (n == 0) return ACT_OK;
     long long blocks = (n / 4 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    adamw_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq,
-                                                                reinterpret_cast<__nv_bfloat16 *>(shadow_bf16), n,
-                                                                n_decay, hyper);
+    adamw_kernel<false><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq,
+                                                                       reinterpret_cast<__nv_bfloat16 *>(shadow_bf16), n,
+                                                                       n_decay, hyper);
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}
+
+extern "C" int act_adamw_bf16grad(float *param, const void *grad_bf16, float *exp_avg, float *exp_avg_sq, void *shadow_bf16,
+                                  long long n, long long n_decay, const float *hyper, void *stream) {
+    using namespace act;
+    if (!param || !grad_bf16 || !exp_avg || !exp_avg_sq || !hyper || n < 0) return ACT_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15)
+        return ACT_EALIGN;
+    if ((reinterpret_cast<uintptr_t>(grad_bf16) & 7) || (n_decay % 4)) return ACT_EALIGN;
+    if (n == 0) return ACT_OK;
+    long long blocks = (n / 4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    adamw_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad_bf16, exp_avg, exp_avg_sq,
+                                                                      reinterpret_cast<__nv_bfloat16 *>(shadow_bf16), n,
+                                                                      n_decay, hyper);
     ACT_CHECK_LAUNCH();
     return ACT_OK;
 }

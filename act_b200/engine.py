@@ -104,6 +104,8 @@ class PretrainStep:
         self.graph = None
         self.graph_b = None
         self.launches_per_step = None
+        if dp.world_size() > 1:
+            self.fp.enable_bf16_comm()
 
     # the device work of one step (capturable: no host sync, no pageable copy), in two halves so that for N>1 the
     # step's one collective sits BETWEEN two graphs (NCCL's watchdog thread and stream capture do not mix safely;
@@ -363,6 +365,8 @@ class AutoencoderStep:
         self.graph = self.graph_b = None
         self.n_itr = 0
         self.launches_per_step = None
+        if dp.world_size() > 1:
+            self.fp.enable_bf16_comm()
 
     def _body_a(self):
         self.fp.zero_grad()

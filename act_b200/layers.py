@@ -137,6 +137,7 @@ class FlatParams:
         self.total = total
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad16 = None                     # bf16 communication copy (enable_bf16_comm)
         self.shadow = torch.zeros(total, dtype=torch.bfloat16, device=dev)
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -249,9 +250,21 @@ class FlatParams:
             host = host.pin_memory()
         self.hyper.copy_(host, non_blocking=True)
 
+    def enable_bf16_comm(self):
+        """N>1: all-reduce a bf16 copy of the flat gradient (half the NVLink bytes and half NCCL's HBM traffic beside the
+        teacher's GEMMs) and apply AdamW from it.  Must be called before the step is captured; ACT_B200_GRAD_COMM=fp32
+        keeps DDP's fp32 all-reduce (the parity mode always does)."""
+        import os
+        if os.environ.get("ACT_B200_GRAD_COMM", "bf16") == "fp32" or ops.act_dtype() == torch.float32:
+            return False
+        if self.grad16 is None:
+            self.grad16 = torch.zeros(self.grad.numel(), dtype=torch.bfloat16, device=self.grad.device)
+        return True
+
     def step(self):
         """One fused AdamW launch over the flat buffers (hyper-parameters read from device memory)."""
-        ops.adamw(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.shadow, self.n_decay, self.hyper)
+        g = self.grad16 if self.grad16 is not None else self.grad
+        ops.adamw(self.flat, g, self.exp_avg, self.exp_avg_sq, self.shadow, self.n_decay, self.hyper)
 
 
 # ------------------------------------------------------------------------------------- Transformer stack

@@ -397,9 +397,20 @@ def scale_by_(x, scalar):
 
 
 def adamw(param, grad, exp_avg, exp_avg_sq, shadow, n_decay, hyper):
-    _lib.call("act_adamw", param, grad, exp_avg, exp_avg_sq, shadow, _lib.ctypes.c_int64(param.numel()),
+    """grad: the flat fp32 gradient, or its all-reduced bf16 copy (N>1, dp.sync_gradients)."""
+    name = "act_adamw_bf16grad" if grad.dtype == torch.bfloat16 else "act_adamw"
+    _lib.call(name, _p(param), _p(grad), exp_avg, exp_avg_sq, shadow, _lib.ctypes.c_int64(param.numel()),
               _lib.ctypes.c_int64(n_decay), hyper)
     _count()
+
+
+def cast_flat_(src, dst):
+    """dst (bf16, flat) = bf16(src) (f32, flat; numel % 4 == 0) on our cast kernel."""
+    n = src.numel()
+    assert dst.numel() == n and n % 4 == 0 and src.dtype == torch.float32 and dst.dtype == torch.bfloat16
+    _lib.call("act_cast_rows", src, 1, n, None, 1, _p(dst), 0, None)
+    _count()
+    return dst
 
 
 

@@ -195,7 +195,11 @@ class Harness:
         wall_ms = (time.perf_counter() - t0) * 1e3
         ms = sum(a.elapsed_time(b) for a, b in evs)
         t = torch.tensor([ms, wall_ms], dtype=torch.float64, device=self.dev)
+        self.last_per_rank_ms = [round(ms / K, 4)]
         if self.world > 1:
+            every = [torch.zeros_like(t) for _ in range(self.world)]
+            self.dist.all_gather(every, t)
+            self.last_per_rank_ms = [round(e[0].item() / K, 4) for e in every]      # device ms/step of every rank
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return t[0].item() / K, max(0.0, t[1].item() / K - fl)
 
@@ -347,6 +351,7 @@ def bench_stage2(h, shape, teacher, steps, warmup, want_roofline, want_student_o
     h.barrier()
     sampler = ClockSampler(h.local) if h.rank == 0 else None
     ms_step, wall_step = h.timed(step, steps)
+    per_rank = list(h.last_per_rank_ms)
     ms_e2e, wall_e2e = h.timed(step_e2e, steps)
     clocks = sampler.stop() if sampler else None
     sustained = h.sustained(step, h.args.sustain_seconds) if want_sustained else None
@@ -354,7 +359,8 @@ def bench_stage2(h, shape, teacher, steps, warmup, want_roofline, want_student_o
     torch.cuda.synchronize()
     res = {"batch": B, "ms_step": ms_step, "wall_step": wall_step, "ms_e2e": ms_e2e, "wall_e2e": wall_e2e,
            "clocks": clocks, "sustained": sustained, "launches": int(eng.launches_per_step),
-           "pipelined": bool(eng.pipeline), "loss": float(loss_host.item()),
+           "pipelined": bool(eng.pipeline), "loss": float(loss_host.item()), "per_rank_ms": per_rank,
+           "grad_comm": "bf16" if getattr(fp, "grad16", None) is not None else "fp32",
            "h2d": int(host[0].numel() * 4 + B * sh["num_group"] + 32)}
     # the same step without the frozen teacher's forward (synthetic target): what the trainable path alone costs
     if want_student_only and teacher == "native":
@@ -516,6 +522,7 @@ def run_ours(args):
                                       "what": "same step with a synthetic teacher target (no teacher forward)"}),
                     "sustained": sus,
                     "gpu_launches": res["launches"], "cuda_graph": not args.no_graph, "pipelined": res["pipelined"],
+                    "per_rank_ms_per_step": res["per_rank_ms"], "grad_comm": res["grad_comm"],
                     "loss": res["loss"], "clocks": res["clocks"], "roofline": roof,
                     "tokenizer_us": res.get("tokenizer_us"),
                     "precision": "bf16 operands, fp32 accumulate (speed mode; ACT_B200_PRECISION=fp32x3 selects the parity mode)",

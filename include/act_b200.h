@@ -423,6 +423,11 @@ int act_scale_by(float *x, const float *scalar, long long n, void *stream);
  * the bf16 copy of the updated parameters (what the GEMMs read). */
 int act_adamw(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, void *shadow_bf16, long long n,
               long long n_decay, const float *hyper, void *stream);
+/* The same update reading the gradient from a bf16 buffer: the N>1 path casts the flat fp32 gradient to bf16 once
+ * (act_cast_rows with M = 1), all-reduces the bf16 copy (half the NVLink bytes of DDP's fp32 buckets,
+ * /root/reference/tools/runner_pretrain.py:84-90) and applies it from there. */
+int act_adamw_bf16grad(float *param, const void *grad_bf16, float *exp_avg, float *exp_avg_sq, void *shadow_bf16,
+                       long long n, long long n_decay, const float *hyper, void *stream);
 
 #ifdef __cplusplus
 }

@@ -34,7 +34,15 @@ def _worker(rank, world, port, q):
     for p in fp.params:                                 # autograd accumulated INTO the flat views
         assert p.grad.data_ptr() == p._act_grad.data_ptr()
     scale = dp.sync_gradients(fp)
-    q.put((rank, w0, fp.grad.clone() * scale, dp.shard_seed(5, rank, 0), fp.n_decay, fp.names))
+    g32 = fp.grad.clone() * scale
+    # bf16 communication (the speed mode's default for N>1): the same step again, all-reduced as a bf16 copy
+    fp.zero_grad()
+    ((model(xs) - ys) ** 2).sum().backward()
+    assert fp.enable_bf16_comm() and fp.grad16.dtype == torch.bfloat16
+    local = fp.grad.clone()
+    dp.sync_gradients(fp)
+    assert torch.equal(fp.grad, local)                  # the fp32 buffer keeps the local gradient; AdamW reads grad16
+    q.put((rank, w0, g32, dp.shard_seed(5, rank, 0), fp.n_decay, fp.names, fp.grad16.float() * scale))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -50,7 +58,9 @@ def test_flat_gradient_allreduce_world2():
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    (_, w_a, g_a, s_a, nd, names), (_, w_b, g_b, s_b, _, _) = res
+    (_, w_a, g_a, s_a, nd, names, g16_a), (_, w_b, g_b, s_b, _, _, g16_b) = res
+    assert torch.equal(g16_a, g16_b)                    # every rank applies the same bf16 sum
+    assert (g16_a - g_a).abs().max() <= 2 ** -7 * g_a.abs().max()     # bf16 rounding of each addend and of the sum
     assert torch.equal(w_a, w_b)                        # broadcast made the replicas identical
     assert torch.allclose(g_a, g_b) and s_a != s_b
     # reference: full-batch gradient of the mean-over-ranks loss on one process
