@@ -106,12 +106,26 @@ __global__ void __launch_bounds__(256) gn_rows_stats_kernel(const __nv_bfloat16 
     const int Cg = C / groups, c_lo = cg * Cg;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float s1 = 0.f, s2 = 0.f;
+    const bool vec = (Cg % 8 == 0) && (C % 8 == 0);
     for (int r = warp; r < R; r += 8) {
         const __nv_bfloat16 *p = x + ((size_t)b * R + r) * C + c_lo;
-        for (int c = lane * 2; c < Cg; c += 64) {
-            const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(p + c));
-            s1 += v.x + v.y;
-            s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, s2));
+        if (vec) {                                                   // 16-byte loads
+            for (int c = lane * 8; c < Cg; c += 256) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4 *>(p + c));
+                const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 v = __bfloat1622float2(h[q]);
+                    s1 += v.x + v.y;
+                    s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, s2));
+                }
+            }
+        } else {
+            for (int c = lane * 2; c < Cg; c += 64) {
+                const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(p + c));
+                s1 += v.x + v.y;
+                s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, s2));
+            }
         }
     }
     const float n = (float)R * Cg;
@@ -186,6 +200,117 @@ __global__ void __launch_bounds__(256) gn_rows_apply_kernel(const __nv_bfloat16 
     }
 }
 
+
+// ---- the hard gumbel-softmax sample without per-element noise ----------------------------------------------------------
+// forward_tokenizer_features draws F.gumbel_softmax(logits, hard=True) (dvae.py:587) = one_hot(argmax_c(logits_c + g_c)),
+// g i.i.d. standard Gumbel.  By the Gumbel-max theorem that index is distributed exactly as Categorical(softmax(logits)),
+// whatever tau.  Drawing it that way needs ONE uniform per row instead of 8192 Gumbel samples (a Philox block + two
+// logarithms per element made gn_rows_apply_kernel<2> compute-bound at 187 us: 7x its HBM time):
+//   pass 1  y = LeakyReLU(GroupNorm(x)) on the fly (8 channels = 16 B per lane and iteration, element (lane + 32 i) * 8 + k),
+//           per-lane online soft-max statistics (running max, sum of exp); warp-level max and an inclusive scan of the lane
+//           sums pick the lane whose sub-range holds  u * total;
+//   pass 2  the 32 lanes re-form that lane's C / 256 vectors (one each, L2 hits), scan their sums and pick the vector, and
+//           its owner walks the 8 elements.  Rounding between the two passes can leave the target a few ulps beyond the last
+//           partial sum: the last element of the range is taken then (probability ~1e-7).
+// Categories are visited in the order (lane, i, k): any fixed order samples the same distribution.
+// Requires C % 256 == 0 and C / 256 <= 32.  noise-injected runs (parity tests) keep the arg-max kernel above.
+__global__ void __launch_bounds__(256) gn_rows_sample_kernel(const __nv_bfloat16 *__restrict__ x,
+                                                             const float *__restrict__ stats,
+                                                             const float *__restrict__ gamma,
+                                                             const float *__restrict__ beta, int rows, int R, int C,
+                                                             int groups, float slope, int *__restrict__ label,
+                                                             const unsigned long long *__restrict__ seed) {
+    pdl_wait();
+    pdl_trigger();
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int b = row / R, Cg = C / groups, NV = C / 256;           // NV vectors of 8 channels per lane
+    const uint4 *xr = reinterpret_cast<const uint4 *>(x + (size_t)row * C);
+    const float *st = stats + (size_t)b * groups * 2;
+
+    auto load_y = [&](int vec, float (&y)[8]) {
+        const int c = vec * 8;
+        const int cg = c / Cg;                                       // Cg % 8 == 0: one group per vector
+        const float mean = __ldg(st + cg * 2), rstd = __ldg(st + cg * 2 + 1);
+        const uint4 u = __ldg(xr + vec);
+        const float4 g0 = __ldg(reinterpret_cast<const float4 *>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4 *>(gamma + c) + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(beta + c)), b1 = __ldg(reinterpret_cast<const float4 *>(beta + c) + 1);
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+        const float2 v0 = __bfloat1622float2(h[0]), v1 = __bfloat1622float2(h[1]), v2 = __bfloat1622float2(h[2]),
+                     v3 = __bfloat1622float2(h[3]);
+        y[0] = (v0.x - mean) * rstd * g0.x + b0.x; y[1] = (v0.y - mean) * rstd * g0.y + b0.y;
+        y[2] = (v1.x - mean) * rstd * g0.z + b0.z; y[3] = (v1.y - mean) * rstd * g0.w + b0.w;
+        y[4] = (v2.x - mean) * rstd * g1.x + b1.x; y[5] = (v2.y - mean) * rstd * g1.y + b1.y;
+        y[6] = (v3.x - mean) * rstd * g1.z + b1.z; y[7] = (v3.y - mean) * rstd * g1.w + b1.w;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y[k] = y[k] > 0.f ? y[k] : y[k] * slope;
+    };
+
+    // pass 1: per-lane running max m and s = sum exp(y - m)
+    float m = -INFINITY, ssum = 0.f;
+    for (int i = 0; i < NV; ++i) {
+        float y[8];
+        load_y(lane + 32 * i, y);
+        float vm = y[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) vm = fmaxf(vm, y[k]);
+        if (vm > m) {
+            ssum *= __expf(m - vm);                                  // exp(-inf) = 0 on the first vector
+            m = vm;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ssum += __expf(y[k] - m);
+    }
+    float M = m;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+    const float mine = ssum * __expf(m - M);
+    float incl = mine;                                               // inclusive scan over lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const float total = __shfl_sync(0xffffffffu, incl, 31);
+    const unsigned long long sd = __ldg(seed);
+    const uint4 rnd = philox4x32_10((uint32_t)row, 0u, 0x43415447u, 0u, (uint32_t)sd, (uint32_t)(sd >> 32));
+    const float target = u01(rnd.x) * total;
+    const uint32_t over = __ballot_sync(0xffffffffu, incl > target);
+    const int L = over ? __ffs(over) - 1 : 31;
+    const float resid = target - (__shfl_sync(0xffffffffu, incl, L) - __shfl_sync(0xffffffffu, mine, L));
+
+    // pass 2: lane j re-forms vector (L + 32 j) of the chosen lane's sub-range
+    float e[8], t = 0.f;
+    if (lane < NV) {
+        float y[8];
+        load_y(L + 32 * lane, y);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { e[k] = __expf(y[k] - M); t += e[k]; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) e[k] = 0.f;
+    }
+    float inc2 = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float v = __shfl_up_sync(0xffffffffu, inc2, o);
+        if (lane >= o) inc2 += v;
+    }
+    const uint32_t over2 = __ballot_sync(0xffffffffu, lane < NV && inc2 > resid);
+    const int J = over2 ? __ffs(over2) - 1 : NV - 1;
+    if (lane == J) {
+        const float r2 = resid - (inc2 - t);
+        float run = 0.f;
+        int kk = 7;
+        bool found = false;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {                                // first k whose running sum exceeds r2
+            run += e[k];
+            if (!found && run > r2) { kk = k; found = true; }
+        }
+        label[row] = (L + 32 * J) * 8 + kk;
+    }
+}
 
 // ---- VPT-deep prompted ViT block entry (visual_embedding_deep_prompt, dvae.py:536-576) ---------------------------
 // The reference rebuilds the sequence before every block: x = cat(dropout(prompt_tokens_i).expand(B), x[:, P:]),
@@ -342,8 +467,18 @@ extern "C" int act_gn_rows(const void *x_bf16, const float *gamma, const float *
         ACT_CUDA(launch_k(gn_rows_apply_kernel<1>, dim3((rows + 7) / 8), dim3(256), 0, st, true, x, (const float *)stats,
                           gamma, beta, rows, R, C, groups, slope, (float *)nullptr, noise, label,
                           (const unsigned long long *)nullptr));
-    else if (seed && label)
-        ACT_CUDA(launch_k(gn_rows_apply_kernel<2>, dim3((rows + 7) / 8), dim3(256), 0, st, true, x, (const float *)stats,
-                          gamma, beta, rows, R, C, groups, slope, (float *)nullptr, (const float *)nullptr, label, seed));
+    else if (seed && label) {
+        static const int gumbel_max = [] {                       // ACT_B200_GUMBEL_MAX=1: per-element Gumbel noise + arg-max (A/B)
+            const char *e = std::getenv("ACT_B200_GUMBEL_MAX");
+            return (e && e[0] == '1') ? 1 : 0;
+        }();
+        const int Cg = C / groups;
+        if (!gumbel_max && C % 256 == 0 && C / 256 <= 32 && Cg % 8 == 0)
+            ACT_CUDA(launch_k(gn_rows_sample_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, true, x, (const float *)stats, gamma,
+                              beta, rows, R, C, groups, slope, label, seed));
+        else
+            ACT_CUDA(launch_k(gn_rows_apply_kernel<2>, dim3((rows + 7) / 8), dim3(256), 0, st, true, x, (const float *)stats,
+                              gamma, beta, rows, R, C, groups, slope, (float *)nullptr, (const float *)nullptr, label, seed));
+    }
     return ACT_OK;
 }

@@ -289,8 +289,11 @@ int act_dgcnn_edge_gn(const float *pq, const long long *idx, const float *gamma,
  * layer5, dvae.py:53-56).  stats f32 [B,groups,2] is scratch (mean, rstd).  out_f32 (nullable) [B*R, C] receives the
  * activations; noise + label (nullable pair): label[row] = argmax_c(activation + noise[row,c]) -- the forward value of
  * F.gumbel_softmax(hard=True) (dvae.py:587) without materialising the one-hot.
- * seed (alternative to noise): the gumbel noise -log(-log(u)) is drawn inside the kernel (Philox4x32-10 keyed by *seed,
- * a 64-bit value in DEVICE memory so that a replayed CUDA graph draws fresh noise every step). */
+ * seed (alternative to noise): the sample is drawn inside the kernel from *seed (a 64-bit value in DEVICE memory so that
+ * a replayed CUDA graph draws afresh every step).  argmax_c(a_c + g_c) with i.i.d. standard Gumbel g is distributed as
+ * Categorical(softmax(a)) (Gumbel-max theorem), so for C % 256 == 0, C <= 8192 the label is drawn that way from ONE
+ * Philox uniform per row (two passes over the row, no per-element noise); other widths, or ACT_B200_GUMBEL_MAX=1, draw
+ * -log(-log(u)) per element (Philox4x32-10) and take the arg-max. */
 int act_gn_rows(const void *x_bf16, const float *gamma, const float *beta, int B, int R, int C, int groups, float eps,
                 float slope, float *stats, float *out_f32, const float *noise, const unsigned long long *seed,
                 int *label, void *stream);

@@ -110,6 +110,37 @@ def test_teacher_features_vs_oracle_and_reference_golden(golden):
     assert rel(want, g["feature"]) < 1e-3                        # the oracle itself reproduces the reference golden
 
 
+def test_categorical_sample_matches_softmax_at_every_position():
+    """The product path draws the hard gumbel-softmax sample as Categorical(softmax(logits)) (Gumbel-max theorem; one
+    uniform per row, csrc/teacher.cu gn_rows_sample_kernel).  Classes placed at every kind of position of the kernel's
+    (lane, vector, element) traversal, graded probabilities: empirical frequencies within 4.5 sigma over 16384 rows."""
+    B, R, C = 16, 1024, 8192
+    h = torch.zeros(B * R, C, device="cuda", dtype=torch.bfloat16)           # GroupNorm(const) = 0 -> logits = leaky(beta)
+    gam = torch.ones(C, device="cuda")
+    hot = [0, 7, 8, 255, 256, 263, 4097, 6000, 8184, 8191]
+    bet = torch.zeros(C, device="cuda")                                      # uniform background (8182 classes, logit 0)
+    vals = torch.linspace(7.0, 9.5, len(hot))
+    for c, v in zip(hot, vals):
+        bet[c] = v
+    logits = torch.where(bet > 0, bet, bet * 0.2)
+    p = torch.softmax(logits.double(), 0)
+    lab = torch.cat([ops.gn_rows(h, gam, bet, B, R, 1e-5, 0.2, seed=torch.tensor([s], dtype=torch.int64, device="cuda"))
+                     for s in (1, 2)])
+    n = lab.numel()
+    assert int(lab.min()) >= 0 and int(lab.max()) < C
+    freq = torch.bincount(lab.long(), minlength=C).double().cpu() / n
+    for c in hot:
+        sigma = float((p[c] * (1 - p[c]) / n).sqrt())
+        assert abs(float(freq[c]) - float(p[c])) < 4.5 * sigma + 1e-4, (c, float(freq[c]), float(p[c]))
+    bg = torch.ones(C, dtype=torch.bool)
+    bg[hot] = False
+    pb, fb = float(p[bg].sum()), float(freq[bg].sum())
+    assert abs(fb - pb) < 4.5 * (pb * (1 - pb) / n) ** 0.5 + 1e-4, (fb, pb)
+    # the background mass spreads over the whole range (all lanes / vectors / elements are reachable)
+    bidx = lab[~torch.isin(lab, torch.tensor(hot, device=lab.device, dtype=lab.dtype))].long()
+    assert bidx.numel() > 100 and (bidx % 8).unique().numel() == 8 and ((bidx // 8) % 32).unique().numel() == 32
+
+
 def test_in_kernel_gumbel_and_prompt_dropout_draws():
     """The product path draws the gumbel noise and the prompt-dropout masks inside the kernels (Philox keyed by a
     device seed).  Distributional checks: P(argmax = c) follows softmax(logits); dropout keeps 90 % and rescales."""
