@@ -40,6 +40,7 @@ __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, 
 // ---------------------------------------------------------------------------------------- (a) edge layer, forward
 // pq f32 [B*G, 2*Cp] (P | Q); idx i64 [B,G,4]; out f32 (row pitch ldo); argj u8 [B*G, Cp]; stats f32 [B,groups,2].
 // grid (groups, B), 256 threads: warp w handles token rows g = w, w+8, ...; lanes stride the group's channels.
+template <bool VEC>
 __global__ void __launch_bounds__(256) dgcnn_edge_train_fwd_kernel(const float *__restrict__ pq,
                                                                    const long long *__restrict__ idx,
                                                                    const float *__restrict__ gamma,
@@ -61,13 +62,26 @@ __global__ void __launch_bounds__(256) dgcnn_edge_train_fwd_kernel(const float *
         const float *pn[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) pn[j] = P + (size_t)__ldg(idx + ((size_t)b * G + g) * 4 + j) * 2 * Cp + c_lo;
-        for (int c = lane; c < Cg; c += 32) {
-            const float qv = __ldg(q + c);
+        if (VEC) {                                                   // 4 channels (16 B) per lane and load
+            for (int c = lane * 4; c < Cg; c += 128) {
+                const float4 qv = __ldg(reinterpret_cast<const float4 *>(q + c));
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float y = __ldg(pn[j] + c) + qv;
-                s1 += y;
-                s2 = fmaf(y, y, s2);
+                for (int j = 0; j < 4; ++j) {
+                    const float4 pv = __ldg(reinterpret_cast<const float4 *>(pn[j] + c));
+                    const float y0 = pv.x + qv.x, y1 = pv.y + qv.y, y2 = pv.z + qv.z, y3 = pv.w + qv.w;
+                    s1 += (y0 + y1) + (y2 + y3);
+                    s2 = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, s2))));
+                }
+            }
+        } else {
+            for (int c = lane; c < Cg; c += 32) {
+                const float qv = __ldg(q + c);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float y = __ldg(pn[j] + c) + qv;
+                    s1 += y;
+                    s2 = fmaf(y, y, s2);
+                }
             }
         }
     }
@@ -86,19 +100,45 @@ __global__ void __launch_bounds__(256) dgcnn_edge_train_fwd_kernel(const float *
         for (int j = 0; j < 4; ++j) pn[j] = P + (size_t)__ldg(idx + ((size_t)b * G + g) * 4 + j) * 2 * Cp + c_lo;
         float *o = out + ((size_t)b * G + g) * ldo + c_lo;
         unsigned char *aj = argj + ((size_t)b * G + g) * Cp + c_lo;
-        for (int c = lane; c < Cg; c += 32) {
-            const float qv = __ldg(q + c);
-            const float ga = __ldg(gamma + c_lo + c) * rstd, be = __ldg(beta + c_lo + c);
-            float best = -INFINITY;
-            int bj = 0;
+        if (VEC) {
+            for (int c = lane * 4; c < Cg; c += 128) {
+                const float4 qv = __ldg(reinterpret_cast<const float4 *>(q + c));
+                const float4 gm = __ldg(reinterpret_cast<const float4 *>(gamma + c_lo + c));
+                const float4 bt = __ldg(reinterpret_cast<const float4 *>(beta + c_lo + c));
+                const float ga[4] = {gm.x * rstd, gm.y * rstd, gm.z * rstd, gm.w * rstd};
+                const float be[4] = {bt.x, bt.y, bt.z, bt.w}, qq[4] = {qv.x, qv.y, qv.z, qv.w};
+                float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                int bj[4] = {0, 0, 0, 0};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float y = (__ldg(pn[j] + c) + qv - mean) * ga + be;
-                y = y > 0.f ? y : y * slope;
-                if (y > best) { best = y; bj = j; }         // first maximum wins
+                for (int j = 0; j < 4; ++j) {
+                    const float4 pv = __ldg(reinterpret_cast<const float4 *>(pn[j] + c));
+                    const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float y = (pp[k] + qq[k] - mean) * ga[k] + be[k];
+                        y = y > 0.f ? y : y * slope;
+                        if (y > best[k]) { best[k] = y; bj[k] = j; }        // first maximum wins
+                    }
+                }
+                *reinterpret_cast<float4 *>(o + c) = make_float4(best[0], best[1], best[2], best[3]);
+                *reinterpret_cast<uchar4 *>(aj + c) = make_uchar4((unsigned char)bj[0], (unsigned char)bj[1],
+                                                                  (unsigned char)bj[2], (unsigned char)bj[3]);
             }
-            o[c] = best;
-            aj[c] = (unsigned char)bj;
+        } else {
+            for (int c = lane; c < Cg; c += 32) {
+                const float qv = __ldg(q + c);
+                const float ga = __ldg(gamma + c_lo + c) * rstd, be = __ldg(beta + c_lo + c);
+                float best = -INFINITY;
+                int bj = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float y = (__ldg(pn[j] + c) + qv - mean) * ga + be;
+                    y = y > 0.f ? y : y * slope;
+                    if (y > best) { best = y; bj = j; }         // first maximum wins
+                }
+                o[c] = best;
+                aj[c] = (unsigned char)bj;
+            }
         }
     }
 }
@@ -120,11 +160,12 @@ __global__ void __launch_bounds__(256) dgcnn_edge_train_bwd_reduce_kernel(
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float *P = pq + (size_t)b * G * 2 * Cp;
     const float mean = __ldg(stats + ((size_t)b * groups + cg) * 2), rstd = __ldg(stats + ((size_t)b * groups + cg) * 2 + 1);
+    // a lane owns channels lane * 4 + 128 * v + k (v < 2, k < 4): 16-byte loads of q / dout / the four neighbour rows
     float dg[8], db[8], ga[8], be[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         dg[i] = db[i] = 0.f;
-        const int c = lane + 32 * i;
+        const int c = lane * 4 + 128 * (i >> 2) + (i & 3);
         ga[i] = c < Cg ? __ldg(gamma + c_lo + c) : 0.f;
         be[i] = c < Cg ? __ldg(beta + c_lo + c) : 0.f;
     }
@@ -135,20 +176,40 @@ __global__ void __launch_bounds__(256) dgcnn_edge_train_bwd_reduce_kernel(
         const long long *ip = idx + row * 4;
         const unsigned char *aj = argj + row * Cp + c_lo;
         const float *dr = dout + row * ldd + c_lo;
+        const float *pn[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = lane + 32 * i;
+        for (int j = 0; j < 4; ++j) pn[j] = P + (size_t)__ldg(ip + j) * 2 * Cp + c_lo;
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            const int c = lane * 4 + 128 * v;
             if (c < Cg) {
-                const int j = aj[c];
-                const float e = __ldg(P + (size_t)__ldg(ip + j) * 2 * Cp + c_lo + c) + __ldg(q + c);
-                const float xh = (e - mean) * rstd;
-                const float y = fmaf(xh, ga[i], be[i]);
-                const float dy = __ldg(dr + c) * (y > 0.f ? 1.f : slope);
-                dg[i] = fmaf(dy, xh, dg[i]);
-                db[i] += dy;
-                const float dxh = dy * ga[i];
-                s1 += dxh;
-                s2 = fmaf(dxh, xh, s2);
+                const uchar4 a4 = *reinterpret_cast<const uchar4 *>(aj + c);
+                const float4 q4 = __ldg(reinterpret_cast<const float4 *>(q + c));
+                const float4 d4 = __ldg(reinterpret_cast<const float4 *>(dr + c));
+                float4 p4[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) p4[j] = __ldg(reinterpret_cast<const float4 *>(pn[j] + c));
+                const int av[4] = {a4.x, a4.y, a4.z, a4.w};
+                const float qv[4] = {q4.x, q4.y, q4.z, q4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = v * 4 + k;
+                    float pv = k == 0 ? p4[0].x : (k == 1 ? p4[0].y : (k == 2 ? p4[0].z : p4[0].w));
+#pragma unroll
+                    for (int j = 1; j < 4; ++j) {
+                        const float cand = k == 0 ? p4[j].x : (k == 1 ? p4[j].y : (k == 2 ? p4[j].z : p4[j].w));
+                        pv = av[k] == j ? cand : pv;
+                    }
+                    const float e = pv + qv[k];
+                    const float xh = (e - mean) * rstd;
+                    const float y = fmaf(xh, ga[i], be[i]);
+                    const float dy = dv[k] * (y > 0.f ? 1.f : slope);
+                    dg[i] = fmaf(dy, xh, dg[i]);
+                    db[i] += dy;
+                    const float dxh = dy * ga[i];
+                    s1 += dxh;
+                    s2 = fmaf(dxh, xh, s2);
+                }
             }
         }
     }
@@ -161,8 +222,8 @@ __global__ void __launch_bounds__(256) dgcnn_edge_train_bwd_reduce_kernel(
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        part[0][warp][lane + 32 * i] = dg[i];
-        part[1][warp][lane + 32 * i] = db[i];
+        part[0][warp][lane * 4 + 128 * (i >> 2) + (i & 3)] = dg[i];
+        part[1][warp][lane * 4 + 128 * (i >> 2) + (i & 3)] = db[i];
     }
     __syncthreads();
     const int c = threadIdx.x;
@@ -386,8 +447,16 @@ extern "C" int act_dgcnn_edge_gn_train_fwd(const float *pq, const long long *idx
     if (!pq || !idx || !gamma || !beta || !out || !argj || !stats || B <= 0 || G <= 0 || Cp <= 0 || groups <= 0)
         return ACT_EINVAL;
     if (kn != 4 || Cp % groups) return ACT_EUNSUPPORTED;
-    ACT_CUDA(launch_k(dgcnn_edge_train_fwd_kernel, dim3(groups, B), dim3(256), 0, (cudaStream_t)stream, true, pq, idx,
+const bool vec = ((Cp / groups) % 4 == 0) && (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(pq) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((reinterpret_cast<uintptr_t>(argj) & 3) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(gamma) & 15) == 0) && ((reinterpret_cast<uintptr_t>(beta) & 15) == 0);
+    if (vec) {
+            ACT_CUDA(launch_k(dgcnn_edge_train_fwd_kernel<true>, dim3(groups, B), dim3(256), 0, (cudaStream_t)stream, true, pq, idx,
                       gamma, beta, G, Cp, groups, eps, slope, out, ldo, argj, stats));
+    } else {
+            ACT_CUDA(launch_k(dgcnn_edge_train_fwd_kernel<false>, dim3(groups, B), dim3(256), 0, (cudaStream_t)stream, true, pq, idx,
+                      gamma, beta, G, Cp, groups, eps, slope, out, ldo, argj, stats));
+    }
     return ACT_OK;
 }
 

@@ -41,7 +41,8 @@ __device__ __forceinline__ float gumbel_from(uint32_t x) {
 
 // pq: f32 [B*G, 2*Cp] (P | Q);  idx: i64 [B, G, KN] neighbour indices within the sample;  out: bf16, row pitch ldo.
 // grid (groups, B), 256 threads: warp w handles token rows g = w, w+8, ...; lanes stride the group's channels.
-template <int KN>
+// VEC: 4 channels (16 B) per lane and load -- Cg % 4 == 0, 16-byte aligned pq rows, 8-byte aligned output slots.
+template <int KN, bool VEC>
 __global__ void __launch_bounds__(256) dgcnn_edge_gn_kernel(const float *__restrict__ pq,
                                                             const long long *__restrict__ idx,
                                                             const float *__restrict__ gamma,
@@ -55,19 +56,31 @@ __global__ void __launch_bounds__(256) dgcnn_edge_gn_kernel(const float *__restr
     const int Cg = Cp / groups, c_lo = cg * Cg;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float *P = pq + (size_t)b * G * 2 * Cp;
+    constexpr int W = VEC ? 4 : 1;
     float s1 = 0.f, s2 = 0.f;
     for (int g = warp; g < G; g += 8) {
         const float *q = P + (size_t)g * 2 * Cp + Cp + c_lo;
         const float *pn[KN];
 #pragma unroll
         for (int j = 0; j < KN; ++j) pn[j] = P + (size_t)__ldg(idx + ((size_t)b * G + g) * KN + j) * 2 * Cp + c_lo;
-        for (int c = lane; c < Cg; c += 32) {
-            const float qv = __ldg(q + c);
+        for (int c = lane * W; c < Cg; c += 32 * W) {
+            if (VEC) {
+                const float4 qv = __ldg(reinterpret_cast<const float4 *>(q + c));
 #pragma unroll
-            for (int j = 0; j < KN; ++j) {
-                const float y = __ldg(pn[j] + c) + qv;
-                s1 += y;
-                s2 = fmaf(y, y, s2);
+                for (int j = 0; j < KN; ++j) {
+                    const float4 pv = __ldg(reinterpret_cast<const float4 *>(pn[j] + c));
+                    const float y0 = pv.x + qv.x, y1 = pv.y + qv.y, y2 = pv.z + qv.z, y3 = pv.w + qv.w;
+                    s1 += (y0 + y1) + (y2 + y3);
+                    s2 = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, s2))));
+                }
+            } else {
+                const float qv = __ldg(q + c);
+#pragma unroll
+                for (int j = 0; j < KN; ++j) {
+                    const float y = __ldg(pn[j] + c) + qv;
+                    s1 += y;
+                    s2 = fmaf(y, y, s2);
+                }
             }
         }
     }
@@ -81,17 +94,42 @@ __global__ void __launch_bounds__(256) dgcnn_edge_gn_kernel(const float *__restr
 #pragma unroll
         for (int j = 0; j < KN; ++j) pn[j] = P + (size_t)__ldg(idx + ((size_t)b * G + g) * KN + j) * 2 * Cp + c_lo;
         __nv_bfloat16 *o = out + ((size_t)b * G + g) * ldo + c_lo;
-        for (int c = lane; c < Cg; c += 32) {
-            const float qv = __ldg(q + c);
-            const float ga = __ldg(gamma + c_lo + c) * rstd, be = __ldg(beta + c_lo + c);
-            float best = -INFINITY;
+        for (int c = lane * W; c < Cg; c += 32 * W) {
+            if (VEC) {
+                const float4 qv = __ldg(reinterpret_cast<const float4 *>(q + c));
+                const float4 gm = __ldg(reinterpret_cast<const float4 *>(gamma + c_lo + c));
+                const float4 be = __ldg(reinterpret_cast<const float4 *>(beta + c_lo + c));
+                const float ga[4] = {gm.x * rstd, gm.y * rstd, gm.z * rstd, gm.w * rstd};
+                const float bb[4] = {be.x, be.y, be.z, be.w};
+                const float qq[4] = {qv.x, qv.y, qv.z, qv.w};
+                float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int j = 0; j < KN; ++j) {
-                float y = (__ldg(pn[j] + c) + qv - mean) * ga + be;
-                y = y > 0.f ? y : y * slope;
-                best = fmaxf(best, y);
+                for (int j = 0; j < KN; ++j) {
+                    const float4 pv = __ldg(reinterpret_cast<const float4 *>(pn[j] + c));
+                    const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float y = (pp[k] + qq[k] - mean) * ga[k] + bb[k];
+                        y = y > 0.f ? y : y * slope;
+                        best[k] = fmaxf(best[k], y);
+                    }
+                }
+                uint2 pk;
+                *reinterpret_cast<__nv_bfloat162 *>(&pk.x) = __floats2bfloat162_rn(best[0], best[1]);
+                *reinterpret_cast<__nv_bfloat162 *>(&pk.y) = __floats2bfloat162_rn(best[2], best[3]);
+                *reinterpret_cast<uint2 *>(o + c) = pk;
+            } else {
+                const float qv = __ldg(q + c);
+                const float ga = __ldg(gamma + c_lo + c) * rstd, be = __ldg(beta + c_lo + c);
+                float best = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < KN; ++j) {
+                    float y = (__ldg(pn[j] + c) + qv - mean) * ga + be;
+                    y = y > 0.f ? y : y * slope;
+                    best = fmaxf(best, y);
+                }
+                o[c] = __float2bfloat16_rn(best);
             }
-            o[c] = __float2bfloat16_rn(best);
         }
     }
 }
@@ -444,8 +482,15 @@ extern "C" int act_dgcnn_edge_gn(const float *pq, const long long *idx, const fl
     using namespace act;
     if (!pq || !idx || !gamma || !beta || !out_bf16 || B <= 0 || G <= 0 || Cp <= 0 || groups <= 0) return ACT_EINVAL;
     if (kn != 4 || Cp % groups) return ACT_EUNSUPPORTED;
-    ACT_CUDA(launch_k(dgcnn_edge_gn_kernel<4>, dim3(groups, B), dim3(256), 0, (cudaStream_t)stream, true, pq, idx, gamma,
-                      beta, G, Cp, groups, eps, slope, reinterpret_cast<__nv_bfloat16 *>(out_bf16), ldo));
+    const bool vec = ((Cp / groups) % 4 == 0) && ((reinterpret_cast<uintptr_t>(pq) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0) && (ldo % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(gamma) & 15) == 0) && ((reinterpret_cast<uintptr_t>(beta) & 15) == 0);
+    if (vec)
+        ACT_CUDA(launch_k(dgcnn_edge_gn_kernel<4, true>, dim3(groups, B), dim3(256), 0, (cudaStream_t)stream, true, pq, idx,
+                          gamma, beta, G, Cp, groups, eps, slope, reinterpret_cast<__nv_bfloat16 *>(out_bf16), ldo));
+    else
+        ACT_CUDA(launch_k(dgcnn_edge_gn_kernel<4, false>, dim3(groups, B), dim3(256), 0, (cudaStream_t)stream, true, pq, idx,
+                          gamma, beta, G, Cp, groups, eps, slope, reinterpret_cast<__nv_bfloat16 *>(out_bf16), ldo));
     return ACT_OK;
 }
 
