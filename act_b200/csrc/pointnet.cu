@@ -95,18 +95,22 @@ __global__ void __launch_bounds__(256) pn_conv1_kernel(const float *__restrict__
                                                        T *__restrict__ out) {
     pdl_wait();
     pdl_trigger();
-    __shared__ float sW[128 * 3], sb[128];
-    for (int i = threadIdx.x; i < 384; i += 256) sW[i] = __ldg(W + i);
-    for (int i = threadIdx.x; i < 128; i += 256) sb[i] = __ldg(b + i);
-    __syncthreads();
+    // a thread keeps ITS 8 channels' weights in registers for every row it visits (re-reading them from shared memory per
+    // row made the kernel LDS-bound: 32 bank-conflicting LDS per 16-byte store)
     const int c0 = (threadIdx.x & 15) * 8;
+    float w[8][3], bb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        w[j][0] = __ldg(W + c * 3); w[j][1] = __ldg(W + c * 3 + 1); w[j][2] = __ldg(W + c * 3 + 2);
+        bb[j] = __ldg(b + c);
+    }
     for (long long m = blockIdx.x * 16LL + (threadIdx.x >> 4); m < M; m += gridDim.x * 16LL) {
         const float x = __ldg(p + m * 3), y = __ldg(p + m * 3 + 1), z = __ldg(p + m * 3 + 2);
         float f[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int c = c0 + j;
-            float v = fmaf(sW[c * 3 + 2], z, fmaf(sW[c * 3 + 1], y, fmaf(sW[c * 3], x, sb[c])));
+            float v = fmaf(w[j][2], z, fmaf(w[j][1], y, fmaf(w[j][0], x, bb[j])));
             f[j] = relu ? fmaxf(v, 0.f) : v;
         }
         V8<T>::st(out + m * 128 + c0, f);
