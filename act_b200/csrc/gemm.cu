@@ -1260,8 +1260,23 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
     if (persistent == 1 && auto_persist && block_n == 0 && !a_mn_major && !b_mn_major && !gmode && splits == 1 &&
         (mode == E_PLAIN || mode == E_RESID || mode == E_STATS) && pair_tiles >= 74 && act::pair_enabled())
         persistent = 2;
+    // fused max-over-32-rows GEMMs with a long K (the mini-PointNet's conv4: K = 512): 128 x 128 single-CTA tiles re-read
+    // the A tile once per column tile and B once per tile -- 256 KB of L2 -> SM traffic per 128 x 128 outputs, which is
+    // what bounds them.  CTA-pair tiles (256 x 384 when N % 384 == 0, else 256 x 256) cut it 2.5x.
+    // ACT_B200_PAIR_GMAX: 0 = never, 1 = K >= 512 (default), 2 = any K.
+    static const int pair_gmax = [] {
+        const char *e = std::getenv("ACT_B200_PAIR_GMAX");
+        return (e && e[0] >= '0' && e[0] <= '9') ? (e[0] - '0') : 1;
+    }();
+    bool pair_gmax_sel = false;
+    if (persistent == 1 && auto_persist && block_n == 0 && !a_mn_major && !b_mn_major && gmode && mode == E_GMAX &&
+        splits == 1 && pair_tiles >= 74 && act::pair_enabled() >= 2 && pair_gmax && (pair_gmax >= 2 || K >= 512) &&
+        (N % 384 == 0 || N % 256 == 0)) {
+        persistent = 2;
+        pair_gmax_sel = true;
+    }
     const bool pair = persistent == 2;
-    if (pair && (a_mn_major || b_mn_major || gmode || splits != 1 || block_n != 0)) return ACT_EUNSUPPORTED;
+    if (pair && (a_mn_major || b_mn_major || (gmode && !pair_gmax_sel) || splits != 1 || block_n != 0)) return ACT_EUNSUPPORTED;
     int BN;
     bool wide384 = false;        // 128 x 384 tiles (two 192-wide MMAs sharing A): narrow outputs with a long K, one round
     bool pair384 = false;        // CTA-pair 256 x 384 tiles: narrow outputs with a long K that fit ONE round of pairs
@@ -1276,6 +1291,11 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
             pair384 = true;
             BN = 96;             // two 192-wide MMAs per k-step: 96 B rows per CTA and MMA
         }
+        if (pair_gmax_sel && N % 384 == 0 && pair_gmax != 3) {      // many rounds of single-buffered 256 x 384 tiles
+            pair384 = true;
+            BN = 96;
+        }
+        if (pair_gmax_sel && pair_gmax == 3 && N % 128 == 0 && N % 256 != 0) BN = 64;   // 256 x 128 tiles, double-buffered (A/B)
     } else if (persistent && block_n == 0 && !a_mn_major && !b_mn_major && !gmode && splits == 1 && N % 384 == 0 && K >= 512 &&
         (long long)((M + 127) / 128) * (N / 384) <= 148 && (long long)((M + 127) / 128) * (N / 384) >= 96) {
         wide384 = true;
@@ -1311,10 +1331,13 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
             return launch_gemm<BN_, (LAY_ & 2) != 0, (LAY_ & 1) != 0, MODE_>(ta, tb, epi, M, N, K, splits, st);       \
     }
     if (pair && pair384) {
+        if (mode == E_GMAX) return launch_gemm_pair<E_GMAX, 192, 2>(ta, tb, epi, M, N, K, st);
         if (mode == E_RESID) return launch_gemm_pair<E_RESID, 192, 2>(ta, tb, epi, M, N, K, st);
         return launch_gemm_pair<E_PLAIN, 192, 2>(ta, tb, epi, M, N, K, st);
     }
     if (pair) {
+        if (mode == E_GMAX && BN == 64) return launch_gemm_pair<E_GMAX, 128, 1>(ta, tb, epi, M, N, K, st);
+        if (mode == E_GMAX) return launch_gemm_pair<E_GMAX>(ta, tb, epi, M, N, K, st);
         if (mode == E_PLAIN) return launch_gemm_pair<E_PLAIN>(ta, tb, epi, M, N, K, st);
         if (mode == E_GELU) return launch_gemm_pair<E_GELU>(ta, tb, epi, M, N, K, st);
         if (mode == E_RESID) return launch_gemm_pair<E_RESID>(ta, tb, epi, M, N, K, st);

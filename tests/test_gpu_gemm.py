@@ -129,7 +129,7 @@ def test_gemm_persistent_splitk_wgrad():
         assert err <= 1e-4 * scale, (err, scale)
 
 
-@pytest.mark.parametrize("persistent", [0, 1])
+@pytest.mark.parametrize("persistent", [0, 1, -1])            # -1: automatic choice = the CTA-pair 256 x 384 tiles here
 def test_gemm_fused_group_max(persistent):
     """Fused max over each 32 consecutive rows on the fp32 accumulators (+ arg-max), with and without `out`."""
     torch.manual_seed(6)
@@ -152,6 +152,11 @@ def test_gemm_fused_group_max(persistent):
     gf2 = torch.zeros(G, N, device="cuda")
     assert ops.gemm(a, w, bias=bias, gmax_f32=gf2, no_out=True, persistent=persistent) is None
     assert torch.equal(gf2, gf)
+    # no output tile, every fused-max output at once: same bits, same arg-max
+    gf3, gb3 = torch.zeros(G, N, device="cuda"), torch.zeros(G, N, dtype=torch.bfloat16, device="cuda")
+    ga3 = torch.full((G, N), 255, dtype=torch.uint8, device="cuda")
+    ops.gemm(a, w, bias=bias, gmax_f32=gf3, gmax_bf16=gb3, garg=ga3, no_out=True, persistent=persistent)
+    assert torch.equal(gf3, gf) and torch.equal(gb3, gb) and torch.equal(ga3, ga)
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
