@@ -114,6 +114,36 @@ __global__ void __launch_bounds__(256) pos_mlp1_bwd_kernel(const void *__restric
     }
 }
 
+// ---- block masking (mask_type 'block', /root/reference/models/act.py:215-243 _mask_center_block) ------------------------
+// Per cloud: the num_mask centres nearest (Euclidean) to centre index[b] are masked -- the reference's
+// argsort(norm(center[index] - center))[:num_mask].  index[b] is drawn on the host (Python's `random`, like the reference) and
+// staged; ranks by counting (stable in the group index), one CTA per cloud, distances in shared memory.  G <= 4096.
+__global__ void __launch_bounds__(128) mask_block_kernel(const float *__restrict__ center, const int *__restrict__ index,
+                                                         int G, int num_mask, uint8_t *__restrict__ mask) {
+    __shared__ float sd[4096];
+    pdl_wait();
+    pdl_trigger();
+    const int b = blockIdx.x;
+    const float *c = center + (size_t)b * G * 3;
+    int i0 = index[b];
+    i0 = i0 < 0 ? 0 : (i0 >= G ? G - 1 : i0);
+    const float x0 = c[i0 * 3], y0 = c[i0 * 3 + 1], z0 = c[i0 * 3 + 2];
+    for (int g = threadIdx.x; g < G; g += 128) {
+        const float dx = x0 - c[g * 3], dy = y0 - c[g * 3 + 1], dz = z0 - c[g * 3 + 2];
+        sd[g] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += 128) {
+        const float d = sd[g];
+        int rank = 0;
+        for (int h = 0; h < G; ++h) {
+            const float e = sd[h];
+            rank += (e < d || (e == d && h < g)) ? 1 : 0;
+        }
+        mask[(size_t)b * G + g] = rank < num_mask ? 1 : 0;
+    }
+}
+
 // ---- order[b, :] = indices of the visible groups (mask == 0) in original order, then of the masked ones ---------------
 // (== torch.argsort(mask, stable=True)); one warp per cloud.
 __global__ void __launch_bounds__(256) mask_order_kernel(const uint8_t *__restrict__ mask, int B, int G,
@@ -328,6 +358,16 @@ extern "C" int act_pos_mlp1_bwd(const void *da, int da_fp32, const float *x, con
     const int grid = (R + 63) / 64 < 148 * 4 ? (R + 63) / 64 : 148 * 4;      // 16 row-lanes x 4 rows per CTA
     if (da_fp32) ACT_CUDA(launch_k(pos_mlp1_bwd_kernel<true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, true, da, x, W, b, R, dW, db));
     else ACT_CUDA(launch_k(pos_mlp1_bwd_kernel<false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, true, da, x, W, b, R, dW, db));
+    return ACT_OK;
+}
+
+extern "C" int act_mask_block(const float *center, const int *index, int B, int G, int num_mask, uint8_t *mask,
+                              void *stream) {
+    using namespace act;
+    if (!center || !index || !mask || B < 0 || G <= 0 || num_mask < 0 || num_mask > G) return ACT_EINVAL;
+    if (G > 4096) return ACT_EUNSUPPORTED;
+    if (B == 0) return ACT_OK;
+    ACT_CUDA(launch_k(mask_block_kernel, dim3(B), dim3(128), 0, (cudaStream_t)stream, true, center, index, G, num_mask, mask));
     return ACT_OK;
 }
 

@@ -108,6 +108,52 @@ __global__ void __launch_bounds__(256) adamw_kernel(float *__restrict__ p, const
     }
 }
 
+// ---- element-wise distillation losses (config.loss = l2 / smoothl1, /root/reference/models/act.py:1188-1191, 1255-1256):
+// nn.MSELoss / nn.SmoothL1Loss (beta = 1) with reduction 'mean' over every element of [B, num_mask, C]; loss and
+// d loss / d student in one pass.  Per-CTA partial sums, added in index order by the last CTA to finish (deterministic).
+__global__ void __launch_bounds__(256) pointwise_loss_kernel(const float *__restrict__ s, const float *__restrict__ t,
+                                                             long long n, int kind, float *__restrict__ partial,
+                                                             unsigned int *__restrict__ counter, float *__restrict__ loss,
+                                                             float *__restrict__ grad) {
+    __shared__ float red[8];
+    __shared__ bool last;
+    const float inv_n = 1.f / (float)n;
+    float acc = 0.f;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+        const float d = s[i] - __ldg(t + i);
+        float l, g;
+        if (kind == 0) {                 // l2
+            l = d * d;
+            g = 2.f * d;
+        } else {                         // smooth l1, beta = 1
+            const float a = fabsf(d);
+            l = a < 1.f ? 0.5f * d * d : a - 0.5f;
+            g = a < 1.f ? d : (d > 0.f ? 1.f : -1.f);
+        }
+        acc += l;
+        if (grad) grad[i] = g * inv_n;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tsum = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tsum += red[w];
+        partial[blockIdx.x] = tsum;
+        __threadfence();
+        last = atomicAdd(counter, 1u) == gridDim.x - 1;
+        if (last) {
+            __threadfence();
+            float tot = 0.f;
+            for (unsigned i = 0; i < gridDim.x; ++i) tot += reinterpret_cast<volatile float *>(partial)[i];
+            *loss = tot * inv_n;
+            *counter = 0u;
+        }
+    }
+}
+
 // dst[i] += src[i]  (tiny per-channel gradient pieces: BatchNorm dgamma / dbeta into the flat gradient buffer)
 __global__ void __launch_bounds__(256) accumulate_kernel(float *__restrict__ dst, const float *__restrict__ src, long long n) {
     for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) dst[i] += __ldg(src + i);
@@ -192,6 +238,18 @@ extern "C" int act_adamw_bf16grad(float *param, const void *grad_bf16, float *ex
     adamw_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad_bf16, exp_avg, exp_avg_sq,
                                                                       reinterpret_cast<__nv_bfloat16 *>(shadow_bf16), n,
                                                                       n_decay, hyper);
+    ACT_CHECK_LAUNCH();
+    return ACT_OK;
+}
+
+extern "C" int act_pointwise_loss(const float *student, const float *teacher, long long n, int kind, float *partial,
+                                  unsigned int *counter, float *loss, float *grad_student, void *stream) {
+    using namespace act;
+    if (!student || !teacher || !partial || !counter || !loss || n <= 0 || (kind != 0 && kind != 1)) return ACT_EINVAL;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 256) blocks = 256;      // partial holds 256 floats
+    pointwise_loss_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(student, teacher, n, kind, partial, counter, loss,
+                                                                         grad_student);
     ACT_CHECK_LAUNCH();
     return ACT_OK;
 }

@@ -40,6 +40,8 @@ class _StateSnapshot:
                     seen.add(b.data_ptr())
                     self.bufs.append((b, b.clone()))
         self.np_state = np.random.get_state()
+        import random
+        self.py_state = random.getstate()                      # block masking draws from Python's `random`
         self.cpu_rng = torch.get_rng_state()
         self.cuda_rng = torch.cuda.get_rng_state(dev)
 
@@ -55,6 +57,8 @@ class _StateSnapshot:
             for b, saved in self.bufs:
                 b.copy_(saved)
         self.np.random.set_state(self.np_state)
+        import random
+        random.setstate(self.py_state)
         torch.set_rng_state(self.cpu_rng)
         torch.cuda.set_rng_state(self.cuda_rng, self.dev)
 
@@ -100,6 +104,13 @@ class PretrainStep:
         # reference's host loop of B numpy shuffles (act.py:255-264).  Same distribution, not the reference's random stream:
         # off by default, so that a seeded run masks the same groups as the reference does.
         self.device_mask = bool(device_mask)
+        # mask_type 'block' (act.py:215-243): the mask depends on the centres, so it is formed inside the step from the
+        # random centre indices, which are drawn on the host with Python's `random` like the reference and staged here
+        enc = getattr(model, "ACT_encoder", None)
+        self.block_mask = getattr(enc, "mask_type", "rand") == "block"
+        if self.block_mask:
+            self._block_idx = torch.zeros(batch, dtype=torch.int32, device=self.dev)
+            enc.block_index = self._block_idx
         self.use_graph = use_graph
         self.graph = None
         self.graph_b = None
@@ -118,6 +129,8 @@ class PretrainStep:
         self.loss.copy_(loss.detach())
 
     def _mask(self):
+        if self.block_mask:
+            return None                              # formed inside the encoder from the staged indices
         if self.device_mask:
             return ops.mask_rand(self._seeds[2:], self.B, self.G, int(self.mask_ratio * self.G))
         return self.mask
@@ -151,7 +164,11 @@ class PretrainStep:
         self._student = None
 
     def _host_prologue(self, points, hyper=True):
-        m = None if self.device_mask else mask_center_rand(self.B, self.G, self.mask_ratio, "cpu")
+        m = None if (self.device_mask or self.block_mask) else mask_center_rand(self.B, self.G, self.mask_ratio, "cpu")
+        if self.block_mask:
+            import random
+            idx = torch.tensor([random.randint(0, self.G - 1) for _ in range(self.B)], dtype=torch.int32)
+            self._block_idx.copy_(idx.pin_memory(), non_blocking=True)
         # a FRESH pinned staging tensor per step: the host runs many replays ahead of the GPU, and a reused staging buffer
         # would be overwritten before its asynchronous copy has executed (torch's caching host allocator recycles a
         # pinned block only after the copies recorded on it have completed)

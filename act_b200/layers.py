@@ -899,6 +899,26 @@ class CosineLossFn(torch.autograd.Function):
         return ops.scale_by_(grad, dloss.reshape(1)).view(ctx.shape), None
 
 
+class PointwiseLossFn(torch.autograd.Function):
+    """config.loss = 'l2' / 'smoothl1' (act.py:1188-1191, 1255-1256): nn.MSELoss / nn.SmoothL1Loss, reduction 'mean'."""
+
+    @staticmethod
+    def forward(ctx, student, teacher, kind):
+        loss, grad = ops.pointwise_loss(student, teacher, kind, want_grad=True)
+        ctx.save_for_backward(grad)
+        ctx.shape = student.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (grad,) = ctx.saved_tensors
+        return ops.scale_by_(grad, dloss.reshape(1)).view(ctx.shape), None, None
+
+
+def pointwise_loss(student, teacher, kind):
+    return PointwiseLossFn.apply(student, teacher, kind)
+
+
 def cosine_loss(student, teacher):
     return CosineLossFn.apply(student, teacher)
 

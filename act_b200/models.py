@@ -67,8 +67,10 @@ class ACT_PointDistillation(nn.Module):
         super().__init__()
         self.config = config
         tc, dc = config.transformer_config, config.dvae_config
-        if tc.cls_loss or tc.proj != "linear" or config.loss != "cosine":
-            raise NotImplementedError("act_b200 implements the shipped config: cls_loss False, proj linear, cosine loss")
+        if tc.cls_loss or tc.proj != "linear" or config.loss not in ("cosine", "l2", "smoothl1"):
+            raise NotImplementedError("act_b200 implements cls_loss False, proj linear, loss cosine (the shipped config) / "
+                                      "l2 / smoothl1")
+        self.loss_type = config.loss
         self.mask_ratio = tc.mask_ratio
         self.embed_dim = tc.embed_dim
         self.ACT_encoder = VisableOnlyMaskTransformer(config)
@@ -170,7 +172,9 @@ class ACT_PointDistillation(nn.Module):
         """act.py:1229-1254: the teacher's features at the masked groups against the student's predictions."""
         G = order.shape[1]
         teacher = ops.gather_rows(teacher_feat.detach(), order, n_vis, G - n_vis)  # teacher_feat[mask], original order
-        return layers.cosine_loss(student, teacher)
+        if self.loss_type == "cosine":
+            return layers.cosine_loss(student, teacher)
+        return layers.pointwise_loss(student, teacher.reshape(student.shape), self.loss_type)    # act.py:1255-1256
 
 
 @register

@@ -194,6 +194,7 @@ class VisableOnlyMaskTransformer(nn.Module):
         self.reduce_dim = (nn.Linear(self.encoder_dims, self.embed_dim) if self.encoder_dims != self.embed_dim
                            else nn.Identity())
         self.mask_type = tc.mask_type
+        self.block_index = None                # mask_type 'block': staged random centre indices (see _mask_center_block)
         self.cls_token = nn.Parameter(torch.randn(1, 1, self.embed_dim))
         self.cls_pos = nn.Parameter(torch.randn(1, 1, self.embed_dim))
         self.pos_embed = nn.Sequential(nn.Linear(3, 128), nn.GELU(), nn.Linear(128, self.embed_dim))
@@ -225,15 +226,30 @@ class VisableOnlyMaskTransformer(nn.Module):
         self.num_mask = int(self.mask_ratio * G)
         return mask_center_rand(B, G, self.mask_ratio, center.device)
 
+    def _mask_center_block(self, center, noaug=False):
+        """act.py:215-243: per cloud, the int(mask_ratio * G) centres nearest to a random centre.  The random centre index is
+        drawn on the host with Python's `random.randint` exactly like the reference (same stream consumption), or read from
+        `self.block_index` (device i32 [B]) when a caller -- engine.PretrainStep -- stages it for a captured step; distances,
+        ranking and the mask are one kernel (csrc/tokens.cu act_mask_block), no host round trip."""
+        import random
+        B, G, _ = center.shape
+        if noaug or self.mask_ratio == 0:
+            return torch.zeros(B, G, dtype=torch.bool, device=center.device)
+        index = self.block_index
+        if index is None:
+            index = torch.tensor([random.randint(0, G - 1) for _ in range(B)], dtype=torch.int32)
+            index = index.pin_memory().to(center.device, non_blocking=True) if center.is_cuda else index
+        return ops.mask_block(center, index, int(self.mask_ratio * G))
+
     def forward(self, neighborhood, center, only_cls_tokens=False, noaug=False, mask=None, return_extras=False):
         """-> (x_vis, mask) like the reference; with return_extras also the dict {order, centers_sorted, encoded} the Stage-II
         model consumes (returned, never kept on the module: a tensor with a grad_fn stored on a module would keep the previous
         step's autograd graph alive and release it in the middle of the next step -- e.g. inside a CUDA-graph capture)."""
-        if self.mask_type != 'rand':
-            raise NotImplementedError("act_b200: only mask_type 'rand' (the shipped config) is implemented")
+        if self.mask_type not in ('rand', 'block'):
+            raise NotImplementedError("act_b200: mask_type 'rand' (the shipped config) or 'block'")
         B, G, _ = center.shape
         if mask is None:
-            mask = self._mask_center_rand(center, noaug=noaug)
+            mask = (self._mask_center_rand if self.mask_type == 'rand' else self._mask_center_block)(center, noaug=noaug)
         num_mask = 0 if (noaug or self.mask_ratio == 0) else int(self.mask_ratio * G)
         n_vis = G - num_mask
         # the permutation "visible groups first" (original order inside each part) replaces the reference's boolean

@@ -396,6 +396,26 @@ def scale_by_(x, scalar):
     return x
 
 
+_PW_SCRATCH = {}
+
+
+def pointwise_loss(student, teacher, kind, want_grad=True):
+    """mean over all elements of (s - t)^2 (kind 'l2') or SmoothL1(s - t) (kind 'smoothl1') -> (loss f32 [], grad or None)."""
+    s, t = _f32c(student), _f32c(teacher)
+    assert s.shape == t.shape
+    key = str(s.device)
+    sc = _PW_SCRATCH.get(key)
+    if sc is None:
+        sc = (torch.empty(256, dtype=torch.float32, device=s.device), torch.zeros(1, dtype=torch.int32, device=s.device))
+        _PW_SCRATCH[key] = sc
+    loss = torch.empty((), dtype=torch.float32, device=s.device)
+    grad = torch.empty_like(s) if want_grad else None
+    _lib.call("act_pointwise_loss", s, t, _lib.ctypes.c_int64(s.numel()), {"l2": 0, "smoothl1": 1}[kind], sc[0], sc[1], loss,
+              grad)
+    _count()
+    return loss, grad
+
+
 def adamw(param, grad, exp_avg, exp_avg_sq, shadow, n_decay, hyper):
     """grad: the flat fp32 gradient, or its all-reduced bf16 copy (N>1, dp.sync_gradients)."""
     name = "act_adamw_bf16grad" if grad.dtype == torch.bfloat16 else "act_adamw"
@@ -430,6 +450,17 @@ def pos_mlp1_bwd(da, x, W, b, dW, db):
     R = x.shape[0]
     _lib.call("act_pos_mlp1_bwd", _p(da), int(da.dtype == torch.float32), x, W, b, R, dW, db)
     _count()
+
+
+def mask_block(center, index, num_mask):
+    """center f32 [B,G,3], index i32 [B] (device) -> bool [B,G]: the num_mask centres nearest to centre index[b] (act.py:215-243)."""
+    center = _f32c(center)
+    B, G, _ = center.shape
+    assert index.dtype == torch.int32 and index.is_cuda and index.numel() == B
+    mask = torch.empty(B, G, dtype=torch.uint8, device=center.device)
+    _lib.call("act_mask_block", center, index, B, G, int(num_mask), mask)
+    _count()
+    return mask.view(torch.bool)
 
 
 def mask_order(mask):

@@ -401,6 +401,11 @@ int act_subsample_norm(const float *raw, const int *sel, int B, int Nraw, int nu
 /* Device-side random mask (the distribution of _mask_center_rand, models/act.py:244-267: exactly num_mask of the G groups
  * of every cloud, uniformly at random; keys from Philox4x32-10 keyed by the 64-bit *seed in device memory).  mask u8 [B,G].
  * An option for loops that do not need the reference's numpy stream; the default mask stays the host draw. */
+/* Block masking (transformer_config.mask_type = 'block', /root/reference/models/act.py:215-243): mask u8 [B,G] = 1 for the
+ * num_mask centres nearest to centre index[b] (i32 [B], drawn by the caller: the reference uses Python's random.randint),
+ * i.e. argsort(norm(center[b, index[b]] - center[b]))[:num_mask]; center f32 [B,G,3]; ties by the lower group index. */
+int act_mask_block(const float *center, const int *index, int B, int G, int num_mask, uint8_t *mask, void *stream);
+
 int act_mask_rand(const unsigned long long *seed, int B, int G, int num_mask, uint8_t *mask, void *stream);
 
 /* ---- Loss and optimizer ------------------------------------------------------------------------------ */
@@ -411,6 +416,13 @@ int act_mask_rand(const unsigned long long *seed, int B, int G, int num_mask, ui
  * d loss / d student. */
 int act_cosine_loss(const float *student, const float *teacher, int R, int C, float eps, float *loss,
                     float *grad_student, void *stream);
+
+/* The element-wise distillation losses of config.loss = "l2" / "smoothl1" (/root/reference/models/act.py:1188-1191,
+ * 1255-1256: nn.MSELoss / nn.SmoothL1Loss(beta = 1), reduction 'mean' over every element): student, teacher f32 [n];
+ * kind 0 = l2, 1 = smooth l1; *loss and grad_student (nullable) = d loss / d student in one pass.  partial f32 [256] and
+ * counter u32 [1] (zero before the first call; re-zeroed by the kernel) are scratch; partial sums are added in index order. */
+int act_pointwise_loss(const float *student, const float *teacher, long long n, int kind, float *partial,
+                       unsigned int *counter, float *loss, float *grad_student, void *stream);
 
 /* Small pieces of the step that would otherwise be library launches inside the captured graph:
  * act_zero: cudaMemsetAsync (optimizer.zero_grad() of the flat gradient buffer, runner_pretrain.py:157; scratch);

@@ -318,3 +318,19 @@ class PointTransformer(nn.Module):
         loss = F.cross_entropy(ret, gt.long())
         acc = (ret.argmax(-1) == gt).sum() / float(gt.size(0))
         return loss, acc * 100
+
+
+def mask_center_block(center, mask_ratio, index=None):
+    """models/act.py:215-243 (_mask_center_block): per cloud, mask the int(ratio * G) centres nearest to a random centre
+    (Python's random.randint, consumed one call per cloud like the reference; `index` injects the draws)."""
+    import random
+    out = []
+    for b, points in enumerate(center):
+        points = points.unsqueeze(0)
+        i = random.randint(0, points.size(1) - 1) if index is None else int(index[b])
+        dist = torch.norm(points[:, i].reshape(1, 1, 3) - points, p=2, dim=-1)
+        idx = torch.argsort(dist, dim=-1, descending=False)[0]
+        m = torch.zeros(len(idx))
+        m[idx[:int(mask_ratio * len(idx))]] = 1
+        out.append(m.bool())
+    return torch.stack(out)

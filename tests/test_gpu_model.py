@@ -342,3 +342,60 @@ def test_engine_device_side_mask_option():
     losses = [eng.run(pts).item() for _ in range(8)]
     assert np.array_equal(np.random.get_state()[1], state)          # the numpy stream is not consumed
     assert all(np.isfinite(l) for l in losses) and len(set(losses)) == len(losses) and losses[-1] < losses[0]
+
+
+def test_block_mask_kernel_and_engine():
+    """transformer_config.mask_type = 'block' (act.py:215-243): the mask kernel against the oracle restatement (pinned to the
+    unmodified reference in tests/test_oracle.py) on the same random centre indices, the module drawing those indices from
+    Python's `random` like the reference, and a captured training step with the indices staged per replay."""
+    import random
+    from act_b200 import ops
+    from act_b200.engine import PretrainStep
+    torch.manual_seed(2)
+    for (B, G, ratio) in ((6, 64, 0.6), (3, 512, 0.6), (4, 64, 0.25)):
+        center = torch.randn(B, G, 3)
+        index = torch.randint(0, G, (B,), dtype=torch.int32)
+        want = ref_model.mask_center_block(center, ratio, index=index)
+        got = ops.mask_block(center.cuda(), index.cuda(), int(ratio * G)).cpu()
+        assert torch.equal(got, want)
+    cfg = models.default_config(mask_ratio=0.6, drop_path_rate=0.0)
+    cfg.transformer_config["mask_type"] = "block"
+    pts = ref_model.synthetic_clouds(4, 1024, seed=9).cuda()
+    model = models.ACT_PointDistillation(cfg, teacher="synthetic").cuda().train()
+    with torch.no_grad():
+        nb, center = model.group_divider(pts)
+        random.seed(11)
+        _, mask = model.ACT_encoder(nb, center)
+    random.seed(11)
+    assert torch.equal(mask.cpu(), ref_model.mask_center_block(center.cpu(), 0.6))     # same stream consumption
+    torch.cuda.synchronize()
+    fp = layers.FlatParams(model, lr=1e-3, exclude=model.UNUSED_PARAMETERS)
+    eng = PretrainStep(model, fp, 4, 1024).capture()
+    losses = [eng.run(pts).item() for _ in range(6)]
+    assert all(np.isfinite(l) for l in losses) and len(set(losses)) == len(losses) and losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("kind", ["l2", "smoothl1"])
+def test_pointwise_distillation_losses(kind):
+    """config.loss = 'l2' / 'smoothl1' (act.py:1188-1191, 1255-1256): the fused loss + gradient kernel against
+    nn.MSELoss / nn.SmoothL1Loss, and a model step with that loss."""
+    from act_b200 import ops
+    torch.manual_seed(4)
+    s = (torch.randn(7, 38, 384, device="cuda") * 1.5).requires_grad_(True)
+    t = torch.randn(7, 38, 384, device="cuda")
+    loss = layers.pointwise_loss(s, t, kind)
+    (loss * 3.0).backward()
+    got = s.grad.clone()
+    s.grad = None
+    ref = (torch.nn.MSELoss() if kind == "l2" else torch.nn.SmoothL1Loss())(s, t)
+    (ref * 3.0).backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item()) and rel(got, s.grad) < 1e-6
+    l2, _ = ops.pointwise_loss(s.detach(), t, kind, want_grad=False)
+    assert l2.item() == loss.item()                                  # deterministic reduction order
+    cfg = models.default_config(mask_ratio=0.6, drop_path_rate=0.0)
+    cfg.loss = kind
+    model = models.ACT_PointDistillation(cfg, teacher="synthetic").cuda().train()
+    pts = ref_model.synthetic_clouds(2, 1024, seed=3).cuda()
+    out = model(pts)
+    out.backward()
+    assert np.isfinite(out.item()) and model.proj_head.weight.grad.abs().sum().item() > 0

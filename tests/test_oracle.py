@@ -175,3 +175,21 @@ def test_stage1_schedules_product_equals_oracle():
     for n in (0, 1, 9999, 10000, 10001, 55000, 100000, 100001, 110000, 110001, 10 ** 6):
         assert dvae.get_temp(n) == ref_dvae.temperature_schedule(n)
         assert dvae.get_kld_weight(n) == ref_dvae.kld_weight_schedule(n)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="authoring container only")
+def test_block_mask_restatement_matches_reference():
+    """oracle.ref_model.mask_center_block against the unmodified VisableOnlyMaskTransformer._mask_center_block
+    (act.py:215-243) on the same Python `random` stream."""
+    import random
+    import types
+    from oracle import ref_model, shims
+    shims.install()
+    import models.act as act
+    center = torch.randn(5, 64, 3)
+    stub = types.SimpleNamespace(mask_ratio=0.6)
+    random.seed(3)
+    want = act.VisableOnlyMaskTransformer._mask_center_block(stub, center)
+    random.seed(3)
+    got = ref_model.mask_center_block(center, 0.6)
+    assert torch.equal(want, got) and int(got.sum()) == 5 * int(0.6 * 64)
