@@ -11,7 +11,7 @@ import re
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libact_b200.so")
+LIB_PATH = os.environ.get("ACT_B200_LIB") or os.path.join(_HERE, "libact_b200.so")   # override: A/B runs of two builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "act_b200.h")
 
 _lib = None

@@ -58,11 +58,19 @@ __global__ void __launch_bounds__(256) dgcnn_edge_gn_kernel(const float *__restr
     const float *P = pq + (size_t)b * G * 2 * Cp;
     constexpr int W = VEC ? 4 : 1;
     float s1 = 0.f, s2 = 0.f;
-    for (int g = warp; g < G; g += 8) {
+    // the neighbour indices of 8 of this warp's tokens are fetched by ONE load (lane = (token, neighbour)) and handed out by
+    // shuffles: the per-token dependent L2 round trip idx -> row address -> row data loses its first hop
+    static_assert(KN == 4, "index prefetch: 8 tokens x 4 neighbours per warp load");
+    for (int g0 = warp; g0 < G; g0 += 64) {
+      const int gl = g0 + 8 * (lane >> 2);
+      const long long my_idx = gl < G ? __ldg(idx + ((size_t)b * G + gl) * KN + (lane & 3)) : 0;
+      for (int tt = 0; tt < 8; ++tt) {
+        const int g = g0 + 8 * tt;
+        if (g >= G) break;
         const float *q = P + (size_t)g * 2 * Cp + Cp + c_lo;
         const float *pn[KN];
 #pragma unroll
-        for (int j = 0; j < KN; ++j) pn[j] = P + (size_t)__ldg(idx + ((size_t)b * G + g) * KN + j) * 2 * Cp + c_lo;
+        for (int j = 0; j < KN; ++j) pn[j] = P + (size_t)__shfl_sync(0xffffffffu, my_idx, tt * 4 + j) * 2 * Cp + c_lo;
         for (int c = lane * W; c < Cg; c += 32 * W) {
             if (VEC) {
                 const float4 qv = __ldg(reinterpret_cast<const float4 *>(q + c));
@@ -83,16 +91,22 @@ __global__ void __launch_bounds__(256) dgcnn_edge_gn_kernel(const float *__restr
                 }
             }
         }
+      }
     }
     const float n = (float)G * KN * Cg;
     const float mean = block_sum_256(s1, red) / n;
     const float var = fmaxf(block_sum_256(s2, red) / n - mean * mean, 0.f);
     const float rstd = rsqrtf(var + eps);
-    for (int g = warp; g < G; g += 8) {
+    for (int g0 = warp; g0 < G; g0 += 64) {
+      const int gl = g0 + 8 * (lane >> 2);
+      const long long my_idx = gl < G ? __ldg(idx + ((size_t)b * G + gl) * KN + (lane & 3)) : 0;
+      for (int tt = 0; tt < 8; ++tt) {
+        const int g = g0 + 8 * tt;
+        if (g >= G) break;
         const float *q = P + (size_t)g * 2 * Cp + Cp + c_lo;
         const float *pn[KN];
 #pragma unroll
-        for (int j = 0; j < KN; ++j) pn[j] = P + (size_t)__ldg(idx + ((size_t)b * G + g) * KN + j) * 2 * Cp + c_lo;
+        for (int j = 0; j < KN; ++j) pn[j] = P + (size_t)__shfl_sync(0xffffffffu, my_idx, tt * 4 + j) * 2 * Cp + c_lo;
         __nv_bfloat16 *o = out + ((size_t)b * G + g) * ldo + c_lo;
         for (int c = lane * W; c < Cg; c += 32 * W) {
             if (VEC) {
@@ -131,6 +145,7 @@ __global__ void __launch_bounds__(256) dgcnn_edge_gn_kernel(const float *__restr
                 o[c] = __float2bfloat16_rn(best);
             }
         }
+      }
     }
 }
 
