@@ -543,11 +543,16 @@ __device__ __forceinline__ void epi_do_chunk(const GemmEpi &epi, uint32_t taddr,
 }
 
 // ------------------------------------------------------------------------------------- the kernel
-template <int BN, bool A_MN, bool B_MN, int STAGES, int MODE>
-__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a,
+// EW: epilogue warps.  4 = one per TMEM lane quadrant, operands of the next chunk prefetched in ping-pong (up to 168
+// registers).  8 = two per quadrant, each draining half of the tile's columns with the late-load epilogue of the
+// persistent kernels (<= 96 registers, so two 320-thread CTAs still share an SM): the transformer's one-round GEMMs
+// (27 row tiles at M = 3456) spend more time in the epilogue's dependent chain than in their 6..24 k-blocks.
+template <int BN, bool A_MN, bool B_MN, int STAGES, int MODE, int EW = 4>
+__global__ void __launch_bounds__(64 + 32 * EW, 2) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                                  const __grid_constant__ CUtensorMap tma_b,
                                                                  const GemmEpi epi, int M, int N, int K,
                                                                  int kb_per_split) {
+    static_assert(EW == 4 || EW == 8, "4 or 8 epilogue warps");
     constexpr uint32_t A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
     constexpr uint32_t B_BYTES = BN * GEMM_BK * 2;
     constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -627,6 +632,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_bf16_kernel(const __grid
             }
             umma_commit(&tmem_full_bar);
         }
+    } else if (EW == 8) {
+        // epilogue warps 2..9 -> TMEM lane quadrant warp % 4, column half (warp - 2) / 4
+        const int e = warp - 2, quad = warp & 3, part = e >> 2;
+        constexpr int WCOLS = BN / 2, NCH = WCOLS / 32;
+        static_assert(WCOLS % 32 == 0, "half a tile = whole 32-column chunks");
+        const int row0 = m0 + quad * 32;
+        EpiPre pa;
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        // the pipeline stages are dead (see below): eight per-warp 4 KB epilogue tiles (STAGES * STAGE_BYTES >= 72 KB)
+        const uint32_t stage = smem_u32(smem) + e * 4096;
+        const uint32_t tbase = tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(part * WCOLS);
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c)
+            epi_do_chunk<MODE, true>(epi, tbase + (uint32_t)(c * 32), nkb > 0, nullptr, pa, row0, M,
+                                     n0 + part * WCOLS + c * 32, N, lane, stage);
     } else {
         // epilogue warps 2..5 -> TMEM lane quadrant warp % 4
         const int quad = warp & 3;
@@ -1116,17 +1137,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1) gem
     }
 }
 
+// ACT_B200_EW8=0 keeps the one-tile kernel on 4 epilogue warps (A/B timing)
+inline bool epi_warps8() {
+    static const bool on = [] {
+        const char *e = std::getenv("ACT_B200_EW8");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 template <int BN, bool A_MN, bool B_MN, int MODE = E_GENERIC>
 static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmEpi &epi, int M, int N, int K,
                        int splits, cudaStream_t st) {
     constexpr int STAGES = BN > 128 ? 2 : 3;     // keep two CTAs resident per SM (<= ~113 KB each)
     constexpr size_t smem = (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024;
-    auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES, MODE>;
-    ACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int total_kb = (K + GEMM_BK - 1) / GEMM_BK;
     const int kbps = (total_kb + splits - 1) / splits;
     const int nsplit = (total_kb + kbps - 1) / kbps;
     dim3 grid((N + BN - 1) / BN, (M + GEMM_BM - 1) / GEMM_BM, nsplit);
+    // measured (scripts/ab_ew8.py, M = 3456): GELU forward 12.8 -> 11.9 us, GELU' dgrad 14.0 -> 13.2 us; the plain, residual
+    // and atomic epilogues are load / store-bound and gain nothing (the split-K wgrad loses 0.1-0.5 us), so they keep 4 warps
+    if constexpr (MODE == E_GELU || MODE == E_MULGELU || MODE == E_MULRELU) {
+        if (epi_warps8()) {
+            auto kern8 = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES, MODE, 8>;
+            ACT_CUDA(cudaFuncSetAttribute(kern8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ACT_CUDA(launch_k(kern8, grid, dim3(64 + 32 * 8), smem, st, true, ta, tb, epi, M, N, K, kbps));
+            return ACT_OK;
+        }
+    }
+    auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES, MODE>;
+    ACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ACT_CUDA(launch_k(kern, grid, dim3(GEMM_THREADS), smem, st, true, ta, tb, epi, M, N, K, kbps));
     return ACT_OK;
 }
@@ -1275,6 +1315,12 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
         persistent = 2;
         pair_gmax_sel = true;
     }
+    bool force384 = false;       // persistent == 3 (explicit): the CTA-pair kernel on 256 x 384 tiles whatever the tile count
+    if (persistent == 3) {
+        if (N % 384 || !(mode == E_PLAIN || mode == E_RESID || mode == E_GELU) || epi.slab_bias) return ACT_EUNSUPPORTED;
+        force384 = true;
+        persistent = 2;
+    }
     const bool pair = persistent == 2;
     if (pair && (a_mn_major || b_mn_major || (gmode && !pair_gmax_sel) || splits != 1 || block_n != 0)) return ACT_EUNSUPPORTED;
     int BN;
@@ -1290,6 +1336,10 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
             2 * t384 > sms / 2 && act::pair_enabled() >= 2) {
             pair384 = true;
             BN = 96;             // two 192-wide MMAs per k-step: 96 B rows per CTA and MMA
+        }
+        if (force384) {
+            pair384 = true;
+            BN = 96;
         }
         if (pair_gmax_sel && N % 384 == 0 && pair_gmax != 3) {      // many rounds of single-buffered 256 x 384 tiles
             pair384 = true;
@@ -1333,6 +1383,7 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
     if (pair && pair384) {
         if (mode == E_GMAX) return launch_gemm_pair<E_GMAX, 192, 2>(ta, tb, epi, M, N, K, st);
         if (mode == E_RESID) return launch_gemm_pair<E_RESID, 192, 2>(ta, tb, epi, M, N, K, st);
+        if (mode == E_GELU) return launch_gemm_pair<E_GELU, 192, 2>(ta, tb, epi, M, N, K, st);
         return launch_gemm_pair<E_PLAIN, 192, 2>(ta, tb, epi, M, N, K, st);
     }
     if (pair) {
