@@ -104,7 +104,9 @@ int act_chamfer_backward(const float *xyz1, const float *xyz2, const int32_t *id
  * persistent: 1 = one CTA per SM looping over tiles with a double-buffered TMEM accumulator (many-tile GEMMs),
  * 2 = the CTA-pair kernel (clusters of two CTAs computing 256 x 256 tiles with tcgen05.mma.cta_group::2; K-major
  * operands, plain / GELU / residual epilogues, no split-K, block_n = 0; ACT_EUNSUPPORTED otherwise), 0 = one tile per
- * CTA, -1 = choose (the pair kernel for K-major plain / residual GEMMs with at least 74 pair tiles).
+ * CTA, -1 = choose (the pair kernel for K-major plain / residual GEMMs with at least 74 pair tiles), 3 = the pair
+ * kernel on 256 x 384 tiles whatever the tile count (N % 384 == 0; plain / GELU / residual epilogues; dispatch sweeps).
+ * The one-tile kernel runs its GELU / GELU' / ReLU' epilogues on 8 epilogue warps (ACT_B200_EW8=0: 4, the A/B).
  * block_n: 64 / 128 / 192 / 256 output-tile width (0 = choose).  resid_row_div: 1, or a multiple of 32 (the broadcast
  * term then enters as a per-32-row-slab bias).  rows_per_scale >= 8.  Requirements: N % 8 == 0, K % 8 == 0 pitches,
  * 16-byte aligned pointers.
