@@ -63,7 +63,51 @@ class _StateSnapshot:
         torch.cuda.set_rng_state(self.cuda_rng, self.dev)
 
 
-class PretrainStep:
+class _InputStaging:
+    """Data-loader style input prefetch shared by the two step engines.  `stage(host_batch)` starts the host->device copy of
+    a pinned host batch on the engine's copy stream into one of two device slots and returns that device tensor; passing
+    it to `run()` makes the consuming stream wait for the copy and then move it into the step's static input buffer (a
+    1.5 MB device-to-device copy).  Calling `stage(batch[i+1])` before `run(staged[i])` overlaps the next batch's PCIe
+    transfer with the current step (the reference's loop does a blocking `points = data.cuda()` at the top of every
+    iteration, runner_pretrain.py:128-131).  Plain `run(host_batch)` still copies in-stream."""
+    _copy_stream = None
+
+    def stage(self, points):
+        if points.is_cuda:
+            return points
+        dev = self.dev
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._slots = [{"buf": torch.empty_like(self.points), "ready": torch.cuda.Event(), "consumed": None}
+                           for _ in range(2)]
+            self._slot_i = 0
+        slot = self._slots[self._slot_i % 2]
+        self._slot_i += 1
+        cs = self._copy_stream
+        if slot["consumed"] is not None:
+            cs.wait_event(slot["consumed"])                    # the step that read this slot has copied it out
+        with torch.cuda.stream(cs):
+            slot["buf"].copy_(points, non_blocking=True)
+            slot["ready"].record(cs)
+        return slot["buf"]
+
+    def _copy_in(self, points):
+        """points -> the static input buffer on the CURRENT stream (no-op when it already is that buffer)."""
+        if points is None or points.data_ptr() == self.points.data_ptr():
+            return
+        cur = torch.cuda.current_stream(self.dev)
+        slot = None
+        if self._copy_stream is not None:
+            slot = next((sl for sl in self._slots if sl["buf"] is points), None)
+        if slot is not None:
+            cur.wait_event(slot["ready"])
+        self.points.copy_(points, non_blocking=True)           # H2D when `points` is a pinned host batch
+        if slot is not None:
+            slot["consumed"] = torch.cuda.Event()
+            slot["consumed"].record(cur)
+
+
+class PretrainStep(_InputStaging):
     """pipeline (default: on when world > 1): the tokenizer and the FROZEN teacher's forward do not depend on the student's
     weights, so (1) step i's gradient all-reduce and AdamW are deferred to the start of step i+1, where the all-reduce runs
     on its own stream beside the teacher branch, and (2) with `run(points, next_points=...)` the tokenizer + teacher forward
@@ -177,8 +221,7 @@ class PretrainStep:
         self._seeds.copy_(torch.randint(0, 2 ** 62, (3,), dtype=torch.int64).pin_memory(), non_blocking=True)
         if hyper:
             self.fp.set_hyper(grad_scale=1.0 / dp.world_size())
-        if points is not None and points.data_ptr() != self.points.data_ptr():
-            self.points.copy_(points, non_blocking=True)       # H2D when `points` is a pinned host batch
+        self._copy_in(points)
 
     def _capture_pipeline(self):
         l0 = ops.LAUNCHES
@@ -233,8 +276,7 @@ class PretrainStep:
         T = self._teacher_stream
         T.wait_event(self._ev_copied)                        # the previous contents have been copied out
         with torch.cuda.stream(T):
-            if points.data_ptr() != self.points.data_ptr():
-                self.points.copy_(points, non_blocking=True)  # H2D when `points` is a pinned host batch
+            self._copy_in(points)
             if self._tseed is not None:                      # fresh pinned staging per step (see _host_prologue)
                 self._tseed.copy_(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).pin_memory(), non_blocking=True)
             self.graph.replay()                              # G0
@@ -356,7 +398,7 @@ class PretrainStep:
         return self.loss
 
 
-class AutoencoderStep:
+class AutoencoderStep(_InputStaging):
     """The Stage-I dVAE training step (tools/runner_autoencoder.py:130-146: temp = get_temp(n_itr); ret = model(points,
     temperature=temp, hard=False); loss_1, loss_2 = get_loss(ret, points); loss_1 + kld_weight * loss_2; backward;
     optimizer.step; zero_grad) as one replayable CUDA graph.  The two schedules are evaluated on the host exactly like
@@ -407,8 +449,7 @@ class AutoencoderStep:
         self.sched.copy_(sched.pin_memory(), non_blocking=True)      # fresh pinned staging per step (see PretrainStep)
         self._seed.copy_(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).pin_memory(), non_blocking=True)
         self.fp.set_hyper(grad_scale=1.0 / dp.world_size())
-        if points is not None and points.data_ptr() != self.points.data_ptr():
-            self.points.copy_(points, non_blocking=True)
+        self._copy_in(points)
 
     def flush(self):
         """Serial schedule: nothing is ever pending (kept for interface parity with PretrainStep)."""
