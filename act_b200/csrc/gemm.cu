@@ -31,10 +31,17 @@ namespace act {
 
 // ACT_OPT_GEMM_SM_CAP: upper bound on the SMs a persistent / CTA-pair GEMM occupies (0 = all).  The frozen teacher's large
 // GEMMs run beside the student's latency-bound chain on another stream; leaving a few SMs free keeps that chain moving.
+#ifndef GEMM_PART
+#define GEMM_PART 0      // this file is compiled once per part (Makefile): part 0 holds the C entry point, see the list below
+#endif
+#if GEMM_PART == 0
 int &gemm_sm_cap() {
     static int cap = 0;
     return cap;
 }
+#else
+int &gemm_sm_cap();
+#endif
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;          // 64 bf16 = 128 B = one swizzle row
@@ -1147,7 +1154,7 @@ inline bool epi_warps8() {
 }
 
 template <int BN, bool A_MN, bool B_MN, int MODE = E_GENERIC>
-static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmEpi &epi, int M, int N, int K,
+int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmEpi &epi, int M, int N, int K,
                        int splits, cudaStream_t st) {
     constexpr int STAGES = BN > 128 ? 2 : 3;     // keep two CTAs resident per SM (<= ~113 KB each)
     constexpr size_t smem = (size_t)STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024;
@@ -1172,7 +1179,7 @@ static int launch_gemm(const CUtensorMap &ta, const CUtensorMap &tb, const GemmE
 }
 
 template <int BN, bool A_MN, bool B_MN, int MODE = E_GENERIC, int NB = 1>
-static int launch_gemm_persistent(const CUtensorMap &ta, const CUtensorMap &tb, const GemmEpi &epi, int M, int N, int K,
+int launch_gemm_persistent(const CUtensorMap &ta, const CUtensorMap &tb, const GemmEpi &epi, int M, int N, int K,
                                   int splits, cudaStream_t st) {
     constexpr int STAGES = NB == 1 ? PersistCfg<MODE>::STAGES : 2;
     constexpr size_t smem = PersistCfg<MODE>::smem(BN, NB, STAGES);
@@ -1204,7 +1211,7 @@ inline int pair_enabled() {
 }
 
 template <int MODE, int PN = 256, int NB = 1>
-static int launch_gemm_pair(const CUtensorMap &ta, const CUtensorMap &tb, const GemmEpi &epi, int M, int N, int K,
+int launch_gemm_pair(const CUtensorMap &ta, const CUtensorMap &tb, const GemmEpi &epi, int M, int N, int K,
                             cudaStream_t st) {
     auto kern = gemm_bf16_pair_kernel<MODE, PN, NB>;
     constexpr size_t PAIR_SMEM = PairCfg<PN, NB>::SMEM;
@@ -1223,8 +1230,83 @@ static int launch_gemm_pair(const CUtensorMap &ta, const CUtensorMap &tb, const 
     return ACT_OK;
 }
 
+
+// ---------------------------------------------------------------- instantiations, spread over translation units
+// A clean build of every epilogue / layout / tile variant in ONE translation unit takes > 6 minutes of ptxas.  The
+// Makefile compiles this file GEMM_PARTS + 1 times (-DGEMM_PART=p): part p defines the instantiations tagged p below and
+// sees all others as `extern template`; part 0 defines none of them and holds act_gemm_bf16.  A variant missing from the
+// list still works (it is then instantiated implicitly in part 0).
+#define GEMM_SIG const CUtensorMap &, const CUtensorMap &, const GemmEpi &, int, int, int, int, cudaStream_t
+#define GEMM_SIG_PAIR const CUtensorMap &, const CUtensorMap &, const GemmEpi &, int, int, int, cudaStream_t
+#define GEMM_PARTS 6
+#if GEMM_PART == 1
+#define GEMM_X1
+#else
+#define GEMM_X1 extern
+#endif
+#if GEMM_PART == 2
+#define GEMM_X2
+#else
+#define GEMM_X2 extern
+#endif
+#if GEMM_PART == 3
+#define GEMM_X3
+#else
+#define GEMM_X3 extern
+#endif
+#if GEMM_PART == 4
+#define GEMM_X4
+#else
+#define GEMM_X4 extern
+#endif
+#if GEMM_PART == 5
+#define GEMM_X5
+#else
+#define GEMM_X5 extern
+#endif
+#if GEMM_PART == 6
+#define GEMM_X6
+#else
+#define GEMM_X6 extern
+#endif
+#define LG(P, BN, A, B, MODE) GEMM_X##P template int launch_gemm<BN, A, B, MODE>(GEMM_SIG);
+#define LP(P, BN, A, B, MODE) GEMM_X##P template int launch_gemm_persistent<BN, A, B, MODE>(GEMM_SIG);
+#define LP2(P, BN, A, B, MODE) GEMM_X##P template int launch_gemm_persistent<BN, A, B, MODE, 2>(GEMM_SIG);
+#define LPAIR(P, MODE, PN, NB) GEMM_X##P template int launch_gemm_pair<MODE, PN, NB>(GEMM_SIG_PAIR);
+// generic epilogue (register-heavy, the slowest to compile): one-tile and persistent kernels, every layout
+LG(1, 64, false, false, E_GENERIC) LG(1, 64, false, true, E_GENERIC) LG(1, 64, true, false, E_GENERIC) LG(1, 64, true, true, E_GENERIC)
+LG(1, 128, false, false, E_GENERIC) LG(1, 128, false, true, E_GENERIC)
+LG(2, 128, true, false, E_GENERIC) LG(2, 128, true, true, E_GENERIC)
+LG(2, 192, false, false, E_GENERIC) LG(2, 192, false, true, E_GENERIC) LG(2, 192, true, false, E_GENERIC) LG(2, 192, true, true, E_GENERIC)
+LP(3, 128, false, false, E_GENERIC) LP(3, 128, false, true, E_GENERIC) LP(3, 128, true, false, E_GENERIC) LP(3, 128, true, true, E_GENERIC)
+LP(4, 256, false, false, E_GENERIC) LP(4, 256, false, true, E_GENERIC) LP(4, 256, true, false, E_GENERIC) LP(4, 256, true, true, E_GENERIC)
+// specialised one-tile kernels: transformer forward / dgrad / wgrad
+LG(5, 128, false, false, E_PLAIN) LG(5, 192, false, false, E_PLAIN) LG(5, 64, false, false, E_PLAIN)
+LG(5, 128, false, true, E_PLAIN) LG(5, 192, false, true, E_PLAIN) LG(5, 64, false, true, E_PLAIN)
+LG(5, 128, false, false, E_GELU) LG(5, 192, false, false, E_GELU)
+LG(5, 128, false, true, E_MULGELU) LG(5, 192, false, true, E_MULGELU)
+LG(5, 128, false, false, E_RESID) LG(5, 64, false, false, E_RESID)
+LG(5, 128, true, true, E_ATOMIC) LG(5, 192, true, true, E_ATOMIC) LG(5, 64, true, true, E_ATOMIC)
+// specialised persistent kernels: mini-PointNet convs, decoder-sized GEMMs, 128 x 384 tiles
+LP(6, 256, false, false, E_PLAIN) LP(6, 128, false, false, E_PLAIN) LP(6, 256, false, true, E_PLAIN) LP(6, 128, false, true, E_PLAIN)
+LP(6, 256, false, false, E_RESID) LP(6, 128, false, false, E_RESID)
+LP(6, 256, false, true, E_MULRELU) LP(6, 128, false, true, E_MULRELU)
+LP(6, 256, false, true, E_MULGELU) LP(6, 128, false, false, E_GELU) LP(6, 256, false, false, E_GELU)
+LP(3, 128, false, false, E_GMAX)
+LP(3, 128, false, false, E_STATS) LP(3, 256, false, false, E_STATS)
+LP(3, 128, true, true, E_ATOMIC) LP(3, 256, true, true, E_ATOMIC)
+LP2(3, 192, false, false, E_RESID) LP2(3, 192, false, false, E_PLAIN)
+// CTA-pair kernels
+LPAIR(4, E_GMAX, 192, 2) LPAIR(4, E_RESID, 192, 2) LPAIR(4, E_GELU, 192, 2) LPAIR(4, E_PLAIN, 192, 2) LPAIR(4, E_GMAX, 128, 1)
+LPAIR(2, E_GMAX, 256, 1) LPAIR(2, E_PLAIN, 256, 1) LPAIR(1, E_GELU, 256, 1) LPAIR(1, E_RESID, 256, 1) LPAIR(1, E_STATS, 256, 1)
+#undef LG
+#undef LP
+#undef LP2
+#undef LPAIR
+
 }  // namespace act
 
+#if GEMM_PART == 0
 extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, int a_mn_major, int b_mn_major,
                              int lda, int ldb, void *out, int ldo, int out_fp32, const float *bias, int act_kind,
                              void *preact_out, const void *mul_in, int ldm, int mul_mode, const float *resid, int ldr,
@@ -1445,3 +1527,4 @@ extern "C" int act_gemm_bf16(const void *A, const void *B, int M, int N, int K, 
 #undef ACT_GEMM_DISPATCH
 #undef ACT_GEMM_DISPATCH_P
 }
+#endif  // GEMM_PART == 0
