@@ -204,6 +204,12 @@ def test_gemm_cta_pair(M, N, K):
     lin = a.float() @ w.float().t()
     check(ops.gemm(a, w, out_dtype=torch.float32, persistent=2), lin, False)
     check(ops.gemm(a, w, bias=bias, persistent=2), lin + bias, True)
+    # bf16 output through TMA (plain epilogue): a column slice of a wider buffer -- the tensor map must clip at N, not at
+    # the 64-column box, and leave the neighbouring columns alone
+    wide = torch.zeros(M, N + 192, dtype=torch.bfloat16, device="cuda")
+    ops.gemm(a, w, bias=bias, out=wide[:, 64:64 + N], persistent=2)
+    check(wide[:, 64:64 + N], lin + bias, True)
+    assert (wide[:, :64] == 0).all() and (wide[:, 64 + N:] == 0).all()
     check(ops.gemm(a, w, bias=bias, act=ops.ACT_GELU, persistent=2), F.gelu(lin + bias), True)
     x = torch.randn(M, N, device="cuda")
     want = x + lin + bias
