@@ -11,6 +11,7 @@
 //       of stored.
 // All kernels use the same access pattern: a thread owns 8 consecutive channels (one 16-byte bf16 vector) of
 // a row, consecutive threads own consecutive vectors, so every warp access is a contiguous 512-byte segment.
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -265,6 +266,53 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(const T *__restrict__ 
         float t = 0.f;
         for (int r = 0; r < rpc; ++r) t += sm[(r * 2 + which) * C + cc];
         atomicAdd((which ? s2 : s1) + cc, t);
+    }
+}
+
+// Column sums of a token-sized [M, C] matrix (a few thousand rows: the bias gradients of the transformer's Linear layers).
+// chan_reduce<2> gives such a matrix one row per CTA iteration when C / 8 approaches 256 threads and ends in one atomic per
+// column from each of several hundred CTAs.  Here the grid is (column blocks of 256) x (row splits): lane = 8 consecutive
+// columns (one 16-byte load, a warp reads 512 contiguous bytes of a row), warp w takes rows w, w + 8, ... of the CTA's row
+// range with 4 loads in flight, warps are combined in shared memory, one atomic per column and CTA.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_tokens_kernel(const T *__restrict__ a, int M, int C, int rows_per_cta,
+                                                            float *__restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ float sm[8][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c0 = blockIdx.x * 256 + lane * 8;
+    const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (c0 < C) {
+        int r = r0 + warp;
+        for (; r + 24 < r1; r += 32) {
+            float f0[8], f1[8], f2[8], f3[8];
+            V8<T>::ld(a + (size_t)r * C + c0, f0);
+            V8<T>::ld(a + (size_t)(r + 8) * C + c0, f1);
+            V8<T>::ld(a + (size_t)(r + 16) * C + c0, f2);
+            V8<T>::ld(a + (size_t)(r + 24) * C + c0, f3);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
+        }
+        for (; r < r1; r += 8) {
+            float f0[8];
+            V8<T>::ld(a + (size_t)r * C + c0, f0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f0[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm[warp][lane * 8 + j] = acc[j];
+    __syncthreads();
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sm[w][threadIdx.x];
+        atomicAdd(out + c, t);
     }
 }
 
@@ -592,6 +640,19 @@ static int chan_reduce_t(int mode, const void *a, const void *x, const float *me
     // 32 would leave most SMs idle)
     const int grid = grid_for(M, rpc * (M >= (1 << 16) ? 32 : 8));
     const T *ap = reinterpret_cast<const T *>(a), *xp = reinterpret_cast<const T *>(x);
+    static const bool tokens_kernel = [] {                  // ACT_B200_COLSUM_TOKENS=0: chan_reduce<2> for every size (A/B)
+        const char *e = std::getenv("ACT_B200_COLSUM_TOKENS");
+        return !(e && e[0] == '0');
+    }();
+    if (mode == 2 && M < (1 << 16) && tokens_kernel) {
+        const int cb = (C + 255) / 256;
+        int splits = (2 * 148 + cb - 1) / cb;               // about two CTAs per SM
+        int rows = (int)((M + splits - 1) / splits);
+        rows = rows < 32 ? 32 : ((rows + 7) / 8) * 8;       // >= 4 rows per warp
+        splits = (int)((M + rows - 1) / rows);
+        ACT_CUDA(launch_k(colsum_tokens_kernel<T>, dim3(cb, splits), dim3(256), 0, st, true, ap, (int)M, C, rows, s1));
+        return ACT_OK;
+    }
     if (mode == 0) ACT_CUDA(launch_k(chan_reduce_kernel<0, T>, dim3(grid), dim3(256), smem, st, true, ap, xp, mean, rstd, M, C, s1, s2));
     else if (mode == 1) ACT_CUDA(launch_k(chan_reduce_kernel<1, T>, dim3(grid), dim3(256), smem, st, true, ap, xp, mean, rstd, M, C, s1, s2));
     else ACT_CUDA(launch_k(chan_reduce_kernel<2, T>, dim3(grid), dim3(256), smem, st, true, ap, xp, mean, rstd, M, C, s1, s2));

@@ -82,6 +82,20 @@ def test_attention_fwd_bwd(B, T, H):
     assert rel(dqkv, dqkv_ref) < 1e-2
 
 
+@pytest.mark.parametrize("M,C,dt", [(3456, 1536, torch.bfloat16), (3456, 384, torch.bfloat16), (8192, 1152, torch.bfloat16),
+                                    (1003, 2048, torch.bfloat16), (37, 8, torch.bfloat16), (4864, 384, torch.float32),
+                                    (70000, 512, torch.bfloat16)])
+def test_colsum_token_sized_and_large(M, C, dt):
+    """Bias-gradient column sums: the (column block x row split) kernel for token-sized matrices and the chan_reduce
+    kernel for the [B*G*k, C] activations (M >= 65536) accumulate into `out` and agree with an fp64 sum."""
+    torch.manual_seed(M + C)
+    x = torch.randn(M, C, device="cuda").to(dt)
+    out = torch.full((C,), 0.5, device="cuda")
+    ops.colsum(x, out)
+    want = x.double().sum(0) + 0.5
+    torch.testing.assert_close(out.double(), want, rtol=1e-4, atol=2e-3 * M ** 0.5)
+
+
 def test_colsum_loss_adamw():
     torch.manual_seed(1)
     x = torch.randn(1000, 1536, device="cuda")
